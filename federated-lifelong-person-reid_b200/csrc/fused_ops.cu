@@ -1,0 +1,637 @@
+// flpr fused memory-bound kernels for the local training step (all flat-arena, multi-tensor by construction:
+// every client keeps its trainable state in ONE contiguous fp32 arena, so "multi-tensor apply" is one launch).
+//
+//   adam / sgd        optimizer step fused with (a) the continual-learning quadratic penalty gradient
+//                     2*lam*(Q*p - R)  [EWC ewc.py:80-85, MAS mas.py:78-83, FedProx fedprox.py:52-57,
+//                     FedCurv fedcurv.py:79-86 all reduce to this form], (b) FedSTIL's L1 sparseness gradient
+//                     lam1*sign(theta - G) and adaptive-weight decay (fedstil.py:639-644), (c) the bf16 compute
+//                     copy of the updated weights, (d) the penalty / L1 *values* for loss reporting.
+//   importance_accum  Fisher (g^2) / MAS (|g|) accumulation (ewc.py:56-78, mas.py:55-76, fedcurv.py:56-77).
+//   ce_label_smooth   fused log-softmax + label-smoothing CE + gradient + top-1 hit count
+//                     (criterions/cross_entropy.py:35-40 and the per-step accuracy at baseline.py:47).
+//   bn_*              NHWC bf16 batch-norm training kernels (stats, apply+residual+ReLU, backward).
+//   rank_eval         CMC first-hit + average precision per query straight from the similarity matrix
+//                     (tools/evaluate.py:11-142) without sorting.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace flpr {
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) v = warp_sum(v);
+  return v;  // valid in warp 0
+}
+
+struct OptArgs {
+  float* p;             // fp32 master
+  const float* g;       // fp32 gradient
+  float* m;             // exp_avg / momentum buffer
+  float* v;             // exp_avg_sq (adam)
+  const float* Q;       // penalty curvature (nullable)
+  const float* R;       // penalty linear term (nullable)
+  const float* G;       // FedSTIL global weight (nullable)
+  __nv_bfloat16* p_bf16;  // compute copy (nullable)
+  float* stats;         // [0] += sum(Q p^2 - 2 R p), [1] += sum |p - G|   (nullable)
+  size_t n;
+  float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt;
+  float lam2;           // penalty strength (gradient gets 2*lam2*(Q p - R))
+  float lam1;           // L1 strength
+  float atten;          // FedSTIL attention scalar a: adaptive weight A = p - a*G (weight decay acts on A)
+  float momentum;
+  int penalty_ones;     // FedProx: Q == 1 without materialising it
+};
+
+template <bool ADAM>
+__global__ void __launch_bounds__(256) fused_opt_kernel(const OptArgs a) {
+  __shared__ float sh[8];
+  float pen = 0.f, l1 = 0.f;
+  const size_t n4 = a.n >> 2;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 p4 = reinterpret_cast<const float4*>(a.p)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(a.g)[i];
+    float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = m4, q4 = m4, r4 = m4, G4 = m4;
+    if (ADAM || a.momentum != 0.f) m4 = reinterpret_cast<const float4*>(a.m)[i];
+    if (ADAM) v4 = reinterpret_cast<const float4*>(a.v)[i];
+    if (a.Q) q4 = reinterpret_cast<const float4*>(a.Q)[i];
+    if (a.R) r4 = reinterpret_cast<const float4*>(a.R)[i];
+    if (a.G) G4 = reinterpret_cast<const float4*>(a.G)[i];
+    float* pp = reinterpret_cast<float*>(&p4);
+    const float* gg = reinterpret_cast<const float*>(&g4);
+    float* mm = reinterpret_cast<float*>(&m4);
+    float* vv = reinterpret_cast<float*>(&v4);
+    const float* qq = reinterpret_cast<const float*>(&q4);
+    const float* rr = reinterpret_cast<const float*>(&r4);
+    const float* GG = reinterpret_cast<const float*>(&G4);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float p = pp[t];
+      float g = gg[t];
+      float decay_base = p;
+      if (a.G) {
+        const float d = p - GG[t];
+        l1 += fabsf(d);
+        g += a.lam1 * ((d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f));
+        decay_base = p - a.atten * GG[t];
+      }
+      if (a.R) {
+        const float q = a.penalty_ones ? 1.f : qq[t];
+        pen += q * p * p - 2.f * rr[t] * p;
+        g += 2.f * a.lam2 * (q * p - rr[t]);
+      }
+      g += a.wd * decay_base;
+      float np;
+      if (ADAM) {
+        const float m = a.beta1 * mm[t] + (1.f - a.beta1) * g;
+        const float v = a.beta2 * vv[t] + (1.f - a.beta2) * g * g;
+        mm[t] = m;
+        vv[t] = v;
+        const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+        np = p - (a.lr / a.bc1) * (m / denom);
+      } else {
+        float d = g;
+        if (a.momentum != 0.f) {
+          d = a.momentum * mm[t] + g;
+          mm[t] = d;
+        }
+        np = p - a.lr * d;
+      }
+      pp[t] = np;
+    }
+    reinterpret_cast<float4*>(a.p)[i] = p4;
+    if (ADAM || a.momentum != 0.f) reinterpret_cast<float4*>(a.m)[i] = m4;
+    if (ADAM) reinterpret_cast<float4*>(a.v)[i] = v4;
+    if (a.p_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p4.x, p4.y), hi = __floats2bfloat162_rn(p4.z, p4.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(a.p_bf16)[i] = u;
+    }
+  }
+  if (a.stats) {
+    const float s0 = block_sum(pen, sh);
+    const float s1 = block_sum(l1, sh);
+    if (threadIdx.x == 0) {
+      if (a.R) atomicAdd(a.stats + 0, s0);
+      if (a.G) atomicAdd(a.stats + 1, s1);
+    }
+  }
+}
+
+// F += scale * g^2 (mode 0) or scale * |g| (mode 1)
+__global__ void __launch_bounds__(256) importance_accum_kernel(float* F, const float* g, size_t n, float scale,
+                                                               int mode) {
+  const size_t n4 = n >> 2, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 f = reinterpret_cast<float4*>(F)[i];
+    const float4 x = reinterpret_cast<const float4*>(g)[i];
+    if (mode == 0) {
+      f.x = fmaf(scale * x.x, x.x, f.x); f.y = fmaf(scale * x.y, x.y, f.y);
+      f.z = fmaf(scale * x.z, x.z, f.z); f.w = fmaf(scale * x.w, x.w, f.w);
+    } else {
+      f.x += scale * fabsf(x.x); f.y += scale * fabsf(x.y); f.z += scale * fabsf(x.z); f.w += scale * fabsf(x.w);
+    }
+    reinterpret_cast<float4*>(F)[i] = f;
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* x, __nv_bfloat16* y, size_t n) {
+  const size_t n4 = n >> 2, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(y)[i] = u;
+  }
+}
+
+// theta = a * G + A   (adaptive compose, fedstil.py:85,120) with bf16 compute copy; scalar attention
+__global__ void __launch_bounds__(256) compose_kernel(const float* G, const float* A, float a, float* theta,
+                                                      __nv_bfloat16* theta_bf16, size_t n) {
+  const size_t n4 = n >> 2, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 g = reinterpret_cast<const float4*>(G)[i];
+    const float4 w = reinterpret_cast<const float4*>(A)[i];
+    const float4 t = make_float4(fmaf(a, g.x, w.x), fmaf(a, g.y, w.y), fmaf(a, g.z, w.z), fmaf(a, g.w, w.w));
+    if (theta) reinterpret_cast<float4*>(theta)[i] = t;
+    if (theta_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y), hi = __floats2bfloat162_rn(t.z, t.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(theta_bf16)[i] = u;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- label-smoothing CE
+// One block per sample. logits: [B, C] (bf16 or fp32, row stride ld). dlogits same layout (bf16 or fp32).
+// stats[0] += loss_row / B ; stats[1] += (argmax == target)
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) ce_ls_kernel(const TIn* logits, const long long* target, TOut* dlogits,
+                                                    float* stats, int B, int C, long long ld, float eps,
+                                                    float grad_scale) {
+  __shared__ float sh[8];
+  __shared__ float s_bcast[2];
+  __shared__ int s_arg;
+  const int row = blockIdx.x;
+  const TIn* z = logits + (long long)row * ld;
+  // pass 1: max (+ argmax) and sum of logits
+  float mx = -INFINITY, sumz = 0.f;
+  int arg = 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float x = static_cast<float>(z[c]);
+    sumz += x;
+    if (x > mx) { mx = x; arg = c; }
+  }
+  // block argmax (first index wins on ties, like torch.max)
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  __shared__ float s_mx[8];
+  __shared__ int s_ai[8];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_mx[w] = mx; s_ai[w] = arg; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bm = s_mx[0];
+    int ba = s_ai[0];
+    for (int i = 1; i < (blockDim.x >> 5); ++i)
+      if (s_mx[i] > bm || (s_mx[i] == bm && s_ai[i] < ba)) { bm = s_mx[i]; ba = s_ai[i]; }
+    s_bcast[0] = bm;
+    s_arg = ba;
+  }
+  __syncthreads();
+  mx = s_bcast[0];
+  const float tot_z = block_sum(sumz, sh);
+  // pass 2: sum exp
+  float se = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) se += __expf(static_cast<float>(z[c]) - mx);
+  const float tot_e = block_sum(se, sh);
+  if (threadIdx.x == 0) s_bcast[1] = tot_e;
+  __syncthreads();
+  const float lse = mx + logf(s_bcast[1]);
+  const long long y = target[row];
+  if (threadIdx.x == 0) {
+    const float zy = static_cast<float>(z[y]);
+    // -(1-eps)*(z_y - lse) - eps/C * (sum z - C*lse)
+    const float loss = -(1.f - eps) * (zy - lse) - (eps / C) * (tot_z - C * lse);
+    atomicAdd(stats + 0, loss / B);
+    if (s_arg == (int)y) atomicAdd(stats + 1, 1.f);
+  }
+  if (dlogits != nullptr) {
+    TOut* d = dlogits + (long long)row * ld;
+    const float smooth = eps / C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float pr = __expf(static_cast<float>(z[c]) - lse);
+      const float t = smooth + ((c == (int)y) ? (1.f - eps) : 0.f);
+      d[c] = static_cast<TOut>((pr - t) * grad_scale);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- batch norm (NHWC, [M, C] bf16)
+// per-channel sum / sum of squares; blockDim.x threads each own 2 adjacent channels, rows split over blockIdx.y
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* x, float* sum, float* sqsum, int M, int C,
+                                                       int rows_per_block) {
+  const int c2 = blockIdx.x * blockDim.x + threadIdx.x;  // channel pair
+  if (c2 * 2 >= C) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, M);
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(x);
+  const size_t c2n = (size_t)C / 2;
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+    const float2 f = __bfloat1622float2(xp[(size_t)r * c2n + c2]);
+    s0 += f.x; s1 += f.y;
+    q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+  }
+  atomicAdd(sum + 2 * c2, s0);
+  atomicAdd(sum + 2 * c2 + 1, s1);
+  atomicAdd(sqsum + 2 * c2, q0);
+  atomicAdd(sqsum + 2 * c2 + 1, q1);
+}
+
+// finalize: mean/rstd, running stats (momentum, unbiased var), scale/shift for the apply pass
+__global__ void bn_finalize_kernel(const float* sum, const float* sqsum, const float* gamma, const float* beta,
+                                   float* mean, float* rstd, float* scale, float* shift, float* running_mean,
+                                   float* running_var, int M, int C, float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mu = sum[c] / M;
+  float var = sqsum[c] / M - mu * mu;
+  var = fmaxf(var, 0.f);
+  const float rs = rsqrtf(var + eps);
+  mean[c] = mu;
+  rstd[c] = rs;
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = g * rs;
+  shift[c] = b - mu * g * rs;
+  if (running_mean) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+    const float unb = (M > 1) ? var * ((float)M / (float)(M - 1)) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+  }
+}
+
+// y = relu?( x*scale[c] + shift[c] (+ residual) ), 8 channels per thread
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* x, const float* scale, const float* shift,
+                                                       const __nv_bfloat16* residual, __nv_bfloat16* y, size_t total8,
+                                                       int C, int relu) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += stride) {
+    const int c0 = (int)((i * 8) % C);
+    uint4 u = reinterpret_cast<const uint4*>(x)[i];
+    uint4 ru = make_uint4(0, 0, 0, 0);
+    if (residual) ru = reinterpret_cast<const uint4*>(residual)[i];
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+    const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&ru);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 f = __bfloat1622float2(h[t]);
+      f.x = fmaf(f.x, scale[c0 + 2 * t], shift[c0 + 2 * t]);
+      f.y = fmaf(f.y, scale[c0 + 2 * t + 1], shift[c0 + 2 * t + 1]);
+      if (residual) {
+        const float2 r = __bfloat1622float2(rh[t]);
+        f.x += r.x; f.y += r.y;
+      }
+      if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+      h[t] = __floats2bfloat162_rn(f.x, f.y);
+    }
+    reinterpret_cast<uint4*>(y)[i] = u;
+  }
+}
+
+// backward reduce: dy_eff = dy * (y > 0 if relu); dgamma_raw[c] += sum dy_eff * xhat ; dbeta[c] += sum dy_eff
+// also writes dy_eff (masked) in place of dres when requested so the residual branch gets its gradient.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* y,
+                                                            const __nv_bfloat16* x, const float* mean,
+                                                            const float* rstd, float* dgamma, float* dbeta,
+                                                            __nv_bfloat16* dres, int M, int C, int rows_per_block,
+                                                            int relu) {
+  const int c2 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c2 * 2 >= C) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, M);
+  const float mu0 = mean[2 * c2], mu1 = mean[2 * c2 + 1], rs0 = rstd[2 * c2], rs1 = rstd[2 * c2 + 1];
+  float g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
+  const size_t c2n = (size_t)C / 2;
+  const __nv_bfloat162* dyp = reinterpret_cast<const __nv_bfloat162*>(dy);
+  const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(y);
+  const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(x);
+  __nv_bfloat162* dr = reinterpret_cast<__nv_bfloat162*>(dres);
+#pragma unroll 2
+  for (int r = r0; r < r1; ++r) {
+    const size_t idx = (size_t)r * c2n + c2;
+    float2 d = __bfloat1622float2(dyp[idx]);
+    if (relu) {
+      const float2 o = __bfloat1622float2(yp[idx]);
+      if (o.x <= 0.f) d.x = 0.f;
+      if (o.y <= 0.f) d.y = 0.f;
+    }
+    if (dr) dr[idx] = __floats2bfloat162_rn(d.x, d.y);
+    const float2 xv = __bfloat1622float2(xp[idx]);
+    g0 = fmaf(d.x, (xv.x - mu0) * rs0, g0);
+    g1 = fmaf(d.y, (xv.y - mu1) * rs1, g1);
+    b0 += d.x; b1 += d.y;
+  }
+  atomicAdd(dgamma + 2 * c2, g0);
+  atomicAdd(dgamma + 2 * c2 + 1, g1);
+  atomicAdd(dbeta + 2 * c2, b0);
+  atomicAdd(dbeta + 2 * c2 + 1, b1);
+}
+
+// dx = gamma*rstd * (dy_eff - dbeta/M - xhat * dgamma/M)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* y,
+                                                           const __nv_bfloat16* x, const float* mean,
+                                                           const float* rstd, const float* gamma,
+                                                           const float* dgamma, const float* dbeta,
+                                                           __nv_bfloat16* dx, size_t total8, int M, int C, int relu) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const float invM = 1.f / M;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += stride) {
+    const int c0 = (int)((i * 8) % C);
+    uint4 du = reinterpret_cast<const uint4*>(dy)[i];
+    const uint4 xu = reinterpret_cast<const uint4*>(x)[i];
+    uint4 yu = make_uint4(0, 0, 0, 0);
+    if (relu) yu = reinterpret_cast<const uint4*>(y)[i];
+    __nv_bfloat162* dh = reinterpret_cast<__nv_bfloat162*>(&du);
+    const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xu);
+    const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&yu);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 d = __bfloat1622float2(dh[t]);
+      const float2 xv = __bfloat1622float2(xh[t]);
+      if (relu) {
+        const float2 o = __bfloat1622float2(yh[t]);
+        if (o.x <= 0.f) d.x = 0.f;
+        if (o.y <= 0.f) d.y = 0.f;
+      }
+      const int ca = c0 + 2 * t, cb = ca + 1;
+      const float ga = gamma ? gamma[ca] : 1.f, gb = gamma ? gamma[cb] : 1.f;
+      const float xa = (xv.x - mean[ca]) * rstd[ca], xb = (xv.y - mean[cb]) * rstd[cb];
+      d.x = ga * rstd[ca] * (d.x - dbeta[ca] * invM - xa * dgamma[ca] * invM);
+      d.y = gb * rstd[cb] * (d.y - dbeta[cb] * invM - xb * dgamma[cb] * invM);
+      dh[t] = __floats2bfloat162_rn(d.x, d.y);
+    }
+    reinterpret_cast<uint4*>(dx)[i] = du;
+  }
+}
+
+// global average pool over HW rows: x [N, HW, C] bf16 -> out [N, C] fp32 (+ optional bf16)
+__global__ void __launch_bounds__(256) gap_fwd_kernel(const __nv_bfloat16* x, float* out, __nv_bfloat16* out_bf16,
+                                                      int HW, int C) {
+  const int n = blockIdx.y;
+  const int c2 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c2 * 2 >= C) return;
+  const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(x) + (size_t)n * HW * (C / 2);
+  float s0 = 0.f, s1 = 0.f;
+  for (int r = 0; r < HW; ++r) {
+    const float2 f = __bfloat1622float2(xp[(size_t)r * (C / 2) + c2]);
+    s0 += f.x; s1 += f.y;
+  }
+  s0 /= HW; s1 /= HW;
+  if (out) { out[(size_t)n * C + 2 * c2] = s0; out[(size_t)n * C + 2 * c2 + 1] = s1; }
+  if (out_bf16) reinterpret_cast<__nv_bfloat162*>(out_bf16)[(size_t)n * (C / 2) + c2] = __floats2bfloat162_rn(s0, s1);
+}
+// dx[n, r, c] = dout[n, c] / HW
+__global__ void __launch_bounds__(256) gap_bwd_kernel(const float* dout, __nv_bfloat16* dx, int HW, int C) {
+  const int n = blockIdx.y;
+  const int c2 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c2 * 2 >= C) return;
+  const float a = dout[(size_t)n * C + 2 * c2] / HW, b = dout[(size_t)n * C + 2 * c2 + 1] / HW;
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  __nv_bfloat162* dp = reinterpret_cast<__nv_bfloat162*>(dx) + (size_t)n * HW * (C / 2);
+  for (int r = 0; r < HW; ++r) dp[(size_t)r * (C / 2) + c2] = v;
+}
+
+// ----------------------------------------------------------------------------- CMC / AP without sorting
+// One block per query. S: [Q, G] similarity (higher = closer). An item g' precedes g iff
+// S[g'] > S[g] or (S[g'] == S[g] and g' > g)   (== np.argsort(sim)[::-1] with a stable sort).
+// out_ap[q] = AP (trapezoid form, tools/evaluate.py:75-82), out_first[q] = rank of first hit (or -1: no match).
+__global__ void __launch_bounds__(256) rank_eval_kernel(const float* S, const long long* qlab, const long long* glab,
+                                                        float* out_ap, int* out_first, int G, long long lds) {
+  extern __shared__ int s_match[];  // indices of matching gallery items (capacity = blockDim-independent, G max)
+  __shared__ int s_nmatch;
+  __shared__ float shf[8];
+  __shared__ float s_ap;
+  __shared__ int s_first;
+  const int q = blockIdx.x;
+  const float* row = S + (long long)q * lds;
+  const long long ql = qlab[q];
+  if (threadIdx.x == 0) { s_nmatch = 0; s_ap = 0.f; s_first = 0x7fffffff; }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x)
+    if (glab[g] == ql) s_match[atomicAdd(&s_nmatch, 1)] = g;
+  __syncthreads();
+  const int R = s_nmatch;
+  if (R == 0) {
+    if (threadIdx.x == 0) { out_ap[q] = 0.f; out_first[q] = -1; }
+    return;
+  }
+  for (int mi = 0; mi < R; ++mi) {
+    const int gm = s_match[mi];
+    const float sm = row[gm];
+    float higher = 0.f, higher_match = 0.f;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      const float s = row[g];
+      const bool before = (s > sm) || (s == sm && g > gm);
+      if (before) {
+        higher += 1.f;
+        if (glab[g] == ql) higher_match += 1.f;
+      }
+    }
+    const float loc = block_sum(higher, shf);
+    __syncthreads();
+    const float im = block_sum(higher_match, shf);
+    if (threadIdx.x == 0) {
+      const float precision = (im + 1.f) / (loc + 1.f);
+      const float old_precision = (loc != 0.f) ? im / loc : 1.f;
+      s_ap += (old_precision + precision) * 0.5f / R;
+      s_first = min(s_first, (int)loc);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out_ap[q] = s_ap; out_first[q] = s_first; }
+}
+
+static inline int grid_for(size_t n_items, int threads, int cap = 148 * 8) {
+  size_t b = (n_items + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > (size_t)cap) b = cap;
+  return (int)b;
+}
+
+}  // namespace flpr
+
+using namespace flpr;
+
+extern "C" {
+
+int flpr_fused_opt(int adam, float* p, const float* g, float* m, float* v, const float* Q, const float* R,
+                   const float* G, void* p_bf16, float* stats, size_t n, float lr, float beta1, float beta2, float eps,
+                   float wd, int step, float lam2, float lam1, float atten, float momentum, int penalty_ones,
+                   cudaStream_t st) {
+  bind_device_of(p);
+  if (n % 4) return -2;
+  OptArgs a;
+  a.p = p; a.g = g; a.m = m; a.v = v; a.Q = Q; a.R = R; a.G = G;
+  a.p_bf16 = reinterpret_cast<__nv_bfloat16*>(p_bf16); a.stats = stats; a.n = n;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = wd;
+  a.bc1 = 1.f - powf(beta1, (float)step);
+  a.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  a.lam2 = lam2; a.lam1 = lam1; a.atten = atten; a.momentum = momentum; a.penalty_ones = penalty_ones;
+  const int grid = grid_for(n / 4, 256);
+  if (adam) fused_opt_kernel<true><<<grid, 256, 0, st>>>(a);
+  else fused_opt_kernel<false><<<grid, 256, 0, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+int flpr_importance_accum(float* F, const float* g, size_t n, float scale, int mode, cudaStream_t st) {
+  bind_device_of(F);
+  if (n % 4) return -2;
+  importance_accum_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(F, g, n, scale, mode);
+  return (int)cudaGetLastError();
+}
+
+int flpr_cast_bf16(const float* x, void* y, size_t n, cudaStream_t st) {
+  bind_device_of(x);
+  if (n % 4) return -2;
+  cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n);
+  return (int)cudaGetLastError();
+}
+
+int flpr_compose(const float* G, const float* A, float a, float* theta, void* theta_bf16, size_t n, cudaStream_t st) {
+  bind_device_of(G);
+  if (n % 4) return -2;
+  compose_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(G, A, a, theta, reinterpret_cast<__nv_bfloat16*>(theta_bf16), n);
+  return (int)cudaGetLastError();
+}
+
+// in_bf16 / out_bf16 select the logits / dlogits dtypes. stats: float[2] (loss mean accum, correct count accum).
+int flpr_ce_label_smooth(const void* logits, const long long* target, void* dlogits, float* stats, int B, int C,
+                         long long ld, float eps, float grad_scale, int in_bf16, int out_bf16, cudaStream_t st) {
+  if (in_bf16 && out_bf16)
+    ce_ls_kernel<__nv_bfloat16, __nv_bfloat16><<<B, 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(logits), target, reinterpret_cast<__nv_bfloat16*>(dlogits), stats, B, C,
+        ld, eps, grad_scale);
+  else if (in_bf16)
+    ce_ls_kernel<__nv_bfloat16, float><<<B, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(logits), target,
+                                                           reinterpret_cast<float*>(dlogits), stats, B, C, ld, eps,
+                                                           grad_scale);
+  else if (out_bf16)
+    ce_ls_kernel<float, __nv_bfloat16><<<B, 256, 0, st>>>(reinterpret_cast<const float*>(logits), target,
+                                                           reinterpret_cast<__nv_bfloat16*>(dlogits), stats, B, C, ld,
+                                                           eps, grad_scale);
+  else
+    ce_ls_kernel<float, float><<<B, 256, 0, st>>>(reinterpret_cast<const float*>(logits), target,
+                                                   reinterpret_cast<float*>(dlogits), stats, B, C, ld, eps, grad_scale);
+  return (int)cudaGetLastError();
+}
+
+// sum/sqsum must be zeroed by the caller (they live in one scratch buffer that is memset once per step).
+int flpr_bn_fwd(const void* x, const float* gamma, const float* beta, const void* residual, void* y, float* sum,
+                float* sqsum, float* mean, float* rstd, float* scale, float* shift, float* running_mean,
+                float* running_var, int M, int C, float eps, float momentum, int relu, cudaStream_t st) {
+  bind_device_of(x);
+  if (C % 8) return -2;
+  const int threads = 128;
+  const int gx = (C / 2 + threads - 1) / threads;
+  int gy = (148 * 4) / gx;
+  if (gy < 1) gy = 1;
+  int rpb = (M + gy - 1) / gy;
+  if (rpb < 16) rpb = 16;
+  gy = (M + rpb - 1) / rpb;
+  bn_stats_kernel<<<dim3(gx, gy), threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), sum, sqsum, M, C, rpb);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sum, sqsum, gamma, beta, mean, rstd, scale, shift, running_mean,
+                                                      running_var, M, C, eps, momentum);
+  const size_t total8 = (size_t)M * C / 8;
+  bn_apply_kernel<<<grid_for(total8, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), scale, shift,
+                                                         reinterpret_cast<const __nv_bfloat16*>(residual),
+                                                         reinterpret_cast<__nv_bfloat16*>(y), total8, C, relu);
+  return (int)cudaGetLastError();
+}
+
+// eval-mode / folded affine: y = relu?(x*scale + shift (+res))
+int flpr_affine_act(const void* x, const float* scale, const float* shift, const void* residual, void* y, int M, int C,
+                    int relu, cudaStream_t st) {
+  bind_device_of(x);
+  if (C % 8) return -2;
+  const size_t total8 = (size_t)M * C / 8;
+  bn_apply_kernel<<<grid_for(total8, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), scale, shift,
+                                                         reinterpret_cast<const __nv_bfloat16*>(residual),
+                                                         reinterpret_cast<__nv_bfloat16*>(y), total8, C, relu);
+  return (int)cudaGetLastError();
+}
+
+// dgamma/dbeta must be zeroed by the caller. dres (nullable) receives the ReLU-masked dy for the residual branch.
+int flpr_bn_bwd(const void* dy, const void* y, const void* x, const float* mean, const float* rstd, const float* gamma,
+                float* dgamma, float* dbeta, void* dres, void* dx, int M, int C, int relu, cudaStream_t st) {
+  bind_device_of(dy);
+  if (C % 8) return -2;
+  const int threads = 128;
+  const int gx = (C / 2 + threads - 1) / threads;
+  int gy = (148 * 4) / gx;
+  if (gy < 1) gy = 1;
+  int rpb = (M + gy - 1) / gy;
+  if (rpb < 16) rpb = 16;
+  gy = (M + rpb - 1) / rpb;
+  bn_bwd_reduce_kernel<<<dim3(gx, gy), threads, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y),
+      reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dres), M,
+      C, rpb, relu);
+  const size_t total8 = (size_t)M * C / 8;
+  bn_bwd_apply_kernel<<<grid_for(total8, 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y),
+      reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, gamma, dgamma, dbeta,
+      reinterpret_cast<__nv_bfloat16*>(dx), total8, M, C, relu);
+  return (int)cudaGetLastError();
+}
+
+int flpr_gap_fwd(const void* x, float* out, void* out_bf16, int N, int HW, int C, cudaStream_t st) {
+  bind_device_of(x);
+  const int threads = 128;
+  gap_fwd_kernel<<<dim3((C / 2 + threads - 1) / threads, N), threads, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), out, reinterpret_cast<__nv_bfloat16*>(out_bf16), HW, C);
+  return (int)cudaGetLastError();
+}
+int flpr_gap_bwd(const float* dout, void* dx, int N, int HW, int C, cudaStream_t st) {
+  bind_device_of(dout);
+  const int threads = 128;
+  gap_bwd_kernel<<<dim3((C / 2 + threads - 1) / threads, N), threads, 0, st>>>(
+      dout, reinterpret_cast<__nv_bfloat16*>(dx), HW, C);
+  return (int)cudaGetLastError();
+}
+
+int flpr_rank_eval(const float* S, const long long* qlab, const long long* glab, float* out_ap, int* out_first, int Q,
+                   int G, long long lds, cudaStream_t st) {
+  bind_device_of(S);
+  const size_t smem = (size_t)G * sizeof(int);
+  if (smem > 200 * 1024) return -3;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(rank_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  rank_eval_kernel<<<Q, 256, smem, st>>>(S, qlab, glab, out_ap, out_first, G, lds);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

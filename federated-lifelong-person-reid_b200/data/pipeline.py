@@ -1,0 +1,182 @@
+"""Per-client lifelong task pipeline (``datasets/datasets_pipeline.py:10-93``).
+
+Semantics kept: ordered task list, ``sustain_rounds`` rounds per task, ``next_task()`` advances and then stays on the
+last task forever, ``get_task(idx)`` returns ``{task_name, tr_epochs, tr_loader, query_loader, gallery_loaders}``.
+Difference: splits are loaded **once** and cached (the reference rebuilds 3 datasets + 3 DataLoaders on every call),
+and by default the loaders are :class:`DeviceBatchLoader` (pinned uint8 -> async H2D -> GPU augmentation).
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Dict, Iterator, List, Optional, Tuple
+
+import torch
+from torch.utils.data import DataLoader
+
+from .augmentation import DeviceAugment, augmentations
+from .datasets import ArrayReIDDataset, ReIDImageDataset
+
+
+class DeviceBatchLoader:
+    """Iterates ``(data, person_id, class_index)`` batches; data lands on ``device`` already augmented.
+
+    Host side: index gather into a pinned staging buffer. Device side: async copy on a dedicated stream,
+    double-buffered so the copy of batch i+1 overlaps the compute of batch i.
+    """
+
+    def __init__(self, dataset: ArrayReIDDataset, batch_size: int, shuffle: bool, level: str, mean, std,
+                 device: torch.device | str = "cpu", dtype: torch.dtype = torch.float32, drop_last: bool = False,
+                 seed: Optional[int] = None):
+        self.dataset = dataset
+        self.batch_size = int(batch_size)
+        self.shuffle = shuffle
+        self.drop_last = drop_last
+        self.device = torch.device(device)
+        self.augment = DeviceAugment(level, mean, std, dtype)
+        self.num_workers = 0
+        self.pin_memory = True
+        self.persistent_workers = False
+        self.multiprocessing_context = None
+        self._gen = torch.Generator()
+        if seed is not None:
+            self._gen.manual_seed(seed)
+        self._stage: List[torch.Tensor] = []
+        self._copy_stream = None
+        self.h2d_bytes = 0
+
+    def to(self, device, dtype: Optional[torch.dtype] = None) -> "DeviceBatchLoader":
+        self.device = torch.device(device)
+        if dtype is not None:
+            self.augment.dtype = dtype
+        return self
+
+    def __len__(self) -> int:
+        n = len(self.dataset)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def _order(self) -> torch.Tensor:
+        n = len(self.dataset)
+        return torch.randperm(n, generator=self._gen) if self.shuffle else torch.arange(n)
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+        ds = self.dataset
+        order = self._order()
+        nb = len(self)
+        cuda = self.device.type == "cuda"
+        if cuda:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(self.device)
+            if not self._stage:
+                shape = (self.batch_size,) + tuple(ds.images.shape[1:])
+                self._stage = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(2)]
+                self._stage_ev = [None, None]
+
+        def stage(bi: int):
+            idx = order[bi * self.batch_size:(bi + 1) * self.batch_size]
+            if not cuda:
+                return ds.images[idx], ds.pids[idx], ds.cidx[idx], None
+            buf = self._stage[bi % 2]
+            if self._stage_ev[bi % 2] is not None:
+                self._stage_ev[bi % 2].synchronize()          # previous copy out of this buffer finished
+            torch.index_select(ds.images, 0, idx, out=buf[:len(idx)])
+            with torch.cuda.stream(self._copy_stream):
+                dev_u8 = buf[:len(idx)].to(self.device, non_blocking=True)
+                pid = ds.pids[idx].to(self.device, non_blocking=True)
+                cid = ds.cidx[idx].to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            self._stage_ev[bi % 2] = ev
+            self.h2d_bytes += dev_u8.numel() + 16 * len(idx)
+            return dev_u8, pid, cid, ev
+
+        nxt = stage(0) if nb else None
+        for bi in range(nb):
+            cur = nxt
+            nxt = stage(bi + 1) if bi + 1 < nb else None
+            u8, pid, cid, ev = cur
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+                u8.record_stream(torch.cuda.current_stream(self.device))
+            yield self.augment(u8), pid, cid
+
+
+class ReIDTaskPipeline:
+    def __init__(self, task_list: List[str], task_opts: Dict, datasets_dir: str, device_loader: bool = True,
+                 source_factory: Optional[Callable[[str, str], ArrayReIDDataset]] = None):
+        self.task_list = task_list
+        self.task_opts = task_opts
+        self.datasets_dir = datasets_dir
+        self.current_task_idx = -1
+        self.task_round_rest = [task_opts["sustain_rounds"] for _ in task_list]
+        self.device_loader = device_loader
+        self.source_factory = source_factory      # (task_name, split) -> ArrayReIDDataset (synthetic / in-memory)
+        self._cache: Dict[int, Dict] = {}
+
+    # ---- reference schedule (datasets_pipeline.py:19-20,81-93) -------------------------------------------------
+    def reach_final_task(self) -> bool:
+        return self.current_task_idx + 1 == len(self.task_list)
+
+    def current_task(self) -> Dict:
+        if self.current_task_idx == -1:
+            self.current_task_idx = 0
+        return self.get_task(self.current_task_idx)
+
+    def next_task(self) -> Dict:
+        if not self.reach_final_task():
+            if self.current_task_idx != -1 and self.task_round_rest[self.current_task_idx]:
+                self.task_round_rest[self.current_task_idx] -= 1
+            else:
+                self.current_task_idx += 1
+                self.task_round_rest[self.current_task_idx] -= 1
+        return self.current_task()
+
+    def state_dict(self) -> Dict:
+        return {"current_task_idx": self.current_task_idx, "task_round_rest": list(self.task_round_rest)}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        self.current_task_idx = int(sd["current_task_idx"])
+        self.task_round_rest = list(sd["task_round_rest"])
+
+    # ---- loaders ----------------------------------------------------------------------------------------------
+    def _split(self, task: str, split: str):
+        aug = self.task_opts["augment_opts"]
+        if self.source_factory is not None:
+            return self.source_factory(task, split)
+        path = os.path.join(self.datasets_dir, task, split)
+        if self.device_loader:
+            return ArrayReIDDataset.from_folder(path, aug["img_size"])
+        level = aug["level"] if split == "train" else "none"
+        return ReIDImageDataset(path, augmentations[level](size=aug["img_size"], mean=aug["norm_mean"],
+                                                           std=aug["norm_std"]))
+
+    def _loader(self, ds, train: bool):
+        aug, lo = self.task_opts["augment_opts"], self.task_opts["loader_opts"]
+        bs = lo["batch_size"]
+        drop_last = len(ds) % bs == 1                                    # datasets_pipeline.py:39
+        if isinstance(ds, ArrayReIDDataset):
+            return DeviceBatchLoader(ds, bs, shuffle=train, level=aug["level"] if train else "none",
+                                     mean=aug["norm_mean"], std=aug["norm_std"], drop_last=drop_last)
+        workers = lo.get("num_workers", 0)
+        return DataLoader(ds, shuffle=train, drop_last=drop_last, batch_size=bs, num_workers=workers,
+                          pin_memory=lo.get("pin_memory", False),
+                          persistent_workers=lo.get("persistent_workers", False) and workers > 0,
+                          multiprocessing_context=lo.get("multiprocessing_context") if workers > 0 else None)
+
+    def get_task(self, idx: int = -1) -> Dict:
+        idx = idx % len(self.task_list)
+        if idx not in self._cache:
+            task = self.task_list[idx]
+            self._cache[idx] = {
+                "task_name": task,
+                "tr_epochs": self.task_opts["train_epochs"],
+                "tr_loader": self._loader(self._split(task, "train"), True),
+                "query_loader": self._loader(self._split(task, "query"), False),
+                "gallery_loaders": self._loader(self._split(task, "gallery"), False),
+            }
+        return self._cache[idx]
+
+    def evict(self, keep: Optional[int] = None) -> None:
+        """Drop cached splits (except ``keep``) – host-RAM control for long task lists."""
+        for k in list(self._cache):
+            if k != keep:
+                del self._cache[k]

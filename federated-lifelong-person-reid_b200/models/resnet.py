@@ -1,0 +1,297 @@
+"""ReID ResNets (18/34/50/101/152) with ``last_stride``, GAP and optional BNNeck.
+
+Capability parity with ``models/resnet.py:45-344`` of the reference: the ``state_dict`` keys follow the torchvision
+naming (``base.conv1``, ``base.layer{1..4}.{i}.conv{j}|bn{j}|downsample.{0,1}``, ``bottleneck``, ``classifier``) so
+reference checkpoints load; train mode returns ``(cls_score, global_feat)``, eval mode returns ``global_feat``.
+
+B200-first differences:
+* the network is explicitly split into a *frozen trunk* and a *trainable head* at the first fine-tuned stage
+  (the reference discovers the same cut with two ``torch.fx`` traces, ``methods/fedstil.py:258-288``);
+* activations are NHWC bf16 on CUDA; the head runs on the tcgen05 GEMM / implicit-GEMM kernels
+  (:mod:`flpr_b200.ops.gemm`) with fused batch-norm kernels, the trunk runs inference-only with folded BN;
+* no network access: ImageNet weights are loaded from ``pretrained_path`` when given, else random init.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..ops import fused as fops
+from ..ops import gemm as gops
+
+_SPECS: Dict[str, Tuple[str, List[int]]] = {
+    "resnet18": ("basic", [2, 2, 2, 2]),
+    "resnet34": ("basic", [3, 4, 6, 3]),
+    "resnet50": ("bottleneck", [3, 4, 6, 3]),
+    "resnet101": ("bottleneck", [3, 4, 23, 3]),
+    "resnet152": ("bottleneck", [3, 8, 36, 3]),
+}
+
+
+def _conv(cin: int, cout: int, k: int, stride: int = 1) -> nn.Conv2d:
+    return nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=k // 2, bias=False)
+
+
+class ResidualUnit(nn.Module):
+    """Basic (two 3x3) or bottleneck (1x1-3x3-1x1) residual unit; attribute names match torchvision."""
+
+    def __init__(self, kind: str, cin: int, width: int, stride: int):
+        super().__init__()
+        self.kind = kind
+        self.stride = stride
+        if kind == "basic":
+            self.expansion = 1
+            self.conv1, self.bn1 = _conv(cin, width, 3, stride), nn.BatchNorm2d(width)
+            self.conv2, self.bn2 = _conv(width, width, 3), nn.BatchNorm2d(width)
+        else:
+            self.expansion = 4
+            self.conv1, self.bn1 = _conv(cin, width, 1), nn.BatchNorm2d(width)
+            self.conv2, self.bn2 = _conv(width, width, 3, stride), nn.BatchNorm2d(width)
+            self.conv3, self.bn3 = _conv(width, width * 4, 1), nn.BatchNorm2d(width * 4)
+        cout = width * self.expansion
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(_conv(cin, cout, 1, stride), nn.BatchNorm2d(cout))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        identity = x if self.downsample is None else self.downsample(x)
+        out = self.relu(self.bn1(self.conv1(x)))
+        if self.kind == "basic":
+            out = self.bn2(self.conv2(out))
+        else:
+            out = self.relu(self.bn2(self.conv2(out)))
+            out = self.bn3(self.conv3(out))
+        return self.relu(out + identity)
+
+
+class ResNetTrunk(nn.Module):
+    def __init__(self, kind: str, depths: Sequence[int], last_stride: int = 2):
+        super().__init__()
+        self.kind = kind
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        cin = 64
+        exp = 1 if kind == "basic" else 4
+        for i, (width, depth, stride) in enumerate(zip((64, 128, 256, 512), depths, (1, 2, 2, last_stride)), 1):
+            units = []
+            for j in range(depth):
+                units.append(ResidualUnit(kind, cin, width, stride if j == 0 else 1))
+                cin = width * exp
+            setattr(self, f"layer{i}", nn.Sequential(*units))
+        self.out_channels = cin
+        self.gap = nn.AdaptiveAvgPool2d(1)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    STAGES = ("stem", "layer1", "layer2", "layer3", "layer4")
+
+    def run_stages(self, x: torch.Tensor, start: int = 0, stop: int = 5) -> torch.Tensor:
+        for i in range(start, stop):
+            if i == 0:
+                x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+            else:
+                x = getattr(self, f"layer{i}")(x)
+        return x
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.run_stages(x)
+        return self.gap(x).flatten(1)
+
+
+def _init_kaiming(m: nn.Module) -> None:       # strong-baseline style init used by the reference's BNNeck head
+    if isinstance(m, nn.Linear):
+        nn.init.kaiming_normal_(m.weight, a=0, mode="fan_out")
+        if m.bias is not None:
+            nn.init.zeros_(m.bias)
+    elif isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)) and m.affine:
+        nn.init.ones_(m.weight)
+        nn.init.zeros_(m.bias)
+
+
+class ResNetReID(nn.Module):
+    def __init__(self, model_name: str, num_classes: int = 1000, last_stride: int = 2, neck: str = "no",
+                 pretrained_path: Optional[str] = None, **kwargs):
+        super().__init__()
+        for k, v in kwargs.items():                      # unknown config keys become attributes (resnet.py:259-260)
+            setattr(self, k, v)
+        if model_name not in _SPECS:
+            raise ValueError(f"No model named {model_name} for generating.")
+        kind, depths = _SPECS[model_name]
+        self.model_name, self.num_classes, self.neck = model_name, num_classes, neck
+        self.base = ResNetTrunk(kind, depths, last_stride)
+        self.in_planes = self.base.out_channels
+        self.gap = nn.AdaptiveAvgPool2d(1)
+        if neck == "no":
+            self.classifier = nn.Linear(self.in_planes, num_classes)
+        elif neck == "bnneck":
+            self.bottleneck = nn.BatchNorm1d(self.in_planes)
+            self.bottleneck.bias.requires_grad_(False)
+            self.classifier = nn.Linear(self.in_planes, num_classes, bias=False)
+            _init_kaiming(self.bottleneck)
+            nn.init.normal_(self.classifier.weight, std=0.001)
+        else:
+            raise ValueError(f"Mismatched neck type for {neck}.")
+        if pretrained_path and os.path.exists(pretrained_path):
+            sd = torch.load(pretrained_path, map_location="cpu")
+            sd = {k: v for k, v in sd.items() if not k.startswith("fc.")}
+            self.base.load_state_dict(sd, strict=False)
+        self.head_start = 5          # index into ResNetTrunk.STAGES where the trainable head begins (5 = neck only)
+
+    # ---------------------------------------------------------------- trunk / head split
+    def configure_split(self, fine_tuning: Optional[Sequence[str]]) -> int:
+        """The head starts at the first trunk stage that contains a fine-tuned sub-module."""
+        start = 5
+        if not fine_tuning:
+            start = 0
+        else:
+            for name in fine_tuning:
+                if name == "base" or name.startswith("base.conv1") or name.startswith("base.bn1"):
+                    start = 0
+                for i in range(1, 5):
+                    if name == f"base.layer{i}" or name.startswith(f"base.layer{i}."):
+                        start = min(start, i)
+        self.head_start = start
+        return start
+
+    def forward_trunk(self, x: torch.Tensor) -> torch.Tensor:
+        """Frozen part: input image batch -> feature map at the cut ("prototype" in FedSTIL terms)."""
+        return self.base.run_stages(x, 0, self.head_start)
+
+    def forward_head(self, fmap: torch.Tensor):
+        """Trainable part: feature map at the cut -> ``(cls_score, global_feat)`` / ``global_feat``."""
+        if fmap.is_cuda and getattr(self, "_fast_head", None) is not None:
+            return self._fast_head(fmap)
+        x = self.base.run_stages(fmap, self.head_start, 5)
+        global_feat = x.mean(dim=(2, 3)) if x.dim() == 4 else x
+        return self._neck(global_feat)
+
+    def _neck(self, global_feat: torch.Tensor):
+        feat = self.bottleneck(global_feat) if self.neck == "bnneck" else global_feat
+        if self.training:
+            return self.classifier(feat), global_feat
+        return global_feat
+
+    def forward(self, x: torch.Tensor):
+        return self.forward_head(self.forward_trunk(x))
+
+    def prototype_shape(self, img_size: Sequence[int]) -> Tuple[int, int, int]:
+        """(C, H, W) of the feature map at the cut for an ``img_size`` input."""
+        h, w = int(img_size[0]), int(img_size[1])
+        if self.head_start == 0:
+            return 3, h, w
+        h, w = (h + 1) // 2, (w + 1) // 2
+        h, w = (h + 1) // 2, (w + 1) // 2
+        c = 64
+        exp = 1 if self.base.kind == "basic" else 4
+        for i in range(1, self.head_start):
+            c = (64, 128, 256, 512)[i - 1] * exp
+            if i >= 2:
+                h, w = (h + 1) // 2, (w + 1) // 2
+        return c, h, w
+
+
+# ------------------------------------------------------------------------------------------------- fast head
+class FastResNetHead:
+    """tcgen05 execution of ``layer{k..4}`` + GAP + BNNeck + classifier over NHWC bf16 activations.
+
+    Shares the ``nn.Parameter`` objects of the wrapped model (weights must be in ``channels_last`` memory format so
+    that the OHWI view is contiguous) and an optional bf16 shadow provider ``shadow(param) -> bf16 tensor`` kept in
+    sync by the fused optimizer. Falls back to cuDNN for the shapes the implicit-GEMM kernel does not cover
+    (stride-2 convolutions), never silently to a different numerics path for the covered ones.
+    """
+
+    def __init__(self, model: ResNetReID, shadow=None):
+        self.m = model
+        self.shadow = shadow or (lambda p: None)
+
+    # conv weight as [Cout, KH, KW, Cin] without copying (channels_last storage)
+    @staticmethod
+    def _ohwi(w: torch.Tensor) -> torch.Tensor:
+        v = w.permute(0, 2, 3, 1)
+        return v if v.is_contiguous() else v.contiguous()
+
+    def _conv(self, x: torch.Tensor, conv: nn.Conv2d) -> torch.Tensor:
+        """x: [N,H,W,C] bf16 -> [N,H',W',Cout] bf16"""
+        w = conv.weight
+        sh = self.shadow(w)
+        k, s = conv.kernel_size[0], conv.stride[0]
+        n, h, wd, c = x.shape
+        if k == 1 and s == 1:
+            w2 = self._ohwi(w).reshape(w.shape[0], c)
+            s2 = self._ohwi(sh).reshape(w.shape[0], c) if sh is not None else None
+            return gops.linear(x.reshape(-1, c), w2, s2).view(n, h, wd, -1)
+        if k == 3 and s == 1 and c % 64 == 0 and 128 % wd == 0 and ((h * wd <= 128 and 128 % (h * wd) == 0)
+                                                                   or (h * wd > 128 and h % (128 // wd) == 0)):
+            return gops.conv3x3(x, self._ohwi(w), self._ohwi(sh) if sh is not None else None)
+        # library fallback (strided convs)
+        y = F.conv2d(x.permute(0, 3, 1, 2), (sh if sh is not None else w.to(torch.bfloat16)) if not w.requires_grad
+                     else w.to(torch.bfloat16), stride=s, padding=k // 2)
+        return y.permute(0, 2, 3, 1).contiguous()
+
+    def _bn(self, x: torch.Tensor, bn: nn.BatchNorm2d, relu: bool, residual: Optional[torch.Tensor] = None):
+        n, h, w, c = x.shape
+        res2 = residual.reshape(-1, c) if residual is not None else None
+        y = fops.batch_norm_nhwc(x.reshape(-1, c), bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                 training=bn.training, eps=bn.eps, momentum=bn.momentum or 0.1, relu=relu,
+                                 residual=res2)
+        if bn.training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        return y.view(n, h, w, c)
+
+    def _unit(self, x: torch.Tensor, u: ResidualUnit) -> torch.Tensor:
+        identity = x
+        if u.downsample is not None:
+            identity = self._bn(self._conv(x, u.downsample[0]), u.downsample[1], relu=False)
+        out = self._bn(self._conv(x, u.conv1), u.bn1, relu=True)
+        if u.kind == "basic":
+            return self._bn(self._conv(out, u.conv2), u.bn2, relu=True, residual=identity)
+        out = self._bn(self._conv(out, u.conv2), u.bn2, relu=True)
+        return self._bn(self._conv(out, u.conv3), u.bn3, relu=True, residual=identity)
+
+    def __call__(self, fmap: torch.Tensor):
+        m = self.m
+        # accept NCHW-logical (channels_last) or NHWC-physical input
+        x = fmap.permute(0, 2, 3, 1) if fmap.shape[1] != fmap.shape[-1] or fmap.dim() == 4 and \
+            fmap.stride(1) == 1 else fmap
+        x = x.contiguous().to(torch.bfloat16)
+        for i in range(max(m.head_start, 1), 5):
+            for u in getattr(m.base, f"layer{i}"):
+                x = self._unit(x, u)
+        n, h, w, c = x.shape
+        global_feat = fops.global_avg_pool_nhwc(x.view(n, h * w, c))                 # fp32 [N, C]
+        if m.neck == "bnneck":
+            bn = m.bottleneck
+            feat = fops.batch_norm_nhwc(global_feat.to(torch.bfloat16), bn.weight, bn.bias, bn.running_mean,
+                                        bn.running_var, training=bn.training, eps=bn.eps, momentum=bn.momentum or 0.1)
+            if bn.training and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        else:
+            feat = global_feat.to(torch.bfloat16)
+        if not m.training:
+            return global_feat
+        w = m.classifier.weight
+        score = gops.linear(feat, w, self.shadow(w))
+        if m.classifier.bias is not None:
+            score = score + m.classifier.bias.to(score.dtype)
+        return score, global_feat
+
+
+def _make(name: str):
+    def ctor(**kwargs):
+        return ResNetReID(model_name=name, **kwargs)
+    ctor.__name__ = name
+    return ctor
+
+
+resnet18, resnet34, resnet50, resnet101, resnet152 = (_make(n) for n in _SPECS)

@@ -1,0 +1,274 @@
+"""Fused memory-bound ops of the local step (``csrc/fused_ops.cu``): flat-arena optimizers with the
+continual-learning penalty folded in, importance accumulation, label-smoothing CE, NHWC batch-norm, pooling."""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import native
+
+
+# --------------------------------------------------------------------------------------------- optimizers
+def fused_optimizer_step(kind: str, p: torch.Tensor, g: torch.Tensor, m: Optional[torch.Tensor],
+                         v: Optional[torch.Tensor], *, lr: float, step: int, beta1: float = 0.9, beta2: float = 0.999,
+                         eps: float = 1e-8, weight_decay: float = 0.0, momentum: float = 0.0,
+                         Q: Optional[torch.Tensor] = None, R: Optional[torch.Tensor] = None, lam2: float = 0.0,
+                         penalty_ones: bool = False, G: Optional[torch.Tensor] = None, lam1: float = 0.0,
+                         atten: float = 0.0, p_bf16: Optional[torch.Tensor] = None,
+                         stats: Optional[torch.Tensor] = None) -> None:
+    """One in-place optimizer step over a flat fp32 arena.
+
+    gradient used:  g + wd * (p - atten*G) + 2*lam2*(Q*p - R) + lam1*sign(p - G)
+    (``Q``/``R`` encode EWC / MAS / FedProx / FedCurv penalties, ``G`` is FedSTIL's global weight;
+    ``stats[0] += sum(Q p^2 - 2 R p)``, ``stats[1] += sum|p - G|`` are the penalty values for loss reporting).
+    """
+    adam = kind == "adam"
+    if not p.is_cuda:
+        with torch.no_grad():
+            grad = g.clone()
+            base = p
+            if G is not None:
+                d = p - G
+                if stats is not None:
+                    stats[1] += d.abs().sum()
+                grad += lam1 * torch.sign(d)
+                base = p - atten * G
+            if R is not None:
+                q = torch.ones_like(p) if penalty_ones or Q is None else Q
+                if stats is not None:
+                    stats[0] += (q * p * p - 2 * R * p).sum()
+                grad += 2 * lam2 * (q * p - R)
+            grad += weight_decay * base
+            if adam:
+                m.mul_(beta1).add_(grad, alpha=1 - beta1)
+                v.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+                bc1 = 1 - beta1 ** step
+                bc2 = 1 - beta2 ** step
+                denom = v.sqrt() / math.sqrt(bc2) + eps
+                p.addcdiv_(m, denom, value=-lr / bc1)
+            else:
+                if momentum != 0.0:
+                    m.mul_(momentum).add_(grad)
+                    grad = m
+                p.add_(grad, alpha=-lr)
+            if p_bf16 is not None:
+                p_bf16.copy_(p)
+        return
+    lib = native.load()
+    rc = lib.flpr_fused_opt(int(adam), native.ptr(p), native.ptr(g), native.ptr(m), native.ptr(v), native.ptr(Q),
+                            native.ptr(R), native.ptr(G), native.ptr(p_bf16), native.ptr(stats), p.numel(), lr, beta1,
+                            beta2, eps, weight_decay, int(step), lam2, lam1, atten, momentum, int(penalty_ones),
+                            native.stream(p.device))
+    native.check(rc, "flpr_fused_opt")
+    native.count_launch()
+
+
+def importance_accumulate(Fbuf: torch.Tensor, g: torch.Tensor, scale: float, mode: str = "fisher") -> None:
+    """``F += scale * g**2`` (fisher) or ``F += scale * |g|`` (mas)."""
+    if not Fbuf.is_cuda:
+        with torch.no_grad():
+            Fbuf.add_((g * g) if mode == "fisher" else g.abs(), alpha=scale)
+        return
+    lib = native.load()
+    rc = lib.flpr_importance_accum(native.ptr(Fbuf), native.ptr(g), Fbuf.numel(), scale, 0 if mode == "fisher" else 1,
+                                   native.stream(Fbuf.device))
+    native.check(rc, "flpr_importance_accum")
+    native.count_launch()
+
+
+def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty_like(x, dtype=torch.bfloat16)
+    if not x.is_cuda or x.numel() % 4 or not x.is_contiguous():
+        out.copy_(x)
+        return out
+    lib = native.load()
+    native.check(lib.flpr_cast_bf16(native.ptr(x), native.ptr(out), x.numel(), native.stream(x.device)), "flpr_cast_bf16")
+    native.count_launch()
+    return out
+
+
+def compose_adaptive(G: torch.Tensor, A: torch.Tensor, atten: float, theta: Optional[torch.Tensor] = None,
+                     theta_bf16: Optional[torch.Tensor] = None) -> None:
+    """theta = atten * G + A (FedSTIL adaptive compose, ``methods/fedstil.py:85``) with optional bf16 copy."""
+    if not G.is_cuda:
+        t = atten * G + A
+        if theta is not None:
+            theta.copy_(t)
+        if theta_bf16 is not None:
+            theta_bf16.copy_(t)
+        return
+    lib = native.load()
+    native.check(lib.flpr_compose(native.ptr(G), native.ptr(A), atten, native.ptr(theta), native.ptr(theta_bf16),
+                                  G.numel(), native.stream(G.device)), "flpr_compose")
+    native.count_launch()
+
+
+# --------------------------------------------------------------------------------------------- losses
+def ce_label_smooth_reference(logits: torch.Tensor, target: torch.Tensor, eps: float) -> torch.Tensor:
+    """fp32 reference of ``criterions/cross_entropy.py:35-40``."""
+    logp = F.log_softmax(logits.float(), dim=1)
+    c = logits.shape[1]
+    t = torch.zeros_like(logp).scatter_(1, target.view(-1, 1), 1.0)
+    t = (1 - eps) * t + eps / c
+    return (-t * logp).mean(0).sum()
+
+
+class _CELabelSmoothFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, eps, stats):
+        b, c = logits.shape
+        dlogits = torch.empty_like(logits)
+        local = torch.zeros(2, dtype=torch.float32, device=logits.device)
+        lib = native.load()
+        rc = lib.flpr_ce_label_smooth(native.ptr(logits), native.ptr(target), native.ptr(dlogits), native.ptr(local), b,
+                                      c, logits.stride(0), eps, 1.0 / b, int(logits.dtype == torch.bfloat16),
+                                      int(dlogits.dtype == torch.bfloat16), native.stream(logits.device))
+        native.check(rc, "flpr_ce_label_smooth")
+        native.count_launch()
+        if stats is not None:
+            stats += local
+        ctx.save_for_backward(dlogits)
+        return local[0]
+
+    @staticmethod
+    def backward(ctx, gout):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * gout.to(dlogits.dtype), None, None, None
+
+
+def ce_label_smooth(logits: torch.Tensor, target: torch.Tensor, eps: float = 0.1,
+                    stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Label-smoothing cross entropy. ``stats`` (float[2], optional) accumulates [loss, #top-1 hits] on device, which
+    replaces the per-step ``.cpu().item()`` syncs of ``methods/baseline.py:47-48``."""
+    if not logits.is_cuda:
+        loss = ce_label_smooth_reference(logits, target, eps)
+        if stats is not None:
+            with torch.no_grad():
+                stats[0] += loss.detach()
+                stats[1] += (logits.argmax(1) == target).sum()
+        return loss
+    assert logits.stride(1) == 1 and logits.dtype in (torch.bfloat16, torch.float32)
+    return _CELabelSmoothFn.apply(logits, target.long().contiguous(), float(eps), stats)
+
+
+# --------------------------------------------------------------------------------------------- batch norm (NHWC)
+class _BNTrainFn(torch.autograd.Function):
+    """Training-mode batch norm over ``[M, C]`` bf16 (NHWC flattened), optional fused residual add + ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, eps, momentum, relu):
+        m, c = x.shape
+        dev = x.device
+        y = torch.empty_like(x)
+        scratch = torch.zeros(6, c, dtype=torch.float32, device=dev)  # sum, sqsum, mean, rstd, scale, shift
+        lib = native.load()
+        rc = lib.flpr_bn_fwd(native.ptr(x), native.ptr(gamma), native.ptr(beta), native.ptr(residual), native.ptr(y),
+                             native.ptr(scratch[0]), native.ptr(scratch[1]), native.ptr(scratch[2]),
+                             native.ptr(scratch[3]), native.ptr(scratch[4]), native.ptr(scratch[5]),
+                             native.ptr(running_mean), native.ptr(running_var), m, c, eps, momentum, int(relu),
+                             native.stream(dev))
+        native.check(rc, "flpr_bn_fwd")
+        native.count_launch(3)
+        ctx.save_for_backward(x, y, gamma, scratch)
+        ctx.relu = relu
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, scratch = ctx.saved_tensors
+        m, c = x.shape
+        dy = dy.contiguous()
+        dgb = torch.zeros(2, c, dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if ctx.has_res else None
+        lib = native.load()
+        rc = lib.flpr_bn_bwd(native.ptr(dy), native.ptr(y), native.ptr(x), native.ptr(scratch[2]),
+                             native.ptr(scratch[3]), native.ptr(gamma), native.ptr(dgb[0]), native.ptr(dgb[1]),
+                             native.ptr(dres), native.ptr(dx), m, c, int(ctx.relu), native.stream(x.device))
+        native.check(rc, "flpr_bn_bwd")
+        native.count_launch(2)
+        return dx, dgb[0], dgb[1], None, None, dres, None, None, None
+
+
+def batch_norm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, running_mean: Optional[torch.Tensor],
+                    running_var: Optional[torch.Tensor], *, training: bool, eps: float = 1e-5, momentum: float = 0.1,
+                    relu: bool = False, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """BatchNorm over ``[M, C]`` (channels last) with fused residual + ReLU. fp32 affine parameters."""
+    if not x.is_cuda:
+        xf = x.float()
+        if training:
+            mean = xf.mean(0)
+            var = xf.var(0, unbiased=False)
+            if running_mean is not None:
+                with torch.no_grad():
+                    n = xf.shape[0]
+                    running_mean.mul_(1 - momentum).add_(mean.detach(), alpha=momentum)
+                    running_var.mul_(1 - momentum).add_(var.detach() * (n / max(n - 1, 1)), alpha=momentum)
+        else:
+            mean, var = running_mean, running_var
+        y = (xf - mean) * torch.rsqrt(var + eps) * gamma + beta
+        if residual is not None:
+            y = y + residual.float()
+        if relu:
+            y = torch.relu(y)
+        return y.to(x.dtype)
+    x = x.contiguous()
+    if training:
+        return _BNTrainFn.apply(x, gamma, beta, running_mean, running_var, residual, eps, momentum, relu)
+    scale = gamma * torch.rsqrt(running_var + eps)
+    shift = beta - running_mean * scale
+    return affine_act(x, scale, shift, relu=relu, residual=residual)
+
+
+def affine_act(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, *, relu: bool = False,
+               residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = relu?(x * scale[c] + shift[c] (+ residual)) over ``[M, C]`` bf16 (inference-mode BN)."""
+    if not x.is_cuda:
+        y = x.float() * scale + shift
+        if residual is not None:
+            y = y + residual.float()
+        return (torch.relu(y) if relu else y).to(x.dtype)
+    m, c = x.shape
+    y = torch.empty_like(x)
+    lib = native.load()
+    rc = lib.flpr_affine_act(native.ptr(x), native.ptr(scale.float().contiguous()),
+                             native.ptr(shift.float().contiguous()), native.ptr(residual), native.ptr(y), m, c,
+                             int(relu), native.stream(x.device))
+    native.check(rc, "flpr_affine_act")
+    native.count_launch()
+    return y
+
+
+class _GapFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        n, hw, c = x.shape
+        out = torch.empty(n, c, dtype=torch.float32, device=x.device)
+        lib = native.load()
+        native.check(lib.flpr_gap_fwd(native.ptr(x), native.ptr(out), None, n, hw, c, native.stream(x.device)),
+                     "flpr_gap_fwd")
+        native.count_launch()
+        ctx.shape = (n, hw, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        n, hw, c = ctx.shape
+        dx = torch.empty(n, hw, c, dtype=torch.bfloat16, device=dout.device)
+        lib = native.load()
+        native.check(lib.flpr_gap_bwd(native.ptr(dout.float().contiguous()), native.ptr(dx), n, hw, c,
+                                      native.stream(dout.device)), "flpr_gap_bwd")
+        native.count_launch()
+        return dx
+
+
+def global_avg_pool_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """``[N, HW, C]`` bf16 -> ``[N, C]`` fp32."""
+    if not x.is_cuda:
+        return x.float().mean(1)
+    return _GapFn.apply(x.contiguous())

@@ -1,0 +1,206 @@
+"""Tensor-core GEMM / implicit-GEMM convolution ops (``csrc/gemm_tcgen05.cu``) and their autograd wrappers.
+
+Layout conventions: activations are NHWC bf16 flattened to ``[pixels, channels]``; weights are ``[out, in]`` (1x1 /
+linear) or ``[out, kh, kw, in]`` (3x3, "OHWI"), i.e. the reduction dim is always contiguous in the forward pass. The
+backward passes reuse the same kernel in its MN-major operand modes, so no tensor is ever transposed in memory.
+
+Reference call sites replaced: ``models/resnet.py:121-141`` (bottleneck convs), ``models/resnet.py:321``
+(classifier), ``tools/evaluate.py:100`` (gallery x query similarity).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import native
+
+
+def _bf(x: torch.Tensor) -> torch.Tensor:
+    return x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: bool = True,
+         out_dtype: torch.dtype = torch.bfloat16, trans_out: bool = False, alpha: float = 1.0,
+         bias_n: Optional[torch.Tensor] = None, bias_m: Optional[torch.Tensor] = None, relu: bool = False,
+         residual: Optional[torch.Tensor] = None, split_k: int = 1, bn: int = 0,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``D[M,N] = alpha * A @ B^T`` with bf16 operands and fp32 accumulation.
+
+    ``a`` is ``[M,K]`` (``a_kmajor``) or ``[K,M]``; ``b`` is ``[N,K]`` (``b_kmajor``) or ``[K,N]``.
+    Returns ``[M,N]`` (``[N,M]`` when ``trans_out``). ``split_k > 1`` accumulates atomically into a zeroed fp32 output.
+    """
+    M, K = (a.shape if a_kmajor else (a.shape[1], a.shape[0]))
+    N, Kb = (b.shape if b_kmajor else (b.shape[1], b.shape[0]))
+    assert K == Kb, f"reduction dims differ: {K} vs {Kb}"
+    if not a.is_cuda:
+        A = a.float() if a_kmajor else a.float().t()
+        B = b.float() if b_kmajor else b.float().t()
+        A, B = A.to(torch.bfloat16).float(), B.to(torch.bfloat16).float()
+        d = alpha * (A @ B.t())
+        if bias_n is not None:
+            d = d + bias_n.float()[None, :]
+        if bias_m is not None:
+            d = d + bias_m.float()[:, None]
+        if trans_out:
+            d = d.t()
+        if residual is not None:
+            d = d + residual.float()
+        if relu:
+            d = torch.relu(d)
+        d = d.to(out_dtype).contiguous()
+        if out is not None:
+            out.copy_(d)
+            return out
+        return d
+
+    lib = native.load()
+    a, b = _bf(a), _bf(b)
+    assert a.stride(-1) == 1 and b.stride(-1) == 1, "operands must be row-major"
+    lda, ldb = a.stride(0), b.stride(0)
+    oshape = (N, M) if trans_out else (M, N)
+    if out is None:
+        if split_k > 1:
+            out = torch.zeros(oshape, dtype=torch.float32, device=a.device)
+        else:
+            out = torch.empty(oshape, dtype=out_dtype, device=a.device)
+    assert out.stride(-1) == 1
+    if split_k > 1:
+        assert out.dtype == torch.float32
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.shape == out.shape and residual.stride() == out.stride()
+    rc = lib.flpr_gemm_bf16(native.ptr(a), native.ptr(b), native.ptr(out), M, N, K, lda, ldb, out.stride(0),
+                            0 if a_kmajor else 1, 0 if b_kmajor else 1, int(out.dtype == torch.bfloat16),
+                            int(trans_out), float(alpha), native.ptr(bias_n), native.ptr(bias_m), int(relu),
+                            native.ptr(residual), int(split_k), int(bn), native.stream(a.device))
+    native.check(rc, "flpr_gemm_bf16")
+    native.count_launch()
+    return out
+
+
+def conv_nhwc(x: torch.Tensor, w: torch.Tensor, *, padding: int = 1, out_dtype: torch.dtype = torch.bfloat16,
+              alpha: float = 1.0, bias: Optional[torch.Tensor] = None, relu: bool = False,
+              residual: Optional[torch.Tensor] = None, bn: int = 0) -> torch.Tensor:
+    """Stride-1 convolution as an implicit GEMM. ``x``: ``[N,H,W,C]`` bf16, ``w``: ``[Cout,KH,KW,C]``.
+
+    Returns ``[N,H,W,Cout]``. Zero padding is produced by TMA out-of-bounds fill.
+    """
+    n, h, wd, c = x.shape
+    cout, kh, kw, c2 = w.shape
+    assert c == c2
+    if not x.is_cuda:
+        xx = x.to(torch.bfloat16).float().permute(0, 3, 1, 2)
+        ww = w.to(torch.bfloat16).float().permute(0, 3, 1, 2)
+        y = alpha * F.conv2d(xx, ww, padding=padding)
+        if bias is not None:
+            y = y + bias.float()[None, :, None, None]
+        y = y.permute(0, 2, 3, 1)
+        if residual is not None:
+            y = y + residual.float()
+        if relu:
+            y = torch.relu(y)
+        return y.to(out_dtype).contiguous()
+    lib = native.load()
+    x, w = _bf(x).contiguous(), _bf(w).contiguous()
+    out = torch.empty((n, h, wd, cout), dtype=out_dtype, device=x.device)
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.shape == out.shape
+    rc = lib.flpr_conv_nhwc_bf16(native.ptr(x), native.ptr(w), native.ptr(out), n, h, wd, c, cout, kh, kw, padding,
+                                 padding, int(out_dtype == torch.bfloat16), float(alpha), native.ptr(bias), int(relu),
+                                 native.ptr(residual), int(bn), native.stream(x.device))
+    native.check(rc, "flpr_conv_nhwc_bf16")
+    native.count_launch()
+    return out
+
+
+def _auto_split(m: int, n: int, k: int) -> int:
+    """split-K factor for weight-gradient GEMMs (small MxN, very long K)."""
+    tiles = ((m + 127) // 128) * ((n + 127) // 128)
+    kb = (k + 63) // 64
+    if tiles >= 148 or kb < 8:
+        return 1
+    return max(1, min(kb // 4, (2 * 148 + tiles - 1) // tiles))
+
+
+class _LinearFn(torch.autograd.Function):
+    """y[M,N] = x[M,K] @ w[N,K]^T using the bf16 compute copy; gradients: dx bf16, dw fp32 (for the fp32 master)."""
+
+    @staticmethod
+    def forward(ctx, x, w_master, w_bf16):
+        ctx.save_for_backward(x, w_bf16)
+        ctx.w_needs_grad = w_master.requires_grad
+        return gemm(x, w_bf16)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _bf(dy).contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dy, w, b_kmajor=False)                               # [M,N] x [N,K]
+        if ctx.w_needs_grad:
+            m, n, k = w.shape[0], w.shape[1], dy.shape[0]
+            dw = gemm(dy, x, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32,
+                      split_k=_auto_split(m, n, k))                        # dy^T x -> [N,K]
+        return dx, dw, None
+
+
+def linear(x: torch.Tensor, w_master: torch.Tensor, w_bf16: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Linear / 1x1-conv on flattened NHWC activations. ``w_master`` fp32 ``[out,in]`` receives the gradient."""
+    if w_bf16 is None:
+        w_bf16 = w_master.detach().to(torch.bfloat16)
+    return _LinearFn.apply(_bf(x), w_master, w_bf16)
+
+
+class _Conv3x3Fn(torch.autograd.Function):
+    """3x3 / stride 1 / pad 1 NHWC convolution. Forward + dgrad on the tcgen05 implicit-GEMM kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w_master, w_bf16):
+        ctx.save_for_backward(x, w_bf16)
+        ctx.w_needs_grad = w_master.requires_grad
+        return conv_nhwc(x, w_bf16, padding=1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _bf(dy).contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            # dgrad = correlation of dy with the spatially flipped, channel-transposed filter
+            wt = w.flip(1, 2).permute(3, 1, 2, 0).contiguous()            # [Cin,KH,KW,Cout]
+            dx = conv_nhwc(dy, wt, padding=1)
+        if ctx.w_needs_grad:
+            dw = conv3x3_wgrad(x, dy)
+        return dx, dw, None
+
+
+def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """dW[Cout,3,3,Cin] (fp32) = sum over pixels of dy (x) shifted x. One MN-major GEMM per filter tap."""
+    n, h, w, cin = x.shape
+    cout = dy.shape[-1]
+    if not x.is_cuda:
+        xx = x.float().permute(0, 3, 1, 2)
+        dd = dy.float().permute(0, 3, 1, 2)
+        g = torch.nn.grad.conv2d_weight(xx, (cout, cin, 3, 3), dd, padding=1)
+        return g.permute(0, 2, 3, 1).contiguous()
+    # shifted copies of x (zero padded) feed the MN-major GEMM; 9 taps share one padded buffer
+    xp = F.pad(x, (0, 0, 1, 1, 1, 1))                                      # [N,H+2,W+2,C]
+    dw = torch.zeros((cout, 3, 3, cin), dtype=torch.float32, device=x.device)
+    dy2 = dy.reshape(-1, cout)
+    m = n * h * w
+    split = _auto_split(cout, cin, m)
+    for kh in range(3):
+        for kw in range(3):
+            xs = xp[:, kh:kh + h, kw:kw + w, :].reshape(m, cin)             # gather is a strided copy
+            out_view = dw[:, kh, kw, :]
+            gemm(dy2, xs, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32, split_k=max(split, 2),
+                 out=out_view)
+    return dw
+
+
+def conv3x3(x: torch.Tensor, w_master: torch.Tensor, w_bf16: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if w_bf16 is None:
+        w_bf16 = w_master.detach().to(torch.bfloat16)
+    return _Conv3x3Fn.apply(_bf(x), w_master, w_bf16)

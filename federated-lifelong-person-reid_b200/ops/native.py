@@ -1,0 +1,126 @@
+"""ctypes bindings for ``lib/libflpr_b200.so`` (the sm_100a kernels in ``csrc/``).
+
+Policy: on a CUDA tensor every op in :mod:`flpr_b200.ops` goes through the native library and raises loudly if the
+library is missing or a launch fails — there is no silent eager fallback on a GPU box. On CPU tensors the ops use a
+plain fp32 PyTorch reference (that is what the CPU test-suite exercises).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+import torch
+
+from .. import _build  # type: ignore
+
+_lock = threading.Lock()
+_lib: Optional[C.CDLL] = None
+
+c_void_p, c_int, c_float, c_size_t, c_ll, c_double = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong, C.c_double
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def available() -> bool:
+    return os.path.exists(_build.LIB_PATH)
+
+
+def _declare(lib: C.CDLL) -> None:
+    P, I, F, Z, L, D = c_void_p, c_int, c_float, c_size_t, c_ll, c_double
+    sig = {
+        "flpr_gemm_bf16": [P, P, P, I, I, I, L, L, L, I, I, I, I, F, P, P, I, P, I, I, P],
+        "flpr_conv_nhwc_bf16": [P, P, P, I, I, I, I, I, I, I, I, I, I, F, P, I, P, I, P],
+        "flpr_symm_alloc": [C.POINTER(P), Z],
+        "flpr_symm_free": [P],
+        "flpr_ipc_get_handle": [P, P],
+        "flpr_ipc_open_handle": [P, C.POINTER(P)],
+        "flpr_ipc_close": [P],
+        "flpr_enable_peer": [I, I],
+        "flpr_comm_read_error": [P, C.POINTER(I)],
+        "flpr_comm_barrier": [I, I, P, D, P],
+        "flpr_comm_reduce_bcast": [I, I, P, D, I, P, P, P, P, Z, I, P],
+        "flpr_comm_mix": [I, I, P, D, I, I, P, P, P, P, P, Z, I, P],
+        "flpr_comm_curv_moments": [I, I, P, D, I, P, P, P, P, P, Z, I, P],
+        "flpr_comm_gather_strided": [I, I, P, D, I, P, P, Z, I, P],
+        "flpr_comm_pull_copy": [I, I, P, D, P, P, P, Z, I, P],
+        "flpr_fused_opt": [I, P, P, P, P, P, P, P, P, P, Z, F, F, F, F, F, I, F, F, F, F, I, P],
+        "flpr_importance_accum": [P, P, Z, F, I, P],
+        "flpr_cast_bf16": [P, P, Z, P],
+        "flpr_compose": [P, P, F, P, P, Z, P],
+        "flpr_ce_label_smooth": [P, P, P, P, I, I, L, F, F, I, I, P],
+        "flpr_bn_fwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, F, F, I, P],
+        "flpr_affine_act": [P, P, P, P, P, I, I, I, P],
+        "flpr_bn_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, P],
+        "flpr_gap_fwd": [P, P, P, I, I, I, P],
+        "flpr_gap_bwd": [P, P, I, I, I, P],
+        "flpr_rank_eval": [P, P, P, P, P, I, I, L, P],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = I
+    for name in ("flpr_gemm_last_error", "flpr_comm_last_error"):
+        getattr(lib, name).restype = C.c_char_p
+        getattr(lib, name).argtypes = []
+    for name in ("flpr_comm_flag_page_bytes", "flpr_comm_max_clients", "flpr_comm_max_local", "flpr_comm_max_ranks"):
+        getattr(lib, name).restype = I
+        getattr(lib, name).argtypes = []
+
+
+def load(build_if_missing: bool = False) -> C.CDLL:
+    """Load (once) and return the native library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_build.LIB_PATH):
+            if build_if_missing:
+                _build.build()
+            else:
+                raise NativeError(
+                    f"native library {_build.LIB_PATH} is missing - run `python __graft_entry__.py build` "
+                    "(ops on CUDA tensors never fall back to eager PyTorch)")
+        lib = C.CDLL(_build.LIB_PATH, mode=C.RTLD_GLOBAL)
+        _declare(lib)
+        _lib = lib
+    return _lib
+
+
+def ptr(t: Optional[torch.Tensor]) -> c_void_p:
+    if t is None:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())
+
+
+def stream(device: Optional[torch.device] = None) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        lib = load()
+        msg = (lib.flpr_gemm_last_error() or b"").decode() + " | " + (lib.flpr_comm_last_error() or b"").decode()
+        raise NativeError(f"{what} failed with code {rc}: {msg}")
+
+
+# launch counter: bench.py reports how many flpr kernels were launched inside the timed region
+_launches = 0
+
+
+def count_launch(n: int = 1) -> None:
+    global _launches
+    _launches += n
+
+
+def launches() -> int:
+    return _launches

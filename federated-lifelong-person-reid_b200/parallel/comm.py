@@ -1,0 +1,339 @@
+"""Federated communicator: one rank per GPU, clients round-robined over ranks, symmetric device arenas.
+
+The reference has no communication layer at all ("network" = dict hand-off + ``torch.save``,
+``experiment.py:189-203,233-241``). Here the exchange is the product:
+
+* ``p2p``  (CUDA)  – every rank ``cudaMalloc``s one arena, IPC handles are swapped once over the bootstrap process
+  group, and the collectives are the hand-written NVLink peer-memory kernels of ``csrc/fedcomm.cu``.
+* ``nccl`` (CUDA)  – the *baseline harness*: the same API expressed with ``torch.distributed`` all-gathers plus local
+  math. This is what the fused kernels are measured against; it is never used by the engine unless asked for.
+* ``gloo`` (CPU)   – plumbing mode for world_size>1 without GPUs (tests, BASELINE config 1).
+* ``local``        – world_size == 1 on CPU.
+
+Buffers are *symmetric*: every rank performs the same sequence of allocations, so a buffer has the same offset in
+every arena and a peer address is ``peer_base[rank] + offset``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from ..ops import native
+
+
+@dataclass
+class _Buf:
+    name: str
+    offset: int        # bytes from arena base
+    n: int             # elements per slot
+    slots: int         # slots per rank (clients per rank) or 1 for rank buffers
+    dtype: torch.dtype
+    per_client: bool
+
+
+class _RawCuda:
+    """Expose a raw device allocation to torch through ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def _dist_ready() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+class FedComm:
+    def __init__(self, device: torch.device | str, num_clients: int, arena_bytes: int = 1 << 30,
+                 mode: Optional[str] = None, timeout_s: float = 30.0, comm_blocks: int = 0, group=None):
+        self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.group = group
+        self.rank = dist.get_rank(group) if _dist_ready() else 0
+        self.world = dist.get_world_size(group) if _dist_ready() else 1
+        self.K = int(num_clients)
+        self.slots = (self.K + self.world - 1) // self.world
+        if mode is None:
+            mode = "p2p" if self.device.type == "cuda" else ("gloo" if self.world > 1 else "local")
+        self.mode = mode
+        self.timeout_s = float(timeout_s)
+        self.arena_bytes = int(arena_bytes)
+        self.bufs: Dict[str, _Buf] = {}
+        self._cursor = 0
+        self._peer_base: List[int] = []
+        self._keep = []
+        self.bytes_moved = 0          # algorithmic NVLink/peer bytes pulled+pushed by this rank
+        if self.mode == "p2p":
+            self._init_p2p()
+            self.comm_blocks = comm_blocks or 148 * 2
+        else:
+            self._arena = torch.zeros(self.arena_bytes, dtype=torch.uint8, device=self.device)
+            self.comm_blocks = 0
+
+    # ------------------------------------------------------------------ placement
+    def owner(self, client: int) -> int:
+        return client % self.world
+
+    def slot(self, client: int) -> int:
+        return client // self.world
+
+    def local_clients(self) -> List[int]:
+        return [c for c in range(self.K) if self.owner(c) == self.rank]
+
+    # ------------------------------------------------------------------ arena
+    def _init_p2p(self) -> None:
+        lib = native.load()
+        self._lib = lib
+        if lib.flpr_comm_max_ranks() < self.world:
+            raise native.NativeError(f"world size {self.world} exceeds MAX_RANKS")
+        if lib.flpr_comm_max_clients() < self.K:
+            raise native.NativeError(f"{self.K} clients exceed MAX_CLIENTS")
+        torch.cuda.set_device(self.device)
+        base = C.c_void_p()
+        native.check(lib.flpr_symm_alloc(C.byref(base), self.arena_bytes), "flpr_symm_alloc")
+        self._base = base.value
+        self._arena = torch.as_tensor(_RawCuda(self._base, self.arena_bytes), device=self.device)
+        self._flag_bytes = ((lib.flpr_comm_flag_page_bytes() + 4095) // 4096) * 4096
+        self._cursor = self._flag_bytes
+        if self.world > 1:
+            handle = (C.c_ubyte * 64)()
+            native.check(lib.flpr_ipc_get_handle(C.c_void_p(self._base), handle), "flpr_ipc_get_handle")
+            handles: List[Optional[bytes]] = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=self.group)
+            for r in range(self.world):
+                if r == self.rank:
+                    self._peer_base.append(self._base)
+                else:
+                    p = C.c_void_p()
+                    buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                    native.check(lib.flpr_ipc_open_handle(buf, C.byref(p)), f"flpr_ipc_open_handle(rank {r})")
+                    self._peer_base.append(p.value)
+            dist.barrier(group=self.group)
+        else:
+            self._peer_base = [self._base]
+        self._flag_pages = (C.c_void_p * self.world)(*[C.c_void_p(b) for b in self._peer_base])
+
+    def close(self) -> None:
+        if self.mode == "p2p" and getattr(self, "_base", None):
+            torch.cuda.synchronize(self.device)
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            for r, p in enumerate(self._peer_base):
+                if r != self.rank:
+                    self._lib.flpr_ipc_close(C.c_void_p(p))
+            self._arena = None
+            self._lib.flpr_symm_free(C.c_void_p(self._base))
+            self._base = None
+
+    def _alloc(self, name: str, n: int, slots: int, dtype: torch.dtype, per_client: bool) -> _Buf:
+        if name in self.bufs:
+            b = self.bufs[name]
+            assert (b.n, b.slots, b.dtype) == (n, slots, dtype), f"buffer {name} re-declared with a different shape"
+            return b
+        item = torch.empty((), dtype=dtype).element_size()
+        assert (n * item) % 16 == 0, "symmetric buffers must be multiples of 16 bytes per slot"
+        nbytes = n * item * slots
+        off = (self._cursor + 255) // 256 * 256
+        if off + nbytes > self.arena_bytes:
+            raise MemoryError(f"symmetric arena exhausted allocating {name}: need {off + nbytes} of {self.arena_bytes}")
+        self._cursor = off + nbytes
+        b = _Buf(name, off, n, slots, dtype, per_client)
+        self.bufs[name] = b
+        return b
+
+    def alloc_client_buffer(self, name: str, n: int, dtype: torch.dtype = torch.float32) -> None:
+        """One slot of ``n`` elements for every client (``ceil(K/world)`` slots per rank)."""
+        self._alloc(name, n, self.slots, dtype, True)
+
+    def alloc_rank_buffer(self, name: str, n: int, dtype: torch.dtype = torch.float32) -> None:
+        self._alloc(name, n, 1, dtype, False)
+
+    def _view(self, b: _Buf, slot: int) -> torch.Tensor:
+        item = torch.empty((), dtype=b.dtype).element_size()
+        start = b.offset + slot * b.n * item
+        return self._arena[start:start + b.n * item].view(b.dtype)
+
+    def client_view(self, name: str, client: int) -> torch.Tensor:
+        assert self.owner(client) == self.rank, f"client {client} is not hosted on rank {self.rank}"
+        return self._view(self.bufs[name], self.slot(client))
+
+    def rank_view(self, name: str) -> torch.Tensor:
+        return self._view(self.bufs[name], 0)
+
+    def _addr(self, b: _Buf, rank: int, slot: int) -> int:
+        item = torch.empty((), dtype=b.dtype).element_size()
+        return self._peer_base[rank] + b.offset + slot * b.n * item
+
+    def _client_ptrs(self, name: str, clients: Sequence[int]):
+        b = self.bufs[name]
+        arr = (C.c_void_p * len(clients))(*[C.c_void_p(self._addr(b, self.owner(c), self.slot(c))) for c in clients])
+        return arr
+
+    def _rank_ptrs(self, name: str):
+        b = self.bufs[name]
+        return (C.c_void_p * self.world)(*[C.c_void_p(self._addr(b, r, 0)) for r in range(self.world)])
+
+    def _remote(self, clients: Sequence[int]) -> int:
+        return sum(1 for c in clients if self.owner(c) != self.rank)
+
+    # ------------------------------------------------------------------ gather helper for non-p2p modes
+    def _gather_clients(self, name: str, clients: Sequence[int]) -> torch.Tensor:
+        """[len(clients), n] on every rank via a library all-gather (baseline / CPU modes)."""
+        b = self.bufs[name]
+        local = torch.stack([self._view(b, s) for s in range(b.slots)]).contiguous()      # [slots, n]
+        if self.world == 1:
+            allb = local
+        else:
+            allb = torch.empty((self.world * b.slots, b.n), dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(allb, local, group=self.group)
+        return torch.stack([allb[self.owner(c) * b.slots + self.slot(c)] for c in clients])
+
+    def check_errors(self) -> None:
+        if self.mode != "p2p":
+            return
+        err = C.c_int(0)
+        self._lib.flpr_comm_read_error(C.c_void_p(self._base), C.byref(err))
+        if err.value:
+            raise native.NativeError("a flpr collective timed out waiting for a peer rank (flag watchdog fired)")
+
+    # ------------------------------------------------------------------ collectives
+    def barrier(self) -> None:
+        if self.mode == "p2p":
+            rc = self._lib.flpr_comm_barrier(self.rank, self.world, self._flag_pages, self.timeout_s,
+                                             native.stream(self.device))
+            native.check(rc, "flpr_comm_barrier")
+            native.count_launch()
+        elif self.world > 1:
+            dist.barrier(group=self.group)
+
+    def reduce_bcast(self, src: str, dst: str, clients: Sequence[int], cnt: Optional[str] = None,
+                     weights: Optional[Sequence[float]] = None) -> None:
+        """C1+C2: ``dst = sum_c w_c * src_c`` on every rank; ``w_c = cnt_c / sum(cnt)`` when ``cnt`` names a
+        per-client scalar buffer (FedAvg ``train_cnt`` weighting, ``methods/fedavg.py:386-397``)."""
+        bs, bd = self.bufs[src], self.bufs[dst]
+        assert bs.n == bd.n and bs.dtype == torch.float32 and bd.dtype == torch.float32
+        if self.mode == "p2p":
+            srcp = self._client_ptrs(src, clients)
+            cntp = self._client_ptrs(cnt, clients) if cnt is not None else None
+            wv = (C.c_float * len(clients))(*[float(x) for x in weights]) if weights is not None else None
+            rc = self._lib.flpr_comm_reduce_bcast(self.rank, self.world, self._flag_pages, self.timeout_s, len(clients),
+                                                  srcp, cntp, wv, self._rank_ptrs(dst), bs.n, self.comm_blocks,
+                                                  native.stream(self.device))
+            native.check(rc, "flpr_comm_reduce_bcast")
+            native.count_launch()
+            share = bs.n * 4 / self.world
+            self.bytes_moved += int(share * self._remote(clients) + share * (self.world - 1))
+            return
+        stack = self._gather_clients(src, clients).float()
+        if cnt is not None:
+            w = self._gather_clients(cnt, clients)[:, 0].float()
+            w = w / w.sum()
+        else:
+            w = torch.tensor(list(weights), dtype=torch.float32, device=stack.device)
+        self.rank_view(dst).copy_((w[:, None] * stack).sum(0))
+
+    def mix(self, src: str, clients: Sequence[int], rows: torch.Tensor, local_clients: Sequence[int],
+            dst_g: Optional[Sequence[torch.Tensor]] = None, dst_theta: Optional[Sequence[torch.Tensor]] = None,
+            dst_bf16: Optional[Sequence[torch.Tensor]] = None) -> None:
+        """C4: for every local client ``i``: ``out_i = sum_j rows[i, j] * src_j`` written to ``dst_g[i]``,
+        ``dst_theta[i]`` (fp32) and ``dst_bf16[i]`` in one pass. ``rows``: ``[len(local_clients), len(clients)]``."""
+        bs = self.bufs[src]
+        L = len(local_clients)
+        if L == 0 and self.mode != "p2p":
+            if self.world > 1:
+                self._gather_clients(src, clients)  # keep the collective sequence aligned
+            return
+        rows_h = rows.detach().float().cpu().contiguous()
+        if self.mode == "p2p":
+            max_l = self._lib.flpr_comm_max_local()
+            srcp = self._client_ptrs(src, clients)
+            # every rank issues the same number of launches (the kernels barrier across ranks)
+            n_launch = (self.slots + max_l - 1) // max_l
+            for it in range(n_launch):
+                idx = list(range(it * max_l, min((it + 1) * max_l, L)))
+                wv = (C.c_float * max(len(idx) * len(clients), 1))(*rows_h[idx].reshape(-1).tolist()) if idx else \
+                    (C.c_float * 1)(0.0)
+
+                def arr(lst):
+                    if lst is None or not idx:
+                        return None
+                    return (C.c_void_p * len(idx))(*[C.c_void_p(lst[i].data_ptr()) for i in idx])
+
+                rc = self._lib.flpr_comm_mix(self.rank, self.world, self._flag_pages, self.timeout_s, len(clients),
+                                             len(idx), srcp, wv, arr(dst_g), arr(dst_theta), arr(dst_bf16), bs.n,
+                                             self.comm_blocks, native.stream(self.device))
+                native.check(rc, "flpr_comm_mix")
+                native.count_launch()
+                if idx:
+                    self.bytes_moved += int(bs.n * 4 * self._remote(clients))
+            return
+        stack = self._gather_clients(src, clients).float()
+        out = rows_h.to(stack.device) @ stack
+        for i in range(L):
+            if dst_g is not None:
+                dst_g[i].view(-1).copy_(out[i])
+            if dst_theta is not None:
+                dst_theta[i].view(-1).copy_(out[i])
+            if dst_bf16 is not None:
+                dst_bf16[i].view(-1).copy_(out[i])
+
+    def curv_moments(self, fisher: str, param: str, clients: Sequence[int], dst_f: str, dst_fp: str, dst_fpp: str
+                     ) -> None:
+        """C3: ``sum_j F_j``, ``sum_j F_j p_j``, ``sum_j F_j p_j^2`` into three rank buffers on every rank."""
+        bf = self.bufs[fisher]
+        if self.mode == "p2p":
+            rc = self._lib.flpr_comm_curv_moments(self.rank, self.world, self._flag_pages, self.timeout_s, len(clients),
+                                                  self._client_ptrs(fisher, clients), self._client_ptrs(param, clients),
+                                                  self._rank_ptrs(dst_f), self._rank_ptrs(dst_fp),
+                                                  self._rank_ptrs(dst_fpp), bf.n, self.comm_blocks,
+                                                  native.stream(self.device))
+            native.check(rc, "flpr_comm_curv_moments")
+            native.count_launch()
+            share = bf.n * 4 / self.world
+            self.bytes_moved += int(2 * share * self._remote(clients) + 3 * share * (self.world - 1))
+            return
+        Fs = self._gather_clients(fisher, clients).float()
+        Ps = self._gather_clients(param, clients).float()
+        self.rank_view(dst_f).copy_(Fs.sum(0))
+        self.rank_view(dst_fp).copy_((Fs * Ps).sum(0))
+        self.rank_view(dst_fpp).copy_((Fs * Ps * Ps).sum(0))
+
+    def gather_strided(self, src: str, clients: Sequence[int], out: torch.Tensor) -> None:
+        """C5/C6: ``out[e, j] = src_{clients[j]}[e]`` (trailing client dim), ``out`` local ``[n, len(clients)]``."""
+        bs = self.bufs[src]
+        assert out.is_contiguous() and out.numel() == bs.n * len(clients)
+        if self.mode == "p2p":
+            rc = self._lib.flpr_comm_gather_strided(self.rank, self.world, self._flag_pages, self.timeout_s,
+                                                    len(clients), self._client_ptrs(src, clients), native.ptr(out),
+                                                    bs.n, self.comm_blocks, native.stream(self.device))
+            native.check(rc, "flpr_comm_gather_strided")
+            native.count_launch()
+            self.bytes_moved += int(bs.n * 4 * self._remote(clients))
+            return
+        stack = self._gather_clients(src, clients).float()
+        out.view(bs.n, len(clients)).copy_(stack.t())
+
+    def pull(self, src: str, client: int, dst: Optional[torch.Tensor] = None,
+             dst_bf16: Optional[torch.Tensor] = None) -> None:
+        """C2: copy client ``client``'s slot of ``src`` (wherever it lives) into local tensors (fp32 and/or bf16)."""
+        bs = self.bufs[src]
+        if self.mode == "p2p":
+            addr = self._addr(bs, self.owner(client), self.slot(client))
+            rc = self._lib.flpr_comm_pull_copy(self.rank, self.world, self._flag_pages, self.timeout_s,
+                                               C.c_void_p(addr), native.ptr(dst), native.ptr(dst_bf16), bs.n,
+                                               self.comm_blocks, native.stream(self.device))
+            native.check(rc, "flpr_comm_pull_copy")
+            native.count_launch()
+            if self.owner(client) != self.rank:
+                self.bytes_moved += bs.n * 4
+            return
+        row = self._gather_clients(src, [client])[0]
+        if dst is not None:
+            dst.view(-1).copy_(row)
+        if dst_bf16 is not None:
+            dst_bf16.view(-1).copy_(row)

@@ -1,0 +1,287 @@
+"""Numerics of every sm_100a kernel against a plain fp32 PyTorch reference (runs on the B200 box)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_gemm(a, b):
+    return a.to(torch.bfloat16).float() @ b.to(torch.bfloat16).float().t()
+
+
+def _close(x, ref, rtol=2e-2, atol=None):
+    ref = ref.float()
+    x = x.float()
+    if atol is None:
+        atol = 2e-2 * ref.abs().max().item() + 1e-6
+    err = (x - ref).abs().max().item()
+    assert torch.allclose(x, ref, rtol=rtol, atol=atol), f"max abs err {err} (ref max {ref.abs().max().item()})"
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (256, 512, 512), (200, 136, 320), (64, 8000, 2048),
+                                   (8192, 512, 1024), (8192, 2048, 512), (77, 24, 72)])
+@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+def test_gemm_kmajor(m, n, k, bn):
+    from flpr_b200.ops.gemm import gemm
+    torch.manual_seed(0)
+    a = torch.randn(m, k, device="cuda")
+    b = torch.randn(n, k, device="cuda")
+    ref = _ref_gemm(a, b)
+    out = gemm(a.bfloat16(), b.bfloat16(), out_dtype=torch.float32, bn=bn)
+    _close(out, ref, rtol=1e-3, atol=1e-3 * math.sqrt(k))
+    outb = gemm(a.bfloat16(), b.bfloat16(), bn=bn)
+    _close(outb, ref)
+
+
+@pytest.mark.parametrize("amaj,bmaj", [(True, False), (False, True), (False, False)])
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (512, 2048, 8192), (2048, 512, 4096), (8192, 1024, 512),
+                                   (136, 72, 200)])
+def test_gemm_mn_major(amaj, bmaj, m, n, k):
+    from flpr_b200.ops.gemm import gemm
+    torch.manual_seed(1)
+    a = torch.randn(m, k, device="cuda")
+    b = torch.randn(n, k, device="cuda")
+    ref = _ref_gemm(a, b)
+    aa = a.bfloat16() if amaj else a.t().contiguous().bfloat16()
+    bb = b.bfloat16() if bmaj else b.t().contiguous().bfloat16()
+    out = gemm(aa, bb, a_kmajor=amaj, b_kmajor=bmaj, out_dtype=torch.float32)
+    _close(out, ref, rtol=1e-3, atol=1e-3 * math.sqrt(k))
+
+
+def test_gemm_epilogues():
+    from flpr_b200.ops.gemm import gemm
+    torch.manual_seed(2)
+    m, n, k = 300, 520, 256
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    b = torch.randn(n, k, device="cuda").bfloat16()
+    bias_n = torch.randn(n, device="cuda")
+    bias_m = torch.randn(m, device="cuda")
+    res = torch.randn(m, n, device="cuda").bfloat16()
+    ref = 0.5 * (a.float() @ b.float().t()) + bias_n[None] + bias_m[:, None] + res.float()
+    out = gemm(a, b, out_dtype=torch.float32, alpha=0.5, bias_n=bias_n, bias_m=bias_m, residual=res)
+    _close(out, ref, rtol=1e-3, atol=2e-2)
+    out = gemm(a, b, out_dtype=torch.bfloat16, alpha=0.5, bias_n=bias_n, bias_m=bias_m, residual=res, relu=True)
+    _close(out, torch.relu(ref))
+    # transposed output (swap-AB style)
+    out_t = gemm(a, b, out_dtype=torch.float32, trans_out=True)
+    _close(out_t, (a.float() @ b.float().t()).t(), rtol=1e-3, atol=2e-2)
+    # split-K
+    k2 = 4096
+    a2 = torch.randn(256, k2, device="cuda").bfloat16()
+    b2 = torch.randn(384, k2, device="cuda").bfloat16()
+    out = gemm(a2, b2, out_dtype=torch.float32, split_k=8)
+    _close(out, a2.float() @ b2.float().t(), rtol=1e-3, atol=0.1)
+
+
+@pytest.mark.parametrize("n,h,w,c,cout", [(4, 16, 8, 512, 512), (3, 8, 4, 64, 128), (2, 32, 16, 128, 64),
+                                          (5, 16, 8, 64, 96), (8, 8, 4, 128, 256)])
+@pytest.mark.parametrize("ks", [1, 3])
+def test_conv_nhwc(n, h, w, c, cout, ks):
+    from flpr_b200.ops.gemm import conv_nhwc
+    torch.manual_seed(3)
+    x = torch.randn(n, h, w, c, device="cuda").bfloat16()
+    wt = (torch.randn(cout, ks, ks, c, device="cuda") / math.sqrt(c * ks * ks)).bfloat16()
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2),
+                                     padding=ks // 2).permute(0, 2, 3, 1)
+    out = conv_nhwc(x, wt, padding=ks // 2, out_dtype=torch.float32)
+    _close(out, ref, rtol=1e-3, atol=2e-2)
+
+
+def test_linear_and_conv_autograd():
+    from flpr_b200.ops.gemm import linear, conv3x3
+    torch.manual_seed(4)
+    x = torch.randn(256, 512, device="cuda").bfloat16().requires_grad_(True)
+    w = (torch.randn(384, 512, device="cuda") / 20).requires_grad_(True)
+    y = linear(x, w)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    wr = w.detach().bfloat16().float().requires_grad_(True)
+    yr = xr @ wr.t()
+    yr.backward(gy.float())
+    _close(y, yr)
+    _close(x.grad, xr.grad)
+    _close(w.grad, wr.grad, rtol=1e-2, atol=0.05 * wr.grad.abs().max().item())
+
+    xc = torch.randn(4, 16, 8, 128, device="cuda").bfloat16().requires_grad_(True)
+    wc = (torch.randn(64, 3, 3, 128, device="cuda") / 30).requires_grad_(True)
+    yc = conv3x3(xc, wc)
+    gc = torch.randn_like(yc)
+    yc.backward(gc)
+    xr = xc.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wc.detach().bfloat16().float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr, padding=1)
+    yr.backward(gc.float().permute(0, 3, 1, 2))
+    _close(yc, yr.permute(0, 2, 3, 1))
+    _close(xc.grad, xr.grad.permute(0, 2, 3, 1))
+    _close(wc.grad, wr.grad.permute(0, 2, 3, 1), rtol=1e-2, atol=0.05 * wr.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("kind", ["adam", "sgd"])
+def test_fused_optimizer(kind):
+    from flpr_b200.ops.fused import fused_optimizer_step
+    torch.manual_seed(5)
+    n = 1 << 20
+    dev = "cuda"
+
+    def mk():
+        torch.manual_seed(5)
+        return [torch.randn(n), torch.randn(n), torch.zeros(n), torch.zeros(n), torch.rand(n), torch.randn(n),
+                torch.randn(n)]
+    cpu = mk()
+    gpu = [t.to(dev) for t in mk()]
+    st_c, st_g = torch.zeros(2), torch.zeros(2, device=dev)
+    shadow = torch.empty(n, dtype=torch.bfloat16, device=dev)
+    for step in (1, 2, 3):
+        for (p, g, m, v, Q, R, G), st, sh in ((cpu, st_c, None), (gpu, st_g, shadow)):
+            fused_optimizer_step(kind, p, g, m, v, lr=1e-3, step=step, weight_decay=1e-5, momentum=0.9, Q=Q, R=R,
+                                 lam2=0.3, G=G, lam1=1e-3, atten=0.9, p_bf16=sh, stats=st)
+    _close(gpu[0].cpu(), cpu[0], rtol=1e-4, atol=1e-5)
+    _close(gpu[2].cpu(), cpu[2], rtol=1e-4, atol=1e-5)
+    _close(st_g.cpu(), st_c, rtol=1e-3, atol=1.0)
+    _close(shadow.float().cpu(), cpu[0], rtol=1e-2, atol=1e-2)
+
+
+def test_importance_and_cast_and_compose():
+    from flpr_b200.ops.fused import importance_accumulate, cast_bf16, compose_adaptive
+    n = 4096 * 33
+    g = torch.randn(n, device="cuda")
+    F1 = torch.zeros(n, device="cuda")
+    importance_accumulate(F1, g, 0.25, "fisher")
+    importance_accumulate(F1, g, 0.5, "mas")
+    _close(F1, 0.25 * g * g + 0.5 * g.abs(), rtol=1e-5, atol=1e-6)
+    _close(cast_bf16(g), g.bfloat16().float(), rtol=0, atol=0)
+    G = torch.randn(n, device="cuda")
+    A = torch.randn(n, device="cuda")
+    th = torch.empty(n, device="cuda")
+    thb = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    compose_adaptive(G, A, 0.9, th, thb)
+    _close(th, 0.9 * G + A, rtol=1e-6, atol=1e-6)
+    _close(thb, (0.9 * G + A).bfloat16(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ce_label_smooth(dtype):
+    from flpr_b200.ops.fused import ce_label_smooth, ce_label_smooth_reference
+    torch.manual_seed(6)
+    b, c = 64, 8000
+    logits = (torch.randn(b, c, device="cuda") * 3).to(dtype).requires_grad_(True)
+    tgt = torch.randint(0, c, (b,), device="cuda")
+    stats = torch.zeros(2, device="cuda")
+    loss = ce_label_smooth(logits, tgt, 0.1, stats)
+    loss.backward()
+    lr = logits.detach().float().requires_grad_(True)
+    ref = ce_label_smooth_reference(lr, tgt, 0.1)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 2e-3 * abs(ref.item())
+    _close(logits.grad, lr.grad, rtol=2e-2, atol=2e-5)
+    assert int(stats[1].item()) == int((lr.argmax(1) == tgt).sum().item())
+
+
+@pytest.mark.parametrize("relu,res", [(False, False), (True, False), (True, True)])
+def test_batch_norm_nhwc(relu, res):
+    from flpr_b200.ops.fused import batch_norm_nhwc
+    torch.manual_seed(7)
+    m, c = 4096, 512
+    x = (torch.randn(m, c, device="cuda") * 2 + 0.5).bfloat16().requires_grad_(True)
+    r = torch.randn(m, c, device="cuda").bfloat16().requires_grad_(True) if res else None
+    gamma = (torch.rand(c, device="cuda") + 0.5).requires_grad_(True)
+    beta = torch.randn(c, device="cuda").requires_grad_(True)
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    y = batch_norm_nhwc(x, gamma, beta, rm, rv, training=True, relu=relu, residual=r)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    rr = r.detach().float().requires_grad_(True) if res else None
+    gr, br = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    yr = torch.nn.functional.batch_norm(xr, rm2, rv2, gr, br, training=True, momentum=0.1, eps=1e-5)
+    if res:
+        yr = yr + rr
+    if relu:
+        yr = torch.relu(yr)
+    yr.backward(gy.float())
+    _close(y, yr, rtol=2e-2, atol=3e-2)
+    _close(x.grad, xr.grad, rtol=5e-2, atol=3e-2)
+    _close(gamma.grad, gr.grad, rtol=2e-2, atol=0.02 * gr.grad.abs().max().item())
+    _close(beta.grad, br.grad, rtol=2e-2, atol=0.02 * br.grad.abs().max().item())
+    _close(rm, rm2, rtol=1e-3, atol=1e-3)
+    _close(rv, rv2, rtol=1e-3, atol=1e-3)
+    if res:
+        _close(r.grad, rr.grad, rtol=2e-2, atol=2e-2)
+
+
+def test_gap():
+    from flpr_b200.ops.fused import global_avg_pool_nhwc
+    x = torch.randn(16, 128, 2048, device="cuda").bfloat16().requires_grad_(True)
+    y = global_avg_pool_nhwc(x)
+    y.backward(torch.ones_like(y))
+    _close(y, x.float().mean(1), rtol=1e-3, atol=1e-3)
+    _close(x.grad, torch.full_like(x, 1 / 128.0).float(), rtol=1e-2, atol=1e-4)
+
+
+def test_rank_eval():
+    from flpr_b200.ops.rank import rank_metrics, rank_metrics_reference, similarity
+    torch.manual_seed(8)
+    q = torch.nn.functional.normalize(torch.randn(300, 2048, device="cuda"), dim=1)
+    g = torch.nn.functional.normalize(torch.randn(1500, 2048, device="cuda"), dim=1)
+    ql = torch.randint(0, 60, (300,))
+    gl = torch.randint(0, 70, (1500,))
+    sim = similarity(q, g, precise=True)
+    _close(sim, q @ g.t(), rtol=1e-4, atol=2e-5)
+    cmc, m_ap = rank_metrics(sim, ql, gl)
+    cmc_r, map_r = rank_metrics_reference(sim.cpu(), ql, gl)
+    assert abs(m_ap - map_r) < 1e-5
+    assert abs(cmc - cmc_r).max() < 1e-9
+
+
+def test_comm_single_rank():
+    """world_size == 1: the peer kernels degenerate to local HBM traffic but run the same code."""
+    from flpr_b200.parallel.comm import FedComm
+    K, n = 8, 4096 * 5
+    comm = FedComm("cuda", K, arena_bytes=64 << 20)
+    comm.alloc_client_buffer("up", n)
+    comm.alloc_client_buffer("cnt", 4)
+    comm.alloc_client_buffer("fisher", n)
+    comm.alloc_rank_buffer("glob", n)
+    for nm in ("f", "fp", "fpp"):
+        comm.alloc_rank_buffer(nm, n)
+    ups, cnts, fis = [], [], []
+    for c in range(K):
+        u = torch.randn(n, device="cuda")
+        comm.client_view("up", c).copy_(u)
+        comm.client_view("cnt", c).fill_(float(10 + c))
+        f = torch.rand(n, device="cuda")
+        comm.client_view("fisher", c).copy_(f)
+        ups.append(u); cnts.append(10.0 + c); fis.append(f)
+    U = torch.stack(ups)
+    w = torch.tensor(cnts, device="cuda"); w = w / w.sum()
+    comm.reduce_bcast("up", "glob", list(range(K)), cnt="cnt")
+    _close(comm.rank_view("glob"), (w[:, None] * U).sum(0), rtol=1e-5, atol=1e-5)
+    rows = torch.softmax(torch.randn(K, K), dim=1)
+    outs_g = [torch.empty(n, device="cuda") for _ in range(K)]
+    outs_t = [torch.empty(n, device="cuda") for _ in range(K)]
+    outs_b = [torch.empty(n, device="cuda", dtype=torch.bfloat16) for _ in range(K)]
+    comm.mix("up", list(range(K)), rows, list(range(K)), outs_g, outs_t, outs_b)
+    ref = rows.cuda() @ U
+    for i in range(K):
+        _close(outs_g[i], ref[i], rtol=1e-5, atol=1e-5)
+        _close(outs_t[i], ref[i], rtol=1e-5, atol=1e-5)
+        _close(outs_b[i], ref[i], rtol=1e-2, atol=2e-2)
+    comm.curv_moments("fisher", "up", list(range(K)), "f", "fp", "fpp")
+    Fs = torch.stack(fis)
+    _close(comm.rank_view("f"), Fs.sum(0), rtol=1e-5, atol=1e-5)
+    _close(comm.rank_view("fp"), (Fs * U).sum(0), rtol=1e-5, atol=1e-4)
+    _close(comm.rank_view("fpp"), (Fs * U * U).sum(0), rtol=1e-5, atol=1e-4)
+    out = torch.empty(n, K, device="cuda")
+    comm.gather_strided("up", list(range(K)), out)
+    _close(out, U.t(), rtol=0, atol=0)
+    d = torch.empty(n, device="cuda"); db = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    comm.pull("up", 3, d, db)
+    _close(d, U[3], rtol=0, atol=0)
+    comm.barrier()
+    torch.cuda.synchronize()
+    comm.check_errors()
+    comm.close()
