@@ -261,10 +261,8 @@ class FastResNetHead:
 
     def __call__(self, fmap: torch.Tensor):
         m = self.m
-        # accept NCHW-logical (channels_last) or NHWC-physical input
-        x = fmap.permute(0, 2, 3, 1) if fmap.shape[1] != fmap.shape[-1] or fmap.dim() == 4 and \
-            fmap.stride(1) == 1 else fmap
-        x = x.contiguous().to(torch.bfloat16)
+        # fmap is logical NCHW (any memory format); channels_last storage makes this permute a free view
+        x = fmap.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
         for i in range(max(m.head_start, 1), 5):
             for u in getattr(m.base, f"layer{i}"):
                 x = self._unit(x, u)
