@@ -156,7 +156,8 @@ struct MixArgs {
   int K;                            // all clients
   int L;                            // local (receiving) clients on this rank
   const float* src[MAX_CLIENTS];    // theta uploads
-  float w[MAX_LOCAL][MAX_CLIENTS];  // mixing rows for the local clients
+  float w[MAX_LOCAL][MAX_CLIENTS];  // mixing rows for the local clients (host-provided)
+  const float* w_dev;               // optional device-resident rows [L*K]: no host sync to launch the mix
   float* dst_g[MAX_LOCAL];          // global_weight of local client i          (nullable)
   float* dst_theta[MAX_LOCAL];      // theta master of local client i           (nullable)
   __nv_bfloat16* dst_bf16[MAX_LOCAL];  // bf16 compute copy of theta            (nullable)
@@ -164,7 +165,7 @@ struct MixArgs {
 };
 
 template <int L>
-__device__ __forceinline__ void mix_body(const MixArgs& a) {
+__device__ __forceinline__ void mix_body(const MixArgs& a, const float (*sw)[MAX_CLIENTS]) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += stride) {
     float4 acc[L];
@@ -180,7 +181,7 @@ __device__ __forceinline__ void mix_body(const MixArgs& a) {
       for (int c = 0; c < 8; ++c)
         if (c0 + c < a.K) {
 #pragma unroll
-          for (int l = 0; l < L; ++l) acc[l] = f4_fma(a.w[l][c0 + c], v[c], acc[l]);
+          for (int l = 0; l < L; ++l) acc[l] = f4_fma(sw[l][c0 + c], v[c], acc[l]);
         }
     }
 #pragma unroll
@@ -193,18 +194,24 @@ __device__ __forceinline__ void mix_body(const MixArgs& a) {
 }
 
 __global__ void __launch_bounds__(COMM_THREADS) fed_mix_kernel(const CommCtx ctx, const MixArgs a) {
+  __shared__ float sw[MAX_LOCAL][MAX_CLIENTS];
   const uint32_t e0 = block_epoch_begin(ctx);
   rank_barrier(ctx, e0 + 1);
+  for (int i = threadIdx.x; i < a.L * a.K; i += blockDim.x) {
+    const int l = i / a.K, c = i - l * a.K;
+    sw[l][c] = a.w_dev ? a.w_dev[i] : a.w[l][c];
+  }
+  __syncthreads();
   switch (a.L) {
     case 0: break;  // rank hosts no receiving client this round: barriers only
-    case 1: mix_body<1>(a); break;
-    case 2: mix_body<2>(a); break;
-    case 3: mix_body<3>(a); break;
-    case 4: mix_body<4>(a); break;
-    case 5: mix_body<5>(a); break;
-    case 6: mix_body<6>(a); break;
-    case 7: mix_body<7>(a); break;
-    default: mix_body<8>(a); break;
+    case 1: mix_body<1>(a, sw); break;
+    case 2: mix_body<2>(a, sw); break;
+    case 3: mix_body<3>(a, sw); break;
+    case 4: mix_body<4>(a, sw); break;
+    case 5: mix_body<5>(a, sw); break;
+    case 6: mix_body<6>(a, sw); break;
+    case 7: mix_body<7>(a, sw); break;
+    default: mix_body<8>(a, sw); break;
   }
   rank_barrier(ctx, e0 + 2);  // nobody may overwrite an upload buffer while a peer is still reading it
   block_epoch_end(ctx, e0 + 2);
@@ -435,7 +442,8 @@ int flpr_comm_reduce_bcast(int rank, int world, void* const* flag_pages, double 
 }
 
 int flpr_comm_mix(int rank, int world, void* const* flag_pages, double timeout_s, int K, int L,
-                  const float* const* src, const float* w_rows /* [L*K] */, float* const* dst_g,
+                  const float* const* src, const float* w_rows /* host [L*K] or null */,
+                  const float* w_dev /* device [L*K] or null */, float* const* dst_g,
                   float* const* dst_theta, void* const* dst_bf16, size_t n, int nblocks, cudaStream_t st) {
   if (K > MAX_CLIENTS || L > MAX_LOCAL || L < 0 || world > MAX_RANKS) return -1;
   if (n % 4) return -2;
@@ -446,11 +454,12 @@ int flpr_comm_mix(int rank, int world, void* const* flag_pages, double timeout_s
   a.L = L;
   for (int i = 0; i < K; ++i) a.src[i] = src[i];
   for (int l = 0; l < L; ++l) {
-    for (int i = 0; i < K; ++i) a.w[l][i] = w_rows[l * K + i];
+    for (int i = 0; i < K; ++i) a.w[l][i] = w_rows ? w_rows[l * K + i] : 0.f;
     a.dst_g[l] = dst_g ? dst_g[l] : nullptr;
     a.dst_theta[l] = dst_theta ? dst_theta[l] : nullptr;
     a.dst_bf16[l] = dst_bf16 ? reinterpret_cast<__nv_bfloat16*>(dst_bf16[l]) : nullptr;
   }
+  a.w_dev = w_dev;
   a.n4 = n / 4;
   fed_mix_kernel<<<clamp_blocks(nblocks), COMM_THREADS, 0, st>>>(c, a);
   return (int)cudaGetLastError();

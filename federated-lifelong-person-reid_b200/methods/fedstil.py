@@ -1,0 +1,484 @@
+"""``fedstil`` – Federated Spatial-Temporal Incremental Learning, the headline method
+(reference ``methods/fedstil.py``).
+
+Reference algorithm -> this implementation
+------------------------------------------
+* *Adaptive layers* ``theta = atten (.) G + A`` with ``G`` and ``atten`` frozen, ``A`` trained
+  (``fedstil.py:24-129``). ``atten`` is never trained and is always re-initialised to ``atten_default``, so it is a
+  scalar ``a``; and ``init_training_weights`` sets ``A0 = (1-a) G`` so the initial ``theta`` equals ``G``. Training
+  ``A`` with gradient ``g_theta`` is therefore *identical* to training ``theta`` directly, with
+  ``A = theta - a G`` (weight decay) and ``A - A0 = theta - G`` (L1 sparseness). We keep ONE fp32 master ``theta``
+  per adaptive layer and fold weight decay on ``A``, ``lambda_l1 * sign(theta - G)`` and the bf16 refresh into the
+  fused optimizer kernel: the per-step compose pass and the 6-11-layer Python L1 loop (``fedstil.py:639-644``)
+  disappear. The reference's accidental training of its ``initial_*`` copies is not reproduced.
+* *Head discovery by torch.fx* (``fedstil.py:258-288``) -> static trunk / head split of the backbone.
+* *Prototype pass* (``fedstil.py:558-617``): eval-mode frozen trunk over the task's train loader; the feature maps
+  at the cut stay on the device (NHWC bf16) instead of bouncing through numpy; ``task_token`` = mean prototype.
+* *Prototype rehearsal* (``fedstil.py:349-399``): herding runs on the device; an exemplar set is an ordered index
+  list into a bank of unique prototypes (the reference stores ``m`` physical copies).
+* *Server* (``fedstil.py:1047-1172``): FedAvg mean into the server model (``calculate``) and the
+  similarity-weighted per-client mix ``out_i = sum_j W_ij theta_j`` (``get_dispatch_incremental_state``) run as
+  peer-memory kernels (``FedComm.reduce_bcast`` / ``FedComm.mix``); the mix writes ``global_weight``, the ``theta``
+  master and its bf16 copy of the receiving client in the same pass (= ``init_training_weights``).
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..criterions import kl_distance
+from ..runtime.modules import ClientModule, ModelModule, OperatorModule, ServerModule, _bind_loader
+
+
+class Model(ModelModule):
+    adaptive_types = (nn.Linear, nn.Conv2d)
+
+    def __init__(self, net, lambda_l1: float = 1e-4, lambda_k: int = 8000, atten_default: float = 0.80, **kwargs):
+        super().__init__(net, **kwargs)
+        self.atten_default = float(atten_default)
+        self.lambda_l1 = float(lambda_l1)
+        self.lambda_k = int(lambda_k)
+        self.adaptive_names: List[str] = self._find_adaptive_layers()
+        self._theta_params = {f"{n}.weight" for n in self.adaptive_names}
+        self.ids: set = set()
+        # exemplar memory: pid -> {"bank": tensor [u, ...] prototypes, "cls": tensor [u], "order": list[int]}
+        self.examplars: Dict[int, Dict[str, Any]] = {}
+        self.G: Optional[torch.Tensor] = None
+
+    # ---- adaptive layers: leaves of type Linear/Conv2d whose parameters are all trainable (fedstil.py:290-347) ------
+    def _find_adaptive_layers(self) -> List[str]:
+        names = []
+        for name, mod in self.net.named_modules():
+            if type(mod) in self.adaptive_types and len(list(mod.children())) == 0:
+                ps = list(mod.parameters())
+                if ps and all(p.requires_grad for p in ps):
+                    names.append(name)
+        return names
+
+    def upload_filter(self, name: str) -> bool:
+        return name in self._theta_params
+
+    def materialize(self, device, compute_dtype="bf16", fine_tuning=None):
+        super().materialize(device, compute_dtype, fine_tuning)
+        self.G = self.arena.master[:self.theta_numel].clone()       # global_weight (frozen between dispatches)
+        return self
+
+    @property
+    def theta_numel(self) -> int:
+        return self.arena.prefix_numel
+
+    def install(self, optimizer) -> None:
+        optimizer.G, optimizer.lam1, optimizer.atten = self.G, self.lambda_l1, self.atten_default
+        if optimizer.stats is None:
+            optimizer.stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+
+    def set_global_weight(self, flat: torch.Tensor) -> None:
+        """New ``global_weight`` + ``init_training_weights()``: theta <- G (A = (1-a) G), bf16 copy refreshed."""
+        n = self.theta_numel
+        self.G.copy_(flat[:n])
+        self.arena.master[:n].copy_(self.G)
+        self.arena.refresh_shadow()
+
+    @property
+    def m(self) -> int:
+        return math.ceil(self.lambda_k / max(len(self.ids), 1))
+
+    # ---- reference checkpoint schema (fedstil.py:444-491) ------------------------------------------------------------
+    def model_state(self) -> Dict:
+        a = self.arena
+        gw, gwa, aw, ab = {}, {}, {}, {}
+        for lname in self.adaptive_names:
+            theta = a.view(a.master, f"{lname}.weight").detach()
+            g = a.view(self.G, f"{lname}.weight").detach()
+            gw[f"{lname}.global_weight"] = g.clone(memory_format=torch.contiguous_format)
+            gwa[f"{lname}.global_weight_atten"] = torch.full((theta.shape[-1],), self.atten_default,
+                                                             device=theta.device)
+            aw[f"{lname}.adaptive_weight"] = (theta - self.atten_default * g).clone(
+                memory_format=torch.contiguous_format)
+            bias = getattr(self.net.get_submodule(lname), "bias", None)
+            if bias is not None:
+                ab[f"{lname}.adaptive_bias"] = bias.detach().clone()
+        skip = {f"{n}.weight" for n in self.adaptive_names} | {f"{n}.bias" for n in self.adaptive_names}
+        pre = {k: v.detach().clone(memory_format=torch.contiguous_format) for k, v in self.net.state_dict().items()
+               if k not in skip}
+        return {"global_weight": gw, "global_weight_atten": gwa, "adaptive_weights": aw, "adaptive_bias": ab,
+                "bn_params": {}, "pre_trained_params": pre}
+
+    def update_model(self, params_state: Dict) -> None:
+        a = self.arena
+        with torch.no_grad():
+            gw = params_state.get("global_weight") or {}
+            aw = params_state.get("adaptive_weights") or {}
+            for key, g in gw.items():
+                lname = key[: -len(".global_weight")]
+                pname = f"{lname}.weight"
+                if pname in a.segments:
+                    a.from_dict({pname: g}, self.G)
+                    if f"{lname}.adaptive_weight" not in aw:
+                        a.from_dict({pname: g}, a.master)              # theta = G until told otherwise
+            for key, w in aw.items():
+                lname = key[: -len(".adaptive_weight")]
+                pname = f"{lname}.weight"
+                if pname in a.segments:
+                    g = a.view(self.G, pname)
+                    a.view(a.master, pname).copy_(self.atten_default * g + w.to(g.device))
+            for key, b in (params_state.get("adaptive_bias") or {}).items():
+                lname = key[: -len(".adaptive_bias")]
+                mod = self.net.get_submodule(lname)
+                if mod.bias is not None:
+                    mod.bias.copy_(b.to(mod.bias.device))
+            pre = params_state.get("pre_trained_params") or {}
+            if pre:
+                own = self.net.state_dict()
+                for k, v in pre.items():
+                    if k in own:
+                        own[k].copy_(v.to(own[k].device))
+        a.refresh_shadow()
+
+    # ---- prototypes ------------------------------------------------------------------------------------------------
+    def forward_trunk(self, data: torch.Tensor) -> torch.Tensor:
+        return self.net.forward_trunk(data)
+
+    def forward_head(self, protos: torch.Tensor):
+        return self.net.forward_head(protos)
+
+    # ---- exemplar memory (fedstil.py:349-399) -----------------------------------------------------------------------
+    def reduce_examplars(self) -> None:
+        m = self.m
+        for pid in self.examplars:
+            self.examplars[pid]["order"] = self.examplars[pid]["order"][:m]
+
+    @torch.no_grad()
+    def build_examplars(self, protos: torch.Tensor, pids: torch.Tensor, classes: torch.Tensor,
+                        person_ids: Sequence[int], batch_size: int = 256) -> None:
+        """Herding on ``forward_head`` features of the epoch's prototype set (exemplars + current task)."""
+        self.eval()
+        feats = []
+        for s in range(0, protos.shape[0], batch_size):
+            with self.autocast():
+                feats.append(self.forward_head(protos[s:s + batch_size]).float())
+        feats = torch.cat(feats) if feats else torch.zeros(0, 1, device=protos.device)
+        keep = set(int(p) for p in person_ids)
+        m = self.m
+        for pid in torch.unique(pids).tolist():
+            if keep and pid not in keep:
+                continue
+            idx = torch.nonzero(pids == pid).squeeze(1)
+            order = herding_select(feats[idx], m)
+            uniq, inverse = torch.unique(torch.tensor(order), return_inverse=True)
+            self.examplars[int(pid)] = {"bank": protos[idx[uniq.to(idx.device)]].clone(),
+                                        "cls": classes[idx[uniq.to(idx.device)]].clone(),
+                                        "order": inverse.tolist()}
+
+    def examplar_tensors(self) -> Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+        """Expanded rehearsal set ``(protos, person_ids, class_ids)`` (duplicates included, like the reference)."""
+        ps, ids, cs = [], [], []
+        for pid, ex in self.examplars.items():
+            if not ex["order"]:
+                continue
+            o = torch.tensor(ex["order"], device=ex["bank"].device)
+            ps.append(ex["bank"][o])
+            cs.append(ex["cls"][o])
+            ids.append(torch.full((len(ex["order"]),), pid, dtype=torch.long, device=ex["bank"].device))
+        if not ps:
+            return None
+        return torch.cat(ps), torch.cat(ids), torch.cat(cs)
+
+    def examplars_state(self, max_bytes: int = 256 << 20) -> Dict:
+        """``{np.int64 pid: [(ndarray proto, class_id), ...]}`` (``fedstil.py:841,846``) when small enough."""
+        total = sum(len(ex["order"]) * ex["bank"][0].numel() * 4 for ex in self.examplars.values() if len(ex["bank"]))
+        if total > max_bytes:
+            return {"_compact": {int(p): {"bank": ex["bank"].cpu(), "cls": ex["cls"].cpu(), "order": ex["order"]}
+                                 for p, ex in self.examplars.items()}}
+        out = {}
+        for pid, ex in self.examplars.items():
+            bank = ex["bank"].float().cpu().numpy()
+            cls = ex["cls"].cpu().tolist()
+            out[np.int64(pid)] = [(bank[i], int(cls[i])) for i in ex["order"]]
+        return out
+
+
+def herding_select(feats: torch.Tensor, m: int) -> List[int]:
+    """iCaRL herding: at step t pick ``argmin_i || mean - (f_i + sum selected) / (t+1) ||`` (duplicates allowed).
+
+    ``argmin_i ||c - f_i||`` with ``c = (t+1) mean - S`` only needs ``||f_i||^2 - 2 f_i.c`` -> one mat-vec per step,
+    no Python loop over samples and no host round-trip per step (indices are collected on the device).
+    """
+    n = feats.shape[0]
+    if n == 0:
+        return []
+    f = feats.float()
+    mean = f.mean(0)
+    sq = (f * f).sum(1)
+    S = torch.zeros_like(mean)
+    picks = torch.empty(m, dtype=torch.long, device=f.device)
+    for t in range(m):
+        c = (t + 1) * mean - S
+        i = torch.argmin(sq - 2 * (f @ c))
+        picks[t] = i
+        S = S + f[i]
+    return picks.tolist()
+
+
+class Operator(OperatorModule):
+
+    @torch.no_grad()
+    def generate_prototypes(self, model: Model, source_loader) -> Dict[str, torch.Tensor]:
+        """Eval-mode trunk pass; returns this epoch's rehearsal+task prototype set and the task token."""
+        model.eval()
+        protos, pids, cids = [], [], []
+        for data, person_id, classes_id in source_loader:
+            data = model.prepare_input(data)
+            with model.autocast():
+                fmap = model.forward_trunk(data)
+            if model.compute_dtype == torch.bfloat16:
+                fmap = fmap.to(torch.bfloat16)
+            protos.append(fmap)
+            pids.append(person_id.to(model.device))
+            cids.append(classes_id.to(model.device))
+        protos, pids, cids = torch.cat(protos), torch.cat(pids), torch.cat(cids)
+        task_token = protos.float().flatten(1).mean(0)
+        ex = model.examplar_tensors()
+        if ex is not None:                                   # ConcatDataset([exemplars, current]) (fedstil.py:590-593)
+            protos = torch.cat([ex[0].to(protos.dtype), protos])
+            pids = torch.cat([ex[1], pids])
+            cids = torch.cat([ex[2], cids])
+        return {"protos": protos, "pids": pids, "cids": cids, "task_token": task_token}
+
+    def forward_train(self, model: Model, data: torch.Tensor):
+        with model.autocast():
+            return model.forward_head(data)
+
+    def invoke_train(self, model: Model, dataloader, **kwargs) -> Dict:
+        device = model.device
+        pset = self.generate_prototypes(model, dataloader)
+        protos, pids = pset["protos"], pset["pids"]
+        n = protos.shape[0]
+        bs = dataloader.batch_size
+        model.train()
+        model.install(self.optimizer)
+        self.optimizer.stats.zero_()
+        acc = torch.zeros(2, dtype=torch.float64, device=device)
+        perm = torch.randperm(n, device=device)
+        n_batches = n // bs if (n % bs == 1) else (n + bs - 1) // bs     # drop_last iff remainder == 1
+        data_cnt = 0
+        for b in range(n_batches):
+            idx = perm[b * bs:(b + 1) * bs]
+            data, target = protos[idx], pids[idx]
+            self.optimizer.zero_grad()
+            out = self._invoke_train(model, data, target, **kwargs)
+            out["loss"].backward()
+            self.optimizer.step()
+            with torch.no_grad():
+                acc[0] += out["loss"].detach().double()
+                acc[1] += (out["score"].argmax(dim=1) == target).sum()
+            data_cnt += len(idx)
+        vals = torch.cat([acc, self.optimizer.stats.double()]).tolist()     # single host sync per epoch
+        loss_sum, hits, _, l1_sum = vals
+        train_loss = (loss_sum + model.lambda_l1 * l1_sum) / max(n_batches, 1)
+        if self.scheduler:
+            self.scheduler.step()
+        return {"task_token": pset["task_token"], "proto_set": pset, "accuracy": hits / max(data_cnt, 1),
+                "loss": train_loss, "batch_count": n_batches, "data_count": data_cnt}
+
+
+class Client(ClientModule):
+    default_ckpt_name = None
+
+    def __init__(self, client_name, model, operator, ckpt_root, model_ckpt_name=None, **kwargs):
+        super().__init__(client_name, model, operator, ckpt_root, model_ckpt_name, **kwargs)
+        self.current_task = None
+        self.task_token: Optional[torch.Tensor] = None
+        self._task_tokens: List[torch.Tensor] = []
+
+    # ---- symmetric buffers ---------------------------------------------------------------------------------------------
+    @classmethod
+    def declare_buffers(cls, comm, model, token_numel: int = 0) -> None:
+        n = model.theta_numel
+        comm.alloc_client_buffer("theta_up", n)
+        comm.alloc_client_buffer("cnt", 4)
+        comm.alloc_rank_buffer("glob", n)
+        if token_numel:
+            comm.alloc_client_buffer("token", (token_numel + 3) // 4 * 4)
+
+    def _named_theta(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        a = self.model.arena
+        return {f"{l}.global_weight": a.view(flat, f"{l}.weight") for l in self.model.adaptive_names}
+
+    # ---- checkpoints -----------------------------------------------------------------------------------------------------
+    def save_model(self, model_name: str) -> None:
+        self.save_state(model_name, self.model.model_state(), True)
+        self.save_state(f"{model_name}_examplars", self.model.examplars_state(), True)
+
+    # ---- protocol ----------------------------------------------------------------------------------------------------------
+    def get_incremental_state(self, **kwargs) -> Dict:
+        n = self.model.theta_numel
+        slot = self.comm.client_view("theta_up", self.client_id)
+        slot.copy_(self.model.arena.master[:n])               # theta = a*G + A  (fedstil.py:851-854)
+        self.comm.client_view("cnt", self.client_id).fill_(float(self.train_cnt))
+        if self.task_token is not None and "token" in self.comm.bufs:
+            tok = self.comm.client_view("token", self.client_id)
+            tok.zero_()
+            tok[:self.task_token.numel()].copy_(self.task_token)
+        return {"train_cnt": self.train_cnt, "task_token": self.task_token,
+                "incremental_sw": self._named_theta(slot), "incremental_bn": {}}
+
+    def get_integrated_state(self, **kwargs) -> Dict:
+        st = self.get_incremental_state()
+        ms = self.model.model_state()
+        return {"train_cnt": st["train_cnt"], "task_token": st["task_token"], "integrated_sw": st["incremental_sw"],
+                "integrated_bn": {}, "pre_trained_params": ms["pre_trained_params"]}
+
+    def update_by_incremental_state(self, state: Dict, **kwargs) -> Any:
+        if state.get("_delivered"):
+            pass                                                # the mix kernel already wrote G / theta / bf16 copy
+        else:
+            self.model.update_model({"global_weight": state["incremental_shared_params"]})
+            self.model.set_global_weight(self.model.G)
+        self.logger.info("Update model succeed by incremental state from server.")
+
+    def update_by_integrated_state(self, state: Dict, **kwargs) -> Any:
+        self.model.update_model({"global_weight": state["integrated_global_weight"],
+                                 "pre_trained_params": state["integrated_pre_trained_params"]})
+        self.model.set_global_weight(self.model.G)
+        self.logger.info("Update model succeed by integrated state from server.")
+
+    # ---- training ----------------------------------------------------------------------------------------------------------
+    def ckpt_name(self, task_name: str) -> str:
+        return self.model_ckpt_name if self.model_ckpt_name else (self.current_task or task_name)
+
+    def before_train(self, task_name, tr_loader, val_loader) -> None:
+        if self.current_task is None or self.current_task != task_name:
+            self.model.ids.update(int(p) for p in tr_loader.dataset.person_ids)
+        self.current_task = task_name
+        self._task_tokens = []
+
+    def after_epoch(self, output: Dict) -> None:
+        self._task_tokens.append(output["task_token"])
+        self.train_cnt += output["data_count"]                 # never reset
+
+    def after_train(self, task_name, tr_loader, val_loader, output) -> None:
+        self.model.reduce_examplars()
+        ps = output.get("proto_set")
+        if ps is not None:
+            self.model.build_examplars(ps["protos"], ps["pids"], ps["cids"], tr_loader.dataset.person_ids)
+            output.pop("proto_set", None)
+        if self._task_tokens:
+            self.task_token = torch.stack(self._task_tokens).mean(0)
+
+
+class Server(ServerModule):
+    def __init__(self, server_name, model, operator, ckpt_root, distance_calculate_step: int = 10,
+                 distance_calculate_decay: float = 0.8, **kwargs):
+        super().__init__(server_name, model, operator, ckpt_root, **kwargs)
+        self.token_memory: Dict[str, List[torch.Tensor]] = {}
+        self.distance_calculate_step = int(distance_calculate_step)
+        self.distance_calculate_decay = float(distance_calculate_decay)
+        self.client_ids: Dict[str, int] = {}
+        self.local_clients: Dict[str, Client] = {}
+        self.uploaded: List[int] = []
+        self._round_uploads: List[str] = []
+        self._delivered: Dict[str, bool] = {}
+
+    def bind_client(self, client_name: str, client_id: int, client: Optional[Client] = None) -> None:
+        self.client_ids[client_name] = client_id
+        if client is not None:
+            self.local_clients[client_name] = client
+
+    def save_model(self, model_name: str) -> None:
+        self.save_state(model_name, self.model.model_state(), True)
+
+    # ---- uploads -----------------------------------------------------------------------------------------------------------
+    def set_client_incremental_state(self, client_name: str, client_state: Optional[Dict]) -> None:
+        if client_name not in self.clients:
+            self.logger.warn(f"Collect incremental state failed from unregistered client {client_name}.")
+            return
+        self.clients[client_name] = client_state if client_state is not None else {"remote": True}
+        cid = self.client_ids[client_name]
+        if cid not in self.uploaded:
+            self.uploaded.append(cid)
+        self._round_uploads.append(client_name)
+        self.logger.info(f"Collect incremental state successfully from client {client_name}.")
+
+    set_client_integrated_state = set_client_incremental_state
+
+    def calculate(self) -> Any:
+        """FedAvg mean of theta into the server model + token exchange (``fedstil.py:1075-1096``)."""
+        if self.uploaded:
+            self.comm.reduce_bcast("theta_up", "glob", self.uploaded, cnt="cnt")
+            self.model.set_global_weight(self.comm.rank_view("glob"))
+        if self._round_uploads and "token" in self.comm.bufs:
+            ids = [self.client_ids[n] for n in self._round_uploads]
+            d = self.comm.bufs["token"].n
+            out = torch.empty(d, len(ids), device=self.model.device)
+            self.comm.gather_strided("token", ids, out)         # tokens of this round's uploads, on every rank
+            toks = out.t().contiguous()
+            for i, name in enumerate(self._round_uploads):
+                self.token_memory.setdefault(name, []).append(toks[i])
+        self._round_uploads = []
+        self.save_state(f"{self.server_name}_tokens", self.token_memory, True)
+
+    # ---- spatial-temporal integration (fedstil.py:1118-1164) ----------------------------------------------------------------
+    def relevance_row(self, client_name: str) -> Tuple[List[str], torch.Tensor]:
+        """Mixing weights of ``client_name`` over ``select_client`` (others in memory order, then itself)."""
+        own = self.token_memory[client_name][-1].unsqueeze(0)
+        select, rel = [], []
+        for c_name, c_tokens in self.token_memory.items():
+            if c_name == client_name:
+                continue
+            hist = c_tokens[::-1 * self.distance_calculate_step]
+            dis = own.new_full((), 1e-8)
+            for decay_cnt, other in enumerate(hist):
+                dis = dis + kl_distance(own, other.unsqueeze(0)) / math.pow(self.distance_calculate_decay, decay_cnt)
+            select.append(c_name)
+            rel.append(1.0 / dis)
+        if not rel:
+            return [client_name], own.new_ones(1)
+        rel = torch.stack(rel)
+        rel = torch.cat([rel, rel.mean().view(1)])
+        select.append(client_name)
+        rel = rel / rel.sum()
+        return select, torch.softmax(rel, dim=0)
+
+    def prepare_dispatch(self, online_names: Sequence[str], first_contact: Sequence[str]) -> None:
+        """Collective: every rank mixes for its local, already-registered online clients in ONE kernel."""
+        self._delivered = {}
+        if not self.uploaded:
+            return
+        recv = [n for n in online_names if n not in first_contact and n in self.local_clients
+                and n in self.token_memory]
+        K = len(self.uploaded)
+        col = {cid: j for j, cid in enumerate(self.uploaded)}
+        dev = self.model.device
+        rows = torch.zeros(len(recv), K, device=dev)
+        for i, name in enumerate(recv):
+            select, w = self.relevance_row(name)
+            for c_name, wv in zip(select, w):
+                self.logger.info(f"Relevant ratio between {name} and {c_name}: {float(wv):.4f}")
+            cols = torch.tensor([col[self.client_ids[c]] for c in select], device=dev)
+            rows[i, cols] = w.to(dev)
+        models = [self.local_clients[n].model for n in recv]
+        n_theta = self.model.theta_numel
+        self.comm.mix("theta_up", self.uploaded, rows, list(range(len(recv))),
+                      dst_g=[m.G for m in models],
+                      dst_theta=[m.arena.master[:n_theta] for m in models],
+                      dst_bf16=[m.arena.shadow[:n_theta] for m in models] if models and models[0].arena.shadow
+                      is not None else None)
+        for n in recv:
+            self._delivered[n] = True
+
+    def get_dispatch_incremental_state(self, client_name: str) -> Optional[Dict]:
+        if client_name not in self.local_clients or not self._delivered.get(client_name):
+            return None
+        cl = self.local_clients[client_name]
+        return {"incremental_shared_params": cl._named_theta(cl.model.G), "_delivered": True}
+
+    def get_dispatch_integrated_state(self, client_name: str) -> Dict:
+        ms = self.model.model_state()
+        return {"integrated_global_weight": ms["global_weight"], "integrated_bn_params": ms["bn_params"],
+                "integrated_pre_trained_params": ms["pre_trained_params"]}

@@ -47,7 +47,7 @@ def _declare(lib: C.CDLL) -> None:
         "flpr_comm_read_error": [P, C.POINTER(I)],
         "flpr_comm_barrier": [I, I, P, D, P],
         "flpr_comm_reduce_bcast": [I, I, P, D, I, P, P, P, P, Z, I, P],
-        "flpr_comm_mix": [I, I, P, D, I, I, P, P, P, P, P, Z, I, P],
+        "flpr_comm_mix": [I, I, P, D, I, I, P, P, P, P, P, P, Z, I, P],
         "flpr_comm_curv_moments": [I, I, P, D, I, P, P, P, P, P, Z, I, P],
         "flpr_comm_gather_strided": [I, I, P, D, I, P, P, Z, I, P],
         "flpr_comm_pull_copy": [I, I, P, D, P, P, P, Z, I, P],

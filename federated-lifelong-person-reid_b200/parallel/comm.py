@@ -248,16 +248,21 @@ class FedComm:
             if self.world > 1:
                 self._gather_clients(src, clients)  # keep the collective sequence aligned
             return
-        rows_h = rows.detach().float().cpu().contiguous()
         if self.mode == "p2p":
+            rows_dev = rows.detach().float().contiguous() if rows.is_cuda else None
+            rows_h = None if rows_dev is not None else rows.detach().float().cpu().contiguous()
             max_l = self._lib.flpr_comm_max_local()
             srcp = self._client_ptrs(src, clients)
             # every rank issues the same number of launches (the kernels barrier across ranks)
             n_launch = (self.slots + max_l - 1) // max_l
             for it in range(n_launch):
                 idx = list(range(it * max_l, min((it + 1) * max_l, L)))
-                wv = (C.c_float * max(len(idx) * len(clients), 1))(*rows_h[idx].reshape(-1).tolist()) if idx else \
-                    (C.c_float * 1)(0.0)
+                wv, wd = None, None
+                if idx and rows_dev is not None:
+                    wd = rows_dev[idx[0]:idx[-1] + 1]
+                    self._keep = [wd]
+                elif idx:
+                    wv = (C.c_float * (len(idx) * len(clients)))(*rows_h[idx].reshape(-1).tolist())
 
                 def arr(lst):
                     if lst is None or not idx:
@@ -265,7 +270,8 @@ class FedComm:
                     return (C.c_void_p * len(idx))(*[C.c_void_p(lst[i].data_ptr()) for i in idx])
 
                 rc = self._lib.flpr_comm_mix(self.rank, self.world, self._flag_pages, self.timeout_s, len(clients),
-                                             len(idx), srcp, wv, arr(dst_g), arr(dst_theta), arr(dst_bf16), bs.n,
+                                             len(idx), srcp, wv, native.ptr(wd), arr(dst_g), arr(dst_theta),
+                                             arr(dst_bf16), bs.n,
                                              self.comm_blocks, native.stream(self.device))
                 native.check(rc, "flpr_comm_mix")
                 native.count_launch()
@@ -273,7 +279,7 @@ class FedComm:
                     self.bytes_moved += int(bs.n * 4 * self._remote(clients))
             return
         stack = self._gather_clients(src, clients).float()
-        out = rows_h.to(stack.device) @ stack
+        out = rows.detach().float().to(stack.device) @ stack
         for i in range(L):
             if dst_g is not None:
                 dst_g[i].view(-1).copy_(out[i])

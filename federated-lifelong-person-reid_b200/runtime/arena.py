@@ -170,11 +170,23 @@ class ArenaOptimizer:
             self.v = a.new_buffer()
         self.step_count += 1
         d = self.defaults
-        fops.fused_optimizer_step(self.kind, a.master, a.grad, self.m, self.v, lr=self.lr, step=self.step_count,
-                                  beta1=d["betas"][0], beta2=d["betas"][1], eps=d["eps"],
-                                  weight_decay=d["weight_decay"], momentum=d["momentum"], Q=self.Q, R=self.R,
-                                  lam2=self.lam2, penalty_ones=self.penalty_ones, G=self.G, lam1=self.lam1,
-                                  atten=self.atten, p_bf16=a.shadow, stats=self.stats)
+
+        def launch(lo: int, hi: int, with_g: bool) -> None:
+            sl = slice(lo, hi)
+            fops.fused_optimizer_step(
+                self.kind, a.master[sl], a.grad[sl], None if self.m is None else self.m[sl],
+                None if self.v is None else self.v[sl], lr=self.lr, step=self.step_count, beta1=d["betas"][0],
+                beta2=d["betas"][1], eps=d["eps"], weight_decay=d["weight_decay"], momentum=d["momentum"],
+                Q=None if self.Q is None else self.Q[sl], R=None if self.R is None else self.R[sl], lam2=self.lam2,
+                penalty_ones=self.penalty_ones, G=self.G[sl] if with_g else None, lam1=self.lam1, atten=self.atten,
+                p_bf16=None if a.shadow is None else a.shadow[sl], stats=self.stats)
+
+        n_g = self.G.numel() if self.G is not None else 0
+        if 0 < n_g < a.numel:          # FedSTIL: only the adaptive-weight prefix carries the L1 / attention terms
+            launch(0, n_g, True)
+            launch(n_g, a.numel, False)
+        else:
+            launch(0, a.numel, n_g > 0)
 
 
 class StepLR:

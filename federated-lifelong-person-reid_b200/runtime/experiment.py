@@ -1,0 +1,323 @@
+"""Experiment runtime (``experiment.py`` of the reference): ``ExperimentStage`` context manager + ``run()``,
+``VirtualContainer`` device-slot allocator, ``ExperimentLog`` (re-exported).
+
+Execution model: SPMD. One process per GPU (``torchrun``), clients round-robined over ranks, the *server* is a role
+replicated on every rank whose aggregation / dispatch are collectives of :class:`flpr_b200.parallel.comm.FedComm`.
+With a single process (``world_size == 1``) all clients live in this process, which is also the CPU plumbing mode.
+
+The communication round is the reference's (``experiment.py:183-243``): sample online clients -> dispatch (integrated
+on first contact, incremental afterwards) -> local training -> validation every ``val_interval`` rounds -> uploads ->
+``server.calculate()``; payload checkpoints ``{round}-{src}-{dst}.ckpt`` are written by a background thread.
+Every phase is timed on the device (CUDA events, max over ranks is taken by the caller) and recorded under
+``perf`` in the experiment log, together with the bytes moved by the collectives.
+"""
+from __future__ import annotations
+
+import os
+import random
+import threading
+from contextlib import contextmanager
+from datetime import datetime
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.distributed as dist
+
+from ..methods import methods
+from ..methods.fedbase import strip_private
+from ..parallel.comm import FedComm
+from ..utils.logger import Logger
+from ..utils.misc import DeviceTimer, clear_cache, same_seeds
+from .builder import parser_clients, parser_server
+from .checkpoint import CheckpointStore
+from .explog import ExperimentLog
+
+__all__ = ["ExperimentStage", "ExperimentLog", "VirtualContainer"]
+
+
+class VirtualContainer:
+    """Device-slot allocator (``experiment.py:58-99``): ``{device: parallel}`` slots, ``possess_device(count)``.
+
+    Race-free re-implementation: a condition variable guards the counters, a request larger than a device's capacity
+    is clamped (the reference lets counters go negative and may hand out ``device=None``)."""
+
+    def __init__(self, devices: Sequence[str], parallel: int = 1) -> None:
+        self._cv = threading.Condition()
+        self.capacity = {d: int(parallel) for d in devices}
+        self.devices = dict(self.capacity)
+
+    def max_worker(self) -> int:
+        return sum(self.capacity.values())
+
+    def acquire_device(self, count: int = 1) -> str:
+        with self._cv:
+            while True:
+                for dev, free in self.devices.items():
+                    need = min(count, self.capacity[dev])
+                    if free >= need:
+                        self.devices[dev] -= need
+                        return dev
+                self._cv.wait()
+
+    def release_device(self, device: str, count: int = 1) -> None:
+        with self._cv:
+            self.devices[device] = min(self.capacity[device], self.devices[device] + min(count, self.capacity[device]))
+            self._cv.notify_all()
+
+    @contextmanager
+    def possess_device(self, count: int = 1):
+        dev = self.acquire_device(count)
+        try:
+            yield dev
+        finally:
+            self.release_device(dev, count)
+
+
+def _dist_env() -> Tuple[int, int, int]:
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+class ExperimentStage:
+    def __init__(self, common_config: Dict, exp_configs: Union[Dict, Sequence[Dict]], source_factory=None):
+        self.common_config = common_config
+        self.exp_configs = [exp_configs] if isinstance(exp_configs, dict) else list(exp_configs)
+        self.rank, self.world, self.local_rank = _dist_env()
+        self.logger = Logger("stage", self.rank if self.world > 1 else None)
+        self.source_factory = source_factory
+        self.device = self._pick_device()
+        self.container = VirtualContainer([str(self.device)], self.common_config.get("parallel", 1))
+        self._owns_pg = False
+        self.last_perf: Dict[str, Any] = {}
+
+    # ------------------------------------------------------------------ environment
+    def _pick_device(self) -> torch.device:
+        devices = self.common_config.get("device", ["cpu"])
+        wants_cuda = any(str(d).startswith("cuda") for d in devices)
+        if wants_cuda and torch.cuda.is_available():
+            if self.world > 1:
+                return torch.device("cuda", self.local_rank % torch.cuda.device_count())
+            first = next(str(d) for d in devices if str(d).startswith("cuda"))
+            return torch.device(first if ":" in first else "cuda:0")
+        return torch.device("cpu")
+
+    def __enter__(self):
+        self.check_environment()
+        return self
+
+    def __exit__(self, exc_type, value, trace):
+        if self._owns_pg and dist.is_initialized():
+            dist.destroy_process_group()
+        if exc_type is not None and issubclass(exc_type, Exception):
+            self.logger.error(value)
+        return False                                   # re-raise the original exception (reference bug fixed)
+
+    def check_environment(self) -> None:
+        try:
+            torch.zeros(1).to(self.device)
+        except Exception as ex:  # pragma: no cover
+            self.logger.error(f"Not available for given device {self.device}:{ex}")
+            raise SystemExit(1)
+        if self.device.type == "cuda":
+            torch.cuda.set_device(self.device)
+        if self.world > 1 and not dist.is_initialized():
+            backend = "nccl" if self.device.type == "cuda" else "gloo"
+            kw = {"device_id": self.device} if backend == "nccl" else {}
+            dist.init_process_group(backend, **kw)
+            self._owns_pg = True
+        datasets_dir = self.common_config["datasets_dir"]
+        if self.source_factory is None and not os.path.exists(datasets_dir):
+            self.logger.error(f"Datasets base directory could not be found with {datasets_dir}.")
+            raise SystemExit(1)
+        if os.path.exists(self.common_config["checkpoints_dir"]):
+            self.logger.warn(f"Checkpoint directory {self.common_config['checkpoints_dir']} is not empty.")
+        self.logger.info("Experiment stage build success.")
+
+    # ------------------------------------------------------------------ one experiment
+    def build(self, exp_config: Dict):
+        """Construct comm, checkpoint store, server replica and the local clients for ``exp_config``."""
+        eng = exp_config["engine_opts"]
+        names = [c["client_name"] for c in exp_config["clients"]]
+        store = CheckpointStore(os.path.join(self.common_config["checkpoints_dir"], exp_config["exp_name"]),
+                                asynchronous=eng.get("async_checkpoint", True),
+                                enabled=eng.get("checkpoints", True))
+        server = parser_server(exp_config, self.common_config, self.device, store)
+        clients = parser_clients(exp_config, self.common_config, self.device, store, None, self.rank, self.world,
+                                 self.source_factory)
+        comm = None
+        client_cls = methods[exp_config["exp_method"]].Client
+        if hasattr(client_cls, "declare_buffers"):
+            need = self._arena_bytes(server, len(names), exp_config)
+            comm = FedComm(self.device, len(names), arena_bytes=need, mode=eng.get("comm_mode"),
+                           timeout_s=eng.get("comm_timeout_s", 60.0))
+            c_, h_, w_ = self._proto_shape(server, exp_config)
+            client_cls.declare_buffers(comm, server.model, c_ * h_ * w_)
+            for c in clients:
+                c.comm = comm
+            server.comm = comm
+        for cid, name in enumerate(names):
+            if hasattr(server, "bind_client"):
+                local = next((c for c in clients if c.client_name == name), None)
+                try:
+                    server.bind_client(name, cid, local)
+                except TypeError:
+                    server.bind_client(name, cid)
+        return store, comm, server, clients, names
+
+    def _proto_shape(self, server, exp_config) -> Tuple[int, int, int]:
+        net = server.model.net
+        size = exp_config["task_opts"]["augment_opts"]["img_size"]
+        if hasattr(net, "prototype_shape"):
+            return net.prototype_shape(size)
+        return (3, int(size[0]), int(size[1]))
+
+    def _arena_bytes(self, server, n_clients: int, exp_config) -> int:
+        mb = exp_config["engine_opts"].get("arena_mb", 0)
+        if mb:
+            return int(mb) << 20
+        slots = (n_clients + self.world - 1) // self.world
+        n = server.model.arena.numel
+        c, h, w = self._proto_shape(server, exp_config)
+        per_client = 2 * n * 4 + c * h * w * 4 + 64          # upload (+fisher) + token + counters
+        return int(slots * per_client + 5 * n * 4 + (8 << 20))
+
+    def run(self) -> None:
+        for exp_config in self.exp_configs:
+            self.run_experiment(exp_config)
+
+    def run_experiment(self, exp_config: Dict) -> ExperimentLog:
+        same_seeds(exp_config["random_seed"])
+        format_time = datetime.now().strftime("%Y-%m-%d-%H-%M")
+        log = ExperimentLog(os.path.join(self.common_config["logs_dir"], f"{exp_config['exp_name']}-{format_time}.json"),
+                            enabled=self.rank == 0)
+        log.record("config", exp_config)
+        self.logger.info(f"Experiment loading succeed: {exp_config['exp_name']}")
+        self.logger.info(f"For more details: {log.save_path}")
+        store, comm, server, clients, names = self.build(exp_config)
+        timer = DeviceTimer(self.device)
+        try:
+            if exp_config["engine_opts"].get("val_at_round0", True):
+                for client in clients:                                  # initial validation (experiment.py:163-173)
+                    self._process_val(client, log, 0, self.container)
+            comm_rounds = int(exp_config["exp_opts"]["comm_rounds"])
+            for curr_round in range(1, comm_rounds + 1):
+                self.logger.info(f"Start communication round: {curr_round:0>3d}/{comm_rounds:0>3d}")
+                self._process_one_round(curr_round, server, clients, names, exp_config, log, timer, comm)
+            self._gather_logs(log)
+        finally:
+            store.flush()
+            store.close()
+            perf = {k: sum(v) for k, v in timer.flush().items()}
+            if comm is not None:
+                perf["comm_bytes"] = comm.bytes_moved
+                comm.check_errors()
+                comm.close()
+            self.last_perf = perf
+            log.record("perf", {f"rank{self.rank}": perf}, flush=True)
+            log.close()
+        del server, clients
+        clear_cache()
+        return log
+
+    # ------------------------------------------------------------------ one round
+    def _process_one_round(self, curr_round, server, clients, names, exp_config, log, timer, comm) -> None:
+        eng = exp_config["engine_opts"]
+        save_payloads = eng.get("save_payload_ckpts", True)
+        local = {c.client_name: c for c in clients}
+        online = random.sample(names, exp_config["exp_opts"]["online_clients"])
+        val_interval = exp_config["exp_opts"]["val_interval"]
+        federated = getattr(type(server), "federated", None)
+        if federated is None:
+            federated = hasattr(server, "uploaded")
+
+        # ---- server -> clients ------------------------------------------------------------------------------------
+        with timer("dispatch"):
+            first = [n for n in online if n not in server.clients]
+            for n in first:
+                server.register_client(n)
+            if hasattr(server, "prepare_dispatch"):
+                server.prepare_dispatch(online, first)
+            for n in online:
+                client = local.get(n)
+                if client is None:
+                    continue
+                if n in first:
+                    state = server.get_dispatch_integrated_state(n)
+                    if state is not None:
+                        client.update_by_integrated_state(state)
+                else:
+                    state = server.get_dispatch_incremental_state(n)
+                    if state is not None:
+                        client.update_by_incremental_state(state)
+                if save_payloads:
+                    server.save_state(f"{curr_round}-{server.server_name}-{n}", strip_private(state), True)
+                del state
+
+        # ---- local training ---------------------------------------------------------------------------------------
+        with timer("train"):
+            for n in online:
+                if n in local:
+                    self._process_train(local[n], log, curr_round, self.container)
+
+        # ---- validation -------------------------------------------------------------------------------------------
+        if curr_round % val_interval == 0:
+            with timer("validate"):
+                for client in clients:
+                    self._process_val(client, log, curr_round, self.container)
+
+        # ---- clients -> server ------------------------------------------------------------------------------------
+        with timer("upload"):
+            for n in online:
+                client = local.get(n)
+                if client is not None:
+                    state = client.get_incremental_state()
+                    if save_payloads:
+                        client.save_state(f"{curr_round}-{n}-{server.server_name}", strip_private(state), True)
+                    if state is not None:
+                        server.set_client_incremental_state(n, state)
+                    del state
+                elif federated:
+                    server.set_client_incremental_state(n, None)      # slot lives on another rank
+        with timer("aggregate"):
+            server.calculate()
+        log.flush()
+
+    def _gather_logs(self, log: ExperimentLog) -> None:
+        """C7: metrics of remote clients are gathered to rank 0, which owns the JSON file."""
+        if self.world > 1:
+            parts: List[Optional[dict]] = [None] * self.world if self.rank == 0 else None
+            dist.gather_object(log.records.get("data", {}), parts, dst=0)
+            if self.rank == 0:
+                for p in parts[1:]:
+                    log.merge({"data": p})
+
+    @staticmethod
+    def _process_train(client, log, curr_round, container) -> None:
+        with container.possess_device() as device:
+            try:
+                task = client.task_pipeline.next_task()
+                if task["tr_epochs"] != 0:
+                    out = client.train(epochs=task["tr_epochs"], task_name=task["task_name"],
+                                       tr_loader=task["tr_loader"], val_loader=task["query_loader"], device=device)
+                    log.record(f"data.{client.client_name}.{curr_round}.{task['task_name']}",
+                               {"tr_acc": out["accuracy"], "tr_loss": out["loss"]})
+            except Exception as ex:
+                client.logger.error(ex)
+                raise
+
+    @staticmethod
+    def _process_val(client, log, curr_round, container) -> None:
+        with container.possess_device(container.max_worker()) as device:
+            try:
+                pipeline = client.task_pipeline
+                for tid in range(len(pipeline.task_list)):
+                    task = pipeline.get_task(tid)
+                    cmc, mAP, _ = client.validate(task_name=task["task_name"], query_loader=task["query_loader"],
+                                                  gallery_loader=task["gallery_loaders"], device=device)
+                    r = lambda k: float(cmc[k]) if len(cmc) > k else float(cmc[-1])  # noqa: E731
+                    log.record(f"data.{client.client_name}.{curr_round}.{task['task_name']}",
+                               {"val_rank_1": r(0), "val_rank_3": r(2), "val_rank_5": r(4), "val_rank_10": r(9),
+                                "val_map": float(mAP)})
+            except Exception as ex:
+                client.logger.error(ex)
+                raise
