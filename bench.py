@@ -1,0 +1,298 @@
+"""Headline benchmark: FedSTIL, ResNet-50, 8 clients, 256x128 crops, one *step* = one federated communication round.
+
+    python bench.py --gpus N --steps K --warmup W [--impl flpr|reference|nccl]
+
+A round (``experiment.py:183-243`` of the reference) = similarity-weighted dispatch to every client -> local training
+of every client (frozen-trunk prototype pass + head training incl. prototype rehearsal + herding) -> theta uploads ->
+FedAvg aggregation into the server model, with the reference's checkpoint files written every round.
+``value`` = images/s summed over all clients (whole job), device-timed with CUDA events, max over ranks.
+``e2e``   = the same metric measured by wall clock around the public API (``ExperimentStage`` rounds): every batch is
+copied host->device from pinned memory and every epoch's loss/accuracy is read back.
+
+``--impl reference`` runs the UNMODIFIED reference installed in ``baseline/_ref`` through its own builder /
+``ExperimentStage._process_one_round`` on the same synthetic workload. ``--impl nccl`` runs this engine with the
+collectives expressed as plain ``torch.distributed`` (NCCL) calls – the "baseline, not the product" harness.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec aggregate over 8 clients (FedSTIL ResNet-50 federated round, 256x128)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="flpr", choices=["flpr", "reference", "nccl"])
+    ap.add_argument("--clients", type=int, default=8)
+    ap.add_argument("--images", type=int, default=512, help="train images per client task")
+    ap.add_argument("--ids", type=int, default=64, help="identities per client task")
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--epochs", type=int, default=1)
+    ap.add_argument("--model", default="resnet50")
+    ap.add_argument("--height", type=int, default=256)
+    ap.add_argument("--width", type=int, default=128)
+    ap.add_argument("--no-ckpt", action="store_true", help="disable checkpoint files (not the headline config)")
+    ap.add_argument("--cpu-debug", action="store_true", help="tiny CPU run to exercise the harness")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def ckpt_root() -> str:
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    return os.path.join(base, f"flpr_bench_{os.getpid()}")
+
+
+def build_config(a, impl: str, world: int):
+    """Common + experiment config (same numbers for both arms)."""
+    root = ckpt_root()
+    common = {"datasets_dir": os.path.join(root, "data"), "checkpoints_dir": os.path.join(root, "ckpts"),
+              "logs_dir": os.path.join(root, "logs"), "parallel": 1,
+              "device": ["cpu"] if a.cpu_debug else [f"cuda:{i}" for i in range(max(a.gpus, 1))],
+              "defaults": {}}
+    exp = {
+        "exp_name": "bench-fedstil", "exp_method": "fedstil", "random_seed": 123,
+        "exp_opts": {"comm_rounds": 10 ** 6, "val_interval": 10 ** 9, "online_clients": a.clients},
+        "model_opts": {"name": a.model, "num_classes": 8000, "last_stride": 1, "neck": "bnneck", "atten_default": 0.9,
+                       "lambda_l1": 1e-3, "lambda_k": a.images, "fine_tuning": ["base.layer4", "classifier"]},
+        "criterion_opts": {"name": "cross_entropy", "num_classes": 8000, "epsilon": 0.1},
+        "optimizer_opts": {"name": "adam", "lr": 1e-3, "weight_decay": 1e-5},
+        "scheduler_opts": {"name": "step_lr", "step_size": 5},
+        "task_opts": {"sustain_rounds": 10 ** 6, "train_epochs": a.epochs,
+                      "augment_opts": {"level": "default", "img_size": [a.height, a.width],
+                                       "norm_mean": [0.485, 0.456, 0.406], "norm_std": [0.229, 0.224, 0.225]},
+                      "loader_opts": {"batch_size": a.batch, "num_workers": 0, "pin_memory": False,
+                                      "persistent_workers": False, "multiprocessing_context": None}},
+        "server": {"server_name": "server", "distance_calculate_step": 10, "distance_calculate_decay": 0.8},
+        "clients": [{"client_name": f"client-{i}", "model_ckpt_name": "fedstil_model",
+                     "tasks": [f"task-{i}-{t}" for t in range(5)]} for i in range(a.clients)],
+        "engine_opts": {"compute_dtype": "bf16", "comm_mode": "nccl" if impl == "nccl" else None,
+                        "val_at_round0": False, "checkpoints": not a.no_ckpt, "save_payload_ckpts": not a.no_ckpt},
+    }
+    return common, exp
+
+
+def cleanup_payloads(ckpt_dir: str) -> None:
+    """Per-round payload files are unique per round; drop them between steps (outside the timed region) so that a
+    long run cannot fill the RAM disk. Model checkpoints (overwritten in place) stay."""
+    for d, _, files in os.walk(ckpt_dir):
+        for f in files:
+            if f[:1].isdigit() and f.endswith(".ckpt"):
+                try:
+                    os.remove(os.path.join(d, f))
+                except OSError:
+                    pass
+
+
+# ================================================================================================== flpr / nccl arms
+def run_flpr(a, impl: str) -> dict:
+    import torch
+    import torch.distributed as dist
+    from flpr_b200.data.synthetic import random_array_split
+    from flpr_b200.ops import native
+    from flpr_b200.runtime.config import merge_experiment
+    from flpr_b200.runtime.experiment import ExperimentStage
+    from flpr_b200.runtime.explog import ExperimentLog
+    from flpr_b200.utils.misc import DeviceTimer, same_seeds
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    common, exp = build_config(a, impl, world)
+    cfg = merge_experiment(common, exp)
+    size = (a.height, a.width)
+
+    def factory(task: str, split: str):
+        cid = int(task.split("-")[1])
+        tid = int(task.split("-")[2])
+        n = a.images if split == "train" else 64
+        return random_array_split(n, a.ids, size, id_offset=(cid * 5 + tid) * a.ids % (8000 - a.ids),
+                                  seed=cid * 100 + tid * 3 + {"train": 0, "query": 1, "gallery": 2}[split])
+
+    with ExperimentStage(common, [cfg], source_factory=factory) as stage:
+        same_seeds(cfg["random_seed"])
+        dev = stage.device
+        store, comm, server, clients, names = stage.build(cfg)
+        log = ExperimentLog(os.path.join(common["logs_dir"], "bench.json"), enabled=False)
+        timer = DeviceTimer(dev)
+        cuda = dev.type == "cuda"
+
+        def sync():
+            if cuda:
+                torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+
+        def one_round(r):
+            stage._process_one_round(r, server, clients, names, cfg, log, timer, comm)
+
+        def after_round():
+            store.flush()
+            if rank == 0:
+                cleanup_payloads(common["checkpoints_dir"])
+
+        r = 0
+        for _ in range(a.warmup):
+            r += 1
+            one_round(r)
+            sync()
+            after_round()
+        sampler = ClockSampler(dev.index or 0) if cuda and rank == 0 else None
+
+        # ---- device-timed region: exactly K rounds ---------------------------------------------------------------
+        sync()
+        if sampler:
+            sampler.start()
+        launches0 = native.launches()
+        h2d0 = sum(getattr(t["tr_loader"], "h2d_bytes", 0) for c in clients for t in c.task_pipeline._cache.values())
+        if cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            r += 1
+            one_round(r)
+        if cuda:
+            e1.record()
+        sync()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        dev_ms = e0.elapsed_time(e1) if cuda else wall_ms
+        launches = native.launches() - launches0
+        h2d1 = sum(getattr(t["tr_loader"], "h2d_bytes", 0) for c in clients for t in c.task_pipeline._cache.values())
+        clocks = sampler.stop() if sampler else None
+        after_round()
+
+        # ---- end-to-end region: K more rounds by wall clock through the public API ---------------------------------
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            r += 1
+            one_round(r)
+            store.flush()                       # checkpoints of the round are on disk before the clock stops
+        sync()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        after_round()
+
+        red = torch.tensor([dev_ms, e2e_ms, float(launches), float(h2d1 - h2d0)], dtype=torch.float64,
+                           device=dev if cuda else "cpu")
+        if world > 1:
+            mx = red.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = red.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            dev_ms, e2e_ms = mx[0].item(), mx[1].item()
+            launches, h2d = int(sm[2].item()), sm[3].item()
+        else:
+            h2d = float(h2d1 - h2d0)
+        phases = {k: round(sum(v) / max(len(v), 1), 3) for k, v in timer.flush().items()}
+        comm_bytes = comm.bytes_moved if comm is not None else 0
+        store.close()
+        if comm is not None:
+            comm.check_errors()
+            comm.close()
+    imgs_per_round = a.clients * a.images * a.epochs
+    ms_per_step = dev_ms / a.steps
+    value = imgs_per_round / (ms_per_step / 1e3)
+    e2e_value = imgs_per_round / (e2e_ms / a.steps / 1e3)
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16" if not a.cpu_debug else "fp32",
+        "data": "synthetic 256x128 uint8 crops in pinned host memory, random-init weights",
+        "impl": impl,
+        "config": {"model": a.model, "method": "fedstil", "clients": a.clients, "global_batch": a.batch * a.clients,
+                   "batch_per_client": a.batch, "images_per_client_task": a.images, "ids_per_task": a.ids,
+                   "seq_len": None, "img_size": [a.height, a.width], "epochs_per_round": a.epochs,
+                   "rehearsal_lambda_k": a.images, "parallelism": f"client-per-rank x{a.gpus} (8 clients round-robin)",
+                   "step_definition": "one federated round: dispatch(mix) + local train of all clients + upload + "
+                                      "aggregate; checkpoints " + ("off" if a.no_ckpt else "on (async writer, RAM disk)"),
+                   "l2": "inputs larger than L2 (per-round working set >> 126 MB: 8 x 400 MB client state + images)"},
+        "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "ms_per_step": round(e2e_ms / a.steps, 3),
+                "h2d_bytes_per_step": int(h2d / a.steps),
+                "d2h_bytes_per_step": int(a.clients * a.epochs * 4 * 8)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "phase_ms_avg": phases,
+        "comm_bytes_rank0": int(comm_bytes),
+    }
+    return out if rank == 0 else {}
+
+
+# ================================================================================================== reference arm
+def run_reference(a) -> dict:
+    from baseline.reference_arm import run_reference_arm
+    return run_reference_arm(a, build_config, cleanup_payloads, METRIC, ClockSampler)
+
+
+def main():
+    a = parse_args()
+    if a.cpu_debug:
+        a.model, a.images, a.ids, a.batch, a.height, a.width, a.clients = "resnet18", 16, 4, 8, 64, 32, 2
+    try:
+        if a.impl == "reference":
+            out = run_reference(a)
+        else:
+            out = run_flpr(a, a.impl)
+    finally:
+        shutil.rmtree(ckpt_root(), ignore_errors=True)
+    if out:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,276 @@
+"""CPU unit tests: config merge, task schedule, log / checkpoint schemas, arena + fused optimizer semantics,
+losses, evaluation, FedSTIL relevance weights, herding, communicator local mode."""
+import json
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from flpr_b200.runtime.config import merge_experiment, ENGINE_DEFAULTS
+from flpr_b200.runtime.explog import ExperimentLog
+from flpr_b200.runtime.checkpoint import CheckpointStore
+from flpr_b200.runtime.arena import ParamArena, ArenaOptimizer, StepLR
+from flpr_b200.data.pipeline import ReIDTaskPipeline
+from flpr_b200.data.synthetic import synthetic_source_factory, make_array_split
+
+
+def test_config_shallow_merge():
+    common = {"defaults": {"random_seed": 1, "model_opts": {"name": "resnet18", "num_classes": 8000, "neck": "bnneck"},
+                           "exp_opts": {"comm_rounds": 60}}}
+    exp = {"exp_name": "x", "model_opts": {"name": "resnet50"}}
+    cfg = merge_experiment(common, exp)
+    assert cfg["model_opts"] == {"name": "resnet50"}           # block replaced wholesale (main.py:19-20)
+    assert cfg["exp_opts"]["comm_rounds"] == 60 and cfg["random_seed"] == 1
+    assert cfg["engine_opts"]["compute_dtype"] == ENGINE_DEFAULTS["compute_dtype"]
+    common["defaults"]["model_opts"]["name"] = "mutated"
+    assert cfg["model_opts"]["name"] == "resnet50"
+
+
+def _task_opts(bs=4, sustain=2):
+    return {"sustain_rounds": sustain, "train_epochs": 1,
+            "augment_opts": {"level": "default", "img_size": [32, 16], "norm_mean": [0.5] * 3, "norm_std": [0.25] * 3},
+            "loader_opts": {"batch_size": bs, "num_workers": 0, "pin_memory": False, "persistent_workers": False,
+                            "multiprocessing_context": None}}
+
+
+def test_task_pipeline_schedule():
+    """sustain_rounds semantics + last-task stickiness (datasets_pipeline.py:81-93)."""
+    p = ReIDTaskPipeline(["a", "b", "c"], _task_opts(sustain=2), "/nonexistent",
+                         source_factory=synthetic_source_factory(num_ids=2, train_per_id=2, size=(32, 16)))
+    seen = [p.next_task()["task_name"] for _ in range(10)]
+    assert seen == ["a", "a", "b", "b", "c", "c", "c", "c", "c", "c"]
+    t = p.get_task(0)
+    assert set(t) == {"task_name", "tr_epochs", "tr_loader", "query_loader", "gallery_loaders"}
+    data, pid, cid = next(iter(t["tr_loader"]))
+    assert data.shape == (4, 3, 32, 16) and pid.dtype == torch.long
+
+
+def test_device_loader_drop_last_rule():
+    ds = make_array_split([1, 2, 3], 3, (16, 8), pin=False)        # 9 images
+    p = ReIDTaskPipeline(["a"], _task_opts(bs=4), "/x", source_factory=lambda t, s: ds)
+    assert len(p.get_task(0)["tr_loader"]) == 2                    # 9 % 4 == 1 -> drop_last
+
+
+def test_experiment_log_schema(tmp_path):
+    log = ExperimentLog(str(tmp_path / "logs" / "e.json"), flush_interval=0.0)
+    log.record("config", {"a": 1})
+    log.record("data.client-0.1.task-0-0", {"tr_acc": 0.5, "tr_loss": 1.0})
+    log.record("data.client-0.1.task-0-0", {"val_rank_1": 0.25, "val_map": 0.1})
+    log.flush()
+    rec = json.load(open(tmp_path / "logs" / "e.json"))
+    assert rec["data"]["client-0"]["1"]["task-0-0"] == {"tr_acc": 0.5, "tr_loss": 1.0, "val_rank_1": 0.25,
+                                                         "val_map": 0.1}
+
+
+@pytest.mark.parametrize("asynchronous", [False, True])
+def test_checkpoint_layout(tmp_path, asynchronous):
+    st = CheckpointStore(str(tmp_path / "exp"), asynchronous=asynchronous)
+    st.save("client-0", "fedavg_model", {"w": torch.ones(3)}, cover=True)
+    st.save("server", "3-server-client-0", {"incremental_model_params": {"a": torch.zeros(2)}}, cover=True)
+    st.flush()
+    assert os.path.exists(tmp_path / "exp" / "client-0" / "fedavg_model.ckpt")
+    assert os.path.exists(tmp_path / "exp" / "server" / "3-server-client-0.ckpt")
+    assert torch.equal(st.load("client-0", "fedavg_model")["w"], torch.ones(3))
+    with pytest.raises(ValueError):
+        st.save("client-0", "fedavg_model", {}, cover=False)
+    assert st.load("client-0", "missing", default_value={"d": 1}) == {"d": 1}
+    st.close()
+
+
+def _toy_model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Conv2d(4, 6, 3, padding=1), torch.nn.Flatten(), torch.nn.Linear(6 * 16, 5))
+
+
+@pytest.mark.parametrize("kind,kw", [("adam", {"weight_decay": 1e-2}), ("sgd", {"momentum": 0.9, "weight_decay": 1e-2}),
+                                     ("sgd", {})])
+def test_arena_optimizer_matches_torch(kind, kw):
+    m1, m2 = _toy_model(), _toy_model()
+    arena = ParamArena(list(m1.named_parameters()), "cpu")
+    opt1 = ArenaOptimizer(kind, arena, lr=1e-2, **kw)
+    opt2 = (torch.optim.Adam if kind == "adam" else torch.optim.SGD)(m2.parameters(), lr=1e-2, **kw)
+    x = torch.randn(3, 4, 4, 4)
+    for _ in range(4):
+        opt1.zero_grad(); opt2.zero_grad()
+        m1(x).square().sum().backward(); m2(x).square().sum().backward()
+        opt1.step(); opt2.step()
+    for (n, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.allclose(p1, p2, atol=1e-6), n
+    # conv weight lives OHWI in the arena and round-trips through to_dict / from_dict
+    sd = arena.to_dict()
+    assert sd["0.weight"].is_contiguous() and torch.equal(sd["0.weight"], m1[0].weight.detach())
+    arena.from_dict({"0.weight": torch.zeros_like(sd["0.weight"])})
+    assert m1[0].weight.abs().sum() == 0
+    opt1.reset_state()
+    assert opt1.step_count == 0 and opt1.lr == 1e-2
+
+
+def test_step_lr_chainable():
+    m = _toy_model()
+    opt = ArenaOptimizer("adam", ParamArena(list(m.named_parameters()), "cpu"), lr=1.0)
+    sch = StepLR(opt, step_size=3, gamma=0.1)
+    lrs = []
+    for _ in range(7):
+        sch.step(); lrs.append(opt.lr)
+    assert np.allclose(lrs, [1, 1, .1, .1, .1, .01, .01])
+    opt.reset_state()
+    sch.step(); sch.step()                                          # epoch 9 -> decay applies to the *reset* lr
+    assert math.isclose(opt.lr, 0.1)
+
+
+def test_fused_penalty_and_l1_gradient_matches_autograd():
+    from flpr_b200.ops.fused import fused_optimizer_step
+    torch.manual_seed(0)
+    n = 64
+    p = torch.randn(n, requires_grad=True)
+    g0 = torch.randn(n); Q = torch.rand(n); p_old = torch.randn(n); G = torch.randn(n)
+    lam2, lam1, a, wd = 0.7, 0.05, 0.9, 0.01
+    loss = (g0 * p).sum() + lam2 * (Q * (p - p_old) ** 2).sum() + lam1 * (p - G).abs().sum() \
+        + 0.5 * wd * ((p - a * G) ** 2).sum()
+    loss.backward()
+    p2 = p.detach().clone()
+    stats = torch.zeros(2)
+    fused_optimizer_step("sgd", p2, g0, None, None, lr=1.0, step=1, weight_decay=wd, Q=Q, R=Q * p_old, lam2=lam2,
+                         G=G, lam1=lam1, atten=a, stats=stats)
+    assert torch.allclose(p.detach() - p2, p.grad, atol=1e-5)
+    assert math.isclose(stats[1].item(), (p.detach() - G).abs().sum().item(), rel_tol=1e-5)
+    const = (Q * p_old ** 2).sum().item()
+    assert math.isclose(stats[0].item() + const, (Q * (p.detach() - p_old) ** 2).sum().item(), rel_tol=1e-4)
+
+
+def test_losses():
+    from flpr_b200.criterions import CrossEntropyLabelSmooth, TripletLoss, DistillKL, kl_distance
+    torch.manual_seed(0)
+    score = torch.randn(6, 10, requires_grad=True)
+    tgt = torch.tensor([0, 1, 2, 3, 4, 5])
+    ce = CrossEntropyLabelSmooth(10, 0.1)(score=score, target=tgt)
+    logp = torch.log_softmax(score, 1)
+    t = torch.zeros(6, 10).scatter_(1, tgt[:, None], 1) * 0.9 + 0.01
+    assert torch.allclose(ce, (-t * logp).mean(0).sum(), atol=1e-6)
+    feat = torch.randn(8, 16)
+    lab = torch.tensor([0, 0, 1, 1, 2, 2, 3, 3])
+    for hard in (True, False):
+        for margin in (0.3, 0):
+            v = TripletLoss(margin=margin, hard_mining=hard)(feature=feat, target=lab)
+            assert torch.isfinite(v)
+    s, tt = torch.randn(4, 7), torch.randn(4, 7)
+    kd = DistillKL(4.0)(y_student=s, y_teacher=tt)
+    ref = torch.nn.functional.kl_div(torch.log_softmax(s / 4, 1), torch.softmax(tt / 4, 1), reduction="sum") * 16 / 4
+    assert torch.allclose(kd, ref)
+    a, b = torch.randn(1, 50), torch.randn(1, 50)
+    q = torch.softmax(b, -1)
+    assert torch.allclose(kl_distance(a, b), (q * (q.log() - torch.log_softmax(a, -1))).sum(), atol=1e-6)
+
+
+def _oracle_evaluate(qf, ql, gf, gl):
+    """Literal port of the reference algorithm (argsort + set ops) used as the test oracle."""
+    total_cmc = np.zeros(len(gl)); total_ap = 0.0
+    for i in range(len(ql)):
+        sim = (gf @ qf[i]).numpy()
+        order = np.argsort(sim)[::-1]
+        right = np.argwhere(gl.numpy() == ql[i].item()).flatten()
+        if len(right) == 0:
+            continue
+        mask = np.isin(order, right)
+        loc = np.argwhere(mask).flatten()
+        cmc = np.zeros(len(order)); cmc[loc[0]:] = 1
+        ap = 0.0
+        for j in range(len(right)):
+            prec = (j + 1) / (loc[j] + 1)
+            old = j / loc[j] if loc[j] != 0 else 1.0
+            ap += (old + prec) / 2 / len(right)
+        total_cmc += cmc; total_ap += ap
+    return total_cmc / len(ql), total_ap / len(ql)
+
+
+def test_evaluate_matches_reference_algorithm():
+    from flpr_b200.evaluation import evaluate
+    torch.manual_seed(1)
+    qf = torch.nn.functional.normalize(torch.randn(40, 32), dim=1)
+    gf = torch.nn.functional.normalize(torch.randn(150, 32), dim=1)
+    ql, gl = torch.randint(0, 12, (40,)), torch.randint(0, 14, (150,))
+    cmc, m_ap = evaluate(qf, ql, gf, gl)
+    cmc_r, map_r = _oracle_evaluate(qf, ql, gf, gl)
+    assert np.allclose(cmc, cmc_r) and math.isclose(m_ap, map_r, rel_tol=1e-9)
+
+
+def test_herding_matches_reference_loop():
+    from flpr_b200.methods.fedstil import herding_select
+    rng = np.random.default_rng(0)
+    feats = rng.normal(size=(9, 6)).astype(np.float32)
+    m = 5
+    mean = feats.sum(0) / len(feats)
+    picked, acc = [], []
+    for i in range(m):                                   # fedstil.py:386-392
+        p = mean - (feats + np.sum(acc, axis=0)) / (i + 1) if acc else mean - feats / (i + 1)
+        idx = int(np.argmin(np.linalg.norm(p, axis=1)))
+        picked.append(idx); acc.append(feats[idx])
+    assert herding_select(torch.from_numpy(feats), m) == picked
+
+
+def test_fedstil_relevance_double_normalisation():
+    """Weights of fedstil.py:1118-1144: inverse decayed KL -> own = mean -> normalise -> softmax."""
+    from flpr_b200.methods.fedstil import Server
+    from flpr_b200.criterions import kl_distance
+    torch.manual_seed(0)
+    srv = Server.__new__(Server)
+    srv.distance_calculate_step, srv.distance_calculate_decay = 2, 0.8
+    mem = {f"c{i}": [torch.randn(20) for _ in range(5)] for i in range(3)}
+    srv.token_memory = mem
+    select, w = srv.relevance_row("c1")
+    assert select == ["c0", "c2", "c1"]
+    own = mem["c1"][-1][None]
+    rel = []
+    for name in ("c0", "c2"):
+        dis = 1e-8
+        for k, tok in enumerate(mem[name][::-2]):
+            dis += kl_distance(own, tok[None]).item() / (0.8 ** k)
+        rel.append(1.0 / dis)
+    rel.append(sum(rel) / len(rel))
+    rel = torch.tensor(rel) / sum(rel)
+    assert torch.allclose(w, torch.softmax(rel, 0), atol=1e-5)
+    srv.token_memory = {"a": [torch.randn(8)], "b": [torch.randn(8)]}
+    _, w2 = srv.relevance_row("a")
+    assert torch.allclose(w2, torch.tensor([0.5, 0.5]))       # N=2 gives exactly 0.5/0.5
+
+
+def test_comm_local_mode_semantics():
+    from flpr_b200.parallel.comm import FedComm
+    comm = FedComm("cpu", 3, arena_bytes=1 << 20)
+    comm.alloc_client_buffer("up", 8); comm.alloc_client_buffer("cnt", 4); comm.alloc_rank_buffer("glob", 8)
+    U = torch.randn(3, 8)
+    for c in range(3):
+        comm.client_view("up", c).copy_(U[c]); comm.client_view("cnt", c).fill_(float(c + 1))
+    comm.reduce_bcast("up", "glob", [0, 2], cnt="cnt")          # only registered clients take part
+    assert torch.allclose(comm.rank_view("glob"), (1 * U[0] + 3 * U[2]) / 4, atol=1e-6)
+    rows = torch.tensor([[0.2, 0.3, 0.5]])
+    g = [torch.empty(8)]
+    comm.mix("up", [0, 1, 2], rows, [0], dst_g=g)
+    assert torch.allclose(g[0], rows[0] @ U, atol=1e-6)
+    out = torch.empty(8, 3)
+    comm.gather_strided("up", [0, 1, 2], out)
+    assert torch.equal(out, U.t())
+
+
+def test_resnet_state_dict_names_and_split():
+    from flpr_b200.models import nets
+    net = nets["resnet18"](num_classes=10, last_stride=1, neck="bnneck")
+    keys = set(net.state_dict().keys())
+    for k in ("base.conv1.weight", "base.layer4.0.conv1.weight", "base.layer4.0.downsample.0.weight",
+              "base.layer4.1.bn2.running_var", "bottleneck.weight", "classifier.weight"):
+        assert k in keys
+    assert "classifier.bias" not in keys and not net.bottleneck.bias.requires_grad
+    assert net.configure_split(["base.layer4", "classifier"]) == 4
+    x = torch.randn(2, 3, 64, 32)
+    net.train()
+    score, feat = net(x)
+    assert score.shape == (2, 10) and feat.shape == (2, 512)
+    assert net.prototype_shape((64, 32)) == tuple(net.forward_trunk(x).shape[1:])
+    net.eval()
+    assert net(x).shape == (2, 512)
+    r50 = nets["resnet50"](num_classes=10, last_stride=1, neck="bnneck")
+    r50.configure_split(["base.layer4", "classifier"])
+    assert r50.prototype_shape((256, 128)) == (1024, 16, 8)     # SURVEY §2.3 (x2 per side at 256x128)
