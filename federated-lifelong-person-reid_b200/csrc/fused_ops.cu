@@ -50,12 +50,20 @@ struct OptArgs {
   float atten;          // FedSTIL attention scalar a: adaptive weight A = p - a*G (weight decay acts on A)
   float momentum;
   int penalty_ones;     // FedProx: Q == 1 without materialising it
+  const float* hyper;   // optional device-resident [lr, step]: keeps a captured CUDA graph valid across steps
 };
 
 template <bool ADAM>
 __global__ void __launch_bounds__(256) fused_opt_kernel(const OptArgs a) {
   __shared__ float sh[8];
   float pen = 0.f, l1 = 0.f;
+  float lr = a.lr, bc1 = a.bc1, bc2_sqrt = a.bc2_sqrt;
+  if (a.hyper != nullptr) {
+    lr = a.hyper[0];
+    const float step = a.hyper[1];
+    bc1 = 1.f - powf(a.beta1, step);
+    bc2_sqrt = sqrtf(1.f - powf(a.beta2, step));
+  }
   const size_t n4 = a.n >> 2;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -97,15 +105,15 @@ __global__ void __launch_bounds__(256) fused_opt_kernel(const OptArgs a) {
         const float v = a.beta2 * vv[t] + (1.f - a.beta2) * g * g;
         mm[t] = m;
         vv[t] = v;
-        const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
-        np = p - (a.lr / a.bc1) * (m / denom);
+        const float denom = sqrtf(v) / bc2_sqrt + a.eps;
+        np = p - (lr / bc1) * (m / denom);
       } else {
         float d = g;
         if (a.momentum != 0.f) {
           d = a.momentum * mm[t] + g;
           mm[t] = d;
         }
-        np = p - a.lr * d;
+        np = p - lr * d;
       }
       pp[t] = np;
     }
@@ -488,7 +496,7 @@ extern "C" {
 int flpr_fused_opt(int adam, float* p, const float* g, float* m, float* v, const float* Q, const float* R,
                    const float* G, void* p_bf16, float* stats, size_t n, float lr, float beta1, float beta2, float eps,
                    float wd, int step, float lam2, float lam1, float atten, float momentum, int penalty_ones,
-                   cudaStream_t st) {
+                   const float* hyper, cudaStream_t st) {
   bind_device_of(p);
   if (n % 4) return -2;
   OptArgs a;
@@ -498,6 +506,7 @@ int flpr_fused_opt(int adam, float* p, const float* g, float* m, float* v, const
   a.bc1 = 1.f - powf(beta1, (float)step);
   a.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   a.lam2 = lam2; a.lam1 = lam1; a.atten = atten; a.momentum = momentum; a.penalty_ones = penalty_ones;
+  a.hyper = hyper;
   const int grid = grid_for(n / 4, 256);
   if (adam) fused_opt_kernel<true><<<grid, 256, 0, st>>>(a);
   else fused_opt_kernel<false><<<grid, 256, 0, st>>>(a);

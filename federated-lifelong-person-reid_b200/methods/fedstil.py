@@ -141,6 +141,21 @@ class Model(ModelModule):
         a.refresh_shadow()
 
     # ---- prototypes ------------------------------------------------------------------------------------------------
+    def folded_trunk(self):
+        """BN-folded, CUDA-graphed frozen trunk (CUDA + bf16 + ResNet only), shared by the clients of a rank."""
+        if self.compute_dtype != torch.bfloat16 or not hasattr(self.net, "base") or \
+                not getattr(self, "use_folded_trunk", True):
+            return None
+        ft = getattr(self, "_folded", None)
+        if ft is None:
+            from ..models.frozen import shared_folded_trunk
+            from ..models.resnet import ResNetReID
+            if not isinstance(self.net, ResNetReID) or self.net.head_start < 1:
+                self.use_folded_trunk = False
+                return None
+            ft = self._folded = shared_folded_trunk(self.net, torch.bfloat16)
+        return ft
+
     def forward_trunk(self, data: torch.Tensor) -> torch.Tensor:
         return self.net.forward_trunk(data)
 
@@ -165,14 +180,17 @@ class Model(ModelModule):
         feats = torch.cat(feats) if feats else torch.zeros(0, 1, device=protos.device)
         keep = set(int(p) for p in person_ids)
         m = self.m
-        for pid in torch.unique(pids).tolist():
-            if keep and pid not in keep:
-                continue
-            idx = torch.nonzero(pids == pid).squeeze(1)
-            order = herding_select(feats[idx], m)
+        upids = [p for p in torch.unique(pids).tolist() if not keep or p in keep]
+        if not upids:
+            return
+        groups = [torch.nonzero(pids == pid).squeeze(1) for pid in upids]
+        picks = herding_select_batched(feats, groups, m).cpu()              # [P, m], one host transfer
+        for gi, pid in enumerate(upids):
+            idx = groups[gi]
+            order = picks[gi].tolist()
             uniq, inverse = torch.unique(torch.tensor(order), return_inverse=True)
-            self.examplars[int(pid)] = {"bank": protos[idx[uniq.to(idx.device)]].clone(),
-                                        "cls": classes[idx[uniq.to(idx.device)]].clone(),
+            sel = idx[uniq.to(idx.device)]
+            self.examplars[int(pid)] = {"bank": protos[sel].clone(), "cls": classes[sel].clone(),
                                         "order": inverse.tolist()}
 
     def examplar_tensors(self) -> Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
@@ -188,6 +206,11 @@ class Model(ModelModule):
         if not ps:
             return None
         return torch.cat(ps), torch.cat(ids), torch.cat(cs)
+
+    def examplars_compact(self) -> Dict:
+        """Compact exemplar memory; the checkpoint writer process expands it to the reference schema."""
+        return {"_compact_examplars": {int(p): {"bank": ex["bank"], "cls": ex["cls"], "order": list(ex["order"])}
+                                       for p, ex in self.examplars.items()}}
 
     def examplars_state(self, max_bytes: int = 256 << 20) -> Dict:
         """``{np.int64 pid: [(ndarray proto, class_id), ...]}`` (``fedstil.py:841,846``) when small enough."""
@@ -225,6 +248,33 @@ def herding_select(feats: torch.Tensor, m: int) -> List[int]:
     return picks.tolist()
 
 
+def herding_select_batched(feats: torch.Tensor, groups: List[torch.Tensor], m: int) -> torch.Tensor:
+    """Herding for all identities at once: ``groups[g]`` indexes the rows of ``feats`` that belong to identity g.
+    Returns ``[len(groups), m]`` positions *within each group* (same rule as :func:`herding_select`)."""
+    P = len(groups)
+    nmax = max(int(g.numel()) for g in groups)
+    dev = feats.device
+    idx = torch.zeros(P, nmax, dtype=torch.long, device=dev)
+    valid = torch.zeros(P, nmax, dtype=torch.bool, device=dev)
+    for gi, g in enumerate(groups):
+        idx[gi, :g.numel()] = g
+        valid[gi, :g.numel()] = True
+    f = feats.float()[idx] * valid.unsqueeze(-1)                             # [P, nmax, D]
+    cnt = valid.sum(1, keepdim=True).clamp(min=1)
+    mean = f.sum(1) / cnt                                                    # [P, D]
+    sq = (f * f).sum(2).masked_fill(~valid, float("inf"))                    # padding can never win the argmin
+    S = torch.zeros_like(mean)
+    picks = torch.empty(P, m, dtype=torch.long, device=dev)
+    ar = torch.arange(P, device=dev)
+    for t in range(m):
+        c = (t + 1) * mean - S
+        score = sq - 2 * torch.bmm(f, c.unsqueeze(2)).squeeze(2)
+        i = torch.argmin(score, dim=1)
+        picks[:, t] = i
+        S = S + f[ar, i]
+    return picks
+
+
 class Operator(OperatorModule):
 
     @torch.no_grad()
@@ -232,12 +282,16 @@ class Operator(OperatorModule):
         """Eval-mode trunk pass; returns this epoch's rehearsal+task prototype set and the task token."""
         model.eval()
         protos, pids, cids = [], [], []
+        folded = model.folded_trunk()
         for data, person_id, classes_id in source_loader:
             data = model.prepare_input(data)
-            with model.autocast():
-                fmap = model.forward_trunk(data)
-            if model.compute_dtype == torch.bfloat16:
-                fmap = fmap.to(torch.bfloat16)
+            if folded is not None:
+                fmap = folded(data).clone()                    # graph-owned output buffer -> keep a copy
+            else:
+                with model.autocast():
+                    fmap = model.forward_trunk(data)
+                if model.compute_dtype == torch.bfloat16:
+                    fmap = fmap.to(torch.bfloat16)
             protos.append(fmap)
             pids.append(person_id.to(model.device))
             cids.append(classes_id.to(model.device))
@@ -254,6 +308,25 @@ class Operator(OperatorModule):
         with model.autocast():
             return model.forward_head(data)
 
+    def _graphed_step(self, model: Model):
+        """One head training step (zero-grad, forward, CE, backward, fused Adam+L1) as a replayable CUDA graph."""
+        st = getattr(self, "_step", None)
+        if st is None:
+            from ..runtime.graphs import GraphedStep
+            self._acc = torch.zeros(2, dtype=torch.float64, device=model.device)
+
+            def fn(data, target):
+                self.optimizer.zero_grad()
+                out = self._invoke_train(model, data, target)
+                out["loss"].backward()
+                self.optimizer.step()
+                with torch.no_grad():
+                    self._acc[0] += out["loss"].detach().double()
+                    self._acc[1] += (out["score"].argmax(dim=1) == target).sum()
+
+            st = self._step = GraphedStep(fn, warmup=2, enabled=getattr(model, "use_cuda_graphs", True))
+        return st
+
     def invoke_train(self, model: Model, dataloader, **kwargs) -> Dict:
         device = model.device
         pset = self.generate_prototypes(model, dataloader)
@@ -263,20 +336,15 @@ class Operator(OperatorModule):
         model.train()
         model.install(self.optimizer)
         self.optimizer.stats.zero_()
-        acc = torch.zeros(2, dtype=torch.float64, device=device)
         perm = torch.randperm(n, device=device)
         n_batches = n // bs if (n % bs == 1) else (n + bs - 1) // bs     # drop_last iff remainder == 1
         data_cnt = 0
+        step = self._graphed_step(model)
+        acc = self._acc
+        acc.zero_()
         for b in range(n_batches):
             idx = perm[b * bs:(b + 1) * bs]
-            data, target = protos[idx], pids[idx]
-            self.optimizer.zero_grad()
-            out = self._invoke_train(model, data, target, **kwargs)
-            out["loss"].backward()
-            self.optimizer.step()
-            with torch.no_grad():
-                acc[0] += out["loss"].detach().double()
-                acc[1] += (out["score"].argmax(dim=1) == target).sum()
+            step(protos[idx], pids[idx])
             data_cnt += len(idx)
         vals = torch.cat([acc, self.optimizer.stats.double()]).tolist()     # single host sync per epoch
         loss_sum, hits, _, l1_sum = vals
@@ -313,7 +381,8 @@ class Client(ClientModule):
     # ---- checkpoints -----------------------------------------------------------------------------------------------------
     def save_model(self, model_name: str) -> None:
         self.save_state(model_name, self.model.model_state(), True)
-        self.save_state(f"{model_name}_examplars", self.model.examplars_state(), True)
+        self.store.save(self.name, f"{model_name}_examplars", self.model.examplars_compact(), True,
+                        post="expand_examplars")
 
     # ---- protocol ----------------------------------------------------------------------------------------------------------
     def get_incremental_state(self, **kwargs) -> Dict:

@@ -1,0 +1,150 @@
+"""Inference-only execution of the frozen ResNet trunk (stem + ``layer1..k-1``) for FedSTIL's prototype pass
+(``methods/fedstil.py:558-617``: eval-mode forward of the whole frozen trunk, repeated every epoch of every round).
+
+What changes versus running the ``nn.Module``: batch-norm is folded into the preceding convolution once
+(eval mode makes it an affine map), weights are kept as bf16 ``channels_last`` tensors, conv+bias+ReLU and
+conv+bias+residual+ReLU are single fused calls, and a whole trunk pass for a given batch size is captured in a CUDA
+graph so that ~160 module dispatches per batch collapse into one launch.
+
+NOTE (round-1 status): the convolutions of the *trunk* still run on cuDNN; the trainable head (layer4 + classifier)
+runs on the hand-written tcgen05 kernels. Trunk implicit-GEMM kernels are listed as future work in DESIGN.md.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d, dtype: torch.dtype) -> Tuple[torch.Tensor, torch.Tensor]:
+    with torch.no_grad():
+        scale = bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+        w = conv.weight.float() * scale.view(-1, 1, 1, 1)
+        b = bn.bias.float() - bn.running_mean.float() * scale
+        if conv.bias is not None:
+            b = b + conv.bias.float() * scale
+    return w.to(dtype).contiguous(memory_format=torch.channels_last), b.to(dtype).contiguous()
+
+
+class FoldedTrunk:
+    def __init__(self, net, dtype: torch.dtype = torch.bfloat16, use_graphs: bool = True):
+        self.net = net
+        self.dtype = dtype
+        self.head_start = net.head_start
+        self.device = next(net.parameters()).device
+        self.ops: List[Tuple] = []
+        base = net.base
+        if self.head_start >= 1:
+            w, b = _fold(base.conv1, base.bn1, dtype)
+            self.ops.append(("conv_relu", w, b, base.conv1.stride, base.conv1.padding))
+            self.ops.append(("maxpool",))
+            for i in range(1, self.head_start):
+                for u in getattr(base, f"layer{i}"):
+                    self.ops.append(("unit", self._fold_unit(u)))
+        self.use_graphs = use_graphs and self.device.type == "cuda"
+        self._graphs: Dict[Tuple[int, int, int], Tuple] = {}
+        self._fused_ok = self._probe_fused()
+
+    def _fold_unit(self, u) -> dict:
+        d = {"kind": u.kind}
+        d["c1"] = _fold(u.conv1, u.bn1, self.dtype) + (u.conv1.stride, u.conv1.padding)
+        d["c2"] = _fold(u.conv2, u.bn2, self.dtype) + (u.conv2.stride, u.conv2.padding)
+        if u.kind != "basic":
+            d["c3"] = _fold(u.conv3, u.bn3, self.dtype) + (u.conv3.stride, u.conv3.padding)
+        if u.downsample is not None:
+            d["ds"] = _fold(u.downsample[0], u.downsample[1], self.dtype) + (u.downsample[0].stride,
+                                                                              u.downsample[0].padding)
+        return d
+
+    def _probe_fused(self) -> bool:
+        if self.device.type != "cuda":
+            return False
+        try:
+            x = torch.zeros(1, 64, 8, 8, device=self.device, dtype=self.dtype).contiguous(
+                memory_format=torch.channels_last)
+            w = torch.zeros(64, 64, 3, 3, device=self.device, dtype=self.dtype).contiguous(
+                memory_format=torch.channels_last)
+            b = torch.zeros(64, device=self.device, dtype=self.dtype)
+            torch.cudnn_convolution_relu(x, w, b, (1, 1), (1, 1), (1, 1), 1)
+            torch.cudnn_convolution_add_relu(x, w, x, 1.0, b, (1, 1), (1, 1), (1, 1), 1)
+            return True
+        except Exception:
+            return False
+
+    # ------------------------------------------------------------------ functional forward
+    def _conv(self, x, w, b, stride, padding, relu: bool, residual: Optional[torch.Tensor] = None):
+        if self._fused_ok and relu:
+            if residual is not None:
+                return torch.cudnn_convolution_add_relu(x, w, residual, 1.0, b, stride, padding, (1, 1), 1)
+            return torch.cudnn_convolution_relu(x, w, b, stride, padding, (1, 1), 1)
+        y = F.conv2d(x, w, b, stride, padding)
+        if residual is not None:
+            y = y + residual
+        return F.relu_(y) if relu else y
+
+    def _forward(self, x: torch.Tensor) -> torch.Tensor:
+        for op in self.ops:
+            if op[0] == "conv_relu":
+                x = self._conv(x, op[1], op[2], op[3], op[4], True)
+            elif op[0] == "maxpool":
+                x = F.max_pool2d(x, 3, 2, 1)
+            else:
+                d = op[1]
+                identity = x if "ds" not in d else self._conv(x, *d["ds"], relu=False)
+                out = self._conv(x, *d["c1"], relu=True)
+                if d["kind"] == "basic":
+                    x = self._conv(out, *d["c2"], relu=True, residual=identity)
+                else:
+                    out = self._conv(out, *d["c2"], relu=True)
+                    x = self._conv(out, *d["c3"], relu=True, residual=identity)
+        return x
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        """``x``: float / bf16 ``[B,3,H,W]`` (any memory format). Returns the feature map at the cut (bf16,
+        channels_last). The returned tensor is a graph-owned buffer when graphs are on: consume it before the next call."""
+        x = x.to(self.dtype).contiguous(memory_format=torch.channels_last)
+        if not self.use_graphs:
+            return self._forward(x)
+        key = tuple(x.shape)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = x.clone()
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._forward(static_in)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self._forward(static_in)
+            entry = (g, static_in, static_out)
+            self._graphs[key] = entry
+        g, static_in, static_out = entry
+        static_in.copy_(x)
+        g.replay()
+        return static_out
+
+
+_SHARED: Dict[Tuple, FoldedTrunk] = {}
+
+
+def shared_folded_trunk(net, dtype: torch.dtype = torch.bfloat16) -> FoldedTrunk:
+    """One folded trunk per (architecture, device) is shared by all clients of a rank whose frozen weights are equal
+    (FedSTIL never changes the trunk; all clients start from the same pre-trained weights)."""
+    dev = next(net.parameters()).device
+    key = (net.model_name, str(dev), net.head_start, dtype)
+    ft = _SHARED.get(key)
+    if ft is not None:
+        a, b = ft.net.base.conv1.weight, net.base.conv1.weight
+        la, lb = getattr(ft.net.base, "layer1")[0].conv1.weight, getattr(net.base, "layer1")[0].conv1.weight
+        if a.shape == b.shape and torch.equal(a, b) and torch.equal(la, lb) and \
+                torch.equal(ft.net.base.bn1.running_var, net.base.bn1.running_var):
+            return ft
+        return FoldedTrunk(net, dtype)
+    ft = FoldedTrunk(net, dtype)
+    _SHARED[key] = ft
+    return ft

@@ -145,6 +145,10 @@ class ArenaOptimizer:
         self.lam1 = 0.0
         self.atten = 0.0
         self.stats: Optional[torch.Tensor] = None
+        # device-resident [lr, step] (CUDA only): a captured CUDA graph of the train step stays valid across steps
+        self.hyper: Optional[torch.Tensor] = None
+        if arena.device.type == "cuda":
+            self.hyper = torch.tensor([self.lr, 0.0], dtype=torch.float32, device=arena.device)
 
     @property
     def param_groups(self) -> List[dict]:           # minimal torch.optim-like surface (lr scheduling / logging)
@@ -161,6 +165,12 @@ class ArenaOptimizer:
             self.v.zero_()
         self.step_count = 0
         self.lr = self.defaults["lr"]
+        self.sync_hyper()
+
+    def sync_hyper(self) -> None:
+        """Push the host-side lr / step counter to the device copy (call after changing ``lr``)."""
+        if self.hyper is not None:
+            self.hyper.copy_(torch.tensor([self.lr, float(self.step_count)]), non_blocking=True)
 
     def step(self) -> None:
         a = self.arena
@@ -170,6 +180,8 @@ class ArenaOptimizer:
             self.v = a.new_buffer()
         self.step_count += 1
         d = self.defaults
+        if self.hyper is not None:
+            self.hyper[1:2].add_(1.0)                 # captured together with the step when graphing
 
         def launch(lo: int, hi: int, with_g: bool) -> None:
             sl = slice(lo, hi)
@@ -179,7 +191,7 @@ class ArenaOptimizer:
                 beta2=d["betas"][1], eps=d["eps"], weight_decay=d["weight_decay"], momentum=d["momentum"],
                 Q=None if self.Q is None else self.Q[sl], R=None if self.R is None else self.R[sl], lam2=self.lam2,
                 penalty_ones=self.penalty_ones, G=self.G[sl] if with_g else None, lam1=self.lam1, atten=self.atten,
-                p_bf16=None if a.shadow is None else a.shadow[sl], stats=self.stats)
+                p_bf16=None if a.shadow is None else a.shadow[sl], stats=self.stats, hyper=self.hyper)
 
         n_g = self.G.numel() if self.G is not None else 0
         if 0 < n_g < a.numel:          # FedSTIL: only the adaptive-weight prefix carries the L1 / attention terms
@@ -201,6 +213,7 @@ class StepLR:
         self.last_epoch += 1
         if self.last_epoch % self.step_size == 0:
             self.optimizer.lr *= self.gamma
+            self.optimizer.sync_hyper()
 
     def state_dict(self) -> dict:
         return {"last_epoch": self.last_epoch}

@@ -139,8 +139,8 @@ class ExperimentStage:
         eng = exp_config["engine_opts"]
         names = [c["client_name"] for c in exp_config["clients"]]
         store = CheckpointStore(os.path.join(self.common_config["checkpoints_dir"], exp_config["exp_name"]),
-                                asynchronous=eng.get("async_checkpoint", True),
-                                enabled=eng.get("checkpoints", True))
+                                asynchronous=eng.get("async_checkpoint", True) and self.device.type == "cuda",
+                                enabled=eng.get("checkpoints", True), workers=eng.get("ckpt_workers", 4))
         server = parser_server(exp_config, self.common_config, self.device, store)
         clients = parser_clients(exp_config, self.common_config, self.device, store, None, self.rank, self.world,
                                  self.source_factory)
@@ -229,6 +229,9 @@ class ExperimentStage:
         federated = getattr(type(server), "federated", None)
         if federated is None:
             federated = hasattr(server, "uploaded")
+
+        if self.device.type == "cuda" and getattr(server, "store", None) is not None:
+            server.store.fence()          # snapshot DMAs of the previous round precede any overwrite of their sources
 
         # ---- server -> clients ------------------------------------------------------------------------------------
         with timer("dispatch"):

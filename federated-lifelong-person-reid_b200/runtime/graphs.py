@@ -1,0 +1,54 @@
+"""CUDA-graph capture of launch-bound inner loops (one training step = ~170 kernel launches whose Python dispatch
+costs more than their device time). A step function is run eagerly a few times (lazy initialisation, allocator
+warm-up), then captured once and replayed with its inputs copied into static buffers."""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from ..ops import native
+
+
+class GraphedStep:
+    """``step(*tensors)`` -> eager for the first ``warmup`` calls of a given input signature, captured on the next
+    call, replayed afterwards. The callable must be free of host synchronisation and keep its outputs in
+    pre-allocated device tensors (accumulators)."""
+
+    def __init__(self, fn: Callable, warmup: int = 2, enabled: bool = True):
+        self.fn = fn
+        self.warmup = warmup
+        self.enabled = enabled
+        self._state: Dict[Tuple, dict] = {}
+
+    @staticmethod
+    def _sig(tensors: Sequence[torch.Tensor]) -> Tuple:
+        return tuple((tuple(t.shape), t.dtype, t.stride()) for t in tensors)
+
+    def __call__(self, *tensors: torch.Tensor) -> None:
+        if not self.enabled or not tensors[0].is_cuda:
+            self.fn(*tensors)
+            return
+        sig = self._sig(tensors)
+        st = self._state.setdefault(sig, {"eager": 0, "graph": None})
+        if st["graph"] is None:
+            if st["eager"] < self.warmup:
+                st["eager"] += 1
+                self.fn(*tensors)
+                return
+            st["static"] = [t.clone() for t in tensors]
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = native.launches()
+            with torch.cuda.graph(g):
+                self.fn(*st["static"])
+            st["launches"] = native.launches() - l0
+            native.count_launch(-st["launches"])          # capture recorded, did not execute
+            st["graph"] = g
+        for s, t in zip(st["static"], tensors):
+            s.copy_(t, non_blocking=True)
+        st["graph"].replay()
+        native.count_launch(st["launches"])
+
+    def reset(self) -> None:
+        self._state.clear()
