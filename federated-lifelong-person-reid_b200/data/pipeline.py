@@ -54,6 +54,16 @@ class DeviceBatchLoader:
         n = len(self.dataset)
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
+    def fetch(self, indices: torch.Tensor):
+        """Augmented device batch for arbitrary dataset indices (rehearsal methods mix exemplars and task data)."""
+        ds = self.dataset
+        idx = indices.cpu()
+        u8 = ds.images[idx]
+        if self.device.type == "cuda":
+            u8 = u8.pin_memory().to(self.device, non_blocking=True)
+            self.h2d_bytes += u8.numel()
+        return self.augment(u8), ds.pids[idx].to(self.device), ds.cidx[idx].to(self.device)
+
     def _order(self) -> torch.Tensor:
         n = len(self.dataset)
         return torch.randperm(n, generator=self._gen) if self.shuffle else torch.arange(n)
