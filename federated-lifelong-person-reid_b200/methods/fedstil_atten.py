@@ -1,0 +1,231 @@
+"""``fedstil-atten`` – FedSTIL with a learned per-client attention over stacked global weights
+(reference ``methods/fedstil_atten.py``).
+
+Differences to ``fedstil``: ``global_weight`` carries a trailing **client** dimension ``K`` and
+``global_weight_atten in R^K`` is *trained*: ``theta = sum_k atten_k * gw[..., k] + aw`` (``fedstil_atten.py:88-96``);
+``aw`` is created once as ``(1 - atten_default) * w`` and persists across dispatches; the L1 term pulls ``atten`` and
+``aw`` towards their values at the last dispatch (``:650-660``). The server does not average: it concatenates every
+registered client's uploaded ``theta`` along the client dim (``:1099-1121``) and sends the stack to everyone
+(``:1145-1149``) – here one strided all-gather (``FedComm.gather_strided``) that writes the ``[n, K]`` layout
+directly on every rank, so dispatch to a local client is a device copy.
+
+The composition is expressed as a ``torch.nn.utils.parametrize`` parametrization of each adaptive layer's ``weight``,
+so the backbone code (including the tensor-core head) is unchanged and autograd routes ``d theta`` to ``aw`` / ``atten``.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.utils.parametrize as parametrize
+
+from . import fedstil as base
+
+
+class _Compose(nn.Module):
+    """weight = (gw_stack @ atten).view_as(aw) + aw ; ``gw_stack`` is ``[numel, Kmax]`` in the weight's own layout."""
+
+    def __init__(self, weight: torch.Tensor, k_max: int, atten_default: float):
+        super().__init__()
+        self.register_buffer("gw", torch.zeros(weight.numel(), k_max))
+        self.gw[:, 0] = weight.detach().reshape(-1)
+        self.atten = nn.Parameter(torch.zeros(k_max))
+        self.k_cur = 1
+        self.atten_default = atten_default
+        with torch.no_grad():
+            self.atten[0] = atten_default
+        self.register_buffer("atten0", self.atten.detach().clone())
+        self.register_buffer("aw0", torch.zeros_like(weight))
+
+    def forward(self, aw: torch.Tensor) -> torch.Tensor:
+        return (self.gw @ self.atten).view_as(aw) + aw
+
+    def right_inverse(self, theta: torch.Tensor) -> torch.Tensor:
+        return theta - (self.gw @ self.atten.detach()).view_as(theta)
+
+
+class Model(base.Model):
+    def __init__(self, net, lambda_l1: float = 1e-4, lambda_k: int = 8000, atten_default: float = 0.80,
+                 num_clients: int = 8, **kwargs):
+        super().__init__(net, lambda_l1, lambda_k, atten_default, **kwargs)
+        self.k_max = int(num_clients)
+        self.composers: Dict[str, _Compose] = {}
+        for lname in self.adaptive_names:
+            mod = self.net.get_submodule(lname)
+            comp = _Compose(mod.weight, self.k_max, self.atten_default)
+            with torch.no_grad():                      # aw = (1 - a) * w  -> initial theta == w
+                mod.weight.mul_(1.0 - self.atten_default)
+            parametrize.register_parametrization(mod, "weight", comp, unsafe=True)
+            comp.aw0.copy_(mod.parametrizations.weight.original.detach())
+            self.composers[lname] = comp
+        self._theta_params = {f"{n}.parametrizations.weight.original" for n in self.adaptive_names}
+
+    def install(self, optimizer) -> None:              # plain optimizer: the L1 term is part of the autograd loss
+        optimizer.G, optimizer.lam1, optimizer.atten = None, 0.0, 0.0
+        if optimizer.stats is None:
+            optimizer.stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+
+    def materialize(self, device, compute_dtype="bf16", fine_tuning=None):
+        base.ModelModule.materialize(self, device, compute_dtype, fine_tuning)
+        self.G = None
+        self.use_cuda_graphs = False                   # atten / K change between rounds: keep the step eager
+        return self
+
+    def sparseness(self) -> torch.Tensor:
+        s = 0.0
+        for lname, comp in self.composers.items():
+            aw = self.net.get_submodule(lname).parametrizations.weight.original
+            s = s + (comp.atten0 - comp.atten).abs().sum() + (comp.aw0 - aw).abs().sum()
+        return s
+
+    def theta_flat(self) -> torch.Tensor:
+        """Composed weights in the arena's prefix order/layout (what a client uploads)."""
+        a = self.arena
+        out = torch.zeros(self.theta_numel, device=self.device)
+        with torch.no_grad():
+            for lname in self.adaptive_names:
+                seg = a.segments[f"{lname}.parametrizations.weight.original"]
+                th = self.net.get_submodule(lname).weight
+                out[seg.offset:seg.offset + seg.numel] = (th.permute(0, 2, 3, 1) if seg.channels_last else th).reshape(-1)
+        return out
+
+    def set_global_stack(self, stack: torch.Tensor, k_cur: int) -> None:
+        """``stack``: ``[theta_numel, Kmax]`` in arena layout; re-initialises atten and the L1 anchors."""
+        a = self.arena
+        with torch.no_grad():
+            for lname, comp in self.composers.items():
+                seg = a.segments[f"{lname}.parametrizations.weight.original"]
+                chunk = stack[seg.offset:seg.offset + seg.numel]                       # [numel, Kmax]
+                if seg.channels_last:
+                    o, i, h, w = seg.shape
+                    chunk = chunk.view(o, h, w, i, -1).permute(0, 3, 1, 2, 4).reshape(seg.numel, -1)
+                comp.gw.copy_(chunk)
+                comp.k_cur = k_cur
+                comp.atten.zero_()
+                comp.atten[:k_cur] = self.atten_default
+                comp.atten0.copy_(comp.atten)
+                comp.aw0.copy_(self.net.get_submodule(lname).parametrizations.weight.original)
+
+    def model_state(self) -> Dict:
+        gw, gwa, aw, ab = {}, {}, {}, {}
+        for lname, comp in self.composers.items():
+            mod = self.net.get_submodule(lname)
+            shape = mod.parametrizations.weight.original.shape
+            gw[f"{lname}.global_weight"] = comp.gw[:, :comp.k_cur].detach().reshape(*shape, comp.k_cur).clone()
+            gwa[f"{lname}.global_weight_atten"] = comp.atten[:comp.k_cur].detach().clone()
+            aw[f"{lname}.adaptive_weight"] = mod.parametrizations.weight.original.detach().clone(
+                memory_format=torch.contiguous_format).unsqueeze(-1)
+            if getattr(mod, "bias", None) is not None:
+                ab[f"{lname}.adaptive_bias"] = mod.bias.detach().clone()
+        skip = set()
+        for n in self.adaptive_names:
+            skip |= {f"{n}.parametrizations.weight.original", f"{n}.bias", f"{n}.parametrizations.weight.0.gw",
+                     f"{n}.parametrizations.weight.0.atten", f"{n}.parametrizations.weight.0.atten0",
+                     f"{n}.parametrizations.weight.0.aw0"}
+        pre = {k: v.detach().clone(memory_format=torch.contiguous_format) for k, v in self.net.state_dict().items()
+               if k not in skip}
+        return {"global_weight": gw, "global_weight_atten": gwa, "adaptive_weights": aw, "adaptive_bias": ab,
+                "bn_params": {}, "pre_trained_params": pre}
+
+    def update_model(self, params_state: Dict) -> None:
+        with torch.no_grad():
+            for key, g in (params_state.get("global_weight") or {}).items():
+                comp = self.composers.get(key[: -len(".global_weight")])
+                if comp is not None:
+                    k = g.shape[-1]
+                    comp.gw.zero_()
+                    comp.gw[:, :k] = g.reshape(-1, k).to(comp.gw.device)
+                    comp.k_cur = k
+            for key, w in (params_state.get("adaptive_weights") or {}).items():
+                lname = key[: -len(".adaptive_weight")]
+                if lname in self.composers:
+                    orig = self.net.get_submodule(lname).parametrizations.weight.original
+                    orig.copy_(w.squeeze(-1).to(orig.device))
+            pre = params_state.get("pre_trained_params") or {}
+            own = self.net.state_dict()
+            for k2, v in pre.items():
+                if k2 in own and own[k2].shape == v.shape:
+                    own[k2].copy_(v.to(own[k2].device))
+        if self.arena is not None:
+            self.arena.refresh_shadow()
+
+    def folded_trunk(self):
+        return base.Model.folded_trunk(self)
+
+
+class Operator(base.Operator):
+    def compute_loss(self, model: Model, score, feature, target) -> torch.Tensor:
+        return super().compute_loss(model, score, feature, target) + model.lambda_l1 * model.sparseness()
+
+
+class Client(base.Client):
+    def get_incremental_state(self, **kwargs) -> Dict:
+        slot = self.comm.client_view("theta_up", self.client_id)
+        slot.copy_(self.model.theta_flat())
+        self.comm.client_view("cnt", self.client_id).fill_(float(self.train_cnt))
+        if self.task_token is not None and "token" in self.comm.bufs:
+            tok = self.comm.client_view("token", self.client_id)
+            tok.zero_()
+            tok[:self.task_token.numel()].copy_(self.task_token)
+        a = self.model.arena
+        named = {f"{l}.global_weight": a.view(slot, f"{l}.parametrizations.weight.original").unsqueeze(-1)
+                 for l in self.model.adaptive_names}
+        return {"train_cnt": self.train_cnt, "task_token": self.task_token, "incremental_sw": named,
+                "incremental_bn": {}}
+
+    def update_by_incremental_state(self, state: Dict, **kwargs) -> Any:
+        self.model.set_global_stack(state["_stack"], state["_k"])
+        self.logger.info("Update model succeed by incremental state from server.")
+
+    def update_by_integrated_state(self, state: Dict, **kwargs) -> Any:
+        self.model.update_model({"pre_trained_params": state.get("integrated_pre_trained_params") or {}})
+        if state.get("_stack") is not None:
+            self.model.set_global_stack(state["_stack"], state["_k"])
+        self.logger.info("Update model succeed by integrated state from server.")
+
+
+class Server(base.Server):
+    def __init__(self, server_name, model, operator, ckpt_root, **kwargs):
+        super().__init__(server_name, model, operator, ckpt_root, **kwargs)
+        self.stack: Optional[torch.Tensor] = None
+
+    def calculate(self) -> Any:
+        """All-gather of every registered client's theta along a trailing client dim (no averaging)."""
+        if self.uploaded:
+            n = self.model.theta_numel
+            if self.stack is None:
+                self.stack = torch.zeros(n, self.model.k_max, device=self.model.device)
+            k = len(self.uploaded)
+            out = torch.empty(n, k, device=self.model.device)
+            self.comm.gather_strided("theta_up", self.uploaded, out)
+            self.stack.zero_()
+            self.stack[:, :k] = out
+            self.model.set_global_stack(self.stack, k)
+        if self._round_uploads and "token" in self.comm.bufs:
+            ids = [self.client_ids[nm] for nm in self._round_uploads]
+            d = self.comm.bufs["token"].n
+            tk = torch.empty(d, len(ids), device=self.model.device)
+            self.comm.gather_strided("token", ids, tk)
+            toks = tk.t().contiguous()
+            for i, name in enumerate(self._round_uploads):
+                self.token_memory.setdefault(name, []).append(toks[i])
+        self._round_uploads = []
+        self.save_state(f"{self.server_name}_tokens", self.token_memory, True)
+
+    def prepare_dispatch(self, online_names: Sequence[str], first_contact: Sequence[str]) -> None:
+        return None
+
+    def _payload(self) -> Dict:
+        return {"_stack": self.stack, "_k": len(self.uploaded)}
+
+    def get_dispatch_incremental_state(self, client_name: str) -> Optional[Dict]:
+        if self.stack is None:
+            return None
+        ms = self.model.model_state()
+        return {"incremental_shared_params": ms["global_weight"], **self._payload()}
+
+    def get_dispatch_integrated_state(self, client_name: str) -> Dict:
+        ms = self.model.model_state()
+        return {"integrated_global_weight": ms["global_weight"], "integrated_bn_params": ms["bn_params"],
+                "integrated_pre_trained_params": ms["pre_trained_params"], **self._payload()}

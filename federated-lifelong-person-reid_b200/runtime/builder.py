@@ -29,6 +29,8 @@ def parser_model(method_name: str, model_config: Dict, device: str | torch.devic
                  engine_opts: Optional[Dict] = None) -> ModelModule:
     engine_opts = engine_opts or {}
     factory_kwargs = {n: p for n, p in model_config.items() if n not in ["name", "fine_tuning"]}
+    if method_name == "fedstil-atten" and "num_clients" in engine_opts:
+        factory_kwargs.setdefault("num_clients", engine_opts["num_clients"])
     net = nets[model_config["name"]](**factory_kwargs)
     if model_config.get("fine_tuning"):
         for p in net.parameters():
@@ -76,7 +78,7 @@ def _operator(exp_config: Dict, model: ModelModule):
 
 def parser_server(exp_config: Dict, common_config: Dict, device="cpu", store: Optional[CheckpointStore] = None,
                   comm=None) -> ServerModule:
-    eng = exp_config.get("engine_opts", {})
+    eng = dict(exp_config.get("engine_opts", {}), num_clients=len(exp_config["clients"]))
     model = parser_model(exp_config["exp_method"], exp_config["model_opts"], device, eng)
     operator = _operator(exp_config, model)
     kwargs = {n: p for n, p in exp_config["server"].items() if n != "server_name"}
@@ -89,7 +91,7 @@ def parser_server(exp_config: Dict, common_config: Dict, device="cpu", store: Op
 def parser_clients(exp_config: Dict, common_config: Dict, device="cpu", store: Optional[CheckpointStore] = None,
                    comm=None, rank: int = 0, world: int = 1, source_factory=None) -> List[ClientModule]:
     """Instantiate the clients hosted on this rank (all of them when ``world == 1``)."""
-    eng = exp_config.get("engine_opts", {})
+    eng = dict(exp_config.get("engine_opts", {}), num_clients=len(exp_config["clients"]))
     clients = []
     for cid, client_config in enumerate(exp_config["clients"]):
         if cid % world != rank:
