@@ -255,36 +255,70 @@ __global__ void __launch_bounds__(256) ce_ls_kernel(const TIn* logits, const lon
 }
 
 // ----------------------------------------------------------------------------- batch norm (NHWC, [M, C] bf16)
-// per-channel sum / sum of squares; blockDim.x threads each own 2 adjacent channels, rows split over blockIdx.y
-__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* x, float* sum, float* sqsum, int M, int C,
+// Column statistics of x[M, C] (bf16): every thread owns 8 adjacent channels (one 16-byte load per row), the rows
+// are split over blockIdx.y (and threadIdx.y when C/8 < 256); per-block partial sums go to part[gridDim.y][2][C]
+// (no atomics, deterministic) and bn_finalize_kernel folds the partials.
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* x, float* part, int M, int C,
                                                        int rows_per_block) {
-  const int c2 = blockIdx.x * blockDim.x + threadIdx.x;  // channel pair
-  if (c2 * 2 >= C) return;
+  __shared__ float sh[16 * 256];
+  const int c8n = C / 8;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c8 = blockIdx.x * blockDim.x + tx;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(r0 + rows_per_block, M);
-  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-  const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(x);
-  const size_t c2n = (size_t)C / 2;
+  float s[8], q[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { s[t] = 0.f; q[t] = 0.f; }
+  if (c8 < c8n) {
+    const uint4* xp = reinterpret_cast<const uint4*>(x);
 #pragma unroll 4
-  for (int r = r0; r < r1; ++r) {
-    const float2 f = __bfloat1622float2(xp[(size_t)r * c2n + c2]);
-    s0 += f.x; s1 += f.y;
-    q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+    for (int r = r0 + ty; r < r1; r += blockDim.y) {
+      const uint4 u = xp[(size_t)r * c8n + c8];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __bfloat1622float2(h[t]);
+        s[2 * t] += f.x; s[2 * t + 1] += f.y;
+        q[2 * t] = fmaf(f.x, f.x, q[2 * t]); q[2 * t + 1] = fmaf(f.y, f.y, q[2 * t + 1]);
+      }
+    }
   }
-  atomicAdd(sum + 2 * c2, s0);
-  atomicAdd(sum + 2 * c2 + 1, s1);
-  atomicAdd(sqsum + 2 * c2, q0);
-  atomicAdd(sqsum + 2 * c2 + 1, q1);
+  const int tid = ty * blockDim.x + tx;
+  for (int off = blockDim.y >> 1; off > 0; off >>= 1) {   // fold the row-lanes of this block
+    __syncthreads();
+    if (ty >= off && ty < 2 * off) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { sh[(t * 2) * 256 + tid - off * blockDim.x] = s[t]; sh[(t * 2 + 1) * 256 + tid - off * blockDim.x] = q[t]; }
+    }
+    __syncthreads();
+    if (ty < off) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { s[t] += sh[(t * 2) * 256 + tid]; q[t] += sh[(t * 2 + 1) * 256 + tid]; }
+    }
+  }
+  if (ty == 0 && c8 < c8n) {
+    float* ps = part + (size_t)blockIdx.y * 2 * C + c8 * 8;
+    float* pq = ps + C;
+    reinterpret_cast<float4*>(ps)[0] = make_float4(s[0], s[1], s[2], s[3]);
+    reinterpret_cast<float4*>(ps)[1] = make_float4(s[4], s[5], s[6], s[7]);
+    reinterpret_cast<float4*>(pq)[0] = make_float4(q[0], q[1], q[2], q[3]);
+    reinterpret_cast<float4*>(pq)[1] = make_float4(q[4], q[5], q[6], q[7]);
+  }
 }
 
-// finalize: mean/rstd, running stats (momentum, unbiased var), scale/shift for the apply pass
-__global__ void bn_finalize_kernel(const float* sum, const float* sqsum, const float* gamma, const float* beta,
+// finalize: fold partials, mean/rstd, running stats (momentum, unbiased var), scale/shift for the apply pass
+__global__ void bn_finalize_kernel(const float* part, int nparts, const float* gamma, const float* beta,
                                    float* mean, float* rstd, float* scale, float* shift, float* running_mean,
                                    float* running_var, int M, int C, float eps, float momentum) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float mu = sum[c] / M;
-  float var = sqsum[c] / M - mu * mu;
+  float sm = 0.f, sq = 0.f;
+  for (int i = 0; i < nparts; ++i) {
+    sm += part[(size_t)i * 2 * C + c];
+    sq += part[(size_t)i * 2 * C + C + c];
+  }
+  const float mu = sm / M;
+  float var = sq / M - mu * mu;
   var = fmaxf(var, 0.f);
   const float rs = rsqrtf(var + eps);
   mean[c] = mu;
@@ -327,43 +361,91 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* x, c
   }
 }
 
-// backward reduce: dy_eff = dy * (y > 0 if relu); dgamma_raw[c] += sum dy_eff * xhat ; dbeta[c] += sum dy_eff
-// also writes dy_eff (masked) in place of dres when requested so the residual branch gets its gradient.
+// backward reduce: dy_eff = dy * (y > 0 if relu); per-block partials of sum dy_eff * xhat and sum dy_eff go to
+// part[gridDim.y][2][C]; also writes dy_eff (masked) to dres when requested so the residual branch gets its gradient.
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* y,
                                                             const __nv_bfloat16* x, const float* mean,
-                                                            const float* rstd, float* dgamma, float* dbeta,
-                                                            __nv_bfloat16* dres, int M, int C, int rows_per_block,
-                                                            int relu) {
-  const int c2 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c2 * 2 >= C) return;
+                                                            const float* rstd, float* part, __nv_bfloat16* dres,
+                                                            int M, int C, int rows_per_block, int relu) {
+  __shared__ float sh[16 * 256];
+  const int c8n = C / 8;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c8 = blockIdx.x * blockDim.x + tx;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(r0 + rows_per_block, M);
-  const float mu0 = mean[2 * c2], mu1 = mean[2 * c2 + 1], rs0 = rstd[2 * c2], rs1 = rstd[2 * c2 + 1];
-  float g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
-  const size_t c2n = (size_t)C / 2;
-  const __nv_bfloat162* dyp = reinterpret_cast<const __nv_bfloat162*>(dy);
-  const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(y);
-  const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(x);
-  __nv_bfloat162* dr = reinterpret_cast<__nv_bfloat162*>(dres);
+  float g[8], b[8], mu[8], rs[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { g[t] = 0.f; b[t] = 0.f; mu[t] = 0.f; rs[t] = 0.f; }
+  if (c8 < c8n) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { mu[t] = mean[c8 * 8 + t]; rs[t] = rstd[c8 * 8 + t]; }
+    const uint4* dyp = reinterpret_cast<const uint4*>(dy);
+    const uint4* yp = reinterpret_cast<const uint4*>(y);
+    const uint4* xp = reinterpret_cast<const uint4*>(x);
+    uint4* dr = reinterpret_cast<uint4*>(dres);
 #pragma unroll 2
-  for (int r = r0; r < r1; ++r) {
-    const size_t idx = (size_t)r * c2n + c2;
-    float2 d = __bfloat1622float2(dyp[idx]);
-    if (relu) {
-      const float2 o = __bfloat1622float2(yp[idx]);
-      if (o.x <= 0.f) d.x = 0.f;
-      if (o.y <= 0.f) d.y = 0.f;
+    for (int r = r0 + ty; r < r1; r += blockDim.y) {
+      const size_t idx = (size_t)r * c8n + c8;
+      uint4 du = dyp[idx];
+      const uint4 xu = xp[idx];
+      __nv_bfloat162* dh = reinterpret_cast<__nv_bfloat162*>(&du);
+      const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xu);
+      if (relu) {
+        const uint4 yu = yp[idx];
+        const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&yu);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float2 d = __bfloat1622float2(dh[t]);
+          const float2 o = __bfloat1622float2(yh[t]);
+          if (o.x <= 0.f) d.x = 0.f;
+          if (o.y <= 0.f) d.y = 0.f;
+          dh[t] = __floats2bfloat162_rn(d.x, d.y);
+        }
+      }
+      if (dr) dr[idx] = du;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 d = __bfloat1622float2(dh[t]);
+        const float2 xv = __bfloat1622float2(xh[t]);
+        g[2 * t] = fmaf(d.x, (xv.x - mu[2 * t]) * rs[2 * t], g[2 * t]);
+        g[2 * t + 1] = fmaf(d.y, (xv.y - mu[2 * t + 1]) * rs[2 * t + 1], g[2 * t + 1]);
+        b[2 * t] += d.x; b[2 * t + 1] += d.y;
+      }
     }
-    if (dr) dr[idx] = __floats2bfloat162_rn(d.x, d.y);
-    const float2 xv = __bfloat1622float2(xp[idx]);
-    g0 = fmaf(d.x, (xv.x - mu0) * rs0, g0);
-    g1 = fmaf(d.y, (xv.y - mu1) * rs1, g1);
-    b0 += d.x; b1 += d.y;
   }
-  atomicAdd(dgamma + 2 * c2, g0);
-  atomicAdd(dgamma + 2 * c2 + 1, g1);
-  atomicAdd(dbeta + 2 * c2, b0);
-  atomicAdd(dbeta + 2 * c2 + 1, b1);
+  const int tid = ty * blockDim.x + tx;
+  for (int off = blockDim.y >> 1; off > 0; off >>= 1) {
+    __syncthreads();
+    if (ty >= off && ty < 2 * off) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { sh[(t * 2) * 256 + tid - off * blockDim.x] = g[t]; sh[(t * 2 + 1) * 256 + tid - off * blockDim.x] = b[t]; }
+    }
+    __syncthreads();
+    if (ty < off) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { g[t] += sh[(t * 2) * 256 + tid]; b[t] += sh[(t * 2 + 1) * 256 + tid]; }
+    }
+  }
+  if (ty == 0 && c8 < c8n) {
+    float* pg = part + (size_t)blockIdx.y * 2 * C + c8 * 8;
+    float* pb = pg + C;
+    reinterpret_cast<float4*>(pg)[0] = make_float4(g[0], g[1], g[2], g[3]);
+    reinterpret_cast<float4*>(pg)[1] = make_float4(g[4], g[5], g[6], g[7]);
+    reinterpret_cast<float4*>(pb)[0] = make_float4(b[0], b[1], b[2], b[3]);
+    reinterpret_cast<float4*>(pb)[1] = make_float4(b[4], b[5], b[6], b[7]);
+  }
+}
+
+__global__ void bn_fold_partials_kernel(const float* part, int nparts, float* dgamma, float* dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float g = 0.f, b = 0.f;
+  for (int i = 0; i < nparts; ++i) {
+    g += part[(size_t)i * 2 * C + c];
+    b += part[(size_t)i * 2 * C + C + c];
+  }
+  dgamma[c] = g;
+  dbeta[c] = b;
 }
 
 // dx = gamma*rstd * (dy_eff - dbeta/M - xhat * dgamma/M)
@@ -555,22 +637,38 @@ int flpr_ce_label_smooth(const void* logits, const long long* target, void* dlog
   return (int)cudaGetLastError();
 }
 
-// sum/sqsum must be zeroed by the caller (they live in one scratch buffer that is memset once per step).
-int flpr_bn_fwd(const void* x, const float* gamma, const float* beta, const void* residual, void* y, float* sum,
-                float* sqsum, float* mean, float* rstd, float* scale, float* shift, float* running_mean,
+static void bn_launch_geometry(int M, int C, dim3& grid, dim3& block, int& rpb) {
+  const int c8n = C / 8;
+  const int bx = c8n >= 256 ? 256 : c8n;              // channel groups per block
+  int by = 1;                                         // row-lanes per block (power of two, <= 16)
+  while (by * 2 * bx <= 256 && by < 16) by *= 2;
+  const int gx = (c8n + bx - 1) / bx;
+  int gy = (148 * 2) / gx;
+  if (gy < 1) gy = 1;
+  rpb = (M + gy - 1) / gy;
+  if (rpb < by * 4) rpb = by * 4;
+  gy = (M + rpb - 1) / rpb;
+  grid = dim3(gx, gy);
+  block = dim3(bx, by);
+}
+
+int flpr_bn_partials_floats(int M, int C) {
+  dim3 g, b; int rpb;
+  bn_launch_geometry(M, C, g, b, rpb);
+  return (int)g.y * 2 * C;
+}
+
+// `part` is scratch of flpr_bn_partials_floats(M, C) floats (no zeroing needed).
+int flpr_bn_fwd(const void* x, const float* gamma, const float* beta, const void* residual, void* y, float* part,
+                float* mean, float* rstd, float* scale, float* shift, float* running_mean,
                 float* running_var, int M, int C, float eps, float momentum, int relu, cudaStream_t st) {
   bind_device_of(x);
   if (C % 8) return -2;
-  const int threads = 128;
-  const int gx = (C / 2 + threads - 1) / threads;
-  int gy = (148 * 4) / gx;
-  if (gy < 1) gy = 1;
-  int rpb = (M + gy - 1) / gy;
-  if (rpb < 16) rpb = 16;
-  gy = (M + rpb - 1) / rpb;
-  bn_stats_kernel<<<dim3(gx, gy), threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), sum, sqsum, M, C, rpb);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sum, sqsum, gamma, beta, mean, rstd, scale, shift, running_mean,
-                                                      running_var, M, C, eps, momentum);
+  dim3 grid, block; int rpb;
+  bn_launch_geometry(M, C, grid, block, rpb);
+  bn_stats_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), part, M, C, rpb);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, (int)grid.y, gamma, beta, mean, rstd, scale, shift,
+                                                      running_mean, running_var, M, C, eps, momentum);
   const size_t total8 = (size_t)M * C / 8;
   bn_apply_kernel<<<grid_for(total8, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), scale, shift,
                                                          reinterpret_cast<const __nv_bfloat16*>(residual),
@@ -590,23 +688,22 @@ int flpr_affine_act(const void* x, const float* scale, const float* shift, const
   return (int)cudaGetLastError();
 }
 
-// dgamma/dbeta must be zeroed by the caller. dres (nullable) receives the ReLU-masked dy for the residual branch.
+// `part` is scratch of flpr_bn_partials_floats(M, C) floats. dres (nullable) receives the ReLU-masked dy for the
+// residual branch.
 int flpr_bn_bwd(const void* dy, const void* y, const void* x, const float* mean, const float* rstd, const float* gamma,
-                float* dgamma, float* dbeta, void* dres, void* dx, int M, int C, int relu, cudaStream_t st) {
+                float* dgamma, float* dbeta, float* part, void* dres, void* dx, int M, int C, int relu,
+                cudaStream_t st) {
   bind_device_of(dy);
   if (C % 8) return -2;
-  const int threads = 128;
-  const int gx = (C / 2 + threads - 1) / threads;
-  int gy = (148 * 4) / gx;
-  if (gy < 1) gy = 1;
-  int rpb = (M + gy - 1) / gy;
-  if (rpb < 16) rpb = 16;
-  gy = (M + rpb - 1) / rpb;
-  bn_bwd_reduce_kernel<<<dim3(gx, gy), threads, 0, st>>>(
+  dim3 grid, block; int rpb;
+  bn_launch_geometry(M, C, grid, block, rpb);
+  bn_bwd_reduce_kernel<<<grid, block, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y),
-      reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dres), M,
-      C, rpb, relu);
+      reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, part, reinterpret_cast<__nv_bfloat16*>(dres), M, C, rpb,
+      relu);
+  bn_fold_partials_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, (int)grid.y, dgamma, dbeta, C);
   const size_t total8 = (size_t)M * C / 8;
+  // the masked dy was materialised in dres when present: the apply pass then needs no ReLU mask of its own
   bn_bwd_apply_kernel<<<grid_for(total8, 256), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y),
       reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, gamma, dgamma, dbeta,

@@ -53,7 +53,8 @@ struct GemmParams {
   int relu;
   const __nv_bfloat16* residual;
   // conv geometry (A operand in OP_CONV mode)
-  int cH, cW, cC, cTH, cNB, cKW, cPadH, cPadW, cTilesPerImg;
+  int cH, cW, cC, cTH, cNB, cKW, cPadH, cPadW, cTilesPerImg, cSplits;
+  long long tap_stride;  // conv wgrad: output column offset per filter tap
 };
 
 template <int BN>
@@ -82,7 +83,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * BM;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int zsplit = (B_MODE == OP_CONV) ? (blockIdx.z % p.cSplits) : blockIdx.z;
+  const int kb_begin = zsplit * p.kb_per_split;
   const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
   const int num_kb = kb_end - kb_begin;
 
@@ -142,9 +144,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         if constexpr (B_MODE == OP_KMAJOR) {
           tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
-        } else {
+        } else if constexpr (B_MODE == OP_MNMAJOR) {
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 64 * 128, &tmB, &full_bar[stage], n0 + j * 64, kb * BK);
+        } else {
+          // weight-gradient of a convolution: K runs over pixels (64 per block), the filter tap (blockIdx.z / splits)
+          // shifts the 4-D box, zero padding comes from TMA out-of-bounds fill
+          const int tap = blockIdx.z / p.cSplits;
+          const int kh = tap / p.cKW;
+          const int kw = tap - kh * p.cKW;
+          const int p0 = kb * BK;
+          const int hw = p.cH * p.cW;
+          const int img = p0 / hw;
+          const int h0 = (p0 - img * hw) / p.cW;
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(sb + j * 64 * 128, &tmB, &full_bar[stage], n0 + j * 64, kw - p.cPadW, h0 + kh - p.cPadH, img);
         }
         if (++stage == L::STAGES) {
           stage = 0;
@@ -154,7 +169,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp_id == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MODE == OP_MNMAJOR, B_MODE == OP_MNMAJOR);
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MODE == OP_MNMAJOR, B_MODE != OP_KMAJOR);
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < num_kb; ++i) {
@@ -170,7 +185,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             da = make_smem_desc_sw128(sa + k * (UMMA_K * 128), 64 * 128, 1024);
           else
             da = make_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
-          if constexpr (B_MODE == OP_MNMAJOR)
+          if constexpr (B_MODE != OP_KMAJOR)
             db = make_smem_desc_sw128(sb + k * (UMMA_K * 128), 64 * 128, 1024);
           else
             db = make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
@@ -196,6 +211,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       tc_fence_after();
     }
     const float bm = (p.bias_m != nullptr && row < p.M) ? p.bias_m[row] : 0.f;
+    const long long tap_off = (B_MODE == OP_CONV) ? (long long)(blockIdx.z / p.cSplits) * p.tap_stride : 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -234,7 +250,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
       } else if (row < p.M) {
-        const long long base = (long long)row * p.ldo + n0 + c0;
+        const long long base = (long long)row * p.ldo + n0 + c0 + tap_off;
         const bool full = (n0 + c0 + 32 <= p.N);
         if (p.residual != nullptr) {
           if (full && ((base & 7) == 0)) {
@@ -413,6 +429,7 @@ static int dispatch_modes(int a_mode, int b_mode, const CUtensorMap& ta, const C
   if (a_mode == OP_MNMAJOR && b_mode == OP_KMAJOR) return launch<BN, OP_MNMAJOR, OP_KMAJOR>(ta, tb, p, splits, st);
   if (a_mode == OP_MNMAJOR && b_mode == OP_MNMAJOR) return launch<BN, OP_MNMAJOR, OP_MNMAJOR>(ta, tb, p, splits, st);
   if (a_mode == OP_CONV && b_mode == OP_KMAJOR) return launch<BN, OP_CONV, OP_KMAJOR>(ta, tb, p, splits, st);
+  if (a_mode == OP_MNMAJOR && b_mode == OP_CONV) return launch<BN, OP_MNMAJOR, OP_CONV>(ta, tb, p, splits, st);
   return set_err("unsupported operand mode combination", -3);
 }
 
@@ -423,7 +440,7 @@ static int pick_bn(int M, int N, int requested) {
   if (N >= 256 && mt * ((N + 255) / 256) >= 148) return 256;
   if (N >= 128 && mt * ((N + 127) / 128) >= 120) return 128;
   if (N <= 64) return 64;
-  return (mt * ((N + 127) / 128) >= 60) ? 128 : 64;
+  return 128;
 }
 
 }  // namespace flpr
@@ -526,6 +543,55 @@ int flpr_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int NIMG, int 
   if (BN == 64) return dispatch_modes<64>(OP_CONV, OP_KMAJOR, ta, tb, p, 1, stream);
   if (BN == 128) return dispatch_modes<128>(OP_CONV, OP_KMAJOR, ta, tb, p, 1, stream);
   return dispatch_modes<256>(OP_CONV, OP_KMAJOR, ta, tb, p, 1, stream);
+}
+
+// Weight gradient of a stride-1 convolution: out[Cout, KH*KW*C] (fp32, tap-major then C) +=
+//   sum over pixels dY[p, cout] * Xshift_tap[p, c].  One launch covers every tap (grid.z = taps * split_k).
+// dY: [NIMG*H*W, Cout] bf16, X: [NIMG,H,W,C] bf16. `out` must be zeroed when split_k > 1 (atomic accumulation).
+int flpr_conv_wgrad_nhwc_bf16(const void* X, const void* dY, float* out, int NIMG, int H, int W, int C, int Cout,
+                              int KH, int KW, int pad_h, int pad_w, int split_k, int bn_req, cudaStream_t stream) {
+  bind_device_of(X);
+  if (C % 64) return set_err("conv wgrad: C must be a multiple of 64", -7);
+  if (Cout % 8) return set_err("conv wgrad: Cout must be a multiple of 8", -11);
+  if (W > 64 || (64 % W)) return set_err("conv wgrad: W must divide 64", -8);
+  int TH, NB;
+  if (H * W >= 64) {
+    if ((H * W) % 64) return set_err("conv wgrad: H*W must be a multiple of 64", -9);
+    TH = 64 / W; NB = 1;
+  } else {
+    if (64 % (H * W)) return set_err("conv wgrad: H*W must divide 64", -9);
+    TH = H; NB = 64 / (H * W);
+  }
+  const int M = Cout, N = C, K = NIMG * H * W;
+  const int BN = (bn_req == 64 || bn_req == 128 || bn_req == 256) ? bn_req : (N >= 128 ? 128 : 64);
+  CUtensorMap ta, tb;
+  int rc;
+  {
+    uint64_t d2[2] = {(uint64_t)M, (uint64_t)K};
+    uint64_t s2[1] = {(uint64_t)Cout * 2};
+    uint32_t b2[2] = {64, BK};
+    if ((rc = get_map(&ta, dY, 2, d2, s2, b2))) return rc;
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NIMG};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {64, (uint32_t)W, (uint32_t)TH, (uint32_t)NB};
+    if ((rc = get_map(&tb, X, 4, dims, str, box))) return rc;
+  }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.kb_total = (K + BK - 1) / BK;
+  int splits = split_k > 1 ? split_k : 1;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.out = out; p.ldo = (long long)KH * KW * C; p.out_bf16 = 0; p.alpha = 1.f;
+  p.atomic_add = splits > 1 ? 1 : 0;
+  p.cH = H; p.cW = W; p.cC = C; p.cTH = TH; p.cNB = NB; p.cKW = KW; p.cPadH = pad_h; p.cPadW = pad_w;
+  p.cSplits = splits; p.tap_stride = C;
+  const int gz = KH * KW * splits;
+  if (BN == 64) return dispatch_modes<64>(OP_MNMAJOR, OP_CONV, ta, tb, p, gz, stream);
+  if (BN == 128) return dispatch_modes<128>(OP_MNMAJOR, OP_CONV, ta, tb, p, gz, stream);
+  return dispatch_modes<256>(OP_MNMAJOR, OP_CONV, ta, tb, p, gz, stream);
 }
 
 }  // extern "C"

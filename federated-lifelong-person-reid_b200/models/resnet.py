@@ -211,9 +211,10 @@ class FastResNetHead:
     (stride-2 convolutions), never silently to a different numerics path for the covered ones.
     """
 
-    def __init__(self, model: ResNetReID, shadow=None):
+    def __init__(self, model: ResNetReID, shadow=None, grad_slot=None):
         self.m = model
         self.shadow = shadow or (lambda p: None)
+        self.grad_slot = grad_slot or (lambda p: None)      # param -> its view of the (zeroed) arena gradient
 
     # conv weight as [Cout, KH, KW, Cin] without copying (channels_last storage)
     @staticmethod
@@ -227,13 +228,16 @@ class FastResNetHead:
         sh = self.shadow(w)
         k, s = conv.kernel_size[0], conv.stride[0]
         n, h, wd, c = x.shape
+        gs = self.grad_slot(w)
         if k == 1 and s == 1:
             w2 = self._ohwi(w).reshape(w.shape[0], c)
             s2 = self._ohwi(sh).reshape(w.shape[0], c) if sh is not None else None
-            return gops.linear(x.reshape(-1, c), w2, s2).view(n, h, wd, -1)
+            g2 = self._ohwi(gs).reshape(w.shape[0], c) if gs is not None else None
+            return gops.linear(x.reshape(-1, c), w2, s2, g2).view(n, h, wd, -1)
         if k == 3 and s == 1 and c % 64 == 0 and 128 % wd == 0 and ((h * wd <= 128 and 128 % (h * wd) == 0)
                                                                    or (h * wd > 128 and h % (128 // wd) == 0)):
-            return gops.conv3x3(x, self._ohwi(w), self._ohwi(sh) if sh is not None else None)
+            return gops.conv3x3(x, self._ohwi(w), self._ohwi(sh) if sh is not None else None,
+                                self._ohwi(gs) if gs is not None else None)
         # library fallback (strided convs)
         y = F.conv2d(x.permute(0, 3, 1, 2), (sh if sh is not None else w.to(torch.bfloat16)) if not w.requires_grad
                      else w.to(torch.bfloat16), stride=s, padding=k // 2)
@@ -279,7 +283,7 @@ class FastResNetHead:
         if not m.training:
             return global_feat
         w = m.classifier.weight
-        score = gops.linear(feat, w, self.shadow(w))
+        score = gops.linear(feat, w, self.shadow(w), self.grad_slot(w))
         if m.classifier.bias is not None:
             score = score + m.classifier.bias.to(score.dtype)
         return score, global_feat

@@ -166,10 +166,11 @@ class _BNTrainFn(torch.autograd.Function):
         m, c = x.shape
         dev = x.device
         y = torch.empty_like(x)
-        scratch = torch.zeros(6, c, dtype=torch.float32, device=dev)  # sum, sqsum, mean, rstd, scale, shift
         lib = native.load()
+        scratch = torch.empty(6, c, dtype=torch.float32, device=dev)  # -, -, mean, rstd, scale, shift
+        part = torch.empty(lib.flpr_bn_partials_floats(m, c), dtype=torch.float32, device=dev)
         rc = lib.flpr_bn_fwd(native.ptr(x), native.ptr(gamma), native.ptr(beta), native.ptr(residual), native.ptr(y),
-                             native.ptr(scratch[0]), native.ptr(scratch[1]), native.ptr(scratch[2]),
+                             native.ptr(part), native.ptr(scratch[2]),
                              native.ptr(scratch[3]), native.ptr(scratch[4]), native.ptr(scratch[5]),
                              native.ptr(running_mean), native.ptr(running_var), m, c, eps, momentum, int(relu),
                              native.stream(dev))
@@ -185,15 +186,17 @@ class _BNTrainFn(torch.autograd.Function):
         x, y, gamma, scratch = ctx.saved_tensors
         m, c = x.shape
         dy = dy.contiguous()
-        dgb = torch.zeros(2, c, dtype=torch.float32, device=x.device)
+        dgb = torch.empty(2, c, dtype=torch.float32, device=x.device)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
         lib = native.load()
+        part = torch.empty(lib.flpr_bn_partials_floats(m, c), dtype=torch.float32, device=x.device)
         rc = lib.flpr_bn_bwd(native.ptr(dy), native.ptr(y), native.ptr(x), native.ptr(scratch[2]),
                              native.ptr(scratch[3]), native.ptr(gamma), native.ptr(dgb[0]), native.ptr(dgb[1]),
-                             native.ptr(dres), native.ptr(dx), m, c, int(ctx.relu), native.stream(x.device))
+                             native.ptr(part), native.ptr(dres), native.ptr(dx), m, c, int(ctx.relu),
+                             native.stream(x.device))
         native.check(rc, "flpr_bn_bwd")
-        native.count_launch(2)
+        native.count_launch(3)
         return dx, dgb[0], dgb[1], None, None, dres, None, None, None
 
 

@@ -114,22 +114,27 @@ def conv_nhwc(x: torch.Tensor, w: torch.Tensor, *, padding: int = 1, out_dtype: 
     return out
 
 
-def _auto_split(m: int, n: int, k: int) -> int:
-    """split-K factor for weight-gradient GEMMs (small MxN, very long K)."""
-    tiles = ((m + 127) // 128) * ((n + 127) // 128)
+def _auto_split(m: int, n: int, k: int, taps: int = 1) -> int:
+    """split-K factor for weight-gradient GEMMs (small MxN, very long K): aim for ~1-2 CTAs per SM."""
+    tiles = ((m + 127) // 128) * ((n + 127) // 128) * taps
     kb = (k + 63) // 64
-    if tiles >= 148 or kb < 8:
+    if tiles >= 120 or kb < 8:
         return 1
-    return max(1, min(kb // 4, (2 * 148 + tiles - 1) // tiles))
+    return max(1, min(kb // 4, (148 + tiles - 1) // tiles))
 
 
 class _LinearFn(torch.autograd.Function):
-    """y[M,N] = x[M,K] @ w[N,K]^T using the bf16 compute copy; gradients: dx bf16, dw fp32 (for the fp32 master)."""
+    """y[M,N] = x[M,K] @ w[N,K]^T using the bf16 compute copy; gradients: dx bf16, dw fp32 (for the fp32 master).
+
+    When ``grad_out`` (the parameter's slot in the zeroed arena gradient buffer) is given, the weight gradient is
+    written straight into it by the GEMM epilogue and ``None`` is returned to autograd: no temporary, no
+    ``AccumulateGrad`` read-modify-write pass."""
 
     @staticmethod
-    def forward(ctx, x, w_master, w_bf16):
+    def forward(ctx, x, w_master, w_bf16, grad_out):
         ctx.save_for_backward(x, w_bf16)
         ctx.w_needs_grad = w_master.requires_grad
+        ctx.grad_out = grad_out
         return gemm(x, w_bf16)
 
     @staticmethod
@@ -141,25 +146,33 @@ class _LinearFn(torch.autograd.Function):
             dx = gemm(dy, w, b_kmajor=False)                               # [M,N] x [N,K]
         if ctx.w_needs_grad:
             m, n, k = w.shape[0], w.shape[1], dy.shape[0]
-            dw = gemm(dy, x, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32,
-                      split_k=_auto_split(m, n, k))                        # dy^T x -> [N,K]
-        return dx, dw, None
+            split = _auto_split(m, n, k)
+            if ctx.grad_out is not None:
+                gemm(dy, x, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32, split_k=split, out=ctx.grad_out)
+            else:
+                dw = gemm(dy, x, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32, split_k=split)
+        return dx, dw, None, None
 
 
-def linear(x: torch.Tensor, w_master: torch.Tensor, w_bf16: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Linear / 1x1-conv on flattened NHWC activations. ``w_master`` fp32 ``[out,in]`` receives the gradient."""
+def linear(x: torch.Tensor, w_master: torch.Tensor, w_bf16: Optional[torch.Tensor] = None,
+           grad_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Linear / 1x1-conv on flattened NHWC activations. ``w_master`` fp32 ``[out,in]`` receives the gradient
+    (directly in ``grad_out`` when given - it must be zero on entry)."""
     if w_bf16 is None:
         w_bf16 = w_master.detach().to(torch.bfloat16)
-    return _LinearFn.apply(_bf(x), w_master, w_bf16)
+    if grad_out is not None and not x.is_cuda:
+        grad_out = None
+    return _LinearFn.apply(_bf(x), w_master, w_bf16, grad_out)
 
 
 class _Conv3x3Fn(torch.autograd.Function):
-    """3x3 / stride 1 / pad 1 NHWC convolution. Forward + dgrad on the tcgen05 implicit-GEMM kernel."""
+    """3x3 / stride 1 / pad 1 NHWC convolution: forward, dgrad and wgrad all on the tcgen05 implicit-GEMM kernel."""
 
     @staticmethod
-    def forward(ctx, x, w_master, w_bf16):
+    def forward(ctx, x, w_master, w_bf16, grad_out):
         ctx.save_for_backward(x, w_bf16)
         ctx.w_needs_grad = w_master.requires_grad
+        ctx.grad_out = grad_out
         return conv_nhwc(x, w_bf16, padding=1)
 
     @staticmethod
@@ -172,35 +185,44 @@ class _Conv3x3Fn(torch.autograd.Function):
             wt = w.flip(1, 2).permute(3, 1, 2, 0).contiguous()            # [Cin,KH,KW,Cout]
             dx = conv_nhwc(dy, wt, padding=1)
         if ctx.w_needs_grad:
-            dw = conv3x3_wgrad(x, dy)
-        return dx, dw, None
+            if ctx.grad_out is not None:
+                conv3x3_wgrad(x, dy, out=ctx.grad_out)
+            else:
+                dw = conv3x3_wgrad(x, dy)
+        return dx, dw, None, None
 
 
-def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
-    """dW[Cout,3,3,Cin] (fp32) = sum over pixels of dy (x) shifted x. One MN-major GEMM per filter tap."""
+def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dW[Cout,3,3,Cin] (fp32) = sum over pixels of dy (x) shifted x. ONE launch: grid.z enumerates the 9 filter
+    taps (x split-K); the shifted / zero-padded view of ``x`` is produced by 4-D TMA boxes, nothing is copied."""
     n, h, w, cin = x.shape
     cout = dy.shape[-1]
     if not x.is_cuda:
         xx = x.float().permute(0, 3, 1, 2)
         dd = dy.float().permute(0, 3, 1, 2)
         g = torch.nn.grad.conv2d_weight(xx, (cout, cin, 3, 3), dd, padding=1)
-        return g.permute(0, 2, 3, 1).contiguous()
-    # shifted copies of x (zero padded) feed the MN-major GEMM; 9 taps share one padded buffer
-    xp = F.pad(x, (0, 0, 1, 1, 1, 1))                                      # [N,H+2,W+2,C]
-    dw = torch.zeros((cout, 3, 3, cin), dtype=torch.float32, device=x.device)
-    dy2 = dy.reshape(-1, cout)
-    m = n * h * w
-    split = _auto_split(cout, cin, m)
-    for kh in range(3):
-        for kw in range(3):
-            xs = xp[:, kh:kh + h, kw:kw + w, :].reshape(m, cin)             # gather is a strided copy
-            out_view = dw[:, kh, kw, :]
-            gemm(dy2, xs, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32, split_k=max(split, 2),
-                 out=out_view)
-    return dw
+        g = g.permute(0, 2, 3, 1).contiguous()
+        if out is not None:
+            out.add_(g)
+            return out
+        return g
+    lib = native.load()
+    x, dy = _bf(x).contiguous(), _bf(dy).contiguous()
+    split = _auto_split(cout, cin, n * h * w, taps=9)
+    if out is None:
+        out = torch.zeros((cout, 3, 3, cin), dtype=torch.float32, device=x.device)
+    assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == cout * 9 * cin
+    rc = lib.flpr_conv_wgrad_nhwc_bf16(native.ptr(x), native.ptr(dy), native.ptr(out), n, h, w, cin, cout, 3, 3, 1, 1,
+                                       int(split), 0, native.stream(x.device))
+    native.check(rc, "flpr_conv_wgrad_nhwc_bf16")
+    native.count_launch()
+    return out
 
 
-def conv3x3(x: torch.Tensor, w_master: torch.Tensor, w_bf16: Optional[torch.Tensor] = None) -> torch.Tensor:
+def conv3x3(x: torch.Tensor, w_master: torch.Tensor, w_bf16: Optional[torch.Tensor] = None,
+            grad_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     if w_bf16 is None:
         w_bf16 = w_master.detach().to(torch.bfloat16)
-    return _Conv3x3Fn.apply(_bf(x), w_master, w_bf16)
+    if grad_out is not None and not x.is_cuda:
+        grad_out = None
+    return _Conv3x3Fn.apply(_bf(x), w_master, w_bf16, grad_out)

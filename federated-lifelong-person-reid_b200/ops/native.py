@@ -38,6 +38,7 @@ def _declare(lib: C.CDLL) -> None:
     sig = {
         "flpr_gemm_bf16": [P, P, P, I, I, I, L, L, L, I, I, I, I, F, P, P, I, P, I, I, P],
         "flpr_conv_nhwc_bf16": [P, P, P, I, I, I, I, I, I, I, I, I, I, F, P, I, P, I, P],
+        "flpr_conv_wgrad_nhwc_bf16": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
         "flpr_symm_alloc": [C.POINTER(P), Z],
         "flpr_symm_free": [P],
         "flpr_ipc_get_handle": [P, P],
@@ -56,9 +57,10 @@ def _declare(lib: C.CDLL) -> None:
         "flpr_cast_bf16": [P, P, Z, P],
         "flpr_compose": [P, P, F, P, P, Z, P],
         "flpr_ce_label_smooth": [P, P, P, P, I, I, L, F, F, I, I, P],
-        "flpr_bn_fwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, F, F, I, P],
+        "flpr_bn_fwd": [P, P, P, P, P, P, P, P, P, P, P, P, I, I, F, F, I, P],
         "flpr_affine_act": [P, P, P, P, P, I, I, I, P],
-        "flpr_bn_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, P],
+        "flpr_bn_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
+        "flpr_bn_partials_floats": [I, I],
         "flpr_gap_fwd": [P, P, P, I, I, I, P],
         "flpr_gap_bwd": [P, P, I, I, I, P],
         "flpr_rank_eval": [P, P, P, P, P, I, I, L, P],

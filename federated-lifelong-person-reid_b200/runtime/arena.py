@@ -87,6 +87,11 @@ class ParamArena:
         seg = self._by_id.get(id(p))
         return None if seg is None else self._view(self.shadow, seg)
 
+    def grad_of(self, p: torch.Tensor) -> Optional[torch.Tensor]:
+        """The parameter's view of the flat gradient buffer (kernels may write weight gradients straight into it)."""
+        seg = self._by_id.get(id(p))
+        return None if seg is None else self._view(self.grad, seg)
+
     def refresh_shadow(self) -> None:
         if self.shadow is not None:
             fops.cast_bf16(self.master, self.shadow)

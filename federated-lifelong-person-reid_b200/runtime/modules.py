@@ -66,7 +66,7 @@ class ModelModule(nn.Module):
         if device.type == "cuda" and self.compute_dtype == torch.bfloat16:
             from ..models.resnet import FastResNetHead, ResNetReID
             if isinstance(self.net, ResNetReID) and 1 <= self.net.head_start <= 4:
-                self.net._fast_head = FastResNetHead(self.net, self.arena.shadow_of)
+                self.net._fast_head = FastResNetHead(self.net, self.arena.shadow_of, self.arena.grad_of)
         return self
 
     def autocast(self):

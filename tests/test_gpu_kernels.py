@@ -213,6 +213,40 @@ def test_batch_norm_nhwc(relu, res):
         _close(r.grad, rr.grad, rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(64, 16, 8, 512, 512), (4, 8, 4, 64, 128), (6, 16, 8, 128, 64), (3, 32, 16, 64, 64)])
+def test_conv3x3_wgrad_kernel(n, h, w, cin, cout):
+    from flpr_b200.ops.gemm import conv3x3_wgrad
+    torch.manual_seed(11)
+    x = torch.randn(n, h, w, cin, device="cuda").bfloat16()
+    dy = (torch.randn(n, h, w, cout, device="cuda") / 8).bfloat16()
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, 3, 3), dy.float().permute(0, 3, 1, 2),
+                                      padding=1).permute(0, 2, 3, 1)
+    out = conv3x3_wgrad(x, dy)
+    _close(out, ref, rtol=1e-2, atol=0.02 * ref.abs().max().item())
+    slot = torch.zeros(cout, 3, 3, cin, device="cuda")
+    conv3x3_wgrad(x, dy, out=slot)
+    _close(slot, ref, rtol=1e-2, atol=0.02 * ref.abs().max().item())
+
+
+@pytest.mark.parametrize("m,c", [(64, 2048), (8192, 512), (1000, 96), (37, 64)])
+def test_batch_norm_shapes(m, c):
+    from flpr_b200.ops.fused import batch_norm_nhwc
+    torch.manual_seed(12)
+    x = (torch.randn(m, c, device="cuda") * 1.5 - 0.3).bfloat16().requires_grad_(True)
+    gamma = (torch.rand(c, device="cuda") + 0.5).requires_grad_(True)
+    beta = torch.randn(c, device="cuda").requires_grad_(True)
+    y = batch_norm_nhwc(x, gamma, beta, None, None, training=True, relu=True)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    gr, br = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    yr = torch.relu(torch.nn.functional.batch_norm(xr, None, None, gr, br, training=True))
+    yr.backward(gy.float())
+    _close(y, yr, rtol=2e-2, atol=3e-2)
+    _close(x.grad, xr.grad, rtol=5e-2, atol=0.03 * xr.grad.abs().max().item() + 1e-3)
+    _close(gamma.grad, gr.grad, rtol=2e-2, atol=0.02 * gr.grad.abs().max().item())
+
+
 def test_gap():
     from flpr_b200.ops.fused import global_avg_pool_nhwc
     x = torch.randn(16, 128, 2048, device="cuda").bfloat16().requires_grad_(True)
