@@ -306,17 +306,36 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* x, f
   }
 }
 
-// finalize: fold partials, mean/rstd, running stats (momentum, unbiased var), scale/shift for the apply pass
-__global__ void bn_finalize_kernel(const float* part, int nparts, const float* gamma, const float* beta,
-                                   float* mean, float* rstd, float* scale, float* shift, float* running_mean,
-                                   float* running_var, int M, int C, float eps, float momentum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float sm = 0.f, sq = 0.f;
-  for (int i = 0; i < nparts; ++i) {
-    sm += part[(size_t)i * 2 * C + c];
-    sq += part[(size_t)i * 2 * C + C + c];
+// Fold per-block partials part[nparts][2][C] -> two per-channel sums. blockDim = (32 channels, 8 part-lanes).
+__device__ __forceinline__ void fold_partials(const float* part, int nparts, int C, int c, float& s0, float& s1,
+                                              float (*sh)[8][32]) {
+  float a = 0.f, b = 0.f;
+  if (c < C) {
+    for (int i = threadIdx.y; i < nparts; i += 8) {
+      a += part[(size_t)i * 2 * C + c];
+      b += part[(size_t)i * 2 * C + C + c];
+    }
   }
+  sh[0][threadIdx.y][threadIdx.x] = a;
+  sh[1][threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  s0 = 0.f; s1 = 0.f;
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s0 += sh[0][j][threadIdx.x]; s1 += sh[1][j][threadIdx.x]; }
+  }
+}
+
+// finalize: fold partials, mean/rstd, running stats (momentum, unbiased var), scale/shift for the apply pass
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* part, int nparts, const float* gamma,
+                                                          const float* beta, float* mean, float* rstd, float* scale,
+                                                          float* shift, float* running_mean, float* running_var, int M,
+                                                          int C, float eps, float momentum) {
+  __shared__ float sh[2][8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float sm, sq;
+  fold_partials(part, nparts, C, c, sm, sq, sh);
+  if (threadIdx.y != 0 || c >= C) return;
   const float mu = sm / M;
   float var = sq / M - mu * mu;
   var = fmaxf(var, 0.f);
@@ -330,6 +349,46 @@ __global__ void bn_finalize_kernel(const float* part, int nparts, const float* g
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
     const float unb = (M > 1) ? var * ((float)M / (float)(M - 1)) : var;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+  }
+}
+
+// y = relu?(x * ca[c] + cb[c] (+ residual)); row-strided: every thread keeps its 8 channels' coefficients in
+// registers and walks the rows of its block (grid = (channel groups, row blocks), block = (bx, by)).
+__global__ void __launch_bounds__(256) bn_affine_rows_kernel(const __nv_bfloat16* x, const float* ca, const float* cb,
+                                                             const __nv_bfloat16* residual, __nv_bfloat16* y, int M,
+                                                             int C, int rows_per_block, int relu) {
+  const int c8n = C / 8;
+  const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c8 >= c8n) return;
+  float a[8], b[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { a[t] = ca[c8 * 8 + t]; b[t] = cb[c8 * 8 + t]; }
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, M);
+  const uint4* xp = reinterpret_cast<const uint4*>(x);
+  const uint4* rp = reinterpret_cast<const uint4*>(residual);
+  uint4* yp = reinterpret_cast<uint4*>(y);
+#pragma unroll 2
+  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    const size_t idx = (size_t)r * c8n + c8;
+    uint4 u = xp[idx];
+    uint4 ru = make_uint4(0, 0, 0, 0);
+    if (residual) ru = rp[idx];
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+    const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&ru);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 f = __bfloat1622float2(h[t]);
+      f.x = fmaf(f.x, a[2 * t], b[2 * t]);
+      f.y = fmaf(f.y, a[2 * t + 1], b[2 * t + 1]);
+      if (residual) {
+        const float2 rr = __bfloat1622float2(rh[t]);
+        f.x += rr.x; f.y += rr.y;
+      }
+      if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+      h[t] = __floats2bfloat162_rn(f.x, f.y);
+    }
+    yp[idx] = u;
   }
 }
 
@@ -436,32 +495,50 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
   }
 }
 
-__global__ void bn_fold_partials_kernel(const float* part, int nparts, float* dgamma, float* dbeta, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float g = 0.f, b = 0.f;
-  for (int i = 0; i < nparts; ++i) {
-    g += part[(size_t)i * 2 * C + c];
-    b += part[(size_t)i * 2 * C + C + c];
-  }
+// dgamma / dbeta totals and the coefficients of  dx = ca*dy_eff + cb*x + cc  (cc folded below):
+//   ca = gamma*rstd, cb = -ca*rstd*dgamma/M, cc = -ca*dbeta/M - cb*mean
+__global__ void __launch_bounds__(256) bn_fold_partials_kernel(const float* part, int nparts, const float* gamma,
+                                                               const float* mean, const float* rstd, float* dgamma,
+                                                               float* dbeta, float* coef /* [3][C] */, int M, int C) {
+  __shared__ float sh[2][8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float g, b;
+  fold_partials(part, nparts, C, c, g, b, sh);
+  if (threadIdx.y != 0 || c >= C) return;
   dgamma[c] = g;
   dbeta[c] = b;
+  const float ga = gamma ? gamma[c] : 1.f;
+  const float ca = ga * rstd[c];
+  const float cb = -ca * rstd[c] * g / M;
+  coef[c] = ca;
+  coef[C + c] = cb;
+  coef[2 * C + c] = -ca * b / M - cb * mean[c];
 }
 
-// dx = gamma*rstd * (dy_eff - dbeta/M - xhat * dgamma/M)
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* y,
-                                                           const __nv_bfloat16* x, const float* mean,
-                                                           const float* rstd, const float* gamma,
-                                                           const float* dgamma, const float* dbeta,
-                                                           __nv_bfloat16* dx, size_t total8, int M, int C, int relu) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const float invM = 1.f / M;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += stride) {
-    const int c0 = (int)((i * 8) % C);
-    uint4 du = reinterpret_cast<const uint4*>(dy)[i];
-    const uint4 xu = reinterpret_cast<const uint4*>(x)[i];
+// dx = ca*dy_eff + cb*x + cc ; dy_eff = dy masked by (y > 0) when relu (row-strided like bn_affine_rows_kernel)
+__global__ void __launch_bounds__(256) bn_bwd_rows_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* y,
+                                                          const __nv_bfloat16* x, const float* coef,
+                                                          __nv_bfloat16* dx, int M, int C, int rows_per_block,
+                                                          int relu) {
+  const int c8n = C / 8;
+  const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c8 >= c8n) return;
+  float ca[8], cb[8], cc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { ca[t] = coef[c8 * 8 + t]; cb[t] = coef[C + c8 * 8 + t]; cc[t] = coef[2 * C + c8 * 8 + t]; }
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, M);
+  const uint4* dyp = reinterpret_cast<const uint4*>(dy);
+  const uint4* yp = reinterpret_cast<const uint4*>(y);
+  const uint4* xp = reinterpret_cast<const uint4*>(x);
+  uint4* dxp = reinterpret_cast<uint4*>(dx);
+#pragma unroll 2
+  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    const size_t idx = (size_t)r * c8n + c8;
+    uint4 du = dyp[idx];
+    const uint4 xu = xp[idx];
     uint4 yu = make_uint4(0, 0, 0, 0);
-    if (relu) yu = reinterpret_cast<const uint4*>(y)[i];
+    if (relu) yu = yp[idx];
     __nv_bfloat162* dh = reinterpret_cast<__nv_bfloat162*>(&du);
     const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xu);
     const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&yu);
@@ -474,14 +551,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
         if (o.x <= 0.f) d.x = 0.f;
         if (o.y <= 0.f) d.y = 0.f;
       }
-      const int ca = c0 + 2 * t, cb = ca + 1;
-      const float ga = gamma ? gamma[ca] : 1.f, gb = gamma ? gamma[cb] : 1.f;
-      const float xa = (xv.x - mean[ca]) * rstd[ca], xb = (xv.y - mean[cb]) * rstd[cb];
-      d.x = ga * rstd[ca] * (d.x - dbeta[ca] * invM - xa * dgamma[ca] * invM);
-      d.y = gb * rstd[cb] * (d.y - dbeta[cb] * invM - xb * dgamma[cb] * invM);
+      d.x = fmaf(ca[2 * t], d.x, fmaf(cb[2 * t], xv.x, cc[2 * t]));
+      d.y = fmaf(ca[2 * t + 1], d.y, fmaf(cb[2 * t + 1], xv.y, cc[2 * t + 1]));
       dh[t] = __floats2bfloat162_rn(d.x, d.y);
     }
-    reinterpret_cast<uint4*>(dx)[i] = du;
+    dxp[idx] = du;
   }
 }
 
@@ -655,7 +729,7 @@ static void bn_launch_geometry(int M, int C, dim3& grid, dim3& block, int& rpb) 
 int flpr_bn_partials_floats(int M, int C) {
   dim3 g, b; int rpb;
   bn_launch_geometry(M, C, g, b, rpb);
-  return (int)g.y * 2 * C;
+  return (int)g.y * 2 * C + 3 * C;   // partials + backward coefficients
 }
 
 // `part` is scratch of flpr_bn_partials_floats(M, C) floats (no zeroing needed).
@@ -667,12 +741,11 @@ int flpr_bn_fwd(const void* x, const float* gamma, const float* beta, const void
   dim3 grid, block; int rpb;
   bn_launch_geometry(M, C, grid, block, rpb);
   bn_stats_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), part, M, C, rpb);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, (int)grid.y, gamma, beta, mean, rstd, scale, shift,
-                                                      running_mean, running_var, M, C, eps, momentum);
-  const size_t total8 = (size_t)M * C / 8;
-  bn_apply_kernel<<<grid_for(total8, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), scale, shift,
-                                                         reinterpret_cast<const __nv_bfloat16*>(residual),
-                                                         reinterpret_cast<__nv_bfloat16*>(y), total8, C, relu);
+  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(part, (int)grid.y, gamma, beta, mean, rstd, scale, shift,
+                                                            running_mean, running_var, M, C, eps, momentum);
+  bn_affine_rows_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), scale, shift,
+                                                reinterpret_cast<const __nv_bfloat16*>(residual),
+                                                reinterpret_cast<__nv_bfloat16*>(y), M, C, rpb, relu);
   return (int)cudaGetLastError();
 }
 
@@ -681,10 +754,11 @@ int flpr_affine_act(const void* x, const float* scale, const float* shift, const
                     int relu, cudaStream_t st) {
   bind_device_of(x);
   if (C % 8) return -2;
-  const size_t total8 = (size_t)M * C / 8;
-  bn_apply_kernel<<<grid_for(total8, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), scale, shift,
-                                                         reinterpret_cast<const __nv_bfloat16*>(residual),
-                                                         reinterpret_cast<__nv_bfloat16*>(y), total8, C, relu);
+  dim3 grid, block; int rpb;
+  bn_launch_geometry(M, C, grid, block, rpb);
+  bn_affine_rows_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), scale, shift,
+                                                reinterpret_cast<const __nv_bfloat16*>(residual),
+                                                reinterpret_cast<__nv_bfloat16*>(y), M, C, rpb, relu);
   return (int)cudaGetLastError();
 }
 
@@ -701,13 +775,15 @@ int flpr_bn_bwd(const void* dy, const void* y, const void* x, const float* mean,
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y),
       reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, part, reinterpret_cast<__nv_bfloat16*>(dres), M, C, rpb,
       relu);
-  bn_fold_partials_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, (int)grid.y, dgamma, dbeta, C);
-  const size_t total8 = (size_t)M * C / 8;
-  // the masked dy was materialised in dres when present: the apply pass then needs no ReLU mask of its own
-  bn_bwd_apply_kernel<<<grid_for(total8, 256), 256, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(y),
-      reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, gamma, dgamma, dbeta,
-      reinterpret_cast<__nv_bfloat16*>(dx), total8, M, C, relu);
+  float* coef = part + (size_t)grid.y * 2 * C;
+  bn_fold_partials_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(part, (int)grid.y, gamma, mean, rstd, dgamma, dbeta,
+                                                                 coef, M, C);
+  // when the masked dy was materialised in dres, read it back (no second ReLU-mask pass over y)
+  const __nv_bfloat16* dy_in = dres ? reinterpret_cast<const __nv_bfloat16*>(dres)
+                                    : reinterpret_cast<const __nv_bfloat16*>(dy);
+  bn_bwd_rows_kernel<<<grid, block, 0, st>>>(dy_in, reinterpret_cast<const __nv_bfloat16*>(y),
+                                             reinterpret_cast<const __nv_bfloat16*>(x), coef,
+                                             reinterpret_cast<__nv_bfloat16*>(dx), M, C, rpb, dres ? 0 : relu);
   return (int)cudaGetLastError();
 }
 

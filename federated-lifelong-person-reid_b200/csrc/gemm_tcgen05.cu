@@ -61,13 +61,16 @@ template <int BN>
 struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
+  // BN <= 128: ~100 KB per CTA so that TWO CTAs are resident per SM and one CTA's epilogue overlaps the other's
+  // MMA main loop (TMEM: 2 x 128 columns). BN = 256 keeps a deeper ring with one CTA per SM.
+  static constexpr int STAGES = (BN <= 64) ? 4 : (BN <= 128 ? 3 : 4);
+  static constexpr int MIN_CTAS = (BN <= 128) ? 2 : 1;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem ptr + alignment slack
 };
 
 template <int BN, int A_MODE, int B_MODE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, SmemLayout<BN>::MIN_CTAS)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
   using L = SmemLayout<BN>;
@@ -212,6 +215,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     const float bm = (p.bias_m != nullptr && row < p.M) ? p.bias_m[row] : 0.f;
     const long long tap_off = (B_MODE == OP_CONV) ? (long long)(blockIdx.z / p.cSplits) * p.tap_stride : 0;
+    // bf16 row-major output without residual: stores are staged through smem (pipeline stage 0 is free once the
+    // accumulator barrier has fired) so that each store instruction writes 8 full 64-byte row segments
+    const bool use_stage = p.out_bf16 && !p.trans_out && !p.atomic_add && p.residual == nullptr &&
+                           ((p.ldo & 7) == 0) && (((n0 + tap_off) & 7) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    uint8_t* stage_buf = smem + q * (32 * 80);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -249,7 +258,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               reinterpret_cast<float*>(p.out)[idx] = x;
           }
         }
-      } else if (row < p.M) {
+      } else if (row < p.M || use_stage) {
         const long long base = (long long)row * p.ldo + n0 + c0 + tap_off;
         const bool full = (n0 + c0 + 32 <= p.N);
         if (p.residual != nullptr) {
@@ -284,15 +293,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         } else if (p.out_bf16) {
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + base;
           if (full && ((base & 7) == 0)) {
+            uint4 pk[4];
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              uint4 u;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk[j4]);
 #pragma unroll
               for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j4 * 8 + t * 2], v[j4 * 8 + t * 2 + 1]);
-              reinterpret_cast<uint4*>(o)[j4] = u;
             }
-          } else {
+            if (use_stage) {
+              // transpose through this warp's private staging tile so that 4 lanes write one row's 64 B contiguously
+              uint8_t* st = stage_buf + lane * 80;
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<uint4*>(st + j4 * 16) = pk[j4];
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int rr = 8 * j + (lane >> 2);
+                const uint4 u = *reinterpret_cast<const uint4*>(stage_buf + rr * 80 + (lane & 3) * 16);
+                const int grow = m0 + q * 32 + rr;
+                if (grow < p.M)
+                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)grow * p.ldo + n0 +
+                                            c0 + tap_off + (lane & 3) * 8) = u;
+              }
+              __syncwarp();
+            } else {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) reinterpret_cast<uint4*>(o)[j4] = pk[j4];
+            }
+          } else if (row < p.M) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (n0 + c0 + j < p.N) o[j] = __float2bfloat16(v[j]);
@@ -437,10 +465,9 @@ static int pick_bn(int M, int N, int requested) {
   if (requested == 64 || requested == 128 || requested == 256) return requested;
   // Aim for >= ~1 wave of 148 SMs; prefer the widest tile that still fills the machine.
   const long long mt = (M + BM - 1) / BM;
-  if (N >= 256 && mt * ((N + 255) / 256) >= 148) return 256;
-  if (N >= 128 && mt * ((N + 127) / 128) >= 120) return 128;
+  (void)mt;
   if (N <= 64) return 64;
-  return 128;
+  return 128;   // two resident CTAs per SM hide the epilogue; 256-wide tiles only on request
 }
 
 }  // namespace flpr
