@@ -1,0 +1,129 @@
+"""End-to-end CPU runs of every method through ``ExperimentStage`` (tiny synthetic workload), log / checkpoint
+schema checks, and the world_size=2 gloo plumbing mode (BASELINE.json config 1)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from flpr_b200.runtime.experiment import ExperimentStage, VirtualContainer
+from helpers import tiny_common, tiny_experiment, tiny_factory
+
+ALL = ["baseline", "ewc", "mas", "icarl", "fedavg", "fedprox", "fedcurv", "fedweit", "fedstil", "fedstil-atten"]
+
+
+def _run(tmp_path, method, **over):
+    common = tiny_common(str(tmp_path))
+    cfg = tiny_experiment(common, method, **over)
+    with ExperimentStage(common, [cfg], source_factory=tiny_factory()) as stage:
+        log = stage.run_experiment(cfg)
+    return common, cfg, log
+
+
+@pytest.mark.parametrize("method", ALL)
+def test_method_runs_and_logs(tmp_path, method):
+    common, cfg, log = _run(tmp_path, method)
+    data = log.records["data"]
+    assert set(data) == {"client-0", "client-1"}
+    for client, rounds in data.items():
+        assert set(rounds) == {"0", "1", "2"}
+        r1 = rounds["1"]
+        task = next(iter(t for t in r1 if "tr_acc" in r1[t]))
+        assert {"tr_acc", "tr_loss", "val_rank_1", "val_rank_3", "val_rank_5", "val_rank_10", "val_map"} <= set(r1[task])
+        assert all(0.0 <= r1[task][k] <= 1.0 for k in ("tr_acc", "val_rank_1", "val_map"))
+    saved = json.load(open(log.save_path))
+    assert saved["config"]["exp_method"] == method and "perf" in saved
+
+
+def test_fedavg_checkpoint_and_payload_schemas(tmp_path):
+    common, cfg, _ = _run(tmp_path, "fedavg")
+    root = os.path.join(common["checkpoints_dir"], cfg["exp_name"])
+    model = torch.load(os.path.join(root, "client-0", "fedavg_model.ckpt"), weights_only=False)
+    assert "net.base.layer4.0.conv1.weight" in model and "net.classifier.weight" in model        # 'net.' prefix
+    up = torch.load(os.path.join(root, "client-0", "2-client-0-server.ckpt"), weights_only=False)
+    assert set(up) == {"train_cnt", "incremental_model_params"}
+    assert "base.layer4.1.conv2.weight" in up["incremental_model_params"]
+    assert up["incremental_model_params"]["classifier.weight"].shape == (8000, 512)
+    down1 = torch.load(os.path.join(root, "server", "1-server-client-0.ckpt"), weights_only=False)
+    down2 = torch.load(os.path.join(root, "server", "2-server-client-0.ckpt"), weights_only=False)
+    assert set(down1) == {"integrated_model_params"} and set(down2) == {"incremental_model_params"}
+
+
+def test_fedstil_checkpoint_schema(tmp_path):
+    common, cfg, _ = _run(tmp_path, "fedstil")
+    root = os.path.join(common["checkpoints_dir"], cfg["exp_name"])
+    m = torch.load(os.path.join(root, "client-1", "fedstil_model.ckpt"), weights_only=False)
+    assert set(m) == {"global_weight", "global_weight_atten", "adaptive_weights", "adaptive_bias", "bn_params",
+                      "pre_trained_params"}
+    assert "classifier.global_weight" in m["global_weight"] and "base.conv1.weight" in m["pre_trained_params"]
+    assert m["global_weight_atten"]["base.layer4.0.conv1.global_weight_atten"].shape == (3,)      # kernel width
+    g, a = m["global_weight"]["classifier.global_weight"], m["adaptive_weights"]["classifier.adaptive_weight"]
+    assert g.shape == a.shape == (8000, 512)
+    ex = torch.load(os.path.join(root, "client-1", "fedstil_model_examplars.ckpt"), weights_only=False)
+    pid, protos = next(iter(ex.items()))
+    assert protos[0][0].shape == (256, 2, 1) and isinstance(protos[0][1], int)
+    up = torch.load(os.path.join(root, "client-1", "2-client-1-server.ckpt"), weights_only=False)
+    assert set(up) == {"train_cnt", "task_token", "incremental_sw", "incremental_bn"}
+    assert up["task_token"].numel() == 256 * 2 * 1
+    toks = torch.load(os.path.join(root, "server", "server_tokens.ckpt"), weights_only=False)
+    assert set(toks) == {"client-0", "client-1"} and len(toks["client-0"]) == 2
+
+
+def test_fedavg_aggregation_uses_stale_uploads(tmp_path):
+    """online_clients < K: the mean runs over every registered client's LAST upload (fedavg.py:386-397)."""
+    from flpr_b200.methods.fedavg import Server
+    common = tiny_common(str(tmp_path))
+    cfg = tiny_experiment(common, "fedavg", n_clients=3)
+    with ExperimentStage(common, [cfg], source_factory=tiny_factory()) as stage:
+        store, comm, server, clients, names = stage.build(cfg)
+        n = clients[0].upload_numel()
+        vals = {0: 1.0, 1: 2.0, 2: 4.0}
+        for c in clients:
+            server.register_client(c.client_name)
+        for c in clients[:2]:
+            c.model.arena.master.fill_(vals[c.client_id]); c.train_cnt = 10
+            server.set_client_incremental_state(c.client_name, c.get_incremental_state())
+        server.calculate()
+        assert torch.allclose(comm.rank_view("glob"), torch.full((n,), 1.5))
+        c = clients[2]; c.model.arena.master.fill_(4.0); c.train_cnt = 20
+        server.set_client_incremental_state(c.client_name, c.get_incremental_state())
+        server.calculate()                                  # clients 0/1 did not upload again: stale states count
+        assert torch.allclose(comm.rank_view("glob"), torch.full((n,), (10 * 1 + 10 * 2 + 20 * 4) / 40))
+        store.close()
+
+
+def test_virtual_container():
+    vc = VirtualContainer(["cuda:0", "cuda:1"], parallel=2)
+    assert vc.max_worker() == 4
+    with vc.possess_device() as d0:
+        with vc.possess_device(vc.max_worker()) as d1:      # clamped: never negative, never None
+            assert d0 is not None and d1 is not None and d0 != d1
+    assert vc.devices == vc.capacity
+
+
+def test_gloo_world2_fedavg_plumbing(tmp_path):
+    """BASELINE.json config 1: fedavg, 2 clients, 1 task, world_size=2 on CPU."""
+    script = os.path.join(os.path.dirname(__file__), "dist_e2e_check.py")
+    env = dict(os.environ, FLPR_TMP=str(tmp_path), OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
+                        "--nproc-per-node", "2", script, "fedavg"], env=env, capture_output=True, text=True, timeout=600)
+    assert "DIST_E2E OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_cli_synthetic(tmp_path):
+    import yaml
+    common = tiny_common(str(tmp_path))
+    common["defaults"]["exp_opts"]["comm_rounds"] = 1
+    cp = tmp_path / "common.yaml"
+    yaml.safe_dump(common, open(cp, "w"))
+    exp = {"exp_name": "cli", "exp_method": "fedavg", "server": {"server_name": "server"},
+           "clients": [{"client_name": "client-0", "tasks": ["task-0-0"]}, {"client_name": "client-1", "tasks": ["task-1-0"]}]}
+    ep = tmp_path / "exp.yaml"
+    yaml.safe_dump(exp, open(ep, "w"))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "main.py"), "--common", str(cp), "--experiments", str(ep),
+                        "--synthetic"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert any(f.startswith("cli-") for f in os.listdir(tmp_path / "logs"))
