@@ -223,7 +223,7 @@ def run_flpr(a, impl: str) -> dict:
         for _ in range(a.steps):
             r += 1
             one_round(r)
-            store.flush()                       # checkpoints of the round are on disk before the clock stops
+        store.flush()                           # every checkpoint of these rounds is on disk before the clock stops
         sync()
         e2e_ms = (time.perf_counter() - t0) * 1e3
         after_round()
@@ -239,7 +239,7 @@ def run_flpr(a, impl: str) -> dict:
             launches, h2d = int(sm[2].item()), sm[3].item()
         else:
             h2d = float(h2d1 - h2d0)
-        phases = {k: round(sum(v) / max(len(v), 1), 3) for k, v in timer.flush().items()}
+        phases = {k: round(sum(v[-2 * a.steps:]) / max(len(v[-2 * a.steps:]), 1), 3) for k, v in timer.flush().items()}
         comm_bytes = comm.bytes_moved if comm is not None else 0
         store.close()
         if comm is not None:

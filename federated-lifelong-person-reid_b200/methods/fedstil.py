@@ -283,18 +283,30 @@ class Operator(OperatorModule):
         model.eval()
         protos, pids, cids = [], [], []
         folded = model.folded_trunk()
+        chunk = int(getattr(model, "trunk_batch", 256))         # the frozen trunk is inference-only: batch it wider
+        pend: List[torch.Tensor] = []
+
+        def flush():
+            if pend:
+                big = torch.cat(pend) if len(pend) > 1 else pend[0]
+                protos.append(folded(big).clone())             # graph-owned output buffer -> keep a copy
+                pend.clear()
+
         for data, person_id, classes_id in source_loader:
             data = model.prepare_input(data)
             if folded is not None:
-                fmap = folded(data).clone()                    # graph-owned output buffer -> keep a copy
+                pend.append(data)
+                if sum(d.shape[0] for d in pend) >= chunk:
+                    flush()
             else:
                 with model.autocast():
                     fmap = model.forward_trunk(data)
                 if model.compute_dtype == torch.bfloat16:
                     fmap = fmap.to(torch.bfloat16)
-            protos.append(fmap)
+                protos.append(fmap)
             pids.append(person_id.to(model.device))
             cids.append(classes_id.to(model.device))
+        flush()
         protos, pids, cids = torch.cat(protos), torch.cat(pids), torch.cat(cids)
         task_token = protos.float().flatten(1).mean(0)
         ex = model.examplar_tensors()

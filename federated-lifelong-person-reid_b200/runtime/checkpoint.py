@@ -79,7 +79,8 @@ def _writer_main(jobs, done) -> None:  # pragma: no cover  (runs in a child proc
                 state = POST[post](state)
             os.makedirs(os.path.dirname(path), exist_ok=True)
             tmp = f"{path}.tmp{os.getpid()}"
-            torch.save(state, tmp)
+            # legacy (non-zip) container: no per-record CRC32 pass over hundreds of MB; torch.load reads both formats
+            torch.save(state, tmp, _use_new_zipfile_serialization=False)
             os.replace(tmp, path)
         except BaseException as ex:
             err = f"{type(ex).__name__}: {ex}"
@@ -107,7 +108,7 @@ class _Slab:
 class CheckpointStore:
     """One instance per process; actors address it with ``(actor_name, state_name)``."""
 
-    def __init__(self, root: str, asynchronous: bool = True, enabled: bool = True, workers: int = 4,
+    def __init__(self, root: str, asynchronous: bool = True, enabled: bool = True, workers: int = 6,
                  max_inflight_bytes: int = 24 << 30):
         self.root = root
         self.enabled = enabled

@@ -140,7 +140,7 @@ class ExperimentStage:
         names = [c["client_name"] for c in exp_config["clients"]]
         store = CheckpointStore(os.path.join(self.common_config["checkpoints_dir"], exp_config["exp_name"]),
                                 asynchronous=eng.get("async_checkpoint", True) and self.device.type == "cuda",
-                                enabled=eng.get("checkpoints", True), workers=eng.get("ckpt_workers", 4))
+                                enabled=eng.get("checkpoints", True), workers=eng.get("ckpt_workers", 6))
         server = parser_server(exp_config, self.common_config, self.device, store)
         clients = parser_clients(exp_config, self.common_config, self.device, store, None, self.rank, self.world,
                                  self.source_factory)
