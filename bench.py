@@ -180,6 +180,8 @@ def run_flpr(a, impl: str) -> dict:
 
         def one_round(r):
             stage._process_one_round(r, server, clients, names, cfg, log, timer, comm)
+            if rank == 0 and r % 2 == 0:        # bound the RAM disk: drop payload files of finished rounds
+                cleanup_payloads(common["checkpoints_dir"])
 
         def after_round():
             store.flush()
