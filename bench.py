@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--model", default="resnet50")
     ap.add_argument("--height", type=int, default=256)
     ap.add_argument("--width", type=int, default=128)
+    ap.add_argument("--parallel", type=int, default=3,
+                    help="clients trained concurrently per device (common.yaml `parallel`; the reference arm keeps its "
+                         "shipped default of 1)")
     ap.add_argument("--no-ckpt", action="store_true", help="disable checkpoint files (not the headline config)")
     ap.add_argument("--cpu-debug", action="store_true", help="tiny CPU run to exercise the harness")
     return ap.parse_args()
@@ -104,7 +107,7 @@ def build_config(a, impl: str, world: int):
     """Common + experiment config (same numbers for both arms)."""
     root = ckpt_root()
     common = {"datasets_dir": os.path.join(root, "data"), "checkpoints_dir": os.path.join(root, "ckpts"),
-              "logs_dir": os.path.join(root, "logs"), "parallel": 1,
+              "logs_dir": os.path.join(root, "logs"), "parallel": 1 if impl == "reference" else max(1, a.parallel),
               "device": ["cpu"] if a.cpu_debug else [f"cuda:{i}" for i in range(max(a.gpus, 1))],
               "defaults": {}}
     exp = {
@@ -260,7 +263,9 @@ def run_flpr(a, impl: str) -> dict:
         "config": {"model": a.model, "method": "fedstil", "clients": a.clients, "global_batch": a.batch * a.clients,
                    "batch_per_client": a.batch, "images_per_client_task": a.images, "ids_per_task": a.ids,
                    "seq_len": None, "img_size": [a.height, a.width], "epochs_per_round": a.epochs,
-                   "rehearsal_lambda_k": a.images, "parallelism": f"client-per-rank x{a.gpus} (8 clients round-robin)",
+                   "rehearsal_lambda_k": a.images,
+                   "parallelism": f"client-per-rank x{a.gpus} (8 clients round-robin, {a.parallel} concurrent client "
+                                  f"streams per GPU)",
                    "step_definition": "one federated round: dispatch(mix) + local train of all clients + upload + "
                                       "aggregate; checkpoints " + ("off" if a.no_ckpt else "on (async writer, RAM disk)"),
                    "l2": "inputs larger than L2 (per-round working set >> 126 MB: 8 x 400 MB client state + images)"},

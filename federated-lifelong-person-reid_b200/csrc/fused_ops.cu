@@ -636,6 +636,137 @@ __global__ void __launch_bounds__(256) rank_eval_kernel(const float* S, const lo
   if (threadIdx.x == 0) { out_ap[q] = s_ap; out_first[q] = s_first; }
 }
 
+
+// ----------------------------------------------------------------------------- input pipeline: fused augmentation
+// uint8 NHWC crops -> normalise -> horizontal flip -> random erasing (value 0) -> bf16 / fp32 NHWC, one pass.
+// Reference: datasets/image_augmentation.py:6-71 (ToTensor, Normalize, RandomHorizontalFlip, RandomErasing).
+// u: [7][B] uniforms in [0,1) (flip, erase-select, area, log-ratio, top, left, spare); the per-sample rectangle is
+// derived here exactly as torchvision does (area in `scale`, aspect log-uniform in `ratio`, one attempt).
+struct AugArgs {
+  const uint8_t* in;
+  void* out;
+  const float* u;
+  int B, H, W;
+  float mean[3], inv_std[3];
+  float flip_p, erase_p, s0, s1, lr0, lr1;
+  int out_bf16;
+};
+
+__global__ void __launch_bounds__(256) augment_u8_kernel(const AugArgs a) {
+  const int b = blockIdx.y;
+  const int quads_per_img = a.H * (a.W / 4);
+  __shared__ int s_flip, s_sel, s_top, s_left, s_eh, s_ew;
+  if (threadIdx.x == 0) {
+    const float* u = a.u + b;
+    const int B = a.B;
+    s_flip = u[0] < a.flip_p;
+    s_sel = u[1 * B] < a.erase_p;
+    const float area = (u[2 * B] * (a.s1 - a.s0) + a.s0) * a.H * a.W;
+    const float ar = __expf(u[3 * B] * (a.lr1 - a.lr0) + a.lr0);
+    const float eh = fminf(fmaxf(rintf(sqrtf(area * ar)), 1.f), (float)(a.H - 1));
+    const float ew = fminf(fmaxf(rintf(sqrtf(area / ar)), 1.f), (float)(a.W - 1));
+    s_eh = (int)eh;
+    s_ew = (int)ew;
+    s_top = (int)floorf(u[4 * B] * (a.H - eh + 1.f));
+    s_left = (int)floorf(u[5 * B] * (a.W - ew + 1.f));
+  }
+  __syncthreads();
+  const int flip = s_flip, sel = s_sel, top = s_top, left = s_left, eh = s_eh, ew = s_ew;
+  const uint8_t* src = a.in + (size_t)b * a.H * a.W * 3;
+  for (int qd = blockIdx.x * blockDim.x + threadIdx.x; qd < quads_per_img; qd += gridDim.x * blockDim.x) {
+    const int y = qd / (a.W / 4);
+    const int x0 = (qd - y * (a.W / 4)) * 4;
+    const int sx0 = flip ? (a.W - 4 - x0) : x0;                     // 4 source pixels (12 B, 4-byte aligned)
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(src + ((size_t)y * a.W + sx0) * 3);
+    const uint32_t w0 = sp[0], w1 = sp[1], w2 = sp[2];
+    uint8_t px[12];
+    *reinterpret_cast<uint32_t*>(px) = w0;
+    *reinterpret_cast<uint32_t*>(px + 4) = w1;
+    *reinterpret_cast<uint32_t*>(px + 8) = w2;
+    float v[12];
+    const bool yin = sel && y >= top && y < top + eh;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int si = flip ? (3 - i) : i;
+      const int x = x0 + i;
+      const bool erase = yin && x >= left && x < left + ew;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        v[i * 3 + c] = erase ? 0.f : ((float)px[si * 3 + c] - a.mean[c]) * a.inv_std[c];
+    }
+    const size_t o = ((size_t)b * a.H * a.W + (size_t)y * a.W + x0) * 3;
+    if (a.out_bf16) {
+      __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) op[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    } else {
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + o);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- herding (iCaRL exemplar selection)
+// One block per identity. feats [n_total, D] fp32, rows of identity g are idx[g*nmax .. g*nmax+cnt[g]).
+// Step t picks argmin_i || mean - (S + f_i)/(t+1) ||  <=>  argmin_i ( |f_i|^2 - 2 f_i . c ),  c = (t+1) mean - S
+// (duplicates allowed, first index wins ties) - methods/fedstil.py:378-395, methods/icarl.py:122-139.
+// The whole m-step loop runs inside the kernel: no per-step launches, no host round trips.
+__global__ void __launch_bounds__(256) herding_kernel(const float* feats, const long long* idx, const int* cnt,
+                                                      long long* picks, int nmax, int D, int m) {
+  extern __shared__ float sh[];          // mean[D] | S[D] | c[D] | score[nmax] | sq[nmax]
+  float* mean = sh;
+  float* S = sh + D;
+  float* c = sh + 2 * D;
+  float* score = sh + 3 * D;
+  float* sq = score + nmax;
+  __shared__ int s_best;
+  const int g = blockIdx.x;
+  const int n = cnt[g];
+  const long long* rows = idx + (size_t)g * nmax;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int d = tid; d < D; d += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += feats[(size_t)rows[i] * D + d];
+    mean[d] = n > 0 ? s / n : 0.f;
+    S[d] = 0.f;
+  }
+  for (int i = warp; i < n; i += nwarps) {
+    const float* f = feats + (size_t)rows[i] * D;
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) s = fmaf(f[d], f[d], s);
+    s = warp_sum(s);
+    if (lane == 0) sq[i] = s;
+  }
+  __syncthreads();
+  for (int t = 0; t < m; ++t) {
+    for (int d = tid; d < D; d += blockDim.x) c[d] = (t + 1) * mean[d] - S[d];
+    __syncthreads();
+    for (int i = warp; i < n; i += nwarps) {
+      const float* f = feats + (size_t)rows[i] * D;
+      float s = 0.f;
+      for (int d = lane; d < D; d += 32) s = fmaf(f[d], c[d], s);
+      s = warp_sum(s);
+      if (lane == 0) score[i] = sq[i] - 2.f * s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int best = 0;
+      float bv = n > 0 ? score[0] : 0.f;
+      for (int i = 1; i < n; ++i)
+        if (score[i] < bv) { bv = score[i]; best = i; }
+      s_best = best;
+      picks[(size_t)g * m + t] = best;
+    }
+    __syncthreads();
+    if (n > 0) {
+      const float* f = feats + (size_t)rows[s_best] * D;
+      for (int d = tid; d < D; d += blockDim.x) S[d] += f[d];
+    }
+    __syncthreads();
+  }
+}
+
 static inline int grid_for(size_t n_items, int threads, int cap = 148 * 8) {
   size_t b = (n_items + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -733,16 +864,24 @@ int flpr_bn_partials_floats(int M, int C) {
 }
 
 // `part` is scratch of flpr_bn_partials_floats(M, C) floats (no zeroing needed).
+// pre_part / pre_nparts: column partials [pre_nparts][2][C] already produced by the convolution's epilogue
+// (gemm_tcgen05.cu, `col_part`): the statistics pass over x is skipped.
 int flpr_bn_fwd(const void* x, const float* gamma, const float* beta, const void* residual, void* y, float* part,
                 float* mean, float* rstd, float* scale, float* shift, float* running_mean,
-                float* running_var, int M, int C, float eps, float momentum, int relu, cudaStream_t st) {
+                float* running_var, int M, int C, float eps, float momentum, int relu, const float* pre_part,
+                int pre_nparts, cudaStream_t st) {
   bind_device_of(x);
   if (C % 8) return -2;
   dim3 grid, block; int rpb;
   bn_launch_geometry(M, C, grid, block, rpb);
-  bn_stats_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), part, M, C, rpb);
-  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(part, (int)grid.y, gamma, beta, mean, rstd, scale, shift,
-                                                            running_mean, running_var, M, C, eps, momentum);
+  if (pre_part != nullptr && pre_nparts > 0) {
+    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(pre_part, pre_nparts, gamma, beta, mean, rstd, scale,
+                                                              shift, running_mean, running_var, M, C, eps, momentum);
+  } else {
+    bn_stats_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), part, M, C, rpb);
+    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(part, (int)grid.y, gamma, beta, mean, rstd, scale,
+                                                              shift, running_mean, running_var, M, C, eps, momentum);
+  }
   bn_affine_rows_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), scale, shift,
                                                 reinterpret_cast<const __nv_bfloat16*>(residual),
                                                 reinterpret_cast<__nv_bfloat16*>(y), M, C, rpb, relu);
@@ -813,6 +952,41 @@ int flpr_rank_eval(const float* S, const long long* qlab, const long long* glab,
     configured = true;
   }
   rank_eval_kernel<<<Q, 256, smem, st>>>(S, qlab, glab, out_ap, out_first, G, lds);
+  return (int)cudaGetLastError();
+}
+
+// in: uint8 [B,H,W,3]; out: bf16 / fp32 [B,H,W,3]; u: fp32 [7][B] uniforms; mean / inv_std in 0..255 units.
+int flpr_augment_u8(const void* in, void* out, const float* u, int B, int H, int W, const float* mean3,
+                    const float* inv_std3, float flip_p, float erase_p, float s0, float s1, float r0, float r1,
+                    int out_bf16, cudaStream_t st) {
+  bind_device_of(in);
+  if (W % 4) return -2;
+  if (B <= 0) return 0;
+  AugArgs a;
+  a.in = reinterpret_cast<const uint8_t*>(in); a.out = out; a.u = u; a.B = B; a.H = H; a.W = W;
+  for (int c = 0; c < 3; ++c) { a.mean[c] = mean3[c]; a.inv_std[c] = inv_std3[c]; }
+  a.flip_p = flip_p; a.erase_p = erase_p; a.s0 = s0; a.s1 = s1; a.lr0 = logf(r0); a.lr1 = logf(r1);
+  a.out_bf16 = out_bf16;
+  const int quads = H * (W / 4);
+  int gx = (quads + 255) / 256;
+  if (gx > 16) gx = 16;
+  augment_u8_kernel<<<dim3(gx, B), 256, 0, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+// picks [P, m] (positions within each identity's row list). feats fp32 [n, D], idx int64 [P, nmax], cnt int32 [P].
+int flpr_herding(const float* feats, const long long* idx, const int* cnt, long long* picks, int P, int nmax, int D,
+                 int m, cudaStream_t st) {
+  bind_device_of(feats);
+  if (P <= 0 || m <= 0) return 0;
+  const size_t smem = (size_t)(3 * D + 2 * nmax) * sizeof(float);
+  if (smem > 200 * 1024) return -3;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(herding_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  herding_kernel<<<P, 256, smem, st>>>(feats, idx, cnt, picks, nmax, D, m);
   return (int)cudaGetLastError();
 }
 

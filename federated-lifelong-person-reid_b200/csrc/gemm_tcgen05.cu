@@ -21,6 +21,7 @@
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -30,7 +31,7 @@
 
 namespace flpr {
 
-enum { OP_KMAJOR = 0, OP_MNMAJOR = 1, OP_CONV = 2 };
+enum { OP_KMAJOR = 0, OP_MNMAJOR = 1, OP_CONV = 2, OP_TAPFLIP = 3 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
@@ -55,6 +56,11 @@ struct GemmParams {
   // conv geometry (A operand in OP_CONV mode)
   int cH, cW, cC, cTH, cNB, cKW, cPadH, cPadW, cTilesPerImg, cSplits;
   long long tap_stride;  // conv wgrad: output column offset per filter tap
+  int cTaps;             // KH*KW (OP_TAPFLIP: B column offset = (cTaps-1-tap) * N)
+  // persistent scheduling
+  int tiles_m, tiles_n, tiles_z, tiles_total;
+  // fused batch-norm statistics: per (m-tile, epilogue-warp) column partials of sum / sum^2 of the fp32 accumulators
+  float* col_part;       // [tiles_m * 4][2][N] or nullptr
 };
 
 template <int BN>
@@ -69,6 +75,261 @@ struct SmemLayout {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem ptr + alignment slack
 };
 
+// Persistent variant: ring + a dedicated store-staging area (the ring is never idle) + 2 accumulator stages in TMEM.
+template <int BN>
+struct PersistLayout {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN <= 128) ? 3 : 4;
+  static constexpr int MIN_CTAS = (BN <= 128) ? 2 : 1;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS = ACC_STAGES * BN;                 // 128/256/512 columns
+  static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;         // 4 epilogue warps x 32 rows x 80 B
+  static constexpr int STORE_BYTES = 4 * 32 * 80;
+  static constexpr int BAR_OFFSET = STORE_OFFSET + STORE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+// ------------------------------------------------------------------------------------------------- shared pieces
+// TMA loads of one K-block (BK = 64) of both operands into one ring stage.
+template <int BN, int A_MODE, int B_MODE>
+__device__ __forceinline__ void load_kblock(const GemmParams& p, const CUtensorMap* tmA, const CUtensorMap* tmB,
+                                            uint8_t* sa, uint8_t* sb, uint64_t* bar, int kb, int mt, int m0, int n0,
+                                            int ztap) {
+  int tapA = 0;
+  if constexpr (A_MODE == OP_KMAJOR) {
+    tma_load_2d(sa, tmA, bar, kb * BK, m0);
+  } else if constexpr (A_MODE == OP_MNMAJOR) {
+    tma_load_2d(sa, tmA, bar, m0, kb * BK);
+    tma_load_2d(sa + 64 * 128, tmA, bar, m0 + 64, kb * BK);
+  } else {
+    const int chunks = p.cC / BK;
+    tapA = kb / chunks;
+    const int cc = kb - tapA * chunks;
+    const int kh = tapA / p.cKW;
+    const int kw = tapA - kh * p.cKW;
+    int img0, h0;
+    if (p.cTilesPerImg <= 1) {
+      img0 = mt * p.cNB;
+      h0 = 0;
+    } else {
+      img0 = mt / p.cTilesPerImg;
+      h0 = (mt - img0 * p.cTilesPerImg) * p.cTH;
+    }
+    tma_load_4d(sa, tmA, bar, cc * BK, kw - p.cPadW, h0 + kh - p.cPadH, img0);
+  }
+  if constexpr (B_MODE == OP_KMAJOR) {
+    tma_load_2d(sb, tmB, bar, kb * BK, n0);
+  } else if constexpr (B_MODE == OP_MNMAJOR) {
+#pragma unroll
+    for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 64 * 128, tmB, bar, n0 + j * 64, kb * BK);
+  } else if constexpr (B_MODE == OP_TAPFLIP) {
+    // data-gradient of a convolution straight from the forward weight W[Cout, taps, Cin]: for A tap t the B operand
+    // is W[:, taps-1-t, :] viewed as [K = Cout rows (stride taps*Cin), N = Cin contiguous] -> no flipped copy.
+    const int chunks = p.cC / BK;                         // A channels (= Cout of the forward conv) per tap
+    const int cc = kb - tapA * chunks;
+    const int col0 = (p.cTaps - 1 - tapA) * p.N + n0;
+#pragma unroll
+    for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 64 * 128, tmB, bar, col0 + j * 64, cc * BK);
+  } else {
+    // weight-gradient of a convolution: K runs over pixels (64 per block), the filter tap (ztap) shifts the 4-D
+    // box, zero padding comes from TMA out-of-bounds fill
+    const int kh = ztap / p.cKW;
+    const int kw = ztap - kh * p.cKW;
+    const int p0 = kb * BK;
+    const int hw = p.cH * p.cW;
+    const int img = p0 / hw;
+    const int h0 = (p0 - img * hw) / p.cW;
+#pragma unroll
+    for (int j = 0; j < BN / 64; ++j)
+      tma_load_4d(sb + j * 64 * 128, tmB, bar, n0 + j * 64, kw - p.cPadW, h0 + kh - p.cPadH, img);
+  }
+}
+
+// The four UMMA_K = 16 steps of one K-block. Called by ONE thread.
+template <int BN, int A_MODE, int B_MODE>
+__device__ __forceinline__ void mma_kblock(uint32_t sa, uint32_t tmem_acc, bool first_kb) {
+  constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MODE == OP_MNMAJOR, B_MODE != OP_KMAJOR);
+  const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+  for (int k = 0; k < BK / UMMA_K; ++k) {
+    uint64_t da, db;
+    if constexpr (A_MODE == OP_MNMAJOR)
+      da = make_smem_desc_sw128(sa + k * (UMMA_K * 128), 64 * 128, 1024);
+    else
+      da = make_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
+    if constexpr (B_MODE != OP_KMAJOR)
+      db = make_smem_desc_sw128(sb + k * (UMMA_K * 128), 64 * 128, 1024);
+    else
+      db = make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
+    umma_f16(tmem_acc, da, db, idesc, (!first_kb || k != 0) ? 1u : 0u);
+  }
+}
+
+// Column sums over the 32 rows held by a warp (lane = row, v[j] = column j) with a butterfly of 31 shuffles:
+// afterwards v[0] on lane l is the total of column l.
+__device__ __forceinline__ void warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = up ? v[j] : v[j + s];
+      const float keep = up ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
+// Epilogue of one 128 x BN tile by the 4 epilogue warps (q = TMEM lane quarter): TMEM -> registers -> alpha / bias /
+// residual / ReLU -> global (bf16 / fp32 / transposed / atomic). `have_acc` false means the accumulator is zero.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, bool have_acc, int mt, int m0,
+                                              int n0, long long tap_off, int q, int lane, uint8_t* stage_buf) {
+  const int row = m0 + q * 32 + lane;
+  const float bm = (p.bias_m != nullptr && row < p.M) ? p.bias_m[row] : 0.f;
+  // bf16 row-major output without residual: stores are staged through smem so that each store instruction writes
+  // 8 full 64-byte row segments
+  const bool use_stage = p.out_bf16 && !p.trans_out && !p.atomic_add && p.residual == nullptr &&
+                         ((p.ldo & 7) == 0) && (((n0 + tap_off) & 7) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    if (have_acc) {
+      tmem_ld_32x32b_x32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c0), r);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = 0u;
+    }
+    if (n0 + c0 >= p.N) continue;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = __uint_as_float(r[j]) * p.alpha + bm;
+      const int col = n0 + c0 + j;
+      if (p.bias_n != nullptr && col < p.N) x += p.bias_n[col];
+      v[j] = x;
+    }
+    if (p.col_part != nullptr) {
+      // fused batch-norm statistics of the raw fp32 conv output (rows >= M are exact zeros: TMA OOB fill)
+      float s1[32], s2[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { s1[j] = v[j]; s2[j] = v[j] * v[j]; }
+      warp_colsum32(s1, lane);
+      warp_colsum32(s2, lane);
+      const int col = n0 + c0 + lane;
+      if (col < p.N) {
+        float* dst = p.col_part + ((size_t)(mt * 4 + q) * 2) * p.N + col;
+        dst[0] = s1[0];
+        dst[p.N] = s2[0];
+      }
+    }
+    if (p.trans_out) {
+      // out[col * ldo + row]: lanes are contiguous in memory -> coalesced per column
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = n0 + c0 + j;
+        if (row < p.M && col < p.N) {
+          const long long idx = (long long)col * p.ldo + row;
+          float x = v[j];
+          if (p.residual != nullptr) x += __bfloat162float(p.residual[idx]);
+          if (p.relu) x = fmaxf(x, 0.f);
+          if (p.atomic_add)
+            atomicAdd(reinterpret_cast<float*>(p.out) + idx, x);
+          else if (p.out_bf16)
+            reinterpret_cast<__nv_bfloat16*>(p.out)[idx] = __float2bfloat16(x);
+          else
+            reinterpret_cast<float*>(p.out)[idx] = x;
+        }
+      }
+    } else if (row < p.M || use_stage) {
+      const long long base = (long long)row * p.ldo + n0 + c0 + tap_off;
+      const bool full = (n0 + c0 + 32 <= p.N);
+      if (p.residual != nullptr && row < p.M) {
+        if (full && ((base & 7) == 0)) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + base);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint4 u = rp[j4];
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float2 f = __bfloat1622float2(h[t]);
+              v[j4 * 8 + t * 2] += f.x;
+              v[j4 * 8 + t * 2 + 1] += f.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) v[j] += __bfloat162float(p.residual[base + j]);
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.atomic_add) {
+        float* o = reinterpret_cast<float*>(p.out) + base;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c0 + j < p.N) atomicAdd(o + j, v[j]);
+      } else if (p.out_bf16) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + base;
+        if (full && ((base & 7) == 0)) {
+          uint4 pk[4];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk[j4]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j4 * 8 + t * 2], v[j4 * 8 + t * 2 + 1]);
+          }
+          if (use_stage) {
+            // transpose through this warp's private staging tile so that 4 lanes write one row's 64 B contiguously
+            uint8_t* st = stage_buf + lane * 80;
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<uint4*>(st + j4 * 16) = pk[j4];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int rr = 8 * j + (lane >> 2);
+              const uint4 u = *reinterpret_cast<const uint4*>(stage_buf + rr * 80 + (lane & 3) * 16);
+              const int grow = m0 + q * 32 + rr;
+              if (grow < p.M)
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)grow * p.ldo + n0 +
+                                          c0 + tap_off + (lane & 3) * 8) = u;
+            }
+            __syncwarp();
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) reinterpret_cast<uint4*>(o)[j4] = pk[j4];
+          }
+        } else if (row < p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) o[j] = __float2bfloat16(v[j]);
+        }
+      } else {
+        float* o = reinterpret_cast<float*>(p.out) + base;
+        if (full && ((base & 3) == 0)) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) o[j] = v[j];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- classic kernel
+// One tile per CTA (grid = tiles_n x tiles_m x splits). Kept as the fallback / comparison path
+// (FLPR_GEMM_PERSIST=0) of the persistent kernel below.
 template <int BN, int A_MODE, int B_MODE>
 __global__ void __launch_bounds__(256, SmemLayout<BN>::MIN_CTAS)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -87,6 +348,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * BM;
   const int zsplit = (B_MODE == OP_CONV) ? (blockIdx.z % p.cSplits) : blockIdx.z;
+  const int ztap = (B_MODE == OP_CONV) ? (blockIdx.z / p.cSplits) : 0;
   const int kb_begin = zsplit * p.kb_per_split;
   const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
   const int num_kb = kb_end - kb_begin;
@@ -118,52 +380,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < num_kb; ++i) {
-        const int kb = kb_begin + i;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * L::STAGE_BYTES;
-        uint8_t* sb = sa + A_STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-        if constexpr (A_MODE == OP_KMAJOR) {
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-        } else if constexpr (A_MODE == OP_MNMAJOR) {
-          tma_load_2d(sa, &tmA, &full_bar[stage], m0, kb * BK);
-          tma_load_2d(sa + 64 * 128, &tmA, &full_bar[stage], m0 + 64, kb * BK);
-        } else {
-          const int chunks = p.cC / BK;
-          const int tap = kb / chunks;
-          const int cc = kb - tap * chunks;
-          const int kh = tap / p.cKW;
-          const int kw = tap - kh * p.cKW;
-          const int mt = blockIdx.y;
-          int img0, h0;
-          if (p.cTilesPerImg <= 1) {
-            img0 = mt * p.cNB;
-            h0 = 0;
-          } else {
-            img0 = mt / p.cTilesPerImg;
-            h0 = (mt - img0 * p.cTilesPerImg) * p.cTH;
-          }
-          tma_load_4d(sa, &tmA, &full_bar[stage], cc * BK, kw - p.cPadW, h0 + kh - p.cPadH, img0);
-        }
-        if constexpr (B_MODE == OP_KMAJOR) {
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
-        } else if constexpr (B_MODE == OP_MNMAJOR) {
-#pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 64 * 128, &tmB, &full_bar[stage], n0 + j * 64, kb * BK);
-        } else {
-          // weight-gradient of a convolution: K runs over pixels (64 per block), the filter tap (blockIdx.z / splits)
-          // shifts the 4-D box, zero padding comes from TMA out-of-bounds fill
-          const int tap = blockIdx.z / p.cSplits;
-          const int kh = tap / p.cKW;
-          const int kw = tap - kh * p.cKW;
-          const int p0 = kb * BK;
-          const int hw = p.cH * p.cW;
-          const int img = p0 / hw;
-          const int h0 = (p0 - img * hw) / p.cW;
-#pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_4d(sb + j * 64 * 128, &tmB, &full_bar[stage], n0 + j * 64, kw - p.cPadW, h0 + kh - p.cPadH, img);
-        }
+        load_kblock<BN, A_MODE, B_MODE>(p, &tmA, &tmB, sa, sa + A_STAGE_BYTES, &full_bar[stage], kb_begin + i,
+                                        blockIdx.y, m0, n0, ztap);
         if (++stage == L::STAGES) {
           stage = 0;
           phase ^= 1;
@@ -172,29 +393,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp_id == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MODE == OP_MNMAJOR, B_MODE != OP_KMAJOR);
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < num_kb; ++i) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-        const uint32_t sb = sa + A_STAGE_BYTES;
-#pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          uint64_t da, db;
-          if constexpr (A_MODE == OP_MNMAJOR)
-            da = make_smem_desc_sw128(sa + k * (UMMA_K * 128), 64 * 128, 1024);
-          else
-            da = make_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
-          if constexpr (B_MODE != OP_KMAJOR)
-            db = make_smem_desc_sw128(sb + k * (UMMA_K * 128), 64 * 128, 1024);
-          else
-            db = make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
-          umma_f16(tmem_base, da, db, idesc, (i | k) != 0);
-        }
-      }
+      if (elect_one()) mma_kblock<BN, A_MODE, B_MODE>(smem_u32(smem + stage * L::STAGE_BYTES), tmem_base, i == 0);
       __syncwarp();
       if (elect_one()) umma_commit(&empty_bar[stage]);
       __syncwarp();
@@ -208,135 +412,152 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if (warp_id >= 4) {
     // ===================== epilogue =====================
     const int q = warp_id & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
     if (num_kb > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
-    const float bm = (p.bias_m != nullptr && row < p.M) ? p.bias_m[row] : 0.f;
-    const long long tap_off = (B_MODE == OP_CONV) ? (long long)(blockIdx.z / p.cSplits) * p.tap_stride : 0;
-    // bf16 row-major output without residual: stores are staged through smem (pipeline stage 0 is free once the
-    // accumulator barrier has fired) so that each store instruction writes 8 full 64-byte row segments
-    const bool use_stage = p.out_bf16 && !p.trans_out && !p.atomic_add && p.residual == nullptr &&
-                           ((p.ldo & 7) == 0) && (((n0 + tap_off) & 7) == 0) &&
-                           ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
-    uint8_t* stage_buf = smem + q * (32 * 80);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      if (num_kb > 0) {
-        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), r);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
+    const long long tap_off = (B_MODE == OP_CONV) ? (long long)ztap * p.tap_stride : 0;
+    // pipeline stage 0 is free once the accumulator barrier has fired -> store staging
+    epilogue_tile<BN>(p, tmem_base, num_kb > 0, blockIdx.y, m0, n0, tap_off, q, lane, smem + q * (32 * 80));
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_id == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- persistent kernel
+// grid = min(#tiles, SMs x resident CTAs); every CTA walks tiles t = blockIdx.x, + gridDim.x, ... (n fastest, so
+// that concurrently running CTAs share the A rows in L2). Two accumulator stages in TMEM: the epilogue warps drain
+// tile i (TMEM -> registers -> global) while the MMA warp already accumulates tile i+1, and the TMA producer runs
+// ahead across tile boundaries, so neither the pipeline fill nor the epilogue is exposed for short-K GEMMs.
+template <int BN, int A_MODE, int B_MODE>
+__global__ void __launch_bounds__(256, PersistLayout<BN>::MIN_CTAS)
+gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                    const GemmParams p) {
+  using L = PersistLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + L::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + L::STAGES;          // [ACC_STAGES]
+  uint64_t* tmem_empty_bar = tmem_full_bar + L::ACC_STAGES;  // [ACC_STAGES]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + L::ACC_STAGES);
+
+  const int warp_id = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_id == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp_id == 1 && lane == 0) {
+    for (int s = 0; s < L::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < L::ACC_STAGES; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);   // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp_id == 2) {
+    tmem_alloc(tmem_ptr_smem, L::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int per_z = p.tiles_m * p.tiles_n;
+
+  if (warp_id == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+        const int z = t / per_z;
+        const int r = t - z * per_z;
+        const int mt = r / p.tiles_n;
+        const int nt = r - mt * p.tiles_n;
+        const int zsplit = (B_MODE == OP_CONV) ? (z % p.cSplits) : z;
+        const int ztap = (B_MODE == OP_CONV) ? (z / p.cSplits) : 0;
+        const int kb_begin = zsplit * p.kb_per_split;
+        const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          load_kblock<BN, A_MODE, B_MODE>(p, &tmA, &tmB, sa, sa + A_STAGE_BYTES, &full_bar[stage], kb, mt, mt * BM,
+                                          nt * BN, ztap);
+          if (++stage == L::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
       }
-      if (n0 + c0 >= p.N) continue;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]) * p.alpha + bm;
-        const int col = n0 + c0 + j;
-        if (p.bias_n != nullptr && col < p.N) x += p.bias_n[col];
-        v[j] = x;
+    }
+  } else if (warp_id == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+      const int z = t / per_z;
+      const int zsplit = (B_MODE == OP_CONV) ? (z % p.cSplits) : z;
+      const int kb_begin = zsplit * p.kb_per_split;
+      const int num_kb = min(kb_begin + p.kb_per_split, p.kb_total) - kb_begin;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);       // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + uint32_t(acc * BN);
+      for (int i = 0; i < num_kb; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) mma_kblock<BN, A_MODE, B_MODE>(smem_u32(smem + stage * L::STAGE_BYTES), tmem_acc, i == 0);
+        __syncwarp();
+        if (elect_one()) umma_commit(&empty_bar[stage]);
+        __syncwarp();
+        if (++stage == L::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
-      if (p.trans_out) {
-        // out[col * ldo + row]: lanes are contiguous in memory -> coalesced per column
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = n0 + c0 + j;
-          if (row < p.M && col < p.N) {
-            const long long idx = (long long)col * p.ldo + row;
-            float x = v[j];
-            if (p.residual != nullptr) x += __bfloat162float(p.residual[idx]);
-            if (p.relu) x = fmaxf(x, 0.f);
-            if (p.atomic_add)
-              atomicAdd(reinterpret_cast<float*>(p.out) + idx, x);
-            else if (p.out_bf16)
-              reinterpret_cast<__nv_bfloat16*>(p.out)[idx] = __float2bfloat16(x);
-            else
-              reinterpret_cast<float*>(p.out)[idx] = x;
-          }
-        }
-      } else if (row < p.M || use_stage) {
-        const long long base = (long long)row * p.ldo + n0 + c0 + tap_off;
-        const bool full = (n0 + c0 + 32 <= p.N);
-        if (p.residual != nullptr) {
-          if (full && ((base & 7) == 0)) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + base);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              uint4 u = rp[j4];
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                float2 f = __bfloat1622float2(h[t]);
-                v[j4 * 8 + t * 2] += f.x;
-                v[j4 * 8 + t * 2 + 1] += f.y;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c0 + j < p.N) v[j] += __bfloat162float(p.residual[base + j]);
-          }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (p.atomic_add) {
-          float* o = reinterpret_cast<float*>(p.out) + base;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < p.N) atomicAdd(o + j, v[j]);
-        } else if (p.out_bf16) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + base;
-          if (full && ((base & 7) == 0)) {
-            uint4 pk[4];
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk[j4]);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j4 * 8 + t * 2], v[j4 * 8 + t * 2 + 1]);
-            }
-            if (use_stage) {
-              // transpose through this warp's private staging tile so that 4 lanes write one row's 64 B contiguously
-              uint8_t* st = stage_buf + lane * 80;
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<uint4*>(st + j4 * 16) = pk[j4];
-              __syncwarp();
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int rr = 8 * j + (lane >> 2);
-                const uint4 u = *reinterpret_cast<const uint4*>(stage_buf + rr * 80 + (lane & 3) * 16);
-                const int grow = m0 + q * 32 + rr;
-                if (grow < p.M)
-                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)grow * p.ldo + n0 +
-                                            c0 + tap_off + (lane & 3) * 8) = u;
-              }
-              __syncwarp();
-            } else {
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) reinterpret_cast<uint4*>(o)[j4] = pk[j4];
-            }
-          } else if (row < p.M) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c0 + j < p.N) o[j] = __float2bfloat16(v[j]);
-          }
-        } else {
-          float* o = reinterpret_cast<float*>(p.out) + base;
-          if (full && ((base & 3) == 0)) {
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4)
-              reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c0 + j < p.N) o[j] = v[j];
-          }
-        }
+      if (elect_one()) umma_commit(&tmem_full_bar[acc]);
+      __syncwarp();
+      if (++acc == L::ACC_STAGES) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp_id >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp_id & 3;
+    uint8_t* stage_buf = smem + L::STORE_OFFSET + q * (32 * 80);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+      const int z = t / per_z;
+      const int r = t - z * per_z;
+      const int mt = r / p.tiles_n;
+      const int nt = r - mt * p.tiles_n;
+      const int ztap = (B_MODE == OP_CONV) ? (z / p.cSplits) : 0;
+      const long long tap_off = (B_MODE == OP_CONV) ? (long long)ztap * p.tap_stride : 0;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<BN>(p, tmem_base + uint32_t(acc * BN), true, mt, mt * BM, nt * BN, tap_off, q, lane, stage_buf);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == L::ACC_STAGES) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   }
@@ -345,7 +566,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   if (warp_id == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
   }
 }
 
@@ -432,18 +653,58 @@ static int get_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* 
   return 0;
 }
 
-template <int BN, int A_MODE, int B_MODE>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int splits, cudaStream_t st) {
-  using L = SmemLayout<BN>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, A_MODE, B_MODE>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
-    if (e != cudaSuccess) return set_err("cudaFuncSetAttribute(smem)", (int)e);
-    configured = true;
+static int g_persist = -1;   // FLPR_GEMM_PERSIST (default 1): persistent kernel with overlapped epilogue
+static int g_sms = 0;
+
+static bool use_persist() {
+  if (g_persist < 0) {
+    const char* e = getenv("FLPR_GEMM_PERSIST");
+    g_persist = (e == nullptr || e[0] != '0') ? 1 : 0;
   }
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
-  kern<<<grid, 256, L::TOTAL, st>>>(ta, tb, p);
+  return g_persist == 1;
+}
+
+static int sm_count() {
+  if (g_sms == 0) {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_sms = n;
+  }
+  return g_sms;
+}
+
+template <int BN, int A_MODE, int B_MODE>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, int splits, cudaStream_t st) {
+  GemmParams p = p_in;
+  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_n = (p.N + BN - 1) / BN;
+  p.tiles_z = splits;
+  p.tiles_total = p.tiles_m * p.tiles_n * splits;
+  if (use_persist()) {
+    using L = PersistLayout<BN>;
+    auto kern = gemm_bf16_tcgen05_persistent_kernel<BN, A_MODE, B_MODE>;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+      if (e != cudaSuccess) return set_err("cudaFuncSetAttribute(smem, persistent)", (int)e);
+      configured = true;
+    }
+    const int slots = sm_count() * L::MIN_CTAS;
+    const int grid = p.tiles_total < slots ? p.tiles_total : slots;
+    kern<<<grid, 256, L::TOTAL, st>>>(ta, tb, p);
+  } else {
+    using L = SmemLayout<BN>;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, A_MODE, B_MODE>;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+      if (e != cudaSuccess) return set_err("cudaFuncSetAttribute(smem)", (int)e);
+      configured = true;
+    }
+    dim3 grid(p.tiles_n, p.tiles_m, splits);
+    kern<<<grid, 256, L::TOTAL, st>>>(ta, tb, p);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err(cudaGetErrorString(e), (int)e);
   return 0;
@@ -457,17 +718,28 @@ static int dispatch_modes(int a_mode, int b_mode, const CUtensorMap& ta, const C
   if (a_mode == OP_MNMAJOR && b_mode == OP_KMAJOR) return launch<BN, OP_MNMAJOR, OP_KMAJOR>(ta, tb, p, splits, st);
   if (a_mode == OP_MNMAJOR && b_mode == OP_MNMAJOR) return launch<BN, OP_MNMAJOR, OP_MNMAJOR>(ta, tb, p, splits, st);
   if (a_mode == OP_CONV && b_mode == OP_KMAJOR) return launch<BN, OP_CONV, OP_KMAJOR>(ta, tb, p, splits, st);
+  if (a_mode == OP_CONV && b_mode == OP_TAPFLIP) return launch<BN, OP_CONV, OP_TAPFLIP>(ta, tb, p, splits, st);
   if (a_mode == OP_MNMAJOR && b_mode == OP_CONV) return launch<BN, OP_MNMAJOR, OP_CONV>(ta, tb, p, splits, st);
   return set_err("unsupported operand mode combination", -3);
 }
 
-static int pick_bn(int M, int N, int requested) {
+static int dispatch_bn(int BN, int a_mode, int b_mode, const CUtensorMap& ta, const CUtensorMap& tb,
+                       const GemmParams& p, int splits, cudaStream_t st) {
+  if (BN == 64) return dispatch_modes<64>(a_mode, b_mode, ta, tb, p, splits, st);
+  if (BN == 128) return dispatch_modes<128>(a_mode, b_mode, ta, tb, p, splits, st);
+  return dispatch_modes<256>(a_mode, b_mode, ta, tb, p, splits, st);
+}
+
+// Tile width. 128 x 256 tiles halve the B-operand smem traffic per MMA (a 128 x 128 tile is smem-bandwidth bound at
+// ~50 % of the tensor peak) but leave one CTA per SM, so they are used when they still give ~a full wave.
+static int pick_bn(int M, int N, int z, int requested) {
   if (requested == 64 || requested == 128 || requested == 256) return requested;
-  // Aim for >= ~1 wave of 148 SMs; prefer the widest tile that still fills the machine.
-  const long long mt = (M + BM - 1) / BM;
-  (void)mt;
   if (N <= 64) return 64;
-  return 128;   // two resident CTAs per SM hide the epilogue; 256-wide tiles only on request
+  if (!use_persist()) return 128;
+  const long long mt = (M + BM - 1) / BM;
+  const long long t256 = mt * ((N + 255) / 256) * (z > 0 ? z : 1);
+  if (N >= 256 && t256 >= 120) return 256;
+  return 128;
 }
 
 }  // namespace flpr
@@ -478,17 +750,30 @@ extern "C" {
 
 const char* flpr_gemm_last_error() { return g_err; }
 
+// 1: persistent kernel (default), 0: classic one-tile-per-CTA kernel, -1: re-read FLPR_GEMM_PERSIST.
+void flpr_gemm_set_persistent(int on) { g_persist = on; }
+
 // D = alpha * op(A) * op(B)^T.  a_mode/b_mode: 0 = [rows,K] (ld = row stride), 1 = [K,rows] (ld = K-row stride).
+// col_part (optional, fp32 [ceil(M/128)*4][2][N]): per-32-row partial column sums / sums of squares of the fp32
+// result (fused batch-norm statistics); requires split_k <= 1 and no transposed output.
 int flpr_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, long long lda, long long ldb,
                    long long ldo, int a_mode, int b_mode, int out_bf16, int trans_out, float alpha,
                    const float* bias_n, const float* bias_m, int relu, const void* residual, int split_k, int bn_req,
-                   cudaStream_t stream) {
+                   float* col_part, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   bind_device_of(A);
   if ((lda % 8) || (ldb % 8)) return set_err("lda/ldb must be multiples of 8 elements (16B TMA stride)", -4);
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
     return set_err("A/B must be 16B aligned", -5);
-  const int BN = pick_bn(M, N, bn_req);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.kb_total = (K + BK - 1) / BK;
+  int splits = split_k > 1 ? split_k : 1;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  const int BN = pick_bn(M, N, splits, bn_req);
   CUtensorMap ta, tb;
   int rc;
   {
@@ -509,46 +794,43 @@ int flpr_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
     str[0] = (uint64_t)ldb * 2;
     if ((rc = get_map(&tb, B, 2, dims, str, box))) return rc;
   }
-  GemmParams p;
-  memset(&p, 0, sizeof(p));
-  p.M = M; p.N = N; p.K = K;
-  p.kb_total = (K + BK - 1) / BK;
-  int splits = split_k > 1 ? split_k : 1;
-  if (splits > p.kb_total) splits = p.kb_total;
-  p.kb_per_split = (p.kb_total + splits - 1) / splits;
-  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.out = out; p.ldo = ldo; p.out_bf16 = out_bf16; p.trans_out = trans_out;
   p.atomic_add = splits > 1 ? 1 : 0;
   if (p.atomic_add && out_bf16) return set_err("split-K requires fp32 output", -6);
+  if (col_part != nullptr && (p.atomic_add || trans_out)) return set_err("col_part needs split_k=1, no transpose", -12);
+  p.col_part = col_part;
   p.alpha = alpha; p.bias_n = bias_n; p.bias_m = bias_m; p.relu = relu;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  if (BN == 64) return dispatch_modes<64>(a_mode, b_mode, ta, tb, p, splits, stream);
-  if (BN == 128) return dispatch_modes<128>(a_mode, b_mode, ta, tb, p, splits, stream);
-  return dispatch_modes<256>(a_mode, b_mode, ta, tb, p, splits, stream);
+  return dispatch_bn(BN, a_mode, b_mode, ta, tb, p, splits, stream);
+}
+
+static int conv_tiling(int H, int W, int* TH, int* NB, int* tiles_per_img) {
+  if (W > 128 || (128 % W)) return set_err("conv: W must divide 128", -8);
+  if (H * W <= 128) {
+    if (128 % (H * W)) return set_err("conv: H*W must divide 128", -9);
+    *TH = H; *NB = 128 / (H * W); *tiles_per_img = 1;
+  } else {
+    *TH = 128 / W;
+    if (H % *TH) return set_err("conv: 128/W must divide H", -10);
+    *NB = 1; *tiles_per_img = H / *TH;
+  }
+  return 0;
 }
 
 // Implicit-GEMM convolution, stride 1: X [NIMG,H,W,C] bf16 NHWC, Wt [Cout, KH*KW*C] bf16 (tap-major, then C),
 // out [NIMG*H*W, Cout]. Requires C % 64 == 0, W a power of two <= 128 and (H*W) | 128 or 128/W | H.
+// col_part: see flpr_gemm_bf16 (fused batch-norm statistics of the conv output).
 int flpr_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int NIMG, int H, int W, int C, int Cout, int KH,
                         int KW, int pad_h, int pad_w, int out_bf16, float alpha, const float* bias_n, int relu,
-                        const void* residual, int bn_req, cudaStream_t stream) {
+                        const void* residual, int bn_req, float* col_part, cudaStream_t stream) {
   bind_device_of(X);
   if (C % 64) return set_err("conv: C must be a multiple of 64", -7);
-  if (W > 128 || (128 % W)) return set_err("conv: W must divide 128", -8);
-  int TH, NB, tiles_per_img;
-  if (H * W <= 128) {
-    if (128 % (H * W)) return set_err("conv: H*W must divide 128", -9);
-    TH = H; NB = 128 / (H * W); tiles_per_img = 1;
-  } else {
-    TH = 128 / W;
-    if (H % TH) return set_err("conv: 128/W must divide H", -10);
-    NB = 1; tiles_per_img = H / TH;
-  }
+  int TH, NB, tiles_per_img, rc;
+  if ((rc = conv_tiling(H, W, &TH, &NB, &tiles_per_img))) return rc;
   const int M = NIMG * H * W;
   const int K = KH * KW * C;
-  const int BN = pick_bn(M, Cout, bn_req);
+  const int BN = pick_bn(M, Cout, 1, bn_req);
   CUtensorMap ta, tb;
-  int rc;
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NIMG};
     uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
@@ -565,11 +847,45 @@ int flpr_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int NIMG, int 
   p.kb_total = K / BK; p.kb_per_split = p.kb_total;
   p.out = out; p.ldo = Cout; p.out_bf16 = out_bf16; p.alpha = alpha; p.bias_n = bias_n; p.relu = relu;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.col_part = col_part;
   p.cH = H; p.cW = W; p.cC = C; p.cTH = TH; p.cNB = NB; p.cKW = KW; p.cPadH = pad_h; p.cPadW = pad_w;
-  p.cTilesPerImg = tiles_per_img;
-  if (BN == 64) return dispatch_modes<64>(OP_CONV, OP_KMAJOR, ta, tb, p, 1, stream);
-  if (BN == 128) return dispatch_modes<128>(OP_CONV, OP_KMAJOR, ta, tb, p, 1, stream);
-  return dispatch_modes<256>(OP_CONV, OP_KMAJOR, ta, tb, p, 1, stream);
+  p.cTilesPerImg = tiles_per_img; p.cTaps = KH * KW;
+  return dispatch_bn(BN, OP_CONV, OP_KMAJOR, ta, tb, p, 1, stream);
+}
+
+// Data gradient of a stride-1 convolution, straight from the FORWARD weight Wt [Cout, KH*KW*Cin] (no flipped /
+// transposed copy): dX[NIMG*H*W, Cin] = sum_taps dY(shifted by the mirrored tap)[., Cout] x Wt[:, tap, :].
+// dY: [NIMG,H,W,Cout] bf16. pad_h/pad_w are the FORWARD paddings (dgrad pads with K-1-pad).
+int flpr_conv_dgrad_nhwc_bf16(const void* dY, const void* Wt, void* out, int NIMG, int H, int W, int Cin, int Cout,
+                              int KH, int KW, int pad_h, int pad_w, int out_bf16, int bn_req, cudaStream_t stream) {
+  bind_device_of(dY);
+  if (Cout % 64) return set_err("conv dgrad: Cout must be a multiple of 64", -7);
+  if (Cin % 64) return set_err("conv dgrad: Cin must be a multiple of 64", -7);
+  int TH, NB, tiles_per_img, rc;
+  if ((rc = conv_tiling(H, W, &TH, &NB, &tiles_per_img))) return rc;
+  const int M = NIMG * H * W;
+  const int K = KH * KW * Cout;
+  const int BN = pick_bn(M, Cin, 1, bn_req);
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)NIMG};
+    uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+    uint32_t box[4] = {64, (uint32_t)W, (uint32_t)TH, (uint32_t)NB};
+    if ((rc = get_map(&ta, dY, 4, dims, str, box))) return rc;
+    uint64_t d2[2] = {(uint64_t)KH * KW * Cin, (uint64_t)Cout};
+    uint64_t s2[1] = {(uint64_t)KH * KW * Cin * 2};
+    uint32_t b2[2] = {64, BK};
+    if ((rc = get_map(&tb, Wt, 2, d2, s2, b2))) return rc;
+  }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = Cin; p.K = K;
+  p.kb_total = K / BK; p.kb_per_split = p.kb_total;
+  p.out = out; p.ldo = Cin; p.out_bf16 = out_bf16; p.alpha = 1.f;
+  p.cH = H; p.cW = W; p.cC = Cout; p.cTH = TH; p.cNB = NB; p.cKW = KW;
+  p.cPadH = KH - 1 - pad_h; p.cPadW = KW - 1 - pad_w;
+  p.cTilesPerImg = tiles_per_img; p.cTaps = KH * KW;
+  return dispatch_bn(BN, OP_CONV, OP_TAPFLIP, ta, tb, p, 1, stream);
 }
 
 // Weight gradient of a stride-1 convolution: out[Cout, KH*KW*C] (fp32, tap-major then C) +=
@@ -614,11 +930,9 @@ int flpr_conv_wgrad_nhwc_bf16(const void* X, const void* dY, float* out, int NIM
   p.out = out; p.ldo = (long long)KH * KW * C; p.out_bf16 = 0; p.alpha = 1.f;
   p.atomic_add = splits > 1 ? 1 : 0;
   p.cH = H; p.cW = W; p.cC = C; p.cTH = TH; p.cNB = NB; p.cKW = KW; p.cPadH = pad_h; p.cPadW = pad_w;
-  p.cSplits = splits; p.tap_stride = C;
+  p.cSplits = splits; p.tap_stride = C; p.cTaps = KH * KW;
   const int gz = KH * KW * splits;
-  if (BN == 64) return dispatch_modes<64>(OP_MNMAJOR, OP_CONV, ta, tb, p, gz, stream);
-  if (BN == 128) return dispatch_modes<128>(OP_MNMAJOR, OP_CONV, ta, tb, p, gz, stream);
-  return dispatch_modes<256>(OP_MNMAJOR, OP_CONV, ta, tb, p, gz, stream);
+  return dispatch_bn(BN, OP_MNMAJOR, OP_CONV, ta, tb, p, gz, stream);
 }
 
 }  // extern "C"

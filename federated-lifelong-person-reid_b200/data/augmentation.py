@@ -48,26 +48,56 @@ class DeviceAugment:
         self.dtype = dtype
         self.scale, self.ratio = scale, ratio
 
+    def _native(self, u8: torch.Tensor, generator) -> torch.Tensor:
+        """One fused sm_100a kernel (``csrc/fused_ops.cu: augment_u8_kernel``): normalise + flip + erase + cast."""
+        import ctypes as C
+        from ..ops import native
+        lib = native.load()
+        b, h, w, _ = u8.shape
+        u8 = u8.contiguous()
+        u = torch.rand(7, b, device=u8.device, generator=generator)
+        out = torch.empty(b, h, w, 3, dtype=self.dtype, device=u8.device)
+        if getattr(self, "_consts", None) is None:
+            m = self.mean.flatten().tolist()
+            i = self.inv_std.flatten().tolist()
+            self._consts = ((C.c_float * 3)(*m), (C.c_float * 3)(*i))
+        mean3, inv3 = self._consts
+        rc = lib.flpr_augment_u8(native.ptr(u8), native.ptr(out), native.ptr(u), b, h, w,
+                                 C.cast(mean3, C.c_void_p), C.cast(inv3, C.c_void_p),
+                                 FLIP_P[self.level], ERASE_P[self.level], self.scale[0], self.scale[1],
+                                 self.ratio[0], self.ratio[1], int(self.dtype == torch.bfloat16),
+                                 native.stream(u8.device))
+        native.check(rc, "flpr_augment_u8")
+        native.count_launch()
+        return out.permute(0, 3, 1, 2)
+
     def __call__(self, u8: torch.Tensor, generator: torch.Generator | None = None) -> torch.Tensor:
+        if u8.is_cuda and u8.shape[2] % 4 == 0 and self.dtype in (torch.bfloat16, torch.float32) \
+                and u8.dtype == torch.uint8:
+            return self._native(u8, generator)
+        return self.reference(u8, generator)
+
+    def reference(self, u8: torch.Tensor, generator: torch.Generator | None = None) -> torch.Tensor:
+        """Plain tensor-op implementation (CPU path and numerics reference of the fused kernel); consumes the same
+        ``[7, B]`` block of uniforms as the kernel, so both produce the same batch from the same generator state."""
         dev = u8.device
         if self.mean.device != dev:
             self.mean, self.inv_std = self.mean.to(dev), self.inv_std.to(dev)
         x = (u8.float() - self.mean) * self.inv_std                       # [B,H,W,3]
         b, h, w, _ = x.shape
+        u = torch.rand(7, b, device=dev, generator=generator)
         if self.level != "none":
-            g = generator
-            flip = torch.rand(b, device=dev, generator=g) < FLIP_P[self.level]
+            flip = u[0] < FLIP_P[self.level]
             x = torch.where(flip.view(b, 1, 1, 1), x.flip(2), x)
             # RandomErasing(value=0): one rectangle per selected sample, area in `scale`, aspect log-uniform in `ratio`
-            sel = torch.rand(b, device=dev, generator=g) < ERASE_P[self.level]
-            area = (torch.rand(b, device=dev, generator=g) * (self.scale[1] - self.scale[0]) + self.scale[0]) * h * w
-            logr = torch.rand(b, device=dev, generator=g) * (math.log(self.ratio[1]) - math.log(self.ratio[0])) \
-                + math.log(self.ratio[0])
+            sel = u[1] < ERASE_P[self.level]
+            area = (u[2] * (self.scale[1] - self.scale[0]) + self.scale[0]) * h * w
+            logr = u[3] * (math.log(self.ratio[1]) - math.log(self.ratio[0])) + math.log(self.ratio[0])
             ar = torch.exp(logr)
             eh = torch.sqrt(area * ar).round().clamp(1, h - 1)
             ew = torch.sqrt(area / ar).round().clamp(1, w - 1)
-            top = (torch.rand(b, device=dev, generator=g) * (h - eh + 1)).floor()
-            left = (torch.rand(b, device=dev, generator=g) * (w - ew + 1)).floor()
+            top = (u[4] * (h - eh + 1)).floor()
+            left = (u[5] * (w - ew + 1)).floor()
             ys = torch.arange(h, device=dev).view(1, h, 1)
             xs = torch.arange(w, device=dev).view(1, 1, w)
             box = (ys >= top.view(b, 1, 1)) & (ys < (top + eh).view(b, 1, 1)) & \

@@ -43,6 +43,8 @@ class DeviceBatchLoader:
         self._stage: List[torch.Tensor] = []
         self._copy_stream = None
         self.h2d_bytes = 0
+        self._labels_dev = None
+        self.bulk_limit_bytes = 2 << 30
 
     def to(self, device, dtype: Optional[torch.dtype] = None) -> "DeviceBatchLoader":
         self.device = torch.device(device)
@@ -68,9 +70,60 @@ class DeviceBatchLoader:
         n = len(self.dataset)
         return torch.randperm(n, generator=self._gen) if self.shuffle else torch.arange(n)
 
-    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+    def _bulk_ok(self) -> bool:
         ds = self.dataset
-        order = self._order()
+        return (self.device.type == "cuda" and ds.images.is_pinned()
+                and ds.images.numel() * ds.images.element_size() <= self.bulk_limit_bytes)
+
+    def iterate(self, batch_size: Optional[int] = None, ordered: bool = False):
+        """Like ``iter(self)`` with a different batch size (the inference-only trunk wants wider batches).
+        ``ordered`` skips the shuffle (the caller does not care about the sample order)."""
+        return self._iter_bulk(batch_size, ordered) if self._bulk_ok() else self._iter_staged(batch_size, ordered)
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+        return self.iterate()
+
+    def _iter_bulk(self, batch_size: Optional[int], ordered: bool):
+        """Pinned split -> ONE async H2D copy per epoch on the copy stream (no host-side gather, no per-batch
+        staging); shuffling and batching are index ops on the device; augmentation is one fused kernel per batch."""
+        ds, dev = self.dataset, self.device
+        bs = int(batch_size or self.batch_size)
+        n = len(ds)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(self._copy_stream):
+            dev_all = ds.images.to(dev, non_blocking=True)
+            if self._labels_dev is None:
+                self._labels_dev = (ds.pids.to(dev, non_blocking=True), ds.cidx.to(dev, non_blocking=True))
+                self.h2d_bytes += 16 * n
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self.h2d_bytes += dev_all.numel()
+        pids, cidx = self._labels_dev
+        shuffle = self.shuffle and not ordered
+        order = self._order().to(dev, non_blocking=True) if shuffle else None
+        cur.wait_event(ev)
+        dev_all.record_stream(cur)
+        last = n // bs * bs if (self.drop_last and batch_size is None) else n
+        for s0 in range(0, last, bs):
+            if shuffle:
+                idx = order[s0:s0 + bs]
+                yield self.augment(dev_all.index_select(0, idx)), pids[idx], cidx[idx]
+            else:
+                yield self.augment(dev_all[s0:s0 + bs]), pids[s0:s0 + bs], cidx[s0:s0 + bs]
+
+    def _iter_staged(self, batch_size: Optional[int] = None, ordered: bool = False):
+        ds = self.dataset
+        order = self._order() if not ordered else torch.arange(len(ds))
+        if batch_size is not None and int(batch_size) != self.batch_size:
+            saved = self.batch_size
+            self.batch_size, self._stage = int(batch_size), []
+            try:
+                yield from self._iter_staged(None, ordered)
+            finally:
+                self.batch_size, self._stage = saved, []
+            return
         nb = len(self)
         cuda = self.device.type == "cuda"
         if cuda:

@@ -46,8 +46,7 @@ class Model(ModelModule):
         self.adaptive_names: List[str] = self._find_adaptive_layers()
         self._theta_params = {f"{n}.weight" for n in self.adaptive_names}
         self.ids: set = set()
-        # exemplar memory: pid -> {"bank": tensor [u, ...] prototypes, "cls": tensor [u], "order": list[int]}
-        self.examplars: Dict[int, Dict[str, Any]] = {}
+        self.ex_gens: List[Dict[str, Any]] = []          # exemplar memory (see "exemplar memory" below)
         self.G: Optional[torch.Tensor] = None
 
     # ---- adaptive layers: leaves of type Linear/Conv2d whose parameters are all trainable (fedstil.py:290-347) ------
@@ -163,67 +162,115 @@ class Model(ModelModule):
         return self.net.forward_head(protos)
 
     # ---- exemplar memory (fedstil.py:349-399) -----------------------------------------------------------------------
+    # Stored as *generations* (one per build_examplars call): ``{"pids": LongTensor[P], "bank": [P, m, ...],
+    # "cls": [P, m], "k": kept exemplars per identity}``. The reference's per-identity python lists
+    # ``{pid: [(prototype, class_id)] * m}`` are a view of this (``examplars`` property, checkpoint writer).
     def reduce_examplars(self) -> None:
         m = self.m
-        for pid in self.examplars:
-            self.examplars[pid]["order"] = self.examplars[pid]["order"][:m]
+        for gen in self.ex_gens:
+            gen["k"] = min(gen["k"], m)
+
+    @property
+    def examplars(self) -> Dict[int, Dict[str, Any]]:
+        out: Dict[int, Dict[str, Any]] = {}
+        for gen in self.ex_gens:
+            k = gen["k"]
+            for gi, pid in enumerate(gen["pid_list"]):
+                out[pid] = {"bank": gen["bank"][gi, :k], "cls": gen["cls"][gi, :k], "order": list(range(k))}
+        return out
 
     @torch.no_grad()
     def build_examplars(self, protos: torch.Tensor, pids: torch.Tensor, classes: torch.Tensor,
                         person_ids: Sequence[int], batch_size: int = 256) -> None:
         """Herding on ``forward_head`` features of the epoch's prototype set (exemplars + current task)."""
         self.eval()
-        feats = []
-        for s in range(0, protos.shape[0], batch_size):
-            with self.autocast():
-                feats.append(self.forward_head(protos[s:s + batch_size]).float())
-        feats = torch.cat(feats) if feats else torch.zeros(0, 1, device=protos.device)
-        keep = set(int(p) for p in person_ids)
+        keep = sorted(set(int(p) for p in person_ids))
         m = self.m
-        upids = [p for p in torch.unique(pids).tolist() if not keep or p in keep]
-        if not upids:
+        dev = protos.device
+        if keep:
+            keep_t = torch.tensor(keep, device=dev)
+            rows = torch.nonzero(torch.isin(pids, keep_t)).squeeze(1)       # one host sync (sizes)
+        else:
+            rows = torch.arange(pids.numel(), device=dev)
+        if rows.numel() == 0 or m <= 0:
             return
-        groups = [torch.nonzero(pids == pid).squeeze(1) for pid in upids]
-        picks = herding_select_batched(feats, groups, m).cpu()              # [P, m], one host transfer
-        for gi, pid in enumerate(upids):
-            idx = groups[gi]
-            order = picks[gi].tolist()
-            uniq, inverse = torch.unique(torch.tensor(order), return_inverse=True)
-            sel = idx[uniq.to(idx.device)]
-            self.examplars[int(pid)] = {"bank": protos[sel].clone(), "cls": classes[sel].clone(),
-                                        "order": inverse.tolist()}
+        feats = []
+        for s in range(0, rows.numel(), batch_size):
+            with self.autocast():
+                feats.append(self.forward_head(protos[rows[s:s + batch_size]]).float())
+        feats = torch.cat(feats)                                             # [n_sel, D], aligned with `rows`
+        sel_pids = pids[rows]
+        order = torch.argsort(sel_pids, stable=True)
+        upid, counts = torch.unique_consecutive(sel_pids[order], return_counts=True)
+        upid_l, counts_l = upid.tolist(), counts.tolist()                    # the second (and last) host sync
+        P, nmax = len(upid_l), max(counts_l)
+        starts = torch.cumsum(counts, 0) - counts
+        ar = torch.arange(nmax, device=dev)
+        pos = (starts[:, None] + ar[None, :]).clamp_(max=order.numel() - 1)
+        idx = order[pos]                                                     # [P, nmax] rows of `feats` per identity
+        picks = herding_select_batched(feats, idx, counts, m)               # [P, m] positions within each identity
+        sel = rows[idx.gather(1, picks)]                                     # [P, m] rows of `protos`
+        gen = {"pids": upid, "pid_list": [int(p) for p in upid_l], "k": m,
+               "bank": protos[sel.reshape(-1)].reshape(P, m, *protos.shape[1:]),
+               "cls": classes[sel.reshape(-1)].reshape(P, m)}
+        # identities that are herded again replace their older exemplars
+        fresh = set(gen["pid_list"])
+        kept = []
+        for old in self.ex_gens:
+            if fresh.isdisjoint(old["pid_list"]):
+                kept.append(old)
+                continue
+            mask = [p not in fresh for p in old["pid_list"]]
+            if any(mask):
+                mk = torch.tensor(mask, device=dev)
+                kept.append({"pids": old["pids"][mk], "pid_list": [p for p, k_ in zip(old["pid_list"], mask) if k_],
+                             "k": old["k"], "bank": old["bank"][mk], "cls": old["cls"][mk]})
+        self.ex_gens = kept + [gen]
 
     def examplar_tensors(self) -> Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
         """Expanded rehearsal set ``(protos, person_ids, class_ids)`` (duplicates included, like the reference)."""
         ps, ids, cs = [], [], []
-        for pid, ex in self.examplars.items():
-            if not ex["order"]:
+        for gen in self.ex_gens:
+            k = gen["k"]
+            if k <= 0 or not gen["pid_list"]:
                 continue
-            o = torch.tensor(ex["order"], device=ex["bank"].device)
-            ps.append(ex["bank"][o])
-            cs.append(ex["cls"][o])
-            ids.append(torch.full((len(ex["order"]),), pid, dtype=torch.long, device=ex["bank"].device))
+            P = len(gen["pid_list"])
+            ps.append(gen["bank"][:, :k].reshape(P * k, *gen["bank"].shape[2:]))
+            cs.append(gen["cls"][:, :k].reshape(-1))
+            ids.append(gen["pids"].repeat_interleave(k))
         if not ps:
             return None
         return torch.cat(ps), torch.cat(ids), torch.cat(cs)
 
     def examplars_compact(self) -> Dict:
         """Compact exemplar memory; the checkpoint writer process expands it to the reference schema."""
-        return {"_compact_examplars": {int(p): {"bank": ex["bank"], "cls": ex["cls"], "order": list(ex["order"])}
-                                       for p, ex in self.examplars.items()}}
+        return {"_compact_gens": [{"pids": g["pids"], "bank": g["bank"], "cls": g["cls"], "k": int(g["k"])}
+                                  for g in self.ex_gens]}
 
     def examplars_state(self, max_bytes: int = 256 << 20) -> Dict:
-        """``{np.int64 pid: [(ndarray proto, class_id), ...]}`` (``fedstil.py:841,846``) when small enough."""
-        total = sum(len(ex["order"]) * ex["bank"][0].numel() * 4 for ex in self.examplars.values() if len(ex["bank"]))
-        if total > max_bytes:
-            return {"_compact": {int(p): {"bank": ex["bank"].cpu(), "cls": ex["cls"].cpu(), "order": ex["order"]}
-                                 for p, ex in self.examplars.items()}}
+        """``{np.int64 pid: [(ndarray proto, class_id), ...]}`` (``fedstil.py:841,846``)."""
         out = {}
         for pid, ex in self.examplars.items():
             bank = ex["bank"].float().cpu().numpy()
             cls = ex["cls"].cpu().tolist()
             out[np.int64(pid)] = [(bank[i], int(cls[i])) for i in ex["order"]]
         return out
+
+    def load_examplars_state(self, state: Dict) -> None:
+        """Inverse of :meth:`examplars_state` (resume from a reference-schema exemplar checkpoint)."""
+        self.ex_gens = []
+        by_len: Dict[int, List] = {}
+        for pid, items in state.items():
+            by_len.setdefault(len(items), []).append((int(pid), items))
+        dt = torch.bfloat16 if self.compute_dtype == torch.bfloat16 else torch.float32
+        for k, group in by_len.items():
+            if k == 0:
+                continue
+            bank = torch.stack([torch.stack([torch.as_tensor(pr) for pr, _ in items]) for _, items in group])
+            cls = torch.tensor([[int(c) for _, c in items] for _, items in group])
+            pl = [pid for pid, _ in group]
+            self.ex_gens.append({"pids": torch.tensor(pl, device=self.device), "pid_list": pl, "k": k,
+                                 "bank": bank.to(self.device, dt), "cls": cls.to(self.device)})
 
 
 def herding_select(feats: torch.Tensor, m: int) -> List[int]:
@@ -248,23 +295,40 @@ def herding_select(feats: torch.Tensor, m: int) -> List[int]:
     return picks.tolist()
 
 
-def herding_select_batched(feats: torch.Tensor, groups: List[torch.Tensor], m: int) -> torch.Tensor:
-    """Herding for all identities at once: ``groups[g]`` indexes the rows of ``feats`` that belong to identity g.
-    Returns ``[len(groups), m]`` positions *within each group* (same rule as :func:`herding_select`)."""
-    P = len(groups)
-    nmax = max(int(g.numel()) for g in groups)
-    dev = feats.device
-    idx = torch.zeros(P, nmax, dtype=torch.long, device=dev)
-    valid = torch.zeros(P, nmax, dtype=torch.bool, device=dev)
+def group_matrix(groups: List[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """List of per-identity row-index vectors -> padded ``[P, nmax]`` index matrix + ``[P]`` counts."""
+    dev = groups[0].device
+    counts = torch.tensor([int(g.numel()) for g in groups], device=dev)
+    idx = torch.zeros(len(groups), int(counts.max()), dtype=torch.long, device=dev)
     for gi, g in enumerate(groups):
         idx[gi, :g.numel()] = g
-        valid[gi, :g.numel()] = True
+    return idx, counts
+
+
+def herding_select_batched(feats: torch.Tensor, idx: torch.Tensor, counts: torch.Tensor, m: int) -> torch.Tensor:
+    """Herding for all identities at once. ``idx[g, :counts[g]]`` are the rows of ``feats`` that belong to identity
+    g. Returns ``[P, m]`` positions *within each identity's row list* (same rule as :func:`herding_select`).
+    CUDA: one kernel, one block per identity, the whole m-step loop on the device (``csrc/fused_ops.cu``)."""
+    P, nmax = idx.shape
+    dev = feats.device
+    picks = torch.empty(P, m, dtype=torch.long, device=dev)
+    if feats.is_cuda:
+        from ..ops import native
+        lib = native.load()
+        f = feats.float().contiguous()
+        rc = lib.flpr_herding(native.ptr(f), native.ptr(idx.contiguous()), native.ptr(counts.to(torch.int32)),
+                              native.ptr(picks), P, nmax, f.shape[1], m, native.stream(dev))
+        if rc == 0:
+            native.count_launch()
+            return picks
+        if rc != -3:                                   # -3: does not fit in shared memory -> tensor-op path below
+            native.check(rc, "flpr_herding")
+    valid = torch.arange(nmax, device=dev)[None, :] < counts[:, None]
     f = feats.float()[idx] * valid.unsqueeze(-1)                             # [P, nmax, D]
-    cnt = valid.sum(1, keepdim=True).clamp(min=1)
+    cnt = counts.view(-1, 1).clamp(min=1)
     mean = f.sum(1) / cnt                                                    # [P, D]
     sq = (f * f).sum(2).masked_fill(~valid, float("inf"))                    # padding can never win the argmin
     S = torch.zeros_like(mean)
-    picks = torch.empty(P, m, dtype=torch.long, device=dev)
     ar = torch.arange(P, device=dev)
     for t in range(m):
         c = (t + 1) * mean - S
@@ -284,15 +348,19 @@ class Operator(OperatorModule):
         protos, pids, cids = [], [], []
         folded = model.folded_trunk()
         chunk = int(getattr(model, "trunk_batch", 256))         # the frozen trunk is inference-only: batch it wider
+        if folded is not None and hasattr(source_loader, "iterate"):
+            batches = source_loader.iterate(chunk, ordered=True)   # sample order is irrelevant here (permuted later)
+        else:
+            batches = source_loader
         pend: List[torch.Tensor] = []
 
         def flush():
             if pend:
                 big = torch.cat(pend) if len(pend) > 1 else pend[0]
-                protos.append(folded(big).clone())             # graph-owned output buffer -> keep a copy
+                protos.append(folded(big))                     # caller-owned copy of the graph's output buffer
                 pend.clear()
 
-        for data, person_id, classes_id in source_loader:
+        for data, person_id, classes_id in batches:
             data = model.prepare_input(data)
             if folded is not None:
                 pend.append(data)
@@ -526,6 +594,39 @@ class Server(ServerModule):
         rel = rel / rel.sum()
         return select, torch.softmax(rel, dim=0)
 
+    def relevance_rows(self, client_names: Sequence[str]) -> Tuple[List[str], torch.Tensor]:
+        """Mixing weights of several receiving clients at once: ``(memory order, W [len(client_names), N])``.
+        Same arithmetic as :meth:`relevance_row` (decayed KL of the task tokens, inverse, own = mean of the others,
+        normalise, softmax) evaluated as a handful of batched tensor ops instead of ``R x N x T`` small ones."""
+        order = list(self.token_memory.keys())
+        N, R = len(order), len(client_names)
+        dev = self.token_memory[order[0]][-1].device
+        if N == 1:
+            return order, torch.ones(R, 1, device=dev)
+        P = torch.stack([self.token_memory[n][-1] for n in client_names]).float()          # [R, D]
+        ent, owner, wgt = [], [], []
+        for j, name in enumerate(order):
+            for t, tok in enumerate(self.token_memory[name][::-1 * self.distance_calculate_step]):
+                ent.append(tok)
+                owner.append(j)
+                wgt.append(1.0 / math.pow(self.distance_calculate_decay, t))
+        Q = torch.stack(ent).float()                                                        # [E, D]
+        logP = F.log_softmax(P, dim=-1)
+        logQ = F.log_softmax(Q, dim=-1)
+        Qs = logQ.exp()
+        A = (Qs * logQ).sum(-1)                                                             # [E]
+        kl = torch.stack([A - (Qs * logP[i]).sum(-1) for i in range(R)])                    # [R, E]
+        owner_t = torch.tensor(owner, device=dev)
+        w_t = torch.tensor(wgt, device=dev, dtype=kl.dtype)
+        dis = torch.full((R, N), 1e-8, device=dev, dtype=kl.dtype).index_add_(1, owner_t, kl * w_t[None, :])
+        rel = 1.0 / dis
+        me = torch.tensor([order.index(n) for n in client_names], device=dev)
+        mask = F.one_hot(me, N).bool()
+        others_mean = rel.masked_fill(mask, 0.0).sum(1, keepdim=True) / (N - 1)
+        rel = torch.where(mask, others_mean, rel)
+        rel = rel / rel.sum(1, keepdim=True)
+        return order, torch.softmax(rel, dim=1)
+
     def prepare_dispatch(self, online_names: Sequence[str], first_contact: Sequence[str]) -> None:
         """Collective: every rank mixes for its local, already-registered online clients in ONE kernel."""
         self._delivered = {}
@@ -537,12 +638,15 @@ class Server(ServerModule):
         col = {cid: j for j, cid in enumerate(self.uploaded)}
         dev = self.model.device
         rows = torch.zeros(len(recv), K, device=dev)
-        for i, name in enumerate(recv):
-            select, w = self.relevance_row(name)
-            for c_name, wv in zip(select, w):
-                self.logger.info(f"Relevant ratio between {name} and {c_name}: {float(wv):.4f}")
-            cols = torch.tensor([col[self.client_ids[c]] for c in select], device=dev)
-            rows[i, cols] = w.to(dev)
+        if recv:
+            order, W = self.relevance_rows(recv)
+            cols = torch.tensor([col[self.client_ids[c]] for c in order], device=dev)
+            rows[:, cols] = W.to(dev)
+            if self.logger.enabled_for_info():
+                flat = W.tolist()                                 # ONE host sync for the whole mixing matrix
+                for name, wr in zip(recv, flat):
+                    for c_name, wv in zip(order, wr):
+                        self.logger.info(f"Relevant ratio between {name} and {c_name}: {wv:.4f}")
         models = [self.local_clients[n].model for n in recv]
         n_theta = self.model.theta_numel
         self.comm.mix("theta_up", self.uploaded, rows, list(range(len(recv))),

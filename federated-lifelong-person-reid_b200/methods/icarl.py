@@ -24,7 +24,7 @@ import torch.nn.functional as F
 from ..runtime.arena import ArenaOptimizer
 from ..runtime.modules import ClientModule, ModelModule, OperatorModule, ServerModule, _bind_loader
 from ..utils.misc import get_one_hot
-from .fedstil import herding_select_batched
+from .fedstil import group_matrix, herding_select_batched
 
 
 class Model(ModelModule):
@@ -120,7 +120,7 @@ class Model(ModelModule):
         if not upids:
             return
         groups = [torch.nonzero(ids == pid).squeeze(1) for pid in upids]
-        picks = herding_select_batched(feats, groups, self.m).cpu()
+        picks = herding_select_batched(feats, *group_matrix(groups), self.m).cpu()
         for gi, pid in enumerate(upids):
             uniq, inverse = torch.unique(picks[gi], return_inverse=True)
             sel = groups[gi][uniq.to(groups[gi].device)]

@@ -11,6 +11,7 @@ runs on the hand-written tcgen05 kernels. Trunk implicit-GEMM kernels are listed
 """
 from __future__ import annotations
 
+import threading
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -44,7 +45,8 @@ class FoldedTrunk:
                 for u in getattr(base, f"layer{i}"):
                     self.ops.append(("unit", self._fold_unit(u)))
         self.use_graphs = use_graphs and self.device.type == "cuda"
-        self._graphs: Dict[Tuple[int, int, int], Tuple] = {}
+        self._graphs: Dict[Tuple, List[dict]] = {}
+        self._slot_lock = threading.Lock()
         self._fused_ok = self._probe_fused()
 
     def _fold_unit(self, u) -> dict:
@@ -104,13 +106,42 @@ class FoldedTrunk:
     @torch.no_grad()
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         """``x``: float / bf16 ``[B,3,H,W]`` (any memory format). Returns the feature map at the cut (bf16,
-        channels_last). The returned tensor is a graph-owned buffer when graphs are on: consume it before the next call."""
+        channels_last) as a tensor owned by the caller.
+
+        One captured graph (+ static input / output buffers) per *slot* and batch shape. Concurrent callers (client
+        threads on different streams) take different slots; a slot is handed over with an event so that its static
+        buffers are never rewritten while a previous user's replay or read-out is still in flight."""
         x = x.to(self.dtype).contiguous(memory_format=torch.channels_last)
         if not self.use_graphs:
             return self._forward(x)
         key = tuple(x.shape)
-        entry = self._graphs.get(key)
-        if entry is None:
+        slot = self._acquire(key, x)
+        try:
+            cur = torch.cuda.current_stream(self.device)
+            if slot["event"] is not None:
+                cur.wait_event(slot["event"])
+            slot["in"].copy_(x)
+            slot["graph"].replay()
+            out = slot["out"].clone()
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            slot["event"] = ev
+        finally:
+            with self._slot_lock:
+                slot["busy"] = False
+        return out
+
+    def _acquire(self, key, x: torch.Tensor) -> dict:
+        from ..runtime.graphs import CAPTURE_LOCK, capture
+        with self._slot_lock:
+            slots = self._graphs.setdefault(key, [])
+            for sl in slots:
+                if not sl["busy"]:
+                    sl["busy"] = True
+                    return sl
+            sl = {"busy": True, "event": None, "graph": None}
+            slots.append(sl)
+        with CAPTURE_LOCK:
             static_in = x.clone()
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
@@ -119,14 +150,10 @@ class FoldedTrunk:
                     self._forward(static_in)
             torch.cuda.current_stream(self.device).wait_stream(side)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with capture(g):
                 static_out = self._forward(static_in)
-            entry = (g, static_in, static_out)
-            self._graphs[key] = entry
-        g, static_in, static_out = entry
-        static_in.copy_(x)
-        g.replay()
-        return static_out
+            sl["graph"], sl["in"], sl["out"] = g, static_in, static_out
+        return sl
 
 
 _SHARED: Dict[Tuple, FoldedTrunk] = {}

@@ -222,8 +222,8 @@ class FastResNetHead:
         v = w.permute(0, 2, 3, 1)
         return v if v.is_contiguous() else v.contiguous()
 
-    def _conv(self, x: torch.Tensor, conv: nn.Conv2d) -> torch.Tensor:
-        """x: [N,H,W,C] bf16 -> [N,H',W',Cout] bf16"""
+    def _conv(self, x: torch.Tensor, conv: nn.Conv2d, want_stats: bool = False):
+        """x: [N,H,W,C] bf16 -> [N,H',W',Cout] bf16 (``(y, col_part)`` with ``want_stats``: fused BN statistics)"""
         w = conv.weight
         sh = self.shadow(w)
         k, s = conv.kernel_size[0], conv.stride[0]
@@ -233,22 +233,38 @@ class FastResNetHead:
             w2 = self._ohwi(w).reshape(w.shape[0], c)
             s2 = self._ohwi(sh).reshape(w.shape[0], c) if sh is not None else None
             g2 = self._ohwi(gs).reshape(w.shape[0], c) if gs is not None else None
+            if want_stats:
+                y, part = gops.linear(x.reshape(-1, c), w2, s2, g2, True)
+                return y.view(n, h, wd, -1), part
             return gops.linear(x.reshape(-1, c), w2, s2, g2).view(n, h, wd, -1)
         if k == 3 and s == 1 and c % 64 == 0 and 128 % wd == 0 and ((h * wd <= 128 and 128 % (h * wd) == 0)
                                                                    or (h * wd > 128 and h % (128 // wd) == 0)):
             return gops.conv3x3(x, self._ohwi(w), self._ohwi(sh) if sh is not None else None,
-                                self._ohwi(gs) if gs is not None else None)
+                                self._ohwi(gs) if gs is not None else None, want_stats)
         # library fallback (strided convs)
         y = F.conv2d(x.permute(0, 3, 1, 2), (sh if sh is not None else w.to(torch.bfloat16)) if not w.requires_grad
                      else w.to(torch.bfloat16), stride=s, padding=k // 2)
-        return y.permute(0, 2, 3, 1).contiguous()
+        y = y.permute(0, 2, 3, 1).contiguous()
+        return (y, None) if want_stats else y
 
-    def _bn(self, x: torch.Tensor, bn: nn.BatchNorm2d, relu: bool, residual: Optional[torch.Tensor] = None):
+    def _conv_bn(self, x: torch.Tensor, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool,
+                 residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """conv -> batch-norm (-> +residual) (-> ReLU). In training mode the batch statistics come out of the
+        convolution's epilogue (fp32 accumulators), so the separate statistics pass over the activation disappears."""
+        if bn.training and x.is_cuda and self.fuse_bn_stats:
+            y, part = self._conv(x, conv, True)
+            return self._bn(y, bn, relu, residual, part)
+        return self._bn(self._conv(x, conv), bn, relu, residual)
+
+    fuse_bn_stats = True
+
+    def _bn(self, x: torch.Tensor, bn: nn.BatchNorm2d, relu: bool, residual: Optional[torch.Tensor] = None,
+            pre_part: Optional[torch.Tensor] = None):
         n, h, w, c = x.shape
         res2 = residual.reshape(-1, c) if residual is not None else None
         y = fops.batch_norm_nhwc(x.reshape(-1, c), bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                  training=bn.training, eps=bn.eps, momentum=bn.momentum or 0.1, relu=relu,
-                                 residual=res2)
+                                 residual=res2, pre_part=pre_part)
         if bn.training and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
         return y.view(n, h, w, c)
@@ -256,12 +272,12 @@ class FastResNetHead:
     def _unit(self, x: torch.Tensor, u: ResidualUnit) -> torch.Tensor:
         identity = x
         if u.downsample is not None:
-            identity = self._bn(self._conv(x, u.downsample[0]), u.downsample[1], relu=False)
-        out = self._bn(self._conv(x, u.conv1), u.bn1, relu=True)
+            identity = self._conv_bn(x, u.downsample[0], u.downsample[1], relu=False)
+        out = self._conv_bn(x, u.conv1, u.bn1, relu=True)
         if u.kind == "basic":
-            return self._bn(self._conv(out, u.conv2), u.bn2, relu=True, residual=identity)
-        out = self._bn(self._conv(out, u.conv2), u.bn2, relu=True)
-        return self._bn(self._conv(out, u.conv3), u.bn3, relu=True, residual=identity)
+            return self._conv_bn(out, u.conv2, u.bn2, relu=True, residual=identity)
+        out = self._conv_bn(out, u.conv2, u.bn2, relu=True)
+        return self._conv_bn(out, u.conv3, u.bn3, relu=True, residual=identity)
 
     def __call__(self, fmap: torch.Tensor):
         m = self.m

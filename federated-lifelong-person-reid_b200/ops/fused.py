@@ -162,20 +162,25 @@ class _BNTrainFn(torch.autograd.Function):
     """Training-mode batch norm over ``[M, C]`` bf16 (NHWC flattened), optional fused residual add + ReLU."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, eps, momentum, relu):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, eps, momentum, relu, pre_part=None):
         m, c = x.shape
         dev = x.device
         y = torch.empty_like(x)
         lib = native.load()
         scratch = torch.empty(6, c, dtype=torch.float32, device=dev)  # -, -, mean, rstd, scale, shift
-        part = torch.empty(lib.flpr_bn_partials_floats(m, c), dtype=torch.float32, device=dev)
+        if pre_part is None:
+            part = torch.empty(lib.flpr_bn_partials_floats(m, c), dtype=torch.float32, device=dev)
+            npre = 0
+        else:                       # statistics already reduced to column partials by the convolution's epilogue
+            part, npre = None, pre_part.shape[0]
+            assert pre_part.is_contiguous() and pre_part.shape[1:] == (2, c)
         rc = lib.flpr_bn_fwd(native.ptr(x), native.ptr(gamma), native.ptr(beta), native.ptr(residual), native.ptr(y),
                              native.ptr(part), native.ptr(scratch[2]),
                              native.ptr(scratch[3]), native.ptr(scratch[4]), native.ptr(scratch[5]),
                              native.ptr(running_mean), native.ptr(running_var), m, c, eps, momentum, int(relu),
-                             native.stream(dev))
+                             native.ptr(pre_part), npre, native.stream(dev))
         native.check(rc, "flpr_bn_fwd")
-        native.count_launch(3)
+        native.count_launch(3 if pre_part is None else 2)
         ctx.save_for_backward(x, y, gamma, scratch)
         ctx.relu = relu
         ctx.has_res = residual is not None
@@ -197,18 +202,26 @@ class _BNTrainFn(torch.autograd.Function):
                              native.stream(x.device))
         native.check(rc, "flpr_bn_bwd")
         native.count_launch(3)
-        return dx, dgb[0], dgb[1], None, None, dres, None, None, None
+        return dx, dgb[0], dgb[1], None, None, dres, None, None, None, None
 
 
 def batch_norm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, running_mean: Optional[torch.Tensor],
                     running_var: Optional[torch.Tensor], *, training: bool, eps: float = 1e-5, momentum: float = 0.1,
-                    relu: bool = False, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """BatchNorm over ``[M, C]`` (channels last) with fused residual + ReLU. fp32 affine parameters."""
+                    relu: bool = False, residual: Optional[torch.Tensor] = None,
+                    pre_part: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """BatchNorm over ``[M, C]`` (channels last) with fused residual + ReLU. fp32 affine parameters.
+    ``pre_part`` ``[P, 2, C]``: column partials (sum, sum of squares) of the producer's fp32 output, written by the
+    GEMM / conv epilogue; when given, the statistics pass over ``x`` is skipped."""
     if not x.is_cuda:
         xf = x.float()
         if training:
-            mean = xf.mean(0)
-            var = xf.var(0, unbiased=False)
+            if pre_part is not None:
+                n = xf.shape[0]
+                mean = pre_part[:, 0].sum(0) / n
+                var = (pre_part[:, 1].sum(0) / n - mean * mean).clamp_min(0)
+            else:
+                mean = xf.mean(0)
+                var = xf.var(0, unbiased=False)
             if running_mean is not None:
                 with torch.no_grad():
                     n = xf.shape[0]
@@ -224,7 +237,7 @@ def batch_norm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, ru
         return y.to(x.dtype)
     x = x.contiguous()
     if training:
-        return _BNTrainFn.apply(x, gamma, beta, running_mean, running_var, residual, eps, momentum, relu)
+        return _BNTrainFn.apply(x, gamma, beta, running_mean, running_var, residual, eps, momentum, relu, pre_part)
     scale = gamma * torch.rsqrt(running_var + eps)
     shift = beta - running_mean * scale
     return affine_act(x, scale, shift, relu=relu, residual=residual)

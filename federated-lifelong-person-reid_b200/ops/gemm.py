@@ -21,15 +21,37 @@ def _bf(x: torch.Tensor) -> torch.Tensor:
     return x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
 
 
+def col_part_rows(m: int) -> int:
+    """Number of partial rows the GEMM epilogue writes for ``m`` output rows (4 epilogue warps per 128-row tile)."""
+    return ((m + 127) // 128) * 4
+
+
+def col_part_buffer(m: int, n: int, device) -> torch.Tensor:
+    return torch.empty(col_part_rows(m), 2, n, dtype=torch.float32, device=device)
+
+
+def _col_part_reference(d: torch.Tensor, col_part: torch.Tensor) -> None:
+    """CPU reference of the fused statistics: 32-row partial sums of ``d`` and ``d*d``."""
+    m, n = d.shape
+    rows = col_part.shape[0]
+    pad = rows * 32 - m
+    dd = torch.cat([d.float(), d.new_zeros(pad, n).float()]) if pad else d.float()
+    dd = dd.view(rows, 32, n)
+    col_part[:, 0].copy_(dd.sum(1))
+    col_part[:, 1].copy_((dd * dd).sum(1))
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: bool = True,
          out_dtype: torch.dtype = torch.bfloat16, trans_out: bool = False, alpha: float = 1.0,
          bias_n: Optional[torch.Tensor] = None, bias_m: Optional[torch.Tensor] = None, relu: bool = False,
          residual: Optional[torch.Tensor] = None, split_k: int = 1, bn: int = 0,
-         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, col_part: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``D[M,N] = alpha * A @ B^T`` with bf16 operands and fp32 accumulation.
 
     ``a`` is ``[M,K]`` (``a_kmajor``) or ``[K,M]``; ``b`` is ``[N,K]`` (``b_kmajor``) or ``[K,N]``.
     Returns ``[M,N]`` (``[N,M]`` when ``trans_out``). ``split_k > 1`` accumulates atomically into a zeroed fp32 output.
+    ``col_part`` (fp32 ``[ceil(M/128)*4, 2, N]``, see :func:`col_part_buffer`) receives per-32-row partial column
+    sums / sums of squares of the fp32 result: the batch-norm statistics pass over the output is fused away.
     """
     M, K = (a.shape if a_kmajor else (a.shape[1], a.shape[0]))
     N, Kb = (b.shape if b_kmajor else (b.shape[1], b.shape[0]))
@@ -39,6 +61,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
         B = b.float() if b_kmajor else b.float().t()
         A, B = A.to(torch.bfloat16).float(), B.to(torch.bfloat16).float()
         d = alpha * (A @ B.t())
+        if col_part is not None:
+            _col_part_reference(d, col_part)
         if bias_n is not None:
             d = d + bias_n.float()[None, :]
         if bias_m is not None:
@@ -73,7 +97,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
     rc = lib.flpr_gemm_bf16(native.ptr(a), native.ptr(b), native.ptr(out), M, N, K, lda, ldb, out.stride(0),
                             0 if a_kmajor else 1, 0 if b_kmajor else 1, int(out.dtype == torch.bfloat16),
                             int(trans_out), float(alpha), native.ptr(bias_n), native.ptr(bias_m), int(relu),
-                            native.ptr(residual), int(split_k), int(bn), native.stream(a.device))
+                            native.ptr(residual), int(split_k), int(bn), native.ptr(col_part),
+                            native.stream(a.device))
     native.check(rc, "flpr_gemm_bf16")
     native.count_launch()
     return out
@@ -81,7 +106,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
 
 def conv_nhwc(x: torch.Tensor, w: torch.Tensor, *, padding: int = 1, out_dtype: torch.dtype = torch.bfloat16,
               alpha: float = 1.0, bias: Optional[torch.Tensor] = None, relu: bool = False,
-              residual: Optional[torch.Tensor] = None, bn: int = 0) -> torch.Tensor:
+              residual: Optional[torch.Tensor] = None, bn: int = 0,
+              col_part: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Stride-1 convolution as an implicit GEMM. ``x``: ``[N,H,W,C]`` bf16, ``w``: ``[Cout,KH,KW,C]``.
 
     Returns ``[N,H,W,Cout]``. Zero padding is produced by TMA out-of-bounds fill.
@@ -93,6 +119,8 @@ def conv_nhwc(x: torch.Tensor, w: torch.Tensor, *, padding: int = 1, out_dtype: 
         xx = x.to(torch.bfloat16).float().permute(0, 3, 1, 2)
         ww = w.to(torch.bfloat16).float().permute(0, 3, 1, 2)
         y = alpha * F.conv2d(xx, ww, padding=padding)
+        if col_part is not None:
+            _col_part_reference(y.permute(0, 2, 3, 1).reshape(-1, cout), col_part)
         if bias is not None:
             y = y + bias.float()[None, :, None, None]
         y = y.permute(0, 2, 3, 1)
@@ -108,8 +136,31 @@ def conv_nhwc(x: torch.Tensor, w: torch.Tensor, *, padding: int = 1, out_dtype: 
         assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.shape == out.shape
     rc = lib.flpr_conv_nhwc_bf16(native.ptr(x), native.ptr(w), native.ptr(out), n, h, wd, c, cout, kh, kw, padding,
                                  padding, int(out_dtype == torch.bfloat16), float(alpha), native.ptr(bias), int(relu),
-                                 native.ptr(residual), int(bn), native.stream(x.device))
+                                 native.ptr(residual), int(bn), native.ptr(col_part), native.stream(x.device))
     native.check(rc, "flpr_conv_nhwc_bf16")
+    native.count_launch()
+    return out
+
+
+def conv_dgrad_nhwc(dy: torch.Tensor, w: torch.Tensor, *, padding: int = 1,
+                    out_dtype: torch.dtype = torch.bfloat16, bn: int = 0) -> torch.Tensor:
+    """Data gradient of a stride-1 convolution from the FORWARD weight ``w`` ``[Cout,KH,KW,Cin]`` (no flipped /
+    transposed weight copy: the kernel walks the taps mirrored and reads ``w`` MN-major). ``dy``: ``[N,H,W,Cout]``."""
+    n, h, wd, cout = dy.shape
+    cout2, kh, kw, cin = w.shape
+    assert cout == cout2
+    if not dy.is_cuda:
+        dd = dy.to(torch.bfloat16).float().permute(0, 3, 1, 2)
+        ww = w.to(torch.bfloat16).float().permute(0, 3, 1, 2)                 # [Cout,Cin,KH,KW]
+        dx = torch.nn.grad.conv2d_input((n, cin, h, wd), ww, dd, padding=padding)
+        return dx.permute(0, 2, 3, 1).to(out_dtype).contiguous()
+    lib = native.load()
+    dy, w = _bf(dy).contiguous(), _bf(w).contiguous()
+    out = torch.empty((n, h, wd, cin), dtype=out_dtype, device=dy.device)
+    rc = lib.flpr_conv_dgrad_nhwc_bf16(native.ptr(dy), native.ptr(w), native.ptr(out), n, h, wd, cin, cout, kh, kw,
+                                       padding, padding, int(out_dtype == torch.bfloat16), int(bn),
+                                       native.stream(dy.device))
+    native.check(rc, "flpr_conv_dgrad_nhwc_bf16")
     native.count_launch()
     return out
 
@@ -131,14 +182,20 @@ class _LinearFn(torch.autograd.Function):
     ``AccumulateGrad`` read-modify-write pass."""
 
     @staticmethod
-    def forward(ctx, x, w_master, w_bf16, grad_out):
+    def forward(ctx, x, w_master, w_bf16, grad_out, want_stats=False):
         ctx.save_for_backward(x, w_bf16)
         ctx.w_needs_grad = w_master.requires_grad
         ctx.grad_out = grad_out
-        return gemm(x, w_bf16)
+        ctx.want_stats = want_stats
+        if not want_stats:
+            return gemm(x, w_bf16)
+        part = col_part_buffer(x.shape[0], w_bf16.shape[0], x.device)
+        y = gemm(x, w_bf16, col_part=part)
+        ctx.mark_non_differentiable(part)
+        return y, part
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, *_):
         x, w = ctx.saved_tensors
         dy = _bf(dy).contiguous()
         dx = dw = None
@@ -151,45 +208,51 @@ class _LinearFn(torch.autograd.Function):
                 gemm(dy, x, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32, split_k=split, out=ctx.grad_out)
             else:
                 dw = gemm(dy, x, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32, split_k=split)
-        return dx, dw, None, None
+        return dx, dw, None, None, None
 
 
 def linear(x: torch.Tensor, w_master: torch.Tensor, w_bf16: Optional[torch.Tensor] = None,
-           grad_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+           grad_out: Optional[torch.Tensor] = None, want_stats: bool = False):
     """Linear / 1x1-conv on flattened NHWC activations. ``w_master`` fp32 ``[out,in]`` receives the gradient
-    (directly in ``grad_out`` when given - it must be zero on entry)."""
+    (directly in ``grad_out`` when given - it must be zero on entry). ``want_stats`` additionally returns the fused
+    batch-norm column partials of the output (``(y, part)``)."""
     if w_bf16 is None:
         w_bf16 = w_master.detach().to(torch.bfloat16)
     if grad_out is not None and not x.is_cuda:
         grad_out = None
-    return _LinearFn.apply(_bf(x), w_master, w_bf16, grad_out)
+    return _LinearFn.apply(_bf(x), w_master, w_bf16, grad_out, want_stats)
 
 
 class _Conv3x3Fn(torch.autograd.Function):
     """3x3 / stride 1 / pad 1 NHWC convolution: forward, dgrad and wgrad all on the tcgen05 implicit-GEMM kernel."""
 
     @staticmethod
-    def forward(ctx, x, w_master, w_bf16, grad_out):
+    def forward(ctx, x, w_master, w_bf16, grad_out, want_stats=False):
         ctx.save_for_backward(x, w_bf16)
         ctx.w_needs_grad = w_master.requires_grad
         ctx.grad_out = grad_out
-        return conv_nhwc(x, w_bf16, padding=1)
+        if not want_stats:
+            return conv_nhwc(x, w_bf16, padding=1)
+        n, h, wd, _ = x.shape
+        part = col_part_buffer(n * h * wd, w_bf16.shape[0], x.device)
+        y = conv_nhwc(x, w_bf16, padding=1, col_part=part)
+        ctx.mark_non_differentiable(part)
+        return y, part
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, *_):
         x, w = ctx.saved_tensors
         dy = _bf(dy).contiguous()
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            # dgrad = correlation of dy with the spatially flipped, channel-transposed filter
-            wt = w.flip(1, 2).permute(3, 1, 2, 0).contiguous()            # [Cin,KH,KW,Cout]
-            dx = conv_nhwc(dy, wt, padding=1)
+            # dgrad straight from the forward weight: mirrored taps + MN-major B operand inside the kernel
+            dx = conv_dgrad_nhwc(dy, w, padding=1)
         if ctx.w_needs_grad:
             if ctx.grad_out is not None:
                 conv3x3_wgrad(x, dy, out=ctx.grad_out)
             else:
                 dw = conv3x3_wgrad(x, dy)
-        return dx, dw, None, None
+        return dx, dw, None, None, None
 
 
 def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -220,9 +283,9 @@ def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, out: Optional[torch.Tensor]
 
 
 def conv3x3(x: torch.Tensor, w_master: torch.Tensor, w_bf16: Optional[torch.Tensor] = None,
-            grad_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+            grad_out: Optional[torch.Tensor] = None, want_stats: bool = False):
     if w_bf16 is None:
         w_bf16 = w_master.detach().to(torch.bfloat16)
     if grad_out is not None and not x.is_cuda:
         grad_out = None
-    return _Conv3x3Fn.apply(_bf(x), w_master, w_bf16, grad_out)
+    return _Conv3x3Fn.apply(_bf(x), w_master, w_bf16, grad_out, want_stats)

@@ -36,8 +36,9 @@ def available() -> bool:
 def _declare(lib: C.CDLL) -> None:
     P, I, F, Z, L, D = c_void_p, c_int, c_float, c_size_t, c_ll, c_double
     sig = {
-        "flpr_gemm_bf16": [P, P, P, I, I, I, L, L, L, I, I, I, I, F, P, P, I, P, I, I, P],
-        "flpr_conv_nhwc_bf16": [P, P, P, I, I, I, I, I, I, I, I, I, I, F, P, I, P, I, P],
+        "flpr_gemm_bf16": [P, P, P, I, I, I, L, L, L, I, I, I, I, F, P, P, I, P, I, I, P, P],
+        "flpr_conv_nhwc_bf16": [P, P, P, I, I, I, I, I, I, I, I, I, I, F, P, I, P, I, P, P],
+        "flpr_conv_dgrad_nhwc_bf16": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
         "flpr_conv_wgrad_nhwc_bf16": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
         "flpr_symm_alloc": [C.POINTER(P), Z],
         "flpr_symm_free": [P],
@@ -57,18 +58,22 @@ def _declare(lib: C.CDLL) -> None:
         "flpr_cast_bf16": [P, P, Z, P],
         "flpr_compose": [P, P, F, P, P, Z, P],
         "flpr_ce_label_smooth": [P, P, P, P, I, I, L, F, F, I, I, P],
-        "flpr_bn_fwd": [P, P, P, P, P, P, P, P, P, P, P, P, I, I, F, F, I, P],
+        "flpr_bn_fwd": [P, P, P, P, P, P, P, P, P, P, P, P, I, I, F, F, I, P, I, P],
         "flpr_affine_act": [P, P, P, P, P, I, I, I, P],
         "flpr_bn_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
         "flpr_bn_partials_floats": [I, I],
         "flpr_gap_fwd": [P, P, P, I, I, I, P],
         "flpr_gap_bwd": [P, P, I, I, I, P],
         "flpr_rank_eval": [P, P, P, P, P, I, I, L, P],
+        "flpr_augment_u8": [P, P, P, I, I, I, P, P, F, F, F, F, F, F, I, P],
+        "flpr_herding": [P, P, P, P, I, I, I, I, P],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = I
+    lib.flpr_gemm_set_persistent.argtypes = [I]
+    lib.flpr_gemm_set_persistent.restype = None
     for name in ("flpr_gemm_last_error", "flpr_comm_last_error"):
         getattr(lib, name).restype = C.c_char_p
         getattr(lib, name).argtypes = []

@@ -52,6 +52,15 @@ def expand_examplars(state: Any) -> Any:
     """Writer-side conversion of the compact exemplar memory into the reference's on-disk schema
     ``{np.int64 pid: [(ndarray prototype, class_id), ...]}`` (``methods/fedstil.py:841,846``)."""
     import numpy as np
+    if isinstance(state, dict) and "_compact_gens" in state:
+        out = {}
+        for gen in state["_compact_gens"]:
+            k = int(gen["k"])
+            bank = gen["bank"][:, :k].float().numpy()
+            cls = gen["cls"][:, :k].tolist()
+            for gi, pid in enumerate(gen["pids"].tolist()):
+                out[np.int64(pid)] = [(bank[gi, j], int(cls[gi][j])) for j in range(k)]
+        return out
     if not isinstance(state, dict) or "_compact_examplars" not in state:
         return state
     out = {}
@@ -122,7 +131,7 @@ class CheckpointStore:
         self._inflight: Dict[int, Tuple[_Slab, int]] = {}
         self._inflight_bytes = 0
         self._pool: Dict[int, List[_Slab]] = {}
-        self._lock = threading.Lock()
+        self._lock = threading.RLock()
         self._copy_stream = None
         self._last_copy_event = None
 
@@ -234,9 +243,10 @@ class CheckpointStore:
 
     def fence(self) -> None:
         """Make the compute stream wait for outstanding snapshot copies (call before sources are overwritten)."""
-        if self._last_copy_event is not None:
-            torch.cuda.current_stream().wait_event(self._last_copy_event)
-            self._last_copy_event = None
+        with self._lock:
+            if self._last_copy_event is not None:
+                torch.cuda.current_stream().wait_event(self._last_copy_event)
+                self._last_copy_event = None
 
     # ------------------------------------------------------------------ public API
     def save(self, actor: str, state_name: Optional[str], state: Any, cover: bool = False,
@@ -244,6 +254,10 @@ class CheckpointStore:
         """``save_state`` of ``modules/client.py:52-63`` / ``modules/server.py:46-57``."""
         if state_name is None or not self.enabled:
             return
+        with self._lock:                                  # client threads checkpoint concurrently
+            self._save_locked(actor, state_name, state, cover, post)
+
+    def _save_locked(self, actor: str, state_name: str, state: Any, cover: bool, post: Optional[str]) -> None:
         self._raise_pending()
         path = self.path(actor, state_name)
         if cover is False and os.path.exists(path):
@@ -302,10 +316,11 @@ class CheckpointStore:
             raise RuntimeError(f"checkpoint writer failed: {err}")
 
     def flush(self) -> None:
-        if self._started:
-            while self._inflight:
-                self._reap(block=True)
-        self._raise_pending()
+        with self._lock:
+            if self._started:
+                while self._inflight:
+                    self._reap(block=True)
+            self._raise_pending()
 
     def close(self) -> None:
         if self._started:

@@ -106,6 +106,10 @@ class ExperimentStage:
         return self
 
     def __exit__(self, exc_type, value, trace):
+        pool = getattr(self, "_pool", None)
+        if pool is not None:
+            pool.shutdown(wait=False)
+            self._pool = None
         if self._owns_pg and dist.is_initialized():
             dist.destroy_process_group()
         if exc_type is not None and issubclass(exc_type, Exception):
@@ -258,9 +262,13 @@ class ExperimentStage:
 
         # ---- local training ---------------------------------------------------------------------------------------
         with timer("train"):
-            for n in online:
-                if n in local:
-                    self._process_train(local[n], log, curr_round, self.container)
+            todo = [local[n] for n in online if n in local]
+            workers = min(self.container.max_worker(), len(todo))
+            if workers > 1 and self.device.type == "cuda" and eng.get("client_threads", True):
+                self._train_parallel(todo, log, curr_round, workers)
+            else:
+                for client in todo:
+                    self._process_train(client, log, curr_round, self.container)
 
         # ---- validation -------------------------------------------------------------------------------------------
         if curr_round % val_interval == 0:
@@ -284,6 +292,47 @@ class ExperimentStage:
         with timer("aggregate"):
             server.calculate()
         log.flush()
+
+    def _train_parallel(self, todo, log, curr_round: int, workers: int) -> None:
+        """``parallel`` clients per device train concurrently (the reference's thread pool, ``experiment.py:206-216``),
+        each on its own CUDA stream: while one client's thread waits for its epoch result (the early-stopping rule
+        needs loss / accuracy on the host) the other threads keep the GPU fed."""
+        from concurrent.futures import ThreadPoolExecutor
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event()
+        start.record(main)
+        done: List[torch.cuda.Event] = []
+
+        def run(client) -> None:
+            torch.cuda.set_device(dev)
+            stream = getattr(client, "_stream", None)
+            if stream is None:
+                stream = client._stream = torch.cuda.Stream(dev)
+            with torch.cuda.stream(stream):
+                stream.wait_event(start)
+                self._process_train(client, log, curr_round, self.container)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+            done.append(ev)
+
+        pool = getattr(self, "_pool", None)
+        if pool is None or getattr(self, "_pool_workers", 0) != workers:
+            if pool is not None:
+                pool.shutdown(wait=True)
+            pool = self._pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="flpr-client")
+            self._pool_workers = workers
+        futures = [pool.submit(run, c) for c in todo]
+        err = None
+        for f in futures:
+            try:
+                f.result(timeout=1800)
+            except Exception as ex:  # noqa: BLE001
+                err = err or ex
+        for ev in done:
+            main.wait_event(ev)
+        if err is not None:
+            raise err
 
     def _gather_logs(self, log: ExperimentLog) -> None:
         """C7: metrics of remote clients are gathered to rank 0, which owns the JSON file."""

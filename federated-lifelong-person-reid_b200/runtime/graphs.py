@@ -3,11 +3,22 @@ costs more than their device time). A step function is run eagerly a few times (
 warm-up), then captured once and replayed with its inputs copied into static buffers."""
 from __future__ import annotations
 
+import threading
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
 from ..ops import native
+
+
+# One capture at a time per process. Captures use the thread-local error mode so that client threads that are NOT
+# capturing (ExperimentStage runs `parallel` clients per device concurrently, each on its own stream) may keep
+# launching / allocating while another thread captures.
+CAPTURE_LOCK = threading.RLock()
+
+
+def capture(graph: "torch.cuda.CUDAGraph", **kw):
+    return torch.cuda.graph(graph, capture_error_mode="thread_local", **kw)
 
 
 class GraphedStep:
@@ -36,15 +47,16 @@ class GraphedStep:
                 st["eager"] += 1
                 self.fn(*tensors)
                 return
-            st["static"] = [t.clone() for t in tensors]
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            l0 = native.launches()
-            with torch.cuda.graph(g):
-                self.fn(*st["static"])
-            st["launches"] = native.launches() - l0
-            native.count_launch(-st["launches"])          # capture recorded, did not execute
-            st["graph"] = g
+            with CAPTURE_LOCK:
+                st["static"] = [t.clone() for t in tensors]
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                l0 = native.launches()
+                with capture(g):
+                    self.fn(*st["static"])
+                st["launches"] = native.launches() - l0
+                native.count_launch(-st["launches"])          # capture recorded, did not execute
+                st["graph"] = g
         for s, t in zip(st["static"], tensors):
             s.copy_(t, non_blocking=True)
         st["graph"].replay()

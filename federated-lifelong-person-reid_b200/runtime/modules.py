@@ -389,4 +389,6 @@ class ServerModule(_Actor):
 def _bind_loader(loader, model: ModelModule) -> None:
     """Point a :class:`DeviceBatchLoader` at the model's device / compute dtype (no-op for torch DataLoaders)."""
     if hasattr(loader, "to") and hasattr(loader, "augment"):
-        loader.to(model.device, torch.float32)
+        # bf16 models get bf16 NHWC batches straight out of the fused augmentation kernel (the first convolution
+        # would cast its input to bf16 anyway)
+        loader.to(model.device, model.compute_dtype if model.device.type == "cuda" else torch.float32)

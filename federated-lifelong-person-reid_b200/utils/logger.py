@@ -10,6 +10,9 @@ class Logger:
     def __init__(self, actuator: str = "unknown", rank: int | None = None):
         self.logger = logging.getLogger(actuator if rank is None else f"{actuator}@r{rank}")
 
+    def enabled_for_info(self) -> bool:
+        return self.logger.isEnabledFor(logging.INFO)
+
     def debug(self, msg) -> None:
         self.logger.debug(msg)
 

@@ -232,6 +232,12 @@ def test_fedstil_relevance_double_normalisation():
     rel.append(sum(rel) / len(rel))
     rel = torch.tensor(rel) / sum(rel)
     assert torch.allclose(w, torch.softmax(rel, 0), atol=1e-5)
+    # the batched form used by prepare_dispatch gives the same rows (columns in memory order)
+    order, W = srv.relevance_rows(["c1", "c0", "c2"])
+    assert order == ["c0", "c1", "c2"]
+    for r, name in enumerate(["c1", "c0", "c2"]):
+        sel, wr = srv.relevance_row(name)
+        assert torch.allclose(W[r, [order.index(c) for c in sel]], wr, atol=1e-5)
     srv.token_memory = {"a": [torch.randn(8)], "b": [torch.randn(8)]}
     _, w2 = srv.relevance_row("a")
     assert torch.allclose(w2, torch.tensor([0.5, 0.5]))       # N=2 gives exactly 0.5/0.5
@@ -274,3 +280,69 @@ def test_resnet_state_dict_names_and_split():
     r50 = nets["resnet50"](num_classes=10, last_stride=1, neck="bnneck")
     r50.configure_split(["base.layer4", "classifier"])
     assert r50.prototype_shape((256, 128)) == (1024, 16, 8)     # SURVEY §2.3 (x2 per side at 256x128)
+
+
+def test_conv_dgrad_cpu_reference_matches_autograd():
+    from flpr_b200.ops.gemm import conv_dgrad_nhwc
+    torch.manual_seed(0)
+    dy = torch.randn(2, 8, 4, 16)
+    w = torch.randn(16, 3, 3, 8) / 10
+    x = torch.zeros(2, 8, 4, 8, requires_grad=True)
+    y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.bfloat16().float().permute(0, 3, 1, 2), padding=1)
+    y.backward(dy.bfloat16().float().permute(0, 3, 1, 2))
+    out = conv_dgrad_nhwc(dy, w, padding=1, out_dtype=torch.float32)
+    assert torch.allclose(out, x.grad, atol=1e-4)
+
+
+def test_fused_bn_statistics_cpu_reference():
+    """linear(want_stats) -> batch_norm(pre_part) equals linear -> batch_norm on the CPU reference path."""
+    from flpr_b200.ops.gemm import linear
+    from flpr_b200.ops.fused import batch_norm_nhwc
+    torch.manual_seed(1)
+    x = torch.randn(100, 32)
+    w = torch.randn(16, 32) / 5
+    g, b = torch.rand(16) + 0.5, torch.randn(16)
+    y, part = linear(x, w, None, None, True)
+    assert part.shape == (4, 2, 16)
+    z1 = batch_norm_nhwc(y, g, b, torch.zeros(16), torch.ones(16), training=True, pre_part=part)
+    z2 = batch_norm_nhwc(linear(x, w), g, b, torch.zeros(16), torch.ones(16), training=True)
+    assert torch.allclose(z1.float(), z2.float(), atol=3e-2)
+
+
+def test_herding_batched_matches_single():
+    from flpr_b200.methods.fedstil import herding_select, herding_select_batched, group_matrix
+    torch.manual_seed(3)
+    feats = torch.randn(60, 16)
+    groups = [torch.arange(0, 7), torch.arange(7, 30), torch.arange(30, 31), torch.arange(31, 60)]
+    idx, counts = group_matrix(groups)
+    picks = herding_select_batched(feats, idx, counts, 9)
+    for gi, g in enumerate(groups):
+        assert picks[gi].tolist() == herding_select(feats[g], 9)
+
+
+def test_fedstil_exemplar_generations_roundtrip():
+    """build -> reduce -> expand -> reference-schema state -> load keeps the rehearsal set."""
+    from flpr_b200.runtime.builder import parser_model
+    cfg = {"name": "resnet18", "num_classes": 50, "last_stride": 1, "neck": "bnneck", "atten_default": 0.9,
+           "lambda_l1": 1e-3, "lambda_k": 12, "fine_tuning": ["base.layer4", "classifier"]}
+    model = parser_model("fedstil", cfg, torch.device("cpu"), {"compute_dtype": "fp32"})
+    c, h, w = model.net.prototype_shape((32, 16))
+    torch.manual_seed(0)
+    protos = torch.randn(24, c, h, w)
+    pids = torch.arange(24) % 4 + 10
+    model.ids.update([10, 11, 12, 13])
+    model.build_examplars(protos, pids, pids.clone(), [10, 11, 12, 13])
+    ex = model.examplar_tensors()
+    assert ex[0].shape[0] == 12 and sorted(set(ex[1].tolist())) == [10, 11, 12, 13]
+    model.ids.update([20, 21])                                   # m shrinks from 3 to 2
+    model.reduce_examplars()
+    assert model.examplar_tensors()[0].shape[0] == 8
+    state = model.examplars_state()
+    assert sorted(int(k) for k in state) == [10, 11, 12, 13] and all(len(v) == 2 for v in state.values())
+    before = model.examplar_tensors()
+    model.load_examplars_state(state)
+    after = model.examplar_tensors()
+    assert torch.allclose(before[0].float(), after[0].float()) and before[1].tolist() == after[1].tolist()
+    # herding the same identities again replaces their exemplars
+    model.build_examplars(protos, pids, pids.clone(), [10, 11])
+    assert sorted(model.examplars.keys()) == [10, 11, 12, 13]

@@ -106,3 +106,27 @@ def test_experiment_on_gpu(tmp_path, method):
                     assert v == v and 0.0 <= v <= 1e4, (k, v)
     root = os.path.join(common["checkpoints_dir"], cfg["exp_name"])
     assert os.path.isdir(os.path.join(root, "client-0"))
+
+
+@pytest.mark.parametrize("method", ["fedstil", "fedavg"])
+def test_experiment_with_concurrent_client_streams(tmp_path, method):
+    """`parallel: 2` = two client threads per device, each on its own CUDA stream (reference experiment.py:206-216)."""
+    from flpr_b200.runtime.experiment import ExperimentStage
+    from flpr_b200.data.synthetic import synthetic_source_factory
+    common = tiny_common(str(tmp_path), device="cuda:0")
+    common["parallel"] = 2
+    common["defaults"]["exp_opts"].update(comm_rounds=3, online_clients=4, val_interval=3)
+    common["defaults"]["task_opts"]["augment_opts"]["img_size"] = [64, 32]
+    common["defaults"]["task_opts"]["loader_opts"]["batch_size"] = 8
+    cfg = tiny_experiment(common, method, n_clients=4)
+    with ExperimentStage(common, [cfg], source_factory=synthetic_source_factory(num_ids=4, train_per_id=4,
+                                                                                size=(64, 32))) as stage:
+        log = stage.run_experiment(cfg)
+    data = log.records["data"]
+    assert len(data) == 4
+    for client in data.values():
+        assert set(client.keys()) >= {"1", "2", "3"} or set(client.keys()) >= {1, 2, 3}
+        for tasks in client.values():
+            for vals in tasks.values():
+                for k, v in vals.items():
+                    assert v == v and 0.0 <= v <= 1e4, (k, v)

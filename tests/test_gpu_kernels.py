@@ -7,6 +7,16 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["persistent", "classic"])
+def gemm_kernel_variant(request):
+    """Every test runs against both tcgen05 GEMM kernels: the persistent one (default) and the one-tile-per-CTA one."""
+    from flpr_b200.ops import native
+    lib = native.load()
+    lib.flpr_gemm_set_persistent(1 if request.param == "persistent" else 0)
+    yield request.param
+    lib.flpr_gemm_set_persistent(1)
+
+
 def _ref_gemm(a, b):
     return a.to(torch.bfloat16).float() @ b.to(torch.bfloat16).float().t()
 
@@ -87,6 +97,75 @@ def test_conv_nhwc(n, h, w, c, cout, ks):
                                      padding=ks // 2).permute(0, 2, 3, 1)
     out = conv_nhwc(x, wt, padding=ks // 2, out_dtype=torch.float32)
     _close(out, ref, rtol=1e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(4, 16, 8, 512, 512), (3, 8, 4, 64, 128), (2, 32, 16, 128, 64),
+                                            (64, 16, 8, 512, 512)])
+@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+def test_conv_dgrad_from_forward_weight(n, h, w, cin, cout, bn):
+    """dgrad straight from the forward weight (mirrored taps, MN-major B operand) vs conv2d_input."""
+    from flpr_b200.ops.gemm import conv_dgrad_nhwc
+    if bn > cin:
+        pytest.skip("tile wider than N")
+    torch.manual_seed(31)
+    dy = torch.randn(n, h, w, cout, device="cuda").bfloat16()
+    wt = (torch.randn(cout, 3, 3, cin, device="cuda") / math.sqrt(cout * 9)).bfloat16()
+    ref = torch.nn.grad.conv2d_input((n, cin, h, w), wt.float().permute(0, 3, 1, 2), dy.float().permute(0, 3, 1, 2),
+                                     padding=1).permute(0, 2, 3, 1)
+    out = conv_dgrad_nhwc(dy, wt, padding=1, out_dtype=torch.float32, bn=bn)
+    _close(out, ref, rtol=1e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("m,n,k", [(8192, 512, 1024), (8192, 2048, 512), (200, 136, 320), (1000, 2048, 256)])
+@pytest.mark.parametrize("bn", [0, 128, 256])
+def test_gemm_fused_bn_statistics(m, n, k, bn):
+    """col_part epilogue: 32-row partial column sums / sums of squares of the fp32 result."""
+    from flpr_b200.ops.gemm import gemm, col_part_buffer
+    torch.manual_seed(32)
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    b = (torch.randn(n, k, device="cuda") / math.sqrt(k)).bfloat16()
+    part = col_part_buffer(m, n, "cuda")
+    part.fill_(float("nan"))
+    y = gemm(a, b, col_part=part, bn=bn)
+    ref = a.float() @ b.float().t()
+    _close(y, ref)
+    assert torch.isfinite(part).all()
+    _close(part[:, 0].sum(0), ref.sum(0), rtol=1e-3, atol=1e-3 * ref.abs().sum(0).max().item())
+    _close(part[:, 1].sum(0), (ref * ref).sum(0), rtol=1e-3, atol=1e-3 * (ref * ref).sum(0).max().item())
+    # first partial row = rows 0..31
+    _close(part[0, 0], ref[:32].sum(0), rtol=1e-3, atol=1e-2)
+
+
+def test_conv_bn_fused_statistics_match_unfused():
+    """conv(+stats in the epilogue) -> BN must equal conv -> BN(with its own statistics pass), fwd and bwd."""
+    from flpr_b200.ops.gemm import conv3x3, linear
+    from flpr_b200.ops.fused import batch_norm_nhwc
+    torch.manual_seed(33)
+    for kind in ("conv", "linear"):
+        outs = []
+        for fused in (True, False):
+            torch.manual_seed(34)
+            if kind == "conv":
+                x = torch.randn(16, 16, 8, 128, device="cuda").bfloat16().requires_grad_(True)
+                w = (torch.randn(256, 3, 3, 128, device="cuda") / 30).requires_grad_(True)
+            else:
+                x = torch.randn(2048, 512, device="cuda").bfloat16().requires_grad_(True)
+                w = (torch.randn(256, 512, device="cuda") / 20).requires_grad_(True)
+            g = torch.rand(256, device="cuda").add_(0.5).requires_grad_(True)
+            b = torch.randn(256, device="cuda").requires_grad_(True)
+            rm, rv = torch.zeros(256, device="cuda"), torch.ones(256, device="cuda")
+            fn = conv3x3 if kind == "conv" else linear
+            if fused:
+                y, part = fn(x, w, None, None, True)
+            else:
+                y, part = fn(x, w), None
+            z = batch_norm_nhwc(y.reshape(-1, 256), g, b, rm, rv, training=True, relu=True, pre_part=part)
+            gz = torch.randn(z.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(5)).bfloat16()
+            z.backward(gz)
+            outs.append((z.detach(), x.grad, w.grad, g.grad, b.grad, rm, rv))
+        for a_, b_ in zip(*outs):
+            # statistics from fp32 accumulators vs from the bf16-rounded activation: bf16-level differences
+            _close(a_, b_, rtol=5e-2, atol=5e-2 * b_.float().abs().max().item() + 1e-6)
 
 
 def test_linear_and_conv_autograd():
@@ -319,3 +398,61 @@ def test_comm_single_rank():
     torch.cuda.synchronize()
     comm.check_errors()
     comm.close()
+
+
+@pytest.mark.parametrize("level", ["none", "default", "drastic"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_fused_augmentation_kernel(level, dtype):
+    """uint8 NHWC -> normalise + flip + erase + cast in one kernel vs the tensor-op reference (same uniforms)."""
+    from flpr_b200.data.augmentation import DeviceAugment
+    aug = DeviceAugment(level, dtype=dtype)
+    u8 = torch.randint(0, 256, (37, 256, 128, 3), dtype=torch.uint8, device="cuda")
+    g = torch.Generator("cuda")
+    g.manual_seed(7)
+    out = aug(u8, g)
+    g.manual_seed(7)
+    ref = aug.reference(u8, g)
+    assert out.shape == ref.shape == (37, 3, 256, 128) and out.dtype == dtype
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-5
+    # a rounding difference in the rectangle size may move an edge by one pixel on a few samples
+    bad = ((out.float() - ref.float()).abs() > tol).flatten(1).any(1).sum().item()
+    assert bad <= 2, f"{bad} samples differ"
+
+
+def test_herding_kernel_matches_tensor_path():
+    from flpr_b200.methods.fedstil import herding_select, herding_select_batched, group_matrix
+    torch.manual_seed(11)
+    feats = torch.randn(300, 2048, device="cuda")
+    sizes = [1, 5, 8, 17, 64, 40]
+    groups, o = [], 0
+    perm = torch.randperm(300, device="cuda")
+    for n in sizes:
+        groups.append(perm[o:o + n])
+        o += n
+    idx, counts = group_matrix(groups)
+    picks = herding_select_batched(feats, idx, counts, 12).cpu()
+    for gi, g in enumerate(groups):
+        ref = herding_select(feats[g].cpu(), 12)
+        assert picks[gi].tolist() == ref, (gi, picks[gi].tolist(), ref)
+
+
+def test_bulk_device_loader_covers_split():
+    from flpr_b200.data.synthetic import random_array_split
+    from flpr_b200.data.pipeline import DeviceBatchLoader
+    ds = random_array_split(100, 10, (64, 32), seed=3)
+    ld = DeviceBatchLoader(ds, 32, shuffle=True, level="none", mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225),
+                           device="cuda", dtype=torch.float32, seed=1)
+    assert ld._bulk_ok()
+    seen, n = [], 0
+    for data, pid, cid in ld:
+        assert data.is_cuda and data.shape[1:] == (3, 64, 32)
+        n += data.shape[0]
+        seen.append(pid)
+    assert n == 100 and sorted(torch.cat(seen).tolist()) == sorted(ds.pids.tolist())
+    wide = [d.shape[0] for d, _, _ in ld.iterate(64, ordered=True)]
+    assert wide == [64, 36]
+    ref = ld.augment.reference(ds.images[:64].cuda())
+    first = next(iter(ld.iterate(64, ordered=True)))[0]
+    assert torch.allclose(first, ref, atol=1e-5)
+    assert ld.h2d_bytes >= 2 * ds.images.numel()
