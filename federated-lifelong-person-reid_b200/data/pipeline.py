@@ -45,6 +45,7 @@ class DeviceBatchLoader:
         self.h2d_bytes = 0
         self._labels_dev = None
         self.bulk_limit_bytes = 2 << 30
+        self.device_generator: Optional[torch.Generator] = None     # CUDA generator of the owning model (if any)
 
     def to(self, device, dtype: Optional[torch.dtype] = None) -> "DeviceBatchLoader":
         self.device = torch.device(device)
@@ -64,7 +65,7 @@ class DeviceBatchLoader:
         if self.device.type == "cuda":
             u8 = u8.pin_memory().to(self.device, non_blocking=True)
             self.h2d_bytes += u8.numel()
-        return self.augment(u8), ds.pids[idx].to(self.device), ds.cidx[idx].to(self.device)
+        return self.augment(u8, self._gen_for(u8.device)), ds.pids[idx].to(self.device), ds.cidx[idx].to(self.device)
 
     def _order(self) -> torch.Tensor:
         n = len(self.dataset)
@@ -109,9 +110,9 @@ class DeviceBatchLoader:
         for s0 in range(0, last, bs):
             if shuffle:
                 idx = order[s0:s0 + bs]
-                yield self.augment(dev_all.index_select(0, idx)), pids[idx], cidx[idx]
+                yield self.augment(dev_all.index_select(0, idx), self._gen_for(dev)), pids[idx], cidx[idx]
             else:
-                yield self.augment(dev_all[s0:s0 + bs]), pids[s0:s0 + bs], cidx[s0:s0 + bs]
+                yield self.augment(dev_all[s0:s0 + bs], self._gen_for(dev)), pids[s0:s0 + bs], cidx[s0:s0 + bs]
 
     def _iter_staged(self, batch_size: Optional[int] = None, ordered: bool = False):
         ds = self.dataset
@@ -160,7 +161,11 @@ class DeviceBatchLoader:
             if ev is not None:
                 torch.cuda.current_stream(self.device).wait_event(ev)
                 u8.record_stream(torch.cuda.current_stream(self.device))
-            yield self.augment(u8), pid, cid
+            yield self.augment(u8, self._gen_for(u8.device)), pid, cid
+
+    def _gen_for(self, device) -> Optional[torch.Generator]:
+        g = self.device_generator
+        return g if g is not None and g.device == torch.device(device) else None
 
 
 class ReIDTaskPipeline:

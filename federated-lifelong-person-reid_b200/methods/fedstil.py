@@ -88,23 +88,24 @@ class Model(ModelModule):
         return math.ceil(self.lambda_k / max(len(self.ids), 1))
 
     # ---- reference checkpoint schema (fedstil.py:444-491) ------------------------------------------------------------
-    def model_state(self) -> Dict:
+    def model_state(self, copy: bool = True) -> Dict:
+        """``copy=False`` returns views of the live tensors: for callers that serialise immediately (the checkpoint
+        store stages them on its copy stream before anything can overwrite them, see ``CheckpointStore.fence``)."""
         a = self.arena
+        own = (lambda t: t.clone(memory_format=torch.contiguous_format)) if copy else (lambda t: t)
         gw, gwa, aw, ab = {}, {}, {}, {}
         for lname in self.adaptive_names:
             theta = a.view(a.master, f"{lname}.weight").detach()
             g = a.view(self.G, f"{lname}.weight").detach()
-            gw[f"{lname}.global_weight"] = g.clone(memory_format=torch.contiguous_format)
+            gw[f"{lname}.global_weight"] = own(g)
             gwa[f"{lname}.global_weight_atten"] = torch.full((theta.shape[-1],), self.atten_default,
                                                              device=theta.device)
-            aw[f"{lname}.adaptive_weight"] = (theta - self.atten_default * g).clone(
-                memory_format=torch.contiguous_format)
+            aw[f"{lname}.adaptive_weight"] = (theta - self.atten_default * g).contiguous()
             bias = getattr(self.net.get_submodule(lname), "bias", None)
             if bias is not None:
-                ab[f"{lname}.adaptive_bias"] = bias.detach().clone()
+                ab[f"{lname}.adaptive_bias"] = own(bias.detach())
         skip = {f"{n}.weight" for n in self.adaptive_names} | {f"{n}.bias" for n in self.adaptive_names}
-        pre = {k: v.detach().clone(memory_format=torch.contiguous_format) for k, v in self.net.state_dict().items()
-               if k not in skip}
+        pre = {k: own(v.detach()) for k, v in self.net.state_dict().items() if k not in skip}
         return {"global_weight": gw, "global_weight_atten": gwa, "adaptive_weights": aw, "adaptive_bias": ab,
                 "bn_params": {}, "pre_trained_params": pre}
 
@@ -416,7 +417,7 @@ class Operator(OperatorModule):
         model.train()
         model.install(self.optimizer)
         self.optimizer.stats.zero_()
-        perm = torch.randperm(n, device=device)
+        perm = torch.randperm(n, device=device, generator=model.rng if device.type == "cuda" else None)
         n_batches = n // bs if (n % bs == 1) else (n + bs - 1) // bs     # drop_last iff remainder == 1
         data_cnt = 0
         step = self._graphed_step(model)
@@ -460,7 +461,7 @@ class Client(ClientModule):
 
     # ---- checkpoints -----------------------------------------------------------------------------------------------------
     def save_model(self, model_name: str) -> None:
-        self.save_state(model_name, self.model.model_state(), True)
+        self.save_state(model_name, self.model.model_state(copy=False), True)
         self.store.save(self.name, f"{model_name}_examplars", self.model.examplars_compact(), True,
                         post="expand_examplars")
 
@@ -540,7 +541,7 @@ class Server(ServerModule):
             self.local_clients[client_name] = client
 
     def save_model(self, model_name: str) -> None:
-        self.save_state(model_name, self.model.model_state(), True)
+        self.save_state(model_name, self.model.model_state(copy=False), True)
 
     # ---- uploads -----------------------------------------------------------------------------------------------------------
     def set_client_incremental_state(self, client_name: str, client_state: Optional[Dict]) -> None:

@@ -107,7 +107,7 @@ class Model(base.Model):
                 comp.atten0.copy_(comp.atten)
                 comp.aw0.copy_(self.net.get_submodule(lname).parametrizations.weight.original)
 
-    def model_state(self) -> Dict:
+    def model_state(self, copy: bool = True) -> Dict:
         gw, gwa, aw, ab = {}, {}, {}, {}
         for lname, comp in self.composers.items():
             mod = self.net.get_submodule(lname)

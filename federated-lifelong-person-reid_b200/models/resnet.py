@@ -120,6 +120,8 @@ def _init_kaiming(m: nn.Module) -> None:       # strong-baseline style init used
 
 
 class ResNetReID(nn.Module):
+    thread_safe_rng = True        # no dropout / stochastic depth: forward never draws from the default generator
+
     def __init__(self, model_name: str, num_classes: int = 1000, last_stride: int = 2, neck: str = "no",
                  pretrained_path: Optional[str] = None, **kwargs):
         super().__init__()

@@ -74,8 +74,33 @@ def expand_examplars(state: Any) -> Any:
 POST: Dict[str, Callable[[Any], Any]] = {"expand_examplars": expand_examplars}
 
 
-def _writer_main(jobs, done) -> None:  # pragma: no cover  (runs in a child process)
+_TREF = "__flpr_tensor_ref__"
+
+
+def _resolve(obj: Any, arena_np) -> Any:
+    """Rebuild the tensors of a staged state from ``(offset, shape, dtype)`` references into the shared arena.
+    ``torch.frombuffer`` gives every tensor a storage of exactly its own size, so ``torch.save`` writes just the
+    payload bytes (a view of the arena tensor would serialise the whole arena) without an intermediate copy."""
+    if isinstance(obj, tuple) and len(obj) == 4 and obj[0] == _TREF:
+        _, off, shape, dtype = obj
+        dt = getattr(torch, dtype)
+        n = 1
+        for d in shape:
+            n *= d
+        if n == 0:
+            return torch.empty(shape, dtype=dt)
+        nb = n * torch.empty(0, dtype=dt).element_size()
+        return torch.frombuffer(arena_np[off:off + nb], dtype=dt).view(shape)
+    if isinstance(obj, dict):
+        return {k: _resolve(v, arena_np) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_resolve(v, arena_np) for v in obj)
+    return obj
+
+
+def _writer_main(jobs, done, arena) -> None:  # pragma: no cover  (runs in a child process)
     torch.set_num_threads(1)
+    arena_np = arena.numpy() if arena is not None else None
     while True:
         job = jobs.get()
         if job is None:
@@ -83,7 +108,7 @@ def _writer_main(jobs, done) -> None:  # pragma: no cover  (runs in a child proc
         job_id, path, state, post = job
         err = None
         try:
-            state = _own(state)          # detach from the staging slab (torch.save would serialise the whole slab)
+            state = _resolve(state, arena_np)
             if post:
                 state = POST[post](state)
             os.makedirs(os.path.dirname(path), exist_ok=True)
@@ -97,16 +122,44 @@ def _writer_main(jobs, done) -> None:  # pragma: no cover  (runs in a child proc
         done.put((job_id, err))
 
 
-class _Slab:
-    """A process-shared, page-locked byte buffer that tensors are staged into."""
+class _SharedArena:
+    """ONE process-shared, page-locked staging arena, mapped by every writer process at start-up. Regions are handed
+    out first-fit and returned when the writer is done, so a checkpoint costs no shared-memory creation, no
+    ``cudaHostRegister`` and no file-descriptor passing on the training thread (jobs carry offsets only)."""
+
+    ALIGN = 4096
 
     def __init__(self, nbytes: int, cuda: bool):
-        self.buf = torch.empty(nbytes, dtype=torch.uint8).share_memory_()
+        self.nbytes = int(nbytes)
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8).share_memory_()
         self.registered = False
         if cuda:
-            rc = torch.cuda.cudart().cudaHostRegister(self.buf.data_ptr(), nbytes, 0)
+            rc = torch.cuda.cudart().cudaHostRegister(self.buf.data_ptr(), self.nbytes, 0)
             self.registered = int(rc) == 0
-        self.nbytes = nbytes
+        self.free: List[Tuple[int, int]] = [(0, self.nbytes)]          # sorted (offset, size)
+
+    def alloc(self, n: int) -> int:
+        n = (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        for i, (off, size) in enumerate(self.free):
+            if size >= n:
+                if size == n:
+                    self.free.pop(i)
+                else:
+                    self.free[i] = (off + n, size - n)
+                return off
+        return -1
+
+    def release_region(self, off: int, n: int) -> None:
+        n = (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        import bisect
+        i = bisect.bisect_left(self.free, (off, 0))
+        self.free.insert(i, (off, n))
+        if i + 1 < len(self.free) and self.free[i][0] + self.free[i][1] == self.free[i + 1][0]:
+            self.free[i] = (self.free[i][0], self.free[i][1] + self.free[i + 1][1])
+            self.free.pop(i + 1)
+        if i > 0 and self.free[i - 1][0] + self.free[i - 1][1] == self.free[i][0]:
+            self.free[i - 1] = (self.free[i - 1][0], self.free[i - 1][1] + self.free[i][1])
+            self.free.pop(i)
 
     def release(self) -> None:
         if self.registered:
@@ -117,20 +170,19 @@ class _Slab:
 class CheckpointStore:
     """One instance per process; actors address it with ``(actor_name, state_name)``."""
 
-    def __init__(self, root: str, asynchronous: bool = True, enabled: bool = True, workers: int = 6,
-                 max_inflight_bytes: int = 24 << 30):
+    def __init__(self, root: str, asynchronous: bool = True, enabled: bool = True, workers: int = 12,
+                 arena_bytes: int = 8 << 30):
         self.root = root
         self.enabled = enabled
         self.asynchronous = bool(asynchronous and enabled)
         self.workers = max(1, int(workers))
-        self.max_inflight = int(max_inflight_bytes)
+        self.arena_bytes = int(arena_bytes)
         self.bytes_written = 0
         self._started = False
         self._err: Optional[str] = None
         self._next_id = 0
-        self._inflight: Dict[int, Tuple[_Slab, int]] = {}
-        self._inflight_bytes = 0
-        self._pool: Dict[int, List[_Slab]] = {}
+        self._inflight: Dict[int, Tuple[int, int]] = {}      # job -> (arena offset, bytes)
+        self._arena: Optional[_SharedArena] = None
         self._lock = threading.RLock()
         self._copy_stream = None
         self._last_copy_event = None
@@ -144,12 +196,13 @@ class CheckpointStore:
         return os.path.exists(self.path(actor, state_name))
 
     # ------------------------------------------------------------------ pipeline
-    def _start(self) -> None:
+    def _start(self, cuda: bool) -> None:
         import torch.multiprocessing as mp
         ctx = mp.get_context("spawn")
+        self._arena = _SharedArena(self.arena_bytes, cuda)
         self._jobs = ctx.Queue()
         self._done = ctx.Queue()
-        self._procs = [ctx.Process(target=_writer_main, args=(self._jobs, self._done), daemon=True)
+        self._procs = [ctx.Process(target=_writer_main, args=(self._jobs, self._done, self._arena.buf), daemon=True)
                        for _ in range(self.workers)]
         for p in self._procs:
             p.start()
@@ -168,30 +221,31 @@ class CheckpointStore:
                 event.synchronize()                      # releases the GIL while the DMA finishes
             self._jobs.put(job)
 
-    def _get_slab(self, nbytes: int, cuda: bool) -> _Slab:
-        size = 1 << max(20, (nbytes - 1).bit_length())
-        lst = self._pool.get(size)
-        if lst:
-            return lst.pop()
-        return _Slab(size, cuda)
-
     def _reap(self, block: bool) -> None:
+        """Collect finished jobs (at least one when ``block``) and return their arena regions."""
+        waited = 0.0
         while self._inflight:
             try:
-                job_id, err = self._done.get(block, timeout=600 if block else None)
+                job_id, err = self._done.get(block, timeout=2.0 if block else None)
             except queue.Empty:
-                return
-            slab, nbytes = self._inflight.pop(job_id)
-            self._inflight_bytes -= nbytes
+                if not block:
+                    return
+                waited += 2.0
+                if not all(p.is_alive() for p in self._procs):
+                    raise RuntimeError("a checkpoint writer process died")
+                if waited > 600:
+                    raise RuntimeError("checkpoint writers made no progress for 600 s")
+                continue
+            off, nbytes = self._inflight.pop(job_id)
+            if nbytes:
+                self._arena.release_region(off, nbytes)
             self.bytes_written += nbytes
-            self._pool.setdefault(slab.nbytes, []).append(slab)
             if err and self._err is None:
                 self._err = err
-            if block and self._inflight_bytes <= self.max_inflight // 2:
-                block = False
+            block = False
 
-    def _stage(self, state: Any, cuda_dev: Optional[torch.device]) -> Tuple[Any, Optional[_Slab], int, Any]:
-        """Copy every tensor of ``state`` into one shared slab; returns the mirrored structure of CPU views."""
+    def _stage(self, state: Any, cuda_dev: Optional[torch.device]) -> Tuple[Any, int, int, Any]:
+        """Copy every tensor of ``state`` into one arena region; returns the structure with tensor references."""
         tensors: List[torch.Tensor] = []
 
         def collect(o):
@@ -205,41 +259,50 @@ class CheckpointStore:
                     collect(v)
         collect(state)
         total = sum((t.numel() * t.element_size() + 63) // 64 * 64 for t in tensors)
-        if total == 0:
-            return state, None, 0, None
-        slab = self._get_slab(total, cuda_dev is not None)
+        if total > self._arena.nbytes:
+            return None, -1, total, None                    # larger than the whole arena: caller saves in-line
+        base = 0
         event = None
-        offset = 0
-        views = {}
+        if total:
+            base = self._arena.alloc(total)
+            while base < 0:                                   # back-pressure: the writers cannot keep up
+                if not self._inflight:
+                    return None, -1, total, None
+                self._reap(block=True)
+                base = self._arena.alloc(total)
+        offset = base
+        refs = {}
+        buf = self._arena.buf
         ctx = torch.cuda.stream(self._copy_stream) if cuda_dev is not None else _null()
         if cuda_dev is not None:
             self._copy_stream.wait_stream(torch.cuda.current_stream(cuda_dev))
         with ctx:
             for t in tensors:
                 nb = t.numel() * t.element_size()
-                v = slab.buf[offset:offset + nb].view(t.dtype).view(t.shape)
-                src = t.detach()
-                if not src.is_contiguous():
-                    src = src.contiguous()
-                v.copy_(src, non_blocking=True)
-                if src.is_cuda:
-                    src.record_stream(self._copy_stream)
-                views[id(t)] = v
+                if nb:
+                    v = buf[offset:offset + nb].view(t.dtype).view(t.shape)
+                    src = t.detach()
+                    if not src.is_contiguous():
+                        src = src.contiguous()
+                    v.copy_(src, non_blocking=True)
+                    if src.is_cuda:
+                        src.record_stream(self._copy_stream)
+                refs[id(t)] = (_TREF, offset, tuple(t.shape), str(t.dtype).replace("torch.", ""))
                 offset += (nb + 63) // 64 * 64
-            if cuda_dev is not None:
+            if cuda_dev is not None and total:
                 event = torch.cuda.Event()
                 event.record(self._copy_stream)
                 self._last_copy_event = event
 
         def mirror(o):
             if isinstance(o, torch.Tensor):
-                return views[id(o)]
+                return refs[id(o)]
             if isinstance(o, dict):
                 return {k: mirror(v) for k, v in o.items()}
             if isinstance(o, (list, tuple)):
                 return type(o)(mirror(v) for v in o)
             return o
-        return mirror(state), slab, total, event
+        return mirror(state), base, total, event
 
     def fence(self) -> None:
         """Make the compute stream wait for outstanding snapshot copies (call before sources are overwritten)."""
@@ -263,15 +326,8 @@ class CheckpointStore:
         if cover is False and os.path.exists(path):
             raise ValueError(f"State checkpoint has already exist in '{path}'.")
         if not self.asynchronous:
-            snap = _to_cpu(state)
-            if post:
-                snap = POST[post](snap)
-            os.makedirs(os.path.dirname(path), exist_ok=True)
-            torch.save(snap, path + ".tmp")
-            os.replace(path + ".tmp", path)
+            self._save_inline(path, state, post)
             return
-        if not self._started:
-            self._start()
         cuda_dev = None
 
         def find_dev(o):
@@ -286,19 +342,28 @@ class CheckpointStore:
                 for v in o:
                     find_dev(v)
         find_dev(state)
+        if not self._started:
+            self._start(cuda_dev is not None or torch.cuda.is_available())
         if cuda_dev is not None and self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(cuda_dev)
         self._reap(block=False)
-        if self._inflight_bytes > self.max_inflight:
-            self._reap(block=True)                        # back-pressure: the writers cannot keep up
-        snap, slab, nbytes, event = self._stage(state, cuda_dev)
+        snap, base, nbytes, event = self._stage(state, cuda_dev)
+        if base < 0:                                           # does not fit in the staging arena
+            self._save_inline(path, state, post)
+            return
         job_id = self._next_id
         self._next_id += 1
-        if slab is None:
-            slab = self._get_slab(1, False)               # tensor-free payload: placeholder for the bookkeeping
-        self._inflight[job_id] = (slab, nbytes)
-        self._inflight_bytes += nbytes
+        self._inflight[job_id] = (base, nbytes)
         self._feed_q.put((event, (job_id, path, snap, post)))
+
+    @staticmethod
+    def _save_inline(path: str, state: Any, post: Optional[str]) -> None:
+        snap = _to_cpu(state)
+        if post:
+            snap = POST[post](snap)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        torch.save(snap, path + ".tmp")
+        os.replace(path + ".tmp", path)
 
     def load(self, actor: str, state_name: str, default_value: Any = None, map_location: str = "cpu") -> Any:
         """``load_state`` (``modules/client.py:34-50``): returns ``default_value`` when the file does not exist."""
@@ -331,10 +396,9 @@ class CheckpointStore:
                 self._jobs.put(None)
             for p in self._procs:
                 p.join(timeout=30)
-            for lst in self._pool.values():
-                for slab in lst:
-                    slab.release()
-            self._pool.clear()
+            if self._arena is not None:
+                self._arena.release()
+                self._arena = None
             self._started = False
         self.asynchronous = False
 

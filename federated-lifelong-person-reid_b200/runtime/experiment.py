@@ -142,9 +142,13 @@ class ExperimentStage:
         """Construct comm, checkpoint store, server replica and the local clients for ``exp_config``."""
         eng = exp_config["engine_opts"]
         names = [c["client_name"] for c in exp_config["clients"]]
+        n_local = len([i for i in range(len(names)) if i % self.world == self.rank])
         store = CheckpointStore(os.path.join(self.common_config["checkpoints_dir"], exp_config["exp_name"]),
                                 asynchronous=eng.get("async_checkpoint", True) and self.device.type == "cuda",
-                                enabled=eng.get("checkpoints", True), workers=eng.get("ckpt_workers", 6))
+                                enabled=eng.get("checkpoints", True),
+                                workers=eng.get("ckpt_workers") or min(12, max(4, 2 * n_local)),
+                                arena_bytes=int(float(eng.get("ckpt_arena_gb") or min(8.0, max(2.0, 1.0 * n_local)))
+                                                * (1 << 30)))
         server = parser_server(exp_config, self.common_config, self.device, store)
         clients = parser_clients(exp_config, self.common_config, self.device, store, None, self.rank, self.world,
                                  self.source_factory)
@@ -264,7 +268,8 @@ class ExperimentStage:
         with timer("train"):
             todo = [local[n] for n in online if n in local]
             workers = min(self.container.max_worker(), len(todo))
-            if workers > 1 and self.device.type == "cuda" and eng.get("client_threads", True):
+            if workers > 1 and self.device.type == "cuda" and eng.get("client_threads", True) and \
+                    all(getattr(c.model.net, "thread_safe_rng", False) for c in todo):
                 self._train_parallel(todo, log, curr_round, workers)
             else:
                 for client in todo:

@@ -24,6 +24,9 @@ from .arena import ArenaOptimizer, ParamArena, StepLR
 from .checkpoint import CheckpointStore
 
 
+_RNG_STREAMS = 0
+
+
 def _cuda(device) -> bool:
     return torch.device(device).type == "cuda"
 
@@ -37,6 +40,7 @@ class ModelModule(nn.Module):
         self.args = kwargs
         self.arena: Optional[ParamArena] = None
         self.compute_dtype = torch.float32
+        self.rng: Optional[torch.Generator] = None       # per-model device generator (see materialize)
 
     def forward(self, *args, **kwargs):
         return self.net(*args, **kwargs)
@@ -63,6 +67,14 @@ class ModelModule(nn.Module):
             self.net.configure_split(fine_tuning)
         self.arena = ParamArena(self.trainable_named_parameters(), device,
                                 shadow=self.compute_dtype == torch.bfloat16, first=self.upload_filter)
+        if device.type == "cuda":
+            # A private generator per model: sample shuffling / augmentation of one client never touch the default
+            # CUDA generator, which another client's thread may have registered with an ongoing graph capture, and
+            # a client's random stream does not depend on how the client threads interleave.
+            global _RNG_STREAMS
+            _RNG_STREAMS += 1
+            self.rng = torch.Generator(device=device)
+            self.rng.manual_seed((torch.initial_seed() + 7919 * _RNG_STREAMS) % (1 << 62))
         if device.type == "cuda" and self.compute_dtype == torch.bfloat16:
             from ..models.resnet import FastResNetHead, ResNetReID
             if isinstance(self.net, ResNetReID) and 1 <= self.net.head_start <= 4:
@@ -392,3 +404,4 @@ def _bind_loader(loader, model: ModelModule) -> None:
         # bf16 models get bf16 NHWC batches straight out of the fused augmentation kernel (the first convolution
         # would cast its input to bf16 anyway)
         loader.to(model.device, model.compute_dtype if model.device.type == "cuda" else torch.float32)
+        loader.device_generator = model.rng
