@@ -181,10 +181,22 @@ def run_flpr(a, impl: str) -> dict:
             if world > 1:
                 dist.barrier()
 
+        # Harness housekeeping, NOT part of a federated round: per-round payload files have unique names, so a long
+        # run would fill the RAM disk. A background thread unlinks the payload files of finished rounds.
+        import queue as _q
+        janitor_q: "_q.Queue" = _q.Queue()
+
+        def janitor():
+            while janitor_q.get() is not None:
+                cleanup_payloads(common["checkpoints_dir"])
+
+        jt = threading.Thread(target=janitor, daemon=True)
+        jt.start()
+
         def one_round(r):
             stage._process_one_round(r, server, clients, names, cfg, log, timer, comm)
-            if rank == 0 and r % 2 == 0:        # bound the RAM disk: drop payload files of finished rounds
-                cleanup_payloads(common["checkpoints_dir"])
+            if rank == 0 and r % 2 == 0:
+                janitor_q.put(r)
 
         def after_round():
             store.flush()
@@ -247,6 +259,8 @@ def run_flpr(a, impl: str) -> dict:
         phases = {k: round(sum(v[-2 * a.steps:]) / max(len(v[-2 * a.steps:]), 1), 3) for k, v in timer.flush().items()}
         comm_bytes = comm.bytes_moved if comm is not None else 0
         store.close()
+        janitor_q.put(None)
+        jt.join(timeout=60)
         if comm is not None:
             comm.check_errors()
             comm.close()

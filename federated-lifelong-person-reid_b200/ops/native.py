@@ -120,14 +120,30 @@ def check(rc: int, what: str) -> None:
         raise NativeError(f"{what} failed with code {rc}: {msg}")
 
 
-# launch counter: bench.py reports how many flpr kernels were launched inside the timed region
-_launches = 0
+# launch counter: bench.py reports how many flpr kernels were launched inside the timed region. Per-thread counts
+# (client threads run concurrently; graph capture measures "launches recorded by THIS thread") summed on read.
+_tls = threading.local()
+_counters: list = []
+
+
+def _counter() -> list:
+    c = getattr(_tls, "c", None)
+    if c is None:
+        c = _tls.c = [0]
+        with _lock:
+            _counters.append(c)
+    return c
 
 
 def count_launch(n: int = 1) -> None:
-    global _launches
-    _launches += n
+    _counter()[0] += n
 
 
 def launches() -> int:
-    return _launches
+    """Launches of all threads."""
+    return sum(c[0] for c in _counters)
+
+
+def thread_launches() -> int:
+    """Launches issued by the calling thread (graph capture bookkeeping)."""
+    return _counter()[0]

@@ -113,8 +113,10 @@ def _writer_main(jobs, done, arena) -> None:  # pragma: no cover  (runs in a chi
                 state = POST[post](state)
             os.makedirs(os.path.dirname(path), exist_ok=True)
             tmp = f"{path}.tmp{os.getpid()}"
-            # legacy (non-zip) container: no per-record CRC32 pass over hundreds of MB; torch.load reads both formats
-            torch.save(state, tmp, _use_new_zipfile_serialization=False)
+            # legacy (non-zip) container: no per-record CRC32 pass over hundreds of MB; torch.load reads both formats.
+            # pickle protocol 4: numpy exemplar arrays go out as raw frames (protocol 2 escapes them byte by byte:
+            # 1.6 s instead of 0.2 s for one client's 268 MB exemplar file); any Python >= 3.4 loads it.
+            torch.save(state, tmp, _use_new_zipfile_serialization=False, pickle_protocol=4)
             os.replace(tmp, path)
         except BaseException as ex:
             err = f"{type(ex).__name__}: {ex}"
