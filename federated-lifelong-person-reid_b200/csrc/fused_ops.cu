@@ -499,14 +499,16 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
 //   ca = gamma*rstd, cb = -ca*rstd*dgamma/M, cc = -ca*dbeta/M - cb*mean
 __global__ void __launch_bounds__(256) bn_fold_partials_kernel(const float* part, int nparts, const float* gamma,
                                                                const float* mean, const float* rstd, float* dgamma,
-                                                               float* dbeta, float* coef /* [3][C] */, int M, int C) {
+                                                               float* dbeta, float* coef /* [3][C] */, int M, int C,
+                                                               int accumulate) {
   __shared__ float sh[2][8][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float g, b;
   fold_partials(part, nparts, C, c, g, b, sh);
   if (threadIdx.y != 0 || c >= C) return;
-  dgamma[c] = g;
-  dbeta[c] = b;
+  // accumulate: dgamma / dbeta point into the (zeroed) flat gradient arena of the optimizer
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + g : g;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + b : b;
   const float ga = gamma ? gamma[c] : 1.f;
   const float ca = ga * rstd[c];
   const float cb = -ca * rstd[c] * g / M;
@@ -905,7 +907,7 @@ int flpr_affine_act(const void* x, const float* scale, const float* shift, const
 // residual branch.
 int flpr_bn_bwd(const void* dy, const void* y, const void* x, const float* mean, const float* rstd, const float* gamma,
                 float* dgamma, float* dbeta, float* part, void* dres, void* dx, int M, int C, int relu,
-                cudaStream_t st) {
+                int accumulate, cudaStream_t st) {
   bind_device_of(dy);
   if (C % 8) return -2;
   dim3 grid, block; int rpb;
@@ -916,7 +918,7 @@ int flpr_bn_bwd(const void* dy, const void* y, const void* x, const float* mean,
       relu);
   float* coef = part + (size_t)grid.y * 2 * C;
   bn_fold_partials_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(part, (int)grid.y, gamma, mean, rstd, dgamma, dbeta,
-                                                                 coef, M, C);
+                                                                 coef, M, C, accumulate);
   // when the masked dy was materialised in dres, read it back (no second ReLU-mask pass over y)
   const __nv_bfloat16* dy_in = dres ? reinterpret_cast<const __nv_bfloat16*>(dres)
                                     : reinterpret_cast<const __nv_bfloat16*>(dy);

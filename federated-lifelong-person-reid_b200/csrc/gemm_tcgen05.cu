@@ -84,8 +84,12 @@ struct PersistLayout {
   static constexpr int MIN_CTAS = (BN <= 128) ? 2 : 1;
   static constexpr int ACC_STAGES = 2;
   static constexpr int TMEM_COLS = ACC_STAGES * BN;                 // 128/256/512 columns
-  static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;         // 4 epilogue warps x 32 rows x 80 B
-  static constexpr int STORE_BYTES = 4 * 32 * 80;
+  // 256-wide tiles (one CTA per SM): 8 epilogue warps, two per TMEM lane quarter, each draining half of the columns
+  // - four warps cannot drain a 128 x 256 fp32 tile within the 4096 MMA cycles of a K = 512 tile.
+  static constexpr int EPI_WARPS = (BN == 256) ? 8 : 4;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;         // epilogue warps x 32 rows x 80 B
+  static constexpr int STORE_BYTES = EPI_WARPS * 32 * 80;
   static constexpr int BAR_OFFSET = STORE_OFFSET + STORE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
@@ -181,11 +185,155 @@ __device__ __forceinline__ void warp_colsum32(float (&v)[32], int lane) {
   }
 }
 
-// Epilogue of one 128 x BN tile by the 4 epilogue warps (q = TMEM lane quarter): TMEM -> registers -> alpha / bias /
-// residual / ReLU -> global (bf16 / fp32 / transposed / atomic). `have_acc` false means the accumulator is zero.
-template <int BN>
+// Epilogue of columns [cb, ce) of one 128 x BN tile by one warp (q = TMEM lane quarter): TMEM -> registers ->
+// alpha / bias / residual / ReLU -> global (bf16 / fp32 / transposed / atomic). `have_acc` false = zero accumulator.
+// The TMEM load of chunk i+1 is issued before chunk i is processed (two register buffers).
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], int mt, int m0, int n0,
+                                               int c0, long long tap_off, int q, int lane, uint8_t* stage_buf,
+                                               float bm, bool use_stage) {
+  const int row = m0 + q * 32 + lane;
+  if (n0 + c0 >= p.N) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = __uint_as_float(r[j]) * p.alpha + bm;
+    const int col = n0 + c0 + j;
+    if (p.bias_n != nullptr && col < p.N) x += p.bias_n[col];
+    v[j] = x;
+  }
+  const bool stats_from_stage = p.col_part != nullptr && use_stage && (n0 + c0 + 32 <= p.N);
+  if (p.col_part != nullptr && !stats_from_stage) {
+    // fused batch-norm statistics of the raw fp32 conv output (rows >= M are exact zeros: TMA OOB fill)
+    float s1[32], s2[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { s1[j] = v[j]; s2[j] = v[j] * v[j]; }
+    warp_colsum32(s1, lane);
+    warp_colsum32(s2, lane);
+    const int col = n0 + c0 + lane;
+    if (col < p.N) {
+      float* dst = p.col_part + ((size_t)(mt * 4 + q) * 2) * p.N + col;
+      dst[0] = s1[0];
+      dst[p.N] = s2[0];
+    }
+  }
+  if (p.trans_out) {
+    // out[col * ldo + row]: lanes are contiguous in memory -> coalesced per column
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = n0 + c0 + j;
+      if (row < p.M && col < p.N) {
+        const long long idx = (long long)col * p.ldo + row;
+        float x = v[j];
+        if (p.residual != nullptr) x += __bfloat162float(p.residual[idx]);
+        if (p.relu) x = fmaxf(x, 0.f);
+        if (p.atomic_add)
+          atomicAdd(reinterpret_cast<float*>(p.out) + idx, x);
+        else if (p.out_bf16)
+          reinterpret_cast<__nv_bfloat16*>(p.out)[idx] = __float2bfloat16(x);
+        else
+          reinterpret_cast<float*>(p.out)[idx] = x;
+      }
+    }
+  } else if (row < p.M || use_stage) {
+    const long long base = (long long)row * p.ldo + n0 + c0 + tap_off;
+    const bool full = (n0 + c0 + 32 <= p.N);
+    if (p.residual != nullptr && row < p.M) {
+      if (full && ((base & 7) == 0)) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + base);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          uint4 u = rp[j4];
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float2 f = __bfloat1622float2(h[t]);
+            v[j4 * 8 + t * 2] += f.x;
+            v[j4 * 8 + t * 2 + 1] += f.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c0 + j < p.N) v[j] += __bfloat162float(p.residual[base + j]);
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.atomic_add) {
+      float* o = reinterpret_cast<float*>(p.out) + base;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + c0 + j < p.N) atomicAdd(o + j, v[j]);
+    } else if (p.out_bf16) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + base;
+      if (full && ((base & 7) == 0)) {
+        uint4 pk[4];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk[j4]);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j4 * 8 + t * 2], v[j4 * 8 + t * 2 + 1]);
+        }
+        if (use_stage) {
+          // transpose through this warp's private staging tile so that 4 lanes write one row's 64 B contiguously
+          uint8_t* st = stage_buf + lane * 80;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<uint4*>(st + j4 * 16) = pk[j4];
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rr = 8 * j + (lane >> 2);
+            const uint4 u = *reinterpret_cast<const uint4*>(stage_buf + rr * 80 + (lane & 3) * 16);
+            const int grow = m0 + q * 32 + rr;
+            if (grow < p.M)
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)grow * p.ldo + n0 +
+                                        c0 + tap_off + (lane & 3) * 8) = u;
+          }
+          if (stats_from_stage) {
+            // fused batch-norm statistics: lane = column, walk the 32 staged rows (the bf16 values that are stored;
+            // rows >= M hold exact zeros). 32 conflict-free 2-byte smem loads instead of 62 shuffles.
+            float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stage_buf + rr * 80 + lane * 2));
+              a1 += x;
+              a2 = fmaf(x, x, a2);
+            }
+            float* dst = p.col_part + ((size_t)(mt * 4 + q) * 2) * p.N + n0 + c0 + lane;
+            dst[0] = a1;
+            dst[p.N] = a2;
+          }
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) reinterpret_cast<uint4*>(o)[j4] = pk[j4];
+        }
+      } else if (row < p.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c0 + j < p.N) o[j] = __float2bfloat16(v[j]);
+      }
+    } else {
+      float* o = reinterpret_cast<float*>(p.out) + base;
+      if (full && ((base & 3) == 0)) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c0 + j < p.N) o[j] = v[j];
+      }
+    }
+  }
+}
+
+template <bool PIPE>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, bool have_acc, int mt, int m0,
-                                              int n0, long long tap_off, int q, int lane, uint8_t* stage_buf) {
+                                              int n0, int cb, int ce, long long tap_off, int q, int lane,
+                                              uint8_t* stage_buf) {
   const int row = m0 + q * 32 + lane;
   const float bm = (p.bias_m != nullptr && row < p.M) ? p.bias_m[row] : 0.f;
   // bf16 row-major output without residual: stores are staged through smem so that each store instruction writes
@@ -193,136 +341,33 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   const bool use_stage = p.out_bf16 && !p.trans_out && !p.atomic_add && p.residual == nullptr &&
                          ((p.ldo & 7) == 0) && (((n0 + tap_off) & 7) == 0) &&
                          ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+  const uint32_t tbase = tmem_acc + (uint32_t(q * 32) << 16);
+  uint32_t ra[32], rb[32];
+  if (!have_acc) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ra[j] = 0u;
+    for (int c0 = cb; c0 < ce; c0 += 32) epilogue_chunk(p, ra, mt, m0, n0, c0, tap_off, q, lane, stage_buf, bm, use_stage);
+    return;
+  }
+  if constexpr (!PIPE) {       // 128-register budget (two CTAs per SM): one register buffer
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
-    uint32_t r[32];
-    if (have_acc) {
-      tmem_ld_32x32b_x32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c0), r);
+    for (int c0 = cb; c0 < ce; c0 += 32) {
+      tmem_ld_32x32b_x32(tbase + uint32_t(c0), ra);
       tmem_ld_wait();
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = 0u;
+      epilogue_chunk(p, ra, mt, m0, n0, c0, tap_off, q, lane, stage_buf, bm, use_stage);
     }
-    if (n0 + c0 >= p.N) continue;
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = __uint_as_float(r[j]) * p.alpha + bm;
-      const int col = n0 + c0 + j;
-      if (p.bias_n != nullptr && col < p.N) x += p.bias_n[col];
-      v[j] = x;
-    }
-    if (p.col_part != nullptr) {
-      // fused batch-norm statistics of the raw fp32 conv output (rows >= M are exact zeros: TMA OOB fill)
-      float s1[32], s2[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) { s1[j] = v[j]; s2[j] = v[j] * v[j]; }
-      warp_colsum32(s1, lane);
-      warp_colsum32(s2, lane);
-      const int col = n0 + c0 + lane;
-      if (col < p.N) {
-        float* dst = p.col_part + ((size_t)(mt * 4 + q) * 2) * p.N + col;
-        dst[0] = s1[0];
-        dst[p.N] = s2[0];
-      }
-    }
-    if (p.trans_out) {
-      // out[col * ldo + row]: lanes are contiguous in memory -> coalesced per column
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = n0 + c0 + j;
-        if (row < p.M && col < p.N) {
-          const long long idx = (long long)col * p.ldo + row;
-          float x = v[j];
-          if (p.residual != nullptr) x += __bfloat162float(p.residual[idx]);
-          if (p.relu) x = fmaxf(x, 0.f);
-          if (p.atomic_add)
-            atomicAdd(reinterpret_cast<float*>(p.out) + idx, x);
-          else if (p.out_bf16)
-            reinterpret_cast<__nv_bfloat16*>(p.out)[idx] = __float2bfloat16(x);
-          else
-            reinterpret_cast<float*>(p.out)[idx] = x;
-        }
-      }
-    } else if (row < p.M || use_stage) {
-      const long long base = (long long)row * p.ldo + n0 + c0 + tap_off;
-      const bool full = (n0 + c0 + 32 <= p.N);
-      if (p.residual != nullptr && row < p.M) {
-        if (full && ((base & 7) == 0)) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + base);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            uint4 u = rp[j4];
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              float2 f = __bfloat1622float2(h[t]);
-              v[j4 * 8 + t * 2] += f.x;
-              v[j4 * 8 + t * 2 + 1] += f.y;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < p.N) v[j] += __bfloat162float(p.residual[base + j]);
-        }
-      }
-      if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-      if (p.atomic_add) {
-        float* o = reinterpret_cast<float*>(p.out) + base;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + c0 + j < p.N) atomicAdd(o + j, v[j]);
-      } else if (p.out_bf16) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + base;
-        if (full && ((base & 7) == 0)) {
-          uint4 pk[4];
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk[j4]);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j4 * 8 + t * 2], v[j4 * 8 + t * 2 + 1]);
-          }
-          if (use_stage) {
-            // transpose through this warp's private staging tile so that 4 lanes write one row's 64 B contiguously
-            uint8_t* st = stage_buf + lane * 80;
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<uint4*>(st + j4 * 16) = pk[j4];
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int rr = 8 * j + (lane >> 2);
-              const uint4 u = *reinterpret_cast<const uint4*>(stage_buf + rr * 80 + (lane & 3) * 16);
-              const int grow = m0 + q * 32 + rr;
-              if (grow < p.M)
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)grow * p.ldo + n0 +
-                                          c0 + tap_off + (lane & 3) * 8) = u;
-            }
-            __syncwarp();
-          } else {
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) reinterpret_cast<uint4*>(o)[j4] = pk[j4];
-          }
-        } else if (row < p.M) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < p.N) o[j] = __float2bfloat16(v[j]);
-        }
-      } else {
-        float* o = reinterpret_cast<float*>(p.out) + base;
-        if (full && ((base & 3) == 0)) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            reinterpret_cast<float4*>(o)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < p.N) o[j] = v[j];
-        }
-      }
+    return;
+  }
+  tmem_ld_32x32b_x32(tbase + uint32_t(cb), ra);
+#pragma unroll 1
+  for (int c0 = cb; c0 < ce; c0 += 64) {
+    tmem_ld_wait();
+    if (c0 + 32 < ce) tmem_ld_32x32b_x32(tbase + uint32_t(c0 + 32), rb);
+    epilogue_chunk(p, ra, mt, m0, n0, c0, tap_off, q, lane, stage_buf, bm, use_stage);
+    if (c0 + 32 < ce) {
+      tmem_ld_wait();
+      if (c0 + 64 < ce) tmem_ld_32x32b_x32(tbase + uint32_t(c0 + 64), ra);
+      epilogue_chunk(p, rb, mt, m0, n0, c0 + 32, tap_off, q, lane, stage_buf, bm, use_stage);
     }
   }
 }
@@ -418,7 +463,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     const long long tap_off = (B_MODE == OP_CONV) ? (long long)ztap * p.tap_stride : 0;
     // pipeline stage 0 is free once the accumulator barrier has fired -> store staging
-    epilogue_tile<BN>(p, tmem_base, num_kb > 0, blockIdx.y, m0, n0, tap_off, q, lane, smem + q * (32 * 80));
+    epilogue_tile<false>(p, tmem_base, num_kb > 0, blockIdx.y, m0, n0, 0, BN, tap_off, q, lane, smem + q * (32 * 80));
   }
 
   tc_fence_before();
@@ -435,7 +480,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 // tile i (TMEM -> registers -> global) while the MMA warp already accumulates tile i+1, and the TMA producer runs
 // ahead across tile boundaries, so neither the pipeline fill nor the epilogue is exposed for short-K GEMMs.
 template <int BN, int A_MODE, int B_MODE>
-__global__ void __launch_bounds__(256, PersistLayout<BN>::MIN_CTAS)
+__global__ void __launch_bounds__(PersistLayout<BN>::THREADS, PersistLayout<BN>::MIN_CTAS)
 gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                     const GemmParams p) {
   using L = PersistLayout<BN>;
@@ -462,7 +507,7 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
     }
     for (int s = 0; s < L::ACC_STAGES; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[s], L::EPI_WARPS);   // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -539,7 +584,9 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
   } else if (warp_id >= 4) {
     // ===================== epilogue =====================
     const int q = warp_id & 3;
-    uint8_t* stage_buf = smem + L::STORE_OFFSET + q * (32 * 80);
+    const int part = (warp_id - 4) >> 2;                      // which column slice of the tile this warp drains
+    constexpr int COLS_PER_WARP = BN / (L::EPI_WARPS / 4);
+    uint8_t* stage_buf = smem + L::STORE_OFFSET + (warp_id - 4) * (32 * 80);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
@@ -551,7 +598,8 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
       const long long tap_off = (B_MODE == OP_CONV) ? (long long)ztap * p.tap_stride : 0;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(p, tmem_base + uint32_t(acc * BN), true, mt, mt * BM, nt * BN, tap_off, q, lane, stage_buf);
+      epilogue_tile<(BN == 256)>(p, tmem_base + uint32_t(acc * BN), true, mt, mt * BM, nt * BN, part * COLS_PER_WARP,
+                    (part + 1) * COLS_PER_WARP, tap_off, q, lane, stage_buf);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -692,7 +740,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     }
     const int slots = sm_count() * L::MIN_CTAS;
     const int grid = p.tiles_total < slots ? p.tiles_total : slots;
-    kern<<<grid, 256, L::TOTAL, st>>>(ta, tb, p);
+    kern<<<grid, L::THREADS, L::TOTAL, st>>>(ta, tb, p);
   } else {
     using L = SmemLayout<BN>;
     auto kern = gemm_bf16_tcgen05_kernel<BN, A_MODE, B_MODE>;

@@ -423,10 +423,16 @@ class Operator(OperatorModule):
         step = self._graphed_step(model)
         acc = self._acc
         acc.zero_()
+        fast = getattr(model.net, "_fast_head", None) if device.type == "cuda" else None
+        if fast is not None:
+            fast.count_batches = False                # 13 one-element kernels per step -> 13 per epoch (below)
         for b in range(n_batches):
             idx = perm[b * bs:(b + 1) * bs]
             step(protos[idx], pids[idx])
             data_cnt += len(idx)
+        if fast is not None:
+            fast.add_batches(n_batches)
+            fast.count_batches = True
         vals = torch.cat([acc, self.optimizer.stats.double()]).tolist()     # single host sync per epoch
         loss_sum, hits, _, l1_sum = vals
         train_loss = (loss_sum + model.lambda_l1 * l1_sum) / max(n_batches, 1)

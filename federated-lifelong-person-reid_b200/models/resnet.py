@@ -266,10 +266,31 @@ class FastResNetHead:
         res2 = residual.reshape(-1, c) if residual is not None else None
         y = fops.batch_norm_nhwc(x.reshape(-1, c), bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                  training=bn.training, eps=bn.eps, momentum=bn.momentum or 0.1, relu=relu,
-                                 residual=res2, pre_part=pre_part)
-        if bn.training and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
+                                 residual=res2, pre_part=pre_part,
+                                 grad_slots=(self.grad_slot(bn.weight), self.grad_slot(bn.bias)))
+        self._count(bn)
         return y.view(n, h, w, c)
+
+    # ``num_batches_tracked`` bookkeeping: one tiny kernel per BN layer per step. A training loop that knows its step
+    # count sets ``count_batches = False`` and calls :meth:`add_batches` once per epoch instead.
+    count_batches = True
+
+    def _count(self, bn) -> None:
+        if self.count_batches and bn.training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+
+    def batch_norms(self):
+        m = self.m
+        out = [b for i in range(max(m.head_start, 1), 5) for b in getattr(m.base, f"layer{i}").modules()
+               if isinstance(b, (nn.BatchNorm1d, nn.BatchNorm2d))]
+        if m.neck == "bnneck":
+            out.append(m.bottleneck)
+        return out
+
+    def add_batches(self, n: int) -> None:
+        for bn in self.batch_norms():
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += int(n)
 
     def _unit(self, x: torch.Tensor, u: ResidualUnit) -> torch.Tensor:
         identity = x
@@ -293,9 +314,9 @@ class FastResNetHead:
         if m.neck == "bnneck":
             bn = m.bottleneck
             feat = fops.batch_norm_nhwc(global_feat.to(torch.bfloat16), bn.weight, bn.bias, bn.running_mean,
-                                        bn.running_var, training=bn.training, eps=bn.eps, momentum=bn.momentum or 0.1)
-            if bn.training and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
+                                        bn.running_var, training=bn.training, eps=bn.eps, momentum=bn.momentum or 0.1,
+                                        grad_slots=(self.grad_slot(bn.weight), self.grad_slot(bn.bias)))
+            self._count(bn)
         else:
             feat = global_feat.to(torch.bfloat16)
         if not m.training:

@@ -162,7 +162,10 @@ class _BNTrainFn(torch.autograd.Function):
     """Training-mode batch norm over ``[M, C]`` bf16 (NHWC flattened), optional fused residual add + ReLU."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, eps, momentum, relu, pre_part=None):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, eps, momentum, relu, pre_part=None,
+                ggrad=None, bgrad=None):
+        """``ggrad`` / ``bgrad``: the affine parameters' slots in the zeroed flat gradient arena; when given, the
+        backward kernel accumulates dgamma / dbeta straight into them (no temporaries, no AccumulateGrad adds)."""
         m, c = x.shape
         dev = x.device
         y = torch.empty_like(x)
@@ -184,6 +187,7 @@ class _BNTrainFn(torch.autograd.Function):
         ctx.save_for_backward(x, y, gamma, scratch)
         ctx.relu = relu
         ctx.has_res = residual is not None
+        ctx.slots = (ggrad, bgrad)
         return y
 
     @staticmethod
@@ -191,24 +195,29 @@ class _BNTrainFn(torch.autograd.Function):
         x, y, gamma, scratch = ctx.saved_tensors
         m, c = x.shape
         dy = dy.contiguous()
-        dgb = torch.empty(2, c, dtype=torch.float32, device=x.device)
+        ggrad, bgrad = ctx.slots
+        direct = ggrad is not None
+        dgb = None if direct else torch.empty(2, c, dtype=torch.float32, device=x.device)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
         lib = native.load()
         part = torch.empty(lib.flpr_bn_partials_floats(m, c), dtype=torch.float32, device=x.device)
         rc = lib.flpr_bn_bwd(native.ptr(dy), native.ptr(y), native.ptr(x), native.ptr(scratch[2]),
-                             native.ptr(scratch[3]), native.ptr(gamma), native.ptr(dgb[0]), native.ptr(dgb[1]),
-                             native.ptr(part), native.ptr(dres), native.ptr(dx), m, c, int(ctx.relu),
+                             native.ptr(scratch[3]), native.ptr(gamma),
+                             native.ptr(ggrad if direct else dgb[0]), native.ptr(bgrad if direct else dgb[1]),
+                             native.ptr(part), native.ptr(dres), native.ptr(dx), m, c, int(ctx.relu), int(direct),
                              native.stream(x.device))
         native.check(rc, "flpr_bn_bwd")
         native.count_launch(3)
-        return dx, dgb[0], dgb[1], None, None, dres, None, None, None, None
+        if direct:
+            return dx, None, None, None, None, dres, None, None, None, None, None, None
+        return dx, dgb[0], dgb[1], None, None, dres, None, None, None, None, None, None
 
 
 def batch_norm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, running_mean: Optional[torch.Tensor],
                     running_var: Optional[torch.Tensor], *, training: bool, eps: float = 1e-5, momentum: float = 0.1,
                     relu: bool = False, residual: Optional[torch.Tensor] = None,
-                    pre_part: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    pre_part: Optional[torch.Tensor] = None, grad_slots=None) -> torch.Tensor:
     """BatchNorm over ``[M, C]`` (channels last) with fused residual + ReLU. fp32 affine parameters.
     ``pre_part`` ``[P, 2, C]``: column partials (sum, sum of squares) of the producer's fp32 output, written by the
     GEMM / conv epilogue; when given, the statistics pass over ``x`` is skipped."""
@@ -237,7 +246,11 @@ def batch_norm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, ru
         return y.to(x.dtype)
     x = x.contiguous()
     if training:
-        return _BNTrainFn.apply(x, gamma, beta, running_mean, running_var, residual, eps, momentum, relu, pre_part)
+        gg, bg = grad_slots if grad_slots is not None else (None, None)
+        if gg is None or bg is None or not gamma.requires_grad or not beta.requires_grad:
+            gg = bg = None                        # both or neither (e.g. the BNNeck bias is frozen)
+        return _BNTrainFn.apply(x, gamma, beta, running_mean, running_var, residual, eps, momentum, relu, pre_part,
+                                gg, bg)
     scale = gamma * torch.rsqrt(running_var + eps)
     shift = beta - running_mean * scale
     return affine_act(x, scale, shift, relu=relu, residual=residual)

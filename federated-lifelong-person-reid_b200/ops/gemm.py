@@ -187,6 +187,7 @@ class _LinearFn(torch.autograd.Function):
         ctx.w_needs_grad = w_master.requires_grad
         ctx.grad_out = grad_out
         ctx.want_stats = want_stats
+        ctx.set_materialize_grads(False)        # no zero tensor for the (non-differentiable) statistics output
         if not want_stats:
             return gemm(x, w_bf16)
         part = col_part_buffer(x.shape[0], w_bf16.shape[0], x.device)
@@ -196,6 +197,8 @@ class _LinearFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, *_):
+        if dy is None:
+            return None, None, None, None, None
         x, w = ctx.saved_tensors
         dy = _bf(dy).contiguous()
         dx = dw = None
@@ -231,6 +234,7 @@ class _Conv3x3Fn(torch.autograd.Function):
         ctx.save_for_backward(x, w_bf16)
         ctx.w_needs_grad = w_master.requires_grad
         ctx.grad_out = grad_out
+        ctx.set_materialize_grads(False)
         if not want_stats:
             return conv_nhwc(x, w_bf16, padding=1)
         n, h, wd, _ = x.shape
@@ -241,6 +245,8 @@ class _Conv3x3Fn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, *_):
+        if dy is None:
+            return None, None, None, None, None
         x, w = ctx.saved_tensors
         dy = _bf(dy).contiguous()
         dx = dw = None

@@ -60,7 +60,7 @@ def _declare(lib: C.CDLL) -> None:
         "flpr_ce_label_smooth": [P, P, P, P, I, I, L, F, F, I, I, P],
         "flpr_bn_fwd": [P, P, P, P, P, P, P, P, P, P, P, P, I, I, F, F, I, P, I, P],
         "flpr_affine_act": [P, P, P, P, P, I, I, I, P],
-        "flpr_bn_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
+        "flpr_bn_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, P],
         "flpr_bn_partials_floats": [I, I],
         "flpr_gap_fwd": [P, P, P, I, I, I, P],
         "flpr_gap_bwd": [P, P, I, I, I, P],

@@ -50,6 +50,14 @@ def test_fast_head_matches_module_forward_backward():
     g_ref = ref.base.layer4[2].conv2.weight.grad
     cos = torch.nn.functional.cosine_similarity(g_fast.flatten(), g_ref.flatten(), dim=0).item()
     assert cos > 0.95, cos
+    # batch-norm affine gradients are accumulated by the backward kernel straight into the arena slots
+    for name, mod in (("base.layer4.2.bn2", ref.base.layer4[2].bn2), ("base.layer4.0.downsample.1",
+                                                                       ref.base.layer4[0].downsample[1])):
+        for leaf in ("weight", "bias"):
+            g_fast = model.arena.view(model.arena.grad, f"{name}.{leaf}")
+            g_ref = getattr(mod, leaf).grad
+            cos = torch.nn.functional.cosine_similarity(g_fast.flatten(), g_ref.flatten(), dim=0).item()
+            assert cos > 0.9, (name, leaf, cos)
 
 
 def test_graphed_step_matches_eager():
