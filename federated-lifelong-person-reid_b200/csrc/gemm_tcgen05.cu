@@ -32,6 +32,7 @@
 namespace flpr {
 
 enum { OP_KMAJOR = 0, OP_MNMAJOR = 1, OP_CONV = 2, OP_TAPFLIP = 3 };
+enum { EPI_GENERIC = 0, EPI_LEAN = 1 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
@@ -61,6 +62,8 @@ struct GemmParams {
   int tiles_m, tiles_n, tiles_z, tiles_total;
   // fused batch-norm statistics: per (m-tile, epilogue-warp) column partials of sum / sum^2 of the fp32 accumulators
   float* col_part;       // [tiles_m * 4][2][N] or nullptr
+  int debug;             // FLPR_GEMM_DEBUG bit mask (bottleneck isolation, results are WRONG when set):
+                         //   1 skip the epilogue body, 2 skip global stores, 4 skip TMA loads (MMA on stale smem)
 };
 
 template <int BN>
@@ -193,6 +196,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
                                                float bm, bool use_stage) {
   const int row = m0 + q * 32 + lane;
   if (n0 + c0 >= p.N) return;
+  if (p.debug & 1) return;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
@@ -204,9 +208,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   const bool stats_from_stage = p.col_part != nullptr && use_stage && (n0 + c0 + 32 <= p.N);
   if (p.col_part != nullptr && !stats_from_stage) {
     // fused batch-norm statistics of the raw fp32 conv output (rows >= M are exact zeros: TMA OOB fill)
+    // (of the value that is stored: bf16-rounded when the output is bf16, like the staged path below)
     float s1[32], s2[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { s1[j] = v[j]; s2[j] = v[j] * v[j]; }
+    for (int j = 0; j < 32; ++j) {
+      const float x = p.out_bf16 ? __bfloat162float(__float2bfloat16(v[j])) : v[j];
+      s1[j] = x;
+      s2[j] = x * x;
+    }
     warp_colsum32(s1, lane);
     warp_colsum32(s2, lane);
     const int col = n0 + c0 + lane;
@@ -278,32 +287,36 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         }
         if (use_stage) {
           // transpose through this warp's private staging tile so that 4 lanes write one row's 64 B contiguously
-          uint8_t* st = stage_buf + lane * 80;
+          const uint32_t sbase = smem_u32(stage_buf);
+          const uint32_t st = sbase + lane * 80;
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<uint4*>(st + j4 * 16) = pk[j4];
+          for (int j4 = 0; j4 < 4; ++j4) sts_128(st + j4 * 16, pk[j4]);
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int rr = 8 * j + (lane >> 2);
-            const uint4 u = *reinterpret_cast<const uint4*>(stage_buf + rr * 80 + (lane & 3) * 16);
+            const uint4 u = lds_128(sbase + rr * 80 + (lane & 3) * 16);
             const int grow = m0 + q * 32 + rr;
-            if (grow < p.M)
+            if (grow < p.M && !(p.debug & 2))
               *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)grow * p.ldo + n0 +
                                         c0 + tap_off + (lane & 3) * 8) = u;
           }
           if (stats_from_stage) {
             // fused batch-norm statistics: lane = column, walk the 32 staged rows (the bf16 values that are stored;
             // rows >= M hold exact zeros). 32 conflict-free 2-byte smem loads instead of 62 shuffles.
-            float a1 = 0.f, a2 = 0.f;
+            float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr) {
-              const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stage_buf + rr * 80 + lane * 2));
+            for (int rr = 0; rr < 32; rr += 2) {
+              const float x = lds_bf16(sbase + rr * 80 + lane * 2);
+              const float y = lds_bf16(sbase + (rr + 1) * 80 + lane * 2);
               a1 += x;
               a2 = fmaf(x, x, a2);
+              b1 += y;
+              b2 = fmaf(y, y, b2);
             }
             float* dst = p.col_part + ((size_t)(mt * 4 + q) * 2) * p.N + n0 + c0 + lane;
-            dst[0] = a1;
-            dst[p.N] = a2;
+            dst[0] = a1 + b1;
+            dst[p.N] = a2 + b2;
           }
           __syncwarp();
         } else {
@@ -368,6 +381,115 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       tmem_ld_wait();
       if (c0 + 64 < ce) tmem_ld_32x32b_x32(tbase + uint32_t(c0 + 64), ra);
       epilogue_chunk(p, rb, mt, m0, n0, c0 + 32, tap_off, q, lane, stage_buf, bm, use_stage);
+    }
+  }
+}
+
+// Lean epilogue (EPI_LEAN): the three hot output kinds - bf16 store (+ fused BN statistics), fp32 store, fp32
+// atomic accumulate (split-K) - all row-major, no bias / residual / ReLU / transpose, N a multiple of 32. Every chunk
+// goes through the warp's 32 x 64-byte staging tile so that one store instruction covers 8 full 64-byte row segments
+// (a lane-per-row store would touch 32 different lines per instruction; the atomic path uses red.v4.f32).
+// A separate, small code path: the generic epilogue above inlines ~7k instructions, which thrashes the instruction
+// cache when it sits in the inner loop of the persistent kernel.
+template <bool PIPE>
+__device__ __forceinline__ void epilogue_tile_lean(const GemmParams& p, uint32_t tmem_acc, int mt, int m0, int n0,
+                                                   int cb, int ce, long long tap_off, int q, int lane,
+                                                   uint32_t sbase) {
+  const uint32_t tbase = tmem_acc + (uint32_t(q * 32) << 16);
+  const uint32_t st = sbase + lane * 80;
+  const int sub_row = lane >> 2, sub_col = lane & 3;
+  const float alpha = p.alpha;
+  uint32_t ra[32], rb[32];
+  auto chunk = [&](const uint32_t (&r)[32], int c0) {
+    if ((p.debug & 1) || n0 + c0 >= p.N) return;       // (tile wider than the matrix: nothing to store)
+    if (p.out_bf16) {
+      uint4 pk[4];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk[j4]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          h[t] = __floats2bfloat162_rn(__uint_as_float(r[j4 * 8 + t * 2]) * alpha,
+                                       __uint_as_float(r[j4 * 8 + t * 2 + 1]) * alpha);
+      }
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) sts_128(st + j4 * 16, pk[j4]);
+      __syncwarp();
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + n0 + c0 + tap_off + sub_col * 8;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = 8 * j + sub_row;
+        const uint4 u = lds_128(sbase + rr * 80 + sub_col * 16);
+        const int grow = m0 + q * 32 + rr;
+        if (grow < p.M) *reinterpret_cast<uint4*>(o + (long long)grow * p.ldo) = u;
+      }
+      if (p.col_part != nullptr) {
+        // fused batch-norm statistics of the stored (bf16) values: lane = column, 32 staged rows (rows >= M are 0)
+        float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 32; rr += 2) {
+          const float x = lds_bf16(sbase + rr * 80 + lane * 2);
+          const float y = lds_bf16(sbase + (rr + 1) * 80 + lane * 2);
+          a1 += x;
+          a2 = fmaf(x, x, a2);
+          b1 += y;
+          b2 = fmaf(y, y, b2);
+        }
+        float* dst = p.col_part + ((size_t)(mt * 4 + q) * 2) * p.N + n0 + c0 + lane;
+        dst[0] = a1 + b1;
+        dst[p.N] = a2 + b2;
+      }
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          uint4 u;
+          u.x = __float_as_uint(__uint_as_float(r[half * 16 + j4 * 4 + 0]) * alpha);
+          u.y = __float_as_uint(__uint_as_float(r[half * 16 + j4 * 4 + 1]) * alpha);
+          u.z = __float_as_uint(__uint_as_float(r[half * 16 + j4 * 4 + 2]) * alpha);
+          u.w = __float_as_uint(__uint_as_float(r[half * 16 + j4 * 4 + 3]) * alpha);
+          sts_128(st + j4 * 16, u);
+        }
+        __syncwarp();
+        float* o = reinterpret_cast<float*>(p.out) + n0 + c0 + half * 16 + tap_off + sub_col * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rr = 8 * j + sub_row;
+          const uint4 u = lds_128(sbase + rr * 80 + sub_col * 16);
+          const int grow = m0 + q * 32 + rr;
+          if (grow < p.M) {
+            float* dst = o + (long long)grow * p.ldo;
+            if (p.atomic_add)
+              red_add_v4_f32(dst, u);
+            else
+              *reinterpret_cast<uint4*>(dst) = u;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  };
+  if constexpr (!PIPE) {
+#pragma unroll 1
+    for (int c0 = cb; c0 < ce; c0 += 32) {
+      tmem_ld_32x32b_x32(tbase + uint32_t(c0), ra);
+      tmem_ld_wait();
+      chunk(ra, c0);
+    }
+  } else {
+    tmem_ld_32x32b_x32(tbase + uint32_t(cb), ra);
+#pragma unroll 1
+    for (int c0 = cb; c0 < ce; c0 += 64) {
+      tmem_ld_wait();
+      if (c0 + 32 < ce) tmem_ld_32x32b_x32(tbase + uint32_t(c0 + 32), rb);
+      chunk(ra, c0);
+      if (c0 + 32 < ce) {
+        tmem_ld_wait();
+        if (c0 + 64 < ce) tmem_ld_32x32b_x32(tbase + uint32_t(c0 + 64), ra);
+        chunk(rb, c0 + 32);
+      }
     }
   }
 }
@@ -479,7 +601,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 // that concurrently running CTAs share the A rows in L2). Two accumulator stages in TMEM: the epilogue warps drain
 // tile i (TMEM -> registers -> global) while the MMA warp already accumulates tile i+1, and the TMA producer runs
 // ahead across tile boundaries, so neither the pipeline fill nor the epilogue is exposed for short-K GEMMs.
-template <int BN, int A_MODE, int B_MODE>
+template <int BN, int A_MODE, int B_MODE, int EPI>
 __global__ void __launch_bounds__(PersistLayout<BN>::THREADS, PersistLayout<BN>::MIN_CTAS)
 gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                     const GemmParams p) {
@@ -538,9 +660,13 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          load_kblock<BN, A_MODE, B_MODE>(p, &tmA, &tmB, sa, sa + A_STAGE_BYTES, &full_bar[stage], kb, mt, mt * BM,
-                                          nt * BN, ztap);
+          if (p.debug & 4) {
+            mbar_arrive(&full_bar[stage]);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            load_kblock<BN, A_MODE, B_MODE>(p, &tmA, &tmB, sa, sa + A_STAGE_BYTES, &full_bar[stage], kb, mt, mt * BM,
+                                            nt * BN, ztap);
+          }
           if (++stage == L::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -598,8 +724,12 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
       const long long tap_off = (B_MODE == OP_CONV) ? (long long)ztap * p.tap_stride : 0;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<(BN == 256)>(p, tmem_base + uint32_t(acc * BN), true, mt, mt * BM, nt * BN, part * COLS_PER_WARP,
-                    (part + 1) * COLS_PER_WARP, tap_off, q, lane, stage_buf);
+      if constexpr (EPI == EPI_LEAN)
+        epilogue_tile_lean<(BN == 256)>(p, tmem_base + uint32_t(acc * BN), mt, mt * BM, nt * BN, part * COLS_PER_WARP,
+                                        (part + 1) * COLS_PER_WARP, tap_off, q, lane, smem_u32(stage_buf));
+      else
+        epilogue_tile<(BN == 256)>(p, tmem_base + uint32_t(acc * BN), true, mt, mt * BM, nt * BN,
+                                   part * COLS_PER_WARP, (part + 1) * COLS_PER_WARP, tap_off, q, lane, stage_buf);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -725,22 +855,43 @@ static int sm_count() {
 template <int BN, int A_MODE, int B_MODE>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, int splits, cudaStream_t st) {
   GemmParams p = p_in;
+  {
+    const char* e = getenv("FLPR_GEMM_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+  }
   p.tiles_m = (p.M + BM - 1) / BM;
   p.tiles_n = (p.N + BN - 1) / BN;
   p.tiles_z = splits;
   p.tiles_total = p.tiles_m * p.tiles_n * splits;
   if (use_persist()) {
     using L = PersistLayout<BN>;
-    auto kern = gemm_bf16_tcgen05_persistent_kernel<BN, A_MODE, B_MODE>;
-    static bool configured = false;
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
-      if (e != cudaSuccess) return set_err("cudaFuncSetAttribute(smem, persistent)", (int)e);
-      configured = true;
-    }
+    // lean epilogue: plain row-major bf16 / fp32 / fp32-atomic output, every 32-column chunk full and 16-byte aligned
+    const long long esz = p.out_bf16 ? 2 : 4;
+    const bool lean = !p.trans_out && p.residual == nullptr && p.bias_n == nullptr && p.bias_m == nullptr &&
+                      !p.relu && (p.N % 32) == 0 && ((p.ldo * esz) % 16) == 0 && ((p.tap_stride * esz) % 16) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.out) % 16) == 0 && !(p.atomic_add && p.out_bf16) &&
+                      !(p.col_part != nullptr && !p.out_bf16) && getenv("FLPR_GEMM_GENERIC_EPI") == nullptr;
     const int slots = sm_count() * L::MIN_CTAS;
     const int grid = p.tiles_total < slots ? p.tiles_total : slots;
-    kern<<<grid, L::THREADS, L::TOTAL, st>>>(ta, tb, p);
+    if (lean) {
+      auto kern = gemm_bf16_tcgen05_persistent_kernel<BN, A_MODE, B_MODE, EPI_LEAN>;
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+        if (e != cudaSuccess) return set_err("cudaFuncSetAttribute(smem, persistent lean)", (int)e);
+        configured = true;
+      }
+      kern<<<grid, L::THREADS, L::TOTAL, st>>>(ta, tb, p);
+    } else {
+      auto kern = gemm_bf16_tcgen05_persistent_kernel<BN, A_MODE, B_MODE, EPI_GENERIC>;
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+        if (e != cudaSuccess) return set_err("cudaFuncSetAttribute(smem, persistent)", (int)e);
+        configured = true;
+      }
+      kern<<<grid, L::THREADS, L::TOTAL, st>>>(ta, tb, p);
+    }
   } else {
     using L = SmemLayout<BN>;
     auto kern = gemm_bf16_tcgen05_kernel<BN, A_MODE, B_MODE>;

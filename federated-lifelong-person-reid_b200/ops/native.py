@@ -121,9 +121,12 @@ def check(rc: int, what: str) -> None:
 
 
 # launch counter: bench.py reports how many flpr kernels were launched inside the timed region. Per-thread counts
-# (client threads run concurrently; graph capture measures "launches recorded by THIS thread") summed on read.
+# summed on read. While a CUDA graph is being captured the launches that belong to the capture are those of the
+# capturing thread and of the autograd engine threads (backward runs there) - everything except OTHER client threads.
 _tls = threading.local()
 _counters: list = []
+_client_threads: set = set()
+_capture = {"owner": None, "count": 0}
 
 
 def _counter() -> list:
@@ -135,8 +138,17 @@ def _counter() -> list:
     return c
 
 
+def register_client_thread() -> None:
+    _client_threads.add(threading.get_ident())
+
+
 def count_launch(n: int = 1) -> None:
     _counter()[0] += n
+    owner = _capture["owner"]
+    if owner is not None:
+        me = threading.get_ident()
+        if me == owner or me not in _client_threads:
+            _capture["count"] += n
 
 
 def launches() -> int:
@@ -144,6 +156,11 @@ def launches() -> int:
     return sum(c[0] for c in _counters)
 
 
-def thread_launches() -> int:
-    """Launches issued by the calling thread (graph capture bookkeeping)."""
-    return _counter()[0]
+def capture_count_begin() -> None:
+    _capture["owner"], _capture["count"] = threading.get_ident(), 0
+
+
+def capture_count_end() -> int:
+    n = _capture["count"]
+    _capture["owner"] = None
+    return n

@@ -310,6 +310,8 @@ class ExperimentStage:
         done: List[torch.cuda.Event] = []
 
         def run(client) -> None:
+            from ..ops import native
+            native.register_client_thread()
             torch.cuda.set_device(dev)
             stream = getattr(client, "_stream", None)
             if stream is None:

@@ -51,10 +51,10 @@ class GraphedStep:
                 st["static"] = [t.clone() for t in tensors]
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                l0 = native.thread_launches()
+                native.capture_count_begin()
                 with capture(g):
                     self.fn(*st["static"])
-                st["launches"] = native.thread_launches() - l0
+                st["launches"] = native.capture_count_end()
                 native.count_launch(-st["launches"])          # capture recorded, did not execute
                 st["graph"] = g
         for s, t in zip(st["static"], tensors):

@@ -130,10 +130,12 @@ def test_gemm_fused_bn_statistics(m, n, k, bn):
     ref = a.float() @ b.float().t()
     _close(y, ref)
     assert torch.isfinite(part).all()
-    _close(part[:, 0].sum(0), ref.sum(0), rtol=1e-3, atol=1e-3 * ref.abs().sum(0).max().item())
-    _close(part[:, 1].sum(0), (ref * ref).sum(0), rtol=1e-3, atol=1e-3 * (ref * ref).sum(0).max().item())
-    # first partial row = rows 0..31
-    _close(part[0, 0], ref[:32].sum(0), rtol=1e-3, atol=1e-2)
+    # the statistics are those of the stored (bf16-rounded) output, accumulated in fp32
+    yf = y.float()
+    _close(part[:, 0].sum(0), yf.sum(0), rtol=1e-4, atol=1e-3 * yf.abs().sum(0).max().item())
+    _close(part[:, 1].sum(0), (yf * yf).sum(0), rtol=1e-4, atol=1e-3 * (yf * yf).sum(0).max().item())
+    _close(part[0, 0], yf[:32].sum(0), rtol=1e-4, atol=1e-3)                   # first partial row = rows 0..31
+    _close(part[:, 0].sum(0), ref.sum(0), rtol=2e-2, atol=2e-2 * ref.abs().sum(0).max().item())
 
 
 def test_conv_bn_fused_statistics_match_unfused():
