@@ -58,6 +58,7 @@ struct GemmParams {
   int cH, cW, cC, cTH, cNB, cKW, cPadH, cPadW, cTilesPerImg, cSplits;
   long long tap_stride;  // conv wgrad: output column offset per filter tap
   int cTaps;             // KH*KW (OP_TAPFLIP: B column offset = (cTaps-1-tap) * N)
+  int cStride;           // convolution stride (A operand: TMA element strides), 1 or 2
   // persistent scheduling
   int tiles_m, tiles_n, tiles_z, tiles_total;
   // fused batch-norm statistics: per (m-tile, epilogue-warp) column partials of sum / sum^2 of the fp32 accumulators
@@ -123,7 +124,7 @@ __device__ __forceinline__ void load_kblock(const GemmParams& p, const CUtensorM
       img0 = mt / p.cTilesPerImg;
       h0 = (mt - img0 * p.cTilesPerImg) * p.cTH;
     }
-    tma_load_4d(sa, tmA, bar, cc * BK, kw - p.cPadW, h0 + kh - p.cPadH, img0);
+    tma_load_4d(sa, tmA, bar, cc * BK, kw - p.cPadW, h0 * p.cStride + kh - p.cPadH, img0);
   }
   if constexpr (B_MODE == OP_KMAJOR) {
     tma_load_2d(sb, tmB, bar, kb * BK, n0);
@@ -404,13 +405,49 @@ __device__ __forceinline__ void epilogue_tile_lean(const GemmParams& p, uint32_t
     if ((p.debug & 1) || n0 + c0 >= p.N) return;       // (tile wider than the matrix: nothing to store)
     if (p.out_bf16) {
       uint4 pk[4];
+      if (p.bias_n == nullptr && p.residual == nullptr && !p.relu) {
 #pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk[j4]);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk[j4]);
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-          h[t] = __floats2bfloat162_rn(__uint_as_float(r[j4 * 8 + t * 2]) * alpha,
-                                       __uint_as_float(r[j4 * 8 + t * 2 + 1]) * alpha);
+          for (int t = 0; t < 4; ++t)
+            h[t] = __floats2bfloat162_rn(__uint_as_float(r[j4 * 8 + t * 2]) * alpha,
+                                         __uint_as_float(r[j4 * 8 + t * 2 + 1]) * alpha);
+        }
+      } else {
+        // inference epilogue of the BN-folded trunk: + bias[col] (+ residual[row, col]) -> ReLU
+        const int grow_l = m0 + q * 32 + lane;
+        const bool has_res = p.residual != nullptr && grow_l < p.M;
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (long long)grow_l * p.ldo + n0 + c0 + tap_off);
+        const float4* bp = reinterpret_cast<const float4*>(p.bias_n + n0 + c0);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          float v[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[j4 * 8 + t]) * alpha;
+          if (p.bias_n != nullptr) {
+            const float4 b0 = bp[j4 * 2], b1 = bp[j4 * 2 + 1];
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (has_res) {
+            const uint4 u = rp[j4];
+            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __bfloat1622float2(rh[t]);
+              v[2 * t] += f.x;
+              v[2 * t + 1] += f.y;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
+          }
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk[j4]);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
+        }
       }
 #pragma unroll
       for (int j4 = 0; j4 < 4; ++j4) sts_128(st + j4 * 16, pk[j4]);
@@ -771,7 +808,7 @@ static bool load_encode() {
 struct MapKey {
   const void* ptr;
   uint64_t d0, d1, d2, d3, s1, s2, s3;
-  uint32_t b0, b1, b2, b3, rank;
+  uint32_t b0, b1, b2, b3, rank, estride, pad_;
   bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
 struct MapKeyHash {
@@ -786,11 +823,12 @@ static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 // rank-2 or rank-4 bf16 tensor map with 128B swizzle, zero OOB fill.
 static int get_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+                   const uint32_t* box, uint32_t spatial_stride = 1) {
   MapKey k;
   memset(&k, 0, sizeof(k));
   k.ptr = ptr;
   k.rank = rank;
+  k.estride = spatial_stride;
   k.d0 = dims[0];
   k.d1 = dims[1];
   k.b0 = box[0];
@@ -815,6 +853,7 @@ static int get_map(CUtensorMap* out, const void* ptr, int rank, const uint64_t* 
   cuuint64_t gstr[3];
   cuuint32_t bx[4];
   cuuint32_t es[4] = {1, 1, 1, 1};
+  if (rank == 4 && spatial_stride > 1) es[1] = es[2] = spatial_stride;   // strided convolution: every s-th pixel
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
@@ -867,8 +906,11 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     using L = PersistLayout<BN>;
     // lean epilogue: plain row-major bf16 / fp32 / fp32-atomic output, every 32-column chunk full and 16-byte aligned
     const long long esz = p.out_bf16 ? 2 : 4;
-    const bool lean = !p.trans_out && p.residual == nullptr && p.bias_n == nullptr && p.bias_m == nullptr &&
-                      !p.relu && (p.N % 32) == 0 && ((p.ldo * esz) % 16) == 0 && ((p.tap_stride * esz) % 16) == 0 &&
+    const bool act = p.residual != nullptr || p.bias_n != nullptr || p.relu;
+    const bool lean = !p.trans_out && p.bias_m == nullptr && (!act || (p.out_bf16 && !p.atomic_add)) &&
+                      (reinterpret_cast<uintptr_t>(p.bias_n) % 16) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.residual) % 16) == 0 &&
+                      (p.N % 32) == 0 && ((p.ldo * esz) % 16) == 0 && ((p.tap_stride * esz) % 16) == 0 &&
                       (reinterpret_cast<uintptr_t>(p.out) % 16) == 0 && !(p.atomic_add && p.out_bf16) &&
                       !(p.col_part != nullptr && !p.out_bf16) && getenv("FLPR_GEMM_GENERIC_EPI") == nullptr;
     const int slots = sm_count() * L::MIN_CTAS;
@@ -1016,25 +1058,29 @@ static int conv_tiling(int H, int W, int* TH, int* NB, int* tiles_per_img) {
   return 0;
 }
 
-// Implicit-GEMM convolution, stride 1: X [NIMG,H,W,C] bf16 NHWC, Wt [Cout, KH*KW*C] bf16 (tap-major, then C),
-// out [NIMG*H*W, Cout]. Requires C % 64 == 0, W a power of two <= 128 and (H*W) | 128 or 128/W | H.
+// Implicit-GEMM convolution (stride 1 or 2): X [NIMG,H,W,C] bf16 NHWC, Wt [Cout, KH*KW*C] bf16 (tap-major, then C),
+// out [NIMG*Ho*Wo, Cout]. Requires C % 64 == 0, Wo a power of two <= 128 and (Ho*Wo) | 128 or 128/Wo | Ho.
+// A strided convolution is the same pipeline: the TMA tensor map walks the input with element strides {1,s,s,1}.
 // col_part: see flpr_gemm_bf16 (fused batch-norm statistics of the conv output).
 int flpr_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int NIMG, int H, int W, int C, int Cout, int KH,
                         int KW, int pad_h, int pad_w, int out_bf16, float alpha, const float* bias_n, int relu,
-                        const void* residual, int bn_req, float* col_part, cudaStream_t stream) {
+                        const void* residual, int bn_req, float* col_part, int stride, cudaStream_t stream) {
   bind_device_of(X);
   if (C % 64) return set_err("conv: C must be a multiple of 64", -7);
+  if (stride != 1 && stride != 2) return set_err("conv: stride must be 1 or 2", -13);
+  const int Ho = (H + 2 * pad_h - KH) / stride + 1;
+  const int Wo = (W + 2 * pad_w - KW) / stride + 1;
   int TH, NB, tiles_per_img, rc;
-  if ((rc = conv_tiling(H, W, &TH, &NB, &tiles_per_img))) return rc;
-  const int M = NIMG * H * W;
+  if ((rc = conv_tiling(Ho, Wo, &TH, &NB, &tiles_per_img))) return rc;
+  const int M = NIMG * Ho * Wo;
   const int K = KH * KW * C;
   const int BN = pick_bn(M, Cout, 1, bn_req);
   CUtensorMap ta, tb;
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NIMG};
     uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-    uint32_t box[4] = {64, (uint32_t)W, (uint32_t)TH, (uint32_t)NB};
-    if ((rc = get_map(&ta, X, 4, dims, str, box))) return rc;
+    uint32_t box[4] = {64, (uint32_t)(Wo * stride), (uint32_t)(TH * stride), (uint32_t)NB};
+    if ((rc = get_map(&ta, X, 4, dims, str, box, (uint32_t)stride))) return rc;
     uint64_t d2[2] = {(uint64_t)K, (uint64_t)Cout};
     uint64_t s2[1] = {(uint64_t)K * 2};
     uint32_t b2[2] = {BK, (uint32_t)BN};
@@ -1047,8 +1093,8 @@ int flpr_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int NIMG, int 
   p.out = out; p.ldo = Cout; p.out_bf16 = out_bf16; p.alpha = alpha; p.bias_n = bias_n; p.relu = relu;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.col_part = col_part;
-  p.cH = H; p.cW = W; p.cC = C; p.cTH = TH; p.cNB = NB; p.cKW = KW; p.cPadH = pad_h; p.cPadW = pad_w;
-  p.cTilesPerImg = tiles_per_img; p.cTaps = KH * KW;
+  p.cH = Ho; p.cW = Wo; p.cC = C; p.cTH = TH; p.cNB = NB; p.cKW = KW; p.cPadH = pad_h; p.cPadW = pad_w;
+  p.cTilesPerImg = tiles_per_img; p.cTaps = KH * KW; p.cStride = stride;
   return dispatch_bn(BN, OP_CONV, OP_KMAJOR, ta, tb, p, 1, stream);
 }
 
@@ -1083,7 +1129,7 @@ int flpr_conv_dgrad_nhwc_bf16(const void* dY, const void* Wt, void* out, int NIM
   p.out = out; p.ldo = Cin; p.out_bf16 = out_bf16; p.alpha = 1.f;
   p.cH = H; p.cW = W; p.cC = Cout; p.cTH = TH; p.cNB = NB; p.cKW = KW;
   p.cPadH = KH - 1 - pad_h; p.cPadW = KW - 1 - pad_w;
-  p.cTilesPerImg = tiles_per_img; p.cTaps = KH * KW;
+  p.cTilesPerImg = tiles_per_img; p.cTaps = KH * KW; p.cStride = 1;
   return dispatch_bn(BN, OP_CONV, OP_TAPFLIP, ta, tb, p, 1, stream);
 }
 

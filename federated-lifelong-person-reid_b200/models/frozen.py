@@ -6,8 +6,12 @@ What changes versus running the ``nn.Module``: batch-norm is folded into the pre
 conv+bias+residual+ReLU are single fused calls, and a whole trunk pass for a given batch size is captured in a CUDA
 graph so that ~160 module dispatches per batch collapse into one launch.
 
-NOTE (round-1 status): the convolutions of the *trunk* still run on cuDNN; the trainable head (layer4 + classifier)
-runs on the hand-written tcgen05 kernels. Trunk implicit-GEMM kernels are listed as future work in DESIGN.md.
+Execution paths of the residual stages (``native`` flag):
+* **native** (default on CUDA when the shapes fit): every 1x1 convolution is a tcgen05 GEMM and every 3x3 / strided
+  convolution an implicit GEMM of ``csrc/gemm_tcgen05.cu`` (NHWC bf16, folded-BN bias + residual + ReLU in the lean
+  epilogue, stride 2 through TMA element strides) - the same kernels as the trainable head;
+* **library** fallback (cuDNN fused conv calls) for shapes the implicit-GEMM tiling does not cover.
+The 7x7 stem convolution (3 input channels) and the max-pool run on cuDNN / ATen in both paths.
 """
 from __future__ import annotations
 
@@ -48,6 +52,9 @@ class FoldedTrunk:
         self._graphs: Dict[Tuple, List[dict]] = {}
         self._slot_lock = threading.Lock()
         self._fused_ok = self._probe_fused()
+        self.native = True
+        self._native_cache: Dict[Tuple, bool] = {}
+        self._prepare_native()
 
     def _fold_unit(self, u) -> dict:
         d = {"kind": u.kind}
@@ -86,7 +93,91 @@ class FoldedTrunk:
             y = y + residual
         return F.relu_(y) if relu else y
 
+    # ------------------------------------------------------------------ native (tcgen05) residual stages
+    def _prepare_native(self) -> None:
+        """OHWI bf16 weights + fp32 biases for the implicit-GEMM kernels."""
+        for op in self.ops:
+            if op[0] != "unit":
+                continue
+            d = op[1]
+            for key in ("c1", "c2", "c3", "ds"):
+                if key in d:
+                    w, b, stride, padding = d[key]
+                    d[key + "n"] = (w.permute(0, 2, 3, 1).contiguous(), b.float().contiguous(), int(stride[0]),
+                                    int(padding[0]))
+
+    def _native_ok(self, shape) -> bool:
+        """Dry shape walk of :meth:`_forward_native`: every convolution must fit the implicit-GEMM tiling."""
+        cached = self._native_cache.get(shape)
+        if cached is not None:
+            return cached
+        from ..ops.gemm import conv_supported
+        ok = getattr(self, "native", True) and self.device.type == "cuda" and self.dtype == torch.bfloat16
+
+        def step(h, w, conv):
+            wt, _, stride, padding = conv
+            k, cin = wt.shape[1], wt.shape[3]
+            good = (cin % 8 == 0) if (k == 1 and stride == 1) else conv_supported(h, w, cin, k, stride, padding)
+            return good, (h + 2 * padding - k) // stride + 1, (w + 2 * padding - k) // stride + 1
+
+        if ok:
+            _, _, h, w = shape
+            h, w = (h + 2 * 3 - 7) // 2 + 1, (w + 2 * 3 - 7) // 2 + 1         # 7x7 / 2 stem
+            h, w = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1                 # 3x3 / 2 max-pool
+            for op in self.ops:
+                if op[0] != "unit" or not ok:
+                    continue
+                d = op[1]
+                if "dsn" in d:
+                    ok = ok and step(h, w, d["dsn"])[0]
+                g, h1, w1 = step(h, w, d["c1n"])
+                ok = ok and g
+                g, h1, w1 = step(h1, w1, d["c2n"])
+                ok = ok and g
+                if "c3n" in d:
+                    g, h1, w1 = step(h1, w1, d["c3n"])
+                    ok = ok and g
+                h, w = h1, w1
+        self._native_cache[shape] = bool(ok)
+        return bool(ok)
+
+    @staticmethod
+    def _nconv(x: torch.Tensor, wt, b, stride: int, padding: int, relu: bool,
+               residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x: [N,H,W,C] bf16 contiguous -> [N,Ho,Wo,Cout]"""
+        from ..ops import gemm as gops
+        cout, k = wt.shape[0], wt.shape[1]
+        n, h, w, c = x.shape
+        if k == 1 and stride == 1:
+            res2 = residual.reshape(-1, cout) if residual is not None else None
+            y = gops.gemm(x.reshape(-1, c), wt.reshape(cout, c), bias_n=b, relu=relu, residual=res2)
+            return y.view(n, h, w, cout)
+        return gops.conv_nhwc(x, wt, padding=padding, stride=stride, bias=b, relu=relu, residual=residual)
+
+    def _forward_native(self, x: torch.Tensor) -> torch.Tensor:
+        for op in self.ops:
+            if op[0] == "conv_relu":
+                x = self._conv(x, op[1], op[2], op[3], op[4], True)
+            elif op[0] == "maxpool":
+                x = F.max_pool2d(x, 3, 2, 1)
+                x = x.permute(0, 2, 3, 1).contiguous()                   # NHWC from here on (free for channels_last)
+            else:
+                d = op[1]
+                identity = x if "dsn" not in d else self._nconv(x, *d["dsn"], relu=False)
+                out = self._nconv(x, *d["c1n"], relu=True)
+                if d["kind"] == "basic":
+                    x = self._nconv(out, *d["c2n"], relu=True, residual=identity)
+                else:
+                    out = self._nconv(out, *d["c2n"], relu=True)
+                    x = self._nconv(out, *d["c3n"], relu=True, residual=identity)
+        return x.permute(0, 3, 1, 2)                                      # logical NCHW, channels_last memory
+
     def _forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._native_ok(tuple(x.shape)) and any(op[0] == "unit" for op in self.ops):
+            return self._forward_native(x)
+        return self._forward_library(x)
+
+    def _forward_library(self, x: torch.Tensor) -> torch.Tensor:
         for op in self.ops:
             if op[0] == "conv_relu":
                 x = self._conv(x, op[1], op[2], op[3], op[4], True)

@@ -107,18 +107,20 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
 def conv_nhwc(x: torch.Tensor, w: torch.Tensor, *, padding: int = 1, out_dtype: torch.dtype = torch.bfloat16,
               alpha: float = 1.0, bias: Optional[torch.Tensor] = None, relu: bool = False,
               residual: Optional[torch.Tensor] = None, bn: int = 0,
-              col_part: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Stride-1 convolution as an implicit GEMM. ``x``: ``[N,H,W,C]`` bf16, ``w``: ``[Cout,KH,KW,C]``.
+              col_part: Optional[torch.Tensor] = None, stride: int = 1) -> torch.Tensor:
+    """Convolution (stride 1 or 2) as an implicit GEMM. ``x``: ``[N,H,W,C]`` bf16, ``w``: ``[Cout,KH,KW,C]``.
 
-    Returns ``[N,H,W,Cout]``. Zero padding is produced by TMA out-of-bounds fill.
+    Returns ``[N,Ho,Wo,Cout]``. Zero padding is produced by TMA out-of-bounds fill; a stride-2 convolution walks
+    the input with TMA element strides (same kernel, same pipeline).
     """
     n, h, wd, c = x.shape
     cout, kh, kw, c2 = w.shape
     assert c == c2
+    ho, wo = (h + 2 * padding - kh) // stride + 1, (wd + 2 * padding - kw) // stride + 1
     if not x.is_cuda:
         xx = x.to(torch.bfloat16).float().permute(0, 3, 1, 2)
         ww = w.to(torch.bfloat16).float().permute(0, 3, 1, 2)
-        y = alpha * F.conv2d(xx, ww, padding=padding)
+        y = alpha * F.conv2d(xx, ww, padding=padding, stride=stride)
         if col_part is not None:
             _col_part_reference(y.permute(0, 2, 3, 1).reshape(-1, cout), col_part)
         if bias is not None:
@@ -131,15 +133,27 @@ def conv_nhwc(x: torch.Tensor, w: torch.Tensor, *, padding: int = 1, out_dtype: 
         return y.to(out_dtype).contiguous()
     lib = native.load()
     x, w = _bf(x).contiguous(), _bf(w).contiguous()
-    out = torch.empty((n, h, wd, cout), dtype=out_dtype, device=x.device)
+    out = torch.empty((n, ho, wo, cout), dtype=out_dtype, device=x.device)
     if residual is not None:
         assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.shape == out.shape
     rc = lib.flpr_conv_nhwc_bf16(native.ptr(x), native.ptr(w), native.ptr(out), n, h, wd, c, cout, kh, kw, padding,
                                  padding, int(out_dtype == torch.bfloat16), float(alpha), native.ptr(bias), int(relu),
-                                 native.ptr(residual), int(bn), native.ptr(col_part), native.stream(x.device))
+                                 native.ptr(residual), int(bn), native.ptr(col_part), int(stride),
+                                 native.stream(x.device))
     native.check(rc, "flpr_conv_nhwc_bf16")
     native.count_launch()
     return out
+
+
+def conv_supported(h: int, w: int, c: int, k: int, stride: int = 1, padding: Optional[int] = None) -> bool:
+    """Shape constraints of the implicit-GEMM kernel (C multiple of 64; output rows tile into 128-pixel M tiles)."""
+    padding = k // 2 if padding is None else padding
+    ho, wo = (h + 2 * padding - k) // stride + 1, (w + 2 * padding - k) // stride + 1
+    if c % 64 or stride not in (1, 2) or wo < 1 or wo > 128 or 128 % wo:
+        return False
+    if ho * wo <= 128:
+        return 128 % (ho * wo) == 0
+    return ho % (128 // wo) == 0
 
 
 def conv_dgrad_nhwc(dy: torch.Tensor, w: torch.Tensor, *, padding: int = 1,

@@ -138,3 +138,36 @@ def test_experiment_with_concurrent_client_streams(tmp_path, method):
             for vals in tasks.values():
                 for k, v in vals.items():
                     assert v == v and 0.0 <= v <= 1e4, (k, v)
+
+
+@pytest.mark.parametrize("name,size", [("resnet50", (256, 128)), ("resnet18", (128, 64))])
+def test_native_trunk_matches_library_trunk(name, size):
+    """Frozen trunk on the tcgen05 implicit-GEMM kernels (incl. the stride-2 convolutions) vs the cuDNN path."""
+    from flpr_b200.models import resnet as R
+    from flpr_b200.models.frozen import FoldedTrunk
+    from flpr_b200.ops import native
+    torch.manual_seed(3)
+    net = getattr(R, name)(num_classes=10, last_stride=1, neck="bnneck").cuda().eval()
+    net.configure_split(["base.layer4", "classifier"])
+    for m in net.modules():                                   # non-trivial folded BN
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.1)
+    ft = FoldedTrunk(net, torch.bfloat16, use_graphs=False)
+    x = torch.randn(16, 3, *size, device="cuda")
+    assert ft._native_ok(tuple(x.shape))
+    before = native.launches()
+    y_native = ft(x)
+    assert native.launches() - before >= 10, "the native trunk path did not run"
+    ft.native = False
+    ft._native_cache.clear()
+    y_lib = ft(x)
+    assert y_native.shape == y_lib.shape
+    err = (y_native.float() - y_lib.float()).abs().max().item()
+    assert err <= 5e-2 * y_lib.float().abs().max().item() + 1e-3, err
+    with torch.no_grad():
+        ref = net.forward_trunk(x)
+    err = (y_native.float() - ref.float()).abs().max().item()
+    assert err <= 8e-2 * ref.abs().max().item() + 1e-3, err

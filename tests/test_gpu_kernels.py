@@ -460,3 +460,40 @@ def test_bulk_device_loader_covers_split():
     first = next(iter(ld.iterate(64, ordered=True)))[0]
     assert torch.allclose(first, ref, atol=1e-5)
     assert ld.h2d_bytes >= 2 * ds.images.numel()
+
+
+@pytest.mark.parametrize("n,h,w,c,cout,ks", [(4, 64, 32, 128, 128, 3), (3, 32, 16, 256, 256, 3), (4, 64, 32, 256, 512, 1),
+                                             (2, 32, 16, 512, 1024, 1), (5, 16, 8, 64, 64, 3)])
+def test_strided_conv_via_tma_element_strides(n, h, w, c, cout, ks):
+    """Stride-2 convolution = the same implicit-GEMM pipeline over a tensor map with element strides {1,2,2,1}."""
+    from flpr_b200.ops.gemm import conv_nhwc
+    torch.manual_seed(41)
+    x = torch.randn(n, h, w, c, device="cuda").bfloat16()
+    wt = (torch.randn(cout, ks, ks, c, device="cuda") / math.sqrt(c * ks * ks)).bfloat16()
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), padding=ks // 2,
+                                     stride=2).permute(0, 2, 3, 1)
+    out = conv_nhwc(x, wt, padding=ks // 2, stride=2, out_dtype=torch.float32)
+    assert out.shape == ref.shape
+    _close(out, ref, rtol=1e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("m,n,k", [(8192, 256, 64), (4096, 64, 256), (1000, 2048, 512)])
+def test_lean_epilogue_bias_residual_relu(m, n, k):
+    """Inference epilogue of the folded trunk: bf16( relu( A B^T + bias[col] + residual ) ) on the lean path."""
+    from flpr_b200.ops.gemm import gemm, conv_nhwc
+    torch.manual_seed(42)
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    b = (torch.randn(n, k, device="cuda") / math.sqrt(k)).bfloat16()
+    bias = torch.randn(n, device="cuda")
+    res = torch.randn(m, n, device="cuda").bfloat16()
+    ref = a.float() @ b.float().t() + bias[None]
+    _close(gemm(a, b, bias_n=bias, relu=True), torch.relu(ref))
+    _close(gemm(a, b, bias_n=bias, relu=True, residual=res), torch.relu(ref + res.float()))
+    _close(gemm(a, b, bias_n=bias), ref)
+    x = torch.randn(8, 16, 8, 128, device="cuda").bfloat16()
+    wt = (torch.randn(256, 3, 3, 128, device="cuda") / 34).bfloat16()
+    bias = torch.randn(256, device="cuda")
+    res = torch.randn(8, 16, 8, 256, device="cuda").bfloat16()
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2),
+                                     padding=1).permute(0, 2, 3, 1) + bias
+    _close(conv_nhwc(x, wt, padding=1, bias=bias, relu=True, residual=res), torch.relu(ref + res.float()))
