@@ -306,12 +306,14 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* x, f
   }
 }
 
-// Fold per-block partials part[nparts][2][C] -> two per-channel sums. blockDim = (32 channels, 8 part-lanes).
+// Fold per-block partials part[nparts][2][C] -> two per-channel sums. blockDim = (32 channels, FOLD_LANES part-lanes).
+constexpr int FOLD_LANES = 32;
 __device__ __forceinline__ void fold_partials(const float* part, int nparts, int C, int c, float& s0, float& s1,
-                                              float (*sh)[8][32]) {
+                                              float (*sh)[FOLD_LANES][33]) {
   float a = 0.f, b = 0.f;
   if (c < C) {
-    for (int i = threadIdx.y; i < nparts; i += 8) {
+#pragma unroll 4
+    for (int i = threadIdx.y; i < nparts; i += FOLD_LANES) {
       a += part[(size_t)i * 2 * C + c];
       b += part[(size_t)i * 2 * C + C + c];
     }
@@ -322,16 +324,16 @@ __device__ __forceinline__ void fold_partials(const float* part, int nparts, int
   s0 = 0.f; s1 = 0.f;
   if (threadIdx.y == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s0 += sh[0][j][threadIdx.x]; s1 += sh[1][j][threadIdx.x]; }
+    for (int j = 0; j < FOLD_LANES; ++j) { s0 += sh[0][j][threadIdx.x]; s1 += sh[1][j][threadIdx.x]; }
   }
 }
 
 // finalize: fold partials, mean/rstd, running stats (momentum, unbiased var), scale/shift for the apply pass
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* part, int nparts, const float* gamma,
+__global__ void __launch_bounds__(32 * FOLD_LANES) bn_finalize_kernel(const float* part, int nparts, const float* gamma,
                                                           const float* beta, float* mean, float* rstd, float* scale,
                                                           float* shift, float* running_mean, float* running_var, int M,
                                                           int C, float eps, float momentum) {
-  __shared__ float sh[2][8][32];
+  __shared__ float sh[2][FOLD_LANES][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float sm, sq;
   fold_partials(part, nparts, C, c, sm, sq, sh);
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(256) bn_affine_rows_kernel(const __nv_bfloat16
   const uint4* xp = reinterpret_cast<const uint4*>(x);
   const uint4* rp = reinterpret_cast<const uint4*>(residual);
   uint4* yp = reinterpret_cast<uint4*>(y);
-#pragma unroll 2
+#pragma unroll 4
   for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
     const size_t idx = (size_t)r * c8n + c8;
     uint4 u = xp[idx];
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
     const uint4* yp = reinterpret_cast<const uint4*>(y);
     const uint4* xp = reinterpret_cast<const uint4*>(x);
     uint4* dr = reinterpret_cast<uint4*>(dres);
-#pragma unroll 2
+#pragma unroll 4
     for (int r = r0 + ty; r < r1; r += blockDim.y) {
       const size_t idx = (size_t)r * c8n + c8;
       uint4 du = dyp[idx];
@@ -497,11 +499,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
 
 // dgamma / dbeta totals and the coefficients of  dx = ca*dy_eff + cb*x + cc  (cc folded below):
 //   ca = gamma*rstd, cb = -ca*rstd*dgamma/M, cc = -ca*dbeta/M - cb*mean
-__global__ void __launch_bounds__(256) bn_fold_partials_kernel(const float* part, int nparts, const float* gamma,
+__global__ void __launch_bounds__(32 * FOLD_LANES) bn_fold_partials_kernel(const float* part, int nparts, const float* gamma,
                                                                const float* mean, const float* rstd, float* dgamma,
                                                                float* dbeta, float* coef /* [3][C] */, int M, int C,
                                                                int accumulate) {
-  __shared__ float sh[2][8][32];
+  __shared__ float sh[2][FOLD_LANES][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float g, b;
   fold_partials(part, nparts, C, c, g, b, sh);
@@ -534,7 +536,7 @@ __global__ void __launch_bounds__(256) bn_bwd_rows_kernel(const __nv_bfloat16* d
   const uint4* yp = reinterpret_cast<const uint4*>(y);
   const uint4* xp = reinterpret_cast<const uint4*>(x);
   uint4* dxp = reinterpret_cast<uint4*>(dx);
-#pragma unroll 2
+#pragma unroll 4
   for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
     const size_t idx = (size_t)r * c8n + c8;
     uint4 du = dyp[idx];
@@ -850,7 +852,7 @@ static void bn_launch_geometry(int M, int C, dim3& grid, dim3& block, int& rpb) 
   int by = 1;                                         // row-lanes per block (power of two, <= 16)
   while (by * 2 * bx <= 256 && by < 16) by *= 2;
   const int gx = (c8n + bx - 1) / bx;
-  int gy = (148 * 2) / gx;
+  int gy = (148 * 4) / gx;
   if (gy < 1) gy = 1;
   rpb = (M + gy - 1) / gy;
   if (rpb < by * 4) rpb = by * 4;
@@ -877,11 +879,11 @@ int flpr_bn_fwd(const void* x, const float* gamma, const float* beta, const void
   dim3 grid, block; int rpb;
   bn_launch_geometry(M, C, grid, block, rpb);
   if (pre_part != nullptr && pre_nparts > 0) {
-    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(pre_part, pre_nparts, gamma, beta, mean, rstd, scale,
+    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, FOLD_LANES), 0, st>>>(pre_part, pre_nparts, gamma, beta, mean, rstd, scale,
                                                               shift, running_mean, running_var, M, C, eps, momentum);
   } else {
     bn_stats_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), part, M, C, rpb);
-    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(part, (int)grid.y, gamma, beta, mean, rstd, scale,
+    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, FOLD_LANES), 0, st>>>(part, (int)grid.y, gamma, beta, mean, rstd, scale,
                                                               shift, running_mean, running_var, M, C, eps, momentum);
   }
   bn_affine_rows_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), scale, shift,
@@ -917,7 +919,7 @@ int flpr_bn_bwd(const void* dy, const void* y, const void* x, const float* mean,
       reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, part, reinterpret_cast<__nv_bfloat16*>(dres), M, C, rpb,
       relu);
   float* coef = part + (size_t)grid.y * 2 * C;
-  bn_fold_partials_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(part, (int)grid.y, gamma, mean, rstd, dgamma, dbeta,
+  bn_fold_partials_kernel<<<(C + 31) / 32, dim3(32, FOLD_LANES), 0, st>>>(part, (int)grid.y, gamma, mean, rstd, dgamma, dbeta,
                                                                  coef, M, C, accumulate);
   // when the masked dy was materialised in dres, read it back (no second ReLU-mask pass over y)
   const __nv_bfloat16* dy_in = dres ? reinterpret_cast<const __nv_bfloat16*>(dres)

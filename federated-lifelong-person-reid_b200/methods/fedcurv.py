@@ -19,6 +19,7 @@ from .penalty import PenaltyModel
 
 
 class Model(PenaltyModel):
+    resume_attrs = ("F", "p_old", "Q", "R", "const", "other_f", "other_fp", "other_const", "have_moments")
     importance_mode = "fisher"
     skip_current_task = False
 

@@ -14,6 +14,7 @@ from .fedbase import FedClient, FedServer
 
 
 class Model(ModelModule):
+    resume_attrs = ("p_old", "has_old")
     def __init__(self, net, lambda_l2: float = 1e-2, **kwargs):
         super().__init__(net, **kwargs)
         self.lambda_l2 = float(lambda_l2)

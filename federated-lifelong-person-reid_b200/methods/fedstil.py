@@ -62,6 +62,22 @@ class Model(ModelModule):
     def upload_filter(self, name: str) -> bool:
         return name in self._theta_params
 
+    # ---- resume manifest ---------------------------------------------------------------------------------------------
+    def resume_extra(self) -> Dict[str, Any]:
+        return {"G": self.G.detach().clone() if self.G is not None else None, "ids": sorted(self.ids),
+                "ex_gens": [{"pids": g["pids"], "bank": g["bank"], "cls": g["cls"], "k": int(g["k"])}
+                            for g in self.ex_gens]}
+
+    def load_resume_extra(self, extra: Dict[str, Any]) -> None:
+        if extra.get("G") is not None and self.G is not None:
+            self.G.copy_(extra["G"].to(self.G.device))
+        self.ids = set(int(i) for i in extra.get("ids", []))
+        self.ex_gens = []
+        for g in extra.get("ex_gens", []):
+            pids = g["pids"].to(self.device)
+            self.ex_gens.append({"pids": pids, "pid_list": [int(p) for p in pids.tolist()], "k": int(g["k"]),
+                                 "bank": g["bank"].to(self.device), "cls": g["cls"].to(self.device)})
+
     def materialize(self, device, compute_dtype="bf16", fine_tuning=None):
         super().materialize(device, compute_dtype, fine_tuning)
         self.G = self.arena.master[:self.theta_numel].clone()       # global_weight (frozen between dispatches)
@@ -409,8 +425,10 @@ class Operator(OperatorModule):
         return st
 
     def invoke_train(self, model: Model, dataloader, **kwargs) -> Dict:
+        from ..utils.trace import nvtx_range
         device = model.device
-        pset = self.generate_prototypes(model, dataloader)
+        with nvtx_range("fedstil/prototype_pass"):
+            pset = self.generate_prototypes(model, dataloader)
         protos, pids = pset["protos"], pset["pids"]
         n = protos.shape[0]
         bs = dataloader.batch_size
@@ -460,6 +478,14 @@ class Client(ClientModule):
         comm.alloc_rank_buffer("glob", n)
         if token_numel:
             comm.alloc_client_buffer("token", (token_numel + 3) // 4 * 4)
+
+    def resume_extra(self) -> Dict[str, Any]:
+        return {"current_task": self.current_task, "task_token": self.task_token}
+
+    def load_resume_extra(self, extra: Dict[str, Any]) -> None:
+        self.current_task = extra.get("current_task")
+        tok = extra.get("task_token")
+        self.task_token = tok.to(self.model.device) if tok is not None else None
 
     def _named_theta(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
         a = self.model.arena
@@ -519,10 +545,12 @@ class Client(ClientModule):
         self.train_cnt += output["data_count"]                 # never reset
 
     def after_train(self, task_name, tr_loader, val_loader, output) -> None:
+        from ..utils.trace import nvtx_range
         self.model.reduce_examplars()
         ps = output.get("proto_set")
         if ps is not None:
-            self.model.build_examplars(ps["protos"], ps["pids"], ps["cids"], tr_loader.dataset.person_ids)
+            with nvtx_range("fedstil/herding"):
+                self.model.build_examplars(ps["protos"], ps["pids"], ps["cids"], tr_loader.dataset.person_ids)
             output.pop("proto_set", None)
         if self._task_tokens:
             self.task_token = torch.stack(self._task_tokens).mean(0)
@@ -548,6 +576,13 @@ class Server(ServerModule):
 
     def save_model(self, model_name: str) -> None:
         self.save_state(model_name, self.model.model_state(copy=False), True)
+
+    def resume_extra(self) -> Dict[str, Any]:
+        return {"token_memory": {k: list(v) for k, v in self.token_memory.items()}}
+
+    def load_resume_extra(self, extra: Dict[str, Any]) -> None:
+        dev = self.model.device
+        self.token_memory = {k: [t.to(dev) for t in v] for k, v in (extra.get("token_memory") or {}).items()}
 
     # ---- uploads -----------------------------------------------------------------------------------------------------------
     def set_client_incremental_state(self, client_name: str, client_state: Optional[Dict]) -> None:

@@ -21,6 +21,7 @@ from ..runtime.modules import ModelModule
 
 
 class PenaltyModel(ModelModule):
+    resume_attrs = ("F", "p_old", "Q", "R", "const")
     importance_mode = "fisher"          # "fisher": g^2, "mas": |g|
     skip_current_task = False           # EWC skips the most recent remembered loader (ewc.py:62-65)
     lambda_key = "lambda_penalty"

@@ -29,6 +29,7 @@ from ..parallel.comm import FedComm
 from ..utils.logger import Logger
 from ..utils.misc import DeviceTimer, clear_cache, same_seeds
 from .builder import parser_clients, parser_server
+from . import resume
 from .checkpoint import CheckpointStore
 from .explog import ExperimentLog
 
@@ -204,13 +205,22 @@ class ExperimentStage:
         store, comm, server, clients, names = self.build(exp_config)
         timer = DeviceTimer(self.device)
         try:
-            if exp_config["engine_opts"].get("val_at_round0", True):
+            if exp_config["engine_opts"].get("val_at_round0", True) and not (
+                    exp_config["engine_opts"].get("resume") and resume.available(store, self.rank)):
                 for client in clients:                                  # initial validation (experiment.py:163-173)
                     self._process_val(client, log, 0, self.container)
             comm_rounds = int(exp_config["exp_opts"]["comm_rounds"])
-            for curr_round in range(1, comm_rounds + 1):
+            eng = exp_config["engine_opts"]
+            first_round = 1
+            if eng.get("resume") and resume.available(store, self.rank):
+                first_round = resume.load(self, store, server, clients, comm) + 1
+                self.logger.info(f"Resumed from the manifest of round {first_round - 1}.")
+            interval = int(eng.get("resume_interval", 0) or 0)
+            for curr_round in range(first_round, comm_rounds + 1):
                 self.logger.info(f"Start communication round: {curr_round:0>3d}/{comm_rounds:0>3d}")
                 self._process_one_round(curr_round, server, clients, names, exp_config, log, timer, comm)
+                if interval and curr_round % interval == 0:
+                    resume.save(self, store, curr_round, server, clients, comm)
             self._gather_logs(log)
         finally:
             store.flush()

@@ -111,6 +111,28 @@ class ModelModule(nn.Module):
     def update_model(self, params_state: Dict[str, torch.Tensor]) -> None:
         self.load_full_state(params_state)
 
+    # ---- resume manifest (runtime/resume.py): method-specific continual-learning state -----------------------------
+    resume_attrs: Tuple[str, ...] = ()       # names of tensor / scalar attributes that a continued run needs
+
+    def resume_extra(self) -> Dict[str, Any]:
+        out = {}
+        for name in self.resume_attrs:
+            v = getattr(self, name, None)
+            out[name] = v.detach().clone() if isinstance(v, torch.Tensor) else v
+        return out
+
+    def load_resume_extra(self, extra: Dict[str, Any]) -> None:
+        for name in self.resume_attrs:
+            if name not in extra:
+                continue
+            v, cur = extra[name], getattr(self, name, None)
+            if isinstance(v, torch.Tensor) and isinstance(cur, torch.Tensor) and cur.shape == v.shape:
+                cur.copy_(v.to(cur.device))
+            elif isinstance(v, torch.Tensor):
+                setattr(self, name, v.to(self.device))
+            else:
+                setattr(self, name, v)
+
 
 class OperatorModule:
     """Holds criterion list / optimizer / scheduler and the train / predict / valid / inference loops
@@ -309,8 +331,10 @@ class ClientModule(_Actor):
         self.before_train(task_name, tr_loader, val_loader)
         output: Dict = {}
         perf_loss, perf_acc, sustained = 1e8, 0, 0
+        from ..utils.trace import nvtx_range
         for epoch in range(1, epochs + 1):
-            output = self.train_one_epoch(task_name, tr_loader, val_loader)
+            with nvtx_range(f"{self.client_name}/epoch{epoch}"):
+                output = self.train_one_epoch(task_name, tr_loader, val_loader)
             accuracy, loss, data_count = output["accuracy"], output["loss"], output["data_count"]
             sustained += 1
             if loss <= perf_loss and accuracy >= perf_acc:
@@ -321,7 +345,8 @@ class ClientModule(_Actor):
             self.logger.info_train(task_name, self.model.device, data_count, perf_acc, perf_loss, epoch, epochs)
         self.after_train(task_name, tr_loader, val_loader, output)
         self.operator.optimizer.reset_state()
-        self.save_model(self.ckpt_name(task_name))
+        with nvtx_range(f"{self.client_name}/checkpoint"):
+            self.save_model(self.ckpt_name(task_name))
         return output
 
     def _features(self, loader) -> Dict:

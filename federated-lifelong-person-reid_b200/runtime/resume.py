@@ -1,0 +1,132 @@
+"""Resume manifest (the reference cannot resume - no round counter, RNG, task-pipeline position,
+server registry or token memory is restorable; a rerun starts at round 1 on stale model files).
+
+``save(stage, ...)`` snapshots, per rank, everything a continued run needs beyond the reference-layout checkpoints:
+
+    {ckpt_root}/{exp}/_resume/rank{r}.ckpt
+        round, python / torch / per-model CUDA generator states,
+        server : registry (``clients`` keys), upload bookkeeping, method extras (FedSTIL token memory, ...)
+        clients: counters, task-pipeline position, optimizer lr / scheduler epoch, full model state,
+                 method extras (FedSTIL global weight, exemplar generations, task tokens, ...)
+        comm   : this rank's slots of every symmetric client buffer (the *last uploads* that the stale-client
+                 aggregation of ``methods/fedavg.py:386-397`` keeps using) and the rank buffers
+
+It goes through the asynchronous :class:`CheckpointStore` like every other snapshot. ``load(stage, ...)`` restores it
+after ``ExperimentStage.build`` and returns the round to continue from. Method plug-ins extend the picture through
+``resume_extra() / load_resume_extra()`` on their ``Model`` / ``Client`` / ``Server`` classes.
+"""
+from __future__ import annotations
+
+import os
+import random
+from typing import Any, Dict, List, Optional
+
+import torch
+
+ACTOR = "_resume"
+
+
+def _cpu(obj: Any) -> Any:
+    if isinstance(obj, torch.Tensor):
+        return obj.detach().cpu()
+    if isinstance(obj, dict):
+        return {k: _cpu(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_cpu(v) for v in obj)
+    return obj
+
+
+def client_state(client) -> Dict:
+    m = client.model
+    op = client.operator
+    st = {"train_cnt": client.train_cnt, "test_cnt": client.test_cnt,
+          "pipeline": client.task_pipeline.state_dict() if getattr(client, "task_pipeline", None) is not None else None,
+          "model": m.full_state(),
+          "opt": {"lr": op.optimizer.lr, "step_count": op.optimizer.step_count} if op.optimizer is not None else None,
+          "sched": op.scheduler.state_dict() if op.scheduler is not None else None,
+          "rng": m.rng.get_state() if getattr(m, "rng", None) is not None else None,
+          "model_extra": m.resume_extra() if hasattr(m, "resume_extra") else {},
+          "client_extra": client.resume_extra() if hasattr(client, "resume_extra") else {}}
+    return st
+
+
+def load_client_state(client, st: Dict) -> None:
+    m = client.model
+    op = client.operator
+    client.train_cnt, client.test_cnt = int(st["train_cnt"]), int(st["test_cnt"])
+    if st.get("pipeline") is not None and getattr(client, "task_pipeline", None) is not None:
+        client.task_pipeline.load_state_dict(st["pipeline"])
+    m.load_full_state(st["model"])
+    if st.get("opt") is not None and op.optimizer is not None:
+        op.optimizer.lr, op.optimizer.step_count = float(st["opt"]["lr"]), int(st["opt"]["step_count"])
+        op.optimizer.sync_hyper()
+    if st.get("sched") is not None and op.scheduler is not None:
+        op.scheduler.load_state_dict(st["sched"])
+    if st.get("rng") is not None and getattr(m, "rng", None) is not None:
+        m.rng.set_state(st["rng"].cpu())
+    if hasattr(m, "load_resume_extra"):
+        m.load_resume_extra(st.get("model_extra") or {})
+    if hasattr(client, "load_resume_extra"):
+        client.load_resume_extra(st.get("client_extra") or {})
+
+
+def save(stage, store, curr_round: int, server, clients, comm) -> None:
+    state: Dict[str, Any] = {
+        "round": int(curr_round), "world": stage.world, "rank": stage.rank,
+        "py_random": random.getstate(), "torch_rng": torch.get_rng_state(),
+        "cuda_rng": torch.cuda.get_rng_state(stage.device) if stage.device.type == "cuda" else None,
+        "server": {"clients": list(server.clients.keys()),
+                   "uploaded": list(getattr(server, "uploaded", [])),
+                   "extra": server.resume_extra() if hasattr(server, "resume_extra") else {},
+                   "model": server.model.full_state()},
+        "clients": {c.client_name: client_state(c) for c in clients},
+        "comm": {},
+    }
+    if comm is not None:
+        bufs: Dict[str, Any] = {}
+        for name, b in comm.bufs.items():
+            if getattr(b, "per_client", False):
+                bufs[name] = {int(cid): comm.client_view(name, cid) for cid in comm.local_clients()}
+            else:
+                bufs[name] = comm.rank_view(name)
+        state["comm"] = bufs
+    store.save(ACTOR, f"rank{stage.rank}", state, True)
+
+
+def available(store, rank: int) -> bool:
+    return os.path.exists(store.path(ACTOR, f"rank{rank}"))
+
+
+def load(stage, store, server, clients, comm) -> int:
+    """Restore a snapshot written by :func:`save`; returns the last completed round."""
+    st = store.load(ACTOR, f"rank{stage.rank}")
+    if int(st.get("world", 1)) != stage.world:
+        raise RuntimeError(f"resume manifest was written with world_size={st.get('world')}, now {stage.world}")
+    random.setstate(st["py_random"])
+    torch.set_rng_state(st["torch_rng"])
+    if st.get("cuda_rng") is not None and stage.device.type == "cuda":
+        torch.cuda.set_rng_state(st["cuda_rng"], stage.device)
+    sv = st["server"]
+    for name in sv["clients"]:
+        if name not in server.clients:
+            server.clients[name] = {"resumed": True}
+    if hasattr(server, "uploaded"):
+        server.uploaded = list(sv["uploaded"])
+    server.model.load_full_state(sv["model"])
+    if hasattr(server, "load_resume_extra"):
+        server.load_resume_extra(sv.get("extra") or {})
+    by_name = {c.client_name: c for c in clients}
+    for name, cs in st["clients"].items():
+        if name in by_name:
+            load_client_state(by_name[name], cs)
+    if comm is not None:
+        for name, val in (st.get("comm") or {}).items():
+            if name not in comm.bufs:
+                continue
+            if isinstance(val, dict):
+                for cid, t in val.items():
+                    comm.client_view(name, int(cid)).copy_(t.to(comm.client_view(name, int(cid)).device))
+            else:
+                comm.rank_view(name).copy_(val.to(comm.rank_view(name).device))
+        comm.barrier()
+    return int(st["round"])

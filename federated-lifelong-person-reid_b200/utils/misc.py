@@ -66,9 +66,11 @@ class DeviceTimer:
     @contextmanager
     def __call__(self, name: str):
         if self.device.type == "cuda":
+            from .trace import nvtx_range
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            yield
+            with nvtx_range(f"flpr/{name}"):
+                yield
             e1.record()
             self._pending.append((name, e0, e1))
         else:
