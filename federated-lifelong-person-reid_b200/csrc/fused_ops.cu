@@ -771,6 +771,79 @@ __global__ void __launch_bounds__(256) herding_kernel(const float* feats, const 
   }
 }
 
+// ----------------------------------------------------------------------------- frozen-trunk stem helpers
+// Space-to-depth + zero padding of the stem input: x [B,H,W,3] bf16 (NHWC) -> y [B, H/2+3, W/2+3, 16] bf16 where
+// cell (i, j) holds the 2x2 pixel block ((i-2)*2 + bh, (j-2)*2 + bw), channel index (bh*2 + bw)*3 + c, channels
+// 12..15 and the border cells are zero. A 7x7 / stride-2 / pad-3 convolution on x is then a 4x4 / stride-1
+// convolution on y whose 4-cell windows are CONTIGUOUS 128-byte runs: the implicit-GEMM kernel loads them with one
+// TMA box per kernel row (tensor map with a 32-byte cell stride, i.e. overlapping 128-byte rows).
+__global__ void __launch_bounds__(256) s2d_pad_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int H, int W) {
+  const int H2 = H / 2 + 3, W2 = W / 2 + 3;
+  const size_t cells = (size_t)B * H2 * W2;
+  for (size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x; cell < cells;
+       cell += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(cell % W2);
+    const int i = (int)((cell / W2) % H2);
+    const int b = (int)(cell / ((size_t)W2 * H2));
+    __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) v[t] = __float2bfloat16(0.f);
+    const int ci = i - 2, cj = j - 2;
+    if (ci >= 0 && ci < H / 2 && cj >= 0 && cj < W / 2) {
+#pragma unroll
+      for (int bh = 0; bh < 2; ++bh)
+#pragma unroll
+        for (int bw = 0; bw < 2; ++bw) {
+          const __nv_bfloat16* src = x + (((size_t)b * H + (ci * 2 + bh)) * W + (cj * 2 + bw)) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v[(bh * 2 + bw) * 3 + c] = src[c];
+        }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(y + cell * 16);
+    dst[0] = reinterpret_cast<const uint4*>(v)[0];
+    dst[1] = reinterpret_cast<const uint4*>(v)[1];
+  }
+}
+
+// 3x3 / stride 2 / pad 1 max-pool over NHWC bf16, 8 channels (16 bytes) per thread.
+__global__ void __launch_bounds__(256) maxpool3x3s2_nhwc_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, int B,
+                                                                int H, int W, int C) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1, c8n = C / 8;
+  const size_t total = (size_t)B * Ho * Wo * c8n;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % c8n);
+    const int ow = (int)((t / c8n) % Wo);
+    const int oh = (int)((t / ((size_t)c8n * Wo)) % Ho);
+    const int b = (int)(t / ((size_t)c8n * Wo * Ho));
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -3.0e38f;
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int ih = oh * 2 - 1 + dh;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const int iw = ow * 2 - 1 + dw;
+        if (iw < 0 || iw >= W) continue;
+        const uint4 u = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + ih) * W + iw) * C + c8 * 8);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(h[k]);
+          m[2 * k] = fmaxf(m[2 * k], f.x);
+          m[2 * k + 1] = fmaxf(m[2 * k + 1], f.y);
+        }
+      }
+    }
+    uint4 o;
+    __nv_bfloat162* oh2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) oh2[k] = __floats2bfloat162_rn(m[2 * k], m[2 * k + 1]);
+    *reinterpret_cast<uint4*>(y + (((size_t)b * Ho + oh) * Wo + ow) * C + c8 * 8) = o;
+  }
+}
+
 static inline int grid_for(size_t n_items, int threads, int cap = 148 * 8) {
   size_t b = (n_items + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -991,6 +1064,26 @@ int flpr_herding(const float* feats, const long long* idx, const int* cnt, long 
     configured = true;
   }
   herding_kernel<<<P, 256, smem, st>>>(feats, idx, cnt, picks, nmax, D, m);
+  return (int)cudaGetLastError();
+}
+
+// x [B,H,W,3] bf16 -> y [B, H/2+3, W/2+3, 16] bf16 (space-to-depth cells, zero borders); H, W even.
+int flpr_s2d_pad(const void* x, void* y, int B, int H, int W, cudaStream_t st) {
+  bind_device_of(x);
+  if ((H & 1) || (W & 1)) return -2;
+  const size_t cells = (size_t)B * (H / 2 + 3) * (W / 2 + 3);
+  s2d_pad_kernel<<<grid_for(cells, 256, 148 * 16), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                reinterpret_cast<__nv_bfloat16*>(y), B, H, W);
+  return (int)cudaGetLastError();
+}
+
+// 3x3 / 2 / pad 1 max-pool, NHWC bf16, C multiple of 8.
+int flpr_maxpool3x3s2(const void* x, void* y, int B, int H, int W, int C, cudaStream_t st) {
+  bind_device_of(x);
+  if (C % 8) return -2;
+  const size_t total = (size_t)B * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * (C / 8);
+  maxpool3x3s2_nhwc_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C);
   return (int)cudaGetLastError();
 }
 

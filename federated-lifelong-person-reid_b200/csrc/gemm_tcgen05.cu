@@ -1064,7 +1064,10 @@ static int conv_tiling(int H, int W, int* TH, int* NB, int* tiles_per_img) {
 // col_part: see flpr_gemm_bf16 (fused batch-norm statistics of the conv output).
 int flpr_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int NIMG, int H, int W, int C, int Cout, int KH,
                         int KW, int pad_h, int pad_w, int out_bf16, float alpha, const float* bias_n, int relu,
-                        const void* residual, int bn_req, float* col_part, int stride, cudaStream_t stream) {
+                        const void* residual, int bn_req, float* col_part, int stride, long long x_stride_w,
+                        long long x_stride_h, long long x_stride_n, cudaStream_t stream) {
+  // x_stride_{w,h,n}: element strides of X (0 = dense NHWC). A W stride smaller than C makes the per-pixel "channel"
+  // vectors overlap: that is how the 7x7 stem convolution runs on 4-cell windows of a space-to-depth input.
   bind_device_of(X);
   if (C % 64) return set_err("conv: C must be a multiple of 64", -7);
   if (stride != 1 && stride != 2) return set_err("conv: stride must be 1 or 2", -13);
@@ -1078,7 +1081,9 @@ int flpr_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int NIMG, int 
   CUtensorMap ta, tb;
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NIMG};
-    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint64_t str[3] = {(uint64_t)(x_stride_w ? x_stride_w : C) * 2,
+                       (uint64_t)(x_stride_h ? x_stride_h : (long long)W * C) * 2,
+                       (uint64_t)(x_stride_n ? x_stride_n : (long long)H * W * C) * 2};
     uint32_t box[4] = {64, (uint32_t)(Wo * stride), (uint32_t)(TH * stride), (uint32_t)NB};
     if ((rc = get_map(&ta, X, 4, dims, str, box, (uint32_t)stride))) return rc;
     uint64_t d2[2] = {(uint64_t)K, (uint64_t)Cout};

@@ -15,6 +15,7 @@ The 7x7 stem convolution (3 input channels) and the max-pool run on cuDNN / ATen
 """
 from __future__ import annotations
 
+import os
 import threading
 from typing import Dict, List, Optional, Tuple
 
@@ -96,6 +97,13 @@ class FoldedTrunk:
     # ------------------------------------------------------------------ native (tcgen05) residual stages
     def _prepare_native(self) -> None:
         """OHWI bf16 weights + fp32 biases for the implicit-GEMM kernels."""
+        from ..ops.gemm import stem_weight_s2d
+        self._stem_w4 = self._stem_bias = None
+        for op in self.ops:
+            if op[0] == "conv_relu" and tuple(op[1].shape[1:]) == (3, 7, 7) and op[1].shape[0] % 32 == 0 \
+                    and tuple(op[3]) == (2, 2) and tuple(op[4]) == (3, 3):
+                self._stem_w4 = stem_weight_s2d(op[1].float()).to(self.dtype).contiguous()
+                self._stem_bias = op[2].float().contiguous()
         for op in self.ops:
             if op[0] != "unit":
                 continue
@@ -155,12 +163,23 @@ class FoldedTrunk:
         return gops.conv_nhwc(x, wt, padding=padding, stride=stride, bias=b, relu=relu, residual=residual)
 
     def _forward_native(self, x: torch.Tensor) -> torch.Tensor:
+        from ..ops import gemm as gops
+        native_stem = getattr(self, "native_stem", True) and os.environ.get("FLPR_NATIVE_STEM", "1") != "0" \
+            and gops.stem_supported(x.shape[2], x.shape[3]) \
+            and self._stem_w4 is not None
         for op in self.ops:
             if op[0] == "conv_relu":
-                x = self._conv(x, op[1], op[2], op[3], op[4], True)
+                if native_stem:
+                    # 7x7 / 2 stem as a 4x4 conv over space-to-depth cells on the tcgen05 kernel (NHWC in, NHWC out)
+                    x = gops.stem_conv(x.permute(0, 2, 3, 1).contiguous(), self._stem_w4, self._stem_bias, relu=True)
+                else:
+                    x = self._conv(x, op[1], op[2], op[3], op[4], True)
             elif op[0] == "maxpool":
-                x = F.max_pool2d(x, 3, 2, 1)
-                x = x.permute(0, 2, 3, 1).contiguous()                   # NHWC from here on (free for channels_last)
+                if native_stem:
+                    x = gops.maxpool3x3s2(x)
+                else:
+                    x = F.max_pool2d(x, 3, 2, 1)
+                    x = x.permute(0, 2, 3, 1).contiguous()               # NHWC from here on (free for channels_last)
             else:
                 d = op[1]
                 identity = x if "dsn" not in d else self._nconv(x, *d["dsn"], relu=False)

@@ -138,7 +138,7 @@ def conv_nhwc(x: torch.Tensor, w: torch.Tensor, *, padding: int = 1, out_dtype: 
         assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.shape == out.shape
     rc = lib.flpr_conv_nhwc_bf16(native.ptr(x), native.ptr(w), native.ptr(out), n, h, wd, c, cout, kh, kw, padding,
                                  padding, int(out_dtype == torch.bfloat16), float(alpha), native.ptr(bias), int(relu),
-                                 native.ptr(residual), int(bn), native.ptr(col_part), int(stride),
+                                 native.ptr(residual), int(bn), native.ptr(col_part), int(stride), 0, 0, 0,
                                  native.stream(x.device))
     native.check(rc, "flpr_conv_nhwc_bf16")
     native.count_launch()
@@ -309,3 +309,96 @@ def conv3x3(x: torch.Tensor, w_master: torch.Tensor, w_bf16: Optional[torch.Tens
     if grad_out is not None and not x.is_cuda:
         grad_out = None
     return _Conv3x3Fn.apply(_bf(x), w_master, w_bf16, grad_out, want_stats)
+
+
+# ------------------------------------------------------------------------------------------------- ResNet stem
+def stem_weight_s2d(w: torch.Tensor) -> torch.Tensor:
+    """7x7 / stride-2 stem weight ``[Cout,3,7,7]`` -> ``[Cout, 4, 64]``: the equivalent 4x4 / stride-1 convolution over
+    2x2 space-to-depth cells (16 channels per cell: 4 sub-pixels x 3 colours + 4 zeros), 4 cells = one 64-wide K block
+    per kernel row. Tap (a, b) of the cell grid covers pixel offsets ``2a + bh - 3`` (a in -2..1, bh in 0..1)."""
+    cout = w.shape[0]
+    out = w.new_zeros(cout, 4, 4, 16)
+    for a in range(4):                       # cell row offset a-2
+        for bh in range(2):
+            kh = 2 * (a - 2) + bh + 3
+            if not 0 <= kh <= 6:
+                continue
+            for b in range(4):
+                for bw in range(2):
+                    kw = 2 * (b - 2) + bw + 3
+                    if not 0 <= kw <= 6:
+                        continue
+                    ch = (bh * 2 + bw) * 3
+                    out[:, a, b, ch:ch + 3] = w[:, :, kh, kw]
+    return out.reshape(cout, 4, 64)
+
+
+def s2d_pad(x: torch.Tensor) -> torch.Tensor:
+    """``[B,H,W,3]`` bf16 -> ``[B, H/2+3, W/2+3, 16]`` bf16 (space-to-depth cells with zero borders)."""
+    b, h, w, c = x.shape
+    assert c == 3 and h % 2 == 0 and w % 2 == 0
+    if not x.is_cuda:
+        y = x.new_zeros(b, h // 2 + 3, w // 2 + 3, 16)
+        cells = x.view(b, h // 2, 2, w // 2, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(b, h // 2, w // 2, 12)
+        y[:, 2:2 + h // 2, 2:2 + w // 2, :12] = cells
+        return y
+    lib = native.load()
+    x = _bf(x).contiguous()
+    y = torch.empty(b, h // 2 + 3, w // 2 + 3, 16, dtype=torch.bfloat16, device=x.device)
+    native.check(lib.flpr_s2d_pad(native.ptr(x), native.ptr(y), b, h, w, native.stream(x.device)), "flpr_s2d_pad")
+    native.count_launch()
+    return y
+
+
+def stem_supported(h: int, w: int) -> bool:
+    if h % 2 or w % 2:
+        return False
+    ho, wo = h // 2, w // 2
+    if wo > 128 or 128 % wo:
+        return False
+    return (128 % (ho * wo) == 0) if ho * wo <= 128 else (ho % (128 // wo) == 0)
+
+
+def stem_conv(x: torch.Tensor, w4: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True) -> torch.Tensor:
+    """ResNet stem (7x7 / 2 / pad 3 convolution + folded-BN bias + ReLU) on the implicit-GEMM kernel.
+    ``x``: ``[B,H,W,3]`` bf16 NHWC, ``w4``: :func:`stem_weight_s2d` of the (folded) weight. Returns ``[B,H/2,W/2,Cout]``."""
+    b, h, w, _ = x.shape
+    cout = w4.shape[0]
+    y2 = s2d_pad(x)                                            # [B, H2, W2, 16]
+    h2, w2 = h // 2 + 3, w // 2 + 3
+    ho, wo = h // 2, w // 2
+    if not x.is_cuda:
+        win = y2.float().unfold(2, 4, 1)                       # [B, H2, wo, 16, 4] windows of 4 cells
+        win = win.permute(0, 1, 2, 4, 3).reshape(b, h2, wo, 64)
+        rows = win.unfold(1, 4, 1)                             # [B, ho, wo, 64, 4]
+        a = rows.permute(0, 1, 2, 4, 3).reshape(b * ho * wo, 256)
+        out = a @ w4.float().reshape(cout, 256).t()
+        if bias is not None:
+            out = out + bias.float()
+        if relu:
+            out = torch.relu(out)
+        return out.to(torch.bfloat16).view(b, ho, wo, cout)
+    lib = native.load()
+    w4 = _bf(w4).contiguous()
+    out = torch.empty(b, ho, wo, cout, dtype=torch.bfloat16, device=x.device)
+    # the input seen by the conv kernel: [B, H2, wo, 64] with a 16-element (one cell) W stride -> overlapping windows
+    rc = lib.flpr_conv_nhwc_bf16(native.ptr(y2), native.ptr(w4), native.ptr(out), b, h2, wo, 64, cout, 4, 1, 0, 0, 1,
+                                 1.0, native.ptr(bias), int(relu), None, 0, None, 1, 16, w2 * 16, h2 * w2 * 16,
+                                 native.stream(x.device))
+    native.check(rc, "flpr_conv_nhwc_bf16 (stem)")
+    native.count_launch()
+    return out
+
+
+def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
+    """3x3 / stride 2 / pad 1 max-pool over NHWC bf16."""
+    b, h, w, c = x.shape
+    if not x.is_cuda:
+        return F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).to(x.dtype).contiguous()
+    lib = native.load()
+    x = _bf(x).contiguous()
+    y = torch.empty(b, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c, dtype=torch.bfloat16, device=x.device)
+    native.check(lib.flpr_maxpool3x3s2(native.ptr(x), native.ptr(y), b, h, w, c, native.stream(x.device)),
+                 "flpr_maxpool3x3s2")
+    native.count_launch()
+    return y

@@ -37,7 +37,7 @@ def _declare(lib: C.CDLL) -> None:
     P, I, F, Z, L, D = c_void_p, c_int, c_float, c_size_t, c_ll, c_double
     sig = {
         "flpr_gemm_bf16": [P, P, P, I, I, I, L, L, L, I, I, I, I, F, P, P, I, P, I, I, P, P],
-        "flpr_conv_nhwc_bf16": [P, P, P, I, I, I, I, I, I, I, I, I, I, F, P, I, P, I, P, I, P],
+        "flpr_conv_nhwc_bf16": [P, P, P, I, I, I, I, I, I, I, I, I, I, F, P, I, P, I, P, I, L, L, L, P],
         "flpr_conv_dgrad_nhwc_bf16": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
         "flpr_conv_wgrad_nhwc_bf16": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
         "flpr_symm_alloc": [C.POINTER(P), Z],
@@ -67,6 +67,8 @@ def _declare(lib: C.CDLL) -> None:
         "flpr_rank_eval": [P, P, P, P, P, I, I, L, P],
         "flpr_augment_u8": [P, P, P, I, I, I, P, P, F, F, F, F, F, F, I, P],
         "flpr_herding": [P, P, P, P, I, I, I, I, P],
+        "flpr_s2d_pad": [P, P, I, I, I, P],
+        "flpr_maxpool3x3s2": [P, P, I, I, I, I, P],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)

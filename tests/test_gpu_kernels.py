@@ -497,3 +497,21 @@ def test_lean_epilogue_bias_residual_relu(m, n, k):
     ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2),
                                      padding=1).permute(0, 2, 3, 1) + bias
     _close(conv_nhwc(x, wt, padding=1, bias=bias, relu=True, residual=res), torch.relu(ref + res.float()))
+
+
+@pytest.mark.parametrize("b,h,w", [(16, 256, 128), (8, 128, 64), (3, 64, 32)])
+def test_native_stem_and_maxpool(b, h, w):
+    """7x7/2 stem as a 4x4 conv over space-to-depth cells (overlapping TMA windows) + NHWC max-pool."""
+    from flpr_b200.ops.gemm import stem_weight_s2d, stem_conv, maxpool3x3s2, s2d_pad
+    torch.manual_seed(51)
+    x = torch.randn(b, h, w, 3, device="cuda").bfloat16()
+    wt = (torch.randn(64, 3, 7, 7, device="cuda") / 12).bfloat16().float()
+    bias = torch.randn(64, device="cuda")
+    cells = s2d_pad(x)
+    assert torch.equal(cells.cpu(), s2d_pad(x.cpu()))
+    ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, stride=2, padding=3))
+    out = stem_conv(x, stem_weight_s2d(wt).bfloat16(), bias)
+    _close(out, ref.permute(0, 2, 3, 1))
+    pooled = maxpool3x3s2(out)
+    refp = torch.nn.functional.max_pool2d(out.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(pooled.float(), refp)
