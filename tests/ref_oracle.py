@@ -1,0 +1,78 @@
+"""Runs pieces of the UNMODIFIED reference (installed in baseline/_ref) as an oracle. Executed in a SUBPROCESS by
+tests/test_reference_parity.py because the reference's top-level package names (datasets, models, tools, ...) must
+not leak into the test process.   python tests/ref_oracle.py <case> <in.pt> <out.pt>"""
+import logging
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+sys.path.insert(0, REF)
+logging.disable(logging.CRITICAL)
+
+
+class _Log:
+    def info(self, *a, **k): pass
+    warn = warning = error = debug = info
+
+
+def main():
+    case, inp, outp = sys.argv[1:4]
+    d = torch.load(inp, weights_only=False)
+    if case == "evaluate":
+        import numpy as np
+        import tools.evaluate as E
+        raw_cmc, raw_map = E.evaluate(d["qf"], d["ql"], d["gf"], d["gl"], device="cpu")
+        # On the reference's pinned stack (torch 1.11 / numpy 1.2x) ``np.argwhere(tensor)`` yields an ``[R, 1]`` numpy
+        # array; on torch 2.x it yields a ``[1, R]`` tensor, so ``len(right_result_index)`` becomes 1 and the AP loop
+        # only scores the FIRST hit. The shim restores the pinned-stack behaviour (the intended trapezoid AP).
+        _aw = np.argwhere
+        E.np.argwhere = lambda a: _aw(a.numpy() if isinstance(a, torch.Tensor) else a)
+        cmc, mAP = E.evaluate(d["qf"], d["ql"], d["gf"], d["gl"], device="cpu")
+        E.np.argwhere = _aw
+        out = {"cmc": torch.as_tensor(cmc).float(), "mAP": float(mAP), "raw_cmc": torch.as_tensor(raw_cmc).float(),
+               "raw_mAP": float(raw_map)}
+    elif case == "distance":
+        from tools.distance import compute_cosine_distance, compute_euclidean_distance, compute_kl_distance
+        out = {"eu": compute_euclidean_distance(d["a"], d["b"]), "cos": compute_cosine_distance(d["a"], d["b"]),
+               "kl": compute_kl_distance(d["a"][:1], d["b"][:1])}
+    elif case == "losses":
+        from criterions.cross_entropy import CrossEntropyLabelSmooth
+        from criterions.triplet_loss import TripletLoss
+        score = d["score"].clone().requires_grad_(True)
+        ce = CrossEntropyLabelSmooth(num_classes=score.shape[1], epsilon=0.1)
+        l1 = ce(score=score, feature=None, target=d["target"])
+        l1.backward()
+        feat = d["feat"].clone().requires_grad_(True)
+        res = {"ce": l1.detach(), "ce_grad": score.grad}
+        for name, kw in (("tri_hard", dict(margin=0.3, hard_mining=True)), ("tri_soft", dict(margin=0, hard_mining=True)),
+                         ("tri_w", dict(margin=0.3, hard_mining=False, norm_feat=True))):
+            t = TripletLoss(**kw)
+            res[name] = t(score=None, feature=feat, target=d["target"]).detach()
+        out = res
+    elif case == "fedavg_calculate":
+        from methods.fedavg import Server
+        srv = Server.__new__(Server)
+        srv.clients = d["clients"]
+        srv.logger = _Log()
+        got = {}
+        srv.update_model = lambda merged: got.update(merged)
+        srv.calculate()
+        out = got
+    elif case == "fedstil_dispatch":
+        from methods.fedstil import Server
+        srv = Server.__new__(Server)
+        srv.clients = d["clients"]
+        srv.token_memory = d["token_memory"]
+        srv.distance_calculate_step, srv.distance_calculate_decay = d["step"], d["decay"]
+        srv.logger = _Log()
+        out = {name: srv.get_dispatch_incremental_state(name)["incremental_shared_params"] for name in d["receivers"]}
+    else:
+        raise SystemExit(f"unknown case {case}")
+    torch.save(out, outp)
+
+
+if __name__ == "__main__":
+    main()
