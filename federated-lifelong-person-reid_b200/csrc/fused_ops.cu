@@ -844,6 +844,167 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_nhwc_kernel(const __nv_bfloa
   }
 }
 
+// ----------------------------------------------------------------------------- Swin window attention (fused)
+// One block per (window, head): S = scale * Q K^T + bias (relative-position bias [+ shift mask]) -> softmax -> P V,
+// everything in shared memory / registers (N <= 64 tokens per window, head dim D <= 64; Swin: N = 49, D = 32).
+// Reference: models/swin_transformer.py:255-286 (QK^T, bias table gather, mask add, softmax, attn @ v as five
+// separate library calls materialising the [B*nW, heads, N, N] score tensor twice).
+// qkv: [BW, N, 3, H, D] (the qkv projection's output), bias: [nWb, H, N, N] fp32 (nWb = 1 or #windows per image;
+// window index = bw % nWb), out: [BW, N, H*D].
+template <typename T>
+__device__ __forceinline__ float attn_ld(const T* p) { return static_cast<float>(*p); }
+template <>
+__device__ __forceinline__ float attn_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T>
+__device__ __forceinline__ void attn_st(T* p, float v) { *p = static_cast<T>(v); }
+template <>
+__device__ __forceinline__ void attn_st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+constexpr int ATT_MAXN = 64;
+constexpr int ATT_MAXD = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(64) window_attn_fwd_kernel(const T* qkv, const float* bias, T* out, int N, int H,
+                                                             int D, int nWb, float scale) {
+  extern __shared__ float sm[];                 // K[N][D+1] | V[N][D+1] | S[N][N+1]
+  const int bw = blockIdx.x, h = blockIdx.y, i = threadIdx.x;
+  const int ld = D + 1;
+  float* Ks = sm;
+  float* Vs = sm + N * ld;
+  float* s = Vs + N * ld + (size_t)i * (N + 1);  // this thread's score row
+  const size_t row_stride = (size_t)3 * H * D;
+  const T* base = qkv + (size_t)bw * N * row_stride + (size_t)h * D;
+  for (int t = threadIdx.x; t < N * D; t += blockDim.x) {
+    const int j = t / D, d = t - j * D;
+    Ks[j * ld + d] = attn_ld(base + j * row_stride + (size_t)H * D + d);
+    Vs[j * ld + d] = attn_ld(base + j * row_stride + (size_t)2 * H * D + d);
+  }
+  __syncthreads();
+  if (i >= N) return;
+  float q[ATT_MAXD];
+#pragma unroll
+  for (int d = 0; d < ATT_MAXD; ++d) q[d] = d < D ? attn_ld(base + i * row_stride + d) * scale : 0.f;
+  const float* brow = bias + (((size_t)(bw % nWb) * H + h) * N + i) * N;
+  float mx = -3.0e38f;
+#pragma unroll 1
+  for (int j = 0; j < N; ++j) {
+    float a = brow[j];
+#pragma unroll
+    for (int d = 0; d < ATT_MAXD; ++d)
+      if (d < D) a = fmaf(q[d], Ks[j * ld + d], a);
+    s[j] = a;
+    mx = fmaxf(mx, a);
+  }
+  float sum = 0.f;
+#pragma unroll 1
+  for (int j = 0; j < N; ++j) {
+    s[j] = __expf(s[j] - mx);
+    sum += s[j];
+  }
+  const float inv = 1.f / sum;
+  float o[ATT_MAXD];
+#pragma unroll
+  for (int d = 0; d < ATT_MAXD; ++d) o[d] = 0.f;
+#pragma unroll 1
+  for (int j = 0; j < N; ++j) {
+    const float pj = s[j] * inv;
+#pragma unroll
+    for (int d = 0; d < ATT_MAXD; ++d)
+      if (d < D) o[d] = fmaf(pj, Vs[j * ld + d], o[d]);
+  }
+  T* orow = out + ((size_t)bw * N + i) * H * D + (size_t)h * D;
+#pragma unroll
+  for (int d = 0; d < ATT_MAXD; ++d)
+    if (d < D) attn_st(orow + d, o[d]);
+}
+
+// Backward: recompute P, then dV = P^T dO, dP = dO V^T, dS = P (.) (dP - rowsum(dP (.) P)), dQ = scale dS K,
+// dK = scale dS^T Q, dBias += dS (atomic over the images that share a window index).
+template <typename T>
+__global__ void __launch_bounds__(64) window_attn_bwd_kernel(const T* qkv, const float* bias, const T* dout, T* dqkv,
+                                                             float* dbias, int N, int H, int D, int nWb,
+                                                             float scale) {
+  extern __shared__ float sm[];                 // Q | K | V | dO : [N][D+1] each ; P | dS : [N][N+1] each
+  const int bw = blockIdx.x, h = blockIdx.y, i = threadIdx.x;
+  const int ld = D + 1, ln = N + 1;
+  float* Qs = sm;
+  float* Ks = Qs + N * ld;
+  float* Vs = Ks + N * ld;
+  float* Os = Vs + N * ld;
+  float* Ps = Os + N * ld;
+  float* Ss = Ps + N * ln;
+  const size_t row_stride = (size_t)3 * H * D;
+  const T* base = qkv + (size_t)bw * N * row_stride + (size_t)h * D;
+  const T* dob = dout + (size_t)bw * N * H * D + (size_t)h * D;
+  for (int t = threadIdx.x; t < N * D; t += blockDim.x) {
+    const int j = t / D, d = t - j * D;
+    Qs[j * ld + d] = attn_ld(base + j * row_stride + d);
+    Ks[j * ld + d] = attn_ld(base + j * row_stride + (size_t)H * D + d);
+    Vs[j * ld + d] = attn_ld(base + j * row_stride + (size_t)2 * H * D + d);
+    Os[j * ld + d] = attn_ld(dob + (size_t)j * H * D + d);
+  }
+  __syncthreads();
+  if (i < N) {
+    const float* brow = bias + (((size_t)(bw % nWb) * H + h) * N + i) * N;
+    float mx = -3.0e38f;
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) {
+      float a = brow[j];
+      for (int d = 0; d < D; ++d) a = fmaf(Qs[i * ld + d] * scale, Ks[j * ld + d], a);
+      Ps[i * ln + j] = a;
+      mx = fmaxf(mx, a);
+    }
+    float sum = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) {
+      const float e = __expf(Ps[i * ln + j] - mx);
+      Ps[i * ln + j] = e;
+      sum += e;
+    }
+    const float inv = 1.f / sum;
+    float delta = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) {
+      const float pj = Ps[i * ln + j] * inv;
+      float dp = 0.f;
+      for (int d = 0; d < D; ++d) dp = fmaf(Os[i * ld + d], Vs[j * ld + d], dp);
+      Ps[i * ln + j] = pj;
+      Ss[i * ln + j] = dp;
+      delta = fmaf(pj, dp, delta);
+    }
+    float* dbrow = dbias ? dbias + (((size_t)(bw % nWb) * H + h) * N + i) * N : nullptr;
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) {
+      const float ds = Ps[i * ln + j] * (Ss[i * ln + j] - delta);
+      Ss[i * ln + j] = ds;
+      if (dbrow) atomicAdd(dbrow + j, ds);
+    }
+    // dQ_i = scale * sum_j dS_ij K_j
+    T* dq = dqkv + ((size_t)bw * N + i) * row_stride + (size_t)h * D;
+    for (int d = 0; d < D; ++d) {
+      float a = 0.f;
+      for (int j = 0; j < N; ++j) a = fmaf(Ss[i * ln + j], Ks[j * ld + d], a);
+      attn_st(dq + d, a * scale);
+    }
+  }
+  __syncthreads();
+  if (i < N) {
+    // column pass (thread = key index j): dK_j = scale * sum_i dS_ij Q_i ; dV_j = sum_i P_ij dO_i
+    const int j = i;
+    T* dk = dqkv + ((size_t)bw * N + j) * row_stride + (size_t)H * D + (size_t)h * D;
+    T* dv = dk + (size_t)H * D;
+    for (int d = 0; d < D; ++d) {
+      float a = 0.f, b = 0.f;
+      for (int r = 0; r < N; ++r) {
+        a = fmaf(Ss[r * ln + j], Qs[r * ld + d], a);
+        b = fmaf(Ps[r * ln + j], Os[r * ld + d], b);
+      }
+      attn_st(dk + d, a * scale);
+      attn_st(dv + d, b);
+    }
+  }
+}
+
 static inline int grid_for(size_t n_items, int threads, int cap = 148 * 8) {
   size_t b = (n_items + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -1084,6 +1245,47 @@ int flpr_maxpool3x3s2(const void* x, void* y, int B, int H, int W, int C, cudaSt
   const size_t total = (size_t)B * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * (C / 8);
   maxpool3x3s2_nhwc_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C);
+  return (int)cudaGetLastError();
+}
+
+// Fused Swin window attention. qkv [BW,N,3,H,D], bias fp32 [nWb,H,N,N], out [BW,N,H*D]; bf16 != 0: bf16 tensors.
+int flpr_window_attn_fwd(const void* qkv, const float* bias, void* out, int BW, int N, int H, int D, int nWb,
+                         float scale, int bf16, cudaStream_t st) {
+  bind_device_of(qkv);
+  if (N > ATT_MAXN || D > ATT_MAXD || N < 1) return -2;
+  const size_t smem = ((size_t)2 * N * (D + 1) + (size_t)N * (N + 1)) * sizeof(float);
+  dim3 grid(BW, H);
+  if (bf16)
+    window_attn_fwd_kernel<__nv_bfloat16><<<grid, 64, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), bias,
+                                                                   reinterpret_cast<__nv_bfloat16*>(out), N, H, D, nWb,
+                                                                   scale);
+  else
+    window_attn_fwd_kernel<float><<<grid, 64, smem, st>>>(reinterpret_cast<const float*>(qkv), bias,
+                                                          reinterpret_cast<float*>(out), N, H, D, nWb, scale);
+  return (int)cudaGetLastError();
+}
+
+// dqkv [BW,N,3,H,D] is fully written; dbias (nullable, fp32 [nWb,H,N,N]) must be zeroed by the caller.
+int flpr_window_attn_bwd(const void* qkv, const float* bias, const void* dout, void* dqkv, float* dbias, int BW, int N,
+                         int H, int D, int nWb, float scale, int bf16, cudaStream_t st) {
+  bind_device_of(qkv);
+  if (N > ATT_MAXN || D > ATT_MAXD || N < 1) return -2;
+  const size_t smem = ((size_t)4 * N * (D + 1) + (size_t)2 * N * (N + 1)) * sizeof(float);
+  dim3 grid(BW, H);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(window_attn_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(window_attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    configured = true;
+  }
+  if (bf16)
+    window_attn_bwd_kernel<__nv_bfloat16><<<grid, 64, smem, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), bias, reinterpret_cast<const __nv_bfloat16*>(dout),
+        reinterpret_cast<__nv_bfloat16*>(dqkv), dbias, N, H, D, nWb, scale);
+  else
+    window_attn_bwd_kernel<float><<<grid, 64, smem, st>>>(reinterpret_cast<const float*>(qkv), bias,
+                                                          reinterpret_cast<const float*>(dout),
+                                                          reinterpret_cast<float*>(dqkv), dbias, N, H, D, nWb, scale);
   return (int)cudaGetLastError();
 }
 

@@ -100,18 +100,24 @@ class WindowAttention(nn.Module):
 
     def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         bw, n, c = x.shape
-        qkv = self.qkv(x).view(bw, n, 3, self.num_heads, c // self.num_heads).permute(2, 0, 3, 1, 4)
+        qkv5 = self.qkv(x).view(bw, n, 3, self.num_heads, c // self.num_heads)
+        drop = self.attn_drop if self.training else 0.0
+        if drop == 0.0 and getattr(self, "fused", True):
+            from ..ops.fused import window_attention, window_attention_supported
+            if window_attention_supported(qkv5):
+                # one fused kernel per (window, head): QK^T + bias (+ mask) -> softmax -> PV, scores never leave the SM
+                out = window_attention(qkv5, self.bias(mask), self.scale)
+                return self.proj_drop(self.proj(out))
+        qkv = qkv5.permute(2, 0, 3, 1, 4)
         q, k, v = qkv[0], qkv[1], qkv[2]
         bias = self.bias(mask).to(q.dtype)
         if mask is not None:
             nw = mask.shape[0]
             q, k, v = (t.view(bw // nw, nw, self.num_heads, n, -1) for t in (q, k, v))
-            out = F.scaled_dot_product_attention(q, k, v, attn_mask=bias.unsqueeze(0),
-                                                 dropout_p=self.attn_drop if self.training else 0.0, scale=self.scale)
+            out = F.scaled_dot_product_attention(q, k, v, attn_mask=bias.unsqueeze(0), dropout_p=drop, scale=self.scale)
             out = out.reshape(bw, self.num_heads, n, -1)
         else:
-            out = F.scaled_dot_product_attention(q, k, v, attn_mask=bias,
-                                                 dropout_p=self.attn_drop if self.training else 0.0, scale=self.scale)
+            out = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, dropout_p=drop, scale=self.scale)
         return self.proj_drop(self.proj(out.transpose(1, 2).reshape(bw, n, c)))
 
 

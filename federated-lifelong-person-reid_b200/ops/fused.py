@@ -303,3 +303,56 @@ def global_avg_pool_nhwc(x: torch.Tensor) -> torch.Tensor:
     if not x.is_cuda:
         return x.float().mean(1)
     return _GapFn.apply(x.contiguous())
+
+
+# --------------------------------------------------------------------------------------------- Swin window attention
+class _WindowAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, bias, scale):
+        bw, n, three, h, d = qkv.shape
+        lib = native.load()
+        qkv = qkv.contiguous()
+        bias = bias.float().contiguous()
+        out = torch.empty(bw, n, h * d, dtype=qkv.dtype, device=qkv.device)
+        rc = lib.flpr_window_attn_fwd(native.ptr(qkv), native.ptr(bias), native.ptr(out), bw, n, h, d, bias.shape[0],
+                                      float(scale), int(qkv.dtype == torch.bfloat16), native.stream(qkv.device))
+        native.check(rc, "flpr_window_attn_fwd")
+        native.count_launch()
+        ctx.save_for_backward(qkv, bias)
+        ctx.scale = float(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, bias = ctx.saved_tensors
+        bw, n, three, h, d = qkv.shape
+        lib = native.load()
+        dout = dout.contiguous().to(qkv.dtype)
+        dqkv = torch.empty_like(qkv)
+        dbias = torch.zeros_like(bias) if ctx.needs_input_grad[1] else None
+        rc = lib.flpr_window_attn_bwd(native.ptr(qkv), native.ptr(bias), native.ptr(dout), native.ptr(dqkv),
+                                      native.ptr(dbias), bw, n, h, d, bias.shape[0], ctx.scale,
+                                      int(qkv.dtype == torch.bfloat16), native.stream(qkv.device))
+        native.check(rc, "flpr_window_attn_bwd")
+        native.count_launch()
+        return dqkv, dbias, None
+
+
+def window_attention_supported(qkv: torch.Tensor) -> bool:
+    return qkv.is_cuda and qkv.dim() == 5 and qkv.shape[1] <= 64 and qkv.shape[4] <= 64 and \
+        qkv.dtype in (torch.bfloat16, torch.float32)
+
+
+def window_attention(qkv: torch.Tensor, bias: torch.Tensor, scale: float) -> torch.Tensor:
+    """Fused window attention (``models/swin_transformer.py:255-286``). ``qkv``: ``[BW, N, 3, heads, D]``, ``bias``:
+    ``[nW or 1, heads, N, N]`` (relative-position bias + shift mask; window index = ``bw % nW``). Returns
+    ``[BW, N, heads*D]``. CPU / unsupported shapes: plain tensor ops."""
+    if window_attention_supported(qkv):
+        return _WindowAttnFn.apply(qkv, bias, scale)
+    bw, n, _, h, d = qkv.shape
+    q, k, v = qkv.float().permute(2, 0, 3, 1, 4)                   # [BW, H, N, D]
+    nwb = bias.shape[0]
+    s = (q * scale) @ k.transpose(-1, -2)
+    s = s.view(bw // nwb, nwb, h, n, n) + bias.float().unsqueeze(0)
+    p = torch.softmax(s.view(bw, h, n, n), dim=-1)
+    return (p @ v).transpose(1, 2).reshape(bw, n, h * d).to(qkv.dtype)

@@ -67,6 +67,8 @@ def _declare(lib: C.CDLL) -> None:
         "flpr_rank_eval": [P, P, P, P, P, I, I, L, P],
         "flpr_augment_u8": [P, P, P, I, I, I, P, P, F, F, F, F, F, F, I, P],
         "flpr_herding": [P, P, P, P, I, I, I, I, P],
+        "flpr_window_attn_fwd": [P, P, P, I, I, I, I, I, F, I, P],
+        "flpr_window_attn_bwd": [P, P, P, P, P, I, I, I, I, I, F, I, P],
         "flpr_s2d_pad": [P, P, I, I, I, P],
         "flpr_maxpool3x3s2": [P, P, I, I, I, I, P],
     }

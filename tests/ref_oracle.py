@@ -69,6 +69,13 @@ def main():
         srv.distance_calculate_step, srv.distance_calculate_decay = d["step"], d["decay"]
         srv.logger = _Log()
         out = {name: srv.get_dispatch_incremental_state(name)["incremental_shared_params"] for name in d["receivers"]}
+    elif case == "swin_forward":
+        from models.swin_transformer import SwinTransformer
+        torch.manual_seed(d["seed"])
+        net = SwinTransformer(img_size=d["img"], embed_dim=d["dim"], depths=d["depths"], num_heads=d["heads"],
+                              window_size=d["ws"], num_classes=d["classes"], drop_path_rate=0.0).eval()
+        with torch.no_grad():
+            out = {"state": net.state_dict(), "feat": net.forward_features(d["x"]), "logits": net(d["x"])}
     else:
         raise SystemExit(f"unknown case {case}")
     torch.save(out, outp)

@@ -171,3 +171,35 @@ def test_native_trunk_matches_library_trunk(name, size):
         ref = net.forward_trunk(x)
     err = (y_native.float() - ref.float()).abs().max().item()
     assert err <= 8e-2 * ref.abs().max().item() + 1e-3, err
+
+
+def test_swin_fused_window_attention_in_model():
+    """Swin-T ReID on the GPU: fused window-attention kernel vs the SDPA path, forward and gradients of the last stage."""
+    from flpr_b200.models.swin import WindowAttention
+    from flpr_b200.models import nets
+    from flpr_b200.ops import native
+    torch.manual_seed(9)
+    net = nets["swin_transformer_tiny"](num_classes=50, neck="bnneck").cuda().train()
+    x = torch.randn(4, 3, 256, 128, device="cuda")
+    outs = []
+    for fused in (True, False):
+        for m in net.modules():
+            if isinstance(m, WindowAttention):
+                m.fused = fused
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        for m in net.modules():
+            if hasattr(m, "p") and m.__class__.__name__ == "DropPath":
+                m.p = 0.0
+        net.zero_grad()
+        before = native.launches()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            score, feat = net(x)
+        score.float().square().mean().backward()
+        if fused:
+            assert native.launches() - before >= 12, "fused attention kernels did not run"
+        g = net.base.layers[3].blocks[1].attn.qkv.weight.grad.detach().clone()
+        outs.append((feat.detach().float(), g.float()))
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=5e-2, atol=5e-2 * outs[1][0].abs().max().item())
+    cos = torch.nn.functional.cosine_similarity(outs[0][1].flatten(), outs[1][1].flatten(), dim=0).item()
+    assert cos > 0.98, cos

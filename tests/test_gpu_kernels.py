@@ -515,3 +515,28 @@ def test_native_stem_and_maxpool(b, h, w):
     pooled = maxpool3x3s2(out)
     refp = torch.nn.functional.max_pool2d(out.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
     assert torch.equal(pooled.float(), refp)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("bw,n,h,d,nwb", [(8, 49, 3, 32, 1), (16, 49, 6, 32, 4), (4, 16, 24, 32, 1), (6, 49, 12, 64, 2)])
+def test_fused_window_attention(dtype, bw, n, h, d, nwb):
+    """Swin window attention in one kernel (fwd + bwd) vs the tensor-op reference in fp32."""
+    from flpr_b200.ops.fused import window_attention
+    torch.manual_seed(61)
+    qkv = torch.randn(bw, n, 3, h, d, device="cuda").to(dtype).requires_grad_(True)
+    bias = (torch.randn(nwb, h, n, n, device="cuda") * 0.5).requires_grad_(True)
+    scale = d ** -0.5
+    out = window_attention(qkv, bias, scale)
+    g = torch.randn_like(out)
+    out.backward(g)
+    q32 = qkv.detach().float().requires_grad_(True)
+    b32 = bias.detach().clone().requires_grad_(True)
+    q, k, v = q32.permute(2, 0, 3, 1, 4)
+    s = (q * scale) @ k.transpose(-1, -2)
+    s = s.view(bw // nwb, nwb, h, n, n) + b32.unsqueeze(0)
+    ref = (torch.softmax(s.view(bw, h, n, n), -1) @ v).transpose(1, 2).reshape(bw, n, h * d)
+    ref.backward(g.float())
+    tol = 3e-2 if dtype == torch.bfloat16 else 1e-4
+    _close(out, ref, rtol=tol, atol=tol * ref.abs().max().item())
+    _close(qkv.grad, q32.grad, rtol=tol, atol=tol * q32.grad.abs().max().item())
+    _close(bias.grad, b32.grad, rtol=tol, atol=tol * b32.grad.abs().max().item() + 1e-6)

@@ -109,3 +109,24 @@ def test_fedstil_mix_matches_reference(tmp_path):
         for key in ("l.global_weight", "m.global_weight"):
             mixed = sum(W[r, order.index(c)] * theta[c][key] for c in names)
             assert torch.allclose(mixed, ref[name][key], atol=1e-5), (name, key)
+
+
+def test_swin_transformer_matches_reference(tmp_path):
+    """Same state dict (key-compatible) -> same features / logits as the reference Swin implementation, on both the
+    fused-attention code path (tensor-op form on CPU) and the SDPA path (shifted windows, masks, patch merging)."""
+    from flpr_b200.models.swin import SwinTransformer, WindowAttention
+    torch.manual_seed(5)
+    cfg = {"img": 56, "dim": 24, "depths": (2, 2), "heads": (2, 4), "ws": 7, "classes": 5, "seed": 7,
+           "x": torch.randn(2, 3, 56, 56)}
+    ref = oracle("swin_forward", cfg, tmp_path)
+    net = SwinTransformer(img_size=56, embed_dim=24, depths=(2, 2), num_heads=(2, 4), window_size=7, num_classes=5,
+                          drop_path_rate=0.0).eval()
+    missing, unexpected = net.load_state_dict(ref["state"], strict=False)
+    assert not [k for k in missing if "relative_position_index" not in k and "attn_mask" not in k], missing
+    for fused in (True, False):
+        for m in net.modules():
+            if isinstance(m, WindowAttention):
+                m.fused = fused
+        with torch.no_grad():
+            assert torch.allclose(net.forward_features(cfg["x"]), ref["feat"], atol=2e-5), fused
+            assert torch.allclose(net(cfg["x"]), ref["logits"], atol=2e-5), fused
