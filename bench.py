@@ -114,7 +114,9 @@ def build_config(a, impl: str, world: int):
         "exp_name": "bench-fedstil", "exp_method": "fedstil", "random_seed": 123,
         "exp_opts": {"comm_rounds": 10 ** 6, "val_interval": 10 ** 9, "online_clients": a.clients},
         "model_opts": {"name": a.model, "num_classes": 8000, "last_stride": 1, "neck": "bnneck", "atten_default": 0.9,
-                       "lambda_l1": 1e-3, "lambda_k": a.images, "fine_tuning": ["base.layer4", "classifier"]},
+                       "lambda_l1": 1e-3, "lambda_k": a.images,
+                       "fine_tuning": ["base.layers.3", "classifier"] if a.model.startswith("swin")
+                       else ["base.layer4", "classifier"]},
         "criterion_opts": {"name": "cross_entropy", "num_classes": 8000, "epsilon": 0.1},
         "optimizer_opts": {"name": "adam", "lr": 1e-3, "weight_decay": 1e-5},
         "scheduler_opts": {"name": "step_lr", "step_size": 5},

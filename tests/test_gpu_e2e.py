@@ -203,3 +203,23 @@ def test_swin_fused_window_attention_in_model():
     assert torch.allclose(outs[0][0], outs[1][0], rtol=5e-2, atol=5e-2 * outs[1][0].abs().max().item())
     cos = torch.nn.functional.cosine_similarity(outs[0][1].flatten(), outs[1][1].flatten(), dim=0).item()
     assert cos > 0.98, cos
+
+
+def test_fedstil_swin_experiment_on_gpu(tmp_path):
+    """BASELINE config 4 in miniature: FedSTIL with a Swin-T backbone (bf16, fused window attention) end to end."""
+    from flpr_b200.runtime.experiment import ExperimentStage
+    from flpr_b200.data.synthetic import synthetic_source_factory
+    common = tiny_common(str(tmp_path), device="cuda:0")
+    common["defaults"]["model_opts"] = {"name": "swin_transformer_tiny", "num_classes": 8000, "neck": "bnneck",
+                                        "fine_tuning": ["base.layers.3", "classifier"]}
+    common["defaults"]["task_opts"]["augment_opts"]["img_size"] = [64, 32]
+    common["defaults"]["task_opts"]["loader_opts"]["batch_size"] = 8
+    cfg = tiny_experiment(common, "fedstil")
+    with ExperimentStage(common, [cfg], source_factory=synthetic_source_factory(num_ids=4, train_per_id=4,
+                                                                                size=(64, 32))) as stage:
+        log = stage.run_experiment(cfg)
+    for client in log.records["data"].values():
+        for tasks in client.values():
+            for vals in tasks.values():
+                for k, v in vals.items():
+                    assert v == v and 0.0 <= v <= 1e4, (k, v)
