@@ -100,10 +100,17 @@ struct PersistLayout {
 
 // ------------------------------------------------------------------------------------------------- shared pieces
 // TMA loads of one K-block (BK = 64) of both operands into one ring stage.
-template <int BN, int A_MODE, int B_MODE>
+template <int BN, int A_MODE, int B_MODE, int CG = 1>
 __device__ __forceinline__ void load_kblock(const GemmParams& p, const CUtensorMap* tmA, const CUtensorMap* tmB,
                                             uint8_t* sa, uint8_t* sb, uint64_t* bar, int kb, int mt, int m0, int n0,
                                             int ztap) {
+  // CG == 2: CTA-pair kernel, `bar` is this CTA's copy of the full barrier; the bytes are credited to the leader's
+  auto tma_load_2d = [](void* d, const CUtensorMap* m, uint64_t* b, int c0, int c1) {
+    if constexpr (CG == 2) flpr::tma2_load_2d(d, m, b, c0, c1); else flpr::tma_load_2d(d, m, b, c0, c1);
+  };
+  auto tma_load_4d = [](void* d, const CUtensorMap* m, uint64_t* b, int c0, int c1, int c2, int c3) {
+    if constexpr (CG == 2) flpr::tma2_load_4d(d, m, b, c0, c1, c2, c3); else flpr::tma_load_4d(d, m, b, c0, c1, c2, c3);
+  };
   int tapA = 0;
   if constexpr (A_MODE == OP_KMAJOR) {
     tma_load_2d(sa, tmA, bar, kb * BK, m0);
@@ -155,9 +162,10 @@ __device__ __forceinline__ void load_kblock(const GemmParams& p, const CUtensorM
 }
 
 // The four UMMA_K = 16 steps of one K-block. Called by ONE thread.
-template <int BN, int A_MODE, int B_MODE>
+template <int BN, int A_MODE, int B_MODE, int CG = 1>
 __device__ __forceinline__ void mma_kblock(uint32_t sa, uint32_t tmem_acc, bool first_kb) {
-  constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MODE == OP_MNMAJOR, B_MODE != OP_KMAJOR);
+  // CG == 2: BN is the pair's N (each CTA holds BN/2 rows of B and 128 rows of A); the instruction covers M = 256
+  constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, A_MODE == OP_MNMAJOR, B_MODE != OP_KMAJOR);
   const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
   for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -170,7 +178,10 @@ __device__ __forceinline__ void mma_kblock(uint32_t sa, uint32_t tmem_acc, bool 
       db = make_smem_desc_sw128(sb + k * (UMMA_K * 128), 64 * 128, 1024);
     else
       db = make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
-    umma_f16(tmem_acc, da, db, idesc, (!first_kb || k != 0) ? 1u : 0u);
+    if constexpr (CG == 2)
+      umma2_f16(tmem_acc, da, db, idesc, (!first_kb || k != 0) ? 1u : 0u);
+    else
+      umma_f16(tmem_acc, da, db, idesc, (!first_kb || k != 0) ? 1u : 0u);
   }
 }
 
@@ -785,6 +796,183 @@ gemm_bf16_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmA, con
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------- CTA-pair kernel
+// cta_group::2: two CTAs of a cluster (one TPC) work on ONE 256 x 256 tile. Each CTA stages 128 rows of A (its half of
+// M) and 128 rows of B (its half of N) - 32 KB per K-block instead of 48 KB for a 128 x 256 single-CTA tile, i.e. a
+// third less L2 -> smem traffic per FLOP, and a 6-stage ring - the leader CTA issues tcgen05.mma.cta_group::2 over both
+// CTAs' shared memory, and each CTA's TMEM receives the accumulators of its 128 rows x 256 columns. Barriers:
+//   full[s]   (leader)  : 2 arrivals (each CTA's producer) + the TMA bytes of both CTAs
+//   empty[s]  (per CTA) : tcgen05.commit multicast from the leader's MMA thread
+//   tmem_full (per CTA) : tcgen05.commit multicast;   tmem_empty (leader): one arrival per epilogue warp of BOTH CTAs
+// Persistent over pairs; lean epilogue only (the host falls back to the single-CTA kernel otherwise).
+struct PairLayout {
+  static constexpr int BN = 256;                       // N of the pair tile
+  static constexpr int BNH = 128;                      // B rows staged per CTA
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + BNH * BK * 2;   // 32 KB
+  static constexpr int STAGES = 6;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STORE_BYTES = EPI_WARPS * 32 * 80;
+  static constexpr int BAR_OFFSET = STORE_OFFSET + STORE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int A_MODE, int B_MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairLayout::THREADS, 1)
+gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                              const GemmParams p) {
+  using L = PairLayout;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + L::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + L::STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + L::ACC_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + L::ACC_STAGES);
+
+  const int warp_id = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+
+  if (warp_id == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp_id == 1 && lane == 0) {
+    for (int s = 0; s < L::STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);                       // the two producers (leader: + expect_tx of both CTAs)
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < L::ACC_STAGES; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 2 * L::EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp_id == 2) {
+    tmem_alloc2(tmem_ptr_smem, L::TMEM_COLS);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // barrier inits of both CTAs visible before any remote access
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int tiles_m2 = (p.tiles_m + 1) >> 1;            // p.tiles_m counts 128-row tiles
+  const int per_z = tiles_m2 * p.tiles_n;
+  const int tiles_total = per_z * p.tiles_z;
+
+  if (warp_id == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < tiles_total; t += npairs) {
+        const int z = t / per_z;
+        const int r = t - z * per_z;
+        const int mt2 = r / p.tiles_n;
+        const int nt = r - mt2 * p.tiles_n;
+        const int mt = mt2 * 2 + (int)rank;
+        const int zsplit = (B_MODE == OP_CONV) ? (z % p.cSplits) : z;
+        const int ztap = (B_MODE == OP_CONV) ? (z / p.cSplits) : 0;
+        const int kb_begin = zsplit * p.kb_per_split;
+        const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          if (leader)
+            mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+          load_kblock<L::BNH, A_MODE, B_MODE, 2>(p, &tmA, &tmB, sa, sa + A_STAGE_BYTES, &full_bar[stage], kb, mt,
+                                                 mt * BM, nt * L::BN + (int)rank * L::BNH, ztap);
+          if (!leader) mbar_arrive_cluster(&full_bar[stage], 0);
+          if (++stage == L::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_id == 1 && leader) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = pair; t < tiles_total; t += npairs) {
+      const int z = t / per_z;
+      const int zsplit = (B_MODE == OP_CONV) ? (z % p.cSplits) : z;
+      const int kb_begin = zsplit * p.kb_per_split;
+      const int num_kb = min(kb_begin + p.kb_per_split, p.kb_total) - kb_begin;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + uint32_t(acc * L::BN);
+      for (int i = 0; i < num_kb; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) mma_kblock<L::BN, A_MODE, B_MODE, 2>(smem_u32(smem + stage * L::STAGE_BYTES), tmem_acc, i == 0);
+        __syncwarp();
+        if (elect_one()) umma2_commit_multicast(&empty_bar[stage]);
+        __syncwarp();
+        if (++stage == L::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (elect_one()) umma2_commit_multicast(&tmem_full_bar[acc]);
+      __syncwarp();
+      if (++acc == L::ACC_STAGES) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp_id >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows x 256 columns) =====================
+    const int q = warp_id & 3;
+    const int part = (warp_id - 4) >> 2;
+    constexpr int COLS_PER_WARP = L::BN / (L::EPI_WARPS / 4);
+    const uint32_t sbase = smem_u32(smem + L::STORE_OFFSET + (warp_id - 4) * (32 * 80));
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = pair; t < tiles_total; t += npairs) {
+      const int z = t / per_z;
+      const int r = t - z * per_z;
+      const int mt2 = r / p.tiles_n;
+      const int nt = r - mt2 * p.tiles_n;
+      const int mt = mt2 * 2 + (int)rank;
+      const int ztap = (B_MODE == OP_CONV) ? (z / p.cSplits) : 0;
+      const long long tap_off = (B_MODE == OP_CONV) ? (long long)ztap * p.tap_stride : 0;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      if (mt < p.tiles_m)
+        epilogue_tile_lean<true>(p, tmem_base + uint32_t(acc * L::BN), mt, mt * BM, nt * L::BN, part * COLS_PER_WARP,
+                                 (part + 1) * COLS_PER_WARP, tap_off, q, lane, sbase);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+      if (++acc == L::ACC_STAGES) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // nobody may still target the peer's smem / TMEM
+  if (warp_id == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, L::TMEM_COLS);
+  }
+}
+
 // =============================================================================== host side
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static std::mutex g_mu;
@@ -891,6 +1079,71 @@ static int sm_count() {
   return g_sms;
 }
 
+static int g_pair = -1;      // FLPR_GEMM_2CTA (default 0 until validated on every shape class): cta_group::2 kernel
+
+static bool use_pair() {
+  if (g_pair < 0) {
+    const char* e = getenv("FLPR_GEMM_2CTA");
+    g_pair = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return g_pair == 1 && use_persist();
+}
+
+// lean epilogue: plain row-major bf16 / fp32 / fp32-atomic output, every 32-column chunk full and 16-byte aligned
+static bool lean_ok(const GemmParams& p) {
+  const long long esz = p.out_bf16 ? 2 : 4;
+  const bool act = p.residual != nullptr || p.bias_n != nullptr || p.relu;
+  return !p.trans_out && p.bias_m == nullptr && (!act || (p.out_bf16 && !p.atomic_add)) &&
+         (reinterpret_cast<uintptr_t>(p.bias_n) % 16) == 0 && (reinterpret_cast<uintptr_t>(p.residual) % 16) == 0 &&
+         (p.N % 32) == 0 && ((p.ldo * esz) % 16) == 0 && ((p.tap_stride * esz) % 16) == 0 &&
+         (reinterpret_cast<uintptr_t>(p.out) % 16) == 0 && !(p.atomic_add && p.out_bf16) &&
+         !(p.col_part != nullptr && !p.out_bf16) && getenv("FLPR_GEMM_GENERIC_EPI") == nullptr;
+}
+
+// CTA-pair kernel eligibility: 256-wide tiles on the lean epilogue, enough pair tiles to fill the 74 SM pairs
+static bool pair_ok(const GemmParams& p, int BN, int splits) {
+  if (!use_pair() || BN != 256 || !lean_ok(p) || p.N < 256) return false;
+  const long long t = (long long)((p.M + 255) / 256) * ((p.N + 255) / 256) * splits;
+  return t >= 60;
+}
+
+template <int A_MODE, int B_MODE>
+static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, int splits,
+                       cudaStream_t st) {
+  GemmParams p = p_in;
+  p.debug = 0;
+  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_n = (p.N + PairLayout::BN - 1) / PairLayout::BN;
+  p.tiles_z = splits;
+  const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n * splits;
+  p.tiles_total = pair_tiles;
+  auto kern = gemm_bf16_tcgen05_pair_kernel<A_MODE, B_MODE>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairLayout::TOTAL);
+    if (e != cudaSuccess) return set_err("cudaFuncSetAttribute(smem, pair)", (int)e);
+    configured = true;
+  }
+  const int max_pairs = sm_count() / 2;
+  const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
+  kern<<<2 * pairs, PairLayout::THREADS, PairLayout::TOTAL, st>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(cudaGetErrorString(e), (int)e);
+  return 0;
+}
+
+static int dispatch_pair(int a_mode, int b_mode, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                         int splits, cudaStream_t st) {
+  if (a_mode == OP_KMAJOR && b_mode == OP_KMAJOR) return launch_pair<OP_KMAJOR, OP_KMAJOR>(ta, tb, p, splits, st);
+  if (a_mode == OP_KMAJOR && b_mode == OP_MNMAJOR) return launch_pair<OP_KMAJOR, OP_MNMAJOR>(ta, tb, p, splits, st);
+  if (a_mode == OP_MNMAJOR && b_mode == OP_KMAJOR) return launch_pair<OP_MNMAJOR, OP_KMAJOR>(ta, tb, p, splits, st);
+  if (a_mode == OP_MNMAJOR && b_mode == OP_MNMAJOR) return launch_pair<OP_MNMAJOR, OP_MNMAJOR>(ta, tb, p, splits, st);
+  if (a_mode == OP_CONV && b_mode == OP_KMAJOR) return launch_pair<OP_CONV, OP_KMAJOR>(ta, tb, p, splits, st);
+  if (a_mode == OP_CONV && b_mode == OP_TAPFLIP) return launch_pair<OP_CONV, OP_TAPFLIP>(ta, tb, p, splits, st);
+  if (a_mode == OP_MNMAJOR && b_mode == OP_CONV) return launch_pair<OP_MNMAJOR, OP_CONV>(ta, tb, p, splits, st);
+  return set_err("unsupported operand mode combination (pair)", -3);
+}
+
 template <int BN, int A_MODE, int B_MODE>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, int splits, cudaStream_t st) {
   GemmParams p = p_in;
@@ -904,15 +1157,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   p.tiles_total = p.tiles_m * p.tiles_n * splits;
   if (use_persist()) {
     using L = PersistLayout<BN>;
-    // lean epilogue: plain row-major bf16 / fp32 / fp32-atomic output, every 32-column chunk full and 16-byte aligned
-    const long long esz = p.out_bf16 ? 2 : 4;
-    const bool act = p.residual != nullptr || p.bias_n != nullptr || p.relu;
-    const bool lean = !p.trans_out && p.bias_m == nullptr && (!act || (p.out_bf16 && !p.atomic_add)) &&
-                      (reinterpret_cast<uintptr_t>(p.bias_n) % 16) == 0 &&
-                      (reinterpret_cast<uintptr_t>(p.residual) % 16) == 0 &&
-                      (p.N % 32) == 0 && ((p.ldo * esz) % 16) == 0 && ((p.tap_stride * esz) % 16) == 0 &&
-                      (reinterpret_cast<uintptr_t>(p.out) % 16) == 0 && !(p.atomic_add && p.out_bf16) &&
-                      !(p.col_part != nullptr && !p.out_bf16) && getenv("FLPR_GEMM_GENERIC_EPI") == nullptr;
+    const bool lean = lean_ok(p);
     const int slots = sm_count() * L::MIN_CTAS;
     const int grid = p.tiles_total < slots ? p.tiles_total : slots;
     if (lean) {
@@ -965,7 +1210,8 @@ static int dispatch_modes(int a_mode, int b_mode, const CUtensorMap& ta, const C
 }
 
 static int dispatch_bn(int BN, int a_mode, int b_mode, const CUtensorMap& ta, const CUtensorMap& tb,
-                       const GemmParams& p, int splits, cudaStream_t st) {
+                       const GemmParams& p, int splits, cudaStream_t st, bool pair = false) {
+  if (pair) return dispatch_pair(a_mode, b_mode, ta, tb, p, splits, st);
   if (BN == 64) return dispatch_modes<64>(a_mode, b_mode, ta, tb, p, splits, st);
   if (BN == 128) return dispatch_modes<128>(a_mode, b_mode, ta, tb, p, splits, st);
   return dispatch_modes<256>(a_mode, b_mode, ta, tb, p, splits, st);
@@ -994,6 +1240,9 @@ const char* flpr_gemm_last_error() { return g_err; }
 // 1: persistent kernel (default), 0: classic one-tile-per-CTA kernel, -1: re-read FLPR_GEMM_PERSIST.
 void flpr_gemm_set_persistent(int on) { g_persist = on; }
 
+// 1: use the cta_group::2 (CTA-pair) kernel where eligible, 0: never, -1: re-read FLPR_GEMM_2CTA.
+void flpr_gemm_set_pair(int on) { g_pair = on; }
+
 // D = alpha * op(A) * op(B)^T.  a_mode/b_mode: 0 = [rows,K] (ld = row stride), 1 = [K,rows] (ld = K-row stride).
 // col_part (optional, fp32 [ceil(M/128)*4][2][N]): per-32-row partial column sums / sums of squares of the fp32
 // result (fused batch-norm statistics); requires split_k <= 1 and no transposed output.
@@ -1015,6 +1264,14 @@ int flpr_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   const int BN = pick_bn(M, N, splits, bn_req);
+  p.out = out; p.ldo = ldo; p.out_bf16 = out_bf16; p.trans_out = trans_out;
+  p.atomic_add = splits > 1 ? 1 : 0;
+  if (p.atomic_add && out_bf16) return set_err("split-K requires fp32 output", -6);
+  if (col_part != nullptr && (p.atomic_add || trans_out)) return set_err("col_part needs split_k=1, no transpose", -12);
+  p.col_part = col_part;
+  p.alpha = alpha; p.bias_n = bias_n; p.bias_m = bias_m; p.relu = relu;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  const bool pair = pair_ok(p, BN, splits);
   CUtensorMap ta, tb;
   int rc;
   {
@@ -1028,21 +1285,14 @@ int flpr_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K,
     str[0] = (uint64_t)lda * 2;
     if ((rc = get_map(&ta, A, 2, dims, str, box))) return rc;
     if (b_mode == OP_KMAJOR) {
-      dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BK; box[1] = (uint32_t)BN;
+      dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BK; box[1] = (uint32_t)(pair ? PairLayout::BNH : BN);
     } else {
       dims[0] = (uint64_t)N; dims[1] = (uint64_t)K; box[0] = 64; box[1] = BK;
     }
     str[0] = (uint64_t)ldb * 2;
     if ((rc = get_map(&tb, B, 2, dims, str, box))) return rc;
   }
-  p.out = out; p.ldo = ldo; p.out_bf16 = out_bf16; p.trans_out = trans_out;
-  p.atomic_add = splits > 1 ? 1 : 0;
-  if (p.atomic_add && out_bf16) return set_err("split-K requires fp32 output", -6);
-  if (col_part != nullptr && (p.atomic_add || trans_out)) return set_err("col_part needs split_k=1, no transpose", -12);
-  p.col_part = col_part;
-  p.alpha = alpha; p.bias_n = bias_n; p.bias_m = bias_m; p.relu = relu;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  return dispatch_bn(BN, a_mode, b_mode, ta, tb, p, splits, stream);
+  return dispatch_bn(BN, a_mode, b_mode, ta, tb, p, splits, stream, pair);
 }
 
 static int conv_tiling(int H, int W, int* TH, int* NB, int* tiles_per_img) {
@@ -1078,6 +1328,16 @@ int flpr_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int NIMG, int 
   const int M = NIMG * Ho * Wo;
   const int K = KH * KW * C;
   const int BN = pick_bn(M, Cout, 1, bn_req);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = Cout; p.K = K;
+  p.kb_total = K / BK; p.kb_per_split = p.kb_total;
+  p.out = out; p.ldo = Cout; p.out_bf16 = out_bf16; p.alpha = alpha; p.bias_n = bias_n; p.relu = relu;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.col_part = col_part;
+  p.cH = Ho; p.cW = Wo; p.cC = C; p.cTH = TH; p.cNB = NB; p.cKW = KW; p.cPadH = pad_h; p.cPadW = pad_w;
+  p.cTilesPerImg = tiles_per_img; p.cTaps = KH * KW; p.cStride = stride;
+  const bool pair = pair_ok(p, BN, 1);
   CUtensorMap ta, tb;
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NIMG};
@@ -1088,19 +1348,10 @@ int flpr_conv_nhwc_bf16(const void* X, const void* Wt, void* out, int NIMG, int 
     if ((rc = get_map(&ta, X, 4, dims, str, box, (uint32_t)stride))) return rc;
     uint64_t d2[2] = {(uint64_t)K, (uint64_t)Cout};
     uint64_t s2[1] = {(uint64_t)K * 2};
-    uint32_t b2[2] = {BK, (uint32_t)BN};
+    uint32_t b2[2] = {BK, (uint32_t)(pair ? PairLayout::BNH : BN)};
     if ((rc = get_map(&tb, Wt, 2, d2, s2, b2))) return rc;
   }
-  GemmParams p;
-  memset(&p, 0, sizeof(p));
-  p.M = M; p.N = Cout; p.K = K;
-  p.kb_total = K / BK; p.kb_per_split = p.kb_total;
-  p.out = out; p.ldo = Cout; p.out_bf16 = out_bf16; p.alpha = alpha; p.bias_n = bias_n; p.relu = relu;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  p.col_part = col_part;
-  p.cH = Ho; p.cW = Wo; p.cC = C; p.cTH = TH; p.cNB = NB; p.cKW = KW; p.cPadH = pad_h; p.cPadW = pad_w;
-  p.cTilesPerImg = tiles_per_img; p.cTaps = KH * KW; p.cStride = stride;
-  return dispatch_bn(BN, OP_CONV, OP_KMAJOR, ta, tb, p, 1, stream);
+  return dispatch_bn(BN, OP_CONV, OP_KMAJOR, ta, tb, p, 1, stream, pair);
 }
 
 // Data gradient of a stride-1 convolution, straight from the FORWARD weight Wt [Cout, KH*KW*Cin] (no flipped /
@@ -1135,7 +1386,7 @@ int flpr_conv_dgrad_nhwc_bf16(const void* dY, const void* Wt, void* out, int NIM
   p.cH = H; p.cW = W; p.cC = Cout; p.cTH = TH; p.cNB = NB; p.cKW = KW;
   p.cPadH = KH - 1 - pad_h; p.cPadW = KW - 1 - pad_w;
   p.cTilesPerImg = tiles_per_img; p.cTaps = KH * KW; p.cStride = 1;
-  return dispatch_bn(BN, OP_CONV, OP_TAPFLIP, ta, tb, p, 1, stream);
+  return dispatch_bn(BN, OP_CONV, OP_TAPFLIP, ta, tb, p, 1, stream, pair_ok(p, BN, 1));
 }
 
 // Weight gradient of a stride-1 convolution: out[Cout, KH*KW*C] (fp32, tap-major then C) +=
@@ -1182,7 +1433,7 @@ int flpr_conv_wgrad_nhwc_bf16(const void* X, const void* dY, float* out, int NIM
   p.cH = H; p.cW = W; p.cC = C; p.cTH = TH; p.cNB = NB; p.cKW = KW; p.cPadH = pad_h; p.cPadW = pad_w;
   p.cSplits = splits; p.tap_stride = C; p.cTaps = KH * KW;
   const int gz = KH * KW * splits;
-  return dispatch_bn(BN, OP_MNMAJOR, OP_CONV, ta, tb, p, gz, stream);
+  return dispatch_bn(BN, OP_MNMAJOR, OP_CONV, ta, tb, p, gz, stream, pair_ok(p, BN, gz));
 }
 
 }  // extern "C"

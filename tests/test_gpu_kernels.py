@@ -7,14 +7,17 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["persistent", "classic"])
+@pytest.fixture(autouse=True, params=["persistent", "classic", "pair"])
 def gemm_kernel_variant(request):
-    """Every test runs against both tcgen05 GEMM kernels: the persistent one (default) and the one-tile-per-CTA one."""
+    """Every test runs against the tcgen05 GEMM kernels: persistent (default), one-tile-per-CTA, and the CTA-pair
+    (cta_group::2) kernel on the shapes it covers."""
     from flpr_b200.ops import native
     lib = native.load()
-    lib.flpr_gemm_set_persistent(1 if request.param == "persistent" else 0)
+    lib.flpr_gemm_set_persistent(0 if request.param == "classic" else 1)
+    lib.flpr_gemm_set_pair(1 if request.param == "pair" else 0)
     yield request.param
     lib.flpr_gemm_set_persistent(1)
+    lib.flpr_gemm_set_pair(-1)
 
 
 def _ref_gemm(a, b):
