@@ -1079,12 +1079,12 @@ static int sm_count() {
   return g_sms;
 }
 
-static int g_pair = -1;      // FLPR_GEMM_2CTA (default 0 until validated on every shape class): cta_group::2 kernel
+static int g_pair = -1;      // FLPR_GEMM_2CTA (default 1): cta_group::2 kernel on the shapes it covers
 
 static bool use_pair() {
   if (g_pair < 0) {
     const char* e = getenv("FLPR_GEMM_2CTA");
-    g_pair = (e != nullptr && e[0] == '1') ? 1 : 0;
+    g_pair = (e == nullptr || e[0] != '0') ? 1 : 0;
   }
   return g_pair == 1 && use_persist();
 }

@@ -14,7 +14,7 @@ def gemm_kernel_variant(request):
     from flpr_b200.ops import native
     lib = native.load()
     lib.flpr_gemm_set_persistent(0 if request.param == "classic" else 1)
-    lib.flpr_gemm_set_pair(1 if request.param == "pair" else 0)
+    lib.flpr_gemm_set_pair(1 if request.param == "pair" else 0)       # "persistent" = single-CTA persistent kernel
     yield request.param
     lib.flpr_gemm_set_persistent(1)
     lib.flpr_gemm_set_pair(-1)
