@@ -147,8 +147,8 @@ class ExperimentStage:
         store = CheckpointStore(os.path.join(self.common_config["checkpoints_dir"], exp_config["exp_name"]),
                                 asynchronous=eng.get("async_checkpoint", True) and self.device.type == "cuda",
                                 enabled=eng.get("checkpoints", True),
-                                workers=eng.get("ckpt_workers") or min(12, max(6, 2 * n_local)),
-                                arena_bytes=int(float(eng.get("ckpt_arena_gb") or min(8.0, max(2.0, 1.0 * n_local)))
+                                workers=eng.get("ckpt_workers") or min(16, max(8, 2 * n_local)),
+                                arena_bytes=int(float(eng.get("ckpt_arena_gb") or min(8.0, max(3.0, 1.5 * n_local)))
                                                 * (1 << 30)))
         server = parser_server(exp_config, self.common_config, self.device, store)
         clients = parser_clients(exp_config, self.common_config, self.device, store, None, self.rank, self.world,
