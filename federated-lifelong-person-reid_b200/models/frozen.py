@@ -11,7 +11,8 @@ Execution paths of the residual stages (``native`` flag):
   convolution an implicit GEMM of ``csrc/gemm_tcgen05.cu`` (NHWC bf16, folded-BN bias + residual + ReLU in the lean
   epilogue, stride 2 through TMA element strides) - the same kernels as the trainable head;
 * **library** fallback (cuDNN fused conv calls) for shapes the implicit-GEMM tiling does not cover.
-The 7x7 stem convolution (3 input channels) and the max-pool run on cuDNN / ATen in both paths.
+The 7x7 / 2 stem (3 input channels) runs natively as a 4x4 convolution over 2x2 space-to-depth cells
+(``ops.gemm.stem_conv``) followed by the NHWC max-pool kernel; ``FLPR_NATIVE_STEM=0`` keeps cuDNN / ATen for the two.
 """
 from __future__ import annotations
 

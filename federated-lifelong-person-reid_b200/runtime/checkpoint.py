@@ -180,6 +180,7 @@ class CheckpointStore:
         self.workers = max(1, int(workers))
         self.arena_bytes = int(arena_bytes)
         self.bytes_written = 0
+        self.muted = False                                # engine_opts.checkpoint_interval: skip this round's files
         self._started = False
         self._err: Optional[str] = None
         self._next_id = 0
@@ -317,7 +318,7 @@ class CheckpointStore:
     def save(self, actor: str, state_name: Optional[str], state: Any, cover: bool = False,
              post: Optional[str] = None) -> None:
         """``save_state`` of ``modules/client.py:52-63`` / ``modules/server.py:46-57``."""
-        if state_name is None or not self.enabled:
+        if state_name is None or not self.enabled or (self.muted and actor != "_resume"):
             return
         with self._lock:                                  # client threads checkpoint concurrently
             self._save_locked(actor, state_name, state, cover, post)

@@ -21,6 +21,12 @@ ENGINE_DEFAULTS: Dict[str, Any] = {
     "arena_mb": 0,                    # 0 -> sized automatically from the model
     "async_checkpoint": True,         # write payload / model checkpoints off the critical path
     "save_payload_ckpts": True,       # '{round}-{src}-{dst}.ckpt' files (experiment.py:199-202,235-238)
+    "checkpoint_interval": 1,         # snapshot every N-th round (1 = every round, like the reference)
+    "ckpt_workers": 0,                # writer processes (0 -> 8..16 by the number of local clients)
+    "ckpt_arena_gb": 0,               # pinned staging arena (0 -> 3..8 GB by the number of local clients)
+    "client_threads": True,           # `parallel` clients per device train concurrently on their own CUDA streams
+    "resume": False,                  # continue from {checkpoints_dir}/{exp}/_resume/rank{r}.ckpt when present
+    "resume_interval": 0,             # write the resume manifest every N rounds (0 = never)
     "device_augment": True,           # run flip / erasing / resize on the GPU
     "cache_prototypes": False,        # FedSTIL: recompute the frozen-trunk pass every epoch like the reference
     "reference_compat": True,         # reproduce documented reference quirks

@@ -248,8 +248,12 @@ class ExperimentStage:
         if federated is None:
             federated = hasattr(server, "uploaded")
 
-        if self.device.type == "cuda" and getattr(server, "store", None) is not None:
-            server.store.fence()          # snapshot DMAs of the previous round precede any overwrite of their sources
+        store = getattr(server, "store", None)
+        if store is not None:
+            every = max(1, int(eng.get("checkpoint_interval", 1) or 1))
+            store.muted = (curr_round % every) != 0
+        if self.device.type == "cuda" and store is not None:
+            store.fence()                 # snapshot DMAs of the previous round precede any overwrite of their sources
 
         # ---- server -> clients ------------------------------------------------------------------------------------
         with timer("dispatch"):

@@ -346,3 +346,23 @@ def test_fedstil_exemplar_generations_roundtrip():
     # herding the same identities again replaces their exemplars
     model.build_examplars(protos, pids, pids.clone(), [10, 11])
     assert sorted(model.examplars.keys()) == [10, 11, 12, 13]
+
+
+def test_stem_as_space_to_depth_conv_cpu_reference():
+    """7x7 / stride-2 / pad-3 stem == 4x4 / stride-1 convolution over zero-padded 2x2 space-to-depth cells."""
+    from flpr_b200.ops.gemm import stem_weight_s2d, stem_conv, maxpool3x3s2, s2d_pad, stem_supported, conv_supported
+    torch.manual_seed(0)
+    x = torch.randn(2, 32, 16, 3).bfloat16()
+    w = (torch.randn(8, 3, 7, 7) / 10).bfloat16().float()
+    b = torch.randn(8)
+    ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w, b, stride=2, padding=3))
+    out = stem_conv(x, stem_weight_s2d(w), b)
+    assert out.shape == (2, 16, 8, 8)
+    assert torch.allclose(out.float(), ref.permute(0, 2, 3, 1), atol=3e-2)
+    cells = s2d_pad(x)
+    assert cells.shape == (2, 19, 11, 16) and float(cells[:, :2].abs().sum()) == 0.0 and float(cells[..., 12:].abs().sum()) == 0
+    pooled = maxpool3x3s2(out)
+    refp = torch.nn.functional.max_pool2d(out.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(pooled.float(), refp)
+    assert stem_supported(256, 128) and stem_supported(128, 64) and not stem_supported(224, 224)
+    assert conv_supported(64, 32, 128, 3, 2) and conv_supported(16, 8, 512, 3, 1) and not conv_supported(14, 14, 256, 3, 1)

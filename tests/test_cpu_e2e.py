@@ -127,3 +127,19 @@ def test_cli_synthetic(tmp_path):
                         "--synthetic"], capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     assert any(f.startswith("cli-") for f in os.listdir(tmp_path / "logs"))
+
+
+def test_checkpoint_interval_skips_rounds(tmp_path):
+    """engine_opts.checkpoint_interval = 2: payload files only for even rounds; model files still exist at the end."""
+    import glob
+    from flpr_b200.runtime.experiment import ExperimentStage
+    common = tiny_common(str(tmp_path))
+    common["defaults"]["exp_opts"].update(comm_rounds=4, val_interval=100)
+    cfg = tiny_experiment(common, "fedavg")
+    cfg["engine_opts"].update(checkpoint_interval=2, val_at_round0=False)
+    with ExperimentStage(common, [cfg], source_factory=tiny_factory()) as stage:
+        stage.run_experiment(cfg)
+    root = os.path.join(common["checkpoints_dir"], cfg["exp_name"])
+    rounds = sorted({int(os.path.basename(f).split("-")[0]) for f in glob.glob(os.path.join(root, "*", "[0-9]*-*.ckpt"))})
+    assert rounds == [2, 4], rounds
+    assert os.path.exists(os.path.join(root, "client-0", "fedavg_model.ckpt"))
