@@ -69,6 +69,19 @@ def main():
         srv.distance_calculate_step, srv.distance_calculate_decay = d["step"], d["decay"]
         srv.logger = _Log()
         out = {name: srv.get_dispatch_incremental_state(name)["incremental_shared_params"] for name in d["receivers"]}
+    elif case == "fedcurv_penalty":
+        import torch.nn as nn
+        from methods.fedcurv import Model
+        m = Model.__new__(Model)
+        nn.Module.__init__(m)
+        m.lambda_penalty = d["lam"]
+        m.params = {n: p.clone().requires_grad_(True) for n, p in d["params"].items()}
+        m.precision_matrices = d["F"]
+        m.params_old = d["p_old"]
+        m.other_precision_matrices = d["others"]            # [(F_j dict, p_j dict), ...]
+        loss = m.penalty()
+        loss.backward()
+        out = {"value": loss.detach(), "grads": {n: p.grad for n, p in m.params.items()}}
     elif case == "swin_forward":
         from models.swin_transformer import SwinTransformer
         torch.manual_seed(d["seed"])

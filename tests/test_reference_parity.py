@@ -130,3 +130,52 @@ def test_swin_transformer_matches_reference(tmp_path):
         with torch.no_grad():
             assert torch.allclose(net.forward_features(cfg["x"]), ref["feat"], atol=2e-5), fused
             assert torch.allclose(net(cfg["x"]), ref["logits"], atol=2e-5), fused
+
+
+def test_fedcurv_three_moment_penalty_matches_reference(tmp_path):
+    """The reference ships (1 + 2K) parameter-sized tensors to every client and loops over them in ``penalty()``
+    (fedcurv.py:79-86, 621-646). Here the server pre-reduces three moments (sum F_j, sum F_j p_j, sum F_j p_j^2) and
+    the optimizer kernel uses ``2 lam (Q p - R)``: same gradient, same value (up to the constant moment)."""
+    import torch.nn as nn
+    from flpr_b200.methods.fedcurv import Model
+    from flpr_b200.ops.fused import fused_optimizer_step
+    from flpr_b200.parallel.comm import FedComm
+    torch.manual_seed(6)
+    net = nn.Sequential(nn.Linear(6, 5), nn.Linear(5, 3))
+    model = Model(net, lambda_penalty=7.0).materialize("cpu", "fp32", None)
+    a = model.arena
+    names = list(a.segments.keys())
+    n = a.numel
+
+    def rnd_dict(pos=False):
+        return {k: (torch.rand_like(a.view(a.master, k)) if pos else torch.randn_like(a.view(a.master, k)))
+                for k in names}
+
+    F_own, p_old = rnd_dict(True), rnd_dict()
+    others = [(rnd_dict(True), rnd_dict()) for _ in range(3)]
+    params = {k: a.view(a.master, k).detach().clone() for k in names}
+    ref = oracle("fedcurv_penalty", {"lam": 7.0, "params": params, "F": F_own, "p_old": p_old, "others": others},
+                 tmp_path)
+    # ours: own Fisher / old params into the model, the others' (F_j, p_j) through the moment collective
+    a.from_dict(F_own, model.F)
+    a.from_dict(p_old, model.p_old)
+    comm = FedComm("cpu", 3, arena_bytes=1 << 20)
+    for nm in ("fisher", "param"):
+        comm.alloc_client_buffer(nm, n)
+    for nm in ("mf", "mfp", "mfpp"):
+        comm.alloc_rank_buffer(nm, n)
+    for cid, (Fj, pj) in enumerate(others):
+        a.from_dict(Fj, comm.client_view("fisher", cid))
+        a.from_dict(pj, comm.client_view("param", cid))
+    comm.curv_moments("fisher", "param", [0, 1, 2], "mf", "mfp", "mfpp")
+    model.set_others(comm.rank_view("mf"), comm.rank_view("mfp"), comm.rank_view("mfpp"))
+    const = float((model.F * model.p_old ** 2).sum() * 0 + comm.rank_view("mfpp").sum())     # sum_j F_j p_j^2
+    assert abs(float(model.penalty()) + 7.0 * const - float(ref["value"])) < 1e-3 * abs(float(ref["value"]))
+    # gradient of the penalty as the fused optimizer sees it: plain SGD step with lr = 1, zero data gradient
+    p0 = a.master.clone()
+    g = torch.zeros_like(p0)
+    fused_optimizer_step("sgd", a.master, g, None, None, lr=1.0, step=1, Q=model.Q, R=model.R, lam2=model.lam)
+    grad_flat = p0 - a.master
+    for k in names:
+        assert torch.allclose(a.view(grad_flat, k), ref["grads"][k], rtol=1e-4, atol=1e-4), k
+    comm.close()
