@@ -366,3 +366,23 @@ def test_stem_as_space_to_depth_conv_cpu_reference():
     assert torch.equal(pooled.float(), refp)
     assert stem_supported(256, 128) and stem_supported(128, 64) and not stem_supported(224, 224)
     assert conv_supported(64, 32, 128, 3, 2) and conv_supported(16, 8, 512, 3, 1) and not conv_supported(14, 14, 256, 3, 1)
+
+
+def test_utility_helpers():
+    import torch.nn as nn
+    from flpr_b200.utils import misc
+    from flpr_b200.utils.winit import weights_init_classifier, weights_init_kaiming
+    assert misc.torch_device("cpu") == "cpu" and misc.torch_device(device="cpu") == "cpu"
+    assert misc.extract_kwargs({"a": 1}, "b", 7) == 7
+    l = torch.tensor(2.0, requires_grad=True)
+    assert float(misc.extract_losses({"x": l, "y": [l, torch.ones(3)], "z": 5})) == 4.0
+    assert misc.random_sample(3, range(10), 4) == misc.random_sample(3, range(10), 4)
+    assert misc.tensor_value(torch.tensor(1.5), torch.tensor(2)) == (1.5, 2.0)
+    net = nn.Sequential(nn.Conv2d(3, 4, 3), nn.BatchNorm2d(4), nn.Flatten(), nn.Linear(4, 2))
+    net.apply(weights_init_kaiming)
+    net[3].apply(weights_init_classifier)
+    assert float(net[3].weight.std()) < 0.01 and float(net[1].weight.mean()) == 1.0
+    with misc.model_on_device(net, "cpu") as m:
+        assert m is net
+    assert misc.module_paths(net.eval(), torch.randn(2, 3, 3, 3)) == ["0", "1", "2", "3"]
+    assert misc.params_state_size({"a": torch.zeros(3, 2), "b": [1, 2.0]}) == 8
