@@ -82,6 +82,23 @@ def main():
         loss = m.penalty()
         loss.backward()
         out = {"value": loss.detach(), "grads": {n: p.grad for n, p in m.params.items()}}
+    elif case == "fedstil_layer_steps":
+        from methods.fedstil import AdaptiveLayer
+        layer = AdaptiveLayer(global_weight=d["G"].clone(), atten_default=d["atten"])
+        params = [p for p in layer.parameters() if p.requires_grad]
+        opt = (torch.optim.Adam(params, lr=d["lr"], weight_decay=d["wd"]) if d["opt"] == "adam"
+               else torch.optim.SGD(params, lr=d["lr"], weight_decay=d["wd"]))
+        thetas = []
+        for x, t in zip(d["xs"], d["ts"]):
+            opt.zero_grad()
+            loss = ((layer(x) - t) ** 2).mean()
+            # the sparseness regulariser of fedstil.py:639-644
+            loss = loss + d["lam1"] * (torch.norm(layer.initial_global_weight_atten - layer.global_weight_atten, p=1) +
+                                       torch.norm(layer.initial_adaptive_weight - layer.adaptive_weight, p=1))
+            loss.backward()
+            opt.step()
+            thetas.append((layer.global_weight_atten * layer.global_weight + layer.adaptive_weight).detach().clone())
+        out = {"thetas": thetas}
     elif case == "swin_forward":
         from models.swin_transformer import SwinTransformer
         torch.manual_seed(d["seed"])

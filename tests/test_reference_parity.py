@@ -179,3 +179,28 @@ def test_fedcurv_three_moment_penalty_matches_reference(tmp_path):
     for k in names:
         assert torch.allclose(a.view(grad_flat, k), ref["grads"][k], rtol=1e-4, atol=1e-4), k
     comm.close()
+
+
+@pytest.mark.parametrize("opt,wd,steps", [("sgd", 0.0, 3), ("adam", 0.0, 2), ("adam", 1e-2, 1)])
+def test_fedstil_theta_training_equals_reference_adaptive_layer(tmp_path, opt, wd, steps):
+    """Training ``theta`` directly with the fused optimizer (weight decay on ``theta - a G``, L1 ``sign(theta - G)``)
+    reproduces the reference's ``AdaptiveLayer`` (frozen ``atten (.) G`` + trained ``A``, L1 towards ``A0``).
+    With weight decay the reference also moves its accidentally trainable ``initial_*`` copies (a documented deviation),
+    which only matters from the second step on."""
+    from flpr_b200.ops.fused import fused_optimizer_step
+    torch.manual_seed(8)
+    G = torch.randn(5, 7)
+    xs = [torch.randn(4, 7) for _ in range(steps)]
+    ts = [torch.randn(4, 5) for _ in range(steps)]
+    a, lr, lam1 = 0.8, 0.05, 1e-2
+    ref = oracle("fedstil_layer_steps", {"G": G, "atten": a, "lr": lr, "wd": wd, "opt": opt, "lam1": lam1,
+                                         "xs": xs, "ts": ts}, tmp_path)
+    theta = G.clone().flatten()
+    Gf = G.clone().flatten()
+    m, v = torch.zeros_like(theta), torch.zeros_like(theta)
+    for i, (x, t) in enumerate(zip(xs, ts)):
+        th = theta.view(5, 7).clone().requires_grad_(True)
+        ((torch.nn.functional.linear(x, th) - t) ** 2).mean().backward()
+        fused_optimizer_step(opt, theta, th.grad.flatten().clone(), m, v, lr=lr, step=i + 1, weight_decay=wd, G=Gf,
+                             lam1=lam1, atten=a)
+        assert torch.allclose(theta.view(5, 7), ref["thetas"][i], atol=2e-6), (opt, i)
