@@ -82,6 +82,25 @@ def main():
         loss = m.penalty()
         loss.backward()
         out = {"value": loss.detach(), "grads": {n: p.grad for n, p in m.params.items()}}
+    elif case == "importance":
+        import torch.nn as nn
+        import torch.nn.functional as F
+        method = d["method"]
+        mod = __import__(f"methods.{method}", fromlist=["Model"])
+        net = nn.Sequential(nn.Linear(6, 5), nn.ReLU(), nn.Linear(5, 4))
+        net.load_state_dict(d["state"])
+
+        class _Op:
+            def _invoke_train(self, model, data, target, **kw):
+                return {"loss": F.cross_entropy(model(data), target)}
+
+        m = mod.Model.__new__(mod.Model)
+        nn.Module.__init__(m)
+        m.net = net
+        m.operator = _Op()
+        m.params = {n: p for n, p in net.named_parameters() if p.requires_grad}
+        m.recall_dataloaders = {name: [(x, y, y) for x, y in batches] for name, batches in d["loaders"].items()}
+        out = {n: t.detach() for n, t in m._calculate_importance().items()}
     elif case == "fedstil_layer_steps":
         from methods.fedstil import AdaptiveLayer
         layer = AdaptiveLayer(global_weight=d["G"].clone(), atten_default=d["atten"])

@@ -204,3 +204,32 @@ def test_fedstil_theta_training_equals_reference_adaptive_layer(tmp_path, opt, w
         fused_optimizer_step(opt, theta, th.grad.flatten().clone(), m, v, lr=lr, step=i + 1, weight_decay=wd, G=Gf,
                              lam1=lam1, atten=a)
         assert torch.allclose(theta.view(5, 7), ref["thetas"][i], atol=2e-6), (opt, i)
+
+
+@pytest.mark.parametrize("method", ["ewc", "mas", "fedcurv"])
+def test_importance_accumulation_matches_reference(tmp_path, method):
+    """Fisher (g^2) / MAS (|g|) importance over the remembered loaders with the reference's ``len(batch) / #batches``
+    weighting; EWC skips the most recent task (ewc.py:62-65), MAS and FedCurv do not."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from flpr_b200.methods import methods
+    torch.manual_seed(9)
+    net = nn.Sequential(nn.Linear(6, 5), nn.ReLU(), nn.Linear(5, 4))
+    state = {k: v.clone() for k, v in net.state_dict().items()}
+    loaders = {f"task-{t}": [(torch.randn(bs, 6), torch.randint(0, 4, (bs,))) for bs in (5, 3, 4)] for t in range(3)}
+    ref = oracle("importance", {"method": method, "state": state, "loaders": loaders}, tmp_path)
+
+    class Op:
+        def _invoke_train(self, model, data, target, **kw):
+            return {"loss": F.cross_entropy(model(data), target)}
+
+    model = methods[method].Model(net, operator=Op()).materialize("cpu", "fp32", None)
+
+    class Loader(list):
+        pass
+    for name, batches in loaders.items():
+        model.recall_dataloaders[name] = Loader([(x, y, y) for x, y in batches])
+    model._calculate_importance()
+    got = model.arena.to_dict(model.F)
+    for k, v in ref.items():
+        assert torch.allclose(got[k], v, rtol=1e-4, atol=1e-6), (method, k)
