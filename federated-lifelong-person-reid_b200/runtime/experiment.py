@@ -281,13 +281,6 @@ class ExperimentStage:
         # ---- local training ---------------------------------------------------------------------------------------
         with timer("train"):
             todo = [local[n] for n in online if n in local]
-            for c in todo:
-                # the C2S payload (= the client's state right after its local training) is produced and snapshotted by
-                # the client itself as soon as it has trained, instead of in a burst at the end of the round: the
-                # protocol order is unchanged (the server still collects in the upload phase below), the checkpoint
-                # writers just get the files earlier
-                c._upload_ctx = (curr_round, server.server_name, save_payloads)
-                c._early_upload = None
             workers = min(self.container.max_worker(), len(todo))
             if workers > 1 and self.device.type == "cuda" and eng.get("client_threads", True) and \
                     all(getattr(c.model.net, "thread_safe_rng", False) for c in todo):
@@ -307,13 +300,9 @@ class ExperimentStage:
             for n in online:
                 client = local.get(n)
                 if client is not None:
-                    early = getattr(client, "_early_upload", None)
-                    if early is not None:
-                        state, client._early_upload = early[0], None
-                    else:
-                        state = client.get_incremental_state()
-                        if save_payloads:
-                            client.save_state(f"{curr_round}-{n}-{server.server_name}", strip_private(state), True)
+                    state = client.get_incremental_state()
+                    if save_payloads:
+                        client.save_state(f"{curr_round}-{n}-{server.server_name}", strip_private(state), True)
                     if state is not None:
                         server.set_client_incremental_state(n, state)
                     del state
@@ -385,14 +374,6 @@ class ExperimentStage:
                                        tr_loader=task["tr_loader"], val_loader=task["query_loader"], device=device)
                     log.record(f"data.{client.client_name}.{curr_round}.{task['task_name']}",
                                {"tr_acc": out["accuracy"], "tr_loss": out["loss"]})
-                ctx = getattr(client, "_upload_ctx", None)
-                if ctx is not None:
-                    rnd, server_name, save_payloads = ctx
-                    client._upload_ctx = None
-                    state = client.get_incremental_state()
-                    if save_payloads:
-                        client.save_state(f"{rnd}-{client.client_name}-{server_name}", strip_private(state), True)
-                    client._early_upload = (state,)
             except Exception as ex:
                 client.logger.error(ex)
                 raise
