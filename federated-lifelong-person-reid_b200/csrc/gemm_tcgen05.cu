@@ -1089,6 +1089,24 @@ static bool use_pair() {
   return g_pair == 1 && use_persist();
 }
 
+// FLPR_GEMM_GENERIC_EPI / FLPR_GEMM_DEBUG are read ONCE (no getenv on the launch path: launches come from several
+// client threads, and getenv is not safe against a concurrent setenv elsewhere in the process).
+static int g_generic_epi = -1;
+static int g_debug = -1;
+
+static bool force_generic_epi() {
+  if (g_generic_epi < 0) g_generic_epi = getenv("FLPR_GEMM_GENERIC_EPI") != nullptr ? 1 : 0;
+  return g_generic_epi == 1;
+}
+
+static int debug_flags() {
+  if (g_debug < 0) {
+    const char* e = getenv("FLPR_GEMM_DEBUG");
+    g_debug = e ? atoi(e) : 0;
+  }
+  return g_debug;
+}
+
 // lean epilogue: plain row-major bf16 / fp32 / fp32-atomic output, every 32-column chunk full and 16-byte aligned
 static bool lean_ok(const GemmParams& p) {
   const long long esz = p.out_bf16 ? 2 : 4;
@@ -1097,7 +1115,7 @@ static bool lean_ok(const GemmParams& p) {
          (reinterpret_cast<uintptr_t>(p.bias_n) % 16) == 0 && (reinterpret_cast<uintptr_t>(p.residual) % 16) == 0 &&
          (p.N % 32) == 0 && ((p.ldo * esz) % 16) == 0 && ((p.tap_stride * esz) % 16) == 0 &&
          (reinterpret_cast<uintptr_t>(p.out) % 16) == 0 && !(p.atomic_add && p.out_bf16) &&
-         !(p.col_part != nullptr && !p.out_bf16) && getenv("FLPR_GEMM_GENERIC_EPI") == nullptr;
+         !(p.col_part != nullptr && !p.out_bf16) && !force_generic_epi();
 }
 
 // CTA-pair kernel eligibility: 256-wide tiles on the lean epilogue, enough pair tiles to fill the 74 SM pairs
@@ -1147,10 +1165,7 @@ static int dispatch_pair(int a_mode, int b_mode, const CUtensorMap& ta, const CU
 template <int BN, int A_MODE, int B_MODE>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, int splits, cudaStream_t st) {
   GemmParams p = p_in;
-  {
-    const char* e = getenv("FLPR_GEMM_DEBUG");
-    p.debug = e ? atoi(e) : 0;
-  }
+  p.debug = debug_flags();
   p.tiles_m = (p.M + BM - 1) / BM;
   p.tiles_n = (p.N + BN - 1) / BN;
   p.tiles_z = splits;
@@ -1242,6 +1257,11 @@ void flpr_gemm_set_persistent(int on) { g_persist = on; }
 
 // 1: use the cta_group::2 (CTA-pair) kernel where eligible, 0: never, -1: re-read FLPR_GEMM_2CTA.
 void flpr_gemm_set_pair(int on) { g_pair = on; }
+
+// bottleneck-isolation switches of scripts/gemm_*: debug bit mask (see GemmParams::debug) and forced generic epilogue;
+// -1 re-reads the FLPR_GEMM_DEBUG / FLPR_GEMM_GENERIC_EPI environment variables at the next launch.
+void flpr_gemm_set_debug(int flags) { g_debug = flags; }
+void flpr_gemm_set_generic_epilogue(int on) { g_generic_epi = on; }
 
 // D = alpha * op(A) * op(B)^T.  a_mode/b_mode: 0 = [rows,K] (ld = row stride), 1 = [K,rows] (ld = K-row stride).
 // col_part (optional, fp32 [ceil(M/128)*4][2][N]): per-32-row partial column sums / sums of squares of the fp32

@@ -80,6 +80,9 @@ def _declare(lib: C.CDLL) -> None:
     lib.flpr_gemm_set_persistent.restype = None
     lib.flpr_gemm_set_pair.argtypes = [I]
     lib.flpr_gemm_set_pair.restype = None
+    for name in ("flpr_gemm_set_debug", "flpr_gemm_set_generic_epilogue"):
+        getattr(lib, name).argtypes = [I]
+        getattr(lib, name).restype = None
     for name in ("flpr_gemm_last_error", "flpr_comm_last_error"):
         getattr(lib, name).restype = C.c_char_p
         getattr(lib, name).argtypes = []
