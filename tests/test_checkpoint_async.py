@@ -43,3 +43,38 @@ def test_async_store_roundtrip(tmp_path):
     assert isinstance(ex[np.int64(7)][0][0], np.ndarray) and ex[np.int64(7)][0][0].dtype == np.float32
     assert st.load("client-0", "big")["x"].numel() == 20 << 20
     st.close()
+
+
+def test_async_store_concurrent_writers_with_back_pressure(tmp_path):
+    """Client threads snapshot concurrently through an arena that is much smaller than the total volume: saves block on
+    the writers (back-pressure), nothing is lost or torn, the arena is fully returned."""
+    import threading
+    st = CheckpointStore(str(tmp_path), asynchronous=True, workers=4, arena_bytes=8 << 20)
+    errors = []
+
+    def client(cid):
+        try:
+            g = torch.Generator().manual_seed(cid)
+            for i in range(25):
+                state = {"w": torch.randn(50_000 + 1000 * cid, generator=g), "i": i, "cid": cid,
+                         "nested": {"v": torch.full((1000,), float(i * 100 + cid))}}
+                st.save(f"client-{cid}", f"s{i}", state, True)          # ~200 KB each, 20 MB in total per client
+        except Exception as ex:  # noqa: BLE001
+            errors.append(ex)
+
+    threads = [threading.Thread(target=client, args=(c,)) for c in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    st.flush()
+    assert st._arena.free == [(0, 8 << 20)]
+    for cid in range(4):
+        g = torch.Generator().manual_seed(cid)
+        for i in range(25):
+            want = torch.randn(50_000 + 1000 * cid, generator=g)
+            got = st.load(f"client-{cid}", f"s{i}")
+            assert got["i"] == i and got["cid"] == cid and torch.equal(got["w"], want)
+            assert float(got["nested"]["v"][0]) == float(i * 100 + cid)
+    st.close()
