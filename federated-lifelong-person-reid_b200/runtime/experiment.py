@@ -285,6 +285,8 @@ class ExperimentStage:
             if workers > 1 and self.device.type == "cuda" and eng.get("client_threads", True) and \
                     all(getattr(c.model.net, "thread_safe_rng", False) for c in todo):
                 self._train_parallel(todo, log, curr_round, workers)
+            elif workers > 1 and self.device.type == "cpu" and eng.get("client_threads") == "force":
+                self._train_parallel_cpu(todo, log, curr_round, workers)
             else:
                 for client in todo:
                     self._process_train(client, log, curr_round, self.container)
@@ -352,6 +354,21 @@ class ExperimentStage:
                 err = err or ex
         for ev in done:
             main.wait_event(ev)
+        if err is not None:
+            raise err
+
+    def _train_parallel_cpu(self, todo, log, curr_round: int, workers: int) -> None:
+        """CPU twin of :meth:`_train_parallel` (``engine_opts.client_threads: force``): the same thread pool without
+        streams - used by the CPU test-suite to exercise the thread-safety of the client path."""
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=workers, thread_name_prefix="flpr-client") as pool:
+            futures = [pool.submit(self._process_train, c, log, curr_round, self.container) for c in todo]
+            err = None
+            for f in futures:
+                try:
+                    f.result(timeout=1800)
+                except Exception as ex:  # noqa: BLE001
+                    err = err or ex
         if err is not None:
             raise err
 

@@ -143,3 +143,23 @@ def test_checkpoint_interval_skips_rounds(tmp_path):
     rounds = sorted({int(os.path.basename(f).split("-")[0]) for f in glob.glob(os.path.join(root, "*", "[0-9]*-*.ckpt"))})
     assert rounds == [2, 4], rounds
     assert os.path.exists(os.path.join(root, "client-0", "fedavg_model.ckpt"))
+
+
+@pytest.mark.parametrize("method", ["fedstil", "fedavg", "ewc"])
+def test_client_threads_on_cpu(tmp_path, method):
+    """`parallel: 3` client threads (forced on CPU): the client path shares no mutable state across clients."""
+    from flpr_b200.runtime.experiment import ExperimentStage
+    common = tiny_common(str(tmp_path))
+    common["parallel"] = 3
+    common["defaults"]["exp_opts"].update(comm_rounds=3, online_clients=4, val_interval=100)
+    cfg = tiny_experiment(common, method, n_clients=4)
+    cfg["engine_opts"].update(client_threads="force", val_at_round0=False)
+    with ExperimentStage(common, [cfg], source_factory=tiny_factory()) as stage:
+        log = stage.run_experiment(cfg)
+    data = log.records["data"]
+    assert len(data) == 4
+    for client in data.values():
+        assert len(client) == 3
+        for tasks in client.values():
+            for vals in tasks.values():
+                assert all(v == v and 0.0 <= v < 1e4 for v in vals.values()), vals
