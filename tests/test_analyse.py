@@ -1,0 +1,33 @@
+"""Offline analysis over the experiment-log JSON schema (``analyse/accuracy.py``, ``analyse/forgetting.py``)."""
+import json
+
+from flpr_b200.analyse import load_logs
+from flpr_b200.analyse.accuracy import accuracy_curves, accuracy_on_round, merged_curve
+from flpr_b200.analyse.forgetting import forgetting_curves, forgetting_on_round
+
+
+def _log():
+    data = {}
+    for c in range(2):
+        rounds = {}
+        for r in (0, 10, 20):
+            rounds[str(r)] = {f"task-{c}-{t}": {"val_map": 0.2 + 0.02 * r - 0.05 * t * (r == 20),
+                                                "val_rank_1": 0.3 + 0.02 * r} for t in range(2)}
+        data[f"client-{c}"] = rounds
+    return {"config": {"exp_name": "x"}, "data": data}
+
+
+def test_accuracy_and_forgetting_tables(tmp_path):
+    path = tmp_path / "log.json"
+    path.write_text(json.dumps(_log()))
+    logs = load_logs(str(path))
+    acc = accuracy_on_round(logs, 20, "val_map", verbose=False)
+    assert acc is not None
+    curves = accuracy_curves(logs, "val_map")
+    assert set(curves) == {"client-0", "client-1"} and len(curves["client-0"]["task-0-0"]) == 3
+    merged = merged_curve(logs, "val_rank_1")
+    assert [r for r, _ in merged] == [0, 10, 20] and abs(merged[-1][1] - 0.7) < 1e-9
+    forget = forgetting_on_round(logs, 20, "val_map", verbose=False)
+    assert forget is not None
+    fc = forgetting_curves(logs, "val_map")
+    assert fc[0][0] == 0 and fc[-1][0] == 20 and fc[-1][1] >= 0.0
