@@ -45,6 +45,8 @@ class DeviceAugment:
         self.level = level
         self.mean = torch.tensor(mean, dtype=torch.float32).view(1, 1, 1, 3) * 255.0
         self.inv_std = 1.0 / (torch.tensor(std, dtype=torch.float32).view(1, 1, 1, 3) * 255.0)
+        self.mean01 = torch.tensor(mean, dtype=torch.float32).view(1, 1, 1, 3)
+        self.std = torch.tensor(std, dtype=torch.float32).view(1, 1, 1, 3)
         self.dtype = dtype
         self.scale, self.ratio = scale, ratio
 
@@ -83,7 +85,12 @@ class DeviceAugment:
         dev = u8.device
         if self.mean.device != dev:
             self.mean, self.inv_std = self.mean.to(dev), self.inv_std.to(dev)
-        x = (u8.float() - self.mean) * self.inv_std                       # [B,H,W,3]
+        if dev.type == "cpu":
+            # the rounding sequence of torchvision's ToTensor + Normalize (image_augmentation.py:6-71): the fp32 CPU
+            # path then feeds the network bit-identical inputs to the reference's
+            x = (u8.float().div_(255.0) - self.mean01) / self.std          # [B,H,W,3]
+        else:
+            x = (u8.float() - self.mean) * self.inv_std                       # [B,H,W,3]
         b, h, w, _ = x.shape
         u = torch.rand(7, b, device=dev, generator=generator)
         if self.level != "none":
@@ -103,5 +110,6 @@ class DeviceAugment:
             box = (ys >= top.view(b, 1, 1)) & (ys < (top + eh).view(b, 1, 1)) & \
                   (xs >= left.view(b, 1, 1)) & (xs < (left + ew).view(b, 1, 1)) & sel.view(b, 1, 1)
             x = x.masked_fill(box.unsqueeze(-1), 0.0)
-        # logical NCHW view over NHWC storage == torch.channels_last
-        return x.to(self.dtype).permute(0, 3, 1, 2)
+        # logical NCHW view over NHWC storage == torch.channels_last (CUDA); plain contiguous NCHW on the CPU
+        out = x.to(self.dtype).permute(0, 3, 1, 2)
+        return out if dev.type == "cuda" else out.contiguous()

@@ -21,12 +21,20 @@ import torch
 from ..runtime.modules import ClientModule, ModelModule, OperatorModule, ServerModule
 
 
+def _reprefix(state: Dict[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]:
+    """Re-key a ``net.*`` state dict with ``prefix`` (``"net."`` or ``""``); accepts either form as input."""
+    return {prefix + (k[4:] if k.startswith("net.") else k): v for k, v in state.items()}
+
+
 class FedClient(ClientModule):
     """Client side of the FedAvg-family exchange."""
 
     default_ckpt_name = "fedavg_model"
     upload_key = "incremental_model_params"
     integrated_key = "integrated_model_params"
+    # FedAvg enumerates the ``ModelModule`` wrapper (keys ``net.*``, methods/fedavg.py:232-242); FedProx / FedCurv
+    # enumerate ``model.net`` (bare keys, methods/fedprox.py:321-331, fedcurv.py:395-411)
+    payload_prefix = "net."
 
     def __init__(self, client_name, model, operator, ckpt_root, model_ckpt_name=None, **kwargs):
         super().__init__(client_name, model, operator, ckpt_root, model_ckpt_name, **kwargs)
@@ -52,12 +60,16 @@ class FedClient(ClientModule):
         return self._upload_numel(self.model)
 
     def _named_prefix(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Named views of the upload prefix of a flat buffer, keyed like the reference's payload."""
         a = self.model.arena
         out = {}
         for name, seg in a.segments.items():
             if seg.offset + seg.numel <= flat.numel():
-                out[name] = a.view(flat, name)
+                out[self.payload_prefix + name] = a.view(flat, name)
         return out
+
+    def _full_state(self) -> Dict[str, torch.Tensor]:
+        return _reprefix(self.model.full_state(), self.payload_prefix)
 
     # ---- protocol -----------------------------------------------------------------------------------------------
     def get_incremental_state(self, **kwargs) -> Dict:
@@ -68,7 +80,7 @@ class FedClient(ClientModule):
         return {"train_cnt": self.train_cnt, self.upload_key: self._named_prefix(slot)}
 
     def get_integrated_state(self, **kwargs) -> Dict:
-        return {"train_cnt": self.train_cnt, self.integrated_key: self.model.full_state()}
+        return {"train_cnt": self.train_cnt, self.integrated_key: self._full_state()}
 
     def apply_global(self, flat: torch.Tensor) -> None:
         """Overwrite the upload-prefix of the arena with ``flat`` (the aggregated parameters)."""
@@ -82,13 +94,14 @@ class FedClient(ClientModule):
         if "_flat" in state:
             self.apply_global(state["_flat"])
         else:
-            self.model.arena.from_dict(state[self.upload_key])
+            self.model.arena.from_dict({k[4:] if k.startswith("net.") else k: v
+                                        for k, v in state[self.upload_key].items()})
         self.logger.info("Update model succeed by incremental state from server.")
 
     def update_by_integrated_state(self, state: Dict, **kwargs) -> Any:
         self.train_cnt = self.test_cnt = 0
         self.before_global_update()
-        self.model.load_full_state(state[self.integrated_key])
+        self.model.load_full_state(_reprefix(state[self.integrated_key], "net."))
         self.logger.info("Update model succeed by integrated state from server.")
 
     def before_global_update(self) -> None:
@@ -103,6 +116,7 @@ class FedServer(ServerModule):
 
     upload_key = "incremental_model_params"
     integrated_key = "integrated_model_params"
+    payload_prefix = "net."
 
     def __init__(self, server_name, model, operator, ckpt_root, **kwargs):
         super().__init__(server_name, model, operator, ckpt_root, **kwargs)
@@ -141,7 +155,8 @@ class FedServer(ServerModule):
     def _named_global(self) -> Dict[str, torch.Tensor]:
         a = self.model.arena
         n = self.comm.bufs["glob"].n if self.comm is not None and "glob" in self.comm.bufs else a.numel
-        return {name: a.view(a.master, name) for name, seg in a.segments.items() if seg.offset + seg.numel <= n}
+        return {self.payload_prefix + name: a.view(a.master, name) for name, seg in a.segments.items()
+                if seg.offset + seg.numel <= n}
 
     def get_dispatch_incremental_state(self, client_name: str) -> Dict:
         a = self.model.arena
@@ -149,7 +164,7 @@ class FedServer(ServerModule):
         return {self.upload_key: self._named_global(), "_flat": a.master[:n]}
 
     def get_dispatch_integrated_state(self, client_name: str) -> Dict:
-        return {self.integrated_key: self.model.full_state()}
+        return {self.integrated_key: _reprefix(self.model.full_state(), self.payload_prefix)}
 
 
 def strip_private(state: Optional[Dict]) -> Optional[Dict]:

@@ -57,6 +57,7 @@ class Operator(OperatorModule):
 
 class Client(FedClient):
     default_ckpt_name = "fedcurv_model"
+    payload_prefix = ""
 
     @classmethod
     def declare_buffers(cls, comm, model, token_numel: int = 0) -> None:
@@ -95,6 +96,7 @@ class Client(FedClient):
 
 
 class Server(FedServer):
+    payload_prefix = ""
     def __init__(self, server_name, model, operator, ckpt_root, **kwargs):
         super().__init__(server_name, model, operator, ckpt_root, **kwargs)
         self.have_moments = False

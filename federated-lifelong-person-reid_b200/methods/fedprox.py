@@ -58,6 +58,7 @@ class Operator(OperatorModule):
 
 class Client(FedClient):
     default_ckpt_name = "fedprox_model"
+    payload_prefix = ""
 
     def before_global_update(self) -> None:
         if getattr(self, "reference_compat", True):
@@ -78,4 +79,5 @@ class Client(FedClient):
 
 
 class Server(FedServer):
+    payload_prefix = ""
     pass

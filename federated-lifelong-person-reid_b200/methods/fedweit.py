@@ -188,6 +188,7 @@ class Client(ClientModule):
     def __init__(self, client_name, model, operator, ckpt_root, model_ckpt_name=None, **kwargs):
         super().__init__(client_name, model, operator, ckpt_root, model_ckpt_name, **kwargs)
         self.current_task: Optional[str] = None
+        self._snapshots: Dict[str, Dict] = {}              # task -> model_state() kept when no checkpoint file is current
 
     @classmethod
     def declare_buffers(cls, comm, model, token_numel: int = 0) -> None:
@@ -207,7 +208,8 @@ class Client(ClientModule):
         aw.copy_(self.model.arena.master[:self.model.aw_numel])
         self.comm.client_view("cnt", self.client_id).fill_(float(self.train_cnt))
         a = self.model.arena
-        named = lambda flat, suffix: {f"{n}.{suffix}": a.view(flat, f"{n}.aw")  # noqa: E731
+        # decomposed weights travel reverse-permuted, like everything the reference's layers hold (fedweit.py:785-802)
+        named = lambda flat, suffix: {f"{n}.{suffix}": tensor_reverse_permute(a.view(flat, f"{n}.aw"))  # noqa: E731
                                       for n in self.model.decomposed_names}
         return {"train_cnt": self.train_cnt, "incremental_aw": named(aw, "aw"), "incremental_gw": named(gw, "sw"),
                 "incremental_bn": {}}
@@ -239,6 +241,43 @@ class Client(ClientModule):
 
     def after_epoch(self, output: Dict) -> None:
         self.train_cnt += output["data_count"]
+
+    # ---- one model per task: other tasks are evaluated with the weights saved at the end of *their* last training
+    #      round (``validate`` / ``inference`` start with ``load_model(task_name)``, fedweit.py:918,945) ----------------
+    def after_train(self, task_name, tr_loader, val_loader, output) -> None:
+        if self.store.enabled and not self.store.muted:
+            self._snapshots.pop(task_name, None)           # the checkpoint written right after this call is current
+        else:
+            self._snapshots[task_name] = self.model.model_state()
+
+    def _swap_in(self, task_name: str) -> Optional[Dict]:
+        """Install the weights of another task's checkpoint; returns the state to restore afterwards."""
+        if self.current_task is None or task_name == self.current_task:
+            return None
+        state = self._snapshots.get(task_name)
+        if state is None and self.store.enabled and self.store.exists(self.name, task_name):
+            state = self.load_state(task_name)
+        if state is None:
+            return None                                    # never trained: the resident weights (load_state default)
+        resident = self.model.model_state()
+        self.model.update_model(state)
+        return resident
+
+    def validate(self, task_name, query_loader, gallery_loader, device="cpu", **kwargs):
+        resident = self._swap_in(task_name)
+        try:
+            return super().validate(task_name, query_loader, gallery_loader, device, **kwargs)
+        finally:
+            if resident is not None:
+                self.model.update_model(resident)
+
+    def inference(self, task_name, query_loader, gallery_loader, device="cpu", **kwargs):
+        resident = self._swap_in(task_name)
+        try:
+            return super().inference(task_name, query_loader, gallery_loader, device, **kwargs)
+        finally:
+            if resident is not None:
+                self.model.update_model(resident)
 
 
 class Server(ServerModule):

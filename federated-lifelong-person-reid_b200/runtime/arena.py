@@ -3,8 +3,10 @@
 Every client keeps its trainable state in ONE contiguous fp32 buffer (``master``), a same-shaped gradient buffer that
 autograd accumulates into in place, an optional bf16 compute copy (``shadow``) refreshed by the optimizer kernel, and
 the optimizer moments. Named ``nn.Parameter`` objects are *views* into the arena, so the reference's dict schemas are
-reconstructed only at checkpoint / payload time. Conv weights are laid out OHWI (``channels_last``) so
-the tcgen05 implicit-GEMM kernels read them without any per-step transpose.
+reconstructed only at checkpoint / payload time. On CUDA, conv weights are laid out OHWI
+(``channels_last``) so the tcgen05 implicit-GEMM kernels read them without any per-step transpose; a CPU arena keeps
+the standard OIHW order, which makes the fp32 CPU path run the very same ATen kernels as the reference (the
+whole-experiment golden tests rely on that).
 
 The optimizers implement ``torch.optim.Adam`` / ``torch.optim.SGD`` semantics (``models/__init__.py:18-21``) with the
 continual-learning penalty, FedSTIL L1 term and bf16 refresh fused into the same pass (``csrc/fused_ops.cu``).
@@ -49,7 +51,7 @@ class ParamArena:
         off = 0
         self.prefix_numel = 0
         for name, p in items:
-            cl = p.dim() == 4
+            cl = p.dim() == 4 and self.device.type == "cuda"
             n = p.numel()
             self.segments[name] = Segment(name, off, n, tuple(p.shape), cl)
             self.params[name] = p

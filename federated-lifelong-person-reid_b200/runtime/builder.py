@@ -25,13 +25,33 @@ from .checkpoint import CheckpointStore
 from .modules import ClientModule, ModelModule, ServerModule
 
 
+_INIT_CACHE: Dict[str, Dict] = {}
+
+
+def _initial_state(engine_opts: Dict, role: Optional[str]) -> Optional[Dict[str, torch.Tensor]]:
+    """``engine_opts.init_state``: path of a ``torch.save``d ``{role name: plain net state_dict}`` table (role = server
+    or client name; ``"*"`` = everyone) loaded into the freshly constructed net – the offline stand-in for the
+    reference's ImageNet download (``models/resnet.py:308-310``) and the hook the golden-parity tests use."""
+    path = engine_opts.get("init_state")
+    if not path or role is None:
+        return None
+    if path not in _INIT_CACHE:
+        _INIT_CACHE.clear()
+        _INIT_CACHE[path] = torch.load(path, map_location="cpu", weights_only=False)
+    table = _INIT_CACHE[path]
+    return table.get(role, table.get("*"))
+
+
 def parser_model(method_name: str, model_config: Dict, device: str | torch.device = "cpu",
-                 engine_opts: Optional[Dict] = None) -> ModelModule:
+                 engine_opts: Optional[Dict] = None, role: Optional[str] = None) -> ModelModule:
     engine_opts = engine_opts or {}
     factory_kwargs = {n: p for n, p in model_config.items() if n not in ["name", "fine_tuning"]}
     if method_name == "fedstil-atten" and "num_clients" in engine_opts:
         factory_kwargs.setdefault("num_clients", engine_opts["num_clients"])
     net = nets[model_config["name"]](**factory_kwargs)
+    init = _initial_state(engine_opts, role)
+    if init is not None:
+        net.load_state_dict(init, strict=True)
     if model_config.get("fine_tuning"):
         for p in net.parameters():
             p.requires_grad = False
@@ -79,7 +99,8 @@ def _operator(exp_config: Dict, model: ModelModule):
 def parser_server(exp_config: Dict, common_config: Dict, device="cpu", store: Optional[CheckpointStore] = None,
                   comm=None) -> ServerModule:
     eng = dict(exp_config.get("engine_opts", {}), num_clients=len(exp_config["clients"]))
-    model = parser_model(exp_config["exp_method"], exp_config["model_opts"], device, eng)
+    model = parser_model(exp_config["exp_method"], exp_config["model_opts"], device, eng,
+                         exp_config["server"]["server_name"])
     operator = _operator(exp_config, model)
     kwargs = {n: p for n, p in exp_config["server"].items() if n != "server_name"}
     return methods[exp_config["exp_method"]].Server(
@@ -96,7 +117,8 @@ def parser_clients(exp_config: Dict, common_config: Dict, device="cpu", store: O
     for cid, client_config in enumerate(exp_config["clients"]):
         if cid % world != rank:
             continue
-        model = parser_model(exp_config["exp_method"], exp_config["model_opts"], device, eng)
+        model = parser_model(exp_config["exp_method"], exp_config["model_opts"], device, eng,
+                             client_config["client_name"])
         operator = _operator(exp_config, model)
         pipeline = ReIDTaskPipeline(task_list=client_config["tasks"], task_opts=exp_config["task_opts"],
                                     datasets_dir=common_config["datasets_dir"],

@@ -44,8 +44,8 @@ def test_fedavg_checkpoint_and_payload_schemas(tmp_path):
     assert "net.base.layer4.0.conv1.weight" in model and "net.classifier.weight" in model        # 'net.' prefix
     up = torch.load(os.path.join(root, "client-0", "2-client-0-server.ckpt"), weights_only=False)
     assert set(up) == {"train_cnt", "incremental_model_params"}
-    assert "base.layer4.1.conv2.weight" in up["incremental_model_params"]
-    assert up["incremental_model_params"]["classifier.weight"].shape == (8000, 512)
+    assert "net.base.layer4.1.conv2.weight" in up["incremental_model_params"]          # fedavg.py:232-237
+    assert up["incremental_model_params"]["net.classifier.weight"].shape == (8000, 512)
     down1 = torch.load(os.path.join(root, "server", "1-server-client-0.ckpt"), weights_only=False)
     down2 = torch.load(os.path.join(root, "server", "2-server-client-0.ckpt"), weights_only=False)
     assert set(down1) == {"integrated_model_params"} and set(down2) == {"incremental_model_params"}

@@ -1,0 +1,192 @@
+"""Whole-experiment golden parity: the UNMODIFIED reference (``baseline/_ref``, subprocess) and this engine
+run the same tiny fp32 CPU experiment – same initial weights, same synthetic splits, every split smaller than one batch
+so the reference's shuffling cannot change the arithmetic – and every payload / model checkpoint the reference wrote is
+compared tensor by tensor with the file this engine wrote under the same name."""
+import copy
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from flpr_b200.data.datasets import ArrayReIDDataset
+from flpr_b200.runtime.config import merge_experiment
+from flpr_b200.runtime.experiment import ExperimentStage
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "methods")),
+                                reason="reference is not installed in baseline/_ref")
+
+H, W, CLIENTS, TASKS, ROUNDS = 32, 16, 2, 2, 2
+
+
+def _common(tmp: str):
+    return {"datasets_dir": os.path.join(tmp, "data"), "checkpoints_dir": os.path.join(tmp, "ckpts"),
+            "logs_dir": os.path.join(tmp, "logs"), "parallel": 1, "device": ["cpu"],
+            "defaults": {
+                "random_seed": 7,
+                "exp_opts": {"comm_rounds": ROUNDS, "val_interval": 1, "online_clients": CLIENTS},
+                "model_opts": {"name": "resnet18", "num_classes": 8000, "last_stride": 1, "neck": "bnneck",
+                               "fine_tuning": ["base.layer4", "classifier"]},
+                "criterion_opts": {"name": "cross_entropy", "num_classes": 8000, "epsilon": 0.1},
+                "optimizer_opts": {"name": "sgd", "lr": 0.05, "momentum": 0.9, "weight_decay": 1e-4},
+                "scheduler_opts": {"name": "step_lr", "step_size": 5},
+                "task_opts": {"sustain_rounds": 1, "train_epochs": 2,
+                              "augment_opts": {"level": "none", "img_size": [H, W],
+                                               "norm_mean": [0.485, 0.456, 0.406], "norm_std": [0.229, 0.224, 0.225]},
+                              "loader_opts": {"batch_size": 32, "num_workers": 0, "pin_memory": False,
+                                              "persistent_workers": False, "multiprocessing_context": None}}}}
+
+
+METHOD_OPTS = {
+    "fedstil": dict(atten_default=0.9, lambda_l1=1e-4, lambda_k=8),
+    "fedstil-atten": dict(atten_default=0.5, lambda_l1=1e-5, lambda_k=8),
+    "fedweit": dict(lambda_l1=1e-3, lambda_l2=100.0, lambda_mask=0.0, kb_cnt=2),
+    "fedprox": dict(lambda_l2=1e-2),
+    "fedcurv": dict(lambda_penalty=10.0),
+    "ewc": dict(lambda_penalty=50.0),
+    "mas": dict(lambda_penalty=0.01),
+    "icarl": dict(k=8, n_classes=50),
+}
+
+
+def _experiment(common, method):
+    exp = {"exp_name": f"golden-{method}", "exp_method": method, "server": {"server_name": "server"},
+           "clients": [{"client_name": f"client-{i}", "tasks": [f"task-{i}-{t}" for t in range(TASKS)]}
+                       for i in range(CLIENTS)]}
+    if method in METHOD_OPTS:
+        exp["model_opts"] = dict(common["defaults"]["model_opts"], **METHOD_OPTS[method])
+    if method.startswith("fedstil"):
+        exp["server"].update(distance_calculate_step=1, distance_calculate_decay=0.8)
+        for c in exp["clients"]:
+            c["model_ckpt_name"] = "fedstil_model"
+    return exp
+
+
+def _splits():
+    g = torch.Generator().manual_seed(99)
+    out = {}
+    for c in range(CLIENTS):
+        for t in range(TASKS):
+            off = 10 * (c * TASKS + t)
+            for split, n in (("train", 12), ("query", 4), ("gallery", 12)):
+                u8 = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, generator=g)
+                pids = torch.arange(n) % 4 + off
+                out[(f"task-{c}-{t}", split)] = (u8, pids)
+    return out
+
+
+def _run_reference(tmp_path, method, splits):
+    tmp = str(tmp_path / "ref")
+    os.makedirs(tmp)
+    common = _common(tmp)
+    exp = dict(copy.deepcopy(common["defaults"]))
+    exp.update(_experiment(common, method))
+    inp, outp = os.path.join(tmp, "in.pt"), os.path.join(tmp, "out.pt")
+    torch.save({"common": common, "exp": exp, "rounds": ROUNDS, "splits": splits}, inp)
+    env = dict(os.environ, TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_golden.py"), inp, outp], capture_output=True,
+                       text=True, env=env, timeout=900, cwd=tmp)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return torch.load(outp, weights_only=False)
+
+
+def _run_ours(tmp_path, method, splits, init):
+    tmp = str(tmp_path / "ours")
+    os.makedirs(tmp)
+    common = _common(tmp)
+    init_path = os.path.join(tmp, "init.pt")
+    torch.save(init, init_path)
+    exp = _experiment(common, method)
+    exp["engine_opts"] = {"compute_dtype": "fp32", "init_state": init_path, "val_at_round0": False,
+                          "client_threads": False}
+    cfg = merge_experiment(common, exp)
+
+    def factory(task, split):
+        u8, pids = splits[(task, split)]
+        return ArrayReIDDataset(u8, pids, pin=False)
+
+    with ExperimentStage(common, [cfg], source_factory=factory) as stage:
+        log = stage.run_experiment(cfg)
+    root = os.path.join(common["checkpoints_dir"], cfg["exp_name"])
+    files = {}
+    for dirpath, _, names in os.walk(root):
+        for n in names:
+            if n.endswith(".ckpt"):
+                p = os.path.join(dirpath, n)
+                files[os.path.relpath(p, root)] = torch.load(p, map_location="cpu", weights_only=False)
+    return files, log.records
+
+
+def _compare(path, a, b, atol, rtol, bad, ignore=()):
+    """Recursive comparison of two checkpoint objects (``a`` = reference); mismatches are appended to ``bad``.
+    ``ignore``: dict keys of the reference that this engine deliberately does not materialise."""
+    import numpy as np
+    if isinstance(a, dict):
+        a = {k: v for k, v in a.items() if str(k) not in ignore}
+        if not isinstance(b, dict) or set(map(str, a)) != set(map(str, b)):
+            bad.append((path, "keys", sorted(map(str, a))[:6], sorted(map(str, b))[:6] if isinstance(b, dict) else type(b)))
+            return
+        bk = {str(k): v for k, v in b.items()}
+        for k, v in a.items():
+            _compare(f"{path}/{k}", v, bk[str(k)], atol, rtol, bad, ignore)
+    elif isinstance(a, (list, tuple)):
+        if not isinstance(b, (list, tuple)) or len(a) != len(b):
+            bad.append((path, "len", len(a), len(b) if hasattr(b, "__len__") else type(b)))
+            return
+        for i, (x, y) in enumerate(zip(a, b)):
+            _compare(f"{path}[{i}]", x, y, atol, rtol, bad, ignore)
+    elif isinstance(a, (torch.Tensor, np.ndarray)):
+        ta, tb = torch.as_tensor(a).float(), torch.as_tensor(b).float()
+        if ta.shape != tb.shape:
+            bad.append((path, "shape", tuple(ta.shape), tuple(tb.shape)))
+        elif not torch.allclose(ta, tb, atol=atol, rtol=rtol):
+            # Both sides run the same ATen kernels, but the reference shuffles its (single) batch differently, so
+            # batch-statistic sums round differently; a pre-activation within ~1e-7 of zero then takes the other
+            # ReLU branch (or an |aw - aw0| ~ 0 element the other L1 sub-gradient sign) and a handful of weights move
+            # by up to lr * |grad|. Those isolated elements are tolerated; a systematic difference is not.
+            d = (ta - tb).abs()
+            outliers = float((d > atol + rtol * ta.abs()).float().mean())
+            if float(d.max()) > 10 * atol + rtol * float(ta.abs().max()) or outliers > 0.05:
+                bad.append((path, "value", float(d.max()), float(ta.abs().max()), f"outliers {outliers:.4f}"))
+    elif isinstance(a, (int, float)):
+        if abs(float(a) - float(b)) > atol + rtol * abs(float(a)):
+            bad.append((path, "scalar", a, b))
+    elif a is None:
+        if b is not None:
+            bad.append((path, "none", a, type(b)))
+
+
+def golden(tmp_path, method, atol=2e-5, rtol=1e-4, skip=(), ignore=()):
+    splits = _splits()
+    ref = _run_reference(tmp_path, method, splits)
+    files, log = _run_ours(tmp_path, method, splits, ref["init"])
+    bad = []
+    missing = [f for f in ref["files"] if f not in files]
+    assert not missing, f"files the reference wrote and this engine did not: {missing}"
+    for name, obj in sorted(ref["files"].items()):
+        if any(s in name for s in skip):
+            continue
+        _compare(name, obj, files[name], atol, rtol, bad, ignore)
+    assert not bad, "\n".join(map(str, bad[:20]))
+    # logged metrics (tr_acc / tr_loss / CMC / mAP) of every client, round and task
+    for client, rounds in ref["log"].get("data", {}).items():
+        for rnd, tasks in rounds.items():
+            for task, metrics in tasks.items():
+                mine = log["data"][client][str(rnd)][task]
+                for k, v in metrics.items():
+                    assert abs(float(mine[k]) - float(v)) < 1e-3, (client, rnd, task, k, v, mine[k])
+    return ref, files
+
+
+# FedCurv: the reference materialises every other client's (F_j, p_j) in its dispatch payload and model checkpoint; this
+# engine exchanges three pre-reduced moment buffers instead (methods/fedcurv.py) - everything else is compared.
+FEDCURV_NOT_MATERIALISED = ("other_precision_matrices", "other_clients_integrated_params",
+                            "other_clients_incremental_params", "other_clients_precision_matrices")
+
+
+@pytest.mark.parametrize("method", ["baseline", "ewc", "mas", "fedavg", "fedprox", "fedcurv", "fedweit", "fedstil"])
+def test_experiment_matches_reference(tmp_path, method):
+    golden(tmp_path, method, ignore=FEDCURV_NOT_MATERIALISED if method == "fedcurv" else ())
