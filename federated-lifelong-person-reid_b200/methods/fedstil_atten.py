@@ -54,8 +54,7 @@ class Model(base.Model):
         for lname in self.adaptive_names:
             mod = self.net.get_submodule(lname)
             comp = _Compose(mod.weight, self.k_max, self.atten_default)
-            with torch.no_grad():                      # aw = (1 - a) * w  -> initial theta == w
-                mod.weight.mul_(1.0 - self.atten_default)
+            # registration stores ``right_inverse(w) = w - a * w`` as the trainable tensor: aw = (1 - a) * w, theta == w
             parametrize.register_parametrization(mod, "weight", comp, unsafe=True)
             comp.aw0.copy_(mod.parametrizations.weight.original.detach())
             self.composers[lname] = comp
@@ -106,6 +105,18 @@ class Model(base.Model):
                 comp.atten[:k_cur] = self.atten_default
                 comp.atten0.copy_(comp.atten)
                 comp.aw0.copy_(self.net.get_submodule(lname).parametrizations.weight.original)
+
+    def init_training_weights(self) -> None:
+        """``AdaptiveLayer.init_training_weights()`` after a dispatch (``fedstil_atten.py:53-84``): attention back to
+        ``atten_default`` over the ``K`` stacked weights, ``aw`` kept, L1 anchors re-taken."""
+        with torch.no_grad():
+            for lname, comp in self.composers.items():
+                comp.atten.zero_()
+                comp.atten[:comp.k_cur] = self.atten_default
+                comp.atten0.copy_(comp.atten)
+                comp.aw0.copy_(self.net.get_submodule(lname).parametrizations.weight.original)
+        if self.arena is not None:
+            self.arena.refresh_shadow()
 
     def model_state(self, copy: bool = True) -> Dict:
         gw, gwa, aw, ab = {}, {}, {}, {}
@@ -158,6 +169,9 @@ class Operator(base.Operator):
     def compute_loss(self, model: Model, score, feature, target) -> torch.Tensor:
         return super().compute_loss(model, score, feature, target) + model.lambda_l1 * model.sparseness()
 
+    def _ce_stats_ok(self, model: Model) -> bool:
+        return False          # the reported loss includes the L1 term (fedstil_atten.py:650-666): accumulate the sum itself
+
 
 class Client(base.Client):
     def get_incremental_state(self, **kwargs) -> Dict:
@@ -182,6 +196,11 @@ class Client(base.Client):
         self.model.update_model({"pre_trained_params": state.get("integrated_pre_trained_params") or {}})
         if state.get("_stack") is not None:
             self.model.set_global_stack(state["_stack"], state["_k"])
+        else:
+            # nothing uploaded yet: the server's own [..., 1] global weight becomes this client's (fedstil_atten.py:
+            # 1145-1157,919-934) - theta = atten * gw_server + aw_client, NOT the client's own initial weights
+            self.model.update_model({"global_weight": state["integrated_global_weight"]})
+            self.model.init_training_weights()
         self.logger.info("Update model succeed by integrated state from server.")
 
 

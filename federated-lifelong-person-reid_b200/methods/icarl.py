@@ -9,14 +9,17 @@
 
 Device-resident differences: exemplars are a bank of unique images + an ordered index list; herding is batched on the
 GPU; growing the classifier re-materialises the parameter arena (the optimizer state is wiped after every ``train()``
-anyway). Reference quirk *not* reproduced: its distillation pass pairs a reshuffled exemplar loader with logits
-recorded in a different shuffle order (``icarl.py:219-223``); here logits and exemplars stay aligned.
+anyway). Reference quirk: its distillation pass pairs a reshuffled exemplar loader with logits recorded in a
+different shuffle order (``icarl.py:86-95,219-223``), i.e. every exemplar is distilled towards the recorded logits of a
+*random* exemplar. ``reference_compat`` (default) reproduces that pairing with two independent permutations; with
+``reference_compat: false`` logits and exemplars stay aligned (textbook iCaRL).
 """
 from __future__ import annotations
 
 import math
 from typing import Any, Dict, List, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -129,8 +132,21 @@ class Model(ModelModule):
     # ---- checkpoint schema {'net_params', 'examplars'} (icarl.py:178-193) ---------------------------------------------
     def model_state(self, *args, **kwargs) -> Dict:
         net = {k: v.detach().clone(memory_format=torch.contiguous_format) for k, v in self.net.state_dict().items()}
-        ex = {int(p): {"bank": e["bank"], "order": list(e["order"])} for p, e in self.examplars.items()}
-        return {"net_params": net, "examplars": ex}
+        return {"net_params": net, "examplars": self.examplars_state()}
+
+    def examplars_state(self, max_bytes: int = 1 << 30) -> Dict:
+        """``{np.int64 pid: [(ndarray image, pid), ...]}`` – the reference's exemplar memory (``icarl.py:135-139``).
+        Beyond ``max_bytes`` of fp32 images (the reference writes ~3 GB per client and round at ``k = 8000``,
+        256x128) the compact ``{pid: {"bank", "order"}}`` form is written instead; both forms load."""
+        n = sum(len(e["order"]) for e in self.examplars.values())
+        per = next((e["bank"][0].numel() * 4 for e in self.examplars.values() if len(e["bank"])), 0)
+        if n * per > max_bytes:
+            return {int(p): {"bank": e["bank"], "order": list(e["order"])} for p, e in self.examplars.items()}
+        out = {}
+        for pid, e in self.examplars.items():
+            bank = e["bank"].float().cpu().numpy()
+            out[np.int64(pid)] = [(bank[i], np.int64(pid)) for i in e["order"]]
+        return out
 
     def update_model(self, params_state: Dict) -> None:
         if "net_params" in params_state:
@@ -146,8 +162,14 @@ class Model(ModelModule):
             if self.arena is not None:
                 self.arena.refresh_shadow()
         if "examplars" in params_state:
-            self.examplars = {int(p): {"bank": e["bank"].to(self.device), "order": list(e["order"])}
-                              for p, e in params_state["examplars"].items() if isinstance(e, dict)}
+            dt = torch.bfloat16 if self.compute_dtype == torch.bfloat16 else torch.float32
+            self.examplars = {}
+            for p, e in params_state["examplars"].items():
+                if isinstance(e, dict):
+                    self.examplars[int(p)] = {"bank": e["bank"].to(self.device), "order": list(e["order"])}
+                elif len(e):                                       # reference form: [(image ndarray, pid), ...]
+                    bank = torch.stack([torch.as_tensor(img) for img, _ in e]).to(self.device, dt)
+                    self.examplars[int(p)] = {"bank": bank, "order": list(range(len(e)))}
 
 
 class Operator(OperatorModule):
@@ -175,10 +197,12 @@ class Operator(OperatorModule):
             n_ex = ex[0].shape[0]
             prev = model.previous_logits
             perm = torch.randperm(min(n_ex, prev.shape[0]), device=device)
+            perm_logits = torch.randperm(len(perm), device=device) if getattr(model, "misaligned_distill", True) \
+                else perm
             for s in range(0, len(perm), bs):
                 idx = perm[s:s + bs]
                 data, target = model.prepare_input(ex[0][idx].float()), ex[1][idx]
-                pl = prev[idx]
+                pl = prev[perm_logits[s:s + bs]]
                 pc = pl.shape[1]
                 self.optimizer.zero_grad()
                 with model.autocast():
@@ -238,12 +262,17 @@ class Client(ClientModule):
     def __init__(self, client_name, model, operator, ckpt_root, model_ckpt_name=None, **kwargs):
         super().__init__(client_name, model, operator, ckpt_root, model_ckpt_name, **kwargs)
         self.model.operator = operator
+        self.model.misaligned_distill = bool(getattr(self, "reference_compat", True))
         if not self.model_ckpt_name:
             self.model_ckpt_name = "icarl_model"
 
     def update_by_integrated_state(self, state: Dict, **kwargs) -> Any:
+        # base ``update_model`` merge (modules/client.py:72-76): every ``net.*`` entry, the n_classes-wide head included
+        # (server and client heads have the configured width at first contact; other widths are skipped by shape)
         sd = {k[4:] if k.startswith("net.") else k: v for k, v in state["model_params"].items()}
-        sd = {k: v for k, v in sd.items() if not k.startswith("classifier.")}   # server head has another width
+        w = sd.get("classifier.weight")
+        if w is not None and w.shape[0] != self.model.n_classes:
+            sd = {k: v for k, v in sd.items() if not k.startswith("classifier.")}
         self.model.update_model({"net_params": sd})
         self.logger.info("Update model succeed by integrated state from server.")
 
@@ -262,4 +291,9 @@ class Client(ClientModule):
 
 class Server(ServerModule):
     def get_dispatch_integrated_state(self, client_name: str) -> Dict:
-        return {"model_params": self.model.full_state()}
+        sd = self.model.full_state()
+        # the reference's Model registers ``features_extractor = net.base`` as a second sub-module, so its state_dict
+        # lists the trunk twice (``icarl.py:59,569-573``); same tensors, alias keys
+        sd.update({"features_extractor." + k[len("net.base."):]: v for k, v in list(sd.items())
+                   if k.startswith("net.base.")})
+        return {"model_params": sd}

@@ -42,6 +42,14 @@ def _initial_state(engine_opts: Dict, role: Optional[str]) -> Optional[Dict[str,
     return table.get(role, table.get("*"))
 
 
+def _load_matching(net: nn.Module, state: Dict[str, torch.Tensor]) -> None:
+    own = net.state_dict()
+    with torch.no_grad():
+        for k, v in state.items():
+            if k in own and own[k].shape == v.shape:
+                own[k].copy_(v)
+
+
 def parser_model(method_name: str, model_config: Dict, device: str | torch.device = "cpu",
                  engine_opts: Optional[Dict] = None, role: Optional[str] = None) -> ModelModule:
     engine_opts = engine_opts or {}
@@ -51,7 +59,7 @@ def parser_model(method_name: str, model_config: Dict, device: str | torch.devic
     net = nets[model_config["name"]](**factory_kwargs)
     init = _initial_state(engine_opts, role)
     if init is not None:
-        net.load_state_dict(init, strict=True)
+        _load_matching(net, init)
     if model_config.get("fine_tuning"):
         for p in net.parameters():
             p.requires_grad = False
@@ -61,6 +69,8 @@ def parser_model(method_name: str, model_config: Dict, device: str | torch.devic
         # the reference builds the BNNeck bias frozen and the blanket un-freeze does not touch it unless listed
     module = methods[method_name]
     model = module.Model(net=net, **factory_kwargs) if hasattr(module, "Model") else ModelModule(net)
+    if init is not None:
+        _load_matching(model.net, init)          # layers the method wrapper re-created (iCaRL's classifier)
     model.materialize(device, engine_opts.get("compute_dtype", "bf16"), model_config.get("fine_tuning"))
     return model
 

@@ -91,6 +91,10 @@ def main():
     init = {exp["server"]["server_name"]: captured[0]}
     for c, sd in zip(clients, captured[1:]):
         init[c.client_name] = sd
+    if exp["exp_method"] == "icarl":       # its Model wrapper swaps in a freshly initialised n_classes-wide classifier
+        snap = lambda m: {k: v.detach().clone() for k, v in m.net.state_dict().items()}  # noqa: E731
+        init = {exp["server"]["server_name"]: snap(server.model), **{c.client_name: snap(c.model) for c in clients}}
+    for c in clients:
         c.task_pipeline = _MemoryPipeline(c.task_pipeline.task_list, exp["task_opts"], make_split, DataLoader, _Split)
     stage = ExperimentStage(common, [exp])
     log = ExperimentLog(os.path.join(common["logs_dir"], "golden.json"))
