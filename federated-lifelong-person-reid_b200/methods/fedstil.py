@@ -257,7 +257,21 @@ class Model(ModelModule):
             ids.append(gen["pids"].repeat_interleave(k))
         if not ps:
             return None
-        return torch.cat(ps), torch.cat(ids), torch.cat(cs)
+        ids_cat, cs_cat = torch.cat(ids), torch.cat(cs)
+        if getattr(self, "relabel_by_class_index", False) and len(ids) > 1:
+            # Reference quirk (reference_compat): the rehearsal set is a ``ReIDImageDataset(source=examplars)`` whose
+            # dict branch keeps ONE person id per *class index* - ``classes[class_id] = person_id``, last insertion
+            # wins (datasets_loader.py:21-27,36-38). Class indices restart at 0 in every task folder, so as soon as
+            # exemplars of two tasks coexist, the older task's exemplars are served (trained, and re-herded) under the
+            # person ids of the newest task that has the same class index.
+            lut = getattr(self, "_cls_lut", None)
+            size = max(int(getattr(self.net, "num_classes", 0) or 0), 1 << 16)
+            if lut is None or lut.numel() != size or lut.device != ids_cat.device:
+                lut = self._cls_lut = torch.zeros(size, dtype=torch.long, device=ids_cat.device)
+            for pid_v, cls_v in zip(ids, cs):                   # generation order == insertion order of the dict
+                lut[cls_v] = pid_v
+            ids_cat = lut[cs_cat]
+        return torch.cat(ps), ids_cat, cs_cat
 
     def examplars_compact(self) -> Dict:
         """Compact exemplar memory; the checkpoint writer process expands it to the reference schema."""
@@ -447,6 +461,7 @@ class Operator(OperatorModule):
         n = protos.shape[0]
         bs = dataloader.batch_size
         model.train()
+        self.begin_epoch()
         model.install(self.optimizer)
         self.optimizer.stats.zero_()
         perm = torch.randperm(n, device=device, generator=model.rng if device.type == "cuda" else None)
@@ -485,6 +500,8 @@ class Client(ClientModule):
         self.current_task = None
         self.task_token: Optional[torch.Tensor] = None
         self._task_tokens: List[torch.Tensor] = []
+        self.model.relabel_by_class_index = bool(getattr(self, "reference_compat", True))
+        self.operator.reset_lr_each_epoch = bool(getattr(self, "reference_compat", True))
 
     # ---- symmetric buffers ---------------------------------------------------------------------------------------------
     @classmethod

@@ -189,6 +189,7 @@ class Client(ClientModule):
         super().__init__(client_name, model, operator, ckpt_root, model_ckpt_name, **kwargs)
         self.current_task: Optional[str] = None
         self._snapshots: Dict[str, Dict] = {}              # task -> model_state() kept when no checkpoint file is current
+        self.operator.reset_lr_each_epoch = bool(getattr(self, "reference_compat", True))
 
     @classmethod
     def declare_buffers(cls, comm, model, token_numel: int = 0) -> None:

@@ -190,6 +190,7 @@ class Operator(OperatorModule):
         device = model.device
         model.train()
         self.rebind(model)
+        self.begin_epoch()
         bs = dataloader.batch_size
         ex = model.examplar_tensors()
         # (1) distillation pass on the exemplars
@@ -263,6 +264,7 @@ class Client(ClientModule):
         super().__init__(client_name, model, operator, ckpt_root, model_ckpt_name, **kwargs)
         self.model.operator = operator
         self.model.misaligned_distill = bool(getattr(self, "reference_compat", True))
+        self.operator.reset_lr_each_epoch = bool(getattr(self, "reference_compat", True))
         if not self.model_ckpt_name:
             self.model_ckpt_name = "icarl_model"
 

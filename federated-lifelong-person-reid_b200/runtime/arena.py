@@ -174,6 +174,12 @@ class ArenaOptimizer:
         self.lr = self.defaults["lr"]
         self.sync_hyper()
 
+    def restore_default_lr(self) -> None:
+        """Back to the configured lr (no device traffic unless a scheduler changed it)."""
+        if self.lr != self.defaults["lr"]:
+            self.lr = self.defaults["lr"]
+            self.sync_hyper()
+
     def sync_hyper(self) -> None:
         """Push the host-side lr / step counter to the device copy (call after changing ``lr``)."""
         if self.hyper is not None:

@@ -169,6 +169,16 @@ class OperatorModule:
         with model.autocast():
             return model.forward(data)
 
+    # Reference quirk (reference_compat): the Operators of fedstil / fedstil-atten / fedweit / icarl rebuild
+    # ``optimizer.param_groups`` from ``optimizer.defaults`` at the top of every ``invoke_train``
+    # (``set_optimizer_parameters``, e.g. fedstil.py:553-556,631), so whatever StepLR did to the lr is undone before
+    # the next epoch - those methods always step with the configured lr. Their clients set this flag.
+    reset_lr_each_epoch = False
+
+    def begin_epoch(self) -> None:
+        if self.reset_lr_each_epoch and self.optimizer is not None:
+            self.optimizer.restore_default_lr()
+
     # ---- loops --------------------------------------------------------------------------------------------------
     def _invoke_train(self, model: ModelModule, data, target, **kwargs) -> Dict:
         score, feature = self.forward_train(model, data)
@@ -177,6 +187,7 @@ class OperatorModule:
     def invoke_train(self, model: ModelModule, dataloader, **kwargs) -> Dict:
         device = model.device
         model.train()
+        self.begin_epoch()
         acc = torch.zeros(2, dtype=torch.float64, device=device)       # [loss sum, top-1 hits] – stays on device
         batch_cnt = data_cnt = 0
         if self.optimizer.stats is not None:

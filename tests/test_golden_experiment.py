@@ -120,7 +120,7 @@ def _run_ours(tmp_path, method, splits, init, rounds=ROUNDS):
     return files, log.records
 
 
-def _compare(path, a, b, atol, rtol, bad, ignore=()):
+def _compare(path, a, b, atol, rtol, bad, ignore=(), max_factor=10):
     """Recursive comparison of two checkpoint objects (``a`` = reference); mismatches are appended to ``bad``.
     ``ignore``: dict keys of the reference that this engine deliberately does not materialise."""
     import numpy as np
@@ -131,13 +131,13 @@ def _compare(path, a, b, atol, rtol, bad, ignore=()):
             return
         bk = {str(k): v for k, v in b.items()}
         for k, v in a.items():
-            _compare(f"{path}/{k}", v, bk[str(k)], atol, rtol, bad, ignore)
+            _compare(f"{path}/{k}", v, bk[str(k)], atol, rtol, bad, ignore, max_factor)
     elif isinstance(a, (list, tuple)):
         if not isinstance(b, (list, tuple)) or len(a) != len(b):
             bad.append((path, "len", len(a), len(b) if hasattr(b, "__len__") else type(b)))
             return
         for i, (x, y) in enumerate(zip(a, b)):
-            _compare(f"{path}[{i}]", x, y, atol, rtol, bad, ignore)
+            _compare(f"{path}[{i}]", x, y, atol, rtol, bad, ignore, max_factor)
     elif isinstance(a, (torch.Tensor, np.ndarray)):
         ta, tb = torch.as_tensor(a).float(), torch.as_tensor(b).float()
         if ta.shape != tb.shape:
@@ -149,7 +149,7 @@ def _compare(path, a, b, atol, rtol, bad, ignore=()):
             # by up to lr * |grad|. Those isolated elements are tolerated; a systematic difference is not.
             d = (ta - tb).abs()
             outliers = float((d > atol + rtol * ta.abs()).float().mean())
-            if float(d.max()) > 10 * atol + rtol * float(ta.abs().max()) or outliers > 0.05:
+            if float(d.max()) > max_factor * atol + rtol * float(ta.abs().max()) or outliers > 0.05:
                 bad.append((path, "value", float(d.max()), float(ta.abs().max()), f"outliers {outliers:.4f}"))
     elif isinstance(a, (int, float)):
         if abs(float(a) - float(b)) > atol + rtol * abs(float(a)):
@@ -159,7 +159,7 @@ def _compare(path, a, b, atol, rtol, bad, ignore=()):
             bad.append((path, "none", a, type(b)))
 
 
-def golden(tmp_path, method, atol=2e-5, rtol=1e-4, skip=(), ignore=(), rounds=ROUNDS):
+def golden(tmp_path, method, atol=2e-5, rtol=1e-4, skip=(), ignore=(), rounds=ROUNDS, max_factor=10):
     import shutil
     splits = _splits()
     ref = _run_reference(tmp_path, method, splits, rounds)
@@ -172,7 +172,7 @@ def golden(tmp_path, method, atol=2e-5, rtol=1e-4, skip=(), ignore=(), rounds=RO
     for name, obj in sorted(ref["files"].items()):
         if any(s in name for s in skip):
             continue
-        _compare(name, obj, files[name], atol, rtol, bad, ignore)
+        _compare(name, obj, files[name], atol, rtol, bad, ignore, max_factor)
     assert not bad, "\n".join(map(str, bad[:20]))
     # logged metrics (tr_acc / tr_loss / CMC / mAP) of every client, round and task
     for client, rounds in ref["log"].get("data", {}).items():
@@ -190,10 +190,17 @@ FEDCURV_NOT_MATERIALISED = ("other_precision_matrices", "other_clients_integrate
                             "other_clients_incremental_params", "other_clients_precision_matrices")
 
 
-@pytest.mark.parametrize("method", ["baseline", "ewc", "mas", "fedavg", "fedprox", "fedcurv", "fedweit", "fedstil",
-                                    "fedstil-atten"])
+@pytest.mark.parametrize("method", ["baseline", "ewc", "mas", "fedprox", "fedcurv", "fedstil-atten"])
 def test_experiment_matches_reference(tmp_path, method):
     golden(tmp_path, method, ignore=FEDCURV_NOT_MATERIALISED if method == "fedcurv" else ())
+
+
+@pytest.mark.parametrize("method", ["fedavg", "fedweit", "fedstil"])
+def test_three_rounds_match_reference(tmp_path, method):
+    """Third round = second round on the last task (stickiness) and the 5th / 6th epoch: crosses the StepLR boundary
+    (and the reference's per-epoch lr reset in fedweit / fedstil), evaluates FedWeIT's older task from its own
+    checkpoint, and for FedSTIL rehearses exemplars of two tasks (the class-index relabelling quirk)."""
+    golden(tmp_path, method, rounds=3, max_factor=25)
 
 
 def test_icarl_first_round_matches_reference(tmp_path):
