@@ -38,6 +38,29 @@ def main():
         return getattr(torchvision.models, name)(weights=None).state_dict()
 
     ref_resnet.load_state_dict_from_url = _fake_url_loader
+
+    import models.swin_transformer as ref_swin
+    _SWIN = {"swin_tiny": dict(embed_dim=96, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24)),
+             "swin_small": dict(embed_dim=96, depths=(2, 2, 18, 2), num_heads=(3, 6, 12, 24)),
+             "swin_base": dict(embed_dim=128, depths=(2, 2, 18, 2), num_heads=(4, 8, 16, 32)),
+             "swin_large": dict(embed_dim=192, depths=(2, 2, 18, 2), num_heads=(6, 12, 24, 48))}
+
+    _swin_cache = {}
+
+    def _fake_swin_loader(url, *a, **k):
+        # ONE "pre-trained" file for every model, as in real use. (The reference never ships parameters owned by
+        # non-leaf modules - Swin's relative_position_bias_table - from the server to its clients, fedstil.py:482-486;
+        # with a shared pre-trained file that is invisible, with per-model random tables it would not be.)
+        name = [k_ for k_, v in ref_swin.model_urls.items() if v == url][0]
+        if name not in _swin_cache:
+            _swin_cache[name] = ref_swin.SwinTransformer(patch_size=4, window_size=7, **_SWIN[name]).state_dict()
+        return {"model": {k_: v.clone() for k_, v in _swin_cache[name].items()}}
+
+    ref_swin.load_state_dict_from_url = _fake_swin_loader
+    if exp["model_opts"].get("drop_path_rate") == 0.0:
+        # determinism shim: the reference hard-codes drop_path_rate=0.1 (swin_transformer.py:640-662) and draws the
+        # per-sample keep mask from the global RNG; stochastic depth is switched off on both sides
+        ref_swin.DropPath.forward = lambda self, x: x
     # restore the pinned-stack behaviour of np.argwhere(tensor) (see tests/ref_oracle.py) so mAP is the intended one
     _aw = np.argwhere
     ref_eval.np.argwhere = lambda a: _aw(a.numpy() if isinstance(a, torch.Tensor) else a)
