@@ -241,6 +241,13 @@ def test_partial_participation_fedstil_matches_reference(tmp_path):
     golden(tmp_path, "fedstil", rounds=3, online=1, max_factor=100)
 
 
+def test_fedstil_on_resnet50_first_round_matches_reference(tmp_path):
+    """The headline backbone (``configs/backbone/experiment_fedstil_res50.yaml``): bottleneck blocks, eleven adaptive
+    layers, 1024-channel prototypes. One round - with nine ReLUs per sample position in ``layer4`` the branch flips
+    of a second round already touch ~5 % of the conv weights (by <= 6e-4)."""
+    golden(tmp_path, "fedstil@resnet50", rounds=1)
+
+
 def test_fedstil_on_swin_matches_reference(tmp_path):
     """FedSTIL over Swin-T (``configs/backbone/experiment_fedstil_swin.yaml``: ``base.layers.3`` + classifier, nine
     adaptive layers with biases, LayerNorm / relative-position tables trained locally, 49 x 768 token maps)."""
