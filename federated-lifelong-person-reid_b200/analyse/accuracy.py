@@ -1,7 +1,7 @@
 """Accuracy analysis (``analyse/accuracy.py``): per-round averages and per-job / per-task / merged curves."""
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 
 def _plt():

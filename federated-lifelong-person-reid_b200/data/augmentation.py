@@ -9,7 +9,7 @@ Two implementations per level:
 from __future__ import annotations
 
 import math
-from typing import Dict, Sequence, Tuple
+from typing import Dict, Sequence
 
 import torch
 

@@ -10,7 +10,7 @@ from typing import Any, Dict
 
 import torch
 
-from ..runtime.modules import ClientModule, ModelModule, OperatorModule, ServerModule
+from ..runtime.modules import ClientModule, OperatorModule, ServerModule
 
 
 class Operator(OperatorModule):

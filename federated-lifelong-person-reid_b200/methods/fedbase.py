@@ -18,7 +18,7 @@ from typing import Any, Dict, List, Optional
 
 import torch
 
-from ..runtime.modules import ClientModule, ModelModule, OperatorModule, ServerModule
+from ..runtime.modules import ClientModule, ModelModule, ServerModule
 
 
 def _reprefix(state: Dict[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]:

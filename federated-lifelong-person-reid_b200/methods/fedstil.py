@@ -32,7 +32,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..criterions import kl_distance
-from ..runtime.modules import ClientModule, ModelModule, OperatorModule, ServerModule, _bind_loader
+from ..runtime.modules import ClientModule, ModelModule, OperatorModule, ServerModule
 
 
 class Model(ModelModule):

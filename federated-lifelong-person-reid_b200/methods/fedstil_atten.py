@@ -14,7 +14,7 @@ so the backbone code (including the tensor-core head) is unchanged and autograd 
 """
 from __future__ import annotations
 
-from typing import Any, Dict, List, Optional, Sequence
+from typing import Any, Dict, Optional, Sequence
 
 import torch
 import torch.nn as nn

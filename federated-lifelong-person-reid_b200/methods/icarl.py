@@ -17,7 +17,7 @@ different shuffle order (``icarl.py:86-95,219-223``), i.e. every exemplar is dis
 from __future__ import annotations
 
 import math
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -25,7 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..runtime.arena import ArenaOptimizer
-from ..runtime.modules import ClientModule, ModelModule, OperatorModule, ServerModule, _bind_loader
+from ..runtime.modules import ClientModule, ModelModule, OperatorModule, ServerModule
 from ..utils.misc import get_one_hot
 from .fedstil import group_matrix, herding_select_batched
 

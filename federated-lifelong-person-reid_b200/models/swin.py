@@ -15,7 +15,7 @@ permute pair; the network exposes the same *frozen trunk | trainable head* split
 from __future__ import annotations
 
 import os
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn

@@ -3,7 +3,7 @@ continual-learning penalty folded in, importance accumulation, label-smoothing C
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 import torch.nn.functional as F

@@ -4,7 +4,7 @@ warm-up), then captured once and replayed with its inputs copied into static buf
 from __future__ import annotations
 
 import threading
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, Sequence, Tuple
 
 import torch
 

@@ -12,7 +12,7 @@ server is a *role* replicated on every rank whose aggregation runs as collective
 from __future__ import annotations
 
 import contextlib
-from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple, Union
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 
 import torch
 import torch.nn as nn

@@ -19,7 +19,7 @@ from __future__ import annotations
 
 import os
 import random
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict
 
 import torch
 
