@@ -48,6 +48,8 @@ class Model(ModelModule):
         self.ids: set = set()
         self.ex_gens: List[Dict[str, Any]] = []          # exemplar memory (see "exemplar memory" below)
         self.G: Optional[torch.Tensor] = None
+        self.train_l1_anchor = False                     # engine_opts.train_l1_anchor (see ArenaOptimizer._anchor_step)
+        self.anchor: Optional[torch.Tensor] = None
 
     # ---- adaptive layers: leaves of type Linear/Conv2d whose parameters are all trainable (fedstil.py:290-347) ------
     def _find_adaptive_layers(self) -> List[str]:
@@ -89,8 +91,16 @@ class Model(ModelModule):
 
     def install(self, optimizer) -> None:
         optimizer.G, optimizer.lam1, optimizer.atten = self.G, self.lambda_l1, self.atten_default
+        if self.train_l1_anchor and self.anchor is None:
+            self.anchor = self.G.clone()
+        optimizer.anchor = self.anchor
         if optimizer.stats is None:
             optimizer.stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+
+    def reset_anchor(self) -> None:
+        """``init_training_weights()`` re-takes the L1 anchors after every dispatch (fedstil.py:71-76,879-892)."""
+        if self.anchor is not None:
+            self.anchor.copy_(self.G)
 
     def set_global_weight(self, flat: torch.Tensor) -> None:
         """New ``global_weight`` + ``init_training_weights()``: theta <- G (A = (1-a) G), bf16 copy refreshed."""
@@ -98,6 +108,7 @@ class Model(ModelModule):
         self.G.copy_(flat[:n])
         self.arena.master[:n].copy_(self.G)
         self.arena.refresh_shadow()
+        self.reset_anchor()
 
     @property
     def m(self) -> int:
@@ -502,6 +513,7 @@ class Client(ClientModule):
         self._task_tokens: List[torch.Tensor] = []
         self.model.relabel_by_class_index = bool(getattr(self, "reference_compat", True))
         self.operator.reset_lr_each_epoch = bool(getattr(self, "reference_compat", True))
+        self.model.train_l1_anchor = bool(getattr(self, "train_l1_anchor", False)) and hasattr(self.model, "G")
 
     # ---- symmetric buffers ---------------------------------------------------------------------------------------------
     @classmethod
@@ -552,7 +564,7 @@ class Client(ClientModule):
 
     def update_by_incremental_state(self, state: Dict, **kwargs) -> Any:
         if state.get("_delivered"):
-            pass                                                # the mix kernel already wrote G / theta / bf16 copy
+            self.model.reset_anchor()                           # the mix kernel already wrote G / theta / bf16 copy
         else:
             self.model.update_model({"global_weight": state["incremental_shared_params"]})
             self.model.set_global_weight(self.model.G)

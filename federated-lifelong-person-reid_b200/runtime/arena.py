@@ -152,6 +152,10 @@ class ArenaOptimizer:
         self.lam1 = 0.0
         self.atten = 0.0
         self.stats: Optional[torch.Tensor] = None
+        # FedSTIL ``train_l1_anchor`` (off by default): the L1 anchor is a trained tensor with its own moments
+        self.anchor: Optional[torch.Tensor] = None
+        self.anchor_m: Optional[torch.Tensor] = None
+        self.anchor_v: Optional[torch.Tensor] = None
         # device-resident [lr, step] (CUDA only): a captured CUDA graph of the train step stays valid across steps
         self.hyper: Optional[torch.Tensor] = None
         if arena.device.type == "cuda":
@@ -170,6 +174,9 @@ class ArenaOptimizer:
             self.m.zero_()
         if self.v is not None:
             self.v.zero_()
+        for buf in (self.anchor_m, self.anchor_v):
+            if buf is not None:
+                buf.zero_()
         self.step_count = 0
         self.lr = self.defaults["lr"]
         self.sync_hyper()
@@ -207,11 +214,65 @@ class ArenaOptimizer:
                 p_bf16=None if a.shadow is None else a.shadow[sl], stats=self.stats, hyper=self.hyper)
 
         n_g = self.G.numel() if self.G is not None else 0
+        lam1, l1_before = self.lam1, None
+        if self.anchor is not None and n_g and lam1 != 0.0:
+            l1_before = self._anchor_step(n_g)
+            self.lam1 = 0.0                # the L1 sub-gradient is already in ``grad``; G still anchors the weight decay
         if 0 < n_g < a.numel:          # FedSTIL: only the adaptive-weight prefix carries the L1 / attention terms
             launch(0, n_g, True)
             launch(n_g, a.numel, False)
         else:
             launch(0, a.numel, n_g > 0)
+        if l1_before is not None:
+            self.lam1 = lam1
+            if self.stats is not None:
+                self.stats[1:2].copy_(l1_before)
+
+    def _anchor_step(self, n: int) -> Optional[torch.Tensor]:
+        """Reference quirk, opt-in (``engine_opts.train_l1_anchor``): FedSTIL's ``initial_adaptive_weight`` is a bare
+        ``Parameter`` whose ``requires_grad`` is never cleared, so the reference's optimizer trains the L1 *anchor*
+        ``aw0`` as well - its gradient is ``-lam1 * sign(aw - aw0) + wd * aw0``. Written with tensor ops
+        only (lr / step come from the device-resident ``hyper`` on CUDA) so it can sit inside a captured step; it is
+        not part of the fused kernel yet, hence off by default. ``anchor`` holds ``theta0 = atten * G + aw0``.
+        Returns what ``stats[1]`` must read after the step: previous value + ``sum |aw - aw0|`` (for loss reporting)."""
+        a, d = self.arena, self.defaults
+        with torch.no_grad():
+            p, g, anc = a.master[:n], a.grad[:n], self.anchor
+            diff = p - anc
+            l1 = None
+            if self.stats is not None:
+                l1 = self.stats[1:2] + diff.abs().sum()
+            if self.hyper is not None:
+                lr, step = self.hyper[0], self.hyper[1]
+            else:
+                lr, step = self.lr, float(self.step_count)
+            # Where the loss gradient is exactly zero (inputs behind a dead ReLU) weight and anchor receive the same
+            # update and stay *identical* in the reference, sign(0) = 0. Two differently fused update formulas cannot
+            # promise bit-identical results, so differences at rounding level (1e-6 of a step) count as zero.
+            s = torch.sign(diff) * (diff.abs() > 1e-6 * lr)
+            g.add_(s, alpha=self.lam1)                                        # d/d aw
+            g0 = s * (-self.lam1)                                             # d/d aw0 = -lam1 * s + wd * aw0
+            g0.add_(anc - self.atten * self.G[:n], alpha=d["weight_decay"])
+            if self.kind == "adam":
+                if self.anchor_m is None:
+                    self.anchor_m, self.anchor_v = torch.zeros_like(anc), torch.zeros_like(anc)
+                b1, b2 = d["betas"]
+                self.anchor_m.mul_(b1).add_(g0, alpha=1 - b1)
+                self.anchor_v.mul_(b2).addcmul_(g0, g0, value=1 - b2)
+                bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+                denom = self.anchor_v.sqrt() / (bc2 ** 0.5) + d["eps"]
+                if isinstance(lr, torch.Tensor):
+                    anc.sub_(self.anchor_m / denom * (lr / bc1))
+                else:
+                    anc.addcdiv_(self.anchor_m, denom, value=-lr / bc1)       # the op sequence of the fp32 CPU step
+            else:
+                if d["momentum"] != 0.0:
+                    if self.anchor_m is None:
+                        self.anchor_m = torch.zeros_like(anc)
+                    self.anchor_m.mul_(d["momentum"]).add_(g0)
+                    g0 = self.anchor_m
+                anc.sub_(g0 * lr) if isinstance(lr, torch.Tensor) else anc.add_(g0, alpha=-lr)
+        return l1
 
 
 class StepLR:

@@ -206,6 +206,39 @@ def test_fedstil_theta_training_equals_reference_adaptive_layer(tmp_path, opt, w
         assert torch.allclose(theta.view(5, 7), ref["thetas"][i], atol=2e-6), (opt, i)
 
 
+# Adam with the shipped weight decay (1e-5: the anchor's gradient is of the order of Adam's eps, so anchor and weight
+# separate by ~lr/2 at once). With a large decay both move by lr * (1 - eps/|g|) and sign(aw - aw0) is decided by a
+# 1e-7-sized difference - the reference's own trajectory is then a matter of fp32 rounding order, nothing to match.
+@pytest.mark.parametrize("opt,wd,steps", [("sgd", 1e-2, 6), ("adam", 1e-5, 6), ("adam", 0.0, 6)])
+def test_fedstil_trained_anchor_matches_reference_adaptive_layer(tmp_path, opt, wd, steps):
+    """``engine_opts.train_l1_anchor``: with the L1 anchor trained like the reference's optimizer trains its
+    ``initial_adaptive_weight`` (gradient ``-lam1 sign(aw - aw0) + wd aw0``), the theta trajectory follows the
+    reference's ``AdaptiveLayer`` over many steps, weight decay included."""
+    import torch.nn as nn
+    from flpr_b200.runtime.arena import ArenaOptimizer, ParamArena
+    torch.manual_seed(8)
+    G = torch.randn(5, 7)
+    xs = [torch.randn(4, 7) for _ in range(steps)]
+    ts = [torch.randn(4, 5) for _ in range(steps)]
+    a, lr, lam1 = 0.8, 0.05, 1e-2
+    ref = oracle("fedstil_layer_steps", {"G": G, "atten": a, "lr": lr, "wd": wd, "opt": opt, "lam1": lam1,
+                                         "xs": xs, "ts": ts}, tmp_path)
+    lin = nn.Linear(7, 5, bias=False)
+    with torch.no_grad():
+        lin.weight.copy_(G)
+    arena = ParamArena([("weight", lin.weight)], "cpu")
+    optim = ArenaOptimizer(opt, arena, lr=lr, weight_decay=wd)
+    optim.G, optim.lam1, optim.atten = G.clone().flatten(), lam1, a
+    optim.anchor = optim.G.clone()
+    optim.stats = torch.zeros(2)
+    for i, (x, t) in enumerate(zip(xs, ts)):
+        optim.zero_grad()
+        ((lin(x) - t) ** 2).mean().backward()
+        optim.step()
+        assert torch.allclose(lin.weight.detach(), ref["thetas"][i], atol=5e-6), (opt, i)
+    assert float(optim.stats[1]) > 0                      # sum |aw - aw0| is still reported
+
+
 @pytest.mark.parametrize("method", ["ewc", "mas", "fedcurv"])
 def test_importance_accumulation_matches_reference(tmp_path, method):
     """Fisher (g^2) / MAS (|g|) importance over the remembered loaders with the reference's ``len(batch) / #batches``
