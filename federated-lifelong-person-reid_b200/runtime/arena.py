@@ -215,7 +215,8 @@ class ArenaOptimizer:
 
         n_g = self.G.numel() if self.G is not None else 0
         lam1, l1_before = self.lam1, None
-        if self.anchor is not None and n_g and lam1 != 0.0:
+        trained_anchor = self.anchor is not None and n_g > 0 and lam1 != 0.0
+        if trained_anchor:
             l1_before = self._anchor_step(n_g)
             self.lam1 = 0.0                # the L1 sub-gradient is already in ``grad``; G still anchors the weight decay
         if 0 < n_g < a.numel:          # FedSTIL: only the adaptive-weight prefix carries the L1 / attention terms
@@ -223,9 +224,9 @@ class ArenaOptimizer:
             launch(n_g, a.numel, False)
         else:
             launch(0, a.numel, n_g > 0)
-        if l1_before is not None:
+        if trained_anchor:
             self.lam1 = lam1
-            if self.stats is not None:
+            if l1_before is not None:
                 self.stats[1:2].copy_(l1_before)
 
     def _anchor_step(self, n: int) -> Optional[torch.Tensor]:
