@@ -1,5 +1,6 @@
 """Evaluation entry points (``tools/evaluate.py``): CMC / mAP on device."""
-from ..ops.rank import evaluate, rank_metrics, rank_metrics_reference, similarity  # noqa: F401
+from ..ops.rank import (evaluate, evaluate_sharded, rank_metrics, rank_metrics_reference,  # noqa: F401
+                        similarity)
 
 
 def calculate_similarity_distance(query_feature, gallery_features):

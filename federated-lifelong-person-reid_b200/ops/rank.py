@@ -92,3 +92,83 @@ def evaluate(query_features: torch.Tensor, query_labels: torch.Tensor, gallery_f
         gallery_features = gallery_features.to(device)
     sim = similarity(query_features, gallery_features, precise=precise)
     return rank_metrics(sim, query_labels, gallery_labels)
+
+
+# ------------------------------------------------------------------------------------------------- gallery-sharded
+def evaluate_sharded(query_features: torch.Tensor, query_labels: torch.Tensor, gallery_shard: torch.Tensor,
+                     gallery_shard_labels: torch.Tensor, group=None, precise: bool = True
+                     ) -> Tuple[np.ndarray, float]:
+    """Exact CMC / mAP when the **gallery is sharded over the ranks** of ``group`` (the dimension that
+    scales in this workload is the gallery, the analogue of sequence parallelism is to give every rank a slice of it).
+
+    Every rank scores its shard against all queries. A hit's position in the global ranking is the number of gallery
+    items that score higher, and that count is a *sum over shards* - so instead of gathering the ``Q x G`` similarity
+    matrix (or merging sorted lists) the ranks exchange only the similarities of the hits (``Q x P``, ``P`` = matches per
+    query and shard) and all-reduce two small count tensors:
+
+        above[r, q, p]     = #{g in shard_r : S[q, g] > s_p}            -> position of hit p in the full ranking
+        hits_above[r, q, p] = #{g in shard_r : S[q, g] > s_p, g a hit}  -> index of hit p among the hits
+
+    from which AP (the reference's trapezoid form, ``tools/evaluate.py:75-82``) and the first-hit position (CMC) follow
+    locally and identically on every rank. Returns what :func:`evaluate` returns on the concatenated gallery.
+    Without an initialised process group (or ``world == 1``) this *is* :func:`evaluate`.
+    """
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return evaluate(query_features, query_labels, gallery_shard, gallery_shard_labels, precise=precise)
+    world = dist.get_world_size(group)
+    dev = query_features.device
+    sim = similarity(query_features, gallery_shard, precise=precise)                   # [Q, Gr]
+    ql = query_labels.to(dev).long()
+    gl = gallery_shard_labels.to(dev).long()
+    nq, ngr = sim.shape
+    match = gl.view(1, -1) == ql.view(-1, 1)                                           # [Q, Gr]
+    # ---- exchange the hit similarities (padded to the largest per-shard hit count) -----------------------------------
+    sizes = torch.tensor([int(match.sum(1).max()) if ngr else 0, ngr], device=dev, dtype=torch.long)
+    size_list = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(size_list, sizes, group=group)
+    pmax = max(int(s[0]) for s in size_list)
+    ng_total = sum(int(s[1]) for s in size_list)
+    if pmax == 0:
+        return np.zeros(ng_total, dtype=np.float64), 0.0
+    neg = torch.finfo(torch.float32).min
+    # hits first (stable), then padding
+    order = torch.argsort((~match).to(torch.int8), dim=1, stable=True)[:, :pmax] if ngr else \
+        torch.zeros(nq, 0, dtype=torch.long, device=dev)
+    mine = torch.full((nq, pmax), neg, dtype=torch.float32, device=dev)
+    valid = torch.zeros(nq, pmax, dtype=torch.bool, device=dev)
+    if ngr:
+        k = order.shape[1]
+        valid[:, :k] = match.gather(1, order)
+        mine[:, :k] = torch.where(valid[:, :k], sim.gather(1, order), torch.full_like(mine[:, :k], neg))
+    hit_list = [torch.empty_like(mine) for _ in range(world)]
+    val_list = [torch.empty(nq, pmax, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(hit_list, mine.contiguous(), group=group)
+    dist.all_gather(val_list, valid.to(torch.uint8).contiguous(), group=group)
+    hits = torch.stack(hit_list, 1).reshape(nq, world * pmax)                           # [Q, W*P]
+    hvalid = torch.stack(val_list, 1).reshape(nq, world * pmax).bool()
+    # ---- local counts: sorted shard rows + searchsorted ---------------------------------------------------------------
+    if ngr:
+        s_sorted, _ = torch.sort(sim, dim=1)                                            # ascending
+        above = ngr - torch.searchsorted(s_sorted, hits.contiguous(), right=True)       # strictly greater
+        pos_only = torch.where(match, sim, torch.full_like(sim, neg))
+        p_sorted, _ = torch.sort(pos_only, dim=1)
+        hits_above = ngr - torch.searchsorted(p_sorted, hits.contiguous(), right=True)
+    else:
+        above = torch.zeros_like(hits, dtype=torch.long)
+        hits_above = torch.zeros_like(hits, dtype=torch.long)
+    counts = torch.stack([above, hits_above]).to(torch.int64)
+    dist.all_reduce(counts, group=group)
+    loc, j = counts[0].double(), counts[1].double()                                     # 0-based rank / hit index
+    # ---- AP and first hit ----------------------------------------------------------------------------------------------
+    n_hits = hvalid.sum(1).double()
+    precision = (j + 1) / (loc + 1)
+    old = torch.where(loc > 0, j / loc.clamp(min=1), torch.ones_like(loc))
+    ap = (torch.where(hvalid, (old + precision) / 2, torch.zeros_like(loc)).sum(1) / n_hits.clamp(min=1))
+    has = n_hits > 0
+    first = torch.where(hvalid, loc, torch.full_like(loc, float(ng_total))).min(1).values.long()
+    hist = torch.bincount(first[has], minlength=ng_total)[:ng_total].double()
+    cmc = torch.cumsum(hist, 0) / nq
+    m_ap = (ap * has).sum() / nq
+    out = torch.cat([cmc, m_ap.view(1)]).cpu().numpy()
+    return out[:-1], float(out[-1])

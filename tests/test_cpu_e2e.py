@@ -112,6 +112,16 @@ def test_gloo_world2_fedavg_plumbing(tmp_path):
     assert "DIST_E2E OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_gallery_sharded_evaluation_matches_full_gallery(world):
+    """gallery sharded over ranks, exact CMC / mAP from all-reduced rank counts (``ops/rank.py``)."""
+    script = os.path.join(os.path.dirname(__file__), "dist_eval_check.py")
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
+                        "--nproc-per-node", str(world), script], env=env, capture_output=True, text=True, timeout=600)
+    assert "DIST_EVAL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_cli_synthetic(tmp_path):
     import yaml
     common = tiny_common(str(tmp_path))
