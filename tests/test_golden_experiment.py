@@ -182,8 +182,18 @@ def _compare(path, a, b, atol, rtol, bad, ignore=(), max_factor=10):
             bad.append((path, "none", a, type(b)))
 
 
-def golden(tmp_path, method, atol=2e-5, rtol=1e-4, skip=(), ignore=(), rounds=ROUNDS, max_factor=10, online=CLIENTS,
-           adam=False, engine=None):
+def golden(tmp_path, method, atol=2e-5, rtol=1e-4, skip=(), ignore=(), rounds=ROUNDS, max_factor=10, online=None,
+           adam=False, engine=None, clients=None):
+    import shutil
+    global CLIENTS
+    saved, CLIENTS = CLIENTS, clients or CLIENTS            # _splits / _experiment read the module-level count
+    try:
+        return _golden(tmp_path, method, atol, rtol, skip, ignore, rounds, max_factor, online or CLIENTS, adam, engine)
+    finally:
+        CLIENTS = saved
+
+
+def _golden(tmp_path, method, atol, rtol, skip, ignore, rounds, max_factor, online, adam, engine):
     import shutil
     splits = _splits()
     ref = _run_reference(tmp_path, method, splits, rounds, online, adam)
@@ -225,6 +235,12 @@ def test_three_rounds_match_reference(tmp_path, method):
     (and the reference's per-epoch lr reset in fedweit / fedstil), evaluates FedWeIT's older task from its own
     checkpoint, and for FedSTIL rehearses exemplars of two tasks (the class-index relabelling quirk)."""
     golden(tmp_path, method, rounds=3, max_factor=25)
+
+
+def test_fedcurv_three_clients_matches_reference(tmp_path):
+    """Two *other* clients per penalty: the three pre-reduced moment buffers against the reference's loop over every
+    other client's ``(F_j, p_j)`` (fedcurv.py:79-86,621-646), three rounds."""
+    golden(tmp_path, "fedcurv", rounds=3, clients=3, max_factor=25, ignore=FEDCURV_NOT_MATERIALISED)
 
 
 def test_fedavg_with_adam_matches_reference(tmp_path):
