@@ -83,14 +83,54 @@ def rank_metrics(sim: torch.Tensor, q_labels: torch.Tensor, g_labels: torch.Tens
     return out[:-1], float(out[-1])
 
 
+def rank_metrics_with_cameras(sim: torch.Tensor, q_labels: torch.Tensor, g_labels: torch.Tensor,
+                              q_cameras: torch.Tensor, g_cameras: torch.Tensor) -> Tuple[np.ndarray, float]:
+    """CMC / mAP with the reference's junk rule (``tools/evaluate.py:12-33,60-67``): gallery items of the query's
+    identity *seen by the query's camera*, and mis-detections (label ``-1``), are removed from the ranking; the hits
+    are the same identity under another camera. Tensor ops on ``sim``'s device (counts instead of a sort per query):
+
+        position(hit) = #{non-junk g : S[q, g] > s_hit},   index among hits = #{hits h : s_h > s_hit}
+    """
+    dev = sim.device
+    ql, gl = q_labels.to(dev).long().view(-1, 1), g_labels.to(dev).long().view(1, -1)
+    qc, gc = q_cameras.to(dev).long().view(-1, 1), g_cameras.to(dev).long().view(1, -1)
+    nq, ng = sim.shape
+    same_id, same_cam = gl == ql, gc == qc
+    junk = (same_id & same_cam) | (gl == -1)
+    hit = same_id & ~same_cam
+    neg = torch.finfo(torch.float32).min
+    s = sim.float()
+    keep = torch.where(junk, torch.full_like(s, neg), s)                 # junk can never outrank anything
+    s_sorted, _ = torch.sort(keep, dim=1)
+    h_sorted, _ = torch.sort(torch.where(hit, s, torch.full_like(s, neg)), dim=1)
+    loc = (ng - torch.searchsorted(s_sorted, s.contiguous(), right=True)).double()      # [Q, G], valid where hit
+    j = (ng - torch.searchsorted(h_sorted, s.contiguous(), right=True)).double()
+    n_hits = hit.sum(1).double()
+    precision = (j + 1) / (loc + 1)
+    old = torch.where(loc > 0, j / loc.clamp(min=1), torch.ones_like(loc))
+    ap = torch.where(hit, (old + precision) / 2, torch.zeros_like(loc)).sum(1) / n_hits.clamp(min=1)
+    has = n_hits > 0
+    first = torch.where(hit, loc, torch.full_like(loc, float(ng))).min(1).values.long()
+    hist = torch.bincount(first[has], minlength=ng)[:ng].double()
+    # the reference's per-query curve keeps the full gallery length even after junk removal (evaluate.py:53,72)
+    cmc = torch.cumsum(hist, 0) / nq
+    out = torch.cat([cmc, ((ap * has).sum() / nq).view(1)]).cpu().numpy()
+    return out[:-1], float(out[-1])
+
+
 def evaluate(query_features: torch.Tensor, query_labels: torch.Tensor, gallery_features: torch.Tensor,
-             gallery_labels: torch.Tensor, device: str | torch.device | None = None, precise: bool = True
-             ) -> Tuple[np.ndarray, float]:
-    """Drop-in for ``tools.evaluate.evaluate`` (no camera-junk filtering: the reference never passes cameras)."""
+             gallery_labels: torch.Tensor, query_camera_labels: torch.Tensor | None = None,
+             gallery_camera_labels: torch.Tensor | None = None, device: str | torch.device | None = None,
+             precise: bool = True) -> Tuple[np.ndarray, float]:
+    """Drop-in for ``tools.evaluate.evaluate`` (same positional order). Camera labels are optional - the reference's
+    runtime never passes them - and switch on its same-camera / mis-detection junk rule."""
     if device is not None:
         query_features = query_features.to(device)
         gallery_features = gallery_features.to(device)
     sim = similarity(query_features, gallery_features, precise=precise)
+    if query_camera_labels is not None and gallery_camera_labels is not None:
+        return rank_metrics_with_cameras(sim, query_labels, gallery_labels, query_camera_labels,
+                                         gallery_camera_labels)
     return rank_metrics(sim, query_labels, gallery_labels)
 
 

@@ -31,9 +31,9 @@ def main():
         _aw = np.argwhere
         E.np.argwhere = lambda a: _aw(a.numpy() if isinstance(a, torch.Tensor) else a)
         cmc, mAP = E.evaluate(d["qf"], d["ql"], d["gf"], d["gl"], device="cpu")
-        E.np.argwhere = _aw
         out = {"cmc": torch.as_tensor(cmc).float(), "mAP": float(mAP), "raw_cmc": torch.as_tensor(raw_cmc).float(),
                "raw_mAP": float(raw_map)}
+        E.np.argwhere = _aw
     elif case == "distance":
         from tools.distance import compute_cosine_distance, compute_euclidean_distance, compute_kl_distance
         out = {"eu": compute_euclidean_distance(d["a"], d["b"]), "cos": compute_cosine_distance(d["a"], d["b"]),

@@ -37,6 +37,38 @@ def test_ranking_metrics_match_reference(tmp_path):
     assert torch.allclose(ref["raw_cmc"], ref["cmc"], atol=1e-6) and ref["raw_mAP"] != pytest.approx(ref["mAP"])
 
 
+def test_camera_junk_rule():
+    """Optional camera labels: same identity under the query's camera and label -1 are junk (evaluate.py:12-33,60-67).
+    The reference's own camera branch cannot run - ``np.setdiff1d`` hands ``evaluate_with_index`` a flat array and
+    ``len(right_result_index[0])`` raises ``TypeError`` - so the rule is checked against a literal per-query
+    re-statement of it (sort, drop junk, locate hits, trapezoid AP)."""
+    import numpy as np
+    from flpr_b200.evaluation import evaluate
+    torch.manual_seed(3)
+    qf = torch.nn.functional.normalize(torch.randn(30, 48), dim=1)
+    gf = torch.nn.functional.normalize(torch.randn(120, 48), dim=1)
+    ql, gl = torch.randint(0, 8, (30,)), torch.randint(0, 8, (120,))
+    gl[::17] = -1                                                     # mis-detections
+    qc, gc = torch.randint(0, 3, (30,)), torch.randint(0, 3, (120,))
+    cmc, mAP = evaluate(qf, ql, gf, gl, qc, gc)
+    sim = (qf @ gf.t()).numpy()
+    total_cmc, total_ap = np.zeros(120), 0.0
+    for i in range(30):
+        order = np.argsort(sim[i])[::-1]
+        same_id, same_cam = gl.numpy() == int(ql[i]), gc.numpy() == int(qc[i])
+        junk = np.flatnonzero((same_id & same_cam) | (gl.numpy() == -1))
+        right = np.flatnonzero(same_id & ~same_cam)
+        if right.size == 0:
+            continue
+        order = order[np.isin(order, junk, invert=True)]
+        loc = np.flatnonzero(np.isin(order, right))
+        total_cmc[loc[0]:] += 1
+        total_ap += sum(((j / l if l else 1.0) + (j + 1) / (l + 1)) / 2 for j, l in enumerate(loc)) / right.size
+    assert np.allclose(cmc, total_cmc / 30, atol=1e-9) and abs(mAP - total_ap / 30) < 1e-9
+    plain_cmc, plain_map = evaluate(qf, ql, gf, gl)
+    assert abs(plain_map - mAP) > 1e-3                                 # the rule does change the numbers here
+
+
 def test_distances_match_reference(tmp_path):
     from flpr_b200 import criterions as C
     torch.manual_seed(1)
