@@ -31,3 +31,27 @@ def test_accuracy_and_forgetting_tables(tmp_path):
     assert forget is not None
     fc = forgetting_curves(logs, "val_map")
     assert fc[0][0] == 0 and fc[-1][0] == 20 and fc[-1][1] >= 0.0
+
+
+def test_grad_cam_and_blended_images(tmp_path):
+    """``analyse/visualize.py``: Grad-CAM over ``net.base.layer4[-1]`` and the blended JPEG writer."""
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    from flpr_b200.analyse.visualize import grad_cam, visualize_models
+    from flpr_b200.models import nets
+    from flpr_b200.runtime.modules import ModelModule
+    torch.manual_seed(0)
+    model = ModelModule(nets["resnet18"](num_classes=10, last_stride=1, neck="bnneck")).eval()
+    x = torch.randn(2, 3, 64, 32)
+    cam = grad_cam(model.net, model.net.base.layer4[-1], x)
+    assert cam.shape == (2, 64, 32) and float(cam.min()) >= 0.0 and float(cam.max()) <= 1.0 + 1e-6
+    assert float(cam.amax(dim=(1, 2)).min()) > 0.99                    # normalised per image
+    paths = []
+    for i in range(2):
+        p = tmp_path / f"im{i}.jpg"
+        Image.fromarray(np.random.RandomState(i).randint(0, 255, (80, 40, 3), dtype=np.uint8)).save(p)
+        paths.append(str(p))
+    written = visualize_models({"fedstil": model}, {7: paths}, str(tmp_path / "out"), size=(64, 32))
+    assert len(written) == 2 and all(Image.open(w).size == (32, 64) for w in written)
