@@ -1,6 +1,7 @@
 """Asynchronous checkpoint pipeline (shared pinned arena + writer processes) on CPU tensors."""
 import os
 
+import pytest
 import numpy as np
 import torch
 
@@ -78,3 +79,27 @@ def test_async_store_concurrent_writers_with_back_pressure(tmp_path):
             assert got["i"] == i and got["cid"] == cid and torch.equal(got["w"], want)
             assert float(got["nested"]["v"][0]) == float(i * 100 + cid)
     st.close()
+
+
+def test_dead_writer_is_detected_not_waited_for(tmp_path):
+    """Fault injection: every writer process is killed while jobs are in flight; ``flush`` must report it
+    within seconds instead of waiting for completions that will never come."""
+    import time
+    st = CheckpointStore(str(tmp_path), asynchronous=True, workers=2, arena_bytes=8 << 20)
+    st.save("client-0", "warm", {"x": torch.zeros(10)}, True)
+    st.flush()                                                     # writers are up
+    for p in st._procs:
+        p.kill()                                                   # exact processes this test started
+    for p in st._procs:
+        p.join(10)
+    for i in range(4):
+        st.save("client-0", f"lost{i}", {"x": torch.randn(1000)}, True)
+    t0 = time.time()
+    with pytest.raises(RuntimeError, match="writer process died"):
+        st.flush()
+    assert time.time() - t0 < 30
+    st._inflight.clear()                                           # nothing left to wait for; release the rest
+    try:
+        st.close()
+    except Exception:
+        pass
