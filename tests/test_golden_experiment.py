@@ -237,6 +237,44 @@ def test_three_rounds_match_reference(tmp_path, method):
     golden(tmp_path, method, rounds=3, max_factor=25)
 
 
+@pytest.mark.parametrize("method", ["fedavg", "fedcurv", "fedstil"])
+def test_world_size_two_matches_reference(tmp_path, method):
+    """SURVEY §7.4 "distributed without a cluster": the same experiment with ONE CLIENT PER RANK (gloo, world_size 2;
+    the collectives run through ``FedComm``'s gloo emulation of the peer-memory kernels, the server role is replicated)
+    against the single-process reference - every file any rank wrote, and every logged metric."""
+    import shutil
+    splits = _splits()
+    ref = _run_reference(tmp_path, method, splits)
+    shutil.rmtree(tmp_path / "ref", ignore_errors=True)
+    torch.save({"init": ref["init"]}, tmp_path / "ref_out.pt")
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
+                        "--nproc-per-node", "2", os.path.join(ROOT, "tests", "dist_golden_check.py"), method,
+                        str(tmp_path), str(ROUNDS)], env=env, capture_output=True, text=True, timeout=1200)
+    assert r.stdout.count("DIST_GOLDEN") == 2, r.stdout[-2000:] + r.stderr[-3000:]
+    outs = [torch.load(tmp_path / f"rank{k}_out.pt", weights_only=False) for k in range(2)]
+    ignore = FEDCURV_NOT_MATERIALISED if method == "fedcurv" else ()
+    bad, seen = [], set()
+    for out in outs:
+        for name, obj in out["files"].items():
+            assert name in ref["files"], f"a rank wrote {name}, the reference did not"
+            seen.add(name)
+            _compare(name, ref["files"][name], obj, 2e-5, 1e-4, bad, ignore, 25)
+    assert not bad, "\n".join(map(str, bad[:20]))
+    assert seen == set(ref["files"]), sorted(set(ref["files"]) - seen)
+    logged = {}
+    for out in outs:
+        for client, rounds in (out["log"].get("data") or {}).items():
+            logged.setdefault(client, {}).update(rounds)
+    for client, rounds in ref["log"]["data"].items():
+        for rnd, tasks in rounds.items():
+            for task, metrics in tasks.items():
+                for k, v in metrics.items():
+                    assert abs(float(logged[client][str(rnd)][task][k]) - float(v)) < 1e-3, (client, rnd, task, k)
+    for k in range(2):
+        shutil.rmtree(tmp_path / f"rank{k}", ignore_errors=True)
+
+
 def test_fedcurv_three_clients_matches_reference(tmp_path):
     """Two *other* clients per penalty: the three pre-reduced moment buffers against the reference's loop over every
     other client's ``(F_j, p_j)`` (fedcurv.py:79-86,621-646), three rounds."""
