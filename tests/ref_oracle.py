@@ -125,6 +125,25 @@ def main():
                               window_size=d["ws"], num_classes=d["classes"], drop_path_rate=0.0).eval()
         with torch.no_grad():
             out = {"state": net.state_dict(), "feat": net.forward_features(d["x"]), "logits": net(d["x"])}
+    elif case == "analyse":
+        # the analysis modules import matplotlib at module level (not installed here): empty stand-ins, the table
+        # functions under test never touch them
+        import contextlib
+        import io
+        import types
+        for name in ("matplotlib", "matplotlib.ticker", "matplotlib.pyplot"):
+            sys.modules.setdefault(name, types.ModuleType(name))
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+        sys.modules["matplotlib"].ticker = sys.modules["matplotlib.ticker"]
+        import analyse.accuracy as ra
+        import analyse.forgetting as rf
+        out = {}
+        for rnd in d["rounds"]:
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                ra.accuracy_on_round(d["logs"], rnd, d["metric"], "metric")
+                rf.forgetting_on_round(d["logs"], rnd, d["metric"], "metric")
+            out[rnd] = buf.getvalue()
     else:
         raise SystemExit(f"unknown case {case}")
     torch.save(out, outp)

@@ -69,6 +69,29 @@ def test_camera_junk_rule():
     assert abs(plain_map - mAP) > 1e-3                                 # the rule does change the numbers here
 
 
+def test_accuracy_and_forgetting_tables_match_reference(tmp_path):
+    """``analyse/accuracy.py::accuracy_on_round`` / ``analyse/forgetting.py::forgetting_on_round`` print per-client and
+    total percentages; the same log dict must give the same lines."""
+    import contextlib
+    import io
+    import random
+    from flpr_b200.analyse.accuracy import accuracy_on_round
+    from flpr_b200.analyse.forgetting import forgetting_on_round
+    rng = random.Random(4)
+    logs = {}
+    for c in range(3):
+        logs[f"client-{c}"] = {str(r): {f"task-{c}-{t}": {"val_map": rng.random(), "val_rank_1": rng.random(),
+                                                          **({"tr_acc": rng.random()} if t == min(r // 2, 2) else {})}
+                                           for t in range(3) if t <= r // 2 + 1} for r in range(0, 7)}
+    ref = oracle("analyse", {"logs": logs, "rounds": [2, 4, 6], "metric": "val_map"}, tmp_path)
+    for rnd in (2, 4, 6):
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            accuracy_on_round(logs, rnd, "val_map", "metric")
+            forgetting_on_round(logs, rnd, "val_map", "metric")
+        assert buf.getvalue() == ref[rnd], (buf.getvalue(), ref[rnd])
+
+
 def test_distances_match_reference(tmp_path):
     from flpr_b200 import criterions as C
     torch.manual_seed(1)
