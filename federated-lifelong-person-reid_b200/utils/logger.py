@@ -38,4 +38,4 @@ class Logger:
             f"Validation '{task_name}' with {query_cnt:,} query images on {gallery_cnt:,} gallery images:\n"
             f"            |- Rank-1 :  {r(0):.2%}\n            |- Rank-3 :  {r(2):.2%}\n"
             f"            |- Rank-5 :  {r(4):.2%}\n            |- Rank-10 : {r(9):.2%}\n"
-            f"            |- mean AP : {mAP:.2%}\n")
+            f"            |- mean AP : {mAP:.2%}\n            ")

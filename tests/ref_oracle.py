@@ -125,6 +125,22 @@ def main():
                               window_size=d["ws"], num_classes=d["classes"], drop_path_rate=0.0).eval()
         with torch.no_grad():
             out = {"state": net.state_dict(), "feat": net.forward_features(d["x"]), "logits": net(d["x"])}
+    elif case == "logger":
+        logging.disable(logging.NOTSET)
+        from tools.logger import Logger
+        msgs = []
+
+        class _H(logging.Handler):
+            def emit(self, record):
+                msgs.append(record.getMessage())
+
+        lg = Logger("client-0")
+        lg.logger.addHandler(_H())
+        lg.logger.propagate = False
+        lg.info_train("task-0-1", "cuda:0", 12345, 0.98765, 1.23456, 3, 5)
+        lg.info_train("task-0-1", "cpu", 7, 0.5, 0.25)
+        lg.info_validation("task-0-1", 1234, 56789, d["cmc"], 0.4321)
+        out = msgs
     elif case == "analyse":
         # the analysis modules import matplotlib at module level (not installed here): empty stand-ins, the table
         # functions under test never touch them

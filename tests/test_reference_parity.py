@@ -92,6 +92,31 @@ def test_accuracy_and_forgetting_tables_match_reference(tmp_path):
         assert buf.getvalue() == ref[rnd], (buf.getvalue(), ref[rnd])
 
 
+def test_console_line_formats_match_reference(tmp_path):
+    """``tools/logger.py:23-39``: the formatted train line and validation block, character for character."""
+    import logging
+    from flpr_b200.utils.logger import Logger
+    cmc = [0.1 * i for i in range(1, 11)]
+    ref = oracle("logger", {"cmc": cmc}, tmp_path)
+    msgs = []
+
+    class _H(logging.Handler):
+        def emit(self, record):
+            msgs.append(record.getMessage())
+
+    lg = Logger("client-0-format-test")
+    handler = _H()
+    lg.logger.addHandler(handler)
+    lg.logger.setLevel(logging.INFO)
+    try:
+        lg.info_train("task-0-1", "cuda:0", 12345, 0.98765, 1.23456, 3, 5)
+        lg.info_train("task-0-1", "cpu", 7, 0.5, 0.25)
+        lg.info_validation("task-0-1", 1234, 56789, cmc, 0.4321)
+    finally:
+        lg.logger.removeHandler(handler)
+    assert msgs == ref
+
+
 def test_distances_match_reference(tmp_path):
     from flpr_b200 import criterions as C
     torch.manual_seed(1)
