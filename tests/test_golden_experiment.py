@@ -22,10 +22,12 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "methods")),
 H, W, CLIENTS, TASKS, ROUNDS = 32, 16, 2, 2, 2
 # The default run keeps the suite around ten minutes on a CPU box; FLPR_GOLDEN_FULL=1 adds the remaining variants
 # (last full run: profiles/golden_parity.md).
+OVERRIDES: dict = {}        # per-test overrides of the shared config (epochs, lr); see test_early_stopping_...
 full = pytest.mark.skipif(os.environ.get("FLPR_GOLDEN_FULL") != "1", reason="set FLPR_GOLDEN_FULL=1 for the full matrix")
 
 
 def _common(tmp: str, rounds: int = ROUNDS, online: int = CLIENTS, adam: bool = False):
+    epochs, sgd_lr = OVERRIDES.get("epochs", 2), OVERRIDES.get("lr", 0.05)
     return {"datasets_dir": os.path.join(tmp, "data"), "checkpoints_dir": os.path.join(tmp, "ckpts"),
             "logs_dir": os.path.join(tmp, "logs"), "parallel": 1, "device": ["cpu"],
             "defaults": {
@@ -37,9 +39,9 @@ def _common(tmp: str, rounds: int = ROUNDS, online: int = CLIENTS, adam: bool = 
                 # SGD + momentum: an update is proportional to the gradient, so a rounding-level difference stays a
                 # rounding-level difference. ``adam=True`` runs the reference's default optimizer instead.
                 "optimizer_opts": ({"name": "adam", "lr": 1e-3, "weight_decay": 1e-5} if adam else
-                                   {"name": "sgd", "lr": 0.05, "momentum": 0.9, "weight_decay": 1e-4}),
+                                   {"name": "sgd", "lr": sgd_lr, "momentum": 0.9, "weight_decay": 1e-4}),
                 "scheduler_opts": {"name": "step_lr", "step_size": 5},
-                "task_opts": {"sustain_rounds": 1, "train_epochs": 2,
+                "task_opts": {"sustain_rounds": 1, "train_epochs": epochs,
                               "augment_opts": {"level": "none", "img_size": [H, W],
                                                "norm_mean": [0.485, 0.456, 0.406], "norm_std": [0.229, 0.224, 0.225]},
                               "loader_opts": {"batch_size": 32, "num_workers": 0, "pin_memory": False,
@@ -59,9 +61,11 @@ METHOD_OPTS = {
 
 
 def _experiment(common, method):
-    backbone = None
+    backbone, shared_ckpt = None, None
     if "@" in method:                                   # "fedstil@swin_transformer_tiny"
         method, backbone = method.split("@")
+    if "+" in method:                                   # "baseline+sm_model": one shared checkpoint name (config "sm")
+        method, shared_ckpt = method.split("+")
     exp = {"exp_name": f"golden-{method}", "exp_method": method, "server": {"server_name": "server"},
            "clients": [{"client_name": f"client-{i}", "tasks": [f"task-{i}-{t}" for t in range(TASKS)]}
                        for i in range(CLIENTS)]}
@@ -71,6 +75,9 @@ def _experiment(common, method):
         exp["server"].update(distance_calculate_step=1, distance_calculate_decay=0.8)
         for c in exp["clients"]:
             c["model_ckpt_name"] = "fedstil_model"
+    if shared_ckpt is not None:
+        for c in exp["clients"]:
+            c["model_ckpt_name"] = shared_ckpt
     if backbone is not None:
         exp["model_opts"] = dict(exp.get("model_opts") or common["defaults"]["model_opts"], name=backbone,
                                  fine_tuning=["base.layers.3", "classifier"] if "swin" in backbone
@@ -115,7 +122,7 @@ def _run_ours(tmp_path, method, splits, init, rounds=ROUNDS, online=CLIENTS, ada
     init_path = os.path.join(tmp, "init.pt")
     torch.save(init, init_path)
     exp = _experiment(common, method)
-    method = method.split("@")[0]
+    method = method.split("@")[0].split("+")[0]
     exp["engine_opts"] = {"compute_dtype": "fp32", "init_state": init_path, "val_at_round0": False,
                           "client_threads": False, **(engine or {})}
     cfg = merge_experiment(common, exp)
@@ -276,6 +283,24 @@ def test_world_size_two_matches_reference(tmp_path, method):
                     assert abs(float(logged[client][str(rnd)][task][k]) - float(v)) < 1e-3, (client, rnd, task, k)
     for k in range(2):
         shutil.rmtree(tmp_path / f"rank{k}", ignore_errors=True)
+
+
+def test_early_stopping_matches_reference(tmp_path):
+    """Eight epochs at a diverging learning rate: the early-stopping rule (three epochs without a simultaneous loss /
+    accuracy improvement, baseline.py:249-255) fires in the fifth epoch, which - as in the reference - is trained but
+    not counted (``train_cnt`` = 4 x 12)."""
+    OVERRIDES.update(epochs=8, lr=2.0)
+    try:
+        ref, files = golden(tmp_path, "fedavg", rounds=1)
+    finally:
+        OVERRIDES.clear()
+    assert ref["files"]["client-0/1-client-0-server.ckpt"]["train_cnt"] == 48
+    assert files["client-0/1-client-0-server.ckpt"]["train_cnt"] == 48
+
+
+def test_single_shared_checkpoint_baseline_matches_reference(tmp_path):
+    """``baseline`` with ``model_ckpt_name`` set (the reference's "sm" configuration: one model for all tasks)."""
+    golden(tmp_path, "baseline+sm_model", rounds=3, max_factor=25)
 
 
 @full
