@@ -28,6 +28,7 @@ full = pytest.mark.skipif(os.environ.get("FLPR_GOLDEN_FULL") != "1", reason="set
 
 def _common(tmp: str, rounds: int = ROUNDS, online: int = CLIENTS, adam: bool = False):
     epochs, sgd_lr = OVERRIDES.get("epochs", 2), OVERRIDES.get("lr", 0.05)
+    criteria = [{"name": "cross_entropy", "num_classes": 8000, "epsilon": 0.1}] + list(OVERRIDES.get("extra_criteria", []))
     return {"datasets_dir": os.path.join(tmp, "data"), "checkpoints_dir": os.path.join(tmp, "ckpts"),
             "logs_dir": os.path.join(tmp, "logs"), "parallel": 1, "device": ["cpu"],
             "defaults": {
@@ -35,7 +36,7 @@ def _common(tmp: str, rounds: int = ROUNDS, online: int = CLIENTS, adam: bool = 
                 "exp_opts": {"comm_rounds": rounds, "val_interval": 1, "online_clients": online},
                 "model_opts": {"name": "resnet18", "num_classes": 8000, "last_stride": 1, "neck": "bnneck",
                                "fine_tuning": ["base.layer4", "classifier"]},
-                "criterion_opts": {"name": "cross_entropy", "num_classes": 8000, "epsilon": 0.1},
+                "criterion_opts": criteria[0] if len(criteria) == 1 else criteria,
                 # SGD + momentum: an update is proportional to the gradient, so a rounding-level difference stays a
                 # rounding-level difference. ``adam=True`` runs the reference's default optimizer instead.
                 "optimizer_opts": ({"name": "adam", "lr": 1e-3, "weight_decay": 1e-5} if adam else
@@ -296,6 +297,16 @@ def test_early_stopping_matches_reference(tmp_path):
         OVERRIDES.clear()
     assert ref["files"]["client-0/1-client-0-server.ckpt"]["train_cnt"] == 48
     assert files["client-0/1-client-0-server.ckpt"]["train_cnt"] == 48
+
+
+def test_cross_entropy_plus_triplet_training_matches_reference(tmp_path):
+    """``criterion_opts`` as a list: label-smoothing CE + hard-mining triplet loss on the global feature, trained for two
+    federated rounds (the reference registers the triplet loss but no shipped config uses it)."""
+    OVERRIDES.update(extra_criteria=[{"name": "triplet_loss", "margin": 0.3, "hard_mining": True, "norm_feat": False}])
+    try:
+        golden(tmp_path, "fedavg")
+    finally:
+        OVERRIDES.clear()
 
 
 def test_single_shared_checkpoint_baseline_matches_reference(tmp_path):
