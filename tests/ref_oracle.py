@@ -51,6 +51,9 @@ def main():
                          ("tri_w", dict(margin=0.3, hard_mining=False, norm_feat=True))):
             t = TripletLoss(**kw)
             res[name] = t(score=None, feature=feat, target=d["target"]).detach()
+        if "teacher" in d:                      # dead code in the reference (not registered), still its definition
+            from criterions.kd_loss import DistillKL
+            res["kd"] = DistillKL(temperature=d["T"])(d["score"], d["teacher"]).detach()
         out = res
     elif case == "fedavg_calculate":
         from methods.fedavg import Server

@@ -132,7 +132,11 @@ def test_losses_match_reference(tmp_path):
     torch.manual_seed(2)
     score, feat = torch.randn(16, 50), torch.randn(16, 24)
     target = torch.arange(16) % 4
-    ref = oracle("losses", {"score": score, "feat": feat, "target": target}, tmp_path)
+    teacher = torch.randn(16, 50)
+    ref = oracle("losses", {"score": score, "feat": feat, "target": target, "teacher": teacher, "T": 4.0}, tmp_path)
+    kd = criterions["kd_loss"](temperature=4.0)
+    assert torch.allclose(kd(score, teacher), ref["kd"], atol=1e-5)
+    assert torch.allclose(kd(score=score, teacher_score=teacher), ref["kd"], atol=1e-5)
     s = score.clone().requires_grad_(True)
     ce = criterions["cross_entropy"](num_classes=50, epsilon=0.1)
     loss = ce(score=s, feature=None, target=target)
