@@ -128,6 +128,13 @@ def main():
                               window_size=d["ws"], num_classes=d["classes"], drop_path_rate=0.0).eval()
         with torch.no_grad():
             out = {"state": net.state_dict(), "feat": net.forward_features(d["x"]), "logits": net(d["x"])}
+    elif case == "explog":
+        from experiment import ExperimentLog
+        log = ExperimentLog(d["path"])
+        for key, value in d["ops"]:
+            log.record(key, value)
+        import json
+        out = {"records": log.records, "file": json.load(open(d["path"]))}
     elif case == "logger":
         logging.disable(logging.NOTSET)
         from tools.logger import Logger

@@ -92,6 +92,24 @@ def test_accuracy_and_forgetting_tables_match_reference(tmp_path):
         assert buf.getvalue() == ref[rnd], (buf.getvalue(), ref[rnd])
 
 
+def test_experiment_log_record_semantics_match_reference(tmp_path):
+    """``ExperimentLog.record`` (experiment.py:16-55): dotted keys create nested dicts; an existing list is appended to,
+    a set added to, a dict updated, anything else replaced - and the JSON file mirrors the records."""
+    import json
+    from flpr_b200.runtime.explog import ExperimentLog
+    ops = [("config", {"exp_name": "x", "seed": 1}), ("data.client-0.1.task-0-0", {"tr_acc": 0.5, "tr_loss": 2.0}),
+           ("data.client-0.1.task-0-0", {"val_map": 0.25}), ("data.client-0.2.task-0-0", {"tr_acc": 0.75}),
+           ("data.client-1.1.task-1-0", {"val_rank_1": 0.1}), ("notes", [1]), ("notes", 2), ("scalar", 3), ("scalar", 4),
+           ("config", {"seed": 2})]
+    ref = oracle("explog", {"path": str(tmp_path / "ref.json"), "ops": ops}, tmp_path)
+    log = ExperimentLog(str(tmp_path / "mine.json"))
+    for key, value in ops:
+        log.record(key, value)
+    log.flush() if hasattr(log, "flush") else None
+    assert log.records == ref["records"]
+    assert json.load(open(tmp_path / "mine.json")) == ref["file"]
+
+
 def test_console_line_formats_match_reference(tmp_path):
     """``tools/logger.py:23-39``: the formatted train line and validation block, character for character."""
     import logging
