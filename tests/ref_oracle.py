@@ -128,6 +128,16 @@ def main():
                               window_size=d["ws"], num_classes=d["classes"], drop_path_rate=0.0).eval()
         with torch.no_grad():
             out = {"state": net.state_dict(), "feat": net.forward_features(d["x"]), "logits": net(d["x"])}
+    elif case == "schedule":
+        from datasets.datasets_pipeline import ReIDTaskPipeline
+        out = {}
+        for sustain in d["sustain"]:
+            pipe = ReIDTaskPipeline(list(d["tasks"]), {"sustain_rounds": sustain}, "unused")
+            pipe.get_task = lambda idx=-1: pipe.task_list[idx]            # no datasets on disk: report the task name
+            seq = []
+            for _ in range(d["calls"]):
+                seq.append((pipe.next_task(), pipe.current_task_idx, list(pipe.task_round_rest), pipe.reach_final_task()))
+            out[sustain] = seq
     elif case == "explog":
         from experiment import ExperimentLog
         log = ExperimentLog(d["path"])

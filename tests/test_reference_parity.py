@@ -92,6 +92,20 @@ def test_accuracy_and_forgetting_tables_match_reference(tmp_path):
         assert buf.getvalue() == ref[rnd], (buf.getvalue(), ref[rnd])
 
 
+def test_task_schedule_matches_reference(tmp_path):
+    """``ReIDTaskPipeline.next_task`` (datasets_pipeline.py:81-93): ``sustain_rounds`` rounds per task, then the last
+    task forever; index, remaining-round counters and ``reach_final_task`` after every call."""
+    from flpr_b200.data.pipeline import ReIDTaskPipeline
+    tasks = ["task-0-0", "task-0-1", "task-0-2"]
+    ref = oracle("schedule", {"tasks": tasks, "sustain": [1, 2, 3], "calls": 14}, tmp_path)
+    for sustain in (1, 2, 3):
+        pipe = ReIDTaskPipeline(list(tasks), {"sustain_rounds": sustain}, "unused")
+        pipe.get_task = lambda idx=-1: pipe.task_list[idx]
+        seq = [(pipe.next_task(), pipe.current_task_idx, list(pipe.task_round_rest), pipe.reach_final_task())
+               for _ in range(14)]
+        assert seq == [tuple(x) for x in ref[sustain]], sustain
+
+
 def test_experiment_log_record_semantics_match_reference(tmp_path):
     """``ExperimentLog.record`` (experiment.py:16-55): dotted keys create nested dicts; an existing list is appended to,
     a set added to, a dict updated, anything else replaced - and the JSON file mirrors the records."""
