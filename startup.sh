@@ -8,4 +8,4 @@ nohup $LAUNCH main.py --experiments \
   configs/basis_exp/experiment_icarl.yaml configs/basis_exp/experiment_fedavg.yaml \
   configs/basis_exp/experiment_fedprox.yaml configs/basis_exp/experiment_fedcurv.yaml \
   configs/basis_exp/experiment_fedweit.yaml configs/basis_exp/experiment_fedstil.yaml \
-  > startup.log 2>&1 &
+  > task.log 2>&1 &
