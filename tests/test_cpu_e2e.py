@@ -173,3 +173,21 @@ def test_client_threads_on_cpu(tmp_path, method):
         for tasks in client.values():
             for vals in tasks.values():
                 assert all(v == v and 0.0 <= v < 1e4 for v in vals.values()), vals
+
+
+def test_fedweit_per_task_evaluation_without_checkpoint_files(tmp_path):
+    """With checkpoint files disabled (or muted by ``checkpoint_interval``) FedWeIT keeps a device snapshot per finished
+    task, so an older task is still evaluated with the weights it had at the end of its own last round."""
+    common, cfg, log = _run(tmp_path, "fedweit", engine_opts={"checkpoints": False})
+    data = log.records["data"]["client-0"]
+    assert {"val_map", "val_rank_1"} <= set(data["2"]["task-0-0"])          # older task evaluated in round 2
+    root = os.path.join(common["checkpoints_dir"], cfg["exp_name"])
+    assert not os.path.exists(os.path.join(root, "client-0", "task-0-0.ckpt"))
+    # same numbers as the run that reads the per-task checkpoint files, and with the files muted on odd rounds
+    _, _, with_files = _run(tmp_path / "files", "fedweit")
+    _, _, muted = _run(tmp_path / "muted", "fedweit", engine_opts={"checkpoint_interval": 2})
+    for other in (with_files, muted):
+        for client in ("client-0", "client-1"):
+            for task, metrics in other.records["data"][client]["2"].items():
+                for k, v in metrics.items():
+                    assert abs(log.records["data"][client]["2"][task][k] - v) < 1e-6, (client, task, k)
