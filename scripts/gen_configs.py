@@ -142,7 +142,15 @@ def _repr_list(dumper, data):
     return dumper.represent_sequence("tag:yaml.org,2002:seq", data, flow_style=flow)
 
 
+def _repr_dict(dumper, data):
+    """Option groups whose values are scalars (or short scalar lists) are written on one line."""
+    leaf = bool(data) and all(not isinstance(v, dict) and not (isinstance(v, list) and any(isinstance(x, (dict, list)) for x in v))
+                             for v in data.values())
+    return dumper.represent_mapping("tag:yaml.org,2002:map", data, flow_style=leaf and len(data) <= 8)
+
+
 _Flow.add_representer(list, _repr_list)
+_Flow.add_representer(dict, _repr_dict)
 
 
 def emit(path, obj, header):
