@@ -122,6 +122,9 @@ def main():
     stage = ExperimentStage(common, [exp])
     log = ExperimentLog(os.path.join(common["logs_dir"], "golden.json"))
     same_seeds(exp["random_seed"])
+    if d.get("val0"):                      # the reference's initial validation pass (experiment.py:163-173), sequential
+        for c in clients:
+            stage._process_val(c, log, 0, stage.container)
     for r in range(1, rounds + 1):
         stage._process_one_round(r, server, clients, exp, log)
 

@@ -101,14 +101,14 @@ def _splits():
     return out
 
 
-def _run_reference(tmp_path, method, splits, rounds=ROUNDS, online=CLIENTS, adam=False):
+def _run_reference(tmp_path, method, splits, rounds=ROUNDS, online=CLIENTS, adam=False, val0=False):
     tmp = str(tmp_path / "ref")
     os.makedirs(tmp)
     common = _common(tmp, rounds, online, adam)
     exp = dict(copy.deepcopy(common["defaults"]))
     exp.update(_experiment(common, method))
     inp, outp = os.path.join(tmp, "in.pt"), os.path.join(tmp, "out.pt")
-    torch.save({"common": common, "exp": exp, "rounds": rounds, "splits": splits}, inp)
+    torch.save({"common": common, "exp": exp, "rounds": rounds, "splits": splits, "val0": val0}, inp)
     env = dict(os.environ, TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_golden.py"), inp, outp], capture_output=True,
                        text=True, env=env, timeout=900, cwd=tmp)
@@ -194,21 +194,25 @@ def _compare(path, a, b, atol, rtol, bad, ignore=(), max_factor=10):
 
 
 def golden(tmp_path, method, atol=2e-5, rtol=1e-4, skip=(), ignore=(), rounds=ROUNDS, max_factor=10, online=None,
-           adam=False, engine=None, clients=None):
+           adam=False, engine=None, clients=None, tasks=None, val0=False):
     import shutil
-    global CLIENTS
-    saved, CLIENTS = CLIENTS, clients or CLIENTS            # _splits / _experiment read the module-level count
+    global CLIENTS, TASKS
+    saved, CLIENTS = CLIENTS, clients or CLIENTS            # _splits / _experiment read the module-level counts
+    saved_t, TASKS = TASKS, tasks or TASKS
     try:
-        return _golden(tmp_path, method, atol, rtol, skip, ignore, rounds, max_factor, online or CLIENTS, adam, engine)
+        return _golden(tmp_path, method, atol, rtol, skip, ignore, rounds, max_factor, online or CLIENTS, adam, engine,
+                       val0)
     finally:
-        CLIENTS = saved
+        CLIENTS, TASKS = saved, saved_t
 
 
-def _golden(tmp_path, method, atol, rtol, skip, ignore, rounds, max_factor, online, adam, engine):
+def _golden(tmp_path, method, atol, rtol, skip, ignore, rounds, max_factor, online, adam, engine, val0=False):
     import shutil
     splits = _splits()
-    ref = _run_reference(tmp_path, method, splits, rounds, online, adam)
+    ref = _run_reference(tmp_path, method, splits, rounds, online, adam, val0)
     shutil.rmtree(tmp_path / "ref", ignore_errors=True)           # hundreds of MB of checkpoints per run
+    if val0:
+        engine = dict(engine or {}, val_at_round0=True)
     files, log = _run_ours(tmp_path, method, splits, ref["init"], rounds, online, adam, engine)
     shutil.rmtree(tmp_path / "ours", ignore_errors=True)
     bad = []
@@ -307,6 +311,15 @@ def test_cross_entropy_plus_triplet_training_matches_reference(tmp_path):
         golden(tmp_path, "fedavg")
     finally:
         OVERRIDES.clear()
+
+
+@pytest.mark.parametrize("method", ["baseline", pytest.param("fedweit", marks=full)])
+def test_three_tasks_with_round0_validation_match_reference(tmp_path, method):
+    """Per-task checkpoints (``mm`` baseline, FedWeIT) over three tasks, three rounds, with the initial validation pass
+    on both sides: a task that was only *validated* must not acquire a checkpoint - the reference's ``load_model`` is a
+    no-op without a file, so an untrained task is evaluated with, and trained from, the most recently loaded weights
+    (``modules/client.py:63-70``, ``methods/baseline.py:237-238,314-315``)."""
+    golden(tmp_path, method, rounds=3, tasks=3, val0=True, max_factor=25)
 
 
 def test_single_shared_checkpoint_baseline_matches_reference(tmp_path):
