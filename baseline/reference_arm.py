@@ -9,7 +9,9 @@ run the reference on a current, offline stack:
   3. ``multiprocessing_context: null`` in ``loader_opts``;
 and, because no dataset exists offline, every client's ``task_pipeline`` is an in-memory equivalent that hands the
 reference its own ``ReIDImageDataset(source=dict)`` / ``DataLoader`` objects holding pre-normalised float tensors
-(this *removes* JPEG decoding and augmentation cost from the reference's timed region – it favours the reference).
+(this *removes* JPEG decoding, ToTensor / Normalize / Resize from the reference's timed region – it favours the
+reference; the random part of its train transform, RandomHorizontalFlip + RandomErasing, is still applied per sample
+by its own torchvision transform objects, so that both arms train on augmented crops and their accuracies compare).
 Multi-GPU follows the reference's own mechanism: one process, ``device: [cuda:0..N-1]``, thread pool.
 """
 from __future__ import annotations
@@ -43,6 +45,8 @@ class _MemoryPipeline:
 
     def _loader(self, task, split, shuffle):
         ds = self._DS(source=self._make_split(task, split))
+        if split == "train" and getattr(self, "train_transform", None) is not None:
+            ds.flpr_transform = self.train_transform
         bs = self.task_opts["loader_opts"]["batch_size"]
         return self._DL(dataset=ds, shuffle=shuffle, drop_last=len(ds) % bs == 1, batch_size=bs, num_workers=0)
 
@@ -70,7 +74,8 @@ class _MemoryPipeline:
         return self.current_task()
 
 
-def run_reference_arm(a, build_config, cleanup_payloads, metric, ClockSampler) -> dict:
+def run_reference_arm(a, build_config, cleanup_payloads, metric, ClockSampler, bench_config=None,
+                      convergence_block=None) -> dict:
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if not os.path.isdir(os.path.join(REF, "methods")):
@@ -125,8 +130,9 @@ def run_reference_arm(a, build_config, cleanup_payloads, metric, ClockSampler) -
     def make_split(task, split):
         cid, tid = int(task.split("-")[1]), int(task.split("-")[2])
         n = a.images if split == "train" else 64
+        # the very bytes and labels flpr_b200.data.synthetic.random_array_split hands to the other arm (NHWC there)
         g = torch.Generator().manual_seed(cid * 100 + tid * 3 + {"train": 0, "query": 1, "gallery": 2}[split])
-        imgs = torch.randint(0, 256, (n, 3, a.height, a.width), dtype=torch.uint8, generator=g)
+        imgs = torch.randint(0, 256, (n, a.height, a.width, 3), dtype=torch.uint8, generator=g).permute(0, 3, 1, 2)
         off = (cid * 5 + tid) * a.ids % (8000 - a.ids)
         pids = (torch.randint(0, a.ids, (n,), generator=g) + off).tolist()
         src = {}
@@ -134,11 +140,31 @@ def run_reference_arm(a, build_config, cleanup_payloads, metric, ClockSampler) -
             src.setdefault(pid, []).append((((imgs[i].float() / 255.0) - mean) / std, pid))
         return src
 
+    # The random part of the reference's own train-time transform (datasets/image_augmentation.py: ToTensor ->
+    # Normalize -> [RandomHorizontalFlip -> RandomErasing(p)] -> Resize): the in-memory splits are already normalised
+    # tensors of the target size, so the reference's RandomHorizontalFlip / RandomErasing instances are applied per
+    # sample, exactly where its DataLoader would apply them. Both arms therefore train on augmented crops.
+    from datasets import augmentations as ref_augmentations
+    import torchvision.transforms as T
+    aug = exp["task_opts"]["augment_opts"]
+    ref_compose = ref_augmentations[aug["level"]](size=aug["img_size"], mean=aug["norm_mean"], std=aug["norm_std"])
+    random_part = [t for t in ref_compose.transforms if isinstance(t, (T.RandomHorizontalFlip, T.RandomErasing))]
+    train_transform = T.Compose(random_part) if random_part else None
+
+    class _Split(ReIDImageDataset):
+        flpr_transform = None
+
+        def __getitem__(self, index):
+            data, person_id, class_index = super().__getitem__(index)
+            if self.flpr_transform is not None:
+                data = self.flpr_transform(data)
+            return data, person_id, class_index
+
     server = parser_server(exp, common)
     clients = parser_clients(exp, common)
     for c in clients:
-        c.task_pipeline = _MemoryPipeline(c.task_pipeline.task_list, exp["task_opts"], make_split, DataLoader,
-                                          ReIDImageDataset)
+        c.task_pipeline = _MemoryPipeline(c.task_pipeline.task_list, exp["task_opts"], make_split, DataLoader, _Split)
+        c.task_pipeline.train_transform = train_transform
     stage = ExperimentStage(common, [exp])
     log = ExperimentLog(os.path.join(common["logs_dir"], "reference-bench.json"))
 
@@ -146,47 +172,84 @@ def run_reference_arm(a, build_config, cleanup_payloads, metric, ClockSampler) -
         for d in range(a.gpus if not a.cpu_debug else 0):
             torch.cuda.synchronize(d)
 
-    r = 0
-    for _ in range(a.warmup):
-        r += 1
-        stage._process_one_round(r, server, clients, exp, log)
-        sync()
-        cleanup_payloads(common["checkpoints_dir"])
+    import signal
+
+    state = {"r": 0, "t_first": None, "t0": None, "stamps": [], "done": False}
     sampler = ClockSampler(0) if not a.cpu_debug else None
+
+    def result(partial: bool) -> dict:
+        """The JSON line from whatever has been measured so far (``partial``: the run was cut short by SIGTERM - the
+        rounds completed inside the timed region, or, if it never got there, the warm-up rounds after the first)."""
+        stamps = state["stamps"]
+        timed = [t for t in stamps if state["t0"] is not None and t > state["t0"]]
+        if timed:
+            steps, ms = len(timed), (timed[-1] - state["t0"]) * 1e3
+        elif len(stamps) >= 2:
+            steps, ms = len(stamps) - 1, (stamps[-1] - stamps[0]) * 1e3
+        else:
+            return _unavailable("terminated before two rounds completed")
+        clocks = sampler.stop() if sampler else None
+        imgs = a.clients * a.images * a.epochs
+        ms_per_step = ms / steps
+        value = imgs / (ms_per_step / 1e3)
+        h2d = a.clients * a.epochs * (2 * a.images) * 3 * a.height * a.width * 4
+        cfg = bench_config(a, "reference", "") if bench_config else {}
+        out = {
+            "metric": metric, "value": round(value, 2), "unit": "images/s", "n_gpus": a.gpus, "steps": steps,
+            "warmup": a.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "fp32 (the reference has no mixed-precision path; cuDNN convolutions run "
+                                          "TF32 under torch's defaults)",
+            "data": "synthetic 256x128 crops (pre-normalised float tensors in host memory), random-init weights",
+            "impl": "reference", "config": cfg,
+            "notes": {"parallelism": f"reference thread-pool over device list cuda:0..{a.gpus - 1}",
+                      "timing": "wall clock bracketed by cudaDeviceSynchronize on every device (the reference syncs "
+                                "the host twice per training step, so wall == device time)"},
+            "e2e": {"value": round(value, 2), "unit": "images/s", "ms_per_step": round(ms_per_step, 3),
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": None},
+            "gpu_launches": 0, "clocks": clocks,
+            "convergence": convergence_block(log.records, state["r"]) if convergence_block else None,
+        }
+        if partial:
+            out["partial"] = True
+            out["steps_requested"] = a.steps
+            out["partial_region"] = "timed" if timed else "warmup (first round excluded)"
+        return out
+
+    def on_term(signum, frame):                     # the driver's per-run limit: report what was measured so far
+        if state["done"]:
+            return
+        state["done"] = True
+        try:
+            print(json.dumps(result(True)), flush=True)
+        finally:
+            os._exit(0)
+
+    if rank == 0:
+        try:
+            signal.signal(signal.SIGTERM, on_term)
+        except ValueError:                              # not the main thread
+            pass
+
+    for _ in range(a.warmup):
+        state["r"] += 1
+        stage._process_one_round(state["r"], server, clients, exp, log)
+        sync()
+        state["stamps"].append(time.perf_counter())
+        cleanup_payloads(common["checkpoints_dir"])
     if sampler:
         sampler.start()
     sync()
-    t0 = time.perf_counter()
+    state["t0"] = time.perf_counter()
     for _ in range(a.steps):
-        r += 1
-        stage._process_one_round(r, server, clients, exp, log)
-    sync()
-    ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop() if sampler else None
+        state["r"] += 1
+        stage._process_one_round(state["r"], server, clients, exp, log)
+        sync()
+        state["stamps"].append(time.perf_counter())
+    state["done"] = True
+    out = result(False)
     cleanup_payloads(common["checkpoints_dir"])
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
-    imgs = a.clients * a.images * a.epochs
-    ms_per_step = ms / a.steps
-    value = imgs / (ms_per_step / 1e3)
-    h2d = a.clients * a.epochs * (2 * a.images) * 3 * a.height * a.width * 4
-    return {
-        "metric": metric, "value": round(value, 2), "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "fp32 (the reference has no mixed-precision path)",
-        "data": "synthetic 256x128 crops (pre-normalised float tensors in host memory), random-init weights",
-        "impl": "reference",
-        "config": {"model": a.model, "method": "fedstil", "clients": a.clients, "global_batch": a.batch * a.clients,
-                   "batch_per_client": a.batch, "images_per_client_task": a.images, "ids_per_task": a.ids,
-                   "img_size": [a.height, a.width], "epochs_per_round": a.epochs, "rehearsal_lambda_k": a.images,
-                   "parallelism": f"reference thread-pool over device list cuda:0..{a.gpus - 1}",
-                   "timing": "wall clock bracketed by cudaDeviceSynchronize on every device (the reference syncs "
-                             "the host twice per training step, so wall == device time)",
-                   "step_definition": "ExperimentStage._process_one_round (dispatch + train + upload + calculate)"},
-        "e2e": {"value": round(value, 2), "unit": "images/s", "ms_per_step": round(ms_per_step, 3),
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": None},
-        "gpu_launches": 0,
-        "clocks": clocks,
-    }
+    return out

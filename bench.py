@@ -134,6 +134,38 @@ def build_config(a, impl: str, world: int):
     return common, exp
 
 
+def bench_config(a, impl: str, parallelism: str) -> dict:
+    """The ``config`` block of the JSON line: the SAME keys and values for every arm (arm-specific remarks go to
+    ``notes``), so that a config diff between the arms shows real differences only."""
+    return {"model": a.model, "method": "fedstil", "clients": a.clients, "global_batch": a.batch * a.clients,
+            "batch_per_client": a.batch, "images_per_client_task": a.images, "ids_per_task": a.ids, "seq_len": None,
+            "img_size": [a.height, a.width], "epochs_per_round": a.epochs, "rehearsal_lambda_k": a.images,
+            "optimizer": "adam lr 1e-3 wd 1e-5", "lambda_l1": 1e-3, "atten_default": 0.9, "num_classes": 8000,
+            "checkpoints": "off" if a.no_ckpt else "reference layout, every round",
+            "step_definition": "one federated round: dispatch (spatial-temporal mix) + local train of all clients "
+                               "(prototype pass, head training with rehearsal, herding) + upload + aggregate",
+            "l2": "inputs larger than L2 (per-round working set >> 126 MB: 8 x 400 MB client state + images)"}
+
+
+def convergence_block(records: dict, rounds: int) -> dict:
+    """Per-round training metrics averaged over the clients, from the experiment log both arms keep
+    (``data.{client}.{round}.{task}.{tr_acc,tr_loss}``): the evidence that the two arms train the same model."""
+    data = (records or {}).get("data", {})
+    acc, loss = [], []
+    for r in range(1, rounds + 1):
+        a_, l_ = [], []
+        for per_round in data.values():
+            for task in (per_round.get(r) or per_round.get(str(r)) or {}).values():
+                if "tr_acc" in task:
+                    a_.append(float(task["tr_acc"]))
+                    l_.append(float(task["tr_loss"]))
+        if a_:
+            acc.append(round(100.0 * sum(a_) / len(a_), 2))
+            loss.append(round(sum(l_) / len(l_), 4))
+    return {"rounds": len(acc), "tr_acc_pct": acc, "tr_loss": loss,
+            "final_tr_acc_pct": acc[-1] if acc else None, "final_tr_loss": loss[-1] if loss else None}
+
+
 def cleanup_payloads(ckpt_dir: str) -> None:
     """Per-round payload files are unique per round; drop them between steps (outside the timed region) so that a
     long run cannot fill the RAM disk. Model checkpoints (overwritten in place) stay."""
@@ -261,6 +293,16 @@ def run_flpr(a, impl: str) -> dict:
         else:
             h2d = float(h2d1 - h2d0)
         phases = {k: round(sum(v[-2 * a.steps:]) / max(len(v[-2 * a.steps:]), 1), 3) for k, v in timer.flush().items()}
+        records = log.records
+        if world > 1:                                   # C7: every rank logs its own clients
+            parts = [None] * world if rank == 0 else None
+            dist.gather_object(log.records.get("data", {}), parts, dst=0)
+            if rank == 0:
+                merged = {}
+                for part in parts:
+                    merged.update(part or {})
+                records = {"data": merged}
+        conv = convergence_block(records, r)
         comm_bytes = comm.bytes_moved if comm is not None else 0
         store.close()
         janitor_q.put(None)
@@ -278,15 +320,12 @@ def run_flpr(a, impl: str) -> dict:
         "vs_baseline": None, "dtype": "bf16" if not a.cpu_debug else "fp32",
         "data": "synthetic 256x128 uint8 crops in pinned host memory, random-init weights",
         "impl": impl,
-        "config": {"model": a.model, "method": "fedstil", "clients": a.clients, "global_batch": a.batch * a.clients,
-                   "batch_per_client": a.batch, "images_per_client_task": a.images, "ids_per_task": a.ids,
-                   "seq_len": None, "img_size": [a.height, a.width], "epochs_per_round": a.epochs,
-                   "rehearsal_lambda_k": a.images,
-                   "parallelism": f"client-per-rank x{a.gpus} (8 clients round-robin, {a.parallel} concurrent client "
-                                  f"streams per GPU)",
-                   "step_definition": "one federated round: dispatch(mix) + local train of all clients + upload + "
-                                      "aggregate; checkpoints " + ("off" if a.no_ckpt else "on (async writer, RAM disk)"),
-                   "l2": "inputs larger than L2 (per-round working set >> 126 MB: 8 x 400 MB client state + images)"},
+        "config": bench_config(a, impl, ""),
+        "notes": {"parallelism": f"client-per-rank x{a.gpus} (8 clients round-robin, {a.parallel} concurrent client "
+                                 f"streams per GPU)",
+                  "semantics": "reference_compat (trained L1 anchors, per-epoch lr reset, exemplar relabelling)",
+                  "timing": "CUDA events on the launching stream, max over ranks"},
+        "convergence": conv,
         "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "ms_per_step": round(e2e_ms / a.steps, 3),
                 "h2d_bytes_per_step": int(h2d / a.steps),
                 "d2h_bytes_per_step": int(a.clients * a.epochs * 4 * 8),
@@ -302,7 +341,7 @@ def run_flpr(a, impl: str) -> dict:
 # ================================================================================================== reference arm
 def run_reference(a) -> dict:
     from baseline.reference_arm import run_reference_arm
-    return run_reference_arm(a, build_config, cleanup_payloads, METRIC, ClockSampler)
+    return run_reference_arm(a, build_config, cleanup_payloads, METRIC, ClockSampler, bench_config, convergence_block)
 
 
 def main():

@@ -37,10 +37,13 @@ constexpr int MAX_COMM_BLOCKS = 512;
 // Layout of the flag page at the start of every rank's arena (uint32 units):
 //   [0, MAX_COMM_BLOCKS*MAX_RANKS)       arrival flags  flag[block][src_rank]
 //   [.., + MAX_COMM_BLOCKS)              per-block epoch counters (local use only)
-//   [.., + 4)                            error word (timeout), local use only
+//   [.., + 4)                            [0] error word (timeout), local use only; [2..3] 64-bit address of a
+//                                        host-mapped mailbox that mirrors the error word (the host reads it without
+//                                        any CUDA call, i.e. after every collective and without a device sync)
 constexpr int FLAG_WORDS = MAX_COMM_BLOCKS * MAX_RANKS;
 constexpr int EPOCH_OFF = FLAG_WORDS;
 constexpr int ERR_OFF = EPOCH_OFF + MAX_COMM_BLOCKS;
+constexpr int MAILBOX_OFF = ERR_OFF + 2;
 constexpr int FLAG_PAGE_WORDS = ERR_OFF + 4;
 
 struct CommCtx {
@@ -59,7 +62,12 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // Block-granular cross-rank barrier: block b of every rank meets block b of every other rank.
 // Release/acquire at system scope makes all prior global writes of the arriving block (including its P2P
 // stores) visible to the waiter.
-__device__ __forceinline__ void rank_barrier(const CommCtx& ctx, uint32_t epoch) {
+// Returns false when the watchdog fired (now or in an earlier collective of this communicator): the caller must then
+// SKIP its load / store phase - a peer's operands may be incomplete, and a partial aggregate must never be pushed to
+// the other ranks - but still runs its remaining barriers so that the epochs stay aligned. The error word is sticky
+// and mirrored into a host-mapped mailbox, which the host polls after every collective (FedComm.check_errors).
+__device__ __forceinline__ bool rank_barrier(const CommCtx& ctx, uint32_t epoch) {
+  int fail = 0;
   __syncthreads();
   if (ctx.world > 1) {
     if (threadIdx.x < ctx.world) {
@@ -71,13 +79,23 @@ __device__ __forceinline__ void rank_barrier(const CommCtx& ctx, uint32_t epoch)
       // signed distance so that the 32-bit epoch may wrap
       while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
         if (gtimer() - t0 > ctx.timeout_ns) {
-          atomicExch(ctx.flags[ctx.rank] + ERR_OFF, 1u);
+          fail = 1;
+          uint32_t* err = ctx.flags[ctx.rank] + ERR_OFF;
+          if (atomicExch(err, 1u) == 0u) {
+            volatile uint32_t* box = *reinterpret_cast<volatile uint32_t* const*>(ctx.flags[ctx.rank] + MAILBOX_OFF);
+            if (box != nullptr) {
+              *box = 1u;
+              __threadfence_system();
+            }
+          }
           break;
         }
       }
     }
-    __syncthreads();
+    if (threadIdx.x == 0 && *reinterpret_cast<volatile uint32_t*>(ctx.flags[ctx.rank] + ERR_OFF) != 0u) fail = 1;
+    fail = __syncthreads_or(fail);
   }
+  return fail == 0;
 }
 
 __device__ __forceinline__ uint32_t block_epoch_begin(const CommCtx& ctx) {
@@ -114,7 +132,7 @@ __global__ void __launch_bounds__(COMM_THREADS)
 fed_reduce_bcast_kernel(const CommCtx ctx, const ReduceArgs a) {
   __shared__ float s_w[MAX_CLIENTS];
   const uint32_t e0 = block_epoch_begin(ctx);
-  rank_barrier(ctx, e0 + 1);  // all uploads (and counters) are complete on every rank
+  const bool ok = rank_barrier(ctx, e0 + 1);  // all uploads (and counters) are complete on every rank
 
   if (threadIdx.x < 32) {
     float tot = 0.f;
@@ -131,7 +149,7 @@ fed_reduce_bcast_kernel(const CommCtx ctx, const ReduceArgs a) {
   const size_t lo = per * ctx.rank;
   const size_t hi = (lo + per < a.n4) ? lo + per : a.n4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+  for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; ok && i < hi; i += stride) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c0 = 0; c0 < a.K; c0 += 8) {
       float4 v[8];
@@ -196,14 +214,14 @@ __device__ __forceinline__ void mix_body(const MixArgs& a, const float (*sw)[MAX
 __global__ void __launch_bounds__(COMM_THREADS) fed_mix_kernel(const CommCtx ctx, const MixArgs a) {
   __shared__ float sw[MAX_LOCAL][MAX_CLIENTS];
   const uint32_t e0 = block_epoch_begin(ctx);
-  rank_barrier(ctx, e0 + 1);
+  const bool ok = rank_barrier(ctx, e0 + 1);
   for (int i = threadIdx.x; i < a.L * a.K; i += blockDim.x) {
     const int l = i / a.K, c = i - l * a.K;
     sw[l][c] = a.w_dev ? a.w_dev[i] : a.w[l][c];
   }
   __syncthreads();
-  switch (a.L) {
-    case 0: break;  // rank hosts no receiving client this round: barriers only
+  switch (ok ? a.L : 0) {
+    case 0: break;  // rank hosts no receiving client this round (or the watchdog fired): barriers only
     case 1: mix_body<1>(a, sw); break;
     case 2: mix_body<2>(a, sw); break;
     case 3: mix_body<3>(a, sw); break;
@@ -230,12 +248,12 @@ struct CurvArgs {
 
 __global__ void __launch_bounds__(COMM_THREADS) fed_curv_moments_kernel(const CommCtx ctx, const CurvArgs a) {
   const uint32_t e0 = block_epoch_begin(ctx);
-  rank_barrier(ctx, e0 + 1);
+  const bool ok = rank_barrier(ctx, e0 + 1);
   const size_t per = (a.n4 + ctx.world - 1) / ctx.world;
   const size_t lo = per * ctx.rank;
   const size_t hi = (lo + per < a.n4) ? lo + per : a.n4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+  for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; ok && i < hi; i += stride) {
     float4 sf = make_float4(0.f, 0.f, 0.f, 0.f), sfp = sf, sfpp = sf;
     for (int c0 = 0; c0 < a.K; c0 += 4) {
       float4 f[4], q[4];
@@ -277,8 +295,8 @@ struct GatherArgs {
 
 __global__ void __launch_bounds__(COMM_THREADS) fed_gather_strided_kernel(const CommCtx ctx, const GatherArgs a) {
   const uint32_t e0 = block_epoch_begin(ctx);
-  rank_barrier(ctx, e0 + 1);
-  const size_t n4 = a.n / 4;
+  const bool ok = rank_barrier(ctx, e0 + 1);
+  const size_t n4 = ok ? a.n / 4 : 0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     for (int c0 = 0; c0 < a.K; c0 += 8) {
@@ -294,7 +312,7 @@ __global__ void __launch_bounds__(COMM_THREADS) fed_gather_strided_kernel(const 
         }
     }
   }
-  for (size_t e = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.n; e += stride)
+  for (size_t e = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; ok && e < a.n; e += stride)
     for (int c = 0; c < a.K; ++c) a.dst[e * a.K + c] = a.src[c][e];
   rank_barrier(ctx, e0 + 2);
   block_epoch_end(ctx, e0 + 2);
@@ -310,9 +328,10 @@ struct CopyArgs {
 
 __global__ void __launch_bounds__(COMM_THREADS) fed_pull_copy_kernel(const CommCtx ctx, const CopyArgs a) {
   const uint32_t e0 = block_epoch_begin(ctx);
-  rank_barrier(ctx, e0 + 1);
+  const bool ok = rank_barrier(ctx, e0 + 1);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (!ok) i = a.n4;
   for (; i + 3 * stride < a.n4; i += 4 * stride) {
     float4 v[4];
 #pragma unroll
@@ -413,6 +432,12 @@ int flpr_comm_read_error(void* local_flag_page, int* out) {
   cudaError_t e = cudaMemcpy(&v, reinterpret_cast<uint32_t*>(local_flag_page) + ERR_OFF, 4, cudaMemcpyDeviceToHost);
   *out = (int)v;
   return (int)e;
+}
+
+// Register a host-mapped (pinned, UVA) 32-bit mailbox that the watchdog mirrors the error word into.
+int flpr_comm_set_mailbox(void* local_flag_page, void* host_mailbox) {
+  unsigned long long addr = reinterpret_cast<unsigned long long>(host_mailbox);
+  return (int)cudaMemcpy(reinterpret_cast<uint32_t*>(local_flag_page) + MAILBOX_OFF, &addr, 8, cudaMemcpyHostToDevice);
 }
 
 int flpr_comm_barrier(int rank, int world, void* const* flag_pages, double timeout_s, cudaStream_t st) {

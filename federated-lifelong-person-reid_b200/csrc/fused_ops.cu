@@ -51,6 +51,13 @@ struct OptArgs {
   float momentum;
   int penalty_ones;     // FedProx: Q == 1 without materialising it
   const float* hyper;   // optional device-resident [lr, step]: keeps a captured CUDA graph valid across steps
+  // FedSTIL trained L1 anchor (reference quirk, methods/fedstil.py:53-76,639-647): `initial_adaptive_weight` is a bare
+  // Parameter whose requires_grad is never cleared, so the reference's optimizer trains the anchor of the L1 term too
+  // (gradient -lam1*sign(aw - aw0) + wd*aw0, own moments). `anchor` holds theta0 = atten*G + aw0 (nullable = constant
+  // anchor G); am / av are its exp_avg (or momentum buffer) / exp_avg_sq.
+  float* anchor;
+  float* am;
+  float* av;
 };
 
 template <bool ADAM>
@@ -75,6 +82,15 @@ __global__ void __launch_bounds__(256) fused_opt_kernel(const OptArgs a) {
     if (a.Q) q4 = reinterpret_cast<const float4*>(a.Q)[i];
     if (a.R) r4 = reinterpret_cast<const float4*>(a.R)[i];
     if (a.G) G4 = reinterpret_cast<const float4*>(a.G)[i];
+    float4 c4 = G4, cm4 = make_float4(0.f, 0.f, 0.f, 0.f), cv4 = cm4;
+    if (a.anchor) {
+      c4 = reinterpret_cast<const float4*>(a.anchor)[i];
+      if (ADAM || a.momentum != 0.f) cm4 = reinterpret_cast<const float4*>(a.am)[i];
+      if (ADAM) cv4 = reinterpret_cast<const float4*>(a.av)[i];
+    }
+    float* cc = reinterpret_cast<float*>(&c4);
+    float* cmm = reinterpret_cast<float*>(&cm4);
+    float* cvv = reinterpret_cast<float*>(&cv4);
     float* pp = reinterpret_cast<float*>(&p4);
     const float* gg = reinterpret_cast<const float*>(&g4);
     float* mm = reinterpret_cast<float*>(&m4);
@@ -88,10 +104,33 @@ __global__ void __launch_bounds__(256) fused_opt_kernel(const OptArgs a) {
       float g = gg[t];
       float decay_base = p;
       if (a.G) {
-        const float d = p - GG[t];
+        const float d = p - cc[t];                         // cc = G unless the anchor is trained
         l1 += fabsf(d);
-        g += a.lam1 * ((d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f));
+        float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+        // Where the loss gradient is exactly zero weight and anchor receive the same update and stay identical in the
+        // reference (sign(0) = 0); differently fused update formulas cannot promise that bit for bit, so differences
+        // at rounding level (1e-6 of a step) count as zero.
+        if (a.anchor && fabsf(d) <= 1e-6f * lr) sgn = 0.f;
+        g += a.lam1 * sgn;
         decay_base = p - a.atten * GG[t];
+        if (a.anchor) {
+          const float c = cc[t];
+          const float g0 = -a.lam1 * sgn + a.wd * (c - a.atten * GG[t]);
+          if (ADAM) {
+            const float m0 = a.beta1 * cmm[t] + (1.f - a.beta1) * g0;
+            const float v0 = a.beta2 * cvv[t] + (1.f - a.beta2) * g0 * g0;
+            cmm[t] = m0;
+            cvv[t] = v0;
+            cc[t] = c - (lr / bc1) * (m0 / (sqrtf(v0) / bc2_sqrt + a.eps));
+          } else {
+            float d0 = g0;
+            if (a.momentum != 0.f) {
+              d0 = a.momentum * cmm[t] + g0;
+              cmm[t] = d0;
+            }
+            cc[t] = c - lr * d0;
+          }
+        }
       }
       if (a.R) {
         const float q = a.penalty_ones ? 1.f : qq[t];
@@ -120,6 +159,11 @@ __global__ void __launch_bounds__(256) fused_opt_kernel(const OptArgs a) {
     reinterpret_cast<float4*>(a.p)[i] = p4;
     if (ADAM || a.momentum != 0.f) reinterpret_cast<float4*>(a.m)[i] = m4;
     if (ADAM) reinterpret_cast<float4*>(a.v)[i] = v4;
+    if (a.anchor) {
+      reinterpret_cast<float4*>(a.anchor)[i] = c4;
+      if (ADAM || a.momentum != 0.f) reinterpret_cast<float4*>(a.am)[i] = cm4;
+      if (ADAM) reinterpret_cast<float4*>(a.av)[i] = cv4;
+    }
     if (a.p_bf16) {
       __nv_bfloat162 lo = __floats2bfloat162_rn(p4.x, p4.y), hi = __floats2bfloat162_rn(p4.z, p4.w);
       uint2 u;
@@ -1021,7 +1065,7 @@ extern "C" {
 int flpr_fused_opt(int adam, float* p, const float* g, float* m, float* v, const float* Q, const float* R,
                    const float* G, void* p_bf16, float* stats, size_t n, float lr, float beta1, float beta2, float eps,
                    float wd, int step, float lam2, float lam1, float atten, float momentum, int penalty_ones,
-                   const float* hyper, cudaStream_t st) {
+                   const float* hyper, float* anchor, float* anchor_m, float* anchor_v, cudaStream_t st) {
   bind_device_of(p);
   if (n % 4) return -2;
   OptArgs a;
@@ -1032,6 +1076,10 @@ int flpr_fused_opt(int adam, float* p, const float* g, float* m, float* v, const
   a.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   a.lam2 = lam2; a.lam1 = lam1; a.atten = atten; a.momentum = momentum; a.penalty_ones = penalty_ones;
   a.hyper = hyper;
+  a.anchor = G != nullptr ? anchor : nullptr; a.am = anchor_m; a.av = anchor_v;
+  if (a.anchor != nullptr && ((adam && (anchor_m == nullptr || anchor_v == nullptr)) ||
+                              (!adam && momentum != 0.f && anchor_m == nullptr)))
+    return -3;
   const int grid = grid_for(n / 4, 256);
   if (adam) fused_opt_kernel<true><<<grid, 256, 0, st>>>(a);
   else fused_opt_kernel<false><<<grid, 256, 0, st>>>(a);

@@ -10,7 +10,9 @@ Reference algorithm -> this implementation
   ``A = theta - a G`` (weight decay) and ``A - A0 = theta - G`` (L1 sparseness). We keep ONE fp32 master ``theta``
   per adaptive layer and fold weight decay on ``A``, ``lambda_l1 * sign(theta - G)`` and the bf16 refresh into the
   fused optimizer kernel: the per-step compose pass and the 6-11-layer Python L1 loop (``fedstil.py:639-644``)
-  disappear. The reference's accidental training of its ``initial_*`` copies is not reproduced.
+  disappear. The reference's accidental training of its ``initial_*`` L1 anchors is reproduced under
+  ``reference_compat`` (``engine_opts.train_l1_anchor``): the anchor and its moments are stepped inside the same fused
+  optimizer kernel (``csrc/fused_ops.cu``; the CPU twin is ``ArenaOptimizer._anchor_step``).
 * *Head discovery by torch.fx* (``fedstil.py:258-288``) -> static trunk / head split of the backbone.
 * *Prototype pass* (``fedstil.py:558-617``): eval-mode frozen trunk over the task's train loader; the feature maps
   at the cut stay on the device (NHWC bf16) instead of bouncing through numpy; ``task_token`` = mean prototype.
@@ -48,7 +50,7 @@ class Model(ModelModule):
         self.ids: set = set()
         self.ex_gens: List[Dict[str, Any]] = []          # exemplar memory (see "exemplar memory" below)
         self.G: Optional[torch.Tensor] = None
-        self.train_l1_anchor = False                     # engine_opts.train_l1_anchor (see ArenaOptimizer._anchor_step)
+        self.train_l1_anchor = False                     # engine_opts.train_l1_anchor (set by the Client)
         self.anchor: Optional[torch.Tensor] = None
 
     # ---- adaptive layers: leaves of type Linear/Conv2d whose parameters are all trainable (fedstil.py:290-347) ------

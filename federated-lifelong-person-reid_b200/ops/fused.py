@@ -18,17 +18,24 @@ def fused_optimizer_step(kind: str, p: torch.Tensor, g: torch.Tensor, m: Optiona
                          Q: Optional[torch.Tensor] = None, R: Optional[torch.Tensor] = None, lam2: float = 0.0,
                          penalty_ones: bool = False, G: Optional[torch.Tensor] = None, lam1: float = 0.0,
                          atten: float = 0.0, p_bf16: Optional[torch.Tensor] = None,
-                         stats: Optional[torch.Tensor] = None, hyper: Optional[torch.Tensor] = None) -> None:
+                         stats: Optional[torch.Tensor] = None, hyper: Optional[torch.Tensor] = None,
+                         anchor: Optional[torch.Tensor] = None, anchor_m: Optional[torch.Tensor] = None,
+                         anchor_v: Optional[torch.Tensor] = None) -> None:
     """One in-place optimizer step over a flat fp32 arena.
 
     gradient used:  g + wd * (p - atten*G) + 2*lam2*(Q*p - R) + lam1*sign(p - G)
     (``Q``/``R`` encode EWC / MAS / FedProx / FedCurv penalties, ``G`` is FedSTIL's global weight;
     ``stats[0] += sum(Q p^2 - 2 R p)``, ``stats[1] += sum|p - G|`` are the penalty values for loss reporting).
+
+    ``anchor`` (CUDA only; the CPU twin is ``ArenaOptimizer._anchor_step``): FedSTIL's *trained* L1 anchor
+    ``theta0 = atten*G + aw0`` replaces ``G`` in the L1 term and is itself stepped in the same pass with gradient
+    ``-lam1*sign(p - theta0) + wd*(theta0 - atten*G)`` and its own moments (reference ``fedstil.py:53-76,639-647``).
     """
     adam = kind == "adam"
     if hyper is not None and not p.is_cuda:
         lr, step = float(hyper[0]), int(hyper[1])
     if not p.is_cuda:
+        assert anchor is None, "the CPU path of the trained anchor is ArenaOptimizer._anchor_step"
         with torch.no_grad():
             grad = g.clone()
             base = p
@@ -63,7 +70,8 @@ def fused_optimizer_step(kind: str, p: torch.Tensor, g: torch.Tensor, m: Optiona
     rc = lib.flpr_fused_opt(int(adam), native.ptr(p), native.ptr(g), native.ptr(m), native.ptr(v), native.ptr(Q),
                             native.ptr(R), native.ptr(G), native.ptr(p_bf16), native.ptr(stats), p.numel(), lr, beta1,
                             beta2, eps, weight_decay, int(step), lam2, lam1, atten, momentum, int(penalty_ones),
-                            native.ptr(hyper), native.stream(p.device))
+                            native.ptr(hyper), native.ptr(anchor if G is not None else None), native.ptr(anchor_m),
+                            native.ptr(anchor_v), native.stream(p.device))
     native.check(rc, "flpr_fused_opt")
     native.count_launch()
 

@@ -47,13 +47,14 @@ def _declare(lib: C.CDLL) -> None:
         "flpr_ipc_close": [P],
         "flpr_enable_peer": [I, I],
         "flpr_comm_read_error": [P, C.POINTER(I)],
+        "flpr_comm_set_mailbox": [P, P],
         "flpr_comm_barrier": [I, I, P, D, P],
         "flpr_comm_reduce_bcast": [I, I, P, D, I, P, P, P, P, Z, I, P],
         "flpr_comm_mix": [I, I, P, D, I, I, P, P, P, P, P, P, Z, I, P],
         "flpr_comm_curv_moments": [I, I, P, D, I, P, P, P, P, P, Z, I, P],
         "flpr_comm_gather_strided": [I, I, P, D, I, P, P, Z, I, P],
         "flpr_comm_pull_copy": [I, I, P, D, P, P, P, Z, I, P],
-        "flpr_fused_opt": [I, P, P, P, P, P, P, P, P, P, Z, F, F, F, F, F, I, F, F, F, F, I, P, P],
+        "flpr_fused_opt": [I, P, P, P, P, P, P, P, P, P, Z, F, F, F, F, F, I, F, F, F, F, I, P, P, P, P, P],
         "flpr_importance_accum": [P, P, Z, F, I, P],
         "flpr_cast_bf16": [P, P, Z, P],
         "flpr_compose": [P, P, F, P, P, Z, P],

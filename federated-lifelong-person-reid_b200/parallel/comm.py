@@ -117,6 +117,10 @@ class FedComm:
         else:
             self._peer_base = [self._base]
         self._flag_pages = (C.c_void_p * self.world)(*[C.c_void_p(b) for b in self._peer_base])
+        # host-mapped mailbox mirroring the watchdog's error word: polled after every collective without a CUDA call
+        self._mailbox = torch.zeros(4, dtype=torch.int32).pin_memory()
+        native.check(lib.flpr_comm_set_mailbox(C.c_void_p(self._base), C.c_void_p(self._mailbox.data_ptr())),
+                     "flpr_comm_set_mailbox")
 
     def close(self) -> None:
         if self.mode == "p2p" and getattr(self, "_base", None):
@@ -193,13 +197,23 @@ class FedComm:
             dist.all_gather_into_tensor(allb, local, group=self.group)
         return torch.stack([allb[self.owner(c) * b.slots + self.slot(c)] for c in clients])
 
+    _TIMEOUT_MSG = ("a flpr collective timed out waiting for a peer rank (flag watchdog fired); the kernels skipped "
+                    "their store phase, no partial aggregate was published")
+
+    def poll_errors(self) -> None:
+        """Non-blocking: raise as soon as a *completed* collective has reported a missed barrier (host-mapped mailbox,
+        no CUDA call, no device sync). Called after every collective launch and at the round boundaries."""
+        if self.mode == "p2p" and int(self._mailbox[0]) != 0:
+            raise native.NativeError(self._TIMEOUT_MSG)
+
     def check_errors(self) -> None:
+        """Blocking: reads the device-side error word (synchronises the device)."""
         if self.mode != "p2p":
             return
         err = C.c_int(0)
         self._lib.flpr_comm_read_error(C.c_void_p(self._base), C.byref(err))
-        if err.value:
-            raise native.NativeError("a flpr collective timed out waiting for a peer rank (flag watchdog fired)")
+        if err.value or int(self._mailbox[0]) != 0:
+            raise native.NativeError(self._TIMEOUT_MSG)
 
     # ------------------------------------------------------------------ collectives
     def barrier(self) -> None:
@@ -226,6 +240,7 @@ class FedComm:
                                                   native.stream(self.device))
             native.check(rc, "flpr_comm_reduce_bcast")
             native.count_launch()
+            self.poll_errors()
             share = bs.n * 4 / self.world
             self.bytes_moved += int(share * self._remote(clients) + share * (self.world - 1))
             return
@@ -275,6 +290,7 @@ class FedComm:
                                              self.comm_blocks, native.stream(self.device))
                 native.check(rc, "flpr_comm_mix")
                 native.count_launch()
+                self.poll_errors()
                 if idx:
                     self.bytes_moved += int(bs.n * 4 * self._remote(clients))
             return
@@ -300,6 +316,7 @@ class FedComm:
                                                   native.stream(self.device))
             native.check(rc, "flpr_comm_curv_moments")
             native.count_launch()
+            self.poll_errors()
             share = bf.n * 4 / self.world
             self.bytes_moved += int(2 * share * self._remote(clients) + 3 * share * (self.world - 1))
             return
@@ -319,6 +336,7 @@ class FedComm:
                                                     bs.n, self.comm_blocks, native.stream(self.device))
             native.check(rc, "flpr_comm_gather_strided")
             native.count_launch()
+            self.poll_errors()
             self.bytes_moved += int(bs.n * 4 * self._remote(clients))
             return
         stack = self._gather_clients(src, clients).float()
@@ -335,6 +353,7 @@ class FedComm:
                                                self.comm_blocks, native.stream(self.device))
             native.check(rc, "flpr_comm_pull_copy")
             native.count_launch()
+            self.poll_errors()
             if self.owner(client) != self.rank:
                 self.bytes_moved += bs.n * 4
             return

@@ -203,20 +203,30 @@ class ArenaOptimizer:
         if self.hyper is not None:
             self.hyper[1:2].add_(1.0)                 # captured together with the step when graphing
 
+        n_g = self.G.numel() if self.G is not None else 0
+        trained_anchor = self.anchor is not None and n_g > 0 and self.lam1 != 0.0
+        fused_anchor = trained_anchor and a.device.type == "cuda" and getattr(self, "fuse_anchor", True)
+        if fused_anchor and self.anchor_m is None and (self.kind == "adam" or d["momentum"] != 0.0):
+            self.anchor_m = torch.zeros_like(self.anchor)
+        if fused_anchor and self.anchor_v is None and self.kind == "adam":
+            self.anchor_v = torch.zeros_like(self.anchor)
+
         def launch(lo: int, hi: int, with_g: bool) -> None:
             sl = slice(lo, hi)
+            anc = with_g and fused_anchor
             fops.fused_optimizer_step(
                 self.kind, a.master[sl], a.grad[sl], None if self.m is None else self.m[sl],
                 None if self.v is None else self.v[sl], lr=self.lr, step=self.step_count, beta1=d["betas"][0],
                 beta2=d["betas"][1], eps=d["eps"], weight_decay=d["weight_decay"], momentum=d["momentum"],
                 Q=None if self.Q is None else self.Q[sl], R=None if self.R is None else self.R[sl], lam2=self.lam2,
                 penalty_ones=self.penalty_ones, G=self.G[sl] if with_g else None, lam1=self.lam1, atten=self.atten,
-                p_bf16=None if a.shadow is None else a.shadow[sl], stats=self.stats, hyper=self.hyper)
+                p_bf16=None if a.shadow is None else a.shadow[sl], stats=self.stats, hyper=self.hyper,
+                anchor=self.anchor[sl] if anc else None,
+                anchor_m=self.anchor_m[sl] if anc and self.anchor_m is not None else None,
+                anchor_v=self.anchor_v[sl] if anc and self.anchor_v is not None else None)
 
-        n_g = self.G.numel() if self.G is not None else 0
         lam1, l1_before = self.lam1, None
-        trained_anchor = self.anchor is not None and n_g > 0 and lam1 != 0.0
-        if trained_anchor:
+        if trained_anchor and not fused_anchor:
             l1_before = self._anchor_step(n_g)
             self.lam1 = 0.0                # the L1 sub-gradient is already in ``grad``; G still anchors the weight decay
         if 0 < n_g < a.numel:          # FedSTIL: only the adaptive-weight prefix carries the L1 / attention terms
@@ -224,17 +234,17 @@ class ArenaOptimizer:
             launch(n_g, a.numel, False)
         else:
             launch(0, a.numel, n_g > 0)
-        if trained_anchor:
+        if trained_anchor and not fused_anchor:
             self.lam1 = lam1
             if l1_before is not None:
                 self.stats[1:2].copy_(l1_before)
 
     def _anchor_step(self, n: int) -> Optional[torch.Tensor]:
-        """Reference quirk, opt-in (``engine_opts.train_l1_anchor``): FedSTIL's ``initial_adaptive_weight`` is a bare
-        ``Parameter`` whose ``requires_grad`` is never cleared, so the reference's optimizer trains the L1 *anchor*
-        ``aw0`` as well - its gradient is ``-lam1 * sign(aw - aw0) + wd * aw0``. Written with tensor ops
-        only (lr / step come from the device-resident ``hyper`` on CUDA) so it can sit inside a captured step; it is
-        not part of the fused kernel yet, hence off by default. ``anchor`` holds ``theta0 = atten * G + aw0``.
+        """Reference quirk (``engine_opts.train_l1_anchor``, on under ``reference_compat``): FedSTIL's
+        ``initial_adaptive_weight`` is a bare ``Parameter`` whose ``requires_grad`` is never cleared, so the reference's
+        optimizer trains the L1 *anchor* ``aw0`` as well - its gradient is
+        ``-lam1 * sign(aw - aw0) + wd * aw0``. This is the fp32 tensor-op form used on the CPU (what the golden tests run);
+        on CUDA the same update is part of ``fused_opt_kernel``. ``anchor`` holds ``theta0 = atten * G + aw0``.
         Returns what ``stats[1]`` must read after the step: previous value + ``sum |aw - aw0|`` (for loss reporting)."""
         a, d = self.arena, self.defaults
         with torch.no_grad():

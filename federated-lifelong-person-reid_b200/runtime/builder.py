@@ -135,8 +135,8 @@ def parser_clients(exp_config: Dict, common_config: Dict, device="cpu", store: O
                                     device_loader=eng.get("device_augment", True), source_factory=source_factory)
         kwargs = {n: p for n, p in client_config.items() if n not in ("client_name",)}
         kwargs.setdefault("reference_compat", eng.get("reference_compat", True))
-        if eng.get("train_l1_anchor"):
-            kwargs.setdefault("train_l1_anchor", True)
+        anchor = eng.get("train_l1_anchor")
+        kwargs.setdefault("train_l1_anchor", bool(eng.get("reference_compat", True) if anchor is None else anchor))
         clients.append(methods[exp_config["exp_method"]].Client(
             client_name=client_config["client_name"], model=model, operator=operator,
             ckpt_root=os.path.join(common_config["checkpoints_dir"], exp_config["exp_name"]),

@@ -189,6 +189,7 @@ class CheckpointStore:
         self._lock = threading.RLock()
         self._copy_stream = None
         self._last_copy_event = None
+        self._actor_events: Dict[str, Any] = {}              # actor -> event of its latest staged snapshot
 
     # ------------------------------------------------------------------ paths
     def path(self, actor: str, state_name: str) -> str:
@@ -307,12 +308,20 @@ class CheckpointStore:
             return o
         return mirror(state), base, total, event
 
-    def fence(self) -> None:
-        """Make the compute stream wait for outstanding snapshot copies (call before sources are overwritten)."""
+    def fence(self, actor: Optional[str] = None) -> None:
+        """Make the compute stream wait for outstanding snapshot copies (call before sources are overwritten).
+        With ``actor`` only the snapshots staged on behalf of that actor are waited for (copies are issued in order on
+        one stream, so this is "everything up to that actor's latest snapshot")."""
         with self._lock:
+            if actor is not None:
+                ev = self._actor_events.pop(actor, None)
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
+                return
             if self._last_copy_event is not None:
                 torch.cuda.current_stream().wait_event(self._last_copy_event)
                 self._last_copy_event = None
+                self._actor_events.clear()
 
     # ------------------------------------------------------------------ public API
     def save(self, actor: str, state_name: Optional[str], state: Any, cover: bool = False,
@@ -351,6 +360,8 @@ class CheckpointStore:
             self._copy_stream = torch.cuda.Stream(cuda_dev)
         self._reap(block=False)
         snap, base, nbytes, event = self._stage(state, cuda_dev)
+        if event is not None:
+            self._actor_events[actor] = event
         if base < 0:                                           # does not fit in the staging arena
             self._save_inline(path, state, post)
             return

@@ -31,7 +31,8 @@ ENGINE_DEFAULTS: Dict[str, Any] = {
     "cache_prototypes": False,        # FedSTIL: recompute the frozen-trunk pass every epoch like the reference
     "reference_compat": True,         # reproduce documented reference quirks
     "val_at_round0": True,
-    "train_l1_anchor": False,         # FedSTIL: also train the L1 anchor like the reference's optimizer does (quirk)
+    "train_l1_anchor": None,          # FedSTIL: also train the L1 anchor like the reference's optimizer does (quirk,
+                                      # fused into the optimizer kernel); None -> follows `reference_compat`
     "init_state": None,               # path of a {server/client name | "*": net state_dict} table loaded at build time
 }
 

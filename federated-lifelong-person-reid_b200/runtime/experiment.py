@@ -99,6 +99,12 @@ class ExperimentStage:
             if self.world > 1:
                 return torch.device("cuda", self.local_rank % torch.cuda.device_count())
             first = next(str(d) for d in devices if str(d).startswith("cuda"))
+            n_cuda = len({str(d) for d in devices if str(d).startswith("cuda")})
+            if n_cuda > 1:
+                # the reference spreads client threads over every listed device inside one process; this engine is
+                # one process per GPU
+                self.logger.warn(f"{n_cuda} CUDA devices are configured but WORLD_SIZE is 1: only {first} is used. "
+                                 f"Launch with `torchrun --nproc-per-node {n_cuda} main.py ...` to use all of them.")
             return torch.device(first if ":" in first else "cuda:0")
         return torch.device("cpu")
 
@@ -254,6 +260,8 @@ class ExperimentStage:
             store.muted = (curr_round % every) != 0
         if self.device.type == "cuda" and store is not None:
             store.fence()                 # snapshot DMAs of the previous round precede any overwrite of their sources
+        if comm is not None:
+            comm.poll_errors()
 
         # ---- server -> clients ------------------------------------------------------------------------------------
         with timer("dispatch"):
@@ -311,7 +319,13 @@ class ExperimentStage:
                 elif federated:
                     server.set_client_incremental_state(n, None)      # slot lives on another rank
         with timer("aggregate"):
+            if store is not None and self.device.type == "cuda":
+                # calculate() overwrites the server replica in place: snapshots staged from live views of it (dispatch
+                # payloads, the server model) must have left the device first; client snapshots keep streaming
+                store.fence(server.name)
             server.calculate()
+        if comm is not None:
+            comm.poll_errors()            # a missed barrier surfaces in the round it happened, not at the very end
         log.flush()
 
     def _train_parallel(self, todo, log, curr_round: int, workers: int) -> None:

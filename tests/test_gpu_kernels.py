@@ -230,6 +230,46 @@ def test_fused_optimizer(kind):
     _close(shadow.float().cpu(), cpu[0], rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize("kind", ["adam", "sgd"])
+def test_fused_trained_l1_anchor(kind):
+    """FedSTIL's trained L1 anchor inside ``fused_opt_kernel`` (reference quirk, fedstil.py:53-76,639-647) against the
+    fp32 tensor-op form on the CPU (``ArenaOptimizer._anchor_step``, the one the golden tests compare with the
+    reference) over several steps: weights, anchor, both moment pairs, the bf16 shadow and the reported L1 sum."""
+    import torch.nn as nn
+    from flpr_b200.runtime.arena import ArenaOptimizer, ParamArena
+    outs = {}
+    for dev in ("cpu", "cuda"):
+        torch.manual_seed(11)
+        lin1, lin2 = nn.Linear(256, 512, bias=False), nn.Linear(512, 64)
+        params = [("a.weight", lin1.weight), ("b.weight", lin2.weight), ("b.bias", lin2.bias)]
+        arena = ParamArena(params, dev, shadow=dev == "cuda", first=lambda n: n == "a.weight")
+        opt = ArenaOptimizer(kind, arena, lr=1e-3 if kind == "adam" else 0.05, weight_decay=1e-4, momentum=0.9)
+        n = arena.prefix_numel
+        torch.manual_seed(12)
+        G = (arena.master[:n].cpu() + 0.01 * torch.randn(n)).to(dev)
+        opt.G, opt.lam1, opt.atten = G, 1e-2, 0.9
+        opt.anchor = G.clone()
+        opt.stats = torch.zeros(2, device=dev)
+        for step in range(4):
+            torch.manual_seed(100 + step)
+            g = torch.randn(arena.numel) * (torch.rand(arena.numel) > 0.3)     # exact zeros: the sign(0) = 0 rule
+            arena.grad.copy_(g.to(dev))
+            opt.step()
+        outs[dev] = [arena.master.cpu(), opt.anchor.cpu(), opt.m.cpu(),
+                     opt.anchor_m.cpu() if opt.anchor_m is not None else torch.zeros(1), opt.stats.cpu(),
+                     arena.shadow.float().cpu() if arena.shadow is not None else None]
+        if dev == "cuda":
+            assert opt.anchor_m is not None                      # the fused path allocated the anchor's moments
+    c, g = outs["cpu"], outs["cuda"]
+    _close(g[0], c[0], rtol=1e-4, atol=2e-6)
+    _close(g[1], c[1], rtol=1e-4, atol=2e-6)
+    _close(g[2], c[2], rtol=1e-3, atol=1e-5)
+    _close(g[3], c[3], rtol=1e-3, atol=1e-6)
+    _close(g[4][1:], c[4][1:], rtol=1e-3, atol=1e-2)
+    _close(g[5], c[0], rtol=1e-2, atol=1e-2)
+    assert (c[1] - G.cpu()).abs().max() > 1e-5                   # the anchor did move
+
+
 def test_importance_and_cast_and_compose():
     from flpr_b200.ops.fused import importance_accumulate, cast_bf16, compose_adaptive
     n = 4096 * 33
