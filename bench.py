@@ -29,6 +29,26 @@ sys.path.insert(0, ROOT)
 
 METRIC = "images/sec aggregate over 8 clients (FedSTIL ResNet-50 federated round, 256x128)"
 
+# method-specific ``model_opts`` (the values of configs/b200/*.yaml) and the checkpoint name of the reference's configs
+METHOD_MODEL_OPTS = {
+    "fedstil": {"atten_default": 0.9, "lambda_l1": 1e-3},
+    "fedstil-atten": {"atten_default": 0.9, "lambda_l1": 1e-3},
+    "fedweit": {"lambda_l1": 1e-3, "lambda_l2": 100.0, "lambda_mask": 0.0, "kb_cnt": 5},
+    "fedprox": {"lambda_l2": 1e-2},
+    "fedcurv": {"lambda_penalty": 10.0},
+    "ewc": {"lambda_penalty": 50.0},
+    "mas": {"lambda_penalty": 0.01},
+    "icarl": {"n_classes": 10},
+}
+LOCAL_ONLY = ("baseline", "ewc", "mas", "icarl")          # single-client lifelong methods (BASELINE config 5)
+
+
+def metric_name(a) -> str:
+    if a.method == "fedstil" and a.model == "resnet50" and a.clients == 8:
+        return METRIC
+    return (f"images/sec aggregate over {a.clients} clients ({a.method} {a.model} federated round, "
+            f"{a.height}x{a.width})")
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -42,6 +62,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--epochs", type=int, default=1)
     ap.add_argument("--model", default="resnet50")
+    ap.add_argument("--method", default="fedstil",
+                    help="federated / continual method (BASELINE configs 3 and 5: fedcurv, ewc, mas, icarl, ...)")
     ap.add_argument("--height", type=int, default=256)
     ap.add_argument("--width", type=int, default=128)
     ap.add_argument("--parallel", type=int, default=3,
@@ -111,10 +133,12 @@ def build_config(a, impl: str, world: int):
               "device": ["cpu"] if a.cpu_debug else [f"cuda:{i}" for i in range(max(a.gpus, 1))],
               "defaults": {}}
     exp = {
-        "exp_name": "bench-fedstil", "exp_method": "fedstil", "random_seed": 123,
+        "exp_name": f"bench-{a.method}", "exp_method": a.method, "random_seed": 123,
         "exp_opts": {"comm_rounds": 10 ** 6, "val_interval": 10 ** 9, "online_clients": a.clients},
-        "model_opts": {"name": a.model, "num_classes": 8000, "last_stride": 1, "neck": "bnneck", "atten_default": 0.9,
-                       "lambda_l1": 1e-3, "lambda_k": a.images,
+        "model_opts": {"name": a.model, "num_classes": 8000, "last_stride": 1, "neck": "bnneck",
+                       **METHOD_MODEL_OPTS.get(a.method, {}),
+                       **({"lambda_k": a.images} if a.method.startswith("fedstil") else {}),
+                       **({"k": a.images} if a.method == "icarl" else {}),
                        "fine_tuning": ["base.layers.3", "classifier"] if a.model.startswith("swin")
                        else ["base.layer4", "classifier"]},
         "criterion_opts": {"name": "cross_entropy", "num_classes": 8000, "epsilon": 0.1},
@@ -126,7 +150,8 @@ def build_config(a, impl: str, world: int):
                       "loader_opts": {"batch_size": a.batch, "num_workers": 0, "pin_memory": False,
                                       "persistent_workers": False, "multiprocessing_context": None}},
         "server": {"server_name": "server", "distance_calculate_step": 10, "distance_calculate_decay": 0.8},
-        "clients": [{"client_name": f"client-{i}", "model_ckpt_name": "fedstil_model",
+        "clients": [{"client_name": f"client-{i}",
+                     **({"model_ckpt_name": "fedstil_model"} if a.method.startswith("fedstil") else {}),
                      "tasks": [f"task-{i}-{t}" for t in range(5)]} for i in range(a.clients)],
         "engine_opts": {"compute_dtype": "bf16", "comm_mode": "nccl" if impl == "nccl" else None,
                         "val_at_round0": False, "checkpoints": not a.no_ckpt, "save_payload_ckpts": not a.no_ckpt},
@@ -137,13 +162,18 @@ def build_config(a, impl: str, world: int):
 def bench_config(a, impl: str, parallelism: str) -> dict:
     """The ``config`` block of the JSON line: the SAME keys and values for every arm (arm-specific remarks go to
     ``notes``), so that a config diff between the arms shows real differences only."""
-    return {"model": a.model, "method": "fedstil", "clients": a.clients, "global_batch": a.batch * a.clients,
+    return {"model": a.model, "method": a.method, "clients": a.clients, "global_batch": a.batch * a.clients,
             "batch_per_client": a.batch, "images_per_client_task": a.images, "ids_per_task": a.ids, "seq_len": None,
-            "img_size": [a.height, a.width], "epochs_per_round": a.epochs, "rehearsal_lambda_k": a.images,
-            "optimizer": "adam lr 1e-3 wd 1e-5", "lambda_l1": 1e-3, "atten_default": 0.9, "num_classes": 8000,
+            "img_size": [a.height, a.width], "epochs_per_round": a.epochs,
+            "rehearsal_lambda_k": a.images if a.method.startswith("fedstil") or a.method == "icarl" else None,
+            "optimizer": "adam lr 1e-3 wd 1e-5", "method_opts": METHOD_MODEL_OPTS.get(a.method, {}),
+            "num_classes": 8000,
             "checkpoints": "off" if a.no_ckpt else "reference layout, every round",
-            "step_definition": "one federated round: dispatch (spatial-temporal mix) + local train of all clients "
-                               "(prototype pass, head training with rehearsal, herding) + upload + aggregate",
+            "step_definition": ("one federated round: dispatch (spatial-temporal mix) + local train of all clients "
+                                "(prototype pass, head training with rehearsal, herding) + upload + aggregate")
+            if a.method.startswith("fedstil") else
+            "one communication round of the reference's loop (experiment.py:183-243): dispatch + local train of all "
+            "online clients (full backbone in train mode) + upload + aggregate",
             "l2": "inputs larger than L2 (per-round working set >> 126 MB: 8 x 400 MB client state + images)"}
 
 
@@ -315,7 +345,7 @@ def run_flpr(a, impl: str) -> dict:
     value = imgs_per_round / (ms_per_step / 1e3)
     e2e_value = imgs_per_round / (e2e_ms / a.steps / 1e3)
     out = {
-        "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
+        "metric": metric_name(a), "value": round(value, 2), "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16" if not a.cpu_debug else "fp32",
         "data": "synthetic 256x128 uint8 crops in pinned host memory, random-init weights",
@@ -341,13 +371,17 @@ def run_flpr(a, impl: str) -> dict:
 # ================================================================================================== reference arm
 def run_reference(a) -> dict:
     from baseline.reference_arm import run_reference_arm
-    return run_reference_arm(a, build_config, cleanup_payloads, METRIC, ClockSampler, bench_config, convergence_block)
+    return run_reference_arm(a, build_config, cleanup_payloads, metric_name(a), ClockSampler, bench_config,
+                             convergence_block)
 
 
 def main():
     a = parse_args()
+    if a.method in LOCAL_ONLY and "--clients" not in sys.argv:
+        a.clients = 1
     if a.cpu_debug:
-        a.model, a.images, a.ids, a.batch, a.height, a.width, a.clients = "resnet18", 16, 4, 8, 64, 32, 2
+        a.model, a.images, a.ids, a.batch, a.height, a.width = "resnet18", 16, 4, 8, 64, 32
+        a.clients = min(a.clients, 2)
     try:
         if a.impl == "reference":
             out = run_reference(a)

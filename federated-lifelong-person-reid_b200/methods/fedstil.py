@@ -432,39 +432,6 @@ class Operator(OperatorModule):
         with model.autocast():
             return model.forward_head(data)
 
-    def _ce_stats_ok(self, model: Model) -> bool:
-        """The fused CE kernel already produces the loss sum and the top-1 hit count on the device: when the only
-        criterion is the label-smoothing CE over the classifier's full width, use its accumulator instead of a
-        separate argmax / compare / sum chain (5 small kernels per step)."""
-        from ..criterions import CrossEntropyLabelSmooth
-        cls = getattr(model.net, "classifier", None)
-        return (len(self.criterion) == 1 and isinstance(self.criterion[0], CrossEntropyLabelSmooth)
-                and cls is not None and getattr(cls, "out_features", -1) == self.criterion[0].num_classes)
-
-    def _graphed_step(self, model: Model):
-        """One head training step (zero-grad, forward, CE, backward, fused Adam+L1) as a replayable CUDA graph."""
-        st = getattr(self, "_step", None)
-        if st is None:
-            from ..runtime.graphs import GraphedStep
-            self._acc = torch.zeros(2, dtype=torch.float64, device=model.device)
-            self._ce_acc = torch.zeros(2, dtype=torch.float32, device=model.device) if self._ce_stats_ok(model) \
-                else None
-            if self._ce_acc is not None:
-                self.criterion[0].stats = self._ce_acc
-
-            def fn(data, target):
-                self.optimizer.zero_grad()
-                out = self._invoke_train(model, data, target)
-                out["loss"].backward()
-                self.optimizer.step()
-                if self._ce_acc is None:
-                    with torch.no_grad():
-                        self._acc[0] += out["loss"].detach().double()
-                        self._acc[1] += (out["score"].argmax(dim=1) == target).sum()
-
-            st = self._step = GraphedStep(fn, warmup=2, enabled=getattr(model, "use_cuda_graphs", True))
-        return st
-
     def invoke_train(self, model: Model, dataloader, **kwargs) -> Dict:
         from ..utils.trace import nvtx_range
         device = model.device
@@ -485,16 +452,12 @@ class Operator(OperatorModule):
         acc.zero_()
         if self._ce_acc is not None:
             self._ce_acc.zero_()
-        fast = getattr(model.net, "_fast_head", None) if device.type == "cuda" else None
-        if fast is not None:
-            fast.count_batches = False                # 13 one-element kernels per step -> 13 per epoch (below)
+        self._bn_counters(model, on=False)            # 13 one-element kernels per step -> 13 per epoch (below)
         for b in range(n_batches):
             idx = perm[b * bs:(b + 1) * bs]
             step(protos[idx], pids[idx])
             data_cnt += len(idx)
-        if fast is not None:
-            fast.add_batches(n_batches)
-            fast.count_batches = True
+        self._bn_counters(model, on=True, add=n_batches)
         src = acc if self._ce_acc is None else self._ce_acc.double()
         vals = torch.cat([src, self.optimizer.stats.double()]).tolist()      # single host sync per epoch
         loss_sum, hits, _, l1_sum = vals

@@ -167,7 +167,13 @@ class ResNetReID(nn.Module):
         return start
 
     def forward_trunk(self, x: torch.Tensor) -> torch.Tensor:
-        """Frozen part: input image batch -> feature map at the cut ("prototype" in FedSTIL terms)."""
+        """Frozen part: input image batch -> feature map at the cut ("prototype" in FedSTIL terms).
+        On CUDA with a bf16 fast head the frozen stages run on the tcgen05 kernels too (:class:`NativeTrunk`) - in
+        train mode with batch-statistic BN and running-stat updates, which is what the reference's ``model.train()``
+        does to the whole net for every method but FedSTIL (``methods/baseline.py:38``, ``models/resnet.py:229-241``)."""
+        nt = getattr(self, "_native_trunk", None)
+        if nt is not None and x.is_cuda and nt.supported(tuple(x.shape)):
+            return nt(x)
         return self.base.run_stages(x, 0, self.head_start)
 
     def forward_head(self, fmap: torch.Tensor):
@@ -224,11 +230,31 @@ class FastResNetHead:
         v = w.permute(0, 2, 3, 1)
         return v if v.is_contiguous() else v.contiguous()
 
-    def _conv(self, x: torch.Tensor, conv: nn.Conv2d, want_stats: bool = False):
+    @staticmethod
+    def _weight_of(layer: nn.Module):
+        """``(weight, kernel, stride)`` of a convolution / linear leaf. Plain ``nn.Conv2d`` / ``nn.Linear`` (also
+        parametrized ones: fedstil-atten's ``weight`` is ``gw_stack @ atten + aw``) expose ``.weight``; FedWeIT's
+        decomposed layers compose ``theta = mask (.) sw + aw + sum_k atten_k aw_kb[..., k]`` on access
+        (``methods/fedweit.py``). A composed weight is an autograd tensor: the native conv / GEMM returns its fp32
+        gradient to autograd, which carries it on into ``aw`` / ``mask`` / ``atten``."""
+        if hasattr(layer, "theta"):
+            w = layer.theta(layer.training)
+            k = w.shape[-1] if w.dim() == 4 else 1
+            s = int(layer.stride[0]) if getattr(layer, "is_conv", False) else 1
+            return w, k, s
+        w = layer.weight
+        if w.dim() == 4:
+            return w, layer.kernel_size[0], layer.stride[0]
+        return w, 1, 1
+
+    def _conv(self, x: torch.Tensor, conv: nn.Module, want_stats: bool = False):
         """x: [N,H,W,C] bf16 -> [N,H',W',Cout] bf16 (``(y, col_part)`` with ``want_stats``: fused BN statistics)"""
-        w = conv.weight
+        w, k, s = self._weight_of(conv)
         sh = self.shadow(w)
-        k, s = conv.kernel_size[0], conv.stride[0]
+        if sh is None and not w.requires_grad and x.is_cuda and isinstance(w, nn.Parameter):
+            sh = self._frozen_bf16(w)
+        if getattr(conv, "bias", None) is not None:
+            raise NotImplementedError("convolutions with a bias are not covered by the fast head")
         n, h, wd, c = x.shape
         gs = self.grad_slot(w)
         if k == 1 and s == 1:
@@ -243,11 +269,37 @@ class FastResNetHead:
                                                                    or (h * wd > 128 and h % (128 // wd) == 0)):
             return gops.conv3x3(x, self._ohwi(w), self._ohwi(sh) if sh is not None else None,
                                 self._ohwi(gs) if gs is not None else None, want_stats)
-        # library fallback (strided convs)
+        if not (torch.is_grad_enabled() and (w.requires_grad or x.requires_grad)) and \
+                gops.conv_supported(h, wd, c, k, s):
+            # forward-only (frozen stage, or no_grad): any stride / kernel size the implicit GEMM covers
+            wb = self._ohwi(sh if sh is not None else self._frozen_bf16(w))
+            ho, wo = (h + 2 * (k // 2) - k) // s + 1, (wd + 2 * (k // 2) - k) // s + 1
+            part = gops.col_part_buffer(n * ho * wo, w.shape[0], x.device) if want_stats else None
+            y = gops.conv_nhwc(x, wb, padding=k // 2, stride=s, col_part=part)
+            return (y, part) if want_stats else y
+        # library fallback (strided convs that need a gradient)
         y = F.conv2d(x.permute(0, 3, 1, 2), (sh if sh is not None else w.to(torch.bfloat16)) if not w.requires_grad
                      else w.to(torch.bfloat16), stride=s, padding=k // 2)
         y = y.permute(0, 2, 3, 1).contiguous()
         return (y, None) if want_stats else y
+
+    # bf16 channels_last copies of FROZEN weights (not in the arena, so no optimizer-maintained shadow exists);
+    # refreshed when the parameter is overwritten in place (first-contact dispatch, checkpoint restore)
+    def _frozen_bf16(self, w: torch.Tensor) -> torch.Tensor:
+        if not isinstance(w, nn.Parameter):             # a composed (temporary) weight: nothing to cache
+            wb = w.detach().to(torch.bfloat16)
+            return wb.contiguous(memory_format=torch.channels_last) if wb.dim() == 4 else wb
+        cache = self.__dict__.setdefault("_frozen_cache", {})
+        key = id(w)
+        hit = cache.get(key)
+        if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
+            return hit[2]
+        with torch.no_grad():
+            wb = w.detach().to(torch.bfloat16)
+            if wb.dim() == 4:
+                wb = wb.contiguous(memory_format=torch.channels_last)
+        cache[key] = (w._version, w.data_ptr(), wb)
+        return wb
 
     def _conv_bn(self, x: torch.Tensor, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool,
                  residual: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -321,11 +373,92 @@ class FastResNetHead:
             feat = global_feat.to(torch.bfloat16)
         if not m.training:
             return global_feat
-        w = m.classifier.weight
+        w = self._weight_of(m.classifier)[0]
         score = gops.linear(feat, w, self.shadow(w), self.grad_slot(w))
         if m.classifier.bias is not None:
             score = score + m.classifier.bias.to(score.dtype)
         return score, global_feat
+
+
+class NativeTrunk(FastResNetHead):
+    """The frozen stages (stem + ``layer1..k-1``) on the tcgen05 kernels, forward only - nothing in them is trainable
+    and their input does not require grad, so no autograd graph is built. ``model.train()``: every BatchNorm
+    normalises with the batch statistics that the producing convolution's epilogue emitted and updates its running
+    statistics (``bn_finalize``); ``model.eval()``: running statistics (``affine_act``).
+
+    Stem: the 7x7 / 2 convolution runs as a 4x4 convolution over 2x2 space-to-depth cells (``ops.gemm.stem_conv``),
+    then BN + ReLU, then the NHWC max-pool kernel. Strided 3x3 / 1x1 convolutions use TMA element strides."""
+
+    def __init__(self, model: ResNetReID):
+        super().__init__(model, None, None)
+        self._stem_cache = None
+
+    def supported(self, shape) -> bool:
+        cache = self.__dict__.setdefault("_ok_cache", {})
+        hit = cache.get(shape)
+        if hit is not None:
+            return hit
+        m = self.m
+        ok = m.head_start >= 1 and len(shape) == 4 and shape[1] == 3 and gops.stem_supported(shape[2], shape[3]) \
+            and m.base.conv1.weight.shape[0] % 32 == 0
+        if ok:
+            h, w = shape[2] // 2, shape[3] // 2
+            h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1                       # 3x3 / 2 max-pool
+            for i in range(1, m.head_start):
+                for u in getattr(m.base, f"layer{i}"):
+                    convs = [u.conv1, u.conv2] + ([u.conv3] if u.kind != "basic" else [])
+                    if u.downsample is not None:
+                        c = u.downsample[0]
+                        ok = ok and self._fits(h, w, c)
+                    for c in convs:
+                        ok = ok and self._fits(h, w, c)
+                        k, st = c.kernel_size[0], c.stride[0]
+                        h, w = (h + 2 * (k // 2) - k) // st + 1, (w + 2 * (k // 2) - k) // st + 1
+        cache[shape] = bool(ok)
+        return bool(ok)
+
+    @staticmethod
+    def _fits(h: int, w: int, conv: nn.Conv2d) -> bool:
+        k, st, cin = conv.kernel_size[0], conv.stride[0], conv.in_channels
+        if k == 1 and st == 1:
+            return cin % 8 == 0
+        return gops.conv_supported(h, w, cin, k, st)
+
+    def _stem(self, x: torch.Tensor) -> torch.Tensor:
+        """``x``: [B,3,H,W] (any memory format / float dtype) -> [B,H/4,W/4,64] bf16 NHWC."""
+        base = self.m.base
+        w = base.conv1.weight
+        hit = self._stem_cache
+        if hit is None or hit[0] != w._version or hit[1] != w.data_ptr():
+            with torch.no_grad():
+                w4 = gops.stem_weight_s2d(w.detach().float()).to(torch.bfloat16).contiguous()
+            hit = self._stem_cache = (w._version, w.data_ptr(), w4)
+        xn = x.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+        b, h, wd, _ = xn.shape
+        bn = base.bn1
+        if bn.training:
+            part = gops.col_part_buffer(b * (h // 2) * (wd // 2), w.shape[0], x.device)
+            y = gops.stem_conv(xn, hit[2], None, relu=False, col_part=part)
+            y = self._bn(y, bn, True, None, part)
+        else:
+            y = self._bn(gops.stem_conv(xn, hit[2], None, relu=False), bn, True)
+        return gops.maxpool3x3s2(y)
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        m = self.m
+        y = self._stem(x)
+        for i in range(1, m.head_start):
+            for u in getattr(m.base, f"layer{i}"):
+                y = self._unit(y, u)
+        return y.permute(0, 3, 1, 2)                     # logical NCHW over channels_last storage
+
+    def batch_norms(self):
+        m = self.m
+        out = [m.base.bn1] if m.head_start >= 1 else []
+        out += [b for i in range(1, m.head_start) for b in getattr(m.base, f"layer{i}").modules()
+                if isinstance(b, nn.BatchNorm2d)]
+        return out
 
 
 def _make(name: str):

@@ -359,9 +359,11 @@ def stem_supported(h: int, w: int) -> bool:
     return (128 % (ho * wo) == 0) if ho * wo <= 128 else (ho % (128 // wo) == 0)
 
 
-def stem_conv(x: torch.Tensor, w4: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True) -> torch.Tensor:
+def stem_conv(x: torch.Tensor, w4: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True,
+              col_part: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ResNet stem (7x7 / 2 / pad 3 convolution + folded-BN bias + ReLU) on the implicit-GEMM kernel.
-    ``x``: ``[B,H,W,3]`` bf16 NHWC, ``w4``: :func:`stem_weight_s2d` of the (folded) weight. Returns ``[B,H/2,W/2,Cout]``."""
+    ``x``: ``[B,H,W,3]`` bf16 NHWC, ``w4``: :func:`stem_weight_s2d` of the (folded) weight. Returns ``[B,H/2,W/2,Cout]``.
+    ``col_part``: fused batch-norm statistics of the output (train-mode BN after an un-folded stem)."""
     b, h, w, _ = x.shape
     cout = w4.shape[0]
     y2 = s2d_pad(x)                                            # [B, H2, W2, 16]
@@ -373,6 +375,8 @@ def stem_conv(x: torch.Tensor, w4: torch.Tensor, bias: Optional[torch.Tensor], r
         rows = win.unfold(1, 4, 1)                             # [B, ho, wo, 64, 4]
         a = rows.permute(0, 1, 2, 4, 3).reshape(b * ho * wo, 256)
         out = a @ w4.float().reshape(cout, 256).t()
+        if col_part is not None:
+            _col_part_reference(out.to(torch.bfloat16).float(), col_part)
         if bias is not None:
             out = out + bias.float()
         if relu:
@@ -383,8 +387,8 @@ def stem_conv(x: torch.Tensor, w4: torch.Tensor, bias: Optional[torch.Tensor], r
     out = torch.empty(b, ho, wo, cout, dtype=torch.bfloat16, device=x.device)
     # the input seen by the conv kernel: [B, H2, wo, 64] with a 16-element (one cell) W stride -> overlapping windows
     rc = lib.flpr_conv_nhwc_bf16(native.ptr(y2), native.ptr(w4), native.ptr(out), b, h2, wo, 64, cout, 4, 1, 0, 0, 1,
-                                 1.0, native.ptr(bias), int(relu), None, 0, None, 1, 16, w2 * 16, h2 * w2 * 16,
-                                 native.stream(x.device))
+                                 1.0, native.ptr(bias), int(relu), None, 0, native.ptr(col_part), 1, 16, w2 * 16,
+                                 h2 * w2 * 16, native.stream(x.device))
     native.check(rc, "flpr_conv_nhwc_bf16 (stem)")
     native.count_launch()
     return out

@@ -76,9 +76,11 @@ class ModelModule(nn.Module):
             self.rng = torch.Generator(device=device)
             self.rng.manual_seed((torch.initial_seed() + 7919 * _RNG_STREAMS) % (1 << 62))
         if device.type == "cuda" and self.compute_dtype == torch.bfloat16:
-            from ..models.resnet import FastResNetHead, ResNetReID
+            from ..models.resnet import FastResNetHead, NativeTrunk, ResNetReID
             if isinstance(self.net, ResNetReID) and 1 <= self.net.head_start <= 4:
                 self.net._fast_head = FastResNetHead(self.net, self.arena.shadow_of, self.arena.grad_of)
+                if getattr(self, "use_native_trunk", True):
+                    self.net._native_trunk = NativeTrunk(self.net)
         return self
 
     def autocast(self):
@@ -184,26 +186,90 @@ class OperatorModule:
         score, feature = self.forward_train(model, data)
         return {"score": score, "feature": feature, "loss": self.compute_loss(model, score, feature, target)}
 
+    # ---- CUDA-graph capture of one training step ------------------------------------------------------------------
+    # A step of the ResNet path is ~400 kernel launches (native trunk + head forward / backward + fused optimizer)
+    # whose Python dispatch costs several times their device time; the step is free of host synchronisation (loss /
+    # accuracy accumulate on the device), so it is captured once per input shape and replayed.
+    graph_step = True                  # sub-classes whose step is not capturable (host-side control flow) clear it
+
+    def _ce_stats_ok(self, model: ModelModule) -> bool:
+        """The fused CE kernel already produces the loss sum and the top-1 hit count on the device: when the only
+        criterion is the label-smoothing CE over the classifier's full width, use its accumulator instead of a
+        separate argmax / compare / sum chain (5 small kernels per step)."""
+        from ..criterions import CrossEntropyLabelSmooth
+        cls = getattr(model.net, "classifier", None)
+        return (len(self.criterion) == 1 and isinstance(self.criterion[0], CrossEntropyLabelSmooth)
+                and cls is not None and getattr(cls, "out_features", -1) == self.criterion[0].num_classes
+                and model.device.type == "cuda")
+
+    def _graph_capable(self, model: ModelModule) -> bool:
+        return (self.graph_step and model.device.type == "cuda" and getattr(model, "use_cuda_graphs", True)
+                and getattr(model.net, "thread_safe_rng", False) and getattr(model.net, "_fast_head", None) is not None)
+
+    def _graphed_step(self, model: ModelModule):
+        """One training step (zero-grad, forward, loss, backward, fused optimizer) as a replayable CUDA graph
+        (eager on the CPU / when capture is not possible); loss / hit accumulators live in ``self._acc``."""
+        st = getattr(self, "_step", None)
+        if st is None:
+            from .graphs import GraphedStep
+            self._acc = torch.zeros(2, dtype=torch.float64, device=model.device)
+            self._ce_acc = torch.zeros(2, dtype=torch.float32, device=model.device) if self._ce_stats_ok(model) \
+                else None
+            if self._ce_acc is not None:
+                self.criterion[0].stats = self._ce_acc
+
+            def fn(data, target):
+                self.optimizer.zero_grad()
+                out = self._invoke_train(model, data, target)
+                out["loss"].backward()
+                self.optimizer.step()
+                if self._ce_acc is None:
+                    with torch.no_grad():
+                        self._acc[0] += out["loss"].detach().double()
+                        self._acc[1] += (out["score"].argmax(dim=1) == target).sum()
+
+            st = self._step = GraphedStep(fn, warmup=2, enabled=self._graph_capable(model))
+        return st
+
+    def _step_totals(self) -> Tuple[float, float]:
+        """(loss sum, top-1 hits) accumulated by the steps since the accumulators were last zeroed: ONE host sync."""
+        src = self._acc if self._ce_acc is None else self._ce_acc.double()
+        loss_sum, hits = src.tolist()
+        return loss_sum, hits
+
+    def _zero_step_totals(self) -> None:
+        self._acc.zero_()
+        if self._ce_acc is not None:
+            self._ce_acc.zero_()
+
+    @staticmethod
+    def _bn_counters(model: ModelModule, on: bool, add: int = 0) -> None:
+        """``num_batches_tracked`` bookkeeping of the native trunk / head: one tiny kernel per BN layer per step ->
+        one per BN layer per epoch."""
+        for name in ("_native_trunk", "_fast_head"):
+            fast = getattr(model.net, name, None)
+            if fast is not None and model.device.type == "cuda":
+                if add:
+                    fast.add_batches(add)
+                fast.count_batches = on
+
     def invoke_train(self, model: ModelModule, dataloader, **kwargs) -> Dict:
         device = model.device
         model.train()
         self.begin_epoch()
-        acc = torch.zeros(2, dtype=torch.float64, device=device)       # [loss sum, top-1 hits] – stays on device
         batch_cnt = data_cnt = 0
         if self.optimizer.stats is not None:
             self.optimizer.stats.zero_()
+        step = self._graphed_step(model)
+        self._zero_step_totals()
+        self._bn_counters(model, on=False)
         for data, person_id, classes_id in dataloader:
             data, target = model.prepare_input(data), person_id.to(device, non_blocking=True)
-            self.optimizer.zero_grad()
-            out = self._invoke_train(model, data, target, **kwargs)
-            out["loss"].backward()
-            self.optimizer.step()
-            with torch.no_grad():
-                acc[0] += out["loss"].detach().double()
-                acc[1] += (out["score"].argmax(dim=1) == target).sum()
+            step(data, target)
             data_cnt += len(data)
             batch_cnt += 1
-        loss_sum, hits = acc.tolist()                                   # the only host sync of the epoch
+        self._bn_counters(model, on=True, add=batch_cnt)
+        loss_sum, hits = self._step_totals()                            # the only host sync of the epoch
         train_loss = loss_sum / max(batch_cnt, 1) + self.extra_loss_value(model, batch_cnt)
         if self.scheduler:
             self.scheduler.step()

@@ -93,7 +93,10 @@ def test_graphed_step_matches_eager():
     assert diff < 5e-3, diff          # split-K atomics make the two runs non-bit-identical
 
 
-@pytest.mark.parametrize("method", ["fedstil", "fedavg", "fedcurv", "ewc"])
+ALL_METHODS = ["baseline", "ewc", "mas", "icarl", "fedavg", "fedprox", "fedcurv", "fedweit", "fedstil", "fedstil-atten"]
+
+
+@pytest.mark.parametrize("method", ALL_METHODS)
 def test_experiment_on_gpu(tmp_path, method):
     from flpr_b200.ops import native
     from flpr_b200.runtime.experiment import ExperimentStage
@@ -223,3 +226,82 @@ def test_fedstil_swin_experiment_on_gpu(tmp_path):
             for vals in tasks.values():
                 for k, v in vals.items():
                     assert v == v and 0.0 <= v <= 1e4, (k, v)
+
+
+@pytest.mark.parametrize("name,size,batch", [("resnet50", (256, 128), 16), ("resnet18", (128, 64), 8)])
+def test_native_train_mode_trunk_matches_module(name, size, batch):
+    """Frozen stages in TRAIN mode (what the reference's ``model.train()`` does to the whole net for every method but
+    FedSTIL, ``methods/baseline.py:38``): batch-statistic BN fed by the conv epilogue's fused statistics, running-stat
+    updates, strided convolutions via TMA element strides, native stem + max-pool - against the fp32 ``nn.Module``."""
+    import copy as _copy
+    from flpr_b200.models import resnet as R
+    torch.manual_seed(4)
+    net = getattr(R, name)(num_classes=10, last_stride=1, neck="bnneck").cuda()
+    net.configure_split(["base.layer4", "classifier"])
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.1)
+    ref = _copy.deepcopy(net).float()
+    trunk = R.NativeTrunk(net)
+    x = torch.randn(batch, 3, *size, device="cuda").contiguous(memory_format=torch.channels_last)
+    assert trunk.supported(tuple(x.shape))
+    net.train(), ref.train()
+    from flpr_b200.ops import native
+    before = native.launches()
+    y = trunk(x)
+    assert native.launches() - before > 50
+    with torch.no_grad():
+        yr = ref.base.run_stages(x, 0, net.head_start)
+    assert y.shape == yr.shape
+    err = (y.float() - yr).abs().max().item()
+    assert err < 0.08 * yr.abs().max().item() + 0.05, (err, yr.abs().max().item())
+    cos = torch.nn.functional.cosine_similarity(y.float().flatten(), yr.flatten(), dim=0).item()
+    assert cos > 0.995, cos
+    # running statistics were updated like nn.BatchNorm2d does (momentum 0.1, unbiased variance)
+    for (n1, b1), (n2, b2) in zip(net.base.named_modules(), ref.base.named_modules()):
+        if isinstance(b1, torch.nn.BatchNorm2d) and not n1.startswith("layer4"):
+            assert torch.allclose(b1.running_mean, b2.running_mean, rtol=0.05, atol=0.02), n1
+            assert torch.allclose(b1.running_var, b2.running_var, rtol=0.08, atol=0.02), n1
+    # eval mode: running statistics
+    net.eval(), ref.eval()
+    y = trunk(x)
+    with torch.no_grad():
+        yr = ref.base.run_stages(x, 0, net.head_start)
+    cos = torch.nn.functional.cosine_similarity(y.float().flatten(), yr.flatten(), dim=0).item()
+    assert cos > 0.995, cos
+
+
+def test_fedavg_training_step_launches_no_library_conv_or_batchnorm(tmp_path):
+    """BASELINE configs 3 / 5 (FedAvg-family and local continual methods train the whole net in ``model.train()``):
+    a captured training step of such a method contains no cuDNN / cuBLAS / ATen batch-norm kernel any more."""
+    from torch.profiler import ProfilerActivity, profile
+    from flpr_b200.runtime.builder import parser_criterion, parser_model
+    from flpr_b200.runtime.arena import ArenaOptimizer
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    cfg = {"name": "resnet50", "num_classes": 8000, "last_stride": 1, "neck": "bnneck",
+           "fine_tuning": ["base.layer4", "classifier"]}
+    model = parser_model("fedavg", cfg, dev, {"compute_dtype": "bf16"})
+    crit = parser_criterion({"name": "cross_entropy", "num_classes": 8000, "epsilon": 0.1})[0]
+    opt = ArenaOptimizer("adam", model.arena, lr=1e-3, weight_decay=1e-5)
+    x = torch.randn(16, 3, 256, 128, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 8000, (16,), device=dev)
+    model.train()
+
+    def step():
+        opt.zero_grad()
+        with model.autocast():
+            score, feat = model(x)
+        crit(score=score, feature=feat, target=y).backward()
+        opt.step()
+    step()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages()]
+    bad = [n for n in names if any(t in n.lower() for t in ("cudnn", "cutlass", "batch_norm", "implicit_gemm",
+                                                             "sgemm", "gemv", "cublas", "xmma"))]
+    assert not bad, bad
+    assert any("tcgen05" in n for n in names), names[:20]
