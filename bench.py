@@ -70,6 +70,11 @@ def parse_args():
                     help="clients trained concurrently per device (common.yaml `parallel`; the reference arm keeps its "
                          "shipped default of 1)")
     ap.add_argument("--no-ckpt", action="store_true", help="disable checkpoint files (not the headline config)")
+    ap.add_argument("--payload-ring", type=int, default=2,
+                    help="rounds of per-round payload checkpoints kept on the RAM disk (older rounds are recycled in "
+                         "place; the harness used to unlink them - a long run must not fill the RAM disk)")
+    ap.add_argument("--staged-ckpt", action="store_true", help="round-1 checkpoint pipeline (pinned arena + writer "
+                                                               "processes) instead of DMA into mapped files")
     ap.add_argument("--cpu-debug", action="store_true", help="tiny CPU run to exercise the harness")
     return ap.parse_args()
 
@@ -154,7 +159,8 @@ def build_config(a, impl: str, world: int):
                      **({"model_ckpt_name": "fedstil_model"} if a.method.startswith("fedstil") else {}),
                      "tasks": [f"task-{i}-{t}" for t in range(5)]} for i in range(a.clients)],
         "engine_opts": {"compute_dtype": "bf16", "comm_mode": "nccl" if impl == "nccl" else None,
-                        "val_at_round0": False, "checkpoints": not a.no_ckpt, "save_payload_ckpts": not a.no_ckpt},
+                        "val_at_round0": False, "checkpoints": not a.no_ckpt, "save_payload_ckpts": not a.no_ckpt,
+                        "mapped_checkpoints": not a.staged_ckpt, "payload_ring": a.payload_ring},
     }
     return common, exp
 
@@ -168,7 +174,7 @@ def bench_config(a, impl: str, parallelism: str) -> dict:
             "rehearsal_lambda_k": a.images if a.method.startswith("fedstil") or a.method == "icarl" else None,
             "optimizer": "adam lr 1e-3 wd 1e-5", "method_opts": METHOD_MODEL_OPTS.get(a.method, {}),
             "num_classes": 8000,
-            "checkpoints": "off" if a.no_ckpt else "reference layout, every round",
+            "checkpoints": "off" if a.no_ckpt else "reference layout, every round, flushed inside the e2e region",
             "step_definition": ("one federated round: dispatch (spatial-temporal mix) + local train of all clients "
                                 "(prototype pass, head training with rehearsal, herding) + upload + aggregate")
             if a.method.startswith("fedstil") else
@@ -257,14 +263,16 @@ def run_flpr(a, impl: str) -> dict:
         jt = threading.Thread(target=janitor, daemon=True)
         jt.start()
 
+        ringed = getattr(store, "mapped", False) and getattr(store, "payload_ring", 0) > 0
+
         def one_round(r):
             stage._process_one_round(r, server, clients, names, cfg, log, timer, comm)
-            if rank == 0 and r % 2 == 0:
+            if rank == 0 and r % 2 == 0 and not ringed:
                 janitor_q.put(r)
 
         def after_round():
             store.flush()
-            if rank == 0:
+            if rank == 0 and not ringed:
                 cleanup_payloads(common["checkpoints_dir"])
 
         r = 0
@@ -288,7 +296,8 @@ def run_flpr(a, impl: str) -> dict:
         for _ in range(a.steps):
             r += 1
             one_round(r)
-        if cuda:
+        store.flush()               # every checkpoint byte of the timed rounds has left the device before the clock
+        if cuda:                    # stops: a short run cannot hide snapshot traffic in a staging buffer
             e1.record()
         sync()
         wall_ms = (time.perf_counter() - t0) * 1e3

@@ -72,6 +72,10 @@ def _declare(lib: C.CDLL) -> None:
         "flpr_window_attn_bwd": [P, P, P, P, P, I, I, I, I, I, F, I, P],
         "flpr_s2d_pad": [P, P, I, I, I, P],
         "flpr_maxpool3x3s2": [P, P, I, I, I, I, P],
+        "flpr_memcpy_d2h_async": [P, P, Z, P],
+        "flpr_memcpy2d_d2h_async": [P, Z, P, Z, Z, Z, P],
+        "flpr_host_register": [P, Z],
+        "flpr_host_unregister": [P],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)

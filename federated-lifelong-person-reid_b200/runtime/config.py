@@ -22,6 +22,10 @@ ENGINE_DEFAULTS: Dict[str, Any] = {
     "async_checkpoint": True,         # write payload / model checkpoints off the critical path
     "save_payload_ckpts": True,       # '{round}-{src}-{dst}.ckpt' files (experiment.py:199-202,235-238)
     "checkpoint_interval": 1,         # snapshot every N-th round (1 = every round, like the reference)
+    "mapped_checkpoints": True,       # CUDA + RAM-disk checkpoints_dir: files are CUDA-registered mappings written by
+                                      # DMA (runtime/mapped_store.py); False = staged writer-process pipeline
+    "payload_ring": 0,                # keep only the last N rounds of '{round}-{src}-{dst}.ckpt' files, recycling the
+                                      # mappings of older rounds (0 = keep every round, like the reference)
     "ckpt_workers": 0,                # writer processes (0 -> 8..16 by the number of local clients)
     "ckpt_arena_gb": 0,               # pinned staging arena (0 -> 3..8 GB by the number of local clients)
     "client_threads": True,           # `parallel` clients per device train concurrently on their own CUDA streams

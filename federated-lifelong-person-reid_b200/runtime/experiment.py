@@ -150,12 +150,19 @@ class ExperimentStage:
         eng = exp_config["engine_opts"]
         names = [c["client_name"] for c in exp_config["clients"]]
         n_local = len([i for i in range(len(names)) if i % self.world == self.rank])
-        store = CheckpointStore(os.path.join(self.common_config["checkpoints_dir"], exp_config["exp_name"]),
-                                asynchronous=eng.get("async_checkpoint", True) and self.device.type == "cuda",
-                                enabled=eng.get("checkpoints", True),
-                                workers=eng.get("ckpt_workers") or min(16, max(8, 2 * n_local)),
-                                arena_bytes=int(float(eng.get("ckpt_arena_gb") or min(8.0, max(3.0, 1.5 * n_local)))
-                                                * (1 << 30)))
+        store_kw = dict(asynchronous=eng.get("async_checkpoint", True) and self.device.type == "cuda",
+                        enabled=eng.get("checkpoints", True),
+                        workers=eng.get("ckpt_workers") or min(16, max(8, 2 * n_local)),
+                        arena_bytes=int(float(eng.get("ckpt_arena_gb") or min(8.0, max(3.0, 1.5 * n_local))) * (1 << 30)))
+        ckpt_root = os.path.join(self.common_config["checkpoints_dir"], exp_config["exp_name"])
+        if eng.get("mapped_checkpoints", True) and self.device.type == "cuda" and store_kw["asynchronous"]:
+            # checkpoint files are CUDA-registered mappings, a snapshot is a set of DMAs into the file (tmpfs only;
+            # other file systems keep the staged writer pipeline)
+            from .mapped_store import MappedCheckpointStore
+            os.makedirs(ckpt_root, exist_ok=True)
+            store = MappedCheckpointStore(ckpt_root, payload_ring=int(eng.get("payload_ring", 0) or 0), **store_kw)
+        else:
+            store = CheckpointStore(ckpt_root, **store_kw)
         server = parser_server(exp_config, self.common_config, self.device, store)
         clients = parser_clients(exp_config, self.common_config, self.device, store, None, self.rank, self.world,
                                  self.source_factory)

@@ -1,0 +1,508 @@
+"""Checkpoint files as persistent, CUDA-registered file mappings: a snapshot is a set of DMAs straight into the file.
+
+The asynchronous :class:`~.checkpoint.CheckpointStore` moves a snapshot device -> pinned arena -> writer process ->
+``torch.save`` -> fresh RAM-disk pages. At 8 GPUs the federated round produces 6.5 GB of reference-layout files per
+90 ms, and the *host* side of that pipeline (page allocation + one CPU copy per byte, ~30 GB/s box-wide) becomes what
+bounds the round (``profiles/r2_scaling.md``). Here the host CPU does not touch the payload at all:
+
+* The byte layout of a checkpoint file is a pure function of the state's *structure* (keys, shapes, dtypes): the
+  legacy ``torch.save`` container is ``[pickles: magic, protocol, sys-info, object graph, storage keys]`` followed by
+  ``[int64 numel][raw bytes]`` per storage. :func:`legacy_layout` emits those pickles itself (tensors reduce to
+  ``_rebuild_tensor_v2`` over persistent storage ids, exactly what ``torch.load`` expects) and pads the storage-key
+  pickle with an ignored junk string so that the data region starts at a fixed offset even when scalars in the object
+  graph (``train_cnt``) change their encoded width from round to round.
+* The file is created once, ``mmap``-ed ``MAP_SHARED`` and page-locked with ``cudaHostRegister``. Saving = rewrite the
+  few-KB pickle prefix + one ``cudaMemcpyAsync`` per tensor from device memory into the mapping, on a copy stream
+  behind an event of the producing stream. Nothing is pickled, staged or copied by a CPU again.
+* Files whose name is unique per round (``{round}-{src}-{dst}.ckpt``) recycle the mappings of rounds that have left
+  the retention window (``engine_opts.payload_ring``; 0 = keep every round like the reference, allocating fresh
+  mappings): the old file is renamed to the new name and overwritten in place.
+* FedSTIL's exemplar file keeps the reference schema ``{np.int64 pid: [(ndarray, class_id), ...]}``
+  (``methods/fedstil.py:841,846``): its pickle is laid out once per exemplar-set structure and the fp32 prototypes are
+  DMA-ed to the recorded array offsets.
+
+Only page-cache-less file systems qualify (tmpfs / ramfs: device DMA does not mark pages dirty, a disk-backed file
+would never be written back); anything else falls back to the staged pipeline of the parent class. On the CPU the
+same layout code runs with plain ``memcpy`` - that is what the CPU test-suite exercises.
+"""
+from __future__ import annotations
+
+import collections
+import ctypes as C
+import io
+import mmap
+import os
+import pickle
+import re
+import threading
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+
+from .checkpoint import CheckpointStore
+
+_PAYLOAD_NAME = re.compile(r"^\d+-")          # '{round}-{src}-{dst}': unique per round
+_SLACK = 512                                  # bytes of padding available for growing scalars
+
+
+# ===================================================================================================== layout
+class _StorageRef:
+    __slots__ = ("key", "dtype", "numel")
+
+    def __init__(self, key: str, dtype: torch.dtype, numel: int):
+        self.key, self.dtype, self.numel = key, dtype, numel
+
+
+def _storage_type(dtype: torch.dtype):
+    """The legacy typed-storage class ``torch.load`` expects in a persistent id (``torch.FloatStorage`` ...)."""
+    return getattr(torch, torch.storage._dtype_to_storage_type_map()[dtype])
+
+
+class _Segment:
+    __slots__ = ("tensor", "offset", "nbytes")
+
+    def __init__(self, tensor: torch.Tensor, offset: int, nbytes: int):
+        self.tensor, self.offset, self.nbytes = tensor, offset, nbytes
+
+
+class Layout:
+    """Byte layout of one checkpoint file: ``prefix`` (pickles, padded to ``data_start``) + storages."""
+
+    def __init__(self, signature, data_start: int, segments: List[_Segment], total: int, headers: List[Tuple[int, int]]):
+        self.signature = signature
+        self.data_start = data_start
+        self.segments = segments
+        self.total = total
+        self.headers = headers              # (offset, numel) of the 8-byte storage headers
+
+
+def _signature(obj: Any):
+    """Structure of a state: everything that determines the byte layout except scalar values."""
+    if isinstance(obj, torch.Tensor):
+        return ("T", tuple(obj.shape), str(obj.dtype))
+    if isinstance(obj, dict):
+        return ("D", type(obj).__name__, tuple((repr(k), _signature(v)) for k, v in obj.items()))
+    if isinstance(obj, (list, tuple)):
+        return ("L", type(obj).__name__, tuple(_signature(v) for v in obj))
+    if isinstance(obj, (bool, int, float, type(None))):
+        return ("S", type(obj).__name__)
+    if isinstance(obj, str):
+        return ("s", len(obj.encode()))
+    return ("O", type(obj).__name__, len(pickle.dumps(obj, protocol=2)))
+
+
+def _main_pickle(state: Any) -> Tuple[bytes, List[Tuple[_StorageRef, torch.Tensor]]]:
+    """The object-graph pickle of the legacy container with every tensor reduced to a contiguous
+    ``_rebuild_tensor_v2`` over its own storage; returns the bytes and the storages in file order."""
+    storages: List[Tuple[_StorageRef, torch.Tensor]] = []
+    by_id: Dict[int, _StorageRef] = {}
+    buf = io.BytesIO()
+
+    class P(pickle.Pickler):
+        def persistent_id(self, obj):                                   # noqa: D401
+            if isinstance(obj, _StorageRef):
+                return ("storage", _storage_type(obj.dtype), obj.key, "cpu", obj.numel, None)
+            return None
+
+        def reducer_override(self, obj):
+            if isinstance(obj, torch.Tensor):
+                ref = by_id.get(id(obj))
+                if ref is None:
+                    ref = _StorageRef(str(len(storages)), obj.dtype, obj.numel())
+                    by_id[id(obj)] = ref
+                    storages.append((ref, obj))
+                stride = []
+                acc = 1
+                for d in reversed(obj.shape):
+                    stride.append(acc)
+                    acc *= max(int(d), 1)
+                return (torch._utils._rebuild_tensor_v2,
+                        (ref, 0, tuple(obj.shape), tuple(reversed(stride)), False, collections.OrderedDict()))
+            return NotImplemented
+
+    P(buf, protocol=2).dump(state)
+    return buf.getvalue(), storages
+
+
+_HEAD: Optional[bytes] = None
+
+
+def _head_pickles() -> bytes:
+    """magic number, protocol version, sys-info: the three leading pickles of the legacy container."""
+    global _HEAD
+    if _HEAD is None:
+        import sys
+        from torch.serialization import (INT_SIZE, LONG_SIZE, MAGIC_NUMBER, PROTOCOL_VERSION, SHORT_SIZE)
+        sys_info = {"protocol_version": PROTOCOL_VERSION, "little_endian": sys.byteorder == "little",
+                    "type_sizes": {"short": SHORT_SIZE, "int": INT_SIZE, "long": LONG_SIZE}}
+        _HEAD = b"".join(pickle.dumps(o, protocol=2) for o in (MAGIC_NUMBER, PROTOCOL_VERSION, sys_info))
+    return _HEAD
+
+
+def _keys_pickle(keys: List[str], pad: int) -> bytes:
+    """``pickle.dumps(keys)`` with ``pad`` (0 or >= 5) extra bytes that every unpickler - including torch's restricted
+    ``weights_only`` one, which knows no ``POP`` - skips over: a junk string pushed *below* the list (``BINUNICODE``),
+    which ``STOP`` leaves on the stack when it pops the result."""
+    body = pickle.dumps(list(keys), protocol=2)
+    assert body[:2] == b"\x80\x02" and (pad == 0 or pad >= 5)
+    junk = b"" if pad == 0 else b"X" + (pad - 5).to_bytes(4, "little") + b" " * (pad - 5)
+    return body[:2] + junk + body[2:]
+
+
+def legacy_layout(state: Any, data_start: Optional[int] = None) -> Tuple[Layout, bytes]:
+    """Layout + prefix bytes of ``state`` in the legacy ``torch.save`` container. With ``data_start`` (a previous
+    layout of the same structure) the prefix is padded to end exactly there; raises ``ValueError`` if it cannot."""
+    main, storages = _main_pickle(state)
+    head = _head_pickles()
+    keys = [ref.key for ref, _ in storages]
+    bare = len(head) + len(main) + len(_keys_pickle(keys, 0))
+    if data_start is None:
+        data_start = (bare + _SLACK + 63) // 64 * 64
+    pad = data_start - bare
+    if pad < 0 or 0 < pad < 5:
+        raise ValueError("prefix outgrew its slack")
+    prefix = head + main + _keys_pickle(keys, pad)
+    assert len(prefix) == data_start
+    off = data_start
+    segments, headers = [], []
+    for ref, t in storages:
+        nb = t.numel() * t.element_size()
+        headers.append((off, t.numel()))
+        segments.append(_Segment(t, off + 8, nb))
+        off += 8 + nb
+    return Layout(_signature(state), data_start, segments, off, headers), prefix
+
+
+# ===================================================================================================== mappings
+def _is_memory_fs(path: str) -> bool:
+    """tmpfs / ramfs: no page cache write-back to miss the device's DMA writes."""
+    probe = os.path.abspath(path)
+    best, kind = "", ""
+    try:
+        with open("/proc/mounts") as f:
+            for line in f:
+                parts = line.split()
+                if len(parts) >= 3 and (probe == parts[1] or probe.startswith(parts[1].rstrip("/") + "/")) \
+                        and len(parts[1]) >= len(best):
+                    best, kind = parts[1], parts[2]
+    except OSError:
+        return False
+    return kind in ("tmpfs", "ramfs", "devtmpfs")
+
+
+class MappedFile:
+    """A checkpoint file mapped into the address space (and page-locked for the device when ``cuda``)."""
+
+    def __init__(self, path: str, size: int, cuda: bool):
+        self.path, self.size = path, int(size)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        tmp = f"{path}.map{os.getpid()}"
+        fd = os.open(tmp, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o644)
+        try:
+            os.ftruncate(fd, self.size)
+            self.mm = mmap.mmap(fd, self.size, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
+        finally:
+            os.close(fd)
+        os.replace(tmp, path)
+        self.view = torch.frombuffer(self.mm, dtype=torch.uint8)
+        self.ptr = self.view.data_ptr()
+        self.registered = False
+        if cuda:
+            rc = torch.cuda.cudart().cudaHostRegister(self.ptr, self.size, 0)
+            self.registered = int(rc) == 0
+            if not self.registered:
+                raise RuntimeError(f"cudaHostRegister failed for {path} ({self.size} bytes): {rc}")
+        self.layout: Optional[Layout] = None
+        self.last_event = None
+
+    def rename(self, new_path: str) -> None:
+        os.makedirs(os.path.dirname(new_path), exist_ok=True)
+        os.replace(self.path, new_path)
+        self.path = new_path
+
+    def close(self) -> None:
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self.ptr)
+            self.registered = False
+        self.view = None
+        try:
+            self.mm.close()
+        except (BufferError, ValueError):
+            pass
+
+
+# ===================================================================================================== the store
+class MappedCheckpointStore(CheckpointStore):
+    """Drop-in :class:`CheckpointStore` whose files are persistent CUDA-registered mappings (see module docstring)."""
+
+    def __init__(self, root: str, asynchronous: bool = True, enabled: bool = True, workers: int = 12,
+                 arena_bytes: int = 8 << 30, payload_ring: int = 0, force_mapped: bool = False):
+        super().__init__(root, asynchronous=asynchronous, enabled=enabled, workers=workers, arena_bytes=arena_bytes)
+        self.payload_ring = int(payload_ring)
+        self.mapped = bool(enabled and (force_mapped or _is_memory_fs(root if os.path.exists(root)
+                                                                        else os.path.dirname(root) or "/")))
+        self._files: Dict[str, MappedFile] = {}                                  # path -> mapping (stable names)
+        self._ring: Dict[Tuple[str, Any], collections.deque] = {}                # (actor, signature) -> mappings
+        self._ex_layouts: Dict[str, Any] = {}
+        self._mlock = threading.RLock()
+        self._lib = None
+        self.dma_bytes = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _native(self):
+        if self._lib is None:
+            from ..ops import native
+            self._lib = native.load()
+        return self._lib
+
+    @staticmethod
+    def _find_device(state: Any) -> Optional[torch.device]:
+        stack = [state]
+        while stack:
+            o = stack.pop()
+            if isinstance(o, torch.Tensor):
+                if o.is_cuda:
+                    return o.device
+            elif isinstance(o, dict):
+                stack.extend(o.values())
+            elif isinstance(o, (list, tuple)):
+                stack.extend(o)
+        return None
+
+    def _acquire(self, actor: str, path: str, layout: Layout, cuda: bool) -> MappedFile:
+        """The mapping that will hold ``path``: the existing one if the layout still fits, a recycled one for
+        per-round names inside a retention ring, else a new file."""
+        name = os.path.basename(path)
+        ringed = self.payload_ring > 0 and _PAYLOAD_NAME.match(name) is not None
+        if ringed:
+            key = (actor, re.sub(r"^\d+-", "", name), layout.signature)
+            dq = self._ring.setdefault(key, collections.deque())
+            mf = None
+            if len(dq) >= self.payload_ring:
+                mf = dq.popleft()
+                if mf.last_event is not None:
+                    mf.last_event.synchronize()
+                try:
+                    mf.rename(path)                 # the file of the round that left the retention window
+                except OSError:                     # somebody unlinked it: its pages cannot be named again
+                    mf.close()
+                    mf = None
+            if mf is None:
+                mf = MappedFile(path, layout.total, cuda)
+            dq.append(mf)
+            return mf
+        mf = self._files.get(path)
+        if mf is not None and (mf.layout is None or mf.layout.signature != layout.signature or mf.size != layout.total):
+            if mf.last_event is not None:
+                mf.last_event.synchronize()
+            mf.close()
+            mf = None
+        if mf is None:
+            mf = self._files[path] = MappedFile(path, layout.total, cuda)
+        return mf
+
+    def _issue(self, mf: MappedFile, layout: Layout, prefix: bytes, dev: Optional[torch.device]) -> None:
+        """Prefix by the CPU (a few KB), storages by DMA (CUDA) or memcpy (CPU tensors)."""
+        import struct
+        view = mf.view
+        view[:len(prefix)] = torch.frombuffer(bytearray(prefix), dtype=torch.uint8)
+        for off, numel in layout.headers:
+            view[off:off + 8] = torch.frombuffer(bytearray(struct.pack("<q", numel)), dtype=torch.uint8)
+        if dev is None:
+            for seg in layout.segments:
+                if seg.nbytes:
+                    src = seg.tensor.detach().contiguous()
+                    view[seg.offset:seg.offset + seg.nbytes] = src.reshape(-1).view(torch.uint8)
+            mf.layout = layout
+            return
+        lib = self._native()
+        from ..ops import native
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        cs = self._copy_stream
+        cs.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cs):
+            for seg in layout.segments:
+                if not seg.nbytes:
+                    continue
+                src = seg.tensor.detach()
+                if not src.is_cuda:
+                    view[seg.offset:seg.offset + seg.nbytes] = src.contiguous().reshape(-1).view(torch.uint8)
+                    continue
+                if not src.is_contiguous():
+                    src = src.contiguous()
+                src.record_stream(cs)
+                rc = lib.flpr_memcpy_d2h_async(C.c_void_p(mf.ptr + seg.offset), native.ptr(src), seg.nbytes,
+                                               C.c_void_p(cs.cuda_stream))
+                native.check(rc, "flpr_memcpy_d2h_async")
+                self.dma_bytes += seg.nbytes
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        mf.last_event = ev
+        mf.layout = layout
+        self._last_copy_event = ev
+
+    # ------------------------------------------------------------------ save
+    def _save_locked(self, actor: str, state_name: str, state: Any, cover: bool, post: Optional[str]) -> None:
+        if not self.mapped:
+            return super()._save_locked(actor, state_name, state, cover, post)
+        self._raise_pending()
+        path = self.path(actor, state_name)
+        if cover is False and os.path.exists(path):
+            raise ValueError(f"State checkpoint has already exist in '{path}'.")
+        dev = self._find_device(state)
+        register = torch.cuda.is_available() and (dev is not None or self.asynchronous)
+        if post == "expand_examplars":
+            if self._save_examplars(actor, path, state, dev):
+                return
+            return super()._save_locked(actor, state_name, state, cover, post)
+        if post is not None:
+            return super()._save_locked(actor, state_name, state, cover, post)
+        with self._mlock:
+            old = self._files.get(path)
+            start = old.layout.data_start if (old is not None and old.layout is not None
+                                              and old.layout.signature == _signature(state)) else None
+            try:
+                layout, prefix = legacy_layout(state, start)
+            except ValueError:
+                layout, prefix = legacy_layout(state, None)
+            mf = self._acquire(actor, path, layout, register)
+            if mf.layout is not None and mf.layout.data_start != layout.data_start:
+                layout, prefix = legacy_layout(state, mf.layout.data_start) \
+                    if mf.layout.signature == layout.signature else (layout, prefix)
+            self._issue(mf, layout, prefix, dev)
+            if mf.last_event is not None:
+                self._actor_events[actor] = mf.last_event
+            self.bytes_written += layout.total
+
+    # ------------------------------------------------------------------ FedSTIL exemplar file (numpy schema)
+    def _save_examplars(self, actor: str, path: str, state: Any, dev: Optional[torch.device]) -> bool:
+        """``{np.int64 pid: [(ndarray fp32 prototype, class_id), ...]}`` laid out once per exemplar-set structure; the
+        prototypes are cast to fp32 on the device and DMA-ed to their array offsets. Returns False to fall back."""
+        import numpy as np
+        if not isinstance(state, dict) or "_compact_gens" not in state:
+            return False
+        gens = state["_compact_gens"]
+        # person / class ids are embedded in the pickle as Python ints: ONE device -> host read for all generations
+        flat = [t for g in gens for t in (g["pids"].reshape(-1), g["cls"][:, :int(g["k"])].reshape(-1))]
+        host = torch.cat(flat).tolist() if flat else []
+        sig_parts, cur = [], 0
+        host_gens = []
+        for g in gens:
+            P, k = int(g["pids"].numel()), int(g["k"])
+            pids = host[cur:cur + P]
+            cur += P
+            cls = [host[cur + i * k:cur + (i + 1) * k] for i in range(P)]
+            cur += P * k
+            host_gens.append((pids, cls))
+            sig_parts.append((tuple(pids), k, tuple(g["bank"].shape[2:]), tuple(map(tuple, cls))))
+        sig = tuple(sig_parts)
+        with self._mlock:
+            cached = self._ex_layouts.get(path)
+            if cached is None or cached[0] != sig:
+                # lay the pickle out with marker-filled placeholder arrays and record every array's data offset
+                out, order = {}, []
+                marker = 1
+                for gi, g in enumerate(gens):
+                    k = int(g["k"])
+                    shape = tuple(g["bank"].shape[2:])
+                    pids_h, cls = host_gens[gi]
+                    for pi, pid in enumerate(pids_h):
+                        items = []
+                        for j in range(k):
+                            arr = np.full(shape, float(marker), dtype=np.float32)
+                            items.append((arr, int(cls[pi][j])))
+                            order.append((gi, pi, j, marker))
+                            marker += 1
+                        out[np.int64(pid)] = items
+                buf = io.BytesIO()
+                torch.save(out, buf, _use_new_zipfile_serialization=False, pickle_protocol=5)
+                raw = buf.getvalue()
+                offsets, pos = [], 0
+                nb = int(np.prod(gens[0]["bank"].shape[2:])) * 4 if gens else 0
+                for (_, _, _, mk) in order:
+                    pat = np.full(min(nb // 4, 16), float(mk), dtype=np.float32).tobytes()
+                    i = raw.find(pat, pos)
+                    if i < 0:
+                        return False
+                    offsets.append(i)
+                    pos = i + nb
+                old = self._files.get(path)
+                if old is not None:
+                    if old.last_event is not None:
+                        old.last_event.synchronize()
+                    old.close()
+                mf = self._files[path] = MappedFile(path, len(raw), torch.cuda.is_available() and
+                                                    (dev is not None or self.asynchronous))
+                mf.view[:] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+                mf.layout = Layout(sig, 0, [], len(raw), [])
+                cached = self._ex_layouts[path] = (sig, offsets, order, nb)
+            _, offsets, order, nb = cached
+            mf = self._files[path]
+            if not order:
+                return True
+            # (generation, pid row) runs with a constant stride between consecutive arrays -> one pitched copy each
+            if dev is None:
+                for (gi, pi, j, _), off in zip(order, offsets):
+                    src = gens[gi]["bank"][pi, j].detach().float().contiguous().reshape(-1).view(torch.uint8)
+                    mf.view[off:off + nb] = src
+                self.bytes_written += mf.size
+                return True
+            lib = self._native()
+            from ..ops import native
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(dev)
+            cs = self._copy_stream
+            cs.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(cs):
+                idx = 0
+                for gi, g in enumerate(gens):
+                    k = int(g["k"])
+                    P = g["bank"].shape[0]
+                    if k <= 0 or P == 0:
+                        continue
+                    f32 = g["bank"][:, :k].detach().float().contiguous()              # [P, k, ...] cast on the device
+                    f32.record_stream(cs)
+                    n_arr = P * k
+                    offs = offsets[idx:idx + n_arr]
+                    pitch = offs[1] - offs[0] if n_arr > 1 else nb
+                    uniform = all(offs[i + 1] - offs[i] == pitch for i in range(n_arr - 1))
+                    if uniform and pitch >= nb:
+                        rc = lib.flpr_memcpy2d_d2h_async(C.c_void_p(mf.ptr + offs[0]), pitch, native.ptr(f32), nb, nb,
+                                                         n_arr, C.c_void_p(cs.cuda_stream))
+                        native.check(rc, "flpr_memcpy2d_d2h_async")
+                    else:
+                        base = f32.data_ptr()
+                        for i, off in enumerate(offs):
+                            rc = lib.flpr_memcpy_d2h_async(C.c_void_p(mf.ptr + off), C.c_void_p(base + i * nb), nb,
+                                                           C.c_void_p(cs.cuda_stream))
+                            native.check(rc, "flpr_memcpy_d2h_async")
+                    self.dma_bytes += n_arr * nb
+                    idx += n_arr
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            mf.last_event = ev
+            self._last_copy_event = ev
+            self._actor_events[actor] = ev
+            self.bytes_written += mf.size
+            return True
+
+    # ------------------------------------------------------------------ synchronisation / teardown
+    def flush(self) -> None:
+        super().flush()
+        with self._mlock:
+            ev = self._last_copy_event
+            if ev is not None:
+                ev.synchronize()
+
+    def close(self) -> None:
+        self.flush()
+        with self._mlock:
+            for mf in self._files.values():
+                mf.close()
+            for dq in self._ring.values():
+                for mf in dq:
+                    mf.close()
+            self._files.clear()
+            self._ring.clear()
+        super().close()

@@ -103,3 +103,132 @@ def test_dead_writer_is_detected_not_waited_for(tmp_path):
         st.close()
     except Exception:
         pass
+
+
+# ------------------------------------------------------------------------------------------------- mapped store
+def _mapped(tmp_path, **kw):
+    from flpr_b200.runtime.mapped_store import MappedCheckpointStore
+    return MappedCheckpointStore(str(tmp_path), asynchronous=False, force_mapped=True, **kw)
+
+
+def test_mapped_store_files_are_plain_torch_checkpoints(tmp_path):
+    """Layout emitted by ``legacy_layout`` = a legacy ``torch.save`` container: loadable by ``torch.load`` (also with
+    ``weights_only=True``), every dtype / empty tensor / nested container / scalar intact, channels-last views saved in
+    logical order."""
+    st = _mapped(tmp_path)
+    cl = torch.randn(4, 6, 3, 3).contiguous(memory_format=torch.channels_last)
+    state = {"train_cnt": 5, "a": torch.randn(1000, 33), "cl": cl, "tok": None, "f": 0.25, "flag": True,
+             "n": {"b": torch.arange(10), "c": [torch.ones(3, dtype=torch.bfloat16), 5, "x"], "e": torch.zeros(0),
+                   "u8": torch.arange(7, dtype=torch.uint8), "t": (torch.tensor(3.5), torch.tensor([True, False]))}}
+    st.save("c0", "m", state, True)
+    for wo in (False, True):
+        out = torch.load(st.path("c0", "m"), weights_only=wo)
+        assert torch.equal(out["a"], state["a"]) and torch.equal(out["cl"], cl) and out["train_cnt"] == 5
+        assert out["tok"] is None and out["f"] == 0.25 and out["flag"] is True
+        assert out["n"]["c"][0].dtype == torch.bfloat16 and out["n"]["c"][1:] == [5, "x"] and out["n"]["e"].numel() == 0
+        assert torch.equal(out["n"]["u8"], state["n"]["u8"]) and out["n"]["t"][0].item() == 3.5
+        assert out["n"]["t"][1].tolist() == [True, False]
+    st.close()
+
+
+def test_mapped_store_overwrites_in_place_and_survives_growing_scalars(tmp_path):
+    st = _mapped(tmp_path)
+    path = st.path("c0", "m")
+    state = {"train_cnt": 5, "w": torch.randn(257, 3)}
+    st.save("c0", "m", state, True)
+    ino, start = os.stat(path).st_ino, st._files[path].layout.data_start
+    for cnt in (200, 70_000, 10 ** 12):                          # BININT1 -> BININT2 -> BININT -> LONG1
+        state = {"train_cnt": cnt, "w": torch.randn(257, 3)}
+        st.save("c0", "m", state, True)
+        assert os.stat(path).st_ino == ino and st._files[path].layout.data_start == start
+        out = st.load("c0", "m")
+        assert out["train_cnt"] == cnt and torch.equal(out["w"], state["w"])
+    st.save("c0", "m", {"train_cnt": 1, "w": torch.randn(300, 3)}, True)       # structure change: new mapping
+    assert st.load("c0", "m")["w"].shape == (300, 3)
+    with pytest.raises(ValueError):
+        st.save("c0", "m", state, False)                         # cover=False refuses to overwrite
+    st.close()
+
+
+def test_mapped_store_payload_ring_recycles_old_rounds(tmp_path):
+    st = _mapped(tmp_path, payload_ring=2)
+    for r in range(1, 7):
+        st.save("client-0", f"{r}-client-0-server", {"train_cnt": r, "w": torch.full((100,), float(r))}, True)
+        st.save("server", f"{r}-server-client-0", {"g": torch.full((50,), float(-r))}, True)
+    assert sorted(os.listdir(tmp_path / "client-0")) == ["5-client-0-server.ckpt", "6-client-0-server.ckpt"]
+    assert sorted(os.listdir(tmp_path / "server")) == ["5-server-client-0.ckpt", "6-server-client-0.ckpt"]
+    assert st.load("client-0", "5-client-0-server")["w"][0] == 5 and st.load("server", "6-server-client-0")["g"][0] == -6
+    os.remove(tmp_path / "client-0" / "5-client-0-server.ckpt")            # a janitor got there first
+    st.save("client-0", "7-client-0-server", {"train_cnt": 7, "w": torch.full((100,), 7.0)}, True)
+    assert st.load("client-0", "7-client-0-server")["train_cnt"] == 7
+    st.close()
+
+
+def test_mapped_store_exemplar_file_keeps_the_reference_schema(tmp_path):
+    st = _mapped(tmp_path)
+    gens = {"_compact_gens": [
+        {"pids": torch.tensor([7, 9]), "bank": torch.randn(2, 3, 4, 2, 2).bfloat16(),
+         "cls": torch.tensor([[1, 2, 3], [4, 5, 6]]), "k": 2},
+        {"pids": torch.tensor([300]), "bank": torch.randn(1, 2, 4, 2, 2).bfloat16(), "cls": torch.tensor([[1, 700]]),
+         "k": 2}]}
+    for _ in range(2):                                           # second save: same structure, in place
+        gens["_compact_gens"][0]["bank"] = torch.randn(2, 3, 4, 2, 2).bfloat16()
+        st.save("c0", "ex", gens, True, post="expand_examplars")
+        ex = st.load("c0", "ex")
+        assert sorted(int(k) for k in ex) == [7, 9, 300] and [len(ex[np.int64(p)]) for p in (7, 9, 300)] == [2, 2, 2]
+        assert ex[np.int64(9)][1][1] == 5 and ex[np.int64(300)][1][1] == 700
+        for gi, g in enumerate(gens["_compact_gens"]):
+            for pi, pid in enumerate(g["pids"].tolist()):
+                for j in range(2):
+                    arr = ex[np.int64(pid)][j][0]
+                    assert arr.dtype == np.float32 and np.array_equal(arr, g["bank"][pi, j].float().numpy())
+    gens["_compact_gens"][0]["k"] = 1                            # reduce_examplars: structure change -> re-laid out
+    st.save("c0", "ex", gens, True, post="expand_examplars")
+    assert len(st.load("c0", "ex")[np.int64(7)]) == 1
+    st.close()
+
+
+def test_mapped_store_runs_a_whole_experiment(tmp_path):
+    """The CPU fedstil experiment through the mapped store: same files, loadable, same values as the in-line store."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from helpers import tiny_common, tiny_experiment, tiny_factory
+    from flpr_b200.runtime import experiment as E
+    from flpr_b200.runtime.mapped_store import MappedCheckpointStore
+    outs = {}
+    for kind in ("inline", "mapped"):
+        common = tiny_common(str(tmp_path / kind))
+        cfg = tiny_experiment(common, "fedstil")
+        cfg["engine_opts"]["val_at_round0"] = False
+        orig = E.CheckpointStore
+        if kind == "mapped":
+            E.CheckpointStore = lambda root, **kw: MappedCheckpointStore(root, force_mapped=True, **kw)
+        try:
+            with E.ExperimentStage(common, [cfg], source_factory=tiny_factory()) as stage:
+                stage.run_experiment(cfg)
+        finally:
+            E.CheckpointStore = orig
+        root = os.path.join(common["checkpoints_dir"], cfg["exp_name"])
+        files = {}
+        for d, _, names in os.walk(root):
+            for n in names:
+                files[os.path.relpath(os.path.join(d, n), root)] = torch.load(os.path.join(d, n), weights_only=False)
+        outs[kind] = files
+    assert set(outs["inline"]) == set(outs["mapped"])
+
+    def same(a, b):
+        if isinstance(a, dict):
+            assert set(map(str, a)) == set(map(str, b))
+            bk = {str(k): v for k, v in b.items()}
+            for k, v in a.items():
+                same(v, bk[str(k)])
+        elif isinstance(a, (list, tuple)):
+            assert len(a) == len(b)
+            for x, y in zip(a, b):
+                same(x, y)
+        elif isinstance(a, (torch.Tensor, np.ndarray)):
+            assert torch.allclose(torch.as_tensor(a).float(), torch.as_tensor(b).float(), atol=1e-6)
+        else:
+            assert a == b or (a != a and b != b)
+    for name in outs["inline"]:
+        same(outs["inline"][name], outs["mapped"][name])

@@ -305,3 +305,44 @@ def test_fedavg_training_step_launches_no_library_conv_or_batchnorm(tmp_path):
                                                              "sgemm", "gemv", "cublas", "xmma"))]
     assert not bad, bad
     assert any("tcgen05" in n for n in names), names[:20]
+
+
+def test_mapped_checkpoint_store_dma_into_registered_files():
+    """Snapshots of device tensors as DMAs straight into CUDA-registered RAM-disk file mappings: files are plain
+    ``torch.load``-able checkpoints, overwritten in place, the exemplar file keeps the numpy schema."""
+    import shutil
+    import tempfile
+    import numpy as np
+    from flpr_b200.runtime.mapped_store import MappedCheckpointStore, _is_memory_fs
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    root = tempfile.mkdtemp(dir=base, prefix="flpr_mapped_")
+    try:
+        st = MappedCheckpointStore(root, asynchronous=True, payload_ring=2, force_mapped=not _is_memory_fs(root))
+        assert st.mapped
+        dev = torch.device("cuda:0")
+        w = torch.randn(512, 3, 3, 256, device=dev).permute(0, 3, 1, 2)          # channels_last view, like the arena's
+        state = {"train_cnt": 3, "global_weight": {"l.global_weight": w}, "bf": torch.randn(1 << 20, device=dev).bfloat16(),
+                 "cpu": torch.arange(5), "e": torch.zeros(0, device=dev)}
+        for rnd in range(1, 5):
+            state["train_cnt"] = rnd * 1000
+            w.mul_(1.5)
+            st.save("client-0", "fedstil_model", state, True)
+            st.fence()
+            st.save("client-0", f"{rnd}-client-0-server", {"train_cnt": rnd, "incremental_sw": {"k": w}}, True)
+        gens = {"_compact_gens": [{"pids": torch.tensor([5, 6, 8], device=dev),
+                                   "bank": torch.randn(3, 4, 64, 16, 8, device=dev).bfloat16(),
+                                   "cls": torch.tensor([[0] * 4, [1] * 4, [2] * 4], device=dev), "k": 4}]}
+        st.save("client-0", "fedstil_model_examplars", gens, True, post="expand_examplars")
+        assert st.dma_bytes > 4 * w.numel() * 4
+        out = st.load("client-0", "fedstil_model")
+        assert out["train_cnt"] == 4000 and torch.equal(out["global_weight"]["l.global_weight"], w.cpu())
+        assert torch.equal(out["bf"], state["bf"].cpu()) and out["e"].numel() == 0 and out["cpu"].tolist() == [0, 1, 2, 3, 4]
+        assert sorted(os.listdir(os.path.join(root, "client-0"))) == ["3-client-0-server.ckpt", "4-client-0-server.ckpt",
+                                                                      "fedstil_model.ckpt", "fedstil_model_examplars.ckpt"]
+        assert st.load("client-0", "4-client-0-server")["train_cnt"] == 4
+        ex = st.load("client-0", "fedstil_model_examplars")
+        assert np.array_equal(ex[np.int64(6)][2][0], gens["_compact_gens"][0]["bank"][1, 2].float().cpu().numpy())
+        assert ex[np.int64(8)][3][1] == 2
+        st.close()
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
