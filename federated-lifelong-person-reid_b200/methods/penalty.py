@@ -93,6 +93,10 @@ class PenaltyModel(ModelModule):
         for ld in loaders:
             if hasattr(ld, "to") and hasattr(ld, "augment"):
                 ld.to(self.device, torch.float32)
+                if self.rng is not None:
+                    # never the default CUDA generator: another client's thread may have it registered with a CUDA-graph
+                    # capture in flight ("Offset increment outside graph capture")
+                    ld.device_generator = self.rng
             for data, person_id, _ in ld:
                 a.zero_grad()
                 data, target = self.prepare_input(data), person_id.to(self.device)

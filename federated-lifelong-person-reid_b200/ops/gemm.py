@@ -233,6 +233,11 @@ def linear(x: torch.Tensor, w_master: torch.Tensor, w_bf16: Optional[torch.Tenso
     """Linear / 1x1-conv on flattened NHWC activations. ``w_master`` fp32 ``[out,in]`` receives the gradient
     (directly in ``grad_out`` when given - it must be zero on entry). ``want_stats`` additionally returns the fused
     batch-norm column partials of the output (``(y, part)``)."""
+    if x.is_cuda and (w_master.shape[0] % 8 or w_master.shape[1] % 8 or x.shape[-1] % 8) and not want_stats:
+        # TMA needs 16-byte row strides in every operand mode of forward / dgrad / wgrad; a head that is not a
+        # multiple of 8 wide (iCaRL grows its classifier by ``n_classes`` at a time, methods/icarl.py) is a tiny GEMM:
+        # plain autograd matmul (the fp32 weight gradient lands in the arena slot through AccumulateGrad)
+        return F.linear(_bf(x), w_master.to(torch.bfloat16))
     if w_bf16 is None:
         w_bf16 = w_master.detach().to(torch.bfloat16)
     if grad_out is not None and not x.is_cuda:

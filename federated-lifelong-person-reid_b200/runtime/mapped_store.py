@@ -11,9 +11,12 @@ bounds the round (``profiles/r2_scaling.md``). Here the host CPU does not touch 
   ``_rebuild_tensor_v2`` over persistent storage ids, exactly what ``torch.load`` expects) and pads the storage-key
   pickle with an ignored junk string so that the data region starts at a fixed offset even when scalars in the object
   graph (``train_cnt``) change their encoded width from round to round.
-* The file is created once, ``mmap``-ed ``MAP_SHARED`` and page-locked with ``cudaHostRegister``. Saving = rewrite the
-  few-KB pickle prefix + one ``cudaMemcpyAsync`` per tensor from device memory into the mapping, on a copy stream
-  behind an event of the producing stream. Nothing is pickled, staged or copied by a CPU again.
+* The file is created once, ``mmap``-ed ``MAP_SHARED`` and page-locked with ``cudaHostRegister``. Saving = (a) the
+  tensors are gathered into a *device-resident image* of the file's data region by one multi-tensor copy on the
+  producing stream - the snapshot is taken at that instant, the sources may be overwritten right away, no fence on the
+  compute stream ever waits for PCIe - and (b) ONE ``cudaMemcpyAsync`` of the image into the mapping on a copy stream.
+  The pickle prefix is re-emitted only when a scalar in the object graph changed. No byte of payload is pickled,
+  staged in host memory or copied by a CPU.
 * Files whose name is unique per round (``{round}-{src}-{dst}.ckpt``) recycle the mappings of rounds that have left
   the retention window (``engine_opts.payload_ring``; 0 = keep every round like the reference, allocating fresh
   mappings): the old file is renamed to the new name and overwritten in place.
@@ -89,6 +92,43 @@ def _signature(obj: Any):
     if isinstance(obj, str):
         return ("s", len(obj.encode()))
     return ("O", type(obj).__name__, len(pickle.dumps(obj, protocol=2)))
+
+
+def _scalars(obj: Any):
+    """The non-tensor leaves of a state (what the pickle prefix depends on besides the structure)."""
+    if isinstance(obj, torch.Tensor):
+        return None
+    if isinstance(obj, dict):
+        return tuple(_scalars(v) for v in obj.values())
+    if isinstance(obj, (list, tuple)):
+        return tuple(_scalars(v) for v in obj)
+    if isinstance(obj, (bool, int, float, str, type(None))):
+        return obj
+    return pickle.dumps(obj, protocol=2)
+
+
+def _tensors_in_order(obj: Any, out: List[torch.Tensor], seen: Dict[int, bool]) -> None:
+    """Tensors in the order the pickler meets them (dict insertion order, depth first), shared objects once."""
+    if isinstance(obj, torch.Tensor):
+        if id(obj) not in seen:
+            seen[id(obj)] = True
+            out.append(obj)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _tensors_in_order(v, out, seen)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _tensors_in_order(v, out, seen)
+
+
+def _rebind(layout: "Layout", state: Any) -> "Layout":
+    """The same byte layout pointing at the tensors of a new state of identical structure."""
+    ts: List[torch.Tensor] = []
+    _tensors_in_order(state, ts, {})
+    if len(ts) != len(layout.segments):
+        raise ValueError("state does not match the cached layout")
+    segs = [_Segment(t, seg.offset, seg.nbytes) for t, seg in zip(ts, layout.segments)]
+    return Layout(layout.signature, layout.data_start, segs, layout.total, layout.headers)
 
 
 def _main_pickle(state: Any) -> Tuple[bytes, List[Tuple[_StorageRef, torch.Tensor]]]:
@@ -214,6 +254,9 @@ class MappedFile:
                 raise RuntimeError(f"cudaHostRegister failed for {path} ({self.size} bytes): {rc}")
         self.layout: Optional[Layout] = None
         self.last_event = None
+        self.stage: Optional[torch.Tensor] = None        # device image of the data region [data_start, size)
+        self.stage_views: Optional[list] = None          # per segment: typed device view into ``stage`` (or None)
+        self.prefix_key = None                           # scalars of the object graph the current prefix was made for
 
     def rename(self, new_path: str) -> None:
         os.makedirs(os.path.dirname(new_path), exist_ok=True)
@@ -301,13 +344,39 @@ class MappedCheckpointStore(CheckpointStore):
             mf = self._files[path] = MappedFile(path, layout.total, cuda)
         return mf
 
-    def _issue(self, mf: MappedFile, layout: Layout, prefix: bytes, dev: Optional[torch.device]) -> None:
-        """Prefix by the CPU (a few KB), storages by DMA (CUDA) or memcpy (CPU tensors)."""
+    def _write_prefix(self, mf: MappedFile, layout: Layout, prefix: bytes) -> None:
         import struct
         view = mf.view
         view[:len(prefix)] = torch.frombuffer(bytearray(prefix), dtype=torch.uint8)
         for off, numel in layout.headers:
             view[off:off + 8] = torch.frombuffer(bytearray(struct.pack("<q", numel)), dtype=torch.uint8)
+
+    def _build_stage(self, mf: MappedFile, layout: Layout, dev: torch.device) -> None:
+        """Device image of the data region: storage headers scattered in once, one typed view per tensor."""
+        import struct
+        ds = layout.data_start
+        mf.stage = torch.empty(max(layout.total - ds, 8), dtype=torch.uint8, device=dev)
+        if layout.headers:
+            pos = torch.tensor([off - ds + b for off, _ in layout.headers for b in range(8)], dtype=torch.long)
+            val = torch.frombuffer(bytearray(b"".join(struct.pack("<q", n) for _, n in layout.headers)),
+                                   dtype=torch.uint8)
+            mf.stage[pos.to(dev)] = val.to(dev)
+        views = []
+        for seg in layout.segments:
+            t = seg.tensor
+            o = seg.offset - ds
+            if seg.nbytes == 0 or o % t.element_size():
+                views.append(None)                       # empty, or misaligned for a typed view: copied byte-wise
+            else:
+                views.append(mf.stage[o:o + seg.nbytes].view(t.dtype).view(t.shape))
+        mf.stage_views = views
+
+    def _issue(self, mf: MappedFile, layout: Layout, prefix: Optional[bytes], dev: Optional[torch.device]) -> None:
+        """Prefix by the CPU (a few KB, only when it changed); storages through the device image + ONE DMA (CUDA) or
+        by memcpy (CPU tensors)."""
+        if prefix is not None:
+            self._write_prefix(mf, layout, prefix)
+        view = mf.view
         if dev is None:
             for seg in layout.segments:
                 if seg.nbytes:
@@ -320,27 +389,47 @@ class MappedCheckpointStore(CheckpointStore):
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(dev)
         cs = self._copy_stream
-        cs.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(cs):
-            for seg in layout.segments:
-                if not seg.nbytes:
-                    continue
-                src = seg.tensor.detach()
-                if not src.is_cuda:
-                    view[seg.offset:seg.offset + seg.nbytes] = src.contiguous().reshape(-1).view(torch.uint8)
-                    continue
-                if not src.is_contiguous():
-                    src = src.contiguous()
-                src.record_stream(cs)
-                rc = lib.flpr_memcpy_d2h_async(C.c_void_p(mf.ptr + seg.offset), native.ptr(src), seg.nbytes,
-                                               C.c_void_p(cs.cuda_stream))
-                native.check(rc, "flpr_memcpy_d2h_async")
-                self.dma_bytes += seg.nbytes
-            ev = torch.cuda.Event()
-            ev.record(cs)
+        cur = torch.cuda.current_stream(dev)
+        if mf.last_event is not None:
+            cur.wait_event(mf.last_event)                # the image is free again once its previous DMA has finished
+        ds = layout.data_start
+        if mf.stage is None or mf.stage_views is None or len(mf.stage_views) != len(layout.segments) \
+                or mf.stage.numel() != max(layout.total - ds, 8):
+            self._build_stage(mf, layout, dev)
+        dsts, srcs = [], []
+        for seg, dv in zip(layout.segments, mf.stage_views):
+            if not seg.nbytes:
+                continue
+            src = seg.tensor.detach()
+            if dv is None:
+                o = seg.offset - ds
+                mf.stage[o:o + seg.nbytes].copy_(src.contiguous().reshape(-1).view(torch.uint8), non_blocking=True)
+            elif src.is_cuda and src.device == dev:
+                dsts.append(dv)
+                srcs.append(src)
+            else:
+                dv.copy_(src, non_blocking=True)
+        if dsts:
+            torch._foreach_copy_(dsts, srcs)             # the snapshot: taken here, on the producing stream
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        cs.wait_event(ready)
+        nbytes = layout.total - ds
+        rc = lib.flpr_memcpy_d2h_async(C.c_void_p(mf.ptr + ds), native.ptr(mf.stage), nbytes,
+                                       C.c_void_p(cs.cuda_stream))
+        native.check(rc, "flpr_memcpy_d2h_async")
+        self.dma_bytes += nbytes
+        ev = torch.cuda.Event()
+        ev.record(cs)
         mf.last_event = ev
         mf.layout = layout
         self._last_copy_event = ev
+
+    def fence(self, actor: Optional[str] = None) -> None:
+        """Snapshots are taken into device images at ``save`` time: there is nothing for the compute stream to wait for
+        (the staged parent class needs the fence because its DMAs read the live tensors)."""
+        if not self.mapped:
+            super().fence(actor)
 
     # ------------------------------------------------------------------ save
     def _save_locked(self, actor: str, state_name: str, state: Any, cover: bool, post: Optional[str]) -> None:
@@ -359,18 +448,36 @@ class MappedCheckpointStore(CheckpointStore):
         if post is not None:
             return super()._save_locked(actor, state_name, state, cover, post)
         with self._mlock:
+            sig = _signature(state)
+            scal = _scalars(state)
             old = self._files.get(path)
-            start = old.layout.data_start if (old is not None and old.layout is not None
-                                              and old.layout.signature == _signature(state)) else None
-            try:
-                layout, prefix = legacy_layout(state, start)
-            except ValueError:
-                layout, prefix = legacy_layout(state, None)
-            mf = self._acquire(actor, path, layout, register)
-            if mf.layout is not None and mf.layout.data_start != layout.data_start:
-                layout, prefix = legacy_layout(state, mf.layout.data_start) \
-                    if mf.layout.signature == layout.signature else (layout, prefix)
-            self._issue(mf, layout, prefix, dev)
+            if old is not None and old.layout is not None and old.layout.signature == sig and old.prefix_key == scal \
+                    and not (self.payload_ring > 0 and _PAYLOAD_NAME.match(os.path.basename(path))):
+                # same structure, same scalars: the pickles in the file are still right - re-point the segments only
+                try:
+                    layout = _rebind(old.layout, state)
+                except ValueError:
+                    layout = None
+            else:
+                layout = None
+            if layout is not None:
+                self._issue(old, layout, None, dev)
+                mf = old
+            else:
+                start = old.layout.data_start if (old is not None and old.layout is not None
+                                                  and old.layout.signature == sig) else None
+                try:
+                    layout, prefix = legacy_layout(state, start)
+                except ValueError:
+                    layout, prefix = legacy_layout(state, None)
+                mf = self._acquire(actor, path, layout, register)
+                if mf.layout is not None and mf.layout.signature == sig and mf.layout.data_start != layout.data_start:
+                    try:
+                        layout, prefix = legacy_layout(state, mf.layout.data_start)     # recycled ring mapping
+                    except ValueError:
+                        pass
+                self._issue(mf, layout, prefix, dev)
+                mf.prefix_key = scal
             if mf.last_event is not None:
                 self._actor_events[actor] = mf.last_event
             self.bytes_written += layout.total
@@ -453,34 +560,46 @@ class MappedCheckpointStore(CheckpointStore):
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(dev)
             cs = self._copy_stream
-            cs.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(cs):
-                idx = 0
-                for gi, g in enumerate(gens):
-                    k = int(g["k"])
-                    P = g["bank"].shape[0]
-                    if k <= 0 or P == 0:
-                        continue
-                    f32 = g["bank"][:, :k].detach().float().contiguous()              # [P, k, ...] cast on the device
-                    f32.record_stream(cs)
-                    n_arr = P * k
-                    offs = offsets[idx:idx + n_arr]
-                    pitch = offs[1] - offs[0] if n_arr > 1 else nb
-                    uniform = all(offs[i + 1] - offs[i] == pitch for i in range(n_arr - 1))
-                    if uniform and pitch >= nb:
-                        rc = lib.flpr_memcpy2d_d2h_async(C.c_void_p(mf.ptr + offs[0]), pitch, native.ptr(f32), nb, nb,
-                                                         n_arr, C.c_void_p(cs.cuda_stream))
-                        native.check(rc, "flpr_memcpy2d_d2h_async")
+            cur = torch.cuda.current_stream(dev)
+            if mf.last_event is not None:
+                cur.wait_event(mf.last_event)
+            lo, hi = offsets[0], offsets[-1] + nb
+            if mf.stage is None or mf.stage.numel() != hi - lo:
+                # device image of the file's array region, pickle bytes between the arrays included (copied up once)
+                mf.stage = mf.view[lo:hi].to(dev, non_blocking=False)
+            idx = 0
+            for gi, g in enumerate(gens):
+                k = int(g["k"])
+                P = g["bank"].shape[0]
+                if k <= 0 or P == 0:
+                    continue
+                f32 = g["bank"][:, :k].detach().float().contiguous().view(P * k, -1)       # cast on the device
+                n_arr = P * k
+                offs = offsets[idx:idx + n_arr]
+                pitch = offs[1] - offs[0] if n_arr > 1 else nb
+                uniform = all(offs[i + 1] - offs[i] == pitch for i in range(n_arr - 1))
+                base = offs[0] - lo
+                if uniform and pitch >= nb:
+                    region = mf.stage[base:base + (n_arr - 1) * pitch + nb]
+                    dst = region.as_strided((n_arr, nb), (pitch, 1))
+                    if pitch % 4 == 0 and base % 4 == 0:
+                        dst.view(torch.float32).copy_(f32)
                     else:
-                        base = f32.data_ptr()
-                        for i, off in enumerate(offs):
-                            rc = lib.flpr_memcpy_d2h_async(C.c_void_p(mf.ptr + off), C.c_void_p(base + i * nb), nb,
-                                                           C.c_void_p(cs.cuda_stream))
-                            native.check(rc, "flpr_memcpy_d2h_async")
-                    self.dma_bytes += n_arr * nb
-                    idx += n_arr
-                ev = torch.cuda.Event()
-                ev.record(cs)
+                        dst.copy_(f32.view(torch.uint8))
+                else:
+                    u8 = f32.view(torch.uint8)
+                    for i, off in enumerate(offs):
+                        mf.stage[off - lo:off - lo + nb].copy_(u8[i])
+                idx += n_arr
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            cs.wait_event(ready)
+            rc = lib.flpr_memcpy_d2h_async(C.c_void_p(mf.ptr + lo), native.ptr(mf.stage), hi - lo,
+                                           C.c_void_p(cs.cuda_stream))
+            native.check(rc, "flpr_memcpy_d2h_async")
+            self.dma_bytes += hi - lo
+            ev = torch.cuda.Event()
+            ev.record(cs)
             mf.last_event = ev
             self._last_copy_event = ev
             self._actor_events[actor] = ev
