@@ -27,4 +27,18 @@ int flpr_host_register(void* ptr, size_t nbytes) {
 
 int flpr_host_unregister(void* ptr) { return (int)cudaHostUnregister(ptr); }
 
+// A CUDA stream of its own. torch.cuda.Stream() hands out streams from a pool of 32 per device round-robin, so two
+// Stream objects can be the SAME hardware queue: a client thread's "own" stream may then coincide with the stream
+// another thread is capturing a CUDA graph on, and that client's eager work (e.g. its augmentation's random draws)
+// lands inside the capture. Client, capture, copy and communication streams are therefore created here and wrapped
+// with torch.cuda.ExternalStream.
+int flpr_stream_create(void** out, int priority) {
+  cudaStream_t s = nullptr;
+  cudaError_t e = cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, priority);
+  *out = (void*)s;
+  return (int)e;
+}
+
+int flpr_stream_destroy(void* s) { return (int)cudaStreamDestroy((cudaStream_t)s); }
+
 }  // extern "C"

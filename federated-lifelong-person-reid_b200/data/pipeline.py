@@ -11,6 +11,8 @@ import os
 from typing import Callable, Dict, Iterator, List, Optional, Tuple
 
 import torch
+
+from ..ops import native as _native
 from torch.utils.data import DataLoader
 
 from .augmentation import DeviceAugment, augmentations
@@ -91,7 +93,7 @@ class DeviceBatchLoader:
         bs = int(batch_size or self.batch_size)
         n = len(ds)
         if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(dev)
+            self._copy_stream = _native.dedicated_stream(dev)
         cur = torch.cuda.current_stream(dev)
         with torch.cuda.stream(self._copy_stream):
             dev_all = ds.images.to(dev, non_blocking=True)
@@ -129,7 +131,7 @@ class DeviceBatchLoader:
         cuda = self.device.type == "cuda"
         if cuda:
             if self._copy_stream is None:
-                self._copy_stream = torch.cuda.Stream(self.device)
+                self._copy_stream = _native.dedicated_stream(self.device)
             if not self._stage:
                 shape = (self.batch_size,) + tuple(ds.images.shape[1:])
                 self._stage = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(2)]

@@ -135,11 +135,28 @@ class Model(ModelModule):
                 ab[f"{lname}.adaptive_bias"] = own(bias.detach())
         skip = {f"{n}.weight" for n in self.adaptive_names} | {f"{n}.bias" for n in self.adaptive_names}
         pre = {k: own(v.detach()) for k, v in self.net.state_dict().items() if k not in skip}
+        if not copy:
+            # The frozen stages never change between dispatches of pre-trained parameters (the trunk runs in eval mode,
+            # fedstil.py:569): the checkpoint store keeps them in its device image instead of re-copying ~250 tensors
+            # on every snapshot. ``_static_version`` is bumped whenever something writes them (update_model).
+            prefixes = self._frozen_prefixes()
+            ver = getattr(self, "_static_version", 0)
+            for k, v in pre.items():
+                if k.startswith(prefixes):
+                    v._flpr_static = ver
         return {"global_weight": gw, "global_weight_atten": gwa, "adaptive_weights": aw, "adaptive_bias": ab,
                 "bn_params": {}, "pre_trained_params": pre}
 
+    def _frozen_prefixes(self) -> Tuple[str, ...]:
+        start = getattr(self.net, "head_start", 0)
+        if not hasattr(self.net, "base") or not isinstance(start, int) or start < 1 or not hasattr(self.net.base, "conv1"):
+            return ("\0",)                               # unknown backbone: nothing is declared static
+        return ("base.conv1.", "base.bn1.") + tuple(f"base.layer{i}." for i in range(1, start))
+
     def update_model(self, params_state: Dict) -> None:
         a = self.arena
+        if params_state.get("pre_trained_params"):
+            self._static_version = getattr(self, "_static_version", 0) + 1
         with torch.no_grad():
             gw = params_state.get("global_weight") or {}
             aw = params_state.get("adaptive_weights") or {}

@@ -254,7 +254,8 @@ class FoldedTrunk:
             slots.append(sl)
         with CAPTURE_LOCK:
             static_in = x.clone()
-            side = torch.cuda.Stream(self.device)
+            from ..ops import native
+            side = native.dedicated_stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
                 for _ in range(2):

@@ -76,6 +76,8 @@ def _declare(lib: C.CDLL) -> None:
         "flpr_memcpy2d_d2h_async": [P, Z, P, Z, Z, Z, P],
         "flpr_host_register": [P, Z],
         "flpr_host_unregister": [P],
+        "flpr_stream_create": [C.POINTER(P), I],
+        "flpr_stream_destroy": [P],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -125,6 +127,21 @@ def ptr(t: Optional[torch.Tensor]) -> c_void_p:
 
 def stream(device: Optional[torch.device] = None) -> c_void_p:
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+_streams: list = []          # keeps the ExternalStream wrappers (and thereby the handles) alive for the process
+
+
+def dedicated_stream(device: Optional[torch.device] = None, priority: int = 0) -> "torch.cuda.Stream":
+    """A CUDA stream that no other ``torch.cuda.Stream()`` object can alias (see ``flpr_stream_create``)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    lib = load()
+    with torch.cuda.device(device):
+        h = c_void_p()
+        check(lib.flpr_stream_create(C.byref(h), int(priority)), "flpr_stream_create")
+        s = torch.cuda.ExternalStream(h.value, device=device)
+    _streams.append(s)
+    return s
 
 
 def check(rc: int, what: str) -> None:

@@ -357,7 +357,7 @@ class CheckpointStore:
         if not self._started:
             self._start(cuda_dev is not None or torch.cuda.is_available())
         if cuda_dev is not None and self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(cuda_dev)
+            self._copy_stream = _dedicated_stream(cuda_dev)
         self._reap(block=False)
         snap, base, nbytes, event = self._stage(state, cuda_dev)
         if event is not None:
@@ -415,6 +415,11 @@ class CheckpointStore:
                 self._arena = None
             self._started = False
         self.asynchronous = False
+
+
+def _dedicated_stream(dev):
+    from ..ops import native
+    return native.dedicated_stream(dev)
 
 
 class _null:

@@ -352,7 +352,7 @@ class ExperimentStage:
             torch.cuda.set_device(dev)
             stream = getattr(client, "_stream", None)
             if stream is None:
-                stream = client._stream = torch.cuda.Stream(dev)
+                stream = client._stream = native.dedicated_stream(dev)
             with torch.cuda.stream(stream):
                 stream.wait_event(start)
                 self._process_train(client, log, curr_round, self.container)

@@ -17,7 +17,19 @@ from ..ops import native
 CAPTURE_LOCK = threading.RLock()
 
 
+_capture_streams: dict = {}
+
+
 def capture(graph: "torch.cuda.CUDAGraph", **kw):
+    """``torch.cuda.graph`` in thread-local error mode on a capture stream of its own (``torch.cuda.graph`` would take
+    one from the 32-stream pool, which a client thread's stream may alias - see ``native.dedicated_stream``).
+    Captures are serialised by ``CAPTURE_LOCK``, so one capture stream per device is enough."""
+    if "stream" not in kw:
+        dev = torch.cuda.current_device()
+        st = _capture_streams.get(dev)
+        if st is None:
+            st = _capture_streams[dev] = native.dedicated_stream(torch.device("cuda", dev))
+        kw["stream"] = st
     return torch.cuda.graph(graph, capture_error_mode="thread_local", **kw)
 
 

@@ -42,7 +42,7 @@ from typing import Any, Dict, List, Optional, Tuple
 
 import torch
 
-from .checkpoint import CheckpointStore
+from .checkpoint import CheckpointStore, _dedicated_stream
 
 _PAYLOAD_NAME = re.compile(r"^\d+-")          # '{round}-{src}-{dst}': unique per round
 _SLACK = 512                                  # bytes of padding available for growing scalars
@@ -257,6 +257,8 @@ class MappedFile:
         self.stage: Optional[torch.Tensor] = None        # device image of the data region [data_start, size)
         self.stage_views: Optional[list] = None          # per segment: typed device view into ``stage`` (or None)
         self.prefix_key = None                           # scalars of the object graph the current prefix was made for
+        self.stage_sig = None
+        self.static_done: Dict[int, Any] = {}            # segment index -> version of a static tensor already in the image
 
     def rename(self, new_path: str) -> None:
         os.makedirs(os.path.dirname(new_path), exist_ok=True)
@@ -287,6 +289,8 @@ class MappedCheckpointStore(CheckpointStore):
         self._files: Dict[str, MappedFile] = {}                                  # path -> mapping (stable names)
         self._ring: Dict[Tuple[str, Any], collections.deque] = {}                # (actor, signature) -> mappings
         self._ex_layouts: Dict[str, Any] = {}
+        self._graveyard: List[MappedFile] = []                                   # retired mappings, closed at close()
+        self._grown: set = set()
         self._mlock = threading.RLock()
         self._lib = None
         self.dma_bytes = 0
@@ -328,20 +332,25 @@ class MappedCheckpointStore(CheckpointStore):
                 try:
                     mf.rename(path)                 # the file of the round that left the retention window
                 except OSError:                     # somebody unlinked it: its pages cannot be named again
-                    mf.close()
+                    self._graveyard.append(mf)
                     mf = None
             if mf is None:
                 mf = MappedFile(path, layout.total, cuda)
             dq.append(mf)
             return mf
         mf = self._files.get(path)
-        if mf is not None and (mf.layout is None or mf.layout.signature != layout.signature or mf.size != layout.total):
-            if mf.last_event is not None:
-                mf.last_event.synchronize()
-            mf.close()
+        if mf is not None and layout.total > mf.size:
+            # outgrown (FedSTIL's token memory gains one token per client and round). The old mapping is only retired:
+            # cudaHostUnregister synchronises the whole device - copy stream included - so it never runs on the hot path
+            self._graveyard.append(mf)
             mf = None
         if mf is None:
-            mf = self._files[path] = MappedFile(path, layout.total, cuda)
+            grows = mf is None and path in self._grown
+            self._grown.add(path)
+            cap = layout.total if not grows else layout.total * 2       # a file that keeps growing gets headroom
+            mf = self._files[path] = MappedFile(path, cap, cuda)
+        elif mf.layout is not None and (mf.layout.signature != layout.signature):
+            mf.stage = mf.stage_views = None                            # same pages, new layout: rebuild the image
         return mf
 
     def _write_prefix(self, mf: MappedFile, layout: Layout, prefix: bytes) -> None:
@@ -387,19 +396,26 @@ class MappedCheckpointStore(CheckpointStore):
         lib = self._native()
         from ..ops import native
         if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(dev)
+            self._copy_stream = _dedicated_stream(dev)
         cs = self._copy_stream
         cur = torch.cuda.current_stream(dev)
         if mf.last_event is not None:
             cur.wait_event(mf.last_event)                # the image is free again once its previous DMA has finished
         ds = layout.data_start
         if mf.stage is None or mf.stage_views is None or len(mf.stage_views) != len(layout.segments) \
-                or mf.stage.numel() != max(layout.total - ds, 8):
+                or mf.stage.numel() != max(layout.total - ds, 8) or mf.stage_sig != layout.signature:
             self._build_stage(mf, layout, dev)
+            mf.stage_sig = layout.signature
+            mf.static_done = {}
         dsts, srcs = [], []
-        for seg, dv in zip(layout.segments, mf.stage_views):
+        for i, (seg, dv) in enumerate(zip(layout.segments, mf.stage_views)):
             if not seg.nbytes:
                 continue
+            ver = getattr(seg.tensor, "_flpr_static", None)
+            if ver is not None:                          # frozen weights: copied into the image once per version
+                if mf.static_done.get(i) == ver:
+                    continue
+                mf.static_done[i] = ver
             src = seg.tensor.detach()
             if dv is None:
                 o = seg.offset - ds
@@ -535,13 +551,17 @@ class MappedCheckpointStore(CheckpointStore):
                     offsets.append(i)
                     pos = i + nb
                 old = self._files.get(path)
-                if old is not None:
+                if old is not None and old.size >= len(raw):
                     if old.last_event is not None:
                         old.last_event.synchronize()
-                    old.close()
-                mf = self._files[path] = MappedFile(path, len(raw), torch.cuda.is_available() and
-                                                    (dev is not None or self.asynchronous))
-                mf.view[:] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+                    mf = old
+                    mf.stage = None
+                else:
+                    if old is not None:
+                        self._graveyard.append(old)
+                    mf = self._files[path] = MappedFile(path, len(raw), torch.cuda.is_available() and
+                                                        (dev is not None or self.asynchronous))
+                mf.view[:len(raw)] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
                 mf.layout = Layout(sig, 0, [], len(raw), [])
                 cached = self._ex_layouts[path] = (sig, offsets, order, nb)
             _, offsets, order, nb = cached
@@ -558,7 +578,7 @@ class MappedCheckpointStore(CheckpointStore):
             lib = self._native()
             from ..ops import native
             if self._copy_stream is None:
-                self._copy_stream = torch.cuda.Stream(dev)
+                self._copy_stream = _dedicated_stream(dev)
             cs = self._copy_stream
             cur = torch.cuda.current_stream(dev)
             if mf.last_event is not None:
@@ -617,6 +637,9 @@ class MappedCheckpointStore(CheckpointStore):
     def close(self) -> None:
         self.flush()
         with self._mlock:
+            for mf in self._graveyard:
+                mf.close()
+            self._graveyard.clear()
             for mf in self._files.values():
                 mf.close()
             for dq in self._ring.values():

@@ -85,6 +85,14 @@ def main():
         agg[n[:80]][0] += 1; agg[n[:80]][1] += (e - s) / 1e3
     for n, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
         print(f"  {ms:8.2f} ms x{c:5d}  {n}")
+    # timeline of the big copies and of the comm kernels (where does the copy engine sit relative to fed_* ?)
+    big = sorted([(e["ts"], e["dur"], e["name"], e["args"].get("bytes", 0), e["args"].get("stream")) for e in ev
+                  if e.get("cat") == "gpu_memcpy" and e["args"].get("bytes", 0) >= (8 << 20)])
+    fed = sorted([(e["ts"], e["dur"], e["name"][:40], 0, e["args"].get("stream")) for e in ev
+                  if e.get("cat") == "kernel" and ("fed_" in e["name"] or "herding" in e["name"])])
+    print("timeline (ms since first kernel): big copies >= 8 MB and fed_* / herding kernels")
+    for ts, dur, name, b, st in sorted(big + fed)[-120:]:
+        print(f"  t={(ts - t_lo) / 1e3:9.2f}  dur={dur / 1e3:8.3f}  {b / 1e6:8.1f} MB  stream {st}  {name}")
     # host-side: time inside synchronising calls
     sync = [(e["name"], e["dur"]) for e in ev if e.get("cat") in ("cuda_runtime", "cuda_driver") and
             ("Synchronize" in e["name"] or "cudaMemcpy" == e["name"])]
