@@ -18,7 +18,15 @@
 //                            (methods/fedstil_atten.py:1099-1121, methods/fedweit.py:999-1009).
 //   fed_pull_copy     C2     first-contact dispatch / token all-gather: peer -> local copy with optional bf16 cast.
 //
+//   fed_reduce_bcast_nvls  C1+C2 through the NVSwitch's multicast / in-fabric reduction (NVLS): every rank first folds
+//                            its own clients into a symmetric partial  sum_c k_c * p_c  (local HBM only), then
+//                            multimem.ld_reduce adds the partials of all ranks INSIDE THE SWITCH for this rank's slice,
+//                            the kernel scales by 1 / sum k and multimem.st broadcasts the slice to every rank's
+//                            destination: each GPU sends and receives the buffer once, whatever the number of ranks.
+//
 // Clients-per-rank is arbitrary (8 clients on 1/2/4/8 GPUs): sources are a table of K pointers, local or peer.
+// Concurrent collectives (aggregation on a communication stream while the next round's mix runs on the compute stream)
+// use different CHANNELS: each channel has its own arrival flags and epoch counters.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -40,16 +48,19 @@ constexpr int MAX_COMM_BLOCKS = 512;
 //   [.., + 4)                            [0] error word (timeout), local use only; [2..3] 64-bit address of a
 //                                        host-mapped mailbox that mirrors the error word (the host reads it without
 //                                        any CUDA call, i.e. after every collective and without a device sync)
+constexpr int MAX_CHANNELS = 4;
 constexpr int FLAG_WORDS = MAX_COMM_BLOCKS * MAX_RANKS;
 constexpr int EPOCH_OFF = FLAG_WORDS;
-constexpr int ERR_OFF = EPOCH_OFF + MAX_COMM_BLOCKS;
+constexpr int CHANNEL_WORDS = FLAG_WORDS + MAX_COMM_BLOCKS;      // one channel: arrival flags + epoch counters
+constexpr int ERR_OFF = MAX_CHANNELS * CHANNEL_WORDS;            // shared by all channels (relative to the page base)
 constexpr int MAILBOX_OFF = ERR_OFF + 2;
 constexpr int FLAG_PAGE_WORDS = ERR_OFF + 4;
 
 struct CommCtx {
   int rank;
   int world;
-  uint32_t* flags[MAX_RANKS];  // flags[r] = base of rank r's flag page (peer-mapped; flags[rank] is local)
+  uint32_t* flags[MAX_RANKS];  // flags[r] = this channel's flags in rank r's flag page (peer-mapped; [rank] is local)
+  uint32_t* err;               // local error word (+2: host mailbox address), shared by all channels
   unsigned long long timeout_ns;
 };
 
@@ -80,9 +91,9 @@ __device__ __forceinline__ bool rank_barrier(const CommCtx& ctx, uint32_t epoch)
       while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
         if (gtimer() - t0 > ctx.timeout_ns) {
           fail = 1;
-          uint32_t* err = ctx.flags[ctx.rank] + ERR_OFF;
+          uint32_t* err = ctx.err;
           if (atomicExch(err, 1u) == 0u) {
-            volatile uint32_t* box = *reinterpret_cast<volatile uint32_t* const*>(ctx.flags[ctx.rank] + MAILBOX_OFF);
+            volatile uint32_t* box = *reinterpret_cast<volatile uint32_t* const*>(ctx.err + (MAILBOX_OFF - ERR_OFF));
             if (box != nullptr) {
               *box = 1u;
               __threadfence_system();
@@ -92,7 +103,7 @@ __device__ __forceinline__ bool rank_barrier(const CommCtx& ctx, uint32_t epoch)
         }
       }
     }
-    if (threadIdx.x == 0 && *reinterpret_cast<volatile uint32_t*>(ctx.flags[ctx.rank] + ERR_OFF) != 0u) fail = 1;
+    if (threadIdx.x == 0 && *reinterpret_cast<volatile uint32_t*>(ctx.err) != 0u) fail = 1;
     fail = __syncthreads_or(fail);
   }
   return fail == 0;
@@ -126,6 +137,7 @@ struct ReduceArgs {
   float w[MAX_CLIENTS];               // explicit weights when cnt == nullptr
   float* dst[MAX_RANKS];              // destination buffer on every rank (peer-mapped)
   size_t n4;                          // length in float4
+  int one_shot;                       // small buffers: every rank reduces everything locally (no push phase)
 };
 
 __global__ void __launch_bounds__(COMM_THREADS)
@@ -144,11 +156,24 @@ fed_reduce_bcast_kernel(const CommCtx ctx, const ReduceArgs a) {
   }
   __syncthreads();
 
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (a.one_shot) {
+    // latency-bound sizes (task tokens, BN statistics): every rank pulls all K sources and reduces the whole buffer
+    // itself - no push phase, the only cross-rank traffic is the loads, and nobody writes into anybody's memory
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ok && i < a.n4; i += stride) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < a.K; ++c)
+        acc = f4_fma(s_w[c], ld_stream_f4(reinterpret_cast<const float4*>(a.src[c]) + i), acc);
+      reinterpret_cast<float4*>(a.dst[ctx.rank])[i] = acc;
+    }
+    rank_barrier(ctx, e0 + 2);  // sources may be overwritten again
+    block_epoch_end(ctx, e0 + 2);
+    return;
+  }
   // two-shot: this rank reduces slice [lo, hi) and pushes the result to every rank
   const size_t per = (a.n4 + ctx.world - 1) / ctx.world;
   const size_t lo = per * ctx.rank;
   const size_t hi = (lo + per < a.n4) ? lo + per : a.n4;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; ok && i < hi; i += stride) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c0 = 0; c0 < a.K; c0 += 8) {
@@ -167,6 +192,79 @@ fed_reduce_bcast_kernel(const CommCtx ctx, const ReduceArgs a) {
 
   rank_barrier(ctx, e0 + 2);  // every rank's slice has landed everywhere
   block_epoch_end(ctx, e0 + 2);
+}
+
+// ----------------------------------------------------------------------------- C1 + C2 over NVLS (multimem)
+// `ld_reduce` on a multicast address returns the SUM over every GPU bound to the multicast object of the word at that
+// offset - the addition happens inside the NVSwitch; `st` on a multicast address writes the word to every GPU.
+__device__ __forceinline__ float4 multimem_ld_reduce_add_f4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f4(float* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+struct NvlsReduceArgs {
+  int L;                            // clients hosted on THIS rank that take part in the mean
+  const float* src[MAX_LOCAL];      // their upload slots (local HBM)
+  const float* cnt[MAX_LOCAL];      // their train_cnt scalars (nullptr -> w[])
+  float w[MAX_LOCAL];
+  int K;                            // all participating clients (for sum k)
+  const float* cnt_all[MAX_CLIENTS];  // every participating client's counter (local or peer), or nullptr -> w_total
+  float w_total;                    // sum of the explicit weights when counters are not used
+  float* partial;                   // this rank's symmetric partial buffer (local address)
+  const float* mc_partial;          // multicast address of the partial buffers
+  float* mc_dst;                    // multicast address of the destination buffers
+  size_t n4;
+};
+
+__global__ void __launch_bounds__(COMM_THREADS)
+fed_reduce_bcast_nvls_kernel(const CommCtx ctx, const NvlsReduceArgs a) {
+  __shared__ float s_w[MAX_LOCAL];
+  __shared__ float s_inv;
+  const uint32_t e0 = block_epoch_begin(ctx);
+  // (1) nobody is still reading last round's partial / destination; every counter is visible
+  bool ok = rank_barrier(ctx, e0 + 1);
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    if (a.cnt_all[0] != nullptr) {
+      for (int c = 0; c < a.K; ++c) tot += *a.cnt_all[c];
+    } else {
+      tot = a.w_total;
+    }
+    s_inv = 1.f / tot;
+    for (int l = 0; l < a.L; ++l) s_w[l] = (a.cnt[0] != nullptr) ? *a.cnt[l] : a.w[l];
+  }
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  // (2) local fold: partial = sum over my clients of k_c * p_c  (zero when this rank hosts no participant)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ok && i < a.n4; i += stride) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int l = 0; l < MAX_LOCAL; ++l)
+      if (l < a.L) acc = f4_fma(s_w[l], ld_stream_f4(reinterpret_cast<const float4*>(a.src[l]) + i), acc);
+    reinterpret_cast<float4*>(a.partial)[i] = acc;
+  }
+  ok = rank_barrier(ctx, e0 + 2) && ok;  // every rank's partial is complete and visible system-wide
+  // (3) my slice: in-switch reduction of the partials, scale, multicast store into every rank's destination
+  const size_t per = (a.n4 + ctx.world - 1) / ctx.world;
+  const size_t lo = per * ctx.rank;
+  const size_t hi = (lo + per < a.n4) ? lo + per : a.n4;
+  const float inv = s_inv;
+  for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; ok && i < hi; i += stride) {
+    float4 v = multimem_ld_reduce_add_f4(a.mc_partial + 4 * i);
+    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    multimem_st_f4(a.mc_dst + 4 * i, v);
+  }
+  rank_barrier(ctx, e0 + 3);  // every slice has landed everywhere
+  block_epoch_end(ctx, e0 + 3);
 }
 
 // ----------------------------------------------------------------------------- C4
@@ -358,6 +456,7 @@ __global__ void fed_barrier_kernel(const CommCtx ctx) {
 }
 
 static char g_comm_err[256] = {0};
+static int g_one_shot_bytes = 1 << 20;   // reduce_bcast buffers up to this size take the one-shot path
 static int comm_fail(cudaError_t e, const char* where) {
   snprintf(g_comm_err, sizeof(g_comm_err), "%s: %s", where, cudaGetErrorString(e));
   return (int)e;
@@ -417,12 +516,17 @@ int flpr_enable_peer(int dev, int peer) {
   return (int)e;
 }
 
+static thread_local int t_channel = 0;   // set by flpr_comm_set_channel for the calling thread's next launches
+
 static CommCtx make_ctx(int rank, int world, void* const* flag_pages, double timeout_s) {
   bind_device_of(flag_pages[rank]);
   CommCtx c;
   c.rank = rank;
   c.world = world;
-  for (int r = 0; r < MAX_RANKS; ++r) c.flags[r] = r < world ? reinterpret_cast<uint32_t*>(flag_pages[r]) : nullptr;
+  const int ch = (t_channel >= 0 && t_channel < MAX_CHANNELS) ? t_channel : 0;
+  for (int r = 0; r < MAX_RANKS; ++r)
+    c.flags[r] = r < world ? reinterpret_cast<uint32_t*>(flag_pages[r]) + (size_t)ch * CHANNEL_WORDS : nullptr;
+  c.err = reinterpret_cast<uint32_t*>(flag_pages[rank]) + ERR_OFF;
   c.timeout_ns = (unsigned long long)(timeout_s * 1e9);
   return c;
 }
@@ -439,6 +543,16 @@ int flpr_comm_set_mailbox(void* local_flag_page, void* host_mailbox) {
   unsigned long long addr = reinterpret_cast<unsigned long long>(host_mailbox);
   return (int)cudaMemcpy(reinterpret_cast<uint32_t*>(local_flag_page) + MAILBOX_OFF, &addr, 8, cudaMemcpyHostToDevice);
 }
+
+// Channel (0 .. MAX_CHANNELS-1) used by the collectives the CALLING THREAD launches from now on. Collectives that may
+// run concurrently (different streams) must use different channels; every rank must use the same channel for the same
+// collective.
+int flpr_comm_set_channel(int channel) {
+  if (channel < 0 || channel >= MAX_CHANNELS) return -1;
+  t_channel = channel;
+  return 0;
+}
+int flpr_comm_max_channels() { return MAX_CHANNELS; }
 
 int flpr_comm_barrier(int rank, int world, void* const* flag_pages, double timeout_s, cudaStream_t st) {
   CommCtx c = make_ctx(rank, world, flag_pages, timeout_s);
@@ -462,9 +576,46 @@ int flpr_comm_reduce_bcast(int rank, int world, void* const* flag_pages, double 
   }
   for (int r = 0; r < world; ++r) a.dst[r] = dst[r];
   a.n4 = n / 4;
-  fed_reduce_bcast_kernel<<<clamp_blocks(nblocks), COMM_THREADS, 0, st>>>(c, a);
+  a.one_shot = (world > 1 && n * sizeof(float) <= (size_t)g_one_shot_bytes) ? 1 : 0;
+  int blocks = clamp_blocks(nblocks);
+  if (a.one_shot) {                      // a few KB .. 1 MB: don't spread 32 k floats over hundreds of barrier-ing blocks
+    const int need = (int)((a.n4 + COMM_THREADS - 1) / COMM_THREADS);
+    blocks = need < 1 ? 1 : (need < blocks ? need : blocks);
+  }
+  fed_reduce_bcast_kernel<<<blocks, COMM_THREADS, 0, st>>>(c, a);
   return (int)cudaGetLastError();
 }
+
+// NVLS variant: `src` / `cnt` are this rank's participating clients (local pointers, L <= MAX_LOCAL), `cnt_all` the
+// counters of all K participants (nullable together with `cnt`: then `w` / `w_total` are used), `partial` the local
+// address and `mc_partial` / `mc_dst` the MULTICAST addresses of the symmetric partial / destination buffers.
+int flpr_comm_reduce_bcast_nvls(int rank, int world, void* const* flag_pages, double timeout_s, int L,
+                                const float* const* src, const float* const* cnt, const float* w, int K,
+                                const float* const* cnt_all, float w_total, float* partial, const float* mc_partial,
+                                float* mc_dst, size_t n, int nblocks, cudaStream_t st) {
+  if (L > MAX_LOCAL || L < 0 || K > MAX_CLIENTS || world > MAX_RANKS) return -1;
+  if (n % 4) return -2;
+  CommCtx c = make_ctx(rank, world, flag_pages, timeout_s);
+  NvlsReduceArgs a;
+  memset(&a, 0, sizeof(a));
+  a.L = L;
+  for (int l = 0; l < L; ++l) {
+    a.src[l] = src[l];
+    a.cnt[l] = cnt ? cnt[l] : nullptr;
+    a.w[l] = w ? w[l] : 0.f;
+  }
+  a.K = K;
+  for (int i = 0; i < K; ++i) a.cnt_all[i] = cnt_all ? cnt_all[i] : nullptr;
+  a.w_total = w_total;
+  a.partial = partial;
+  a.mc_partial = mc_partial;
+  a.mc_dst = mc_dst;
+  a.n4 = n / 4;
+  fed_reduce_bcast_nvls_kernel<<<clamp_blocks(nblocks), COMM_THREADS, 0, st>>>(c, a);
+  return (int)cudaGetLastError();
+}
+
+void flpr_comm_set_one_shot_bytes(int bytes) { g_one_shot_bytes = bytes; }
 
 int flpr_comm_mix(int rank, int world, void* const* flag_pages, double timeout_s, int K, int L,
                   const float* const* src, const float* w_rows /* host [L*K] or null */,

@@ -50,6 +50,8 @@ def _declare(lib: C.CDLL) -> None:
         "flpr_comm_set_mailbox": [P, P],
         "flpr_comm_barrier": [I, I, P, D, P],
         "flpr_comm_reduce_bcast": [I, I, P, D, I, P, P, P, P, Z, I, P],
+        "flpr_comm_reduce_bcast_nvls": [I, I, P, D, I, P, P, P, I, P, F, P, P, P, Z, I, P],
+        "flpr_comm_set_channel": [I],
         "flpr_comm_mix": [I, I, P, D, I, I, P, P, P, P, P, P, Z, I, P],
         "flpr_comm_curv_moments": [I, I, P, D, I, P, P, P, P, P, Z, I, P],
         "flpr_comm_gather_strided": [I, I, P, D, I, P, P, Z, I, P],
@@ -93,7 +95,10 @@ def _declare(lib: C.CDLL) -> None:
     for name in ("flpr_gemm_last_error", "flpr_comm_last_error"):
         getattr(lib, name).restype = C.c_char_p
         getattr(lib, name).argtypes = []
-    for name in ("flpr_comm_flag_page_bytes", "flpr_comm_max_clients", "flpr_comm_max_local", "flpr_comm_max_ranks"):
+    lib.flpr_comm_set_one_shot_bytes.argtypes = [I]
+    lib.flpr_comm_set_one_shot_bytes.restype = None
+    for name in ("flpr_comm_flag_page_bytes", "flpr_comm_max_clients", "flpr_comm_max_local", "flpr_comm_max_ranks",
+                 "flpr_comm_max_channels"):
         getattr(lib, name).restype = I
         getattr(lib, name).argtypes = []
 

@@ -3,8 +3,10 @@
 The reference has no communication layer at all ("network" = dict hand-off + ``torch.save``,
 ``experiment.py:189-203,233-241``). Here the exchange is the product:
 
-* ``p2p``  (CUDA)  – every rank ``cudaMalloc``s one arena, IPC handles are swapped once over the bootstrap process
-  group, and the collectives are the hand-written NVLink peer-memory kernels of ``csrc/fedcomm.cu``.
+* ``p2p``  (CUDA)  – every rank owns one symmetric arena that all peers map, and the collectives are the hand-written
+  NVLink peer-memory kernels of ``csrc/fedcomm.cu``. The arena is built on the CUDA VMM API with an NVSwitch
+  *multicast* view (``parallel/vmm.py``: ``multimem.ld_reduce`` / ``multimem.st`` = reduction / broadcast inside the
+  switch, used by the FedAvg-style ``reduce_bcast``) when the box supports it, else ``cudaMalloc`` + CUDA IPC.
 * ``nccl`` (CUDA)  – the *baseline harness*: the same API expressed with ``torch.distributed`` all-gathers plus local
   math. This is what the fused kernels are measured against; it is never used by the engine unless asked for.
 * ``gloo`` (CPU)   – plumbing mode for world_size>1 without GPUs (tests, BASELINE config 1).
@@ -68,6 +70,12 @@ class FedComm:
         self._peer_base: List[int] = []
         self._keep = []
         self.bytes_moved = 0          # algorithmic NVLink/peer bytes pulled+pushed by this rank
+        self.nvls = True              # use the multicast (in-switch) reduce when the arena has a multicast view
+        self.nvls_min_bytes = 1 << 20
+        self.nvls_launches = 0
+        self._mc_base = 0
+        self._vmm = None
+        self.backend = mode
         if self.mode == "p2p":
             self._init_p2p()
             self.comm_blocks = comm_blocks or 148 * 2
@@ -87,6 +95,7 @@ class FedComm:
 
     # ------------------------------------------------------------------ arena
     def _init_p2p(self) -> None:
+        import os
         lib = native.load()
         self._lib = lib
         if lib.flpr_comm_max_ranks() < self.world:
@@ -94,13 +103,46 @@ class FedComm:
         if lib.flpr_comm_max_clients() < self.K:
             raise native.NativeError(f"{self.K} clients exceed MAX_CLIENTS")
         torch.cuda.set_device(self.device)
-        base = C.c_void_p()
-        native.check(lib.flpr_symm_alloc(C.byref(base), self.arena_bytes), "flpr_symm_alloc")
-        self._base = base.value
-        self._arena = torch.as_tensor(_RawCuda(self._base, self.arena_bytes), device=self.device)
         self._flag_bytes = ((lib.flpr_comm_flag_page_bytes() + 4095) // 4096) * 4096
         self._cursor = self._flag_bytes
-        if self.world > 1:
+        self._vmm = None
+        self._mc_base = 0
+        self.backend = "ipc"
+        self.backend_note = ""
+        if self.world > 1 and os.environ.get("FLPR_COMM_VMM", "1") != "0":
+            # VMM arena + NVSwitch multicast view; any failure (every rank takes the same branch: the decision is
+            # all-reduced) leaves the cudaMalloc + IPC arena below
+            from .vmm import SymmetricVmm
+            err = None
+            try:
+                vmm = SymmetricVmm(self.device, self.arena_bytes, self.rank, self.world, self.group,
+                                   multicast=os.environ.get("FLPR_COMM_NVLS", "1") != "0")
+            except Exception as ex:  # noqa: BLE001  (driver / cuda-python / fabric problems of any kind)
+                vmm, err = None, f"{type(ex).__name__}: {ex}"
+            ok = torch.tensor([0 if vmm is None else 1], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if ok.item():
+                self._vmm = vmm
+                self.arena_bytes = vmm.size
+                self._base = vmm.base
+                self._peer_base = list(vmm.peer_base)
+                self._mc_base = vmm.mc_base
+                self.backend = "vmm+nvls" if vmm.mc_base else "vmm"
+                self.backend_note = getattr(vmm, "mc_error", "")
+            else:
+                if vmm is not None:
+                    vmm.close()
+                self.backend_note = err or "a peer rank could not build the VMM arena"
+        if self._vmm is None:
+            base = C.c_void_p()
+            native.check(lib.flpr_symm_alloc(C.byref(base), self.arena_bytes), "flpr_symm_alloc")
+            self._base = base.value
+        self._arena = torch.as_tensor(_RawCuda(self._base, self.arena_bytes), device=self.device)
+        if self._vmm is not None:
+            self._arena.zero_()
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+        elif self.world > 1:
             handle = (C.c_ubyte * 64)()
             native.check(lib.flpr_ipc_get_handle(C.c_void_p(self._base), handle), "flpr_ipc_get_handle")
             handles: List[Optional[bytes]] = [None] * self.world
@@ -122,16 +164,27 @@ class FedComm:
         native.check(lib.flpr_comm_set_mailbox(C.c_void_p(self._base), C.c_void_p(self._mailbox.data_ptr())),
                      "flpr_comm_set_mailbox")
 
+    def set_channel(self, channel: int) -> None:
+        """Flag channel of the collectives launched by the calling thread from now on (concurrent collectives - one
+        on a communication stream, one on the compute stream - must use different channels; same choice on every
+        rank)."""
+        if self.mode == "p2p":
+            native.check(self._lib.flpr_comm_set_channel(int(channel)), "flpr_comm_set_channel")
+
     def close(self) -> None:
         if self.mode == "p2p" and getattr(self, "_base", None):
             torch.cuda.synchronize(self.device)
             if self.world > 1:
                 dist.barrier(group=self.group)
-            for r, p in enumerate(self._peer_base):
-                if r != self.rank:
-                    self._lib.flpr_ipc_close(C.c_void_p(p))
             self._arena = None
-            self._lib.flpr_symm_free(C.c_void_p(self._base))
+            if self._vmm is not None:
+                self._vmm.close()
+                self._vmm = None
+            else:
+                for r, p in enumerate(self._peer_base):
+                    if r != self.rank:
+                        self._lib.flpr_ipc_close(C.c_void_p(p))
+                self._lib.flpr_symm_free(C.c_void_p(self._base))
             self._base = None
 
     def _alloc(self, name: str, n: int, slots: int, dtype: torch.dtype, per_client: bool) -> _Buf:
@@ -231,6 +284,10 @@ class FedComm:
         per-client scalar buffer (FedAvg ``train_cnt`` weighting, ``methods/fedavg.py:386-397``)."""
         bs, bd = self.bufs[src], self.bufs[dst]
         assert bs.n == bd.n and bs.dtype == torch.float32 and bd.dtype == torch.float32
+        if self.mode == "p2p" and self._mc_base and self.nvls and bs.n * 4 > self.nvls_min_bytes:
+            mine = [c for c in clients if self.owner(c) == self.rank]
+            if len(mine) <= self._lib.flpr_comm_max_local():
+                return self._reduce_bcast_nvls(src, dst, clients, mine, cnt, weights)
         if self.mode == "p2p":
             srcp = self._client_ptrs(src, clients)
             cntp = self._client_ptrs(cnt, clients) if cnt is not None else None
@@ -251,6 +308,33 @@ class FedComm:
         else:
             w = torch.tensor(list(weights), dtype=torch.float32, device=stack.device)
         self.rank_view(dst).copy_((w[:, None] * stack).sum(0))
+
+    def _reduce_bcast_nvls(self, src, dst, clients, mine, cnt, weights) -> None:
+        """C1+C2 through the switch: local fold of this rank's clients -> ``multimem.ld_reduce`` of the partials for
+        this rank's slice -> scale -> ``multimem.st`` into every rank's destination (``fed_reduce_bcast_nvls``)."""
+        bs, bd = self.bufs[src], self.bufs[dst]
+        pname = f"_nvls_partial_{bs.n}"
+        if pname not in self.bufs:
+            self.alloc_rank_buffer(pname, bs.n)              # symmetric: every rank reaches this line in the same call
+        bp = self.bufs[pname]
+        srcp = self._client_ptrs(src, mine) if mine else None
+        cntp = self._client_ptrs(cnt, mine) if (cnt is not None and mine) else None
+        cnt_all = self._client_ptrs(cnt, clients) if cnt is not None else None
+        wv, w_total = None, 0.0
+        if cnt is None:
+            wmap = {c: float(w) for c, w in zip(clients, weights)}
+            w_total = 1.0                                    # explicit weights are used as given (not re-normalised)
+            wv = (C.c_float * max(len(mine), 1))(*[wmap[c] for c in mine]) if mine else None
+        rc = self._lib.flpr_comm_reduce_bcast_nvls(
+            self.rank, self.world, self._flag_pages, self.timeout_s, len(mine), srcp, cntp, wv, len(clients), cnt_all,
+            w_total, C.c_void_p(self._addr(bp, self.rank, 0)), C.c_void_p(self._mc_base + bp.offset),
+            C.c_void_p(self._mc_base + bd.offset), bs.n, self.comm_blocks, native.stream(self.device))
+        native.check(rc, "flpr_comm_reduce_bcast_nvls")
+        native.count_launch()
+        self.poll_errors()
+        self.nvls_launches += 1
+        share = bs.n * 4 / self.world
+        self.bytes_moved += int(share * (self.world - 1) * 2)     # pulled through the switch + multicast out
 
     def mix(self, src: str, clients: Sequence[int], rows: torch.Tensor, local_clients: Sequence[int],
             dst_g: Optional[Sequence[torch.Tensor]] = None, dst_theta: Optional[Sequence[torch.Tensor]] = None,

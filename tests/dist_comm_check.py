@@ -51,10 +51,30 @@ def main():
             ok = False
             print(f"[rank {rank}] MISMATCH {what}: max err {err}", flush=True)
 
+    if rank == 0:
+        print(f"COMM backend={comm.backend} mc={'yes' if getattr(comm, '_mc_base', 0) else 'no'} "
+              f"note={getattr(comm, 'backend_note', '')!r}", flush=True)
     for it in range(3):  # repeat: exercises the epoch counters
-        comm.reduce_bcast("up", "glob", clients, cnt="cnt")
         w = cnts / cnts.sum()
-        close(comm.rank_view("glob"), (w[:, None] * U).sum(0), 1e-4, "reduce_bcast")
+        for nvls in ((True, False) if getattr(comm, "_mc_base", 0) else (False,)):
+            comm.nvls, comm.nvls_min_bytes = nvls, 0
+            comm.rank_view("glob").zero_()
+            comm.reduce_bcast("up", "glob", clients, cnt="cnt")
+            close(comm.rank_view("glob"), (w[:, None] * U).sum(0), 1e-4, f"reduce_bcast nvls={nvls}")
+            sub = clients[1::2]                                        # stale / partial participation, explicit weights
+            ws = [0.5 / len(sub)] * len(sub)
+            comm.reduce_bcast("up", "glob", sub, weights=ws)
+            close(comm.rank_view("glob"), 0.5 * U[sub].mean(0), 1e-4, f"reduce_bcast weights nvls={nvls}")
+        # a second channel (a collective on a communication stream next to one on the compute stream)
+        if use_cuda:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                comm.set_channel(1)
+                comm.reduce_bcast("up", "glob", clients, cnt="cnt")
+                comm.set_channel(0)
+            torch.cuda.current_stream().wait_stream(side)
+            close(comm.rank_view("glob"), (w[:, None] * U).sum(0), 1e-4, "reduce_bcast channel 1")
         rows = torch.softmax(torch.randn(K, K, generator=torch.Generator().manual_seed(it)), dim=1)
         loc = comm.local_clients()
         og = [torch.empty(n, device=dev) for _ in loc]
@@ -95,8 +115,15 @@ def main():
         dst = [torch.empty(nb, device=dev) for _ in loc]
         rows = torch.softmax(torch.randn(K, K), dim=1)
         res = {}
-        for name, fn in (("reduce_bcast", lambda: comm2.reduce_bcast("theta", "g", clients, weights=[1.0 / K] * K)),
-                         ("mix", lambda: comm2.mix("theta", clients, rows[loc], loc, dst, None, None))):
+
+        def rb(nvls):
+            comm2.nvls = nvls
+            comm2.reduce_bcast("theta", "g", clients, weights=[1.0 / K] * K)
+        cases = [("reduce_bcast", lambda: rb(False)), ("mix", lambda: comm2.mix("theta", clients, rows[loc], loc, dst,
+                                                                               None, None))]
+        if getattr(comm2, "_mc_base", 0):
+            cases.insert(1, ("reduce_bcast_nvls", lambda: rb(True)))
+        for name, fn in cases:
             for _ in range(3):
                 fn()
             torch.cuda.synchronize(); dist.barrier()
@@ -117,6 +144,10 @@ def main():
             print(f"BW world={world} K={K} S={S/1e6:.1f}MB reduce_bcast {res['reduce_bcast']:.3f} ms "
                   f"({rb_bytes/res['reduce_bcast']/1e6:.1f} GB/s ingress/rank) mix {res['mix']:.3f} ms "
                   f"({mix_bytes/res['mix']/1e6:.1f} GB/s ingress/rank)", flush=True)
+            if "reduce_bcast_nvls" in res:
+                print(f"BW world={world} K={K} S={S/1e6:.1f}MB reduce_bcast_nvls {res['reduce_bcast_nvls']:.3f} ms "
+                      f"(switch does the {world}-way add; each GPU sends and receives S once: "
+                      f"{S/res['reduce_bcast_nvls']/1e6:.1f} GB/s per direction)", flush=True)
         comm2.close()
     comm.close()
     flag = torch.tensor([0 if ok else 1], device=dev)

@@ -346,3 +346,20 @@ def test_mapped_checkpoint_store_dma_into_registered_files():
         st.close()
     finally:
         shutil.rmtree(root, ignore_errors=True)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least two GPUs on the box")
+def test_peer_memory_collectives_on_two_or_more_gpus():
+    """One rank per GPU under torchrun: every collective of ``csrc/fedcomm.cu`` (peer loads / stores over NVLink, the
+    NVLS multicast reduce when the switch offers it, a second flag channel on a side stream, three epochs) against the
+    plain tensor arithmetic; prints the achieved bandwidths."""
+    import subprocess
+    import sys
+    n = min(torch.cuda.device_count(), 8)
+    n = 8 if n >= 8 else (4 if n >= 4 else 2)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
+                        "--nproc-per-node", str(n), os.path.join(root, "tests", "dist_comm_check.py")],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, FLPR_BW_N=str(8_000_000)))
+    print(r.stdout[-2000:])
+    assert r.returncode == 0 and "DIST_COMM_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
