@@ -628,9 +628,14 @@ class Server(ServerModule):
 
     def calculate(self) -> Any:
         """FedAvg mean of theta into the server model + token exchange (``fedstil.py:1075-1096``)."""
-        if self.uploaded:
-            self.comm.reduce_bcast("theta_up", "glob", self.uploaded, cnt="cnt")
-            self.model.set_global_weight(self.comm.rank_view("glob"))
+        self.calculate_urgent()
+        self.calculate_deferred()
+
+    # The round loop may split the aggregation (``engine_opts.overlap_aggregate``): what the NEXT dispatch depends on -
+    # the task tokens, a few hundred KB - stays on the compute stream; the 125 MB FedAvg mean into the server replica
+    # (needed only by first-contact dispatches and the server checkpoint) runs on the communication stream, on its own
+    # flag channel, concurrently with the next round's mix and local training.
+    def calculate_urgent(self) -> None:
         if self._round_uploads and "token" in self.comm.bufs:
             ids = [self.client_ids[n] for n in self._round_uploads]
             d = self.comm.bufs["token"].n
@@ -641,6 +646,11 @@ class Server(ServerModule):
                 self.token_memory.setdefault(name, []).append(toks[i])
         self._round_uploads = []
         self.save_state(f"{self.server_name}_tokens", self.token_memory, True)
+
+    def calculate_deferred(self) -> None:
+        if self.uploaded:
+            self.comm.reduce_bcast("theta_up", "glob", self.uploaded, cnt="cnt")
+            self.model.set_global_weight(self.comm.rank_view("glob"))
 
     # ---- spatial-temporal integration (fedstil.py:1118-1164) ----------------------------------------------------------------
     def relevance_row(self, client_name: str) -> Tuple[List[str], torch.Tensor]:

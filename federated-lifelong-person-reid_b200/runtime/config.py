@@ -28,6 +28,9 @@ ENGINE_DEFAULTS: Dict[str, Any] = {
                                       # mappings of older rounds (0 = keep every round, like the reference)
     "ckpt_workers": 0,                # writer processes (0 -> 8..16 by the number of local clients)
     "ckpt_arena_gb": 0,               # pinned staging arena (0 -> 3..8 GB by the number of local clients)
+    "overlap_aggregate": True,        # methods with a deferred aggregation part (FedSTIL's 125 MB FedAvg mean into the
+                                      # server replica) run it on a communication stream / second flag channel,
+                                      # concurrently with the next round's mix and local training
     "client_threads": True,           # `parallel` clients per device train concurrently on their own CUDA streams
     "resume": False,                  # continue from {checkpoints_dir}/{exp}/_resume/rank{r}.ckpt when present
     "resume_interval": 0,             # write the resume manifest every N rounds (0 = never)

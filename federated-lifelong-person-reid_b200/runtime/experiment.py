@@ -233,9 +233,13 @@ class ExperimentStage:
                 self.logger.info(f"Start communication round: {curr_round:0>3d}/{comm_rounds:0>3d}")
                 self._process_one_round(curr_round, server, clients, names, exp_config, log, timer, comm)
                 if interval and curr_round % interval == 0:
+                    if self.device.type == "cuda":
+                        self._join_deferred_aggregate()          # the manifest snapshots the server replica
                     resume.save(self, store, curr_round, server, clients, comm)
             self._gather_logs(log)
         finally:
+            if self.device.type == "cuda":
+                self._join_deferred_aggregate()
             store.flush()
             store.close()
             perf = {k: sum(v) for k, v in timer.flush().items()}
@@ -273,6 +277,8 @@ class ExperimentStage:
         # ---- server -> clients ------------------------------------------------------------------------------------
         with timer("dispatch"):
             first = [n for n in online if n not in server.clients]
+            if first:
+                self._join_deferred_aggregate()      # a first-contact dispatch reads the server replica
             for n in first:
                 server.register_client(n)
             if hasattr(server, "prepare_dispatch"):
@@ -313,6 +319,7 @@ class ExperimentStage:
                     self._process_val(client, log, curr_round, self.container)
 
         # ---- clients -> server ------------------------------------------------------------------------------------
+        self._join_deferred_aggregate()              # last round's deferred mean has read the upload slots
         with timer("upload"):
             for n in online:
                 client = local.get(n)
@@ -330,10 +337,44 @@ class ExperimentStage:
                 # calculate() overwrites the server replica in place: snapshots staged from live views of it (dispatch
                 # payloads, the server model) must have left the device first; client snapshots keep streaming
                 store.fence(server.name)
-            server.calculate()
+            overlap = (eng.get("overlap_aggregate", True) and self.device.type == "cuda" and comm is not None
+                       and getattr(comm, "mode", "") == "p2p" and hasattr(server, "calculate_deferred"))
+            if overlap:
+                # BASELINE.json: "federated rounds overlap aggregation with the next client's local step on CUDA
+                # streams". The part of the aggregation the next dispatch depends on stays here; the bulk runs on the
+                # communication stream (flag channel 1) next to the next round's mix / prototype pass / training.
+                server.calculate_urgent()
+                cs = self._comm_stream()
+                main = torch.cuda.current_stream(self.device)
+                cs.wait_stream(main)
+                with torch.cuda.stream(cs):
+                    comm.set_channel(1)
+                    try:
+                        server.calculate_deferred()
+                    finally:
+                        comm.set_channel(0)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                self._agg_event = ev
+            else:
+                server.calculate()
         if comm is not None:
             comm.poll_errors()            # a missed barrier surfaces in the round it happened, not at the very end
         log.flush()
+
+    def _comm_stream(self):
+        st = getattr(self, "_comm_stream_obj", None)
+        if st is None:
+            from ..ops import native
+            st = self._comm_stream_obj = native.dedicated_stream(self.device, priority=-1)
+        return st
+
+    def _join_deferred_aggregate(self) -> None:
+        """Make the compute stream wait for an aggregation that is still running on the communication stream."""
+        ev = getattr(self, "_agg_event", None)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self._agg_event = None
 
     def _train_parallel(self, todo, log, curr_round: int, workers: int) -> None:
         """``parallel`` clients per device train concurrently (the reference's thread pool, ``experiment.py:206-216``),
