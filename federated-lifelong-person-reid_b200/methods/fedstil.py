@@ -626,6 +626,9 @@ class Server(ServerModule):
 
     set_client_integrated_state = set_client_incremental_state
 
+    split_calculate = True      # ``calculate() == calculate_urgent() + calculate_deferred()`` (sub-classes that
+                                # override ``calculate`` must clear it)
+
     def calculate(self) -> Any:
         """FedAvg mean of theta into the server model + token exchange (``fedstil.py:1075-1096``)."""
         self.calculate_urgent()

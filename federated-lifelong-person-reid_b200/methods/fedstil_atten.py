@@ -205,6 +205,8 @@ class Client(base.Client):
 
 
 class Server(base.Server):
+    split_calculate = False         # the next dispatch needs the whole gathered stack: nothing can be deferred
+
     def __init__(self, server_name, model, operator, ckpt_root, **kwargs):
         super().__init__(server_name, model, operator, ckpt_root, **kwargs)
         self.stack: Optional[torch.Tensor] = None

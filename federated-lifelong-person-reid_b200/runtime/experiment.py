@@ -338,7 +338,7 @@ class ExperimentStage:
                 # payloads, the server model) must have left the device first; client snapshots keep streaming
                 store.fence(server.name)
             overlap = (eng.get("overlap_aggregate", True) and self.device.type == "cuda" and comm is not None
-                       and getattr(comm, "mode", "") == "p2p" and hasattr(server, "calculate_deferred"))
+                       and getattr(comm, "mode", "") == "p2p" and getattr(server, "split_calculate", False))
             if overlap:
                 # BASELINE.json: "federated rounds overlap aggregation with the next client's local step on CUDA
                 # streams". The part of the aggregation the next dispatch depends on stays here; the bulk runs on the
