@@ -7,7 +7,8 @@ bounds the round (``profiles/r2_scaling.md``). Here the host CPU does not touch 
 
 * The byte layout of a checkpoint file is a pure function of the state's *structure* (keys, shapes, dtypes): the
   legacy ``torch.save`` container is ``[pickles: magic, protocol, sys-info, object graph, storage keys]`` followed by
-  ``[int64 numel][raw bytes]`` per storage. :func:`legacy_layout` emits those pickles itself (tensors reduce to
+  ``[int64 numel][raw bytes]`` per storage; all tensors of one dtype are laid out as views of ONE storage, so the data
+  region is contiguous per dtype. :func:`legacy_layout` emits those pickles itself (tensors reduce to
   ``_rebuild_tensor_v2`` over persistent storage ids, exactly what ``torch.load`` expects) and pads the storage-key
   pickle with an ignored junk string so that the data region starts at a fixed offset even when scalars in the object
   graph (``train_cnt``) change their encoded width from round to round.
@@ -127,41 +128,57 @@ def _rebind(layout: "Layout", state: Any) -> "Layout":
     _tensors_in_order(state, ts, {})
     if len(ts) != len(layout.segments):
         raise ValueError("state does not match the cached layout")
+    by_dtype: Dict[torch.dtype, List[torch.Tensor]] = {}
+    for t in ts:                                            # file order: dtypes by first appearance, tensors in order
+        by_dtype.setdefault(t.dtype, []).append(t)
+    ts = [t for group in by_dtype.values() for t in group]
+    if any(t.numel() * t.element_size() != seg.nbytes for t, seg in zip(ts, layout.segments)):
+        raise ValueError("state does not match the cached layout")
     segs = [_Segment(t, seg.offset, seg.nbytes) for t, seg in zip(ts, layout.segments)]
     return Layout(layout.signature, layout.data_start, segs, layout.total, layout.headers)
 
 
-def _main_pickle(state: Any) -> Tuple[bytes, List[Tuple[_StorageRef, torch.Tensor]]]:
-    """The object-graph pickle of the legacy container with every tensor reduced to a contiguous
-    ``_rebuild_tensor_v2`` over its own storage; returns the bytes and the storages in file order."""
-    storages: List[Tuple[_StorageRef, torch.Tensor]] = []
-    by_id: Dict[int, _StorageRef] = {}
-    buf = io.BytesIO()
+def _main_pickle(state: Any) -> Tuple[bytes, List[Tuple[_StorageRef, List[Tuple[torch.Tensor, int]]]]]:
+    """The object-graph pickle of the legacy container. All tensors of one dtype are views of ONE storage (a tensor is
+    ``_rebuild_tensor_v2(storage, element offset, size, contiguous strides)``): the file then holds a single
+    ``[numel][data]`` record per dtype, i.e. the data region is contiguous - one DMA per dtype, no record headers in
+    between. Returns the bytes and ``[(storage, [(tensor, element offset), ...]), ...]`` in file order."""
+    def run(numels: Optional[Dict[torch.dtype, int]]):
+        groups: Dict[torch.dtype, Tuple[_StorageRef, List[Tuple[torch.Tensor, int]]]] = {}
+        by_id: Dict[int, Tuple[_StorageRef, int]] = {}
+        buf = io.BytesIO()
 
-    class P(pickle.Pickler):
-        def persistent_id(self, obj):                                   # noqa: D401
-            if isinstance(obj, _StorageRef):
-                return ("storage", _storage_type(obj.dtype), obj.key, "cpu", obj.numel, None)
-            return None
+        class P(pickle.Pickler):
+            def persistent_id(self, obj):                                   # noqa: D401
+                if isinstance(obj, _StorageRef):
+                    return ("storage", _storage_type(obj.dtype), obj.key, "cpu", obj.numel, None)
+                return None
 
-        def reducer_override(self, obj):
-            if isinstance(obj, torch.Tensor):
-                ref = by_id.get(id(obj))
-                if ref is None:
-                    ref = _StorageRef(str(len(storages)), obj.dtype, obj.numel())
-                    by_id[id(obj)] = ref
-                    storages.append((ref, obj))
-                stride = []
-                acc = 1
-                for d in reversed(obj.shape):
-                    stride.append(acc)
-                    acc *= max(int(d), 1)
-                return (torch._utils._rebuild_tensor_v2,
-                        (ref, 0, tuple(obj.shape), tuple(reversed(stride)), False, collections.OrderedDict()))
-            return NotImplemented
+            def reducer_override(self, obj):
+                if isinstance(obj, torch.Tensor):
+                    hit = by_id.get(id(obj))
+                    if hit is None:
+                        g = groups.get(obj.dtype)
+                        if g is None:
+                            ref = _StorageRef(str(len(groups)), obj.dtype, numels[obj.dtype] if numels else 0)
+                            g = groups[obj.dtype] = (ref, [])
+                        off = sum(t.numel() for t, _ in g[1][-1:]) + (g[1][-1][1] if g[1] else 0)
+                        g[1].append((obj, off))
+                        hit = by_id[id(obj)] = (g[0], off)
+                    stride, acc = [], 1
+                    for d in reversed(obj.shape):
+                        stride.append(acc)
+                        acc *= max(int(d), 1)
+                    return (torch._utils._rebuild_tensor_v2,
+                            (hit[0], hit[1], tuple(obj.shape), tuple(reversed(stride)), False, collections.OrderedDict()))
+                return NotImplemented
 
-    P(buf, protocol=2).dump(state)
-    return buf.getvalue(), storages
+        P(buf, protocol=2).dump(state)
+        return buf.getvalue(), list(groups.values())
+
+    _, groups = run(None)                                   # pass 1: which tensors, how many elements per dtype
+    numels = {ref.dtype: (members[-1][1] + members[-1][0].numel() if members else 0) for ref, members in groups}
+    return run(numels)                                      # pass 2: the real pickle (storage sizes are part of it)
 
 
 _HEAD: Optional[bytes] = None
@@ -192,9 +209,9 @@ def _keys_pickle(keys: List[str], pad: int) -> bytes:
 def legacy_layout(state: Any, data_start: Optional[int] = None) -> Tuple[Layout, bytes]:
     """Layout + prefix bytes of ``state`` in the legacy ``torch.save`` container. With ``data_start`` (a previous
     layout of the same structure) the prefix is padded to end exactly there; raises ``ValueError`` if it cannot."""
-    main, storages = _main_pickle(state)
+    main, groups = _main_pickle(state)
     head = _head_pickles()
-    keys = [ref.key for ref, _ in storages]
+    keys = [ref.key for ref, _ in groups]
     bare = len(head) + len(main) + len(_keys_pickle(keys, 0))
     if data_start is None:
         data_start = (bare + _SLACK + 63) // 64 * 64
@@ -205,11 +222,14 @@ def legacy_layout(state: Any, data_start: Optional[int] = None) -> Tuple[Layout,
     assert len(prefix) == data_start
     off = data_start
     segments, headers = [], []
-    for ref, t in storages:
-        nb = t.numel() * t.element_size()
-        headers.append((off, t.numel()))
-        segments.append(_Segment(t, off + 8, nb))
-        off += 8 + nb
+    for ref, members in groups:
+        esz = torch.empty(0, dtype=ref.dtype).element_size()
+        numel = members[-1][1] + members[-1][0].numel() if members else 0
+        headers.append((off, numel))
+        base = off + 8
+        for t, eoff in members:
+            segments.append(_Segment(t, base + eoff * esz, t.numel() * esz))
+        off = base + numel * esz
     return Layout(_signature(state), data_start, segments, off, headers), prefix
 
 
@@ -258,6 +278,7 @@ class MappedFile:
         self.stage_views: Optional[list] = None          # per segment: typed device view into ``stage`` (or None)
         self.prefix_key = None                           # scalars of the object graph the current prefix was made for
         self.stage_sig = None
+        self.stage_runs: List[Tuple[int, int]] = []      # (file offset, bytes) of the DMA runs
         self.static_done: Dict[int, Any] = {}            # segment index -> version of a static tensor already in the image
 
     def rename(self, new_path: str) -> None:
@@ -361,15 +382,10 @@ class MappedCheckpointStore(CheckpointStore):
             view[off:off + 8] = torch.frombuffer(bytearray(struct.pack("<q", numel)), dtype=torch.uint8)
 
     def _build_stage(self, mf: MappedFile, layout: Layout, dev: torch.device) -> None:
-        """Device image of the data region: storage headers scattered in once, one typed view per tensor."""
-        import struct
+        """Device image of the data region (no host traffic: the per-dtype record headers in it are never transferred,
+        the DMAs skip them) and one typed view per tensor."""
         ds = layout.data_start
         mf.stage = torch.empty(max(layout.total - ds, 8), dtype=torch.uint8, device=dev)
-        if layout.headers:
-            pos = torch.tensor([off - ds + b for off, _ in layout.headers for b in range(8)], dtype=torch.long)
-            val = torch.frombuffer(bytearray(b"".join(struct.pack("<q", n) for _, n in layout.headers)),
-                                   dtype=torch.uint8)
-            mf.stage[pos.to(dev)] = val.to(dev)
         views = []
         for seg in layout.segments:
             t = seg.tensor
@@ -379,6 +395,14 @@ class MappedCheckpointStore(CheckpointStore):
             else:
                 views.append(mf.stage[o:o + seg.nbytes].view(t.dtype).view(t.shape))
         mf.stage_views = views
+        # DMA runs: the data of each record (between two 8-byte headers)
+        runs, hdrs = [], sorted(off for off, _ in layout.headers)
+        for i, h in enumerate(hdrs):
+            lo = h + 8
+            hi = hdrs[i + 1] if i + 1 < len(hdrs) else layout.total
+            if hi > lo:
+                runs.append((lo, hi - lo))
+        mf.stage_runs = runs
 
     def _issue(self, mf: MappedFile, layout: Layout, prefix: Optional[bytes], dev: Optional[torch.device]) -> None:
         """Prefix by the CPU (a few KB, only when it changed); storages through the device image + ONE DMA (CUDA) or
@@ -430,11 +454,12 @@ class MappedCheckpointStore(CheckpointStore):
         ready = torch.cuda.Event()
         ready.record(cur)
         cs.wait_event(ready)
-        nbytes = layout.total - ds
-        rc = lib.flpr_memcpy_d2h_async(C.c_void_p(mf.ptr + ds), native.ptr(mf.stage), nbytes,
-                                       C.c_void_p(cs.cuda_stream))
-        native.check(rc, "flpr_memcpy_d2h_async")
-        self.dma_bytes += nbytes
+        base = mf.stage.data_ptr()
+        for lo, nbytes in mf.stage_runs:                 # one DMA per dtype record
+            rc = lib.flpr_memcpy_d2h_async(C.c_void_p(mf.ptr + lo), C.c_void_p(base + lo - ds), nbytes,
+                                           C.c_void_p(cs.cuda_stream))
+            native.check(rc, "flpr_memcpy_d2h_async")
+            self.dma_bytes += nbytes
         ev = torch.cuda.Event()
         ev.record(cs)
         mf.last_event = ev

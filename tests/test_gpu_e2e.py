@@ -251,25 +251,43 @@ def test_native_train_mode_trunk_matches_module(name, size, batch):
     before = native.launches()
     y = trunk(x)
     assert native.launches() - before > 50
+    ref16 = _copy.deepcopy(ref)
     with torch.no_grad():
         yr = ref.base.run_stages(x, 0, net.head_start)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y16 = ref16.base.run_stages(x, 0, net.head_start)
     assert y.shape == yr.shape
-    err = (y.float() - yr).abs().max().item()
-    assert err < 0.08 * yr.abs().max().item() + 0.05, (err, yr.abs().max().item())
+
+    def rel(a, b):
+        return ((a.float() - b.float()).norm() / b.float().norm()).item()
+    # Yardstick: PyTorch's own bf16 (autocast, cuDNN / ATen) against the fp32 module. Forty bf16 layers with batch
+    # statistics on a random-init net drift by ~25 % (rel. Frobenius) at the ResNet-50 cut - the native trunk must sit
+    # at that level (measured: 0.2538 vs 0.2559), and close to the bf16 module itself.
+    lib_err, nat_err = rel(y16, yr), rel(y, yr)
+    assert nat_err <= 1.15 * lib_err + 5e-3, (nat_err, lib_err)
     cos = torch.nn.functional.cosine_similarity(y.float().flatten(), yr.flatten(), dim=0).item()
-    assert cos > 0.995, cos
+    cos16 = torch.nn.functional.cosine_similarity(y16.float().flatten(), yr.flatten(), dim=0).item()
+    assert cos >= cos16 - 5e-3, (cos, cos16)
     # running statistics were updated like nn.BatchNorm2d does (momentum 0.1, unbiased variance)
     for (n1, b1), (n2, b2) in zip(net.base.named_modules(), ref.base.named_modules()):
         if isinstance(b1, torch.nn.BatchNorm2d) and not n1.startswith("layer4"):
-            assert torch.allclose(b1.running_mean, b2.running_mean, rtol=0.05, atol=0.02), n1
-            assert torch.allclose(b1.running_var, b2.running_var, rtol=0.08, atol=0.02), n1
+            if n1 in ("bn1", "layer1.0.bn1"):            # shallow: bf16 drift is negligible, the arithmetic is checked
+                assert torch.allclose(b1.running_mean, b2.running_mean, rtol=0.03, atol=5e-3), n1
+                assert torch.allclose(b1.running_var, b2.running_var, rtol=0.05, atol=5e-3), n1
+            else:                                        # deep: same statistics up to the drift measured above
+                c = torch.nn.functional.cosine_similarity(b1.running_mean, b2.running_mean, dim=0).item()
+                assert c > 0.9, (n1, c)
+                ratio = (b1.running_var / b2.running_var).mean().item()
+                assert 0.8 < ratio < 1.25, (n1, ratio)
+            assert int(b1.num_batches_tracked) == 1, n1
     # eval mode: running statistics
     net.eval(), ref.eval()
     y = trunk(x)
     with torch.no_grad():
         yr = ref.base.run_stages(x, 0, net.head_start)
-    cos = torch.nn.functional.cosine_similarity(y.float().flatten(), yr.flatten(), dim=0).item()
-    assert cos > 0.995, cos
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y16 = ref.base.run_stages(x, 0, net.head_start)
+    assert rel(y, yr) <= 1.15 * rel(y16, yr) + 5e-3, (rel(y, yr), rel(y16, yr))
 
 
 def test_fedavg_training_step_launches_no_library_conv_or_batchnorm(tmp_path):
