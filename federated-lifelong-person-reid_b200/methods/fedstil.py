@@ -118,10 +118,15 @@ class Model(ModelModule):
 
     # ---- reference checkpoint schema (fedstil.py:444-491) ------------------------------------------------------------
     def model_state(self, copy: bool = True) -> Dict:
-        """``copy=False`` returns views of the live tensors: for callers that serialise immediately (the checkpoint
-        store stages them on its copy stream before anything can overwrite them, see ``CheckpointStore.fence``)."""
+        """``copy=False`` returns views of the live tensors for callers that serialise immediately (the checkpoint
+        store snapshots them when ``save`` is called). That dict is *persistent*: the same object, over the same
+        device buffers, is handed out on every call - only the flat ``adaptive_weight = theta - a G`` buffer behind
+        its ``adaptive_weights`` views is recomputed (one fused op) - so the store can keep its copy plan
+        (``PersistentState.plan_token``) instead of re-analysing ~330 tensors on every snapshot."""
+        if not copy:
+            return self._persistent_state()
         a = self.arena
-        own = (lambda t: t.clone(memory_format=torch.contiguous_format)) if copy else (lambda t: t)
+        own = lambda t: t.clone(memory_format=torch.contiguous_format)          # noqa: E731
         gw, gwa, aw, ab = {}, {}, {}, {}
         for lname in self.adaptive_names:
             theta = a.view(a.master, f"{lname}.weight").detach()
@@ -135,17 +140,43 @@ class Model(ModelModule):
                 ab[f"{lname}.adaptive_bias"] = own(bias.detach())
         skip = {f"{n}.weight" for n in self.adaptive_names} | {f"{n}.bias" for n in self.adaptive_names}
         pre = {k: own(v.detach()) for k, v in self.net.state_dict().items() if k not in skip}
-        if not copy:
-            # The frozen stages never change between dispatches of pre-trained parameters (the trunk runs in eval mode,
-            # fedstil.py:569): the checkpoint store keeps them in its device image instead of re-copying ~250 tensors
-            # on every snapshot. ``_static_version`` is bumped whenever something writes them (update_model).
+        return {"global_weight": gw, "global_weight_atten": gwa, "adaptive_weights": aw, "adaptive_bias": ab,
+                "bn_params": {}, "pre_trained_params": pre}
+
+    def _persistent_state(self) -> Dict:
+        from ..runtime.checkpoint import PersistentState
+        a = self.arena
+        n = self.theta_numel
+        ver = getattr(self, "_static_version", 0)
+        st = getattr(self, "_pstate", None)
+        if st is None or st.plan_token[1] != ver or self._pstate_ptr != (a.master.data_ptr(), self.G.data_ptr()):
+            self._aw_flat = torch.empty(n, dtype=torch.float32, device=a.master.device)
+            gw, gwa, aw, ab = {}, {}, {}, {}
+            for lname in self.adaptive_names:
+                theta = a.view(a.master, f"{lname}.weight").detach()
+                gw[f"{lname}.global_weight"] = a.view(self.G, f"{lname}.weight").detach()
+                gwa[f"{lname}.global_weight_atten"] = torch.full((theta.shape[-1],), self.atten_default,
+                                                                 device=theta.device)
+                aw[f"{lname}.adaptive_weight"] = a.view(self._aw_flat, f"{lname}.weight")
+                bias = getattr(self.net.get_submodule(lname), "bias", None)
+                if bias is not None:
+                    ab[f"{lname}.adaptive_bias"] = bias.detach()
+            skip = {f"{nm}.weight" for nm in self.adaptive_names} | {f"{nm}.bias" for nm in self.adaptive_names}
+            pre = {k: v.detach() for k, v in self.net.state_dict().items() if k not in skip}
+            # The frozen stages never change between dispatches of pre-trained parameters (the trunk runs in eval
+            # mode, fedstil.py:569): the checkpoint store keeps them in its device image instead of re-copying ~250
+            # tensors on every snapshot. ``_static_version`` is bumped whenever something writes them (update_model).
             prefixes = self._frozen_prefixes()
-            ver = getattr(self, "_static_version", 0)
             for k, v in pre.items():
                 if k.startswith(prefixes):
                     v._flpr_static = ver
-        return {"global_weight": gw, "global_weight_atten": gwa, "adaptive_weights": aw, "adaptive_bias": ab,
-                "bn_params": {}, "pre_trained_params": pre}
+            st = self._pstate = PersistentState(
+                {"global_weight": gw, "global_weight_atten": gwa, "adaptive_weights": aw, "adaptive_bias": ab,
+                 "bn_params": {}, "pre_trained_params": pre})
+            st.plan_token = (id(self), ver)
+            self._pstate_ptr = (a.master.data_ptr(), self.G.data_ptr())
+        torch.sub(a.master[:n].detach(), self.G, alpha=self.atten_default, out=self._aw_flat)   # A = theta - a G
+        return st
 
     def _frozen_prefixes(self) -> Tuple[str, ...]:
         start = getattr(self.net, "head_start", 0)

@@ -27,6 +27,13 @@ import torch
 os.environ.setdefault("TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD", "1")  # exemplar ckpts hold numpy objects
 
 
+class PersistentState(dict):
+    """A state dict whose structure AND tensor objects stay the same from one ``save`` to the next (views of
+    long-lived device buffers; only their contents change). ``plan_token`` identifies that binding: a store may cache
+    whatever it derived from the structure (byte layout, copy plan) for as long as the token is unchanged."""
+    plan_token: Any = None
+
+
 def _to_cpu(obj: Any) -> Any:
     if isinstance(obj, torch.Tensor):
         return obj.detach().to("cpu", copy=True)

@@ -278,6 +278,8 @@ class MappedFile:
         self.stage_views: Optional[list] = None          # per segment: typed device view into ``stage`` (or None)
         self.prefix_key = None                           # scalars of the object graph the current prefix was made for
         self.stage_sig = None
+        self.plan_token = None                           # PersistentState binding the cached layout was made for
+        self.plan_dev = None
         self.stage_runs: List[Tuple[int, int]] = []      # (file offset, bytes) of the DMA runs
         self.static_done: Dict[int, Any] = {}            # segment index -> version of a static tensor already in the image
 
@@ -489,9 +491,20 @@ class MappedCheckpointStore(CheckpointStore):
         if post is not None:
             return super()._save_locked(actor, state_name, state, cover, post)
         with self._mlock:
+            old = self._files.get(path)
+            tok = getattr(state, "plan_token", None)
+            if tok is not None and old is not None and old.layout is not None and old.plan_token == tok \
+                    and old.plan_dev == dev:
+                # persistent state: same structure, same tensor objects - the cached copy plan is still valid
+                self._issue(old, old.layout, None, dev)
+                if old.last_event is not None:
+                    self._actor_events[actor] = old.last_event
+                self.bytes_written += old.layout.total
+                return
+            if tok is not None:
+                state = dict(state)             # a plain dict in the file: readers must not need our classes
             sig = _signature(state)
             scal = _scalars(state)
-            old = self._files.get(path)
             if old is not None and old.layout is not None and old.layout.signature == sig and old.prefix_key == scal \
                     and not (self.payload_ring > 0 and _PAYLOAD_NAME.match(os.path.basename(path))):
                 # same structure, same scalars: the pickles in the file are still right - re-point the segments only
@@ -519,6 +532,7 @@ class MappedCheckpointStore(CheckpointStore):
                         pass
                 self._issue(mf, layout, prefix, dev)
                 mf.prefix_key = scal
+            mf.plan_token, mf.plan_dev = tok, dev
             if mf.last_event is not None:
                 self._actor_events[actor] = mf.last_event
             self.bytes_written += layout.total

@@ -150,6 +150,23 @@ def test_mapped_store_overwrites_in_place_and_survives_growing_scalars(tmp_path)
     st.close()
 
 
+def test_mapped_store_persistent_state_plan(tmp_path):
+    """``PersistentState``: the same dict object over the same buffers - the second save reuses the cached layout (no
+    re-analysis), static tensors are not copied again, the file holds a plain dict."""
+    from flpr_b200.runtime.checkpoint import PersistentState
+    st = _mapped(tmp_path)
+    w, frozen = torch.randn(64, 8), torch.randn(32)
+    frozen._flpr_static = 0
+    state = PersistentState({"w": {"a": w}, "pre": {"f": frozen}})
+    state.plan_token = ("m", 0)
+    st.save("c0", "m", state, True)
+    w.mul_(2.0)
+    st.save("c0", "m", state, True)
+    out = torch.load(st.path("c0", "m"), weights_only=True)
+    assert type(out) is dict and torch.equal(out["w"]["a"], w) and torch.equal(out["pre"]["f"], frozen)
+    st.close()
+
+
 def test_mapped_store_payload_ring_recycles_old_rounds(tmp_path):
     st = _mapped(tmp_path, payload_ring=2)
     for r in range(1, 7):
