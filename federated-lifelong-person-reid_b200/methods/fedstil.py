@@ -679,7 +679,38 @@ class Server(ServerModule):
             for i, name in enumerate(self._round_uploads):
                 self.token_memory.setdefault(name, []).append(toks[i])
         self._round_uploads = []
-        self.save_state(f"{self.server_name}_tokens", self.token_memory, True)
+        self._save_tokens()
+
+    def _save_tokens(self) -> None:
+        """``{server}_tokens.ckpt`` (fedstil.py:1096). The token history grows by one tensor per client and round, so
+        its file is re-laid out every time; token tensors are never modified once appended, which makes the snapshot a
+        list of references - on CUDA it is written by a background thread of rank 0 (the server role is replicated:
+        every rank would write the same bytes), off the round's critical path."""
+        comm = self.comm
+        if comm is not None and getattr(comm, "rank", 0) != 0:
+            return
+        dev = self.model.device
+        if dev.type != "cuda" or not self.store.enabled or getattr(self.store, "muted", False):
+            self.save_state(f"{self.server_name}_tokens", self.token_memory, True)
+            return
+        snap = {k: list(v) for k, v in self.token_memory.items()}
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        pool = getattr(self, "_token_pool", None)
+        if pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = self._token_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="flpr-tokens")
+        path = self.store.path(self.name, f"{self.server_name}_tokens")
+
+        def write():
+            import os
+            ready.synchronize()
+            torch.cuda.set_device(dev)
+            cpu = {k: [t.detach().cpu() for t in v] for k, v in snap.items()}
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            torch.save(cpu, path + ".tmp")
+            os.replace(path + ".tmp", path)
+        self.store.track(pool.submit(write))               # ``store.flush()`` waits for it like for any snapshot
 
     def calculate_deferred(self) -> None:
         if self.uploaded:

@@ -401,7 +401,16 @@ class CheckpointStore:
             err, self._err = self._err, None
             raise RuntimeError(f"checkpoint writer failed: {err}")
 
+    def track(self, future) -> None:
+        """A write some actor performs on its own thread (FedSTIL's token history): ``flush`` waits for it too."""
+        with self._lock:
+            self._external = [f for f in getattr(self, "_external", []) if not f.done()] + [future]
+
     def flush(self) -> None:
+        with self._lock:
+            pending, self._external = list(getattr(self, "_external", [])), []
+        for f in pending:
+            f.result()
         with self._lock:
             if self._started:
                 while self._inflight:

@@ -312,6 +312,7 @@ class MappedCheckpointStore(CheckpointStore):
         self._files: Dict[str, MappedFile] = {}                                  # path -> mapping (stable names)
         self._ring: Dict[Tuple[str, Any], collections.deque] = {}                # (actor, signature) -> mappings
         self._ex_layouts: Dict[str, Any] = {}
+        self._ring_layouts: Dict[Any, Any] = {}                                  # ring key -> (layout, prefix, scalars)
         self._graveyard: List[MappedFile] = []                                   # retired mappings, closed at close()
         self._grown: set = set()
         self._mlock = threading.RLock()
@@ -514,16 +515,40 @@ class MappedCheckpointStore(CheckpointStore):
                     layout = None
             else:
                 layout = None
+            ring_key = None
+            if layout is None and self.payload_ring > 0 and _PAYLOAD_NAME.match(os.path.basename(path)):
+                # per-round names: the layout (and, without changing scalars, the prefix) of last round's file of the
+                # same kind is reused - nothing is pickled for an S2C payload, whose state holds tensors only
+                ring_key = (actor, re.sub(r"^\d+-", "", os.path.basename(path)), sig)
+                hit = self._ring_layouts.get(ring_key)
+                if hit is not None and hit[2] == scal:
+                    try:
+                        layout = _rebind(hit[0], state)
+                    except ValueError:
+                        layout = None
+                    if layout is not None:
+                        mf = self._acquire(actor, path, layout, register)
+                        self._issue(mf, layout, hit[1] if mf.prefix_key != (sig, scal) else None, dev)
+                        mf.prefix_key = (sig, scal)
+                        mf.plan_token, mf.plan_dev = None, dev
+                        if mf.last_event is not None:
+                            self._actor_events[actor] = mf.last_event
+                        self.bytes_written += layout.total
+                        return
             if layout is not None:
                 self._issue(old, layout, None, dev)
                 mf = old
             else:
                 start = old.layout.data_start if (old is not None and old.layout is not None
                                                   and old.layout.signature == sig) else None
+                if start is None and ring_key is not None and ring_key in self._ring_layouts:
+                    start = self._ring_layouts[ring_key][0].data_start      # recycled mappings keep their data offset
                 try:
                     layout, prefix = legacy_layout(state, start)
                 except ValueError:
                     layout, prefix = legacy_layout(state, None)
+                if ring_key is not None:
+                    self._ring_layouts[ring_key] = (layout, prefix, scal)
                 mf = self._acquire(actor, path, layout, register)
                 if mf.layout is not None and mf.layout.signature == sig and mf.layout.data_start != layout.data_start:
                     try:
@@ -531,7 +556,7 @@ class MappedCheckpointStore(CheckpointStore):
                     except ValueError:
                         pass
                 self._issue(mf, layout, prefix, dev)
-                mf.prefix_key = scal
+                mf.prefix_key = scal if ring_key is None else (sig, scal)
             mf.plan_token, mf.plan_dev = tok, dev
             if mf.last_event is not None:
                 self._actor_events[actor] = mf.last_event
