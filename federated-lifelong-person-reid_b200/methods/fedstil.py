@@ -273,9 +273,9 @@ class Model(ModelModule):
         if rows.numel() == 0 or m <= 0:
             return
         feats = []
+        fwd = self._herding_forward()
         for s in range(0, rows.numel(), batch_size):
-            with self.autocast():
-                feats.append(self.forward_head(protos[rows[s:s + batch_size]]).float())
+            feats.append(fwd(protos[rows[s:s + batch_size]]))
         feats = torch.cat(feats)                                             # [n_sel, D], aligned with `rows`
         sel_pids = pids[rows]
         order = torch.argsort(sel_pids, stable=True)
@@ -304,6 +304,21 @@ class Model(ModelModule):
                 kept.append({"pids": old["pids"][mk], "pid_list": [p for p, k_ in zip(old["pid_list"], mask) if k_],
                              "k": old["k"], "bank": old["bank"][mk], "cls": old["cls"][mk]})
         self.ex_gens = kept + [gen]
+
+    def _herding_forward(self):
+        """Eval-mode head forward that produces the herding features, CUDA-graph captured per batch shape: ~100 eager
+        launches per 256-prototype batch cost three times their device time in Python dispatch."""
+        fwd = getattr(self, "_herd_fwd", None)
+        if fwd is None:
+            from ..runtime.graphs import GraphedForward
+
+            def fn(x):
+                with self.autocast():
+                    return self.forward_head(x).float()
+            ok = (self.device.type == "cuda" and getattr(self, "use_cuda_graphs", True)
+                  and getattr(self.net, "thread_safe_rng", False) and getattr(self.net, "_fast_head", None) is not None)
+            fwd = self._herd_fwd = GraphedForward(fn, warmup=1, enabled=ok)
+        return fwd
 
     def examplar_tensors(self) -> Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
         """Expanded rehearsal set ``(protos, person_ids, class_ids)`` (duplicates included, like the reference)."""

@@ -93,6 +93,7 @@ class Model(ModelModule):
         if ex is None:
             return
         self.net.train()                                          # as in the reference (icarl.py:89)
+        self._mode_uniform = None                                 # (sub-modules toggled behind ModelModule.train)
         outs = []
         for s in range(0, ex[0].shape[0], batch_size):
             with self.autocast():

@@ -76,3 +76,39 @@ class GraphedStep:
 
     def reset(self) -> None:
         self._state.clear()
+
+
+class GraphedForward:
+    """``y = fn(x)`` for a no-grad forward (e.g. the eval-mode head that produces herding features): eager for the first
+    ``warmup`` calls of an input signature, then captured and replayed; returns a tensor the caller owns."""
+
+    def __init__(self, fn: Callable, warmup: int = 1, enabled: bool = True):
+        self.fn, self.warmup, self.enabled = fn, warmup, enabled
+        self._state: Dict[Tuple, dict] = {}
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        if not self.enabled or not x.is_cuda:
+            return self.fn(x)
+        sig = (tuple(x.shape), x.dtype, x.stride())
+        st = self._state.setdefault(sig, {"eager": 0, "graph": None})
+        if st["graph"] is None:
+            if st["eager"] < self.warmup:
+                st["eager"] += 1
+                return self.fn(x)
+            with CAPTURE_LOCK:
+                st["in"] = x.clone()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                native.capture_count_begin()
+                with capture(g):
+                    st["out"] = self.fn(st["in"])
+                st["launches"] = native.capture_count_end()
+                native.count_launch(-st["launches"])
+                st["graph"] = g
+        st["in"].copy_(x, non_blocking=True)
+        st["graph"].replay()
+        native.count_launch(st["launches"])
+        return st["out"].clone()
+
+    def reset(self) -> None:
+        self._state.clear()

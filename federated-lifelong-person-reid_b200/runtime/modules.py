@@ -45,6 +45,15 @@ class ModelModule(nn.Module):
     def forward(self, *args, **kwargs):
         return self.net(*args, **kwargs)
 
+    def train(self, mode: bool = True):
+        """``nn.Module.train`` walks ~160 sub-modules; the round loop toggles train / eval several times per client and
+        round, mostly to the mode the model is already in."""
+        if self.training == mode and getattr(self, "_mode_uniform", None) == mode:
+            return self
+        super().train(mode)
+        self._mode_uniform = mode
+        return self
+
     @property
     def device(self) -> torch.device:
         return next(self.parameters()).device

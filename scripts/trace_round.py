@@ -85,6 +85,17 @@ def main():
         agg[n[:80]][0] += 1; agg[n[:80]][1] += (e - s) / 1e3
     for n, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
         print(f"  {ms:8.2f} ms x{c:5d}  {n}")
+    # idle gaps of the whole device (all streams): where the GPU waits for the host
+    allk = sorted([(k[0], k[1], k[2]) for k in kern] + [(c[0], c[1], c[2]) for c in cpy])
+    gaps, cur_end, last_name = [], allk[0][1], allk[0][2]
+    for s_, e_, n_ in allk[1:]:
+        if s_ > cur_end + 200:                       # > 0.2 ms idle
+            gaps.append((s_ - cur_end, cur_end - t_lo, last_name[:50], n_[:50]))
+        if e_ > cur_end:
+            cur_end, last_name = e_, n_
+    print(f"idle gaps > 0.2 ms: {len(gaps)}, total {sum(g[0] for g in gaps) / 1e3:.1f} ms")
+    for g in sorted(gaps, reverse=True)[:40]:
+        print(f"  gap {g[0] / 1e3:7.2f} ms at t={g[1] / 1e3:9.2f}  after [{g[2]}]  before [{g[3]}]")
     # timeline of the big copies and of the comm kernels (where does the copy engine sit relative to fed_* ?)
     big = sorted([(e["ts"], e["dur"], e["name"], e["args"].get("bytes", 0), e["args"].get("stream")) for e in ev
                   if e.get("cat") == "gpu_memcpy" and e["args"].get("bytes", 0) >= (8 << 20)])
