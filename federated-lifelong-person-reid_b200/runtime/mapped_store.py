@@ -95,6 +95,26 @@ def _signature(obj: Any):
     return ("O", type(obj).__name__, len(pickle.dumps(obj, protocol=2)))
 
 
+def _has_foreign(obj: Any) -> bool:
+    """True when the state holds bulk data that is not a tensor (numpy arrays: iCaRL's exemplar images in the
+    reference schema). Such states keep the staged pipeline - their payload lives inside the pickle itself."""
+    stack = [obj]
+    while stack:
+        o = stack.pop()
+        if isinstance(o, (torch.Tensor, bool, int, float, str, type(None))):
+            continue
+        if isinstance(o, dict):
+            stack.extend(o.keys())
+            stack.extend(o.values())
+        elif isinstance(o, (list, tuple)):
+            stack.extend(o)
+        else:
+            nbytes = getattr(o, "nbytes", None)
+            if nbytes is None or nbytes > 64:
+                return True
+    return False
+
+
 def _scalars(obj: Any):
     """The non-tensor leaves of a state (what the pickle prefix depends on besides the structure)."""
     if isinstance(obj, torch.Tensor):
@@ -489,7 +509,7 @@ class MappedCheckpointStore(CheckpointStore):
             if self._save_examplars(actor, path, state, dev):
                 return
             return super()._save_locked(actor, state_name, state, cover, post)
-        if post is not None:
+        if post is not None or _has_foreign(state):
             return super()._save_locked(actor, state_name, state, cover, post)
         with self._mlock:
             old = self._files.get(path)
