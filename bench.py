@@ -140,7 +140,8 @@ def build_config(a, impl: str, world: int):
     exp = {
         "exp_name": f"bench-{a.method}", "exp_method": a.method, "random_seed": 123,
         "exp_opts": {"comm_rounds": 10 ** 6, "val_interval": 10 ** 9, "online_clients": a.clients},
-        "model_opts": {"name": a.model, "num_classes": 8000, "last_stride": 1, "neck": "bnneck",
+        "model_opts": {"name": a.model, "num_classes": 8000, "neck": "bnneck",
+                       **({} if a.model.startswith("swin") else {"last_stride": 1}),
                        **METHOD_MODEL_OPTS.get(a.method, {}),
                        **({"lambda_k": a.images} if a.method.startswith("fedstil") else {}),
                        **({"k": a.images} if a.method == "icarl" else {}),

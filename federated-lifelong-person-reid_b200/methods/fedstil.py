@@ -495,6 +495,12 @@ class Operator(OperatorModule):
         with model.autocast():
             return model.forward_head(data)
 
+    def _graph_capable(self, model: ModelModule) -> bool:
+        # the head step (prototype batch in, device-side accumulators out) is capturable for every backbone; Swin's
+        # stochastic depth draws from the default generator, which torch registers with the capture - and a backbone
+        # that is not ``thread_safe_rng`` is never trained on concurrent client threads
+        return model.device.type == "cuda" and getattr(model, "use_cuda_graphs", True)
+
     def invoke_train(self, model: Model, dataloader, **kwargs) -> Dict:
         from ..utils.trace import nvtx_range
         device = model.device

@@ -30,6 +30,52 @@ _SPECS = {
 }
 
 
+class TcLinear(nn.Linear):
+    """``nn.Linear`` whose CUDA / bf16 forward, data gradient and weight gradient run on the tcgen05 GEMM kernel
+    (``ops.gemm.linear``: bf16 compute copy of the weight kept by the fused optimizer, fp32 weight gradient written by
+    the GEMM epilogue straight into the parameter's slot of the arena gradient buffer). Same parameters, same
+    ``state_dict`` keys: an existing ``nn.Linear`` is switched over by re-classing it (:func:`use_tensor_core_linears`).
+    The bias stays an fp32 parameter; its gradient is the column sum of the output gradient (autograd)."""
+
+    _flpr_shadow = None          # param -> bf16 view (ParamArena.shadow_of)
+    _flpr_grad_slot = None       # param -> fp32 gradient view (ParamArena.grad_of)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        w = self.weight
+        native_ok = x.is_cuda and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0 and (
+            x.dtype == torch.bfloat16 or (x.dtype == torch.float32 and torch.is_autocast_enabled()))
+        if not native_ok:
+            return F.linear(x, w.to(x.dtype) if w.dtype != x.dtype else w,
+                            None if self.bias is None else self.bias.to(x.dtype))
+        from ..ops import gemm as gops
+        sh = self._flpr_shadow(w) if self._flpr_shadow is not None else None
+        if sh is None and not w.requires_grad:
+            sh = self._frozen_copy(w)                          # frozen stage: cached bf16 copy
+        gs = self._flpr_grad_slot(w) if (self._flpr_grad_slot is not None and w.requires_grad) else None
+        x2 = x.reshape(-1, x.shape[-1])
+        y = gops.linear(x2 if x2.dtype == torch.bfloat16 else x2.to(torch.bfloat16), w, sh, gs)
+        if self.bias is not None:
+            y = y + self.bias.to(y.dtype)
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    def _frozen_copy(self, w: torch.Tensor) -> torch.Tensor:
+        hit = self.__dict__.get("_flpr_wb")
+        if hit is None or hit[0] != w._version or hit[1] != w.data_ptr():
+            hit = self.__dict__["_flpr_wb"] = (w._version, w.data_ptr(), w.detach().to(torch.bfloat16))
+        return hit[2]
+
+
+def use_tensor_core_linears(root: nn.Module, shadow=None, grad_slot=None) -> int:
+    """Re-class every plain ``nn.Linear`` under ``root`` to :class:`TcLinear`; returns how many were switched."""
+    n = 0
+    for m in root.modules():
+        if type(m) is nn.Linear:
+            m.__class__ = TcLinear
+            m._flpr_shadow, m._flpr_grad_slot = shadow, grad_slot
+            n += 1
+    return n
+
+
 class DropPath(nn.Module):
     def __init__(self, p: float = 0.0):
         super().__init__()

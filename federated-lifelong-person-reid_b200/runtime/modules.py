@@ -90,6 +90,11 @@ class ModelModule(nn.Module):
                 self.net._fast_head = FastResNetHead(self.net, self.arena.shadow_of, self.arena.grad_of)
                 if getattr(self, "use_native_trunk", True):
                     self.net._native_trunk = NativeTrunk(self.net)
+            from ..models.swin import SwinTransformerReID, use_tensor_core_linears
+            if isinstance(self.net, SwinTransformerReID) and getattr(self, "use_tc_linears", True):
+                # every Linear of the backbone (qkv / proj / fc1 / fc2 / patch merging) and the classifier on the
+                # tcgen05 GEMM: trainable ones with the optimizer-maintained bf16 copy and direct gradient slots
+                use_tensor_core_linears(self.net, self.arena.shadow_of, self.arena.grad_of)
         return self
 
     def autocast(self):

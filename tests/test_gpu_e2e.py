@@ -382,3 +382,50 @@ def test_peer_memory_collectives_on_two_or_more_gpus():
                        capture_output=True, text=True, timeout=900, env=dict(os.environ, FLPR_BW_N=str(8_000_000)))
     print(r.stdout[-2000:])
     assert r.returncode == 0 and "DIST_COMM_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_swin_head_step_runs_its_linears_on_tcgen05():
+    """BASELINE config 4 (FedSTIL over Swin-T, bf16): every Linear of the trainable stage and the classifier runs on the
+    tcgen05 GEMM (forward, dgrad, wgrad into the arena slot) - no cuBLAS / cuBLASLt kernel in a head step - and the step
+    agrees with the fp32 module."""
+    import copy as _copy
+    from torch.profiler import ProfilerActivity, profile
+    from flpr_b200.models.swin import TcLinear
+    from flpr_b200.runtime.builder import parser_model
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    cfg = {"name": "swin_transformer_tiny", "num_classes": 8000, "neck": "bnneck", "atten_default": 0.9,
+           "lambda_l1": 1e-3, "lambda_k": 64, "drop_path_rate": 0.0, "fine_tuning": ["base.layers.3", "classifier"]}
+    model = parser_model("fedstil", cfg, dev, {"compute_dtype": "bf16"})
+    net = model.net
+    assert isinstance(net.classifier, TcLinear) and isinstance(net.base.layers[3].blocks[0].mlp.fc1, TcLinear)
+    tokens = (torch.randn(16, 49, 768, device=dev) * 0.5)
+    tgt = torch.randint(0, 8000, (16,), device=dev)
+    net.train()
+    ref = _copy.deepcopy(net).float()
+    for p in ref.parameters():
+        p.data = p.data.clone()
+    rs, rf = ref.forward_head(tokens)
+    torch.nn.functional.cross_entropy(rs, tgt).backward()
+
+    def step():
+        model.arena.zero_grad()
+        with model.autocast():
+            s, f = net.forward_head(tokens.to(torch.bfloat16))
+        torch.nn.functional.cross_entropy(s.float(), tgt).backward()
+        return s, f
+    s, f = step()
+    torch.cuda.synchronize()
+    assert torch.allclose(f.float(), rf, rtol=5e-2, atol=5e-2 * rf.abs().max().item())
+    for name in ("classifier.weight", "base.layers.3.blocks.1.mlp.fc2.weight", "base.layers.3.blocks.0.attn.qkv.weight"):
+        g_fast = model.arena.view(model.arena.grad, name)
+        g_ref = dict(ref.named_parameters())[name].grad
+        cos = torch.nn.functional.cosine_similarity(g_fast.flatten(), g_ref.flatten(), dim=0).item()
+        assert cos > 0.97, (name, cos)
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages()]
+    bad = [n for n in names if any(t in n.lower() for t in ("cublas", "cutlass", "gemv", "sgemm", "xmma", "nvjet"))]
+    assert not bad, bad
+    assert any("tcgen05" in n for n in names)
