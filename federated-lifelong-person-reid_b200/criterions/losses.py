@@ -80,18 +80,23 @@ class TripletLoss(CriterionModule):
         e = torch.exp(dist - mx) * mask
         return e / (e.sum(dim=1, keepdim=True) + 1e-6)
 
-    def forward(self, feature=None, target=None, score=None, **kwargs):
+    def mine(self, feature: torch.Tensor, target: torch.Tensor):
+        """``(dist_ap, dist_an)``: on CUDA the Gram matrix runs on the tcgen05 GEMM (forward and both gradients) with
+        the distance / mask / mining arithmetic fused in one kernel per direction (``csrc/loss_ops.cu``)."""
+        if fops.mined_distances_supported(feature) and getattr(self, "fused", True):
+            x = F.normalize(feature.float(), p=2, dim=1) if self.norm_feat else feature
+            return fops.mined_distances(x, target, bool(self.norm_feat), bool(self.hard_mining))
         dist = cosine_dist(feature, feature) if self.norm_feat else euclidean_dist(feature, feature)
         n = dist.size(0)
         same = target.view(n, 1).eq(target.view(1, n))
         is_pos, is_neg = same.float(), (~same).float()
         if self.hard_mining:
-            dist_ap = (dist * is_pos).max(dim=1)[0]
-            dist_an = (dist * is_neg + is_pos * 1e9).min(dim=1)[0]
-        else:
-            ap, an = dist * is_pos, dist * is_neg
-            dist_ap = (ap * self._softmax_weights(ap, is_pos)).sum(1)
-            dist_an = (an * self._softmax_weights(-an, is_neg)).sum(1)
+            return (dist * is_pos).max(dim=1)[0], (dist * is_neg + is_pos * 1e9).min(dim=1)[0]
+        ap, an = dist * is_pos, dist * is_neg
+        return (ap * self._softmax_weights(ap, is_pos)).sum(1), (an * self._softmax_weights(-an, is_neg)).sum(1)
+
+    def forward(self, feature=None, target=None, score=None, **kwargs):
+        dist_ap, dist_an = self.mine(feature, target)
         y = torch.ones_like(dist_an)
         if self.margin is not None and self.margin > 0:
             return F.margin_ranking_loss(dist_an, dist_ap, y, margin=self.margin)
@@ -115,7 +120,4 @@ class DistillKL(CriterionModule):
         t = y_teacher if y_teacher is not None else teacher_score
         if t is None:
             return s.new_zeros(())
-        T = self.temperature
-        p_s = F.log_softmax(s.float() / T, dim=1)
-        p_t = F.softmax(t.float() / T, dim=1)
-        return F.kl_div(p_s, p_t, reduction="sum") * (T ** 2) / s.shape[0]
+        return fops.kd_kl(s, t, self.temperature)          # fused forward + gradient on CUDA (csrc/loss_ops.cu)

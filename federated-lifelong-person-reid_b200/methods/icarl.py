@@ -209,9 +209,13 @@ class Operator(OperatorModule):
                 self.optimizer.zero_grad()
                 with model.autocast():
                     score, _ = model.forward(data)
-                score = score.float()
-                loss = F.binary_cross_entropy_with_logits(score, get_one_hot(target, model.n_classes)) + \
-                    F.binary_cross_entropy_with_logits(score[:, :pc], torch.sigmoid(pl[:, :pc]))
+                if score.is_cuda:
+                    from ..ops.fused import bce_distill          # both BCE terms + gradient in one kernel
+                    loss = bce_distill(score, target, pl[:, :pc])
+                else:
+                    score = score.float()
+                    loss = F.binary_cross_entropy_with_logits(score, get_one_hot(target, model.n_classes)) + \
+                        F.binary_cross_entropy_with_logits(score[:, :pc], torch.sigmoid(pl[:, :pc]))
                 loss.backward()
                 self.optimizer.step()
         # (2) criterion pass over exemplars U task (ConcatDataset + shuffle)

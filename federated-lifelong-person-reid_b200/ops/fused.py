@@ -364,3 +364,147 @@ def window_attention(qkv: torch.Tensor, bias: torch.Tensor, scale: float) -> tor
     s = s.view(bw // nwb, nwb, h, n, n) + bias.float().unsqueeze(0)
     p = torch.softmax(s.view(bw, h, n, n), dim=-1)
     return (p @ v).transpose(1, 2).reshape(bw, n, h * d).to(qkv.dtype)
+
+
+# --------------------------------------------------------------------------------------------- metric / KD losses
+class _MinedDistancesFn(torch.autograd.Function):
+    """``(dist_ap, dist_an)`` of the fast-reid triplet loss (``criterions/triplet_loss.py:89-127``): Gram matrix on the
+    tcgen05 GEMM (bf16 hi / lo split: ~fp32 accuracy, the distances are differences of large numbers), distance row +
+    masks + hard / softmax-weighted mining in one kernel per anchor; backward = one small kernel that folds the mining
+    Jacobians with the incoming gradients into ``S = W + W^T`` and ONE tcgen05 GEMM ``S @ X``."""
+
+    @staticmethod
+    def forward(ctx, x, labels, cosine, hard):
+        from .rank import similarity
+        lib = native.load()
+        xf = x.float().contiguous()
+        b = xf.shape[0]
+        dev = xf.device
+        G = similarity(xf, xf, precise=True)                                  # [B, B] fp32
+        sq = (xf * xf).sum(1) if not cosine else None
+        dist_ap = torch.empty(b, dtype=torch.float32, device=dev)
+        dist_an = torch.empty(b, dtype=torch.float32, device=dev)
+        jap = torch.empty(b, b, dtype=torch.float32, device=dev)
+        jan = torch.empty(b, b, dtype=torch.float32, device=dev)
+        lab = labels.to(dev).long().contiguous()
+        rc = lib.flpr_triplet_mine_fwd(native.ptr(G), G.stride(0), native.ptr(sq), native.ptr(lab), b, int(cosine),
+                                       int(hard), native.ptr(dist_ap), native.ptr(dist_an), native.ptr(jap),
+                                       native.ptr(jan), native.stream(dev))
+        native.check(rc, "flpr_triplet_mine_fwd")
+        native.count_launch()
+        ctx.save_for_backward(xf, jap, jan)
+        ctx.cosine = bool(cosine)
+        ctx.in_dtype = x.dtype
+        return dist_ap, dist_an
+
+    @staticmethod
+    def backward(ctx, g_ap, g_an):
+        from .gemm import gemm
+        xf, jap, jan = ctx.saved_tensors
+        b, d = xf.shape
+        dev = xf.device
+        lib = native.load()
+        lds = (b + 7) // 8 * 8
+        S = torch.empty(b, lds, dtype=torch.bfloat16, device=dev)
+        rs = torch.empty(b, dtype=torch.float32, device=dev)
+        g_ap = (g_ap if g_ap is not None else torch.zeros(b, device=dev)).float().contiguous()
+        g_an = (g_an if g_an is not None else torch.zeros(b, device=dev)).float().contiguous()
+        rc = lib.flpr_triplet_mine_bwd(native.ptr(jap), native.ptr(jan), native.ptr(g_ap), native.ptr(g_an), b,
+                                       native.ptr(S), lds, native.ptr(rs), native.stream(dev))
+        native.check(rc, "flpr_triplet_mine_bwd")
+        native.count_launch()
+        xb = xf.to(torch.bfloat16)
+        if lds != b:
+            xb = torch.nn.functional.pad(xb, (0, 0, 0, lds - b))
+        # S [B, K = B'] (K-major) x X [K = B', N = D] (MN-major): fp32 out; hi / lo split of X keeps fp32-level accuracy
+        sx = gemm(S, xb, b_kmajor=False, out_dtype=torch.float32)
+        x_lo = (xf - xf.to(torch.bfloat16).float()).to(torch.bfloat16)
+        if lds != b:
+            x_lo = torch.nn.functional.pad(x_lo, (0, 0, 0, lds - b))
+        sx = sx + gemm(S, x_lo, b_kmajor=False, out_dtype=torch.float32)
+        if ctx.cosine:
+            dx = -sx                                                           # d(1 - <xi, xj>) / d xi = -xj
+        else:
+            dx = 2.0 * (rs[:, None] * xf - sx)                                 # d|xi - xj|^2 / d xi = 2 (xi - xj)
+        return dx.to(ctx.in_dtype), None, None, None
+
+
+def mined_distances(x: torch.Tensor, labels: torch.Tensor, cosine: bool, hard: bool):
+    """``(dist_ap, dist_an)`` for a feature batch ``x`` ``[B, D]`` (already L2-normalised when ``cosine``)."""
+    return _MinedDistancesFn.apply(x, labels, cosine, hard)
+
+
+def mined_distances_supported(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dim() == 2 and x.shape[1] % 8 == 0 and 2 <= x.shape[0] <= 4096
+
+
+class _KDKLFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, t, temperature):
+        lib = native.load()
+        s, t = s.contiguous(), t.contiguous().to(s.dtype)
+        b, c = s.shape
+        ds = torch.empty(b, c, dtype=torch.float32, device=s.device)
+        loss = torch.zeros(1, dtype=torch.float32, device=s.device)
+        rc = lib.flpr_kd_kl(native.ptr(s), native.ptr(t), native.ptr(ds), native.ptr(loss), b, c, s.stride(0),
+                            t.stride(0), float(temperature), int(s.dtype == torch.bfloat16), native.stream(s.device))
+        native.check(rc, "flpr_kd_kl")
+        native.count_launch()
+        ctx.save_for_backward(ds)
+        ctx.in_dtype = s.dtype
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (ds,) = ctx.saved_tensors
+        return (ds * g).to(ctx.in_dtype), None, None
+
+
+def kd_kl(student: torch.Tensor, teacher: torch.Tensor, temperature: float) -> torch.Tensor:
+    """``KL(softmax(t/T) || softmax(s/T)) * T^2 / B`` (``criterions/kd_loss.py:10-27``), fused forward + gradient."""
+    if not student.is_cuda or student.dtype not in (torch.float32, torch.bfloat16):
+        T = temperature
+        p_s = F.log_softmax(student.float() / T, dim=1)
+        p_t = F.softmax(teacher.float() / T, dim=1)
+        return F.kl_div(p_s, p_t, reduction="sum") * (T ** 2) / student.shape[0]
+    return _KDKLFn.apply(student, teacher.detach(), temperature)
+
+
+class _BCEDistillFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, target, prev):
+        lib = native.load()
+        z = z.contiguous()
+        b, c = z.shape
+        p = 0 if prev is None else min(int(prev.shape[1]), c)
+        prev_f = None if prev is None else prev.float().contiguous()
+        dz = torch.empty(b, c, dtype=torch.float32, device=z.device)
+        loss = torch.zeros(1, dtype=torch.float32, device=z.device)
+        rc = lib.flpr_bce_distill(native.ptr(z), native.ptr(target.to(z.device).long().contiguous()),
+                                  native.ptr(prev_f), native.ptr(dz), native.ptr(loss), b, c, p, z.stride(0),
+                                  0 if prev_f is None else prev_f.stride(0), int(z.dtype == torch.bfloat16),
+                                  native.stream(z.device))
+        native.check(rc, "flpr_bce_distill")
+        native.count_launch()
+        ctx.save_for_backward(dz)
+        ctx.in_dtype = z.dtype
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        return (dz * g).to(ctx.in_dtype), None, None
+
+
+def bce_distill(score: torch.Tensor, target: torch.Tensor, prev_logits: Optional[torch.Tensor]) -> torch.Tensor:
+    """iCaRL's distillation-pass loss (``methods/icarl.py:226-234``): ``BCEWithLogits(score, onehot(target))`` +
+    ``BCEWithLogits(score[:, :P], sigmoid(prev_logits))`` (both mean-reduced), one fused kernel with gradient."""
+    if not score.is_cuda or score.dtype not in (torch.float32, torch.bfloat16):
+        z = score.float()
+        onehot = torch.zeros_like(z).scatter_(1, target.view(-1, 1).to(z.device), 1.0)
+        loss = F.binary_cross_entropy_with_logits(z, onehot)
+        if prev_logits is not None:
+            p = min(prev_logits.shape[1], z.shape[1])
+            loss = loss + F.binary_cross_entropy_with_logits(z[:, :p], torch.sigmoid(prev_logits[:, :p].float()))
+        return loss
+    return _BCEDistillFn.apply(score, target, None if prev_logits is None else prev_logits.detach())

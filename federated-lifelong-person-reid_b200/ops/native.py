@@ -74,6 +74,10 @@ def _declare(lib: C.CDLL) -> None:
         "flpr_window_attn_bwd": [P, P, P, P, P, I, I, I, I, I, F, I, P],
         "flpr_s2d_pad": [P, P, I, I, I, P],
         "flpr_maxpool3x3s2": [P, P, I, I, I, I, P],
+        "flpr_triplet_mine_fwd": [P, L, P, P, I, I, I, P, P, P, P, P],
+        "flpr_triplet_mine_bwd": [P, P, P, P, I, P, L, P, P],
+        "flpr_kd_kl": [P, P, P, P, I, I, L, L, F, I, P],
+        "flpr_bce_distill": [P, P, P, P, P, I, I, I, L, L, I, P],
         "flpr_memcpy_d2h_async": [P, P, Z, P],
         "flpr_memcpy2d_d2h_async": [P, Z, P, Z, Z, Z, P],
         "flpr_host_register": [P, Z],

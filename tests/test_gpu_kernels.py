@@ -583,3 +583,60 @@ def test_fused_window_attention(dtype, bw, n, h, d, nwb):
     _close(out, ref, rtol=tol, atol=tol * ref.abs().max().item())
     _close(qkv.grad, q32.grad, rtol=tol, atol=tol * q32.grad.abs().max().item())
     _close(bias.grad, b32.grad, rtol=tol, atol=tol * b32.grad.abs().max().item() + 1e-6)
+
+
+@pytest.mark.parametrize("cosine", [False, True])
+@pytest.mark.parametrize("hard", [False, True])
+@pytest.mark.parametrize("margin", [0.3, None])
+def test_fused_triplet_loss_matches_tensor_ops(cosine, hard, margin):
+    """Triplet loss with the Gram matrix on the tcgen05 GEMM and fused mining (``csrc/loss_ops.cu``), forward and the
+    gradient w.r.t. the features, against the plain fp32 tensor-op form (``criterions/triplet_loss.py:89-127``)."""
+    from flpr_b200.criterions import TripletLoss
+    torch.manual_seed(3)
+    b, d = 64, 2048
+    labels = torch.arange(16, device="cuda").repeat_interleave(4)[torch.randperm(b, device="cuda")]
+    x0 = (torch.randn(b, d, device="cuda") * 0.5 + labels[:, None].float() * 0.01)
+    outs = []
+    for fused in (True, False):
+        x = x0.clone().requires_grad_(True)
+        crit = TripletLoss(margin=margin, norm_feat=cosine, hard_mining=hard)
+        crit.fused = fused
+        loss = crit(feature=x, target=labels)
+        loss.backward()
+        outs.append((loss.detach(), x.grad.detach()))
+    (lf, gf), (lr, gr) = outs
+    assert abs(lf.item() - lr.item()) <= 2e-3 * max(1.0, abs(lr.item())), (lf.item(), lr.item())
+    cos = torch.nn.functional.cosine_similarity(gf.flatten(), gr.flatten(), dim=0).item()
+    assert cos > 0.999, cos
+    assert (gf - gr).abs().max().item() <= 2e-2 * gr.abs().max().item() + 1e-7
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_kd_and_bce_distill(dtype):
+    import torch.nn.functional as F
+    from flpr_b200.ops.fused import bce_distill, kd_kl
+    torch.manual_seed(5)
+    b, c, p = 48, 730, 500
+    s0 = (torch.randn(b, c, device="cuda") * 2).to(dtype)
+    t = (torch.randn(b, c, device="cuda") * 2).to(dtype)
+    s = s0.clone().requires_grad_(True)
+    T = 4.0
+    loss = kd_kl(s, t, T)
+    loss.backward()
+    sr = s0.float().clone().requires_grad_(True)
+    ref = F.kl_div(F.log_softmax(sr / T, dim=1), F.softmax(t.float() / T, dim=1), reduction="sum") * T * T / b
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 2e-3 * max(1.0, abs(ref.item()))
+    _close(s.grad.float(), sr.grad, rtol=2e-2, atol=2e-2 * sr.grad.abs().max().item())
+    # iCaRL distillation pass
+    tgt = torch.randint(0, c, (b,), device="cuda")
+    prev = torch.randn(b, p, device="cuda")
+    z = s0.clone().requires_grad_(True)
+    l2 = bce_distill(z, tgt, prev)
+    l2.backward()
+    zr = s0.float().clone().requires_grad_(True)
+    onehot = torch.zeros(b, c, device="cuda").scatter_(1, tgt.view(-1, 1), 1.0)
+    r2 = F.binary_cross_entropy_with_logits(zr, onehot) + F.binary_cross_entropy_with_logits(zr[:, :p], torch.sigmoid(prev))
+    r2.backward()
+    assert abs(l2.item() - r2.item()) < 2e-3 * max(1.0, abs(r2.item()))
+    _close(z.grad.float(), zr.grad, rtol=2e-2, atol=2e-2 * zr.grad.abs().max().item())
