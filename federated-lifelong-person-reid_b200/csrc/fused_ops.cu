@@ -964,6 +964,176 @@ __global__ void __launch_bounds__(64) window_attn_fwd_kernel(const T* qkv, const
 
 // Backward: recompute P, then dV = P^T dO, dP = dO V^T, dS = P (.) (dP - rowsum(dP (.) P)), dQ = scale dS K,
 // dK = scale dS^T Q, dBias += dS (atomic over the images that share a window index).
+
+// ----------------------------------------------------------------------------- Swin window attention on tcgen05
+// Forward only (the frozen stages never need a gradient; the trainable stage's backward keeps the kernel above).
+// A persistent CTA of 128 threads walks (window, head) pairs. Per pair:
+//   * Q [N x 32], K [N x 32] are copied into 128B-swizzled K-major operand tiles (rows = tokens padded to 128 / 64, the
+//     K extent padded 32 -> 64 with zeros written once), V is TRANSPOSED on the way in (Vt [32 x N], K extent = keys);
+//   * S = Q K^T: two tcgen05.mma (M 128, N 64, K 16) into 64 TMEM columns;
+//   * softmax: thread = row (tcgen05.ld 32x32b gives every thread its whole 64-column score row, so max / sum need no
+//     shuffles), + relative-position bias (+ shift mask), exp2 with the scale folded in; P (bf16, un-normalised) is
+//     written back as the next A operand, 1 / sum stays in a register;
+//   * O = P V: four tcgen05.mma (M 128, N 32, K 16) into 32 more TMEM columns; epilogue scales by 1 / sum and stores
+//     the 64-byte output row.
+// Swin: N = 49 (or 16), D = 32 for every model size. Reference: models/swin_transformer.py:255-286.
+constexpr int WA_THREADS = 128;
+constexpr int WA_SQ = 0;                       // 128 rows x 128 B
+constexpr int WA_SK = 128 * 128;               //  64 rows x 128 B
+constexpr int WA_SVT = WA_SK + 64 * 128;       //  32 rows x 128 B
+constexpr int WA_SP = WA_SVT + 32 * 128;       // 128 rows x 128 B   (WA_SVT is 4 KB: WA_SP stays 1024-aligned)
+constexpr int WA_BAR = WA_SP + 128 * 128;
+constexpr int WA_SMEM = WA_BAR + 64 + 1024;
+
+// byte offset of 16-byte chunk `c` (0..7) of row `r` in a K-major SWIZZLE_128B tile (8-row x 128 B atoms)
+__device__ __forceinline__ uint32_t wa_swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+__global__ void __launch_bounds__(WA_THREADS, 4)
+window_attn_fwd_tc_kernel(const __nv_bfloat16* qkv, const float* bias, __nv_bfloat16* out, int N, int H, int nWb,
+                          float scale, int total_pairs) {
+  extern __shared__ uint8_t wa_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wa_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + WA_BAR);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + WA_BAR + 16);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int D = 32;
+
+  for (int i = tid; i < WA_BAR / 16; i += WA_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t sQ = smem_u32(smem + WA_SQ), sK = smem_u32(smem + WA_SK), sVt = smem_u32(smem + WA_SVT),
+                 sP = smem_u32(smem + WA_SP);
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+  constexpr uint32_t idesc_o = make_idesc_bf16(128, 32, 0, 0);
+  const size_t row_stride = (size_t)3 * H * D;
+  const float sl2 = scale * 1.4426950408889634f;            // exp(x) = exp2(x * log2 e)
+  uint32_t phase = 0;
+
+  for (int p = blockIdx.x; p < total_pairs; p += gridDim.x) {
+    const int bw = p / H, h = p - bw * H;
+    const __nv_bfloat16* base = qkv + (size_t)bw * N * row_stride + (size_t)h * D;
+    // ---- operands: Q, K row-wise (4 chunks of 16 B per token), V transposed
+    for (int t = tid; t < N * 4; t += WA_THREADS) {
+      const int r = t >> 2, c = t & 3;
+      const __nv_bfloat16* src = base + (size_t)r * row_stride + c * 8;
+      const uint4 q = *reinterpret_cast<const uint4*>(src);
+      const uint4 k = *reinterpret_cast<const uint4*>(src + (size_t)H * D);
+      const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)2 * H * D);
+      sts_128(sQ + wa_swz(r, c), q);
+      sts_128(sK + wa_swz(r, c), k);
+      const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int d = c * 8 + e;                             // Vt[d][r]
+        *reinterpret_cast<__nv_bfloat16*>(smem + WA_SVT + wa_swz(d, r >> 3) + (r & 7) * 2) = ve[e];
+      }
+    }
+    fence_proxy_async();                                     // generic-proxy smem writes -> visible to tcgen05.mma
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k)                            // D = 32 -> two K = 16 steps (the padded half is zero)
+        umma_f16(tmem, make_smem_desc_sw128(sQ + k * 32, 16, 1024), make_smem_desc_sw128(sK + k * 32, 16, 1024),
+                 idesc_s, k != 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- softmax: thread = row
+    const int r = tid;
+    float inv = 0.f;
+    if (warp < 2) {                                          // rows 0..63 (N <= 64); warp-uniform TMEM loads
+      uint32_t s0[32], s1[32];
+      const uint32_t tb = tmem + (uint32_t(warp * 32) << 16);
+      tmem_ld_32x32b_x32(tb, s0);
+      tmem_ld_32x32b_x32(tb + 32, s1);
+      tmem_ld_wait();
+      if (r < N) {
+        const float* brow = bias + (((size_t)(bw % nWb) * H + h) * N + r) * N;
+        float v[64];
+        float mx = -3.0e38f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const float sc = __uint_as_float(j < 32 ? s0[j & 31] : s1[j & 31]);
+          const float x = (j < N) ? fmaf(sc, sl2, brow[j] * 1.4426950408889634f) : -3.0e38f;
+          v[j] = x;
+          mx = fmaxf(mx, x);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const float e = (j < N) ? exp2f(v[j] - mx) : 0.f;
+          v[j] = e;
+          sum += e;
+        }
+        inv = 1.f / sum;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 pk;
+          __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) hh[t] = __floats2bfloat162_rn(v[c * 8 + 2 * t], v[c * 8 + 2 * t + 1]);
+          sts_128(sP + wa_swz(r, c), pk);
+        }
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)                            // K = 64 keys -> four K = 16 steps
+        umma_f16(tmem + 64, make_smem_desc_sw128(sP + k * 32, 16, 1024), make_smem_desc_sw128(sVt + k * 32, 16, 1024),
+                 idesc_o, k != 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    if (warp < 2) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem + 64 + (uint32_t(warp * 32) << 16), o);
+      tmem_ld_wait();
+      if (r < N) {
+        __nv_bfloat16* dst = out + ((size_t)bw * N + r) * H * D + (size_t)h * D;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 pk;
+          __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            hh[t] = __floats2bfloat162_rn(__uint_as_float(o[c * 8 + 2 * t]) * inv,
+                                          __uint_as_float(o[c * 8 + 2 * t + 1]) * inv);
+          reinterpret_cast<uint4*>(dst)[c] = pk;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                                         // operands / accumulators free for the next pair
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(64) window_attn_bwd_kernel(const T* qkv, const float* bias, const T* dout, T* dqkv,
                                                              float* dbias, int N, int H, int D, int nWb,
@@ -1297,10 +1467,34 @@ int flpr_maxpool3x3s2(const void* x, void* y, int B, int H, int W, int C, cudaSt
 }
 
 // Fused Swin window attention. qkv [BW,N,3,H,D], bias fp32 [nWb,H,N,N], out [BW,N,H*D]; bf16 != 0: bf16 tensors.
+static int g_window_attn_tc = 1;
+void flpr_window_attn_set_tc(int on) { g_window_attn_tc = on; }
+
 int flpr_window_attn_fwd(const void* qkv, const float* bias, void* out, int BW, int N, int H, int D, int nWb,
                          float scale, int bf16, cudaStream_t st) {
   bind_device_of(qkv);
   if (N > ATT_MAXN || D > ATT_MAXD || N < 1) return -2;
+  if (bf16 && D == 32 && g_window_attn_tc && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    // tensor-core path: persistent CTAs over (window, head) pairs, QK^T and PV on tcgen05 with TMEM accumulators
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(window_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           WA_SMEM);
+      if (e != cudaSuccess) return (int)e;
+      configured = true;
+    }
+    const long long pairs = (long long)BW * H;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long cap = (long long)sms * 4;
+    const int grid_tc = (int)(pairs < cap ? pairs : cap);
+    window_attn_fwd_tc_kernel<<<grid_tc, WA_THREADS, WA_SMEM, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), bias,
+                                                                    reinterpret_cast<__nv_bfloat16*>(out), N, H, nWb,
+                                                                    scale, (int)pairs);
+    return (int)cudaGetLastError();
+  }
   const size_t smem = ((size_t)2 * N * (D + 1) + (size_t)N * (N + 1)) * sizeof(float);
   dim3 grid(BW, H);
   if (bf16)

@@ -99,6 +99,8 @@ def _declare(lib: C.CDLL) -> None:
     for name in ("flpr_gemm_last_error", "flpr_comm_last_error"):
         getattr(lib, name).restype = C.c_char_p
         getattr(lib, name).argtypes = []
+    lib.flpr_window_attn_set_tc.argtypes = [I]
+    lib.flpr_window_attn_set_tc.restype = None
     lib.flpr_comm_set_one_shot_bytes.argtypes = [I]
     lib.flpr_comm_set_one_shot_bytes.restype = None
     for name in ("flpr_comm_flag_page_bytes", "flpr_comm_max_clients", "flpr_comm_max_local", "flpr_comm_max_ranks",

@@ -640,3 +640,30 @@ def test_fused_kd_and_bce_distill(dtype):
     r2.backward()
     assert abs(l2.item() - r2.item()) < 2e-3 * max(1.0, abs(r2.item()))
     _close(z.grad.float(), zr.grad, rtol=2e-2, atol=2e-2 * zr.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("bw,n,h,nwb", [(64 * 64, 49, 3, 64), (64 * 16, 49, 6, 16), (64, 49, 24, 1), (37, 16, 12, 1)])
+def test_window_attention_tcgen05_forward(bw, n, h, nwb):
+    """The tcgen05 forward (QK^T and PV on the tensor cores, TMEM accumulators, thread-per-row softmax) against the
+    CUDA-core kernel and the fp32 tensor-op reference, at the real Swin-T stage shapes (batch 64)."""
+    from flpr_b200.ops import native
+    from flpr_b200.ops.fused import window_attention
+    lib = native.load()
+    torch.manual_seed(7)
+    d = 32
+    qkv = torch.randn(bw, n, 3, h, d, device="cuda").to(torch.bfloat16)
+    bias = torch.randn(nwb, h, n, n, device="cuda") * 0.5
+    bias[:, :, :, -3:] -= 100.0 * (torch.rand(nwb, h, n, 3, device="cuda") > 0.7)       # shift-mask like entries
+    scale = d ** -0.5
+    outs = {}
+    for tc in (1, 0):
+        lib.flpr_window_attn_set_tc(tc)
+        with torch.no_grad():
+            outs[tc] = window_attention(qkv, bias, scale).float()
+    lib.flpr_window_attn_set_tc(1)
+    q, k, v = qkv.float().permute(2, 0, 3, 1, 4)
+    s = (q * scale) @ k.transpose(-1, -2)
+    s = s.view(bw // nwb, nwb, h, n, n) + bias.unsqueeze(0)
+    ref = (torch.softmax(s.view(bw, h, n, n), -1) @ v).transpose(1, 2).reshape(bw, n, h * d)
+    _close(outs[1], ref, rtol=3e-2, atol=3e-2 * ref.abs().max().item())
+    _close(outs[1], outs[0], rtol=3e-2, atol=3e-2 * ref.abs().max().item())
