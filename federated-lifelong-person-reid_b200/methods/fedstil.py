@@ -455,7 +455,7 @@ class Operator(OperatorModule):
         protos, pids, cids = [], [], []
         folded = model.folded_trunk()
         chunk = int(getattr(model, "trunk_batch", 256))         # the frozen trunk is inference-only: batch it wider
-        if folded is not None and hasattr(source_loader, "iterate"):
+        if hasattr(source_loader, "iterate") and (folded is not None or model.device.type == "cuda"):
             batches = source_loader.iterate(chunk, ordered=True)   # sample order is irrelevant here (permuted later)
         else:
             batches = source_loader

@@ -53,9 +53,7 @@ class TcLinear(nn.Linear):
             sh = self._frozen_copy(w)                          # frozen stage: cached bf16 copy
         gs = self._flpr_grad_slot(w) if (self._flpr_grad_slot is not None and w.requires_grad) else None
         x2 = x.reshape(-1, x.shape[-1])
-        y = gops.linear(x2 if x2.dtype == torch.bfloat16 else x2.to(torch.bfloat16), w, sh, gs)
-        if self.bias is not None:
-            y = y + self.bias.to(y.dtype)
+        y = gops.linear(x2 if x2.dtype == torch.bfloat16 else x2.to(torch.bfloat16), w, sh, gs, False, self.bias)
         return y.view(*x.shape[:-1], w.shape[0])
 
     def _frozen_copy(self, w: torch.Tensor) -> torch.Tensor:
@@ -65,14 +63,35 @@ class TcLinear(nn.Linear):
         return hit[2]
 
 
+class FrozenLayerNorm(nn.LayerNorm):
+    """LayerNorm of a FROZEN stage on the bf16 path: under autocast ``layer_norm`` is an fp32 op, which turns the whole
+    residual stream of the inference-only trunk into fp32 (twice the HBM traffic for every add / norm / cast). With
+    frozen parameters and no gradient the bf16 kernel (fp32 statistics inside) is used on bf16 activations instead."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not (x.is_cuda and x.dtype == torch.bfloat16 and not torch.is_grad_enabled()
+                and not self.weight.requires_grad):
+            return super().forward(x)
+        hit = self.__dict__.get("_flpr_wb")
+        w = self.weight
+        if hit is None or hit[0] != (w._version, self.bias._version):
+            hit = self.__dict__["_flpr_wb"] = ((w._version, self.bias._version), w.detach().to(torch.bfloat16),
+                                               self.bias.detach().to(torch.bfloat16))
+        with torch.autocast(device_type="cuda", enabled=False):
+            return F.layer_norm(x, self.normalized_shape, hit[1], hit[2], self.eps)
+
+
 def use_tensor_core_linears(root: nn.Module, shadow=None, grad_slot=None) -> int:
-    """Re-class every plain ``nn.Linear`` under ``root`` to :class:`TcLinear`; returns how many were switched."""
+    """Re-class every plain ``nn.Linear`` under ``root`` to :class:`TcLinear` (and the frozen ``nn.LayerNorm``s to
+    :class:`FrozenLayerNorm`); returns how many Linears were switched."""
     n = 0
     for m in root.modules():
         if type(m) is nn.Linear:
             m.__class__ = TcLinear
             m._flpr_shadow, m._flpr_grad_slot = shadow, grad_slot
             n += 1
+        elif type(m) is nn.LayerNorm and m.elementwise_affine and not m.weight.requires_grad:
+            m.__class__ = FrozenLayerNorm
     return n
 
 

@@ -196,14 +196,15 @@ class _LinearFn(torch.autograd.Function):
     ``AccumulateGrad`` read-modify-write pass."""
 
     @staticmethod
-    def forward(ctx, x, w_master, w_bf16, grad_out, want_stats=False):
+    def forward(ctx, x, w_master, w_bf16, grad_out, want_stats=False, bias=None):
         ctx.save_for_backward(x, w_bf16)
         ctx.w_needs_grad = w_master.requires_grad
         ctx.grad_out = grad_out
         ctx.want_stats = want_stats
+        ctx.has_bias = bias is not None
         ctx.set_materialize_grads(False)        # no zero tensor for the (non-differentiable) statistics output
         if not want_stats:
-            return gemm(x, w_bf16)
+            return gemm(x, w_bf16, bias_n=bias)  # (+ bias[col] in the GEMM epilogue: no separate broadcast-add pass)
         part = col_part_buffer(x.shape[0], w_bf16.shape[0], x.device)
         y = gemm(x, w_bf16, col_part=part)
         ctx.mark_non_differentiable(part)
@@ -212,10 +213,10 @@ class _LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, *_):
         if dy is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         x, w = ctx.saved_tensors
         dy = _bf(dy).contiguous()
-        dx = dw = None
+        dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = gemm(dy, w, b_kmajor=False)                               # [M,N] x [N,K]
         if ctx.w_needs_grad:
@@ -225,11 +226,13 @@ class _LinearFn(torch.autograd.Function):
                 gemm(dy, x, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32, split_k=split, out=ctx.grad_out)
             else:
                 dw = gemm(dy, x, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32, split_k=split)
-        return dx, dw, None, None, None
+        if ctx.has_bias and ctx.needs_input_grad[5]:
+            db = dy.float().sum(0)
+        return dx, dw, None, None, None, db
 
 
 def linear(x: torch.Tensor, w_master: torch.Tensor, w_bf16: Optional[torch.Tensor] = None,
-           grad_out: Optional[torch.Tensor] = None, want_stats: bool = False):
+           grad_out: Optional[torch.Tensor] = None, want_stats: bool = False, bias: Optional[torch.Tensor] = None):
     """Linear / 1x1-conv on flattened NHWC activations. ``w_master`` fp32 ``[out,in]`` receives the gradient
     (directly in ``grad_out`` when given - it must be zero on entry). ``want_stats`` additionally returns the fused
     batch-norm column partials of the output (``(y, part)``)."""
@@ -237,12 +240,14 @@ def linear(x: torch.Tensor, w_master: torch.Tensor, w_bf16: Optional[torch.Tenso
         # TMA needs 16-byte row strides in every operand mode of forward / dgrad / wgrad; a head that is not a
         # multiple of 8 wide (iCaRL grows its classifier by ``n_classes`` at a time, methods/icarl.py) is a tiny GEMM:
         # plain autograd matmul (the fp32 weight gradient lands in the arena slot through AccumulateGrad)
-        return F.linear(_bf(x), w_master.to(torch.bfloat16))
+        return F.linear(_bf(x), w_master.to(torch.bfloat16), None if bias is None else bias.to(torch.bfloat16))
     if w_bf16 is None:
         w_bf16 = w_master.detach().to(torch.bfloat16)
     if grad_out is not None and not x.is_cuda:
         grad_out = None
-    return _LinearFn.apply(_bf(x), w_master, w_bf16, grad_out, want_stats)
+    if bias is not None and (want_stats or bias.dtype != torch.float32 or not bias.is_contiguous()):
+        return _LinearFn.apply(_bf(x), w_master, w_bf16, grad_out, want_stats) + bias.to(torch.bfloat16)
+    return _LinearFn.apply(_bf(x), w_master, w_bf16, grad_out, want_stats, bias)
 
 
 class _Conv3x3Fn(torch.autograd.Function):
