@@ -349,9 +349,11 @@ class ExperimentStage:
                 cs.wait_stream(main)
                 with torch.cuda.stream(cs):
                     comm.set_channel(1)
-                    try:
-                        server.calculate_deferred()
+                    comm.block_cap = int(eng.get("overlap_comm_blocks", 24))   # a small grid: its blocks spin at the
+                    try:                                                        # barriers while a peer is late, and they
+                        server.calculate_deferred()                             # share the SMs with the training kernels
                     finally:
+                        comm.block_cap = 0
                         comm.set_channel(0)
                     ev = torch.cuda.Event()
                     ev.record(cs)

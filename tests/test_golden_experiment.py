@@ -384,8 +384,14 @@ def test_partial_participation_fedavg_matches_reference(tmp_path):
 def test_partial_participation_fedstil_matches_reference(tmp_path):
     """Late first contact receives the server's FedAvg-mean global weight (fedstil.py:1075-1096), the next dispatch is
     a relevance mix over token histories of different lengths. (A few ReLU-branch flips are larger here - the heads are
-    far from converged, gradients are big - hence the wider bound on isolated elements.)"""
-    golden(tmp_path, "fedstil", rounds=3, online=1, max_factor=100)
+    far from converged, gradients are big - hence the wider bound on isolated elements. lr 0.01 for the same reason as
+    the three-round test: with the trained L1 anchor the lr-0.05 momentum trajectory amplifies one flip into a
+    visibly different third round.)"""
+    OVERRIDES.update(lr=0.01)
+    try:
+        golden(tmp_path, "fedstil", rounds=3, online=1, max_factor=100)
+    finally:
+        OVERRIDES.clear()
 
 
 @full
