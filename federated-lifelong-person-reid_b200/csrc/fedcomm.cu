@@ -258,7 +258,12 @@ fed_reduce_bcast_nvls_kernel(const CommCtx ctx, const NvlsReduceArgs a) {
   const size_t lo = per * ctx.rank;
   const size_t hi = (lo + per < a.n4) ? lo + per : a.n4;
   const float inv = s_inv;
-  for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; ok && i < hi; i += stride) {
+  // The barriers pair block b of this rank with block b of every peer, so a block may only consume what the SAME
+  // block index produced on the peers: walk this block's own fold positions (b*T + t + k*stride) and keep the ones
+  // that fall into my slice. The slice is still spread evenly over the grid.
+  const size_t first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t skip = (lo > first) ? (lo - first + stride - 1) / stride : 0;
+  for (size_t i = first + skip * stride; ok && i < hi; i += stride) {
     float4 v = multimem_ld_reduce_add_f4(a.mc_partial + 4 * i);
     v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
     multimem_st_f4(a.mc_dst + 4 * i, v);

@@ -236,10 +236,12 @@ class FedComm:
         b = self.bufs[name]
         return (C.c_void_p * self.world)(*[C.c_void_p(self._addr(b, r, 0)) for r in range(self.world)])
 
-    def _blocks(self, nbytes: int) -> int:
+    def _grid_for(self, nbytes: int) -> int:
         """Grid size of a collective moving ``nbytes`` per rank. Every block takes part in the cross-rank barriers (and
         spins while a peer is late), so small buffers use few blocks; ``self.block_cap`` (set around a collective that
-        runs next to compute kernels) bounds the SM footprint of the spinning."""
+        runs next to compute kernels) bounds the SM footprint of the spinning. Block b of one rank pairs with block b
+        of every peer, so ``nbytes`` (and ``block_cap``) MUST be computed from rank-invariant quantities only - never
+        from how many clients this rank happens to host."""
         want = max(4, (int(nbytes) + (256 << 10) - 1) // (256 << 10))
         cap = self.block_cap or self.comm_blocks
         return int(min(want, cap, self.comm_blocks))
@@ -303,7 +305,7 @@ class FedComm:
             wv = (C.c_float * len(clients))(*[float(x) for x in weights]) if weights is not None else None
             rc = self._lib.flpr_comm_reduce_bcast(self.rank, self.world, self._flag_pages, self.timeout_s, len(clients),
                                                   srcp, cntp, wv, self._rank_ptrs(dst), bs.n,
-                                                  self._blocks(bs.n * 4 * max(len(clients), 1) // max(self.world, 1)),
+                                                  self._grid_for(bs.n * 4 * max(len(clients), 1) // max(self.world, 1)),
                                                   native.stream(self.device))
             native.check(rc, "flpr_comm_reduce_bcast")
             native.count_launch()
@@ -338,7 +340,7 @@ class FedComm:
         rc = self._lib.flpr_comm_reduce_bcast_nvls(
             self.rank, self.world, self._flag_pages, self.timeout_s, len(mine), srcp, cntp, wv, len(clients), cnt_all,
             w_total, C.c_void_p(self._addr(bp, self.rank, 0)), C.c_void_p(self._mc_base + bp.offset),
-            C.c_void_p(self._mc_base + bd.offset), bs.n, self._blocks(bs.n * 4 * max(len(mine), 1)),
+            C.c_void_p(self._mc_base + bd.offset), bs.n, self._grid_for(bs.n * 4 * len(clients) // self.world),
             native.stream(self.device))
         native.check(rc, "flpr_comm_reduce_bcast_nvls")
         native.count_launch()
@@ -382,7 +384,7 @@ class FedComm:
                 rc = self._lib.flpr_comm_mix(self.rank, self.world, self._flag_pages, self.timeout_s, len(clients),
                                              len(idx), srcp, wv, native.ptr(wd), arr(dst_g), arr(dst_theta),
                                              arr(dst_bf16), bs.n,
-                                             self._blocks(bs.n * 4 * len(clients)), native.stream(self.device))
+                                             self._grid_for(bs.n * 4 * len(clients)), native.stream(self.device))
                 native.check(rc, "flpr_comm_mix")
                 native.count_launch()
                 self.poll_errors()
@@ -408,7 +410,7 @@ class FedComm:
                                                   self._client_ptrs(fisher, clients), self._client_ptrs(param, clients),
                                                   self._rank_ptrs(dst_f), self._rank_ptrs(dst_fp),
                                                   self._rank_ptrs(dst_fpp), bf.n,
-                                                  self._blocks(2 * bf.n * 4 * max(len(clients), 1) // max(self.world, 1)),
+                                                  self._grid_for(2 * bf.n * 4 * max(len(clients), 1) // max(self.world, 1)),
                                                   native.stream(self.device))
             native.check(rc, "flpr_comm_curv_moments")
             native.count_launch()
@@ -429,7 +431,7 @@ class FedComm:
         if self.mode == "p2p":
             rc = self._lib.flpr_comm_gather_strided(self.rank, self.world, self._flag_pages, self.timeout_s,
                                                     len(clients), self._client_ptrs(src, clients), native.ptr(out),
-                                                    bs.n, self._blocks(bs.n * 4 * len(clients)),
+                                                    bs.n, self._grid_for(bs.n * 4 * len(clients)),
                                                     native.stream(self.device))
             native.check(rc, "flpr_comm_gather_strided")
             native.count_launch()
@@ -447,7 +449,7 @@ class FedComm:
             addr = self._addr(bs, self.owner(client), self.slot(client))
             rc = self._lib.flpr_comm_pull_copy(self.rank, self.world, self._flag_pages, self.timeout_s,
                                                C.c_void_p(addr), native.ptr(dst), native.ptr(dst_bf16), bs.n,
-                                               self._blocks(bs.n * 4), native.stream(self.device))
+                                               self._grid_for(bs.n * 4), native.stream(self.device))
             native.check(rc, "flpr_comm_pull_copy")
             native.count_launch()
             self.poll_errors()

@@ -28,7 +28,7 @@ if what == "head":
     proto = (torch.randn(64, 1024, 16, 8, device=dev) * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, 8000, (64,), device=dev)
     model.train()
-    for _ in range(3):
+    for _ in range(int(os.environ.get('NSTEPS', '3'))):
         opt.zero_grad()
         with model.autocast():
             score, feat = model.forward_head(proto)
