@@ -1,6 +1,7 @@
 """Evaluation entry points (``tools/evaluate.py``): CMC / mAP on device."""
 from ..ops.rank import (evaluate, evaluate_sharded, rank_metrics, rank_metrics_reference,  # noqa: F401
                         similarity)
+from .sharded import ShardedRanker  # noqa: F401
 
 
 def calculate_similarity_distance(query_feature, gallery_features):

@@ -31,6 +31,10 @@ ENGINE_DEFAULTS: Dict[str, Any] = {
     "overlap_aggregate": True,        # methods with a deferred aggregation part (FedSTIL's 125 MB FedAvg mean into the
                                       # server replica) run it on a communication stream / second flag channel,
                                       # concurrently with the next round's mix and local training
+    "overlap_comm_blocks": 24,        # grid of that overlapped collective (its blocks spin at the cross-rank barriers
+                                      # next to the training kernels)
+    "sharded_validation": False,      # world > 1: all ranks rank every client's gallery in 1/world slices
+                                      # (evaluation/sharded.py) instead of each rank validating its own clients alone
     "client_threads": True,           # `parallel` clients per device train concurrently on their own CUDA streams
     "resume": False,                  # continue from {checkpoints_dir}/{exp}/_resume/rank{r}.ckpt when present
     "resume_interval": 0,             # write the resume manifest every N rounds (0 = never)

@@ -220,8 +220,7 @@ class ExperimentStage:
         try:
             if exp_config["engine_opts"].get("val_at_round0", True) and not (
                     exp_config["engine_opts"].get("resume") and resume.available(store, self.rank)):
-                for client in clients:                                  # initial validation (experiment.py:163-173)
-                    self._process_val(client, log, 0, self.container)
+                self._validate_all(clients, names, exp_config, log, 0)   # initial validation (experiment.py:163-173)
             comm_rounds = int(exp_config["exp_opts"]["comm_rounds"])
             eng = exp_config["engine_opts"]
             first_round = 1
@@ -315,8 +314,7 @@ class ExperimentStage:
         # ---- validation -------------------------------------------------------------------------------------------
         if curr_round % val_interval == 0:
             with timer("validate"):
-                for client in clients:
-                    self._process_val(client, log, curr_round, self.container)
+                self._validate_all(clients, names, exp_config, log, curr_round)
 
         # ---- clients -> server ------------------------------------------------------------------------------------
         self._join_deferred_aggregate()              # last round's deferred mean has read the upload slots
@@ -363,6 +361,32 @@ class ExperimentStage:
         if comm is not None:
             comm.poll_errors()            # a missed barrier surfaces in the round it happened, not at the very end
         log.flush()
+
+    def _validate_all(self, clients, names, exp_config, log, curr_round: int) -> None:
+        """Validation of every client on every task (``experiment.py:163-173, :218-229``). Default: each rank validates
+        the clients it hosts. ``engine_opts.sharded_validation`` (world > 1): all ranks walk the global (client, task)
+        list together and rank every gallery in ``1 / world`` slices (``evaluation/sharded.py``)."""
+        eng = exp_config["engine_opts"]
+        if not (eng.get("sharded_validation", False) and self.world > 1):
+            for client in clients:
+                self._process_val(client, log, curr_round, self.container)
+            return
+        from ..evaluation.sharded import ShardedRanker
+        ranker = getattr(self, "_ranker_obj", None)
+        if ranker is None:
+            ranker = self._ranker_obj = ShardedRanker(self.device)
+        local = {c.client_name: c for c in clients}
+        for cid, cfg in enumerate(exp_config["clients"]):
+            client = local.get(cfg["client_name"])
+            if client is not None:
+                client._ranker = ranker
+                try:
+                    self._process_val(client, log, curr_round, self.container)
+                finally:
+                    client._ranker = None
+            else:
+                for _ in range(len(cfg["tasks"])):                   # one collective per task of that client
+                    ranker.participate(cid % self.world)
 
     def _comm_stream(self):
         st = getattr(self, "_comm_stream_obj", None)

@@ -448,7 +448,9 @@ class ClientModule(_Actor):
         gallery = self._features(gallery_loader)
         query = self._features(query_loader)
         self.test_cnt += len(gallery["features"]) + len(query["features"])
-        cmc, mAP = evaluate(query["features"], query["labels"], gallery["features"], gallery["labels"])
+        # ``_ranker``: set by the experiment loop for ``engine_opts.sharded_validation`` (collective, gallery-sharded)
+        rank_fn = getattr(self, "_ranker", None) or evaluate
+        cmc, mAP = rank_fn(query["features"], query["labels"], gallery["features"], gallery["labels"])
         allf = torch.cat([query["features"], gallery["features"]], dim=0)
         avg_rep = allf.sum(dim=0) / max(len(allf), 1)
         self.logger.info_validation(task_name, len(query["features"]), len(gallery["features"]), cmc, mAP)

@@ -122,6 +122,19 @@ def test_gallery_sharded_evaluation_matches_full_gallery(world):
     assert "DIST_EVAL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("method,world", [("fedavg", 2), ("fedweit", 3)])
+def test_sharded_validation_logs_the_same_metrics(tmp_path, method, world):
+    """``engine_opts.sharded_validation``: all ranks rank every client's gallery in ``1 / world`` slices
+    (``evaluation/sharded.py``); CMC / mAP of every client, round and task equal the per-rank validation's (fedweit: the
+    per-task checkpoint swap around ``validate`` happens on the owner only)."""
+    script = os.path.join(os.path.dirname(__file__), "dist_sharded_val_check.py")
+    env = dict(os.environ, FLPR_TMP=str(tmp_path), OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
+                        "--nproc-per-node", str(world), script, method], env=env, capture_output=True, text=True,
+                       timeout=900)
+    assert "DIST_SHARDED_VAL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_cli_synthetic(tmp_path):
     import yaml
     common = tiny_common(str(tmp_path))
