@@ -22,6 +22,7 @@ import sys
 import time
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+_T_IMPORT = time.perf_counter()          # ~process start: bench.py imports this module first thing in the arm
 REF = os.path.join(HERE, "_ref")
 
 
@@ -230,23 +231,41 @@ def run_reference_arm(a, build_config, cleanup_payloads, metric, ClockSampler, b
         except ValueError:                              # not the main thread
             pass
 
+    # Own time budget (FLPR_REF_BUDGET_S, default 780 s from process start): the reference needs ~50 s per round, the
+    # driver's per-run limit ended round 1's scaling runs (25 rounds) without a line. Past the budget - and with at
+    # least two timed rounds measured - the arm stops and reports what it has, flagged ``partial`` like a SIGTERM.
+    budget = float(os.environ.get("FLPR_REF_BUDGET_S", "780"))
+    t_start = _T_IMPORT
+
+    def over_budget() -> bool:
+        return budget > 0 and time.perf_counter() - t_start > budget
+
     for _ in range(a.warmup):
         state["r"] += 1
         stage._process_one_round(state["r"], server, clients, exp, log)
         sync()
         state["stamps"].append(time.perf_counter())
         cleanup_payloads(common["checkpoints_dir"])
+        if over_budget() and len(state["stamps"]) >= 3:
+            break
     if sampler:
         sampler.start()
     sync()
-    state["t0"] = time.perf_counter()
-    for _ in range(a.steps):
-        state["r"] += 1
-        stage._process_one_round(state["r"], server, clients, exp, log)
-        sync()
-        state["stamps"].append(time.perf_counter())
+    cut = over_budget() and len(state["stamps"]) >= 3
+    if not cut:
+        state["t0"] = time.perf_counter()
+        for i in range(a.steps):
+            state["r"] += 1
+            stage._process_one_round(state["r"], server, clients, exp, log)
+            sync()
+            state["stamps"].append(time.perf_counter())
+            if over_budget() and i + 1 >= 2 and i + 1 < a.steps:
+                cut = True
+                break
     state["done"] = True
-    out = result(False)
+    out = result(cut)
+    if cut:
+        out["partial_reason"] = f"own time budget of {budget:.0f} s (FLPR_REF_BUDGET_S)"
     cleanup_payloads(common["checkpoints_dir"])
     if world > 1:
         import torch.distributed as dist
