@@ -243,6 +243,29 @@ def test_fedstil_relevance_double_normalisation():
     assert torch.allclose(w2, torch.tensor([0.5, 0.5]))       # N=2 gives exactly 0.5/0.5
 
 
+def test_collective_grid_depends_on_rank_invariant_sizes_only():
+    """Block b of a rank pairs with block b of every peer (per-block flag epochs), so every rank must launch the same
+    grid: ``_grid_for`` sees byte counts only, is monotonic, bounded by ``comm_blocks`` and by ``block_cap``; and no
+    launch site may derive its argument from the clients hosted on the calling rank (the round-2 NVLS desync)."""
+    import inspect
+    import re
+    from flpr_b200.parallel import comm as C
+
+    class Fake:
+        comm_blocks, block_cap = 296, 0
+    f = Fake()
+    g = lambda n: C.FedComm._grid_for(f, n)                                       # noqa: E731
+    assert g(0) == 4 and g(32 << 10) == 4 and g(1 << 20) == 4 and g(125 << 20) == 296
+    assert all(g(a) <= g(b) for a, b in zip(range(0, 1 << 28, 1 << 20), range(1 << 20, (1 << 28) + 1, 1 << 20)))
+    f.block_cap = 24
+    assert g(125 << 20) == 24 and g(32 << 10) == 4
+    src = inspect.getsource(C.FedComm)
+    args = re.findall(r"_grid_for\(([^\n]*)", src)
+    assert len(args) >= 6
+    for a in args:
+        assert "mine" not in a and "local" not in a and "idx" not in a and "self.rank" not in a, a
+
+
 def test_comm_local_mode_semantics():
     from flpr_b200.parallel.comm import FedComm
     comm = FedComm("cpu", 3, arena_bytes=1 << 20)

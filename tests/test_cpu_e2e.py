@@ -135,6 +135,16 @@ def test_sharded_validation_logs_the_same_metrics(tmp_path, method, world):
     assert "DIST_SHARDED_VAL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_comm_soak_script_in_plumbing_mode():
+    """``scripts/comm_soak.py`` (randomised arrival / participation / sizes / channels; meant for >= 2 GPUs) stays
+    runnable: three gloo ranks, every result checked against the host-side reference."""
+    script = os.path.join(os.path.dirname(os.path.dirname(__file__)), "scripts", "comm_soak.py")
+    env = dict(os.environ, FLPR_FORCE_CPU="1", OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
+                        "--nproc-per-node", "3", script, "40"], env=env, capture_output=True, text=True, timeout=600)
+    assert "COMM_SOAK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_cli_synthetic(tmp_path):
     import yaml
     common = tiny_common(str(tmp_path))
