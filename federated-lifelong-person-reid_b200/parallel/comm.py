@@ -296,8 +296,13 @@ class FedComm:
         bs, bd = self.bufs[src], self.bufs[dst]
         assert bs.n == bd.n and bs.dtype == torch.float32 and bd.dtype == torch.float32
         if self.mode == "p2p" and self._mc_base and self.nvls and bs.n * 4 > self.nvls_min_bytes:
-            mine = [c for c in clients if self.owner(c) == self.rank]
-            if len(mine) <= self._lib.flpr_comm_max_local():
+            # the kernel choice must be the same on every rank: decide on the largest number of participants hosted
+            # by ANY rank, not on how many this rank hosts
+            per_rank = [0] * self.world
+            for c in clients:
+                per_rank[self.owner(c)] += 1
+            if max(per_rank) <= self._lib.flpr_comm_max_local():
+                mine = [c for c in clients if self.owner(c) == self.rank]
                 return self._reduce_bcast_nvls(src, dst, clients, mine, cnt, weights)
         if self.mode == "p2p":
             srcp = self._client_ptrs(src, clients)

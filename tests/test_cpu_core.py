@@ -264,6 +264,8 @@ def test_collective_grid_depends_on_rank_invariant_sizes_only():
     assert len(args) >= 6
     for a in args:
         assert "mine" not in a and "local" not in a and "idx" not in a and "self.rank" not in a, a
+    # ... and the NVLS / two-shot kernel choice is taken on the per-rank maximum of hosted participants
+    assert "max(per_rank) <= self._lib.flpr_comm_max_local()" in src
 
 
 def test_comm_local_mode_semantics():
