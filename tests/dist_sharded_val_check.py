@@ -25,7 +25,10 @@ def run(tag: str, sharded: bool, method: str):
 
 
 def main():
+    import torch.distributed as dist
     method = sys.argv[1] if len(sys.argv) > 1 else "fedavg"
+    dist.init_process_group("gloo")               # ONE group for both runs (the stages then neither create nor destroy
+                                                  # it: re-initialising on the same store races on the old mesh keys)
     plain, c0, rank = run("plain", False, method)
     shard, c1, _ = run("sharded", True, method)
     ok = c0 == 0 and c1 == 3 * 2 * 3            # 3 clients x 2 tasks x (round 0 + 2 rounds), on every rank
@@ -44,6 +47,8 @@ def main():
         ok = ok and not bad and vals >= 3 * 3 * 2 * 5 and len(plain) == 3
         print("DIST_SHARDED_VAL", "OK" if ok else "FAILED", f"metrics={vals} collectives={c1}", json.dumps(bad[:5]),
               flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":
