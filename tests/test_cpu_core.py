@@ -411,3 +411,52 @@ def test_utility_helpers():
         assert m is net
     assert misc.module_paths(net.eval(), torch.randn(2, 3, 3, 3)) == ["0", "1", "2", "3"]
     assert misc.params_state_size({"a": torch.zeros(3, 2), "b": [1, 2.0]}) == 8
+
+
+def test_token_file_writer_latest_wins_and_appends(tmp_path, monkeypatch):
+    """FedSTIL's growing ``{server}_tokens.ckpt``: requests that arrive while a write is in flight replace the waiting
+    one (no backlog), the final file holds the newest history, and every token is copied to the host exactly once."""
+    import threading
+    import time
+    from flpr_b200.methods.fedstil import TokenFileWriter
+    w = TokenFileWriter(torch.device("cpu"))
+    path = str(tmp_path / "srv" / "server_tokens.ckpt")
+    gate = threading.Event()
+    real_save = torch.save
+
+    def slow_save(obj, f, *a, **k):
+        gate.wait(5.0)
+        return real_save(obj, f, *a, **k)
+    monkeypatch.setattr(torch, "save", slow_save)
+    mem = {"a": [], "b": []}
+    futs = []
+    for r in range(6):
+        for k in mem:
+            mem[k].append(torch.full((4,), float(10 * r + (k == "b"))))
+        f = w.submit({k: list(v) for k, v in mem.items()}, None, path)
+        if f is not None:
+            futs.append(f)
+        time.sleep(0.01)
+    assert len(futs) == 1 and w.replaced >= 4           # one drain task; the waiting request was replaced 4+ times
+    gate.set()
+    futs[0].result(timeout=30)
+    monkeypatch.setattr(torch, "save", real_save)
+    got = torch.load(path)
+    assert [float(t[0]) for t in got["a"]] == [0.0, 10.0, 20.0, 30.0, 40.0, 50.0]
+    assert [float(t[0]) for t in got["b"]] == [1.0, 11.0, 21.0, 31.0, 41.0, 51.0]
+    assert w.writes <= 3 and w.copied == 12
+    # appended history: only the new tokens are copied; a replaced history is detected by identity
+    mem["a"].append(torch.full((4,), 60.0))
+    w.submit({k: list(v) for k, v in mem.items()}, None, path).result(timeout=30)
+    assert w.copied == 13
+    mem = {"a": [torch.zeros(4), torch.ones(4)]}
+    w.submit({k: list(v) for k, v in mem.items()}, None, path).result(timeout=30)
+    got = torch.load(path)
+    assert list(got) == ["a"] and [float(t[0]) for t in got["a"]] == [0.0, 1.0] and w.copied == 15
+    # a failing write does not wedge the writer
+    monkeypatch.setattr(torch, "save", lambda *a, **k: (_ for _ in ()).throw(OSError("disk full")))
+    f = w.submit({"a": list(mem["a"])}, None, path)
+    with pytest.raises(OSError):
+        f.result(timeout=30)
+    monkeypatch.setattr(torch, "save", real_save)
+    w.submit({"a": list(mem["a"])}, None, path).result(timeout=30)
