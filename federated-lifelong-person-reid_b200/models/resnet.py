@@ -215,8 +215,9 @@ class FastResNetHead:
 
     Shares the ``nn.Parameter`` objects of the wrapped model (weights must be in ``channels_last`` memory format so
     that the OHWI view is contiguous) and an optional bf16 shadow provider ``shadow(param) -> bf16 tensor`` kept in
-    sync by the fused optimizer. Falls back to cuDNN for the shapes the implicit-GEMM kernel does not cover
-    (stride-2 convolutions), never silently to a different numerics path for the covered ones.
+    sync by the fused optimizer. Stride-2 convolutions that need gradients run on the same kernels
+    (``ops.gemm.conv_stride2``); only shapes outside the implicit-GEMM tiling constraints (feature maps whose width is
+    not a power of two <= 128, channels not a multiple of 64) use the cuDNN fallback.
     """
 
     def __init__(self, model: ResNetReID, shadow=None, grad_slot=None):
@@ -277,7 +278,13 @@ class FastResNetHead:
             part = gops.col_part_buffer(n * ho * wo, w.shape[0], x.device) if want_stats else None
             y = gops.conv_nhwc(x, wb, padding=k // 2, stride=s, col_part=part)
             return (y, part) if want_stats else y
-        # library fallback (strided convs that need a gradient)
+        if s == 2 and k in (1, 3) and gops.conv_s2_supported(h, wd, c, w.shape[0], k):
+            # strided conv that needs a gradient (``last_stride: 2``, or a head cut above layer4): forward with TMA
+            # element strides, dgrad / wgrad through the stride-1 kernels on the zero-stuffed output gradient
+            wv = self._ohwi(w)
+            return gops.conv_stride2(x, wv, self._ohwi(sh) if sh is not None else None,
+                                     self._ohwi(gs) if gs is not None else None, want_stats)
+        # library fallback (shapes outside the implicit-GEMM tiling constraints)
         y = F.conv2d(x.permute(0, 3, 1, 2), (sh if sh is not None else w.to(torch.bfloat16)) if not w.requires_grad
                      else w.to(torch.bfloat16), stride=s, padding=k // 2)
         y = y.permute(0, 2, 3, 1).contiguous()

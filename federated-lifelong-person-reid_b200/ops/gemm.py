@@ -321,6 +321,102 @@ def conv3x3(x: torch.Tensor, w_master: torch.Tensor, w_bf16: Optional[torch.Tens
     return _Conv3x3Fn.apply(_bf(x), w_master, w_bf16, grad_out, want_stats)
 
 
+# ------------------------------------------------------------------------------------------------- stride-2 convs
+def zero_stuff2(t: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """``[N,Ho,Wo,C]`` -> ``[N,h,w,C]`` with ``t`` at the even positions and zeros elsewhere (the gradient of taking
+    every second row / column of an ``h x w`` map)."""
+    n, ho, wo, c = t.shape
+    assert 2 * (ho - 1) < h and 2 * (wo - 1) < w, "stride-2 map does not fit its stride-1 parent"
+    out = t.new_zeros(n, h, w, c)
+    out[:, 0:2 * ho:2, 0:2 * wo:2] = t
+    return out
+
+
+def conv_s2_supported(h: int, w: int, cin: int, cout: int, k: int) -> bool:
+    """Shapes for which forward, data gradient and weight gradient of a ``k x k`` / stride-2 / pad ``k//2``
+    convolution all run on the tcgen05 kernels (:class:`_ConvStride2Fn`)."""
+    if k == 1:
+        return cin % 8 == 0 and cout % 8 == 0 and conv_supported(h, w, cin, 1, 2, 0)
+    if k != 3:
+        return False
+    fwd = conv_supported(h, w, cin, 3, 2)
+    dgrad = cout % 64 == 0 and cin % 64 == 0 and conv_supported(h, w, cout, 3, 1)     # over the stride-1 parent map
+    wgrad = cout % 8 == 0 and w <= 64 and 64 % w == 0 and ((h * w) % 64 == 0 or 64 % (h * w) == 0)
+    return fwd and dgrad and wgrad
+
+
+class _ConvStride2Fn(torch.autograd.Function):
+    """``k x k`` (k = 1 or 3) / stride 2 / pad ``k//2`` NHWC convolution with every pass on the tcgen05 kernels.
+
+    Forward: the implicit-GEMM kernel walks the input with TMA element strides. Backward: a stride-2 convolution is
+    its stride-1 parent sampled at the even output positions (``y[i] = z[2i]``), so ``dL/dz`` is ``dy`` zero-stuffed
+    to the parent resolution and the validated stride-1 dgrad / wgrad kernels apply unchanged (3x3; the stuffed
+    zeros cost 4x the tensor-core work of one layer per ResNet stage - the only strided 3x3 a ResNet stage has).
+    1x1: ``dx`` = zero-stuffed ``dy @ W`` and ``dW = dy^T @ x[:, ::2, ::2]`` - two plain GEMMs at the output
+    resolution. Reference site: ``models/resnet.py:182`` (``last_stride: 2``) / any head cut above ``layer4``."""
+
+    @staticmethod
+    def forward(ctx, x, w_master, w_bf16, grad_out, want_stats=False):
+        ctx.save_for_backward(x, w_bf16)
+        ctx.w_needs_grad = w_master.requires_grad
+        ctx.grad_out = grad_out
+        ctx.set_materialize_grads(False)
+        k = w_bf16.shape[1]
+        if not want_stats:
+            return conv_nhwc(x, w_bf16, padding=k // 2, stride=2)
+        n, h, wd, _ = x.shape
+        ho, wo = (h + 2 * (k // 2) - k) // 2 + 1, (wd + 2 * (k // 2) - k) // 2 + 1
+        part = col_part_buffer(n * ho * wo, w_bf16.shape[0], x.device)
+        y = conv_nhwc(x, w_bf16, padding=k // 2, stride=2, col_part=part)
+        ctx.mark_non_differentiable(part)
+        return y, part
+
+    @staticmethod
+    def backward(ctx, dy, *_):
+        if dy is None:
+            return None, None, None, None, None
+        x, w = ctx.saved_tensors
+        dy = _bf(dy).contiguous()
+        n, h, wd, cin = x.shape
+        cout, k = w.shape[0], w.shape[1]
+        dx = dw = None
+        if k == 3:
+            dz = zero_stuff2(dy, h, wd)                           # dL/d(stride-1 parent output)
+            if ctx.needs_input_grad[0]:
+                dx = conv_dgrad_nhwc(dz, w, padding=1)
+            if ctx.w_needs_grad:
+                if ctx.grad_out is not None:
+                    conv3x3_wgrad(x, dz, out=ctx.grad_out)
+                else:
+                    dw = conv3x3_wgrad(x, dz)
+            return dx, dw, None, None, None
+        _, ho, wo, _ = dy.shape
+        dy2 = dy.reshape(-1, cout)
+        if ctx.needs_input_grad[0]:
+            dxs = gemm(dy2, w.reshape(cout, cin), b_kmajor=False)             # [N*Ho*Wo, Cin]
+            dx = zero_stuff2(dxs.view(n, ho, wo, cin), h, wd)
+        if ctx.w_needs_grad:
+            xs = x[:, ::2, ::2].contiguous().reshape(-1, cin)                 # the pixels the 1x1 / 2 conv reads
+            split = _auto_split(cout, cin, xs.shape[0])
+            if ctx.grad_out is not None:
+                gemm(dy2, xs, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32, split_k=split,
+                     out=ctx.grad_out.reshape(cout, cin))
+            else:
+                dw = gemm(dy2, xs, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32,
+                          split_k=split).view(cout, 1, 1, cin)
+        return dx, dw, None, None, None
+
+
+def conv_stride2(x: torch.Tensor, w_master: torch.Tensor, w_bf16: Optional[torch.Tensor] = None,
+                 grad_out: Optional[torch.Tensor] = None, want_stats: bool = False):
+    """``x``: ``[N,H,W,Cin]`` bf16, ``w_master``: ``[Cout,k,k,Cin]`` (k = 1 or 3). See :class:`_ConvStride2Fn`."""
+    if w_bf16 is None:
+        w_bf16 = w_master.detach().to(torch.bfloat16)
+    if grad_out is not None and not x.is_cuda:
+        grad_out = None
+    return _ConvStride2Fn.apply(_bf(x), w_master, w_bf16, grad_out, want_stats)
+
+
 # ------------------------------------------------------------------------------------------------- ResNet stem
 def stem_weight_s2d(w: torch.Tensor) -> torch.Tensor:
     """7x7 / stride-2 stem weight ``[Cout,3,7,7]`` -> ``[Cout, 4, 64]``: the equivalent 4x4 / stride-1 convolution over
