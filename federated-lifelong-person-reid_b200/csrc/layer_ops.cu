@@ -1,0 +1,348 @@
+// flpr layer-level fused element-wise kernels (memory-bound passes that used to be chains of ATen ops):
+//
+//   wcompose_fwd / wcompose_bwd   decomposed-weight composition of FedWeIT (methods/fedweit.py:122-136 of the reference)
+//                                 and fedstil-atten (methods/fedstil_atten.py:88-96):
+//                                     theta[e] = prune(aw[e]) + sum_k atten[k] * stack[e, k] + prune(mask[row(e)]) * sw[e]
+//                                 one pass writes theta in fp32 (autograd master) and bf16 (tensor-core operand); the
+//                                 backward pass produces d aw (pruned pass-through), d mask (one value per output unit)
+//                                 and d atten (deterministic two-stage reduction) from d theta in one sweep.
+//   ln_rows                       LayerNorm over the channel dim of bf16 token rows, one warp per token, fp32 statistics;
+//                                 optionally the destination is the (cyclically shifted) window layout of a Swin block
+//                                 (models/swin_transformer.py:358-380: norm1 -> roll -> window_partition in one pass).
+//   window_merge_add              window_reverse -> roll back -> + shortcut (models/swin_transformer.py:383-391) in one pass.
+//   gelu_rows                     exact (erf) GELU over bf16 rows (models/swin_transformer.py:118-140, frozen stages).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace flpr {
+
+constexpr int WC_MAXK = 16;
+
+__device__ __forceinline__ float prune_val(float v, float thr, int prune) {
+  return (prune && !(fabsf(v) > thr)) ? 0.f : v;
+}
+
+// ------------------------------------------------------------------------------------------------- compose forward
+__global__ void __launch_bounds__(256) wcompose_fwd_kernel(const float* __restrict__ aw, const float* __restrict__ stack,
+                                                           const float* __restrict__ atten, int kb, int ks,
+                                                           const float* __restrict__ sw, const float* __restrict__ mask,
+                                                           long long row_len, float thr_aw, float thr_mask, int prune,
+                                                           float* __restrict__ out_f32,
+                                                           __nv_bfloat16* __restrict__ out_bf16, long long n) {
+  __shared__ float s_att[WC_MAXK];
+  if (threadIdx.x < kb) s_att[threadIdx.x] = atten[threadIdx.x];
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+    float acc = prune_val(aw[e], thr_aw, prune);
+    if (kb > 0) {
+      const float* sp = stack + e * ks;
+      float kacc = 0.f;
+      for (int k = 0; k < kb; ++k) kacc = fmaf(s_att[k], sp[k], kacc);
+      acc += kacc;
+    }
+    if (sw != nullptr) acc = fmaf(prune_val(mask[e / row_len], thr_mask, prune), sw[e], acc);
+    if (out_f32 != nullptr) out_f32[e] = acc;
+    if (out_bf16 != nullptr) out_bf16[e] = __float2bfloat16(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- compose backward
+// One block per row r (FedWeIT: one output unit; fedstil-atten: an arbitrary chunk): d_aw element-wise, the row's
+// partial sums of d theta * stack[., k] into part_att[r, k] and of d theta * sw into d_mask[r].
+__global__ void __launch_bounds__(256) wcompose_bwd_kernel(const float* __restrict__ dth, const float* __restrict__ aw,
+                                                           const float* __restrict__ stack, int kb, int ks,
+                                                           const float* __restrict__ sw, const float* __restrict__ mask,
+                                                           long long row_len, float thr_aw, float thr_mask, int prune,
+                                                           float* __restrict__ d_aw, float* __restrict__ part_att,
+                                                           float* __restrict__ d_mask, long long n) {
+  __shared__ float sh[8][WC_MAXK + 1];
+  const long long r = blockIdx.x;
+  const long long beg = r * row_len;
+  long long end = beg + row_len;
+  if (end > n) end = n;
+  float acc[WC_MAXK];
+#pragma unroll
+  for (int k = 0; k < WC_MAXK; ++k) acc[k] = 0.f;
+  float am = 0.f;
+  for (long long e = beg + threadIdx.x; e < end; e += blockDim.x) {
+    const float g = dth[e];
+    if (d_aw != nullptr) d_aw[e] = (prune && !(fabsf(aw[e]) > thr_aw)) ? 0.f : g;
+    if (kb > 0) {
+      const float* sp = stack + e * ks;
+#pragma unroll
+      for (int k = 0; k < WC_MAXK; ++k)
+        if (k < kb) acc[k] = fmaf(g, sp[k], acc[k]);
+    }
+    if (sw != nullptr) am = fmaf(g, sw[e], am);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < WC_MAXK; ++k) {
+    const float v = warp_sum(acc[k]);
+    if (l == 0) sh[w][k] = v;
+  }
+  {
+    const float v = warp_sum(am);
+    if (l == 0) sh[w][WC_MAXK] = v;
+  }
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  if (threadIdx.x <= WC_MAXK) {
+    float t = 0.f;
+    for (int i = 0; i < nw; ++i) t += sh[i][threadIdx.x];
+    if (threadIdx.x < kb && part_att != nullptr) part_att[r * kb + threadIdx.x] = t;
+    if (threadIdx.x == WC_MAXK && d_mask != nullptr) d_mask[r] = (prune && !(fabsf(mask[r]) > thr_mask)) ? 0.f : t;
+  }
+}
+
+// d_att[k] = sum_r part[r, k]   (one block per k, fixed summation order -> deterministic)
+__global__ void __launch_bounds__(256) wcompose_colsum_kernel(const float* __restrict__ part, long long rows, int kb,
+                                                              float* __restrict__ d_att) {
+  __shared__ float sh[8];
+  const int k = blockIdx.x;
+  float t = 0.f;
+  for (long long r = threadIdx.x; r < rows; r += blockDim.x) t += part[r * kb + k];
+  t = warp_sum(t);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) s += sh[i];
+    d_att[k] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- Swin token kernels
+// window layout row (b, wh, ww, ph, pw)  <->  image row (b, (wh*ws+ph + shift) % H, (ww*ws+pw + shift) % W)
+__device__ __forceinline__ long long window_row_to_image_row(long long r, int H, int W, int ws, int shift) {
+  const int ws2 = ws * ws, nWw = W / ws, nWh = H / ws;
+  const long long win = r / ws2;
+  const int pos = (int)(r - win * ws2);
+  const int ph = pos / ws, pw = pos - ph * ws;
+  const int wwi = (int)(win % nWw);
+  const long long t = win / nWw;
+  const int whi = (int)(t % nWh);
+  const long long b = t / nWh;
+  const int hh = (whi * ws + ph + shift) % H, ww = (wwi * ws + pw + shift) % W;
+  return (b * H + hh) * W + ww;
+}
+
+__device__ __forceinline__ long long image_row_to_window_row(long long r, int H, int W, int ws, int shift) {
+  const int ws2 = ws * ws, nWw = W / ws, nWh = H / ws;
+  const long long b = r / ((long long)H * W);
+  const int rem = (int)(r - b * (long long)H * W);
+  const int hh = rem / W, ww = rem - hh * W;
+  const int h2 = (hh - shift + H) % H, w2 = (ww - shift + W) % W;
+  const long long win = (b * nWh + h2 / ws) * nWw + w2 / ws;
+  return win * ws2 + (h2 % ws) * ws + (w2 % ws);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 p = __bfloat1622float2(h[t]);
+    f[2 * t] = p.x;
+    f[2 * t + 1] = p.y;
+  }
+}
+
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(f[2 * t], f[2 * t + 1]);
+  return u;
+}
+
+// One warp per destination row; VPL = 16-byte vectors per lane (C <= 256 * VPL). window != 0: the destination rows are
+// in window layout and row r normalises the image row window_row_to_image_row(r).
+template <int VPL>
+__global__ void __launch_bounds__(256) ln_rows_kernel(const __nv_bfloat16* __restrict__ x,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      __nv_bfloat16* __restrict__ out, long long rows, int C, float eps,
+                                                      int window, int H, int W, int ws, int shift) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  if (r >= rows) return;
+  const long long src = window ? window_row_to_image_row(r, H, W, ws, shift) : r;
+  const uint4* xp = reinterpret_cast<const uint4*>(x + src * C);
+  const int nvec = C >> 3;
+  float v[VPL][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const uint4 u = xp[idx];
+      unpack8(u, v[i]);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) s += v[i][t];
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[i][t] = 0.f;
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    if (lane + 32 * i < nvec) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float d = v[i][t] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  uint4* op = reinterpret_cast<uint4*>(out + r * C);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * idx], g1 = reinterpret_cast<const float4*>(gamma)[2 * idx + 1];
+      const float4 b0 = reinterpret_cast<const float4*>(beta)[2 * idx], b1 = reinterpret_cast<const float4*>(beta)[2 * idx + 1];
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float y[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) y[t] = fmaf((v[i][t] - mean) * rstd, gg[t], bb[t]);
+      op[idx] = pack8(y);
+    }
+  }
+}
+
+// out[image row r] = shortcut[r] + win[image_row_to_window_row(r)]   (8 channels per thread)
+__global__ void __launch_bounds__(256) window_merge_add_kernel(const __nv_bfloat16* __restrict__ win,
+                                                               const __nv_bfloat16* __restrict__ shortcut,
+                                                               __nv_bfloat16* __restrict__ out, long long rows, int C,
+                                                               int H, int W, int ws, int shift) {
+  const int nvec = C >> 3;
+  const long long total = rows * nvec;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / nvec;
+    const int vi = (int)(i - r * nvec);
+    const long long src = image_row_to_window_row(r, H, W, ws, shift);
+    const uint4 a = reinterpret_cast<const uint4*>(shortcut + r * C)[vi];
+    const uint4 b = reinterpret_cast<const uint4*>(win + src * C)[vi];
+    float fa[8], fb[8];
+    unpack8(a, fa);
+    unpack8(b, fb);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) fa[t] += fb[t];
+    reinterpret_cast<uint4*>(out + r * C)[vi] = pack8(fa);
+  }
+}
+
+// exact GELU, 8 bf16 per thread
+__global__ void __launch_bounds__(256) gelu_rows_kernel(const __nv_bfloat16* __restrict__ x,
+                                                        __nv_bfloat16* __restrict__ out, long long nvec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 u = reinterpret_cast<const uint4*>(x)[i];
+    float f[8];
+    unpack8(u, f);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) f[t] = 0.5f * f[t] * (1.f + erff(f[t] * 0.70710678118654752440f));
+    reinterpret_cast<uint4*>(out)[i] = pack8(f);
+  }
+}
+
+static int grid_for(long long work_items, int threads) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace flpr
+
+using namespace flpr;
+
+extern "C" {
+
+int flpr_wcompose_max_k() { return WC_MAXK; }
+
+int flpr_wcompose_fwd(const float* aw, const float* stack, const float* atten, int kb, int ks, const float* sw,
+                      const float* mask, long long row_len, float thr_aw, float thr_mask, int prune, float* out_f32,
+                      void* out_bf16, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (kb < 0 || kb > WC_MAXK || (kb > 0 && ks < kb) || row_len <= 0) return -21;
+  bind_device_of(aw);
+  wcompose_fwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(aw, stack, atten, kb, ks, sw, mask, row_len, thr_aw, thr_mask,
+                                                        prune, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), n);
+  return (int)cudaGetLastError();
+}
+
+// part_att: [rows, kb] scratch; d_att: [kb]; d_aw may be null (no pruning: d aw == d theta); d_mask null without sw.
+int flpr_wcompose_bwd(const float* dth, const float* aw, const float* stack, int kb, int ks, const float* sw,
+                      const float* mask, long long row_len, float thr_aw, float thr_mask, int prune, float* d_aw,
+                      float* part_att, float* d_mask, float* d_att, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (kb < 0 || kb > WC_MAXK || (kb > 0 && ks < kb) || row_len <= 0) return -21;
+  bind_device_of(dth);
+  const long long rows = (n + row_len - 1) / row_len;
+  if (rows > 0x7fffffffLL) return -22;
+  wcompose_bwd_kernel<<<(unsigned)rows, 256, 0, st>>>(dth, aw, stack, kb, ks, sw, mask, row_len, thr_aw, thr_mask, prune,
+                                                      d_aw, part_att, d_mask, n);
+  int rc = (int)cudaGetLastError();
+  if (rc) return rc;
+  if (kb > 0 && d_att != nullptr) {
+    wcompose_colsum_kernel<<<kb, 256, 0, st>>>(part_att, rows, kb, d_att);
+    rc = (int)cudaGetLastError();
+  }
+  return rc;
+}
+
+// LayerNorm over rows of C bf16 channels (C % 8 == 0, C <= 2048). window != 0: see ln_rows_kernel.
+int flpr_ln_rows(const void* x, const float* gamma, const float* beta, void* out, long long rows, int C, float eps,
+                 int window, int H, int W, int ws, int shift, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (C % 8 || C <= 0 || C > 2048) return -23;
+  if (window && (ws <= 0 || H % ws || W % ws || shift < 0 || shift >= ws || rows % ((long long)H * W))) return -24;
+  bind_device_of(x);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out);
+  const int nvec = C / 8;
+  if (nvec <= 32)
+    ln_rows_kernel<1><<<grid, 256, 0, st>>>(xp, gamma, beta, op, rows, C, eps, window, H, W, ws, shift);
+  else if (nvec <= 64)
+    ln_rows_kernel<2><<<grid, 256, 0, st>>>(xp, gamma, beta, op, rows, C, eps, window, H, W, ws, shift);
+  else if (nvec <= 128)
+    ln_rows_kernel<4><<<grid, 256, 0, st>>>(xp, gamma, beta, op, rows, C, eps, window, H, W, ws, shift);
+  else
+    ln_rows_kernel<8><<<grid, 256, 0, st>>>(xp, gamma, beta, op, rows, C, eps, window, H, W, ws, shift);
+  return (int)cudaGetLastError();
+}
+
+int flpr_window_merge_add(const void* win, const void* shortcut, void* out, long long rows, int C, int H, int W, int ws,
+                          int shift, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (C % 8 || ws <= 0 || H % ws || W % ws || shift < 0 || shift >= ws || rows % ((long long)H * W)) return -24;
+  bind_device_of(win);
+  window_merge_add_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(win), reinterpret_cast<const __nv_bfloat16*>(shortcut),
+      reinterpret_cast<__nv_bfloat16*>(out), rows, C, H, W, ws, shift);
+  return (int)cudaGetLastError();
+}
+
+int flpr_gelu_rows(const void* x, void* out, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (n % 8) return -23;
+  bind_device_of(x);
+  gelu_rows_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                         reinterpret_cast<__nv_bfloat16*>(out), n / 8);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

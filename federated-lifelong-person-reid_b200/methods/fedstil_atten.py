@@ -21,28 +21,47 @@ import torch.nn as nn
 import torch.nn.utils.parametrize as parametrize
 
 from . import fedstil as base
+from ..ops import layer as lops
 
 
 class _Compose(nn.Module):
-    """weight = (gw_stack @ atten).view_as(aw) + aw ; ``gw_stack`` is ``[numel, Kmax]`` in the weight's own layout."""
+    """weight = sum_k atten_k * gw[..., k] + aw ; ``gw`` has the weight's logical shape plus a trailing client dim
+    ``Kmax`` and is *stored* in the weight's own element order (OHWI + K on CUDA, see ``Model.materialize``), so the
+    fused compose kernel (``ops.layer.compose_weight``: one pass, fp32 + bf16 results, ``d atten`` by a deterministic
+    two-stage reduction) walks ``aw`` and ``gw`` with the same flat index. Every other access goes through the logical
+    shape, so the storage order is invisible outside this class."""
 
     def __init__(self, weight: torch.Tensor, k_max: int, atten_default: float):
         super().__init__()
-        self.register_buffer("gw", torch.zeros(weight.numel(), k_max))
-        self.gw[:, 0] = weight.detach().reshape(-1)
+        self.register_buffer("gw", torch.zeros(*weight.shape, k_max))
+        self.gw[..., 0] = weight.detach()
         self.atten = nn.Parameter(torch.zeros(k_max))
         self.k_cur = 1
+        self.k_max = int(k_max)
         self.atten_default = atten_default
         with torch.no_grad():
             self.atten[0] = atten_default
         self.register_buffer("atten0", self.atten.detach().clone())
         self.register_buffer("aw0", torch.zeros_like(weight))
 
+    def _mix(self, atten: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+        return (self.gw.reshape(-1, self.k_max) @ atten).view(like.shape)
+
     def forward(self, aw: torch.Tensor) -> torch.Tensor:
-        return (self.gw @ self.atten).view_as(aw) + aw
+        if aw.is_cuda and self.k_max <= lops.WC_MAX_K and lops.enabled("wcompose", aw.device) \
+                and lops.stack_phys(self.gw, aw) is not None:
+            theta, t16 = lops.compose_weight(aw, self.gw, self.atten, self.k_max)
+            theta._flpr_bf16 = t16                       # the fast head's tensor-core operand: no separate cast pass
+            return theta
+        return self._mix(self.atten, aw) + aw
 
     def right_inverse(self, theta: torch.Tensor) -> torch.Tensor:
-        return theta - (self.gw @ self.atten.detach()).view_as(theta)
+        return theta - self._mix(self.atten.detach(), theta)
+
+    def align_storage(self, aw: torch.Tensor) -> None:
+        """Re-lay ``gw`` out in ``aw``'s physical element order (after the arena moved ``aw`` to OHWI storage)."""
+        with torch.no_grad():
+            self.gw = lops.stack_aligned(self.gw, aw)
 
 
 class Model(base.Model):
@@ -67,6 +86,10 @@ class Model(base.Model):
 
     def materialize(self, device, compute_dtype="bf16", fine_tuning=None):
         base.ModelModule.materialize(self, device, compute_dtype, fine_tuning)
+        for lname, comp in self.composers.items():
+            comp.align_storage(self.net.get_submodule(lname).parametrizations.weight.original)
+        if self.device.type == "cuda":
+            lops.enabled("wcompose", self.device)      # one-time on-device self-check of the compose kernels, up front
         self.G = None
         self.use_cuda_graphs = False                   # atten / K change between rounds: keep the step eager
         return self
@@ -95,11 +118,13 @@ class Model(base.Model):
         with torch.no_grad():
             for lname, comp in self.composers.items():
                 seg = a.segments[f"{lname}.parametrizations.weight.original"]
-                chunk = stack[seg.offset:seg.offset + seg.numel]                       # [numel, Kmax]
+                chunk = stack[seg.offset:seg.offset + seg.numel]                       # [numel, Kmax], arena order
                 if seg.channels_last:
                     o, i, h, w = seg.shape
-                    chunk = chunk.view(o, h, w, i, -1).permute(0, 3, 1, 2, 4).reshape(seg.numel, -1)
-                comp.gw.copy_(chunk)
+                    chunk = chunk.view(o, h, w, i, -1).permute(0, 3, 1, 2, 4)          # logical view, no copy
+                else:
+                    chunk = chunk.view(*seg.shape, -1)
+                comp.gw.copy_(chunk)                     # gw is stored in the same element order: a straight copy
                 comp.k_cur = k_cur
                 comp.atten.zero_()
                 comp.atten[:k_cur] = self.atten_default
@@ -123,7 +148,8 @@ class Model(base.Model):
         for lname, comp in self.composers.items():
             mod = self.net.get_submodule(lname)
             shape = mod.parametrizations.weight.original.shape
-            gw[f"{lname}.global_weight"] = comp.gw[:, :comp.k_cur].detach().reshape(*shape, comp.k_cur).clone()
+            gw[f"{lname}.global_weight"] = comp.gw[..., :comp.k_cur].detach().clone(
+                memory_format=torch.contiguous_format)
             gwa[f"{lname}.global_weight_atten"] = comp.atten[:comp.k_cur].detach().clone()
             aw[f"{lname}.adaptive_weight"] = mod.parametrizations.weight.original.detach().clone(
                 memory_format=torch.contiguous_format).unsqueeze(-1)
@@ -146,7 +172,7 @@ class Model(base.Model):
                 if comp is not None:
                     k = g.shape[-1]
                     comp.gw.zero_()
-                    comp.gw[:, :k] = g.reshape(-1, k).to(comp.gw.device)
+                    comp.gw[..., :k] = g.reshape(*comp.gw.shape[:-1], k).to(comp.gw.device)
                     comp.k_cur = k
             for key, w in (params_state.get("adaptive_weights") or {}).items():
                 lname = key[: -len(".adaptive_weight")]

@@ -26,6 +26,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops import layer as lops
 from ..runtime.modules import ClientModule, ModelModule, OperatorModule, ServerModule
 from ..utils.misc import tensor_reverse_permute
 
@@ -57,9 +58,41 @@ class Decomposed(nn.Module):
         return w * (w.abs() > thr).to(w.dtype)
 
     def theta(self, prune: bool) -> torch.Tensor:
+        if self.aw.is_cuda and self.kb_cnt <= lops.WC_MAX_K and lops.enabled("wcompose", self.aw.device):
+            th = self._theta_fused(prune)
+            if th is not None:
+                return th
         aw = self._prune(self.aw, self.lambda_l1) if prune else self.aw
         mask = self._prune(self.mask, self.lambda_mask) if prune else self.mask
         return self._bmask(mask, self.sw) * self.sw + aw + (self.aw_kb * self.atten).sum(-1)
+
+    def _theta_fused(self, prune: bool, use_ref: bool = False) -> Optional[torch.Tensor]:
+        """One kernel instead of the ~10 element-wise passes of the expression above (``csrc/layer_ops.cu``): reads
+        ``aw``, ``sw``, the ``kb`` stacked weights, writes ``theta`` in fp32 (carries the gradient) and bf16 (the
+        tensor-core operand, attached as ``theta._flpr_bf16`` for the fast head); the backward kernel returns
+        ``d aw`` / ``d mask`` / ``d atten`` from ``d theta`` in one sweep. ``sw`` and ``aw_kb`` are kept in ``aw``'s
+        storage order (OHWI on CUDA) - they are only ever written through logical-shape ``copy_``s."""
+        aw = self.aw
+        if not (aw.is_contiguous() or lops.is_channels_last_4d(aw)) or lops.stack_phys(self.aw_kb, aw) is None \
+                or lops.is_channels_last_4d(aw) != lops.is_channels_last_4d(self.sw) or not (
+                    self.sw.is_contiguous() or lops.is_channels_last_4d(self.sw)):
+            return None                                   # storage not aligned (see align_storage): original expression
+        theta, t16 = lops.compose_weight(aw, self.aw_kb, self.atten, self.kb_cnt, self.sw, self.mask,
+                                         self.lambda_l1, self.lambda_mask, prune, use_ref)
+        theta._flpr_bf16 = t16
+        return theta
+
+    def align_storage(self) -> None:
+        """Keep ``sw`` and ``aw_kb`` in ``aw``'s storage order (called once the arena has moved ``aw`` to OHWI storage;
+        never from inside a step: replacing a buffer during a CUDA-graph capture would strand the old one)."""
+        aw = self.aw
+        with torch.no_grad():
+            self.aw_kb = lops.stack_aligned(self.aw_kb, aw)
+            if lops.is_channels_last_4d(aw):
+                if not lops.is_channels_last_4d(self.sw):
+                    self.sw = self.sw.contiguous(memory_format=torch.channels_last)
+            elif not self.sw.is_contiguous():
+                self.sw = self.sw.contiguous()
 
     def reinit(self) -> None:
         with torch.no_grad():
@@ -94,6 +127,14 @@ class Model(ModelModule):
             parent = net.get_submodule(name.rsplit(".", 1)[0]) if "." in name else net
             setattr(parent, name.rsplit(".", 1)[-1], Decomposed(mod, self.kb_cnt, self.lambda_l1, self.lambda_mask))
             self.decomposed_names.append(name)
+
+    def materialize(self, device, compute_dtype: str = "bf16", fine_tuning=None):
+        super().materialize(device, compute_dtype, fine_tuning)
+        for _, layer in self.decomposed_module_leaves():
+            layer.align_storage()
+        if self.device.type == "cuda":
+            lops.enabled("wcompose", self.device)      # one-time on-device self-check of the compose kernels, up front
+        return self
 
     def decomposed_module_leaves(self):
         return [(n, self.net.get_submodule(n)) for n in self.decomposed_names]

@@ -248,10 +248,16 @@ class FastResNetHead:
             return w, layer.kernel_size[0], layer.stride[0]
         return w, 1, 1
 
+    def _shadow_of(self, w: torch.Tensor):
+        """bf16 compute copy of ``w``: the optimizer-maintained arena shadow of a parameter, or the bf16 twin that a
+        fused weight composition wrote next to its fp32 result (``ops.layer.compose_weight``)."""
+        sh = self.shadow(w)
+        return sh if sh is not None else getattr(w, "_flpr_bf16", None)
+
     def _conv(self, x: torch.Tensor, conv: nn.Module, want_stats: bool = False):
         """x: [N,H,W,C] bf16 -> [N,H',W',Cout] bf16 (``(y, col_part)`` with ``want_stats``: fused BN statistics)"""
         w, k, s = self._weight_of(conv)
-        sh = self.shadow(w)
+        sh = self._shadow_of(w)
         if sh is None and not w.requires_grad and x.is_cuda and isinstance(w, nn.Parameter):
             sh = self._frozen_bf16(w)
         if getattr(conv, "bias", None) is not None:
@@ -381,7 +387,7 @@ class FastResNetHead:
         if not m.training:
             return global_feat
         w = self._weight_of(m.classifier)[0]
-        score = gops.linear(feat, w, self.shadow(w), self.grad_slot(w))
+        score = gops.linear(feat, w, self._shadow_of(w), self.grad_slot(w))
         if m.classifier.bias is not None:
             score = score + m.classifier.bias.to(score.dtype)
         return score, global_feat

@@ -30,6 +30,9 @@ _SPECS = {
 }
 
 
+from ..ops import layer as lops  # noqa: E402
+
+
 class TcLinear(nn.Linear):
     """``nn.Linear`` whose CUDA / bf16 forward, data gradient and weight gradient run on the tcgen05 GEMM kernel
     (``ops.gemm.linear``: bf16 compute copy of the weight kept by the fused optimizer, fp32 weight gradient written by
@@ -77,6 +80,14 @@ class FrozenLayerNorm(nn.LayerNorm):
         if hit is None or hit[0] != (w._version, self.bias._version):
             hit = self.__dict__["_flpr_wb"] = ((w._version, self.bias._version), w.detach().to(torch.bfloat16),
                                                self.bias.detach().to(torch.bfloat16))
+        c = x.shape[-1]
+        if c % 8 == 0 and c <= 2048 and len(self.normalized_shape) == 1 and w.dtype == torch.float32 \
+                and self.bias is not None and lops.enabled("swin_tokens", x.device):
+            # native warp-per-token kernel (fp32 statistics, fp32 gamma / beta): ATen's bf16 LayerNorm was 1.9 ms of the
+            # 6.3 ms Swin-T trunk forward (profiles/r2_results.md) for ~0.15 ms worth of HBM traffic
+            x2 = x.reshape(-1, c)
+            return lops.ln_rows(x2 if x2.is_contiguous() else x2.contiguous(), self.weight, self.bias,
+                                self.eps).view(x.shape)
         with torch.autocast(device_type="cuda", enabled=False):
             return F.layer_norm(x, self.normalized_shape, hit[1], hit[2], self.eps)
 
@@ -217,10 +228,51 @@ class SwinTransformerBlock(nn.Module):
             mask = mask.masked_fill(mask != 0, -100.0).masked_fill(mask == 0, 0.0)
         self.register_buffer("attn_mask", mask)
 
+    def _fused_ok(self, x: torch.Tensor) -> bool:
+        """Frozen stage on the bf16 inference path (prototype pass / frozen stages of a training step)."""
+        if not (x.is_cuda and x.dtype == torch.bfloat16 and not torch.is_grad_enabled()):
+            return False
+        c = x.shape[-1]
+        if c % 8 or c > 2048 or self.window_size * self.window_size < 1:
+            return False
+        if self.training and (self.drop_path.p > 0.0 or self.mlp.drop.p > 0.0):
+            return False
+        frozen = not any(p.requires_grad for p in (self.norm1.weight, self.norm2.weight, self.mlp.fc1.weight,
+                                                   self.mlp.fc2.weight))
+        fp32 = all(p is not None and p.dtype == torch.float32 for p in (
+            self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias, self.mlp.fc2.bias))
+        return frozen and fp32 and lops.enabled("swin_tokens", x.device)
+
+    def _forward_fused(self, x: torch.Tensor) -> torch.Tensor:
+        """Same block, four fewer passes over the token stream: ``norm1`` writes straight into the layout of the shifted
+        windows (norm + roll + window partition = one kernel), window reverse + roll back + residual is one kernel,
+        ``norm2`` is the native LayerNorm, and the second residual add happens in the ``fc2`` GEMM epilogue."""
+        from ..ops import gemm as gops
+        h, w = self.resolution
+        b, l, c = x.shape
+        ws, sh = self.window_size, self.shift_size
+        x2 = x.reshape(b * l, c)
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        win = lops.ln_rows(x2, self.norm1.weight, self.norm1.bias, self.norm1.eps, (h, w, ws, sh))
+        win = self.attn(win.view(-1, ws * ws, c), self.attn_mask).reshape(-1, c)
+        if win.dtype != torch.bfloat16:
+            win = win.to(torch.bfloat16)
+        x2 = lops.window_merge_add(win if win.is_contiguous() else win.contiguous(), x2, h, w, ws, sh)
+        y = lops.ln_rows(x2, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        hid = self.mlp.fc1(y).reshape(b * l, -1)
+        hid = lops.gelu_rows(hid if (hid.dtype == torch.bfloat16 and hid.is_contiguous())
+                             else hid.to(torch.bfloat16).contiguous())
+        fc2 = self.mlp.fc2
+        wb = fc2._frozen_copy(fc2.weight) if hasattr(fc2, "_frozen_copy") else fc2.weight.detach().to(torch.bfloat16)
+        out = gops.gemm(hid, wb, bias_n=fc2.bias.detach().float(), residual=x2)
+        return out.view(b, l, c)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         h, w = self.resolution
         b, l, c = x.shape
         assert l == h * w, "input feature has wrong size"
+        if self._fused_ok(x):
+            return self._forward_fused(x)
         shortcut = x
         x = self.norm1(x).view(b, h, w, c)
         if self.shift_size > 0:

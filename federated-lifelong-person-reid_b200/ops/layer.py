@@ -1,0 +1,517 @@
+"""Layer-level fused element-wise ops (``csrc/layer_ops.cu``): decomposed-weight composition for FedWeIT /
+fedstil-atten and the Swin token kernels (LayerNorm written straight into the shifted-window layout, window merge +
+residual, GELU).
+
+Every op has a plain PyTorch formulation (``*_ref``) with the same index mathematics: it is the CPU path, the yardstick
+of the tests, and the yardstick of :func:`enabled` - a one-time numerics self-check that each kernel family runs on
+the device before its first use (these kernels were written after the round's last GPU session; a family whose check
+fails is switched off with a loud warning and its callers keep their PyTorch formulation, so a kernel bug can cost
+speed but not correctness).
+
+Reference sites: ``methods/fedweit.py:122-136`` (decomposed layer), ``methods/fedstil_atten.py:88-96`` (stacked global
+weights), ``models/swin_transformer.py:118-140`` (MLP), ``:358-395`` (block: norm -> roll -> window partition ->
+attention -> window reverse -> roll -> residual).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import threading
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import native
+
+_log = logging.getLogger("flpr.ops.layer")
+c_ll, c_int, c_float = native.c_ll, native.c_int, native.c_float
+
+
+def _declare(lib) -> None:
+    if getattr(lib, "_flpr_layer_declared", False):
+        return
+    P, I, Fl, L = native.c_void_p, native.c_int, native.c_float, native.c_ll
+    sig = {
+        "flpr_wcompose_fwd": [P, P, P, I, I, P, P, L, Fl, Fl, I, P, P, L, P],
+        "flpr_wcompose_bwd": [P, P, P, I, I, P, P, L, Fl, Fl, I, P, P, P, P, L, P],
+        "flpr_ln_rows": [P, P, P, P, L, I, Fl, I, I, I, I, I, P],
+        "flpr_window_merge_add": [P, P, P, L, I, I, I, I, I, P],
+        "flpr_gelu_rows": [P, P, L, P],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = I
+    lib.flpr_wcompose_max_k.argtypes = []
+    lib.flpr_wcompose_max_k.restype = I
+    lib._flpr_layer_declared = True
+
+
+def _lib():
+    lib = native.load()
+    _declare(lib)
+    return lib
+
+
+WC_MAX_K = 16      # flpr_wcompose_max_k(): stacked weights per element the compose kernels keep in registers
+
+
+# ===================================================================================================== physical layouts
+def is_channels_last_4d(t: torch.Tensor) -> bool:
+    """4-D tensor stored OHWI (``channels_last``) and not simultaneously plain-contiguous."""
+    return t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def phys_flat(t: torch.Tensor) -> torch.Tensor:
+    """1-D view of ``t`` in its storage (physical) order. ``t`` must be dense: contiguous, or 4-D channels_last."""
+    if t.is_contiguous():
+        return t.reshape(-1)
+    if is_channels_last_4d(t):
+        return t.permute(0, 2, 3, 1).reshape(-1)
+    raise ValueError("tensor is neither contiguous nor channels_last-dense")
+
+
+def like_phys(flat: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
+    """View the flat physical-order buffer ``flat`` with ``ref``'s logical shape and strides."""
+    if is_channels_last_4d(ref):
+        o, i, h, w = ref.shape
+        return flat.view(o, h, w, i).permute(0, 3, 1, 2)
+    return flat.view(ref.shape)
+
+
+def flat_like(g: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
+    """``g`` (logical shape of ``ref``, any strides) flattened in ``ref``'s physical order (copies only if needed)."""
+    if is_channels_last_4d(ref):
+        return g.permute(0, 2, 3, 1).contiguous().reshape(-1)
+    return g.contiguous().reshape(-1)
+
+
+def stack_phys(stack: torch.Tensor, ref: torch.Tensor) -> Optional[torch.Tensor]:
+    """``stack``: ``[*ref.shape, K]``. Returns the ``[numel, K]`` view whose row order is ``ref``'s physical order, or
+    ``None`` when the stack is not stored that way (see :func:`stack_aligned`)."""
+    if is_channels_last_4d(ref):
+        v = stack.permute(0, 2, 3, 1, 4)
+        return v.reshape(-1, stack.shape[-1]) if v.is_contiguous() else None
+    return stack.reshape(-1, stack.shape[-1]) if stack.is_contiguous() else None
+
+
+def stack_aligned(stack: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
+    """A tensor equal to ``stack`` (same logical shape) stored in ``ref``'s physical element order + trailing K."""
+    if stack_phys(stack, ref) is not None:
+        return stack
+    if is_channels_last_4d(ref):
+        return stack.permute(0, 2, 3, 1, 4).contiguous().permute(0, 3, 1, 2, 4)
+    return stack.contiguous()
+
+
+# ===================================================================================================== compose
+def wcompose_fwd_ref(aw, stack, atten, kb, sw, mask, row_len, thr_aw, thr_mask, prune):
+    a = aw * (aw.abs() > thr_aw).to(aw.dtype) if prune else aw
+    th = a
+    if kb > 0:
+        th = th + (stack[:, :kb] * atten[:kb]).sum(-1)
+    if sw is not None:
+        m = mask * (mask.abs() > thr_mask).to(mask.dtype) if prune else mask
+        th = th + m.repeat_interleave(row_len)[:aw.numel()] * sw
+    return th
+
+
+def wcompose_fwd(aw: torch.Tensor, stack: Optional[torch.Tensor], atten: Optional[torch.Tensor], kb: int,
+                 sw: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, row_len: int = 1,
+                 thr_aw: float = 0.0, thr_mask: float = 0.0, prune: bool = False, want_f32: bool = True,
+                 want_bf16: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """``theta[e] = prune(aw[e]) + sum_{k<kb} atten[k] stack[e, k] + prune(mask[e // row_len]) sw[e]`` over flat fp32
+    buffers; returns ``(theta_fp32, theta_bf16)`` (either may be skipped)."""
+    n = aw.numel()
+    if not aw.is_cuda:
+        th = wcompose_fwd_ref(aw, stack, atten, kb, sw, mask, row_len, thr_aw, thr_mask, prune)
+        return (th if want_f32 else None), (th.to(torch.bfloat16) if want_bf16 else None)
+    lib = _lib()
+    assert aw.dtype == torch.float32 and aw.is_contiguous() and 0 <= kb <= WC_MAX_K
+    ks = 0
+    if kb > 0:
+        assert stack.dtype == torch.float32 and stack.is_contiguous() and stack.shape[0] == n and stack.shape[1] >= kb
+        assert atten.dtype == torch.float32 and atten.is_contiguous() and atten.numel() >= kb
+        ks = stack.shape[1]
+    if sw is not None:
+        assert sw.dtype == torch.float32 and sw.is_contiguous() and sw.numel() == n
+        assert mask.dtype == torch.float32 and mask.is_contiguous() and mask.numel() * row_len >= n
+    o32 = torch.empty(n, dtype=torch.float32, device=aw.device) if want_f32 else None
+    o16 = torch.empty(n, dtype=torch.bfloat16, device=aw.device) if want_bf16 else None
+    rc = lib.flpr_wcompose_fwd(native.ptr(aw), native.ptr(stack if kb > 0 else None),
+                               native.ptr(atten if kb > 0 else None), int(kb), int(ks), native.ptr(sw),
+                               native.ptr(mask if sw is not None else None), int(row_len), float(thr_aw),
+                               float(thr_mask), int(bool(prune)), native.ptr(o32), native.ptr(o16), n,
+                               native.stream(aw.device))
+    native.check(rc, "flpr_wcompose_fwd")
+    native.count_launch()
+    return o32, o16
+
+
+def wcompose_bwd_ref(dth, aw, stack, kb, sw, mask, row_len, thr_aw, thr_mask, prune):
+    d_aw = dth * (aw.abs() > thr_aw).to(dth.dtype) if prune else None
+    d_att = (dth[:, None] * stack[:, :kb]).sum(0) if kb > 0 else None
+    d_mask = None
+    if sw is not None:
+        rows = mask.numel()
+        prod = dth * sw
+        pad = rows * row_len - prod.numel()
+        if pad:
+            prod = torch.cat([prod, prod.new_zeros(pad)])
+        d_mask = prod.view(rows, row_len).sum(1)
+        if prune:
+            d_mask = d_mask * (mask.abs() > thr_mask).to(d_mask.dtype)
+    return d_aw, d_att, d_mask
+
+
+def wcompose_bwd(dth: torch.Tensor, aw: torch.Tensor, stack: Optional[torch.Tensor], kb: int,
+                 sw: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, row_len: int = 1,
+                 thr_aw: float = 0.0, thr_mask: float = 0.0, prune: bool = False, chunk: int = 8192):
+    """Gradients of :func:`wcompose_fwd` w.r.t. ``aw`` (``None`` = identical to ``dth``: nothing was pruned),
+    ``atten[:kb]`` and ``mask``. Without ``sw`` the rows of the reduction are arbitrary ``chunk``-element pieces."""
+    if not dth.is_cuda:
+        return wcompose_bwd_ref(dth, aw, stack, kb, sw, mask, row_len, thr_aw, thr_mask, prune)
+    lib = _lib()
+    n = dth.numel()
+    assert dth.dtype == torch.float32 and dth.is_contiguous() and aw.is_contiguous() and 0 <= kb <= WC_MAX_K
+    if sw is None:
+        row_len = int(chunk)
+    rows = (n + row_len - 1) // row_len
+    ks = stack.shape[1] if kb > 0 else 0
+    if kb > 0:
+        assert stack.dtype == torch.float32 and stack.is_contiguous() and stack.shape[0] == n
+    d_aw = torch.empty_like(dth) if prune else None
+    part = torch.empty(rows, max(kb, 1), dtype=torch.float32, device=dth.device) if kb > 0 else None
+    d_att = torch.empty(kb, dtype=torch.float32, device=dth.device) if kb > 0 else None
+    d_mask = torch.empty(rows, dtype=torch.float32, device=dth.device) if sw is not None else None
+    if sw is not None:
+        assert mask.numel() == rows and sw.is_contiguous() and mask.is_contiguous()
+    rc = lib.flpr_wcompose_bwd(native.ptr(dth), native.ptr(aw), native.ptr(stack if kb > 0 else None), int(kb),
+                               int(ks), native.ptr(sw), native.ptr(mask if sw is not None else None), int(row_len),
+                               float(thr_aw), float(thr_mask), int(bool(prune)), native.ptr(d_aw), native.ptr(part),
+                               native.ptr(d_mask), native.ptr(d_att), n, native.stream(dth.device))
+    native.check(rc, "flpr_wcompose_bwd")
+    native.count_launch(2 if kb > 0 else 1)
+    return d_aw, d_att, d_mask
+
+
+class _WComposeFn(torch.autograd.Function):
+    """``theta = prune(aw) + sum_k atten_k stack[..., k] (+ prune(mask)[o] * sw)`` on the weight's own storage order.
+
+    ``aw`` (trainable, weight-shaped) fixes the physical layout; ``sw`` and ``stack[..., k]`` must be stored in the same
+    element order (:func:`stack_aligned`). Returns ``(theta_fp32, theta_bf16)`` shaped / strided like ``aw``; the bf16
+    tensor is the tensor-core operand (non-differentiable), the fp32 one carries the gradient."""
+
+    @staticmethod
+    def forward(ctx, aw, mask, atten, sw, stack, kb, thr_aw, thr_mask, prune, use_ref):
+        aw_f = phys_flat(aw.detach())
+        st = stack_phys(stack, aw) if kb > 0 else None
+        assert kb == 0 or st is not None, "stack is not stored in the weight's physical order"
+        sw_f = phys_flat(sw) if sw is not None else None
+        if sw_f is not None:
+            assert is_channels_last_4d(sw) == is_channels_last_4d(aw) or sw.numel() == sw.shape[0], "sw / aw layouts differ"
+        row_len = aw.numel() // aw.shape[0]
+        at = atten.detach() if atten is not None else None
+        mk = mask.detach().contiguous() if mask is not None else None
+        if use_ref:
+            th = wcompose_fwd_ref(aw_f, st, at, kb, sw_f, mk, row_len, thr_aw, thr_mask, prune)
+            th32, th16 = th, th.to(torch.bfloat16)
+        else:
+            th32, th16 = wcompose_fwd(aw_f, st, at, kb, sw_f, mk, row_len, thr_aw, thr_mask, prune)
+        ctx.save_for_backward(aw, mask, atten, sw, stack)
+        ctx.cfg = (kb, thr_aw, thr_mask, prune, use_ref, row_len)
+        theta, theta16 = like_phys(th32, aw), like_phys(th16, aw)
+        ctx.mark_non_differentiable(theta16)
+        return theta, theta16
+
+    @staticmethod
+    def backward(ctx, g, _g16):
+        aw, mask, atten, sw, stack = ctx.saved_tensors
+        kb, thr_aw, thr_mask, prune, use_ref, row_len = ctx.cfg
+        if g is None:
+            return (None,) * 10
+        gf = flat_like(g.float(), aw)
+        aw_f = phys_flat(aw.detach())
+        st = stack_phys(stack, aw) if kb > 0 else None
+        sw_f = phys_flat(sw) if sw is not None else None
+        mk = mask.detach().contiguous() if mask is not None else None
+        fn = wcompose_bwd_ref if use_ref else wcompose_bwd
+        d_aw, d_att, d_mask = fn(gf, aw_f, st, kb, sw_f, mk, row_len, thr_aw, thr_mask, prune)
+        g_aw = like_phys(gf if d_aw is None else d_aw, aw) if ctx.needs_input_grad[0] else None
+        g_mask = d_mask.view(mask.shape) if (mask is not None and ctx.needs_input_grad[1] and d_mask is not None) else None
+        g_att = None
+        if atten is not None and ctx.needs_input_grad[2]:
+            g_att = torch.zeros_like(atten)
+            if kb > 0:
+                g_att[:kb] = d_att
+        return g_aw, g_mask, g_att, None, None, None, None, None, None, None
+
+
+def compose_weight(aw: torch.Tensor, stack: Optional[torch.Tensor], atten: Optional[torch.Tensor], kb: int,
+                   sw: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, thr_aw: float = 0.0,
+                   thr_mask: float = 0.0, prune: bool = False, use_ref: bool = False):
+    """Differentiable fused composition; returns ``(theta_fp32, theta_bf16)`` (see :class:`_WComposeFn`)."""
+    return _WComposeFn.apply(aw, mask, atten, sw, stack, int(kb), float(thr_aw), float(thr_mask), bool(prune),
+                             bool(use_ref or not aw.is_cuda))
+
+
+# ===================================================================================================== Swin token ops
+def window_src_rows(rows: int, H: int, W: int, ws: int, shift: int, device) -> torch.Tensor:
+    """Image-layout row read by each window-layout row: window token ``(b, wh, ww, ph, pw)`` of the cyclically shifted
+    map is image token ``(b, (wh*ws+ph+shift) % H, (ww*ws+pw+shift) % W)`` (``roll(-shift)`` then window partition)."""
+    r = torch.arange(rows, device=device)
+    ws2, nww, nwh = ws * ws, W // ws, H // ws
+    win, pos = r // ws2, r % ws2
+    ph, pw = pos // ws, pos % ws
+    wwi, t = win % nww, win // nww
+    whi, b = t % nwh, t // nwh
+    hh, ww = (whi * ws + ph + shift) % H, (wwi * ws + pw + shift) % W
+    return (b * H + hh) * W + ww
+
+
+def image_src_rows(rows: int, H: int, W: int, ws: int, shift: int, device) -> torch.Tensor:
+    """Window-layout row that lands on each image-layout row (window reverse then ``roll(+shift)``)."""
+    r = torch.arange(rows, device=device)
+    ws2, nww, nwh = ws * ws, W // ws, H // ws
+    b, rem = r // (H * W), r % (H * W)
+    hh, ww = rem // W, rem % W
+    h2, w2 = (hh - shift + H) % H, (ww - shift + W) % W
+    win = (b * nwh + h2 // ws) * nww + w2 // ws
+    return win * ws2 + (h2 % ws) * ws + (w2 % ws)
+
+
+def ln_rows_ref(x, gamma, beta, eps, window=None):
+    rows, c = x.shape
+    src = x if window is None else x[window_src_rows(rows, *window, device=x.device)]
+    return F.layer_norm(src.float(), (c,), gamma.float(), beta.float(), eps).to(x.dtype)
+
+
+def ln_rows(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+            window: Optional[Tuple[int, int, int, int]] = None) -> torch.Tensor:
+    """LayerNorm over the last dim of ``x`` ``[rows, C]`` (bf16, fp32 statistics, fp32 ``gamma`` / ``beta``).
+    ``window = (H, W, ws, shift)``: ``x`` is in image layout ``[B*H*W, C]`` and the result is written in the layout of
+    the shifted windows ``[B*nW*ws*ws, C]`` (norm -> roll -> window partition in one pass)."""
+    if not x.is_cuda:
+        return ln_rows_ref(x, gamma, beta, eps, window)
+    lib = _lib()
+    rows, c = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and c % 8 == 0 and c <= 2048
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.is_contiguous() and beta.is_contiguous()
+    out = torch.empty_like(x)
+    h, w, ws, sh = window if window is not None else (0, 0, 0, 0)
+    rc = lib.flpr_ln_rows(native.ptr(x), native.ptr(gamma), native.ptr(beta), native.ptr(out), rows, c, float(eps),
+                          int(window is not None), int(h), int(w), int(ws), int(sh), native.stream(x.device))
+    native.check(rc, "flpr_ln_rows")
+    native.count_launch()
+    return out
+
+
+def window_merge_add_ref(win, shortcut, H, W, ws, shift):
+    rows = shortcut.shape[0]
+    return (shortcut.float() + win[image_src_rows(rows, H, W, ws, shift, win.device)].float()).to(shortcut.dtype)
+
+
+def window_merge_add(win: torch.Tensor, shortcut: torch.Tensor, H: int, W: int, ws: int, shift: int) -> torch.Tensor:
+    """``shortcut + roll(window_reverse(win), +shift)`` over ``[B*H*W, C]`` bf16 rows in one pass."""
+    if not win.is_cuda:
+        return window_merge_add_ref(win, shortcut, H, W, ws, shift)
+    lib = _lib()
+    rows, c = shortcut.shape
+    assert win.shape == shortcut.shape and win.dtype == torch.bfloat16 and shortcut.dtype == torch.bfloat16
+    assert win.is_contiguous() and shortcut.is_contiguous() and c % 8 == 0
+    out = torch.empty_like(shortcut)
+    rc = lib.flpr_window_merge_add(native.ptr(win), native.ptr(shortcut), native.ptr(out), rows, c, int(H), int(W),
+                                   int(ws), int(shift), native.stream(win.device))
+    native.check(rc, "flpr_window_merge_add")
+    native.count_launch()
+    return out
+
+
+def gelu_rows(x: torch.Tensor) -> torch.Tensor:
+    """Exact (erf) GELU over a bf16 tensor."""
+    if not x.is_cuda:
+        return F.gelu(x.float()).to(x.dtype)
+    lib = _lib()
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() % 8 == 0
+    out = torch.empty_like(x)
+    native.check(lib.flpr_gelu_rows(native.ptr(x), native.ptr(out), x.numel(), native.stream(x.device)),
+                 "flpr_gelu_rows")
+    native.count_launch()
+    return out
+
+
+# ===================================================================================================== self-checks
+_state: Dict[str, bool] = {}
+_lock = threading.Lock()
+
+
+def _close(a: torch.Tensor, b: torch.Tensor, rtol: float, atol_frac: float) -> bool:
+    a, b = a.float(), b.float()
+    if a.shape != b.shape or not bool(torch.isfinite(a).all()):
+        return False
+    atol = atol_frac * float(b.abs().max()) + 1e-6
+    return bool(torch.allclose(a, b, rtol=rtol, atol=atol))
+
+
+def _check_wcompose(dev) -> bool:
+    g = torch.Generator(device="cpu").manual_seed(11)
+    ok = True
+    for (rows, row_len, kb, ks, with_sw, prune) in ((24, 200, 5, 5, True, True), (7, 8192, 8, 8, False, False),
+                                                    (5, 333, 0, 0, True, True), (3, 1000, 3, 6, True, False)):
+        n = rows * row_len - (3 if not with_sw else 0)
+        aw = (torch.randn(n, generator=g) * 0.01).to(dev)
+        stack = torch.randn(n, max(ks, 1), generator=g).to(dev) if kb else None
+        atten = torch.randn(max(ks, 1), generator=g).to(dev) if kb else None
+        sw = torch.randn(n, generator=g).to(dev) if with_sw else None
+        mask = torch.rand(rows, generator=g).to(dev) if with_sw else None
+        thr = 0.008
+        r32 = wcompose_fwd_ref(aw, stack, atten, kb, sw, mask, row_len, thr, 0.5, prune)
+        o32, o16 = wcompose_fwd(aw, stack, atten, kb, sw, mask, row_len, thr, 0.5, prune)
+        ok = ok and _close(o32, r32, 1e-5, 1e-6) and _close(o16, r32, 1e-2, 1e-2)
+        dth = torch.randn(n, generator=g).to(dev)
+        ra, rt, rm = wcompose_bwd_ref(dth, aw, stack, kb, sw, mask, row_len if with_sw else 8192, thr, 0.5, prune)
+        da, dt, dm = wcompose_bwd(dth, aw, stack, kb, sw, mask, row_len, thr, 0.5, prune)
+        ok = ok and ((da is None) == (ra is None)) and (da is None or bool(torch.equal(da, ra)))
+        ok = ok and (kb == 0 or _close(dt, rt, 1e-4, 1e-5)) and (not with_sw or _close(dm, rm, 1e-4, 1e-5))
+    return ok
+
+
+def _check_swin_tokens(dev) -> bool:
+    from . import gemm as gops
+    g = torch.Generator(device="cpu").manual_seed(12)
+    ok = True
+    for (b, h, w, ws, shift, c) in ((2, 14, 14, 7, 3, 96), (1, 8, 4, 4, 0, 192), (3, 7, 7, 7, 0, 768),
+                                    (1, 14, 7, 7, 2, 1536)):
+        rows = b * h * w
+        x = torch.randn(rows, c, generator=g).to(dev).to(torch.bfloat16)
+        gamma, beta = (1 + 0.1 * torch.randn(c, generator=g)).to(dev), (0.1 * torch.randn(c, generator=g)).to(dev)
+        for window in (None, (h, w, ws, shift)):
+            ok = ok and _close(ln_rows(x, gamma, beta, 1e-5, window), ln_rows_ref(x, gamma, beta, 1e-5, window),
+                               2e-2, 1e-2)
+        win = torch.randn(rows, c, generator=g).to(dev).to(torch.bfloat16)
+        ok = ok and bool(torch.equal(window_merge_add(win, x, h, w, ws, shift),
+                                     window_merge_add_ref(win, x, h, w, ws, shift)))
+        ok = ok and _close(gelu_rows(x), F.gelu(x.float()), 1e-2, 1e-2)
+    # fc2 of the Swin MLP with bias and the residual stream folded into the GEMM epilogue (N = 96: three 32-column chunks)
+    for (m, n, k) in ((392, 96, 384), (98, 768, 3072)):
+        a = torch.randn(m, k, generator=g).to(dev).to(torch.bfloat16)
+        wt = (torch.randn(n, k, generator=g) / k ** 0.5).to(dev).to(torch.bfloat16)
+        bias = torch.randn(n, generator=g).to(dev)
+        res = torch.randn(m, n, generator=g).to(dev).to(torch.bfloat16)
+        y = gops.gemm(a, wt, bias_n=bias, residual=res)
+        ref = a.float() @ wt.float().t() + bias + res.float()
+        ok = ok and _close(y, ref, 2e-2, 1e-2)
+    return ok
+
+
+_CHECKS = {"wcompose": _check_wcompose, "swin_tokens": _check_swin_tokens}
+
+
+def run_checks_inprocess(device) -> Dict[str, bool]:
+    """Run every family's numerics check on ``device`` in THIS process (what the isolated child of :func:`enabled`
+    executes; also ``FLPR_LAYER_SELFCHECK=inprocess``)."""
+    dev = torch.device(device)
+    out: Dict[str, bool] = {}
+    for family, fn in _CHECKS.items():
+        try:
+            with torch.no_grad(), torch.autocast(device_type="cuda", enabled=False):
+                ok = bool(fn(dev))
+            torch.cuda.synchronize(dev)
+        except Exception as ex:  # noqa: BLE001  (a failed launch must not take the experiment down)
+            _log.error("flpr layer kernels '%s': self-check raised %s: %s", family, type(ex).__name__, ex)
+            ok = False
+        out[family] = ok
+    return out
+
+
+def _cache_path(dev: torch.device) -> str:
+    import hashlib
+    import tempfile
+    from .. import _build
+    try:
+        with open(_build.STAMP) as f:
+            stamp = f.read().strip()[:16]
+    except OSError:
+        stamp = "nostamp"
+    gpu = hashlib.sha1(torch.cuda.get_device_name(dev).encode()).hexdigest()[:8]
+    return os.path.join(tempfile.gettempdir(), f"flpr_layer_selfcheck_{stamp}_{gpu}.json")
+
+
+def _checks_isolated(dev: torch.device) -> Dict[str, bool]:
+    """The checks in a child process with its own CUDA context: a kernel fault there (illegal address = sticky context
+    error) costs the child, not the experiment. The verdict is cached per (library build, GPU model) in the temp dir."""
+    import json
+    import subprocess
+    import sys
+    path = _cache_path(dev)
+    try:
+        with open(path) as f:
+            return {k: bool(v) for k, v in json.load(f).items()}
+    except (OSError, ValueError):
+        pass
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, FLPR_LAYER_SELFCHECK="inprocess",
+               PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    code = ("import json,sys,torch;from flpr_b200.ops import layer as L;"
+            f"torch.cuda.set_device({idx});r=L.run_checks_inprocess('cuda:{idx}');"
+            "print('FLPR_SELFCHECK '+json.dumps(r))")
+    verdict = {k: False for k in _CHECKS}
+    try:
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=300)
+        for line in r.stdout.splitlines():
+            if line.startswith("FLPR_SELFCHECK "):
+                verdict.update({k: bool(v) for k, v in json.loads(line[len("FLPR_SELFCHECK "):]).items()})
+                break
+        else:
+            _log.error("flpr layer kernels: self-check child exited with code %s: %s", r.returncode, r.stderr[-2000:])
+    except Exception as ex:  # noqa: BLE001
+        _log.error("flpr layer kernels: self-check child failed: %s: %s", type(ex).__name__, ex)
+    try:
+        tmp = f"{path}.{os.getpid()}.tmp"
+        with open(tmp, "w") as f:
+            json.dump(verdict, f)
+        os.replace(tmp, path)
+    except OSError:
+        pass
+    return verdict
+
+
+def enabled(family: str, device=None) -> bool:
+    """True when the kernel ``family`` (``wcompose`` / ``swin_tokens``) passed its one-time on-device numerics check
+    (run in an isolated child process, cached per library build + GPU model). ``FLPR_LAYER_OPS=0`` switches every
+    family off, ``FLPR_LAYER_OPS=force`` on without a check; ``FLPR_LAYER_SELFCHECK=inprocess`` runs the checks in the
+    calling process (not during a CUDA-graph capture: the check synchronises)."""
+    hit = _state.get(family)
+    if hit is not None:
+        return hit
+    mode = os.environ.get("FLPR_LAYER_OPS", "1")
+    if mode == "0" or not torch.cuda.is_available():
+        _state[family] = False
+        return False
+    if mode == "force":
+        _state[family] = True
+        return True
+    inproc = os.environ.get("FLPR_LAYER_SELFCHECK", "isolated") == "inprocess"
+    if inproc and torch.cuda.is_current_stream_capturing():
+        return False
+    with _lock:
+        hit = _state.get(family)
+        if hit is not None:
+            return hit
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        verdict = run_checks_inprocess(dev) if inproc else _checks_isolated(dev)
+        for fam in _CHECKS:
+            ok = bool(verdict.get(fam, False))
+            if not ok:
+                _log.error("flpr layer kernels '%s' FAILED their on-device numerics self-check: the PyTorch "
+                           "formulation is used instead (slower, same results)", fam)
+            _state[fam] = ok
+        return _state[family]
+
+
+def status() -> Dict[str, bool]:
+    return dict(_state)

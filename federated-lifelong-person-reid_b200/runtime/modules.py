@@ -95,6 +95,8 @@ class ModelModule(nn.Module):
                 # every Linear of the backbone (qkv / proj / fc1 / fc2 / patch merging) and the classifier on the
                 # tcgen05 GEMM: trainable ones with the optimizer-maintained bf16 copy and direct gradient slots
                 use_tensor_core_linears(self.net, self.arena.shadow_of, self.arena.grad_of)
+                from ..ops import layer as lops
+                lops.enabled("swin_tokens", device)    # one-time on-device self-check of the token kernels, up front
         return self
 
     def autocast(self):

@@ -73,3 +73,184 @@ def check_fast_head_last_stride2(device):
         assert a is not None, name
         cos = F.cosine_similarity(a.float().flatten(), b.flatten(), dim=0).item()
         assert cos > 0.97, (name, cos)
+
+
+# ------------------------------------------------------------------------------------------------ fused weight composition
+def check_compose_function(device, channels_last, use_ref):
+    """``ops.layer.compose_weight`` (kernel or its flat reference) vs autograd through the original expression, on
+    plain and on channels_last (OHWI, the CUDA arena layout) storage."""
+    from flpr_b200.ops import layer as lops
+    g = torch.Generator().manual_seed(3)
+    for shape, kb in (((16, 8, 3, 3), 5), ((24, 40), 3), ((8, 16, 1, 1), 2)):
+        def mk(*s, scale=1.0):
+            return (torch.randn(*s, generator=g) * scale).to(device)
+        aw, sw, stack = mk(*shape, scale=0.01), mk(*shape), mk(*shape, kb)
+        mask, atten = torch.rand(shape[0], generator=g).to(device), mk(kb)
+        if channels_last and len(shape) == 4:
+            aw = aw.contiguous(memory_format=torch.channels_last)
+            sw = sw.contiguous(memory_format=torch.channels_last)
+        stack = lops.stack_aligned(stack, aw)
+        assert lops.stack_phys(stack, aw) is not None
+        thr_aw, thr_mask = 0.008, 0.4
+        outs = []
+        for fused in (False, True):
+            a, m, t = (x.detach().clone().requires_grad_(True) for x in (aw, mask, atten))
+            if channels_last and len(shape) == 4:
+                a = aw.detach().clone(memory_format=torch.channels_last).requires_grad_(True)
+            if fused:
+                th, th16 = lops.compose_weight(a, stack, t, kb, sw, m, thr_aw, thr_mask, True, use_ref)
+                assert th16.dtype == torch.bfloat16 and th16.shape == th.shape and th16.stride() == th.stride()
+                close(th16, th, rtol=1e-2, atol=1e-2 * th.abs().max().item())
+            else:
+                pa = a * (a.abs() > thr_aw).to(a.dtype)
+                pm = m * (m.abs() > thr_mask).to(m.dtype)
+                th = pm.view(-1, *([1] * (len(shape) - 1))) * sw + pa + (stack * t).sum(-1)
+            gy = torch.randn(shape, generator=torch.Generator().manual_seed(9)).to(device)
+            (th * gy).sum().backward()
+            outs.append((th.detach(), a.grad, m.grad, t.grad))
+        for x, y in zip(*outs):
+            close(x, y, rtol=1e-4, atol=1e-5 * y.abs().max().item() + 1e-6)
+    # stacked form without a shared weight (fedstil-atten): theta = aw + stack @ atten, d aw is the incoming gradient
+    aw, stack, atten = mk(10, 6, 3, 3), mk(10, 6, 3, 3, 4), mk(4)
+    if channels_last:
+        aw = aw.contiguous(memory_format=torch.channels_last)
+    stack = lops.stack_aligned(stack, aw)
+    a, t = aw.clone().requires_grad_(True), atten.clone().requires_grad_(True)
+    th, _ = lops.compose_weight(a, stack, t, 4, use_ref=use_ref)
+    th.sum().backward()
+    close(th, aw + (stack * atten).sum(-1), rtol=1e-5, atol=1e-5)
+    close(a.grad, torch.ones_like(aw), rtol=0, atol=0)
+    close(t.grad, stack.reshape(-1, 4).sum(0), rtol=1e-4, atol=1e-4)
+
+
+def check_fedweit_layer_fused(device, channels_last, use_ref):
+    """``Decomposed._theta_fused`` vs the original ``theta`` expression of the same layer (values + gradients), incl.
+    the storage re-alignment of ``sw`` / ``aw_kb`` and logical-shape writes into them afterwards."""
+    import torch.nn as nn
+    from flpr_b200.methods.fedweit import Decomposed
+    torch.manual_seed(5)
+    for src in (nn.Conv2d(16, 32, 3, padding=1, bias=False), nn.Linear(48, 24, bias=False)):
+        layer = Decomposed(src, kb_cnt=3, lambda_l1=0.02, lambda_mask=0.1).to(device)
+        with torch.no_grad():
+            layer.aw_kb.copy_(torch.randn_like(layer.aw_kb) * 0.05)
+            layer.atten.copy_(torch.randn(3) * 0.3)
+            layer.mask.copy_(torch.rand_like(layer.mask))
+        if channels_last and layer.is_conv:
+            layer.aw.data = layer.aw.data.contiguous(memory_format=torch.channels_last)
+        layer.align_storage()
+        layer.train()
+        ref = layer.theta(True) if device == "cpu" else None
+        if ref is None:                                   # on CUDA theta() is the fused path: rebuild the expression
+            pa = layer.aw * (layer.aw.abs() > layer.lambda_l1)
+            pm = layer.mask * (layer.mask.abs() > layer.lambda_mask)
+            ref = layer._bmask(pm, layer.sw) * layer.sw + pa + (layer.aw_kb * layer.atten).sum(-1)
+        gy = torch.randn(ref.shape).to(device)
+        (ref * gy).sum().backward()
+        want = [p.grad.clone() for p in (layer.aw, layer.mask, layer.atten)]
+        for p in (layer.aw, layer.mask, layer.atten):
+            p.grad = None
+        th = layer._theta_fused(True, use_ref)
+        assert th is not None and th._flpr_bf16.dtype == torch.bfloat16
+        (th * gy).sum().backward()
+        close(th, ref, rtol=1e-5, atol=1e-6)
+        for p, w in zip((layer.aw, layer.mask, layer.atten), want):
+            close(p.grad, w, rtol=1e-4, atol=1e-5 * w.abs().max().item() + 1e-7)
+        # logical-shape writes (dispatch) keep working on the re-aligned buffers
+        new_kb = torch.randn(*layer.aw.shape, 3).to(device)
+        with torch.no_grad():
+            layer.aw_kb.copy_(new_kb)
+            layer.reinit()
+        th2 = layer._theta_fused(False, use_ref)
+        close(th2, layer.mask.view(-1, *([1] * (layer.sw.dim() - 1))) * layer.sw + layer.aw + (new_kb * layer.atten).sum(-1),
+              rtol=1e-5, atol=1e-6)
+
+
+def check_atten_composer_storage(device, use_ref):
+    """fedstil-atten ``_Compose`` with the weight in OHWI storage (what the CUDA arena does): ``gw`` re-aligned, logical
+    accessors unchanged, arena-order stack chunks land correctly, fused composition == the matmul formulation."""
+    from flpr_b200.methods.fedstil_atten import _Compose
+    from flpr_b200.ops import layer as lops
+    torch.manual_seed(7)
+    w = torch.randn(12, 8, 3, 3).to(device)
+    comp = _Compose(w, 4, 0.8).to(device)
+    aw = comp.right_inverse(w).contiguous(memory_format=torch.channels_last)          # (1 - a) * w, OHWI storage
+    before = comp._mix(comp.atten.detach(), aw).clone()
+    comp.align_storage(aw)
+    assert lops.stack_phys(comp.gw, aw) is not None and comp.gw.shape == (12, 8, 3, 3, 4)
+    close(comp._mix(comp.atten.detach(), aw), before, rtol=0, atol=0)
+    close(comp.gw[..., 0], w, rtol=0, atol=0)
+    # a dispatched stack arrives in arena (physical) order: [numel, Kmax] rows ordered (o, h, w, i)
+    logical = torch.randn(12, 8, 3, 3, 4).to(device)
+    chunk = logical.permute(0, 2, 3, 1, 4).reshape(-1, 4).contiguous()
+    comp.gw.copy_(chunk.view(12, 3, 3, 8, 4).permute(0, 3, 1, 2, 4))
+    close(comp.gw, logical, rtol=0, atol=0)
+    assert lops.stack_phys(comp.gw, aw) is not None                                   # the copy kept the storage order
+    close(lops.stack_phys(comp.gw, aw), chunk, rtol=0, atol=0)
+    with torch.no_grad():
+        comp.atten.copy_(torch.tensor([0.8, 0.8, 0.1, 0.0]))
+    a = aw.clone(memory_format=torch.channels_last).requires_grad_(True)
+    th, t16 = lops.compose_weight(a, comp.gw, comp.atten, comp.k_max, use_ref=use_ref)
+    ref = (logical * comp.atten.detach()).sum(-1) + aw
+    close(th, ref, rtol=1e-5, atol=1e-5)
+    assert th.stride() == aw.stride() and t16.stride() == aw.stride()
+    gy = torch.randn(12, 8, 3, 3).to(device)
+    (th * gy).sum().backward()
+    close(a.grad, gy, rtol=0, atol=0)
+    close(comp.atten.grad, (logical * gy[..., None]).reshape(-1, 4).sum(0), rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ Swin token kernels
+def check_swin_token_ops(device):
+    """``ln_rows`` (plain / shifted-window destination), ``window_merge_add`` and ``gelu_rows`` against the block's
+    original formulation: ``LayerNorm -> roll -> window_partition`` and ``window_reverse -> roll -> + shortcut``."""
+    from flpr_b200.models.swin import window_partition, window_reverse
+    from flpr_b200.ops import layer as lops
+    g = torch.Generator().manual_seed(21)
+    for (b, h, w, ws, shift, c) in ((2, 14, 14, 7, 3, 96), (1, 8, 4, 4, 0, 192), (3, 7, 7, 7, 0, 768),
+                                    (1, 14, 7, 7, 2, 1536), (2, 8, 8, 4, 1, 384)):
+        x = torch.randn(b * h * w, c, generator=g).to(device).to(torch.bfloat16)
+        gamma = (1 + 0.1 * torch.randn(c, generator=g)).to(device)
+        beta = (0.1 * torch.randn(c, generator=g)).to(device)
+        ln = F.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
+        close(lops.ln_rows(x, gamma, beta, 1e-5), ln, rtol=2e-2, atol=2e-2)
+        img = ln.view(b, h, w, c)
+        if shift:
+            img = torch.roll(img, shifts=(-shift, -shift), dims=(1, 2))
+        want = window_partition(img, ws).reshape(-1, c)
+        close(lops.ln_rows(x, gamma, beta, 1e-5, (h, w, ws, shift)), want, rtol=2e-2, atol=2e-2)
+        win = torch.randn(b * h * w, c, generator=g).to(device).to(torch.bfloat16)
+        back = window_reverse(win.view(-1, ws * ws, c), ws, h, w)
+        if shift:
+            back = torch.roll(back, shifts=(shift, shift), dims=(1, 2))
+        want = (x.float() + back.reshape(-1, c).float()).to(torch.bfloat16)
+        got = lops.window_merge_add(win, x, h, w, ws, shift)
+        assert torch.equal(got, want)
+        close(lops.gelu_rows(x), F.gelu(x.float()), rtol=1e-2, atol=1e-2)
+
+
+def check_swin_block_fused(device):
+    """``SwinTransformerBlock._forward_fused`` (frozen bf16 path) vs the plain fp32 block."""
+    import copy
+    from flpr_b200.models.swin import SwinTransformerBlock
+    torch.manual_seed(3)
+    for (dim, res, heads, ws, shift) in ((96, (14, 14), 3, 7, 3), (192, (14, 14), 6, 7, 0), (384, (7, 7), 12, 7, 0)):
+        blk = SwinTransformerBlock(dim, res, heads, ws, shift).to(device).eval()
+        for p in blk.parameters():
+            p.requires_grad_(False)
+        with torch.no_grad():
+            for p in blk.parameters():
+                if p.dim() == 1:
+                    p.add_(torch.randn_like(p) * 0.05)
+        x = torch.randn(2, res[0] * res[1], dim).to(device)
+        with torch.no_grad():
+            ref = blk(x)
+            fast = copy.deepcopy(blk)
+            if device == "cpu":
+                fast = fast.to(torch.bfloat16)
+            else:
+                from flpr_b200.models.swin import use_tensor_core_linears
+                use_tensor_core_linears(fast)
+                assert fast._fused_ok(x.to(torch.bfloat16)), "fused path not taken"
+            out = fast._forward_fused(x.to(torch.bfloat16))
+        assert out.dtype == torch.bfloat16 and out.shape == ref.shape
+        close(out, ref, rtol=5e-2, atol=5e-2 * ref.abs().max().item())

@@ -13,3 +13,25 @@ def test_conv_stride2_matches_conv2d(k, n, h, w, cin, cout):
 
 def test_fast_head_last_stride2():
     L.check_fast_head_last_stride2("cpu")
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_compose_function_reference_path(channels_last):
+    L.check_compose_function("cpu", channels_last, use_ref=True)
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_fedweit_layer_fused_theta(channels_last):
+    L.check_fedweit_layer_fused("cpu", channels_last, use_ref=True)
+
+
+def test_atten_composer_storage_alignment():
+    L.check_atten_composer_storage("cpu", use_ref=True)
+
+
+def test_swin_token_ops_reference_index_maths():
+    L.check_swin_token_ops("cpu")
+
+
+def test_swin_block_fused_forward():
+    L.check_swin_block_fused("cpu")
