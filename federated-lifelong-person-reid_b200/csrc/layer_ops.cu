@@ -11,6 +11,8 @@
 //                                 (models/swin_transformer.py:358-380: norm1 -> roll -> window_partition in one pass).
 //   window_merge_add              window_reverse -> roll back -> + shortcut (models/swin_transformer.py:383-391) in one pass.
 //   gelu_rows                     exact (erf) GELU over bf16 rows (models/swin_transformer.py:118-140, frozen stages).
+//   apply_global                  receiving end of the FedAvg-family dispatch (methods/fedavg.py:413-430,
+//                                 fedprox.py:351-364): master <- global, bf16 copy, FedProx anchor snapshot, one pass.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -256,6 +258,30 @@ __global__ void __launch_bounds__(256) gelu_rows_kernel(const __nv_bfloat16* __r
   }
 }
 
+// C2 tail on the receiving client: master <- aggregated parameters, bf16 compute copy refreshed and the FedProx anchor
+// snapshotted in the same pass (snap_mode 1: the weights being replaced = the reference's order of operations,
+// methods/fedprox.py:351-364; 2: the incoming global model = textbook FedProx). 4 floats per thread.
+__global__ void __launch_bounds__(256) apply_global_kernel(const float4* __restrict__ flat, float4* __restrict__ master,
+                                                           uint2* __restrict__ shadow, float4* __restrict__ p_old,
+                                                           int snap_mode, long long n4) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = flat[i];
+    if (p_old != nullptr) {
+      if (snap_mode == 1) p_old[i] = master[i];
+      else if (snap_mode == 2) p_old[i] = v;
+    }
+    master[i] = v;
+    if (shadow != nullptr) {
+      uint2 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+      h[0] = __floats2bfloat162_rn(v.x, v.y);
+      h[1] = __floats2bfloat162_rn(v.z, v.w);
+      shadow[i] = u;
+    }
+  }
+}
+
 static int grid_for(long long work_items, int threads) {
   long long g = (work_items + threads - 1) / threads;
   const long long cap = 148LL * 16;
@@ -271,6 +297,20 @@ using namespace flpr;
 extern "C" {
 
 int flpr_wcompose_max_k() { return WC_MAXK; }
+
+// n must be a multiple of 4 and every pointer 16-byte aligned (8 for shadow): arena prefixes are.
+int flpr_apply_global(const float* flat, float* master, void* shadow, float* p_old, int snap_mode, long long n,
+                      cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (n % 4) return -25;
+  if (((uintptr_t)flat | (uintptr_t)master | (uintptr_t)p_old) & 15 || ((uintptr_t)shadow & 7)) return -26;
+  bind_device_of(master);
+  apply_global_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(flat),
+                                                            reinterpret_cast<float4*>(master),
+                                                            reinterpret_cast<uint2*>(shadow),
+                                                            reinterpret_cast<float4*>(p_old), snap_mode, n / 4);
+  return (int)cudaGetLastError();
+}
 
 int flpr_wcompose_fwd(const float* aw, const float* stack, const float* atten, int kb, int ks, const float* sw,
                       const float* mask, long long row_len, float thr_aw, float thr_mask, int prune, float* out_f32,

@@ -18,6 +18,7 @@ from typing import Any, Dict, List, Optional
 
 import torch
 
+from ..ops import layer as lops
 from ..runtime.modules import ClientModule, ModelModule, ServerModule
 
 
@@ -47,6 +48,8 @@ class FedClient(ClientModule):
     def declare_buffers(cls, comm, model, token_numel: int = 0) -> None:
         """Symmetric allocations – executed identically on every rank (also ranks hosting no client)."""
         n = cls._upload_numel(model)
+        if model.device.type == "cuda":
+            lops.enabled("apply", model.device)           # one-time isolated self-check of the dispatch kernel, up front
         comm.alloc_client_buffer("up", n)
         comm.alloc_client_buffer("cnt", 4)
         comm.alloc_rank_buffer("glob", n)
@@ -82,10 +85,22 @@ class FedClient(ClientModule):
     def get_integrated_state(self, **kwargs) -> Dict:
         return {"train_cnt": self.train_cnt, self.integrated_key: self._full_state()}
 
-    def apply_global(self, flat: torch.Tensor) -> None:
-        """Overwrite the upload-prefix of the arena with ``flat`` (the aggregated parameters)."""
+    def apply_global(self, flat: torch.Tensor, p_old: Optional[torch.Tensor] = None, snap_mode: int = 0) -> None:
+        """Overwrite the upload-prefix of the arena with ``flat`` (the aggregated parameters). On CUDA one kernel writes
+        the fp32 master, the bf16 compute copy and - FedProx - the proximal anchor ``p_old`` (``snap_mode`` 1: the
+        weights being replaced, 2: the incoming ones) in the same pass (``ops.layer.apply_global``)."""
         a = self.model.arena
-        a.master[:flat.numel()].copy_(flat)
+        n = flat.numel()
+        if flat.is_cuda and lops.enabled("apply", flat.device):
+            lops.apply_global(flat, a.master, a.shadow, p_old, snap_mode)
+            if n < a.numel and p_old is not None and snap_mode:
+                p_old[n:].copy_(a.master[n:])            # (the tail of the arena is not part of the exchange)
+            return
+        if p_old is not None and snap_mode == 1:
+            p_old.copy_(a.master)
+        a.master[:n].copy_(flat)
+        if p_old is not None and snap_mode == 2:
+            p_old.copy_(a.master)
         a.refresh_shadow()
 
     def update_by_incremental_state(self, state: Dict, **kwargs) -> Any:

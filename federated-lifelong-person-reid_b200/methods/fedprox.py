@@ -65,6 +65,14 @@ class Client(FedClient):
             self.model.remember_params()                  # previous *local* weights (reference behaviour)
 
     def update_by_incremental_state(self, state, **kwargs):
+        if "_flat" in state:
+            # device-resident dispatch: global -> master, bf16 copy and the proximal anchor in ONE pass (C2 fusion);
+            # anchor = the weights being replaced (reference order of operations) or the incoming global model
+            self.train_cnt = self.test_cnt = 0
+            self.apply_global(state["_flat"], self.model.p_old, 1 if getattr(self, "reference_compat", True) else 2)
+            self.model.has_old = True
+            self.logger.info("Update model succeed by incremental state from server.")
+            return
         super().update_by_incremental_state(state, **kwargs)
         if not getattr(self, "reference_compat", True):
             self.model.remember_params()                  # textbook FedProx: anchor = incoming global model

@@ -38,6 +38,7 @@ def _declare(lib) -> None:
         "flpr_ln_rows": [P, P, P, P, L, I, Fl, I, I, I, I, I, P],
         "flpr_window_merge_add": [P, P, P, L, I, I, I, I, I, P],
         "flpr_gelu_rows": [P, P, L, P],
+        "flpr_apply_global": [P, P, P, P, I, L, P],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -341,6 +342,37 @@ def gelu_rows(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ===================================================================================================== dispatch apply
+def apply_global_ref(flat, master, shadow, p_old, snap_mode):
+    n = flat.numel()
+    if p_old is not None and snap_mode == 1:
+        p_old[:n].copy_(master[:n])
+    master[:n].copy_(flat)
+    if p_old is not None and snap_mode == 2:
+        p_old[:n].copy_(flat)
+    if shadow is not None:
+        shadow[:n].copy_(flat)
+
+
+def apply_global(flat: torch.Tensor, master: torch.Tensor, shadow: Optional[torch.Tensor] = None,
+                 p_old: Optional[torch.Tensor] = None, snap_mode: int = 0) -> None:
+    """Receiving end of a FedAvg-family dispatch: ``master[:n] <- flat`` with the bf16 compute copy refreshed and the
+    FedProx anchor snapshotted in the same pass (``snap_mode`` 1: the weights being replaced, 2: the incoming ones)."""
+    n = flat.numel()
+    ok = flat.is_cuda and n % 4 == 0 and flat.dtype == torch.float32 and flat.is_contiguous() and \
+        all(t is None or (t.is_contiguous() and t.data_ptr() % 16 == 0) for t in (flat, master, shadow, p_old))
+    if not ok:
+        return apply_global_ref(flat, master, shadow, p_old, snap_mode)
+    lib = _lib()
+    assert master.dtype == torch.float32 and master.numel() >= n
+    assert shadow is None or (shadow.dtype == torch.bfloat16 and shadow.numel() >= n)
+    assert p_old is None or (p_old.dtype == torch.float32 and p_old.numel() >= n)
+    rc = lib.flpr_apply_global(native.ptr(flat), native.ptr(master), native.ptr(shadow),
+                               native.ptr(p_old if snap_mode else None), int(snap_mode), n, native.stream(flat.device))
+    native.check(rc, "flpr_apply_global")
+    native.count_launch()
+
+
 # ===================================================================================================== self-checks
 _state: Dict[str, bool] = {}
 _lock = threading.Lock()
@@ -405,7 +437,25 @@ def _check_swin_tokens(dev) -> bool:
     return ok
 
 
-_CHECKS = {"wcompose": _check_wcompose, "swin_tokens": _check_swin_tokens}
+def _check_apply(dev) -> bool:
+    g = torch.Generator(device="cpu").manual_seed(13)
+    ok = True
+    for n, total, mode, with_shadow in ((4096, 5000, 1, True), (1 << 20, 1 << 20, 2, True), (64, 64, 0, False),
+                                        (12, 16, 1, False)):
+        flat = torch.randn(n, generator=g).to(dev)
+        m0 = torch.randn(total, generator=g).to(dev)
+        res = []
+        for fn in (apply_global_ref, apply_global):
+            master, p_old = m0.clone(), torch.zeros(total, device=dev)
+            shadow = torch.zeros(total, dtype=torch.bfloat16, device=dev) if with_shadow else None
+            fn(flat, master, shadow, p_old if mode else None, mode)
+            res.append((master, p_old, shadow))
+        for a, b in zip(*res):
+            ok = ok and (a is None) == (b is None) and (a is None or bool(torch.equal(a, b)))
+    return ok
+
+
+_CHECKS = {"wcompose": _check_wcompose, "swin_tokens": _check_swin_tokens, "apply": _check_apply}
 
 
 def run_checks_inprocess(device) -> Dict[str, bool]:

@@ -254,3 +254,28 @@ def check_swin_block_fused(device):
             out = fast._forward_fused(x.to(torch.bfloat16))
         assert out.dtype == torch.bfloat16 and out.shape == ref.shape
         close(out, ref, rtol=5e-2, atol=5e-2 * ref.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------------------ dispatch apply
+def check_apply_global(device):
+    """``ops.layer.apply_global`` (master <- global + bf16 copy + FedProx anchor in one pass) vs the three copies."""
+    from flpr_b200.ops import layer as lops
+    g = torch.Generator().manual_seed(31)
+    for n, total, mode in ((4096, 5000, 1), (1 << 18, 1 << 18, 2), (64, 64, 0)):
+        flat = torch.randn(n, generator=g).to(device)
+        m0 = torch.randn(total, generator=g).to(device)
+        res = []
+        for fn in (lops.apply_global_ref, lops.apply_global):
+            master, p_old = m0.clone(), torch.zeros(total).to(device)
+            shadow = torch.zeros(total, dtype=torch.bfloat16).to(device)
+            fn(flat, master, shadow, p_old if mode else None, mode)
+            res.append((master, p_old, shadow))
+        for a, b in zip(*res):
+            assert torch.equal(a, b)
+        master, p_old, shadow = res[1]
+        assert torch.equal(master[:n], flat) and torch.equal(master[n:], m0[n:])
+        assert torch.equal(shadow[:n], flat.to(torch.bfloat16))
+        if mode == 1:
+            assert torch.equal(p_old[:n], m0[:n])
+        elif mode == 2:
+            assert torch.equal(p_old[:n], flat)

@@ -35,3 +35,7 @@ def test_swin_token_ops_reference_index_maths():
 
 def test_swin_block_fused_forward():
     L.check_swin_block_fused("cpu")
+
+
+def test_apply_global_reference_semantics():
+    L.check_apply_global("cpu")

@@ -16,6 +16,7 @@ def test_layer_kernel_self_checks_pass():
     from flpr_b200.ops import layer as lops
     assert lops.enabled("wcompose", "cuda:0"), "compose kernels failed their numerics self-check"
     assert lops.enabled("swin_tokens", "cuda:0"), "Swin token kernels failed their numerics self-check"
+    assert lops.enabled("apply", "cuda:0"), "dispatch-apply kernel failed its numerics self-check"
 
 
 @pytest.mark.parametrize("k,n,h,w,cin,cout", [(3, 8, 16, 8, 512, 512), (1, 8, 16, 8, 1024, 2048), (3, 4, 32, 16, 128, 256),
@@ -41,6 +42,10 @@ def test_fedweit_layer_fused_theta_native(channels_last):
 
 def test_atten_composer_native():
     L.check_atten_composer_storage("cuda", use_ref=False)
+
+
+def test_apply_global_kernel():
+    L.check_apply_global("cuda")
 
 
 def test_swin_token_kernels():
