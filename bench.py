@@ -50,6 +50,16 @@ def metric_name(a) -> str:
             f"{a.height}x{a.width})")
 
 
+def _layer_kernel_status():
+    """Which ``csrc/layer_ops.cu`` families (weight composition, Swin token kernels, dispatch apply) were consulted by
+    this run and whether they passed their on-device self-check (empty: the method / model uses none of them)."""
+    try:
+        from flpr_b200.ops import layer as lops
+        return lops.status()
+    except Exception:  # noqa: BLE001
+        return {}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -364,7 +374,8 @@ def run_flpr(a, impl: str) -> dict:
         "notes": {"parallelism": f"client-per-rank x{a.gpus} (8 clients round-robin, {a.parallel} concurrent client "
                                  f"streams per GPU)",
                   "semantics": "reference_compat (trained L1 anchors, per-epoch lr reset, exemplar relabelling)",
-                  "timing": "CUDA events on the launching stream, max over ranks"},
+                  "timing": "CUDA events on the launching stream, max over ranks",
+                  "layer_kernels": _layer_kernel_status()},
         "convergence": conv,
         "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "ms_per_step": round(e2e_ms / a.steps, 3),
                 "h2d_bytes_per_step": int(h2d / a.steps),

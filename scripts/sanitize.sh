@@ -1,6 +1,6 @@
 #!/bin/bash
 # compute-sanitizer jobs for the hand-written kernels. Run on a GPU box:
-#   gpurun -- 'bash scripts/sanitize.sh memcheck'      (or racecheck / synccheck / initcheck / all)
+#   gpurun -- 'bash scripts/sanitize.sh memcheck'      (or racecheck / synccheck / initcheck / all / late)
 # The selection keeps the instrumented run short; the full suite is `pytest tests/test_gpu_kernels.py`.
 #
 # racecheck / synccheck target the kernels whose correctness rests on shared-memory hand-offs and barriers:
@@ -20,6 +20,20 @@ run() {
   echo "sanitizer ${tool} exit: $?"
   tail -5 "gpurun_out/sanitizer_${tool}.log"
 }
+# layer_ops.cu (compose / Swin token / dispatch-apply kernels): block reductions through shared memory + warp shuffles
+run_late() {
+  local tool=$1
+  FLPR_LAYER_SELFCHECK=inprocess timeout 1500 compute-sanitizer --tool "$tool" --error-exitcode 9 \
+    --log-file "gpurun_out/sanitizer_${tool}_layer_ops.log" \
+    python -m pytest tests/test_zz_gpu_late.py -q -x --timeout 1200 -p no:cacheprovider \
+      -k "compose_kernels or swin_token_kernels or apply_global_kernel" 2>&1 | tail -4
+  echo "sanitizer ${tool} (layer_ops) exit: $?"
+  tail -5 "gpurun_out/sanitizer_${tool}_layer_ops.log"
+}
+if [ "$TOOL" = "late" ]; then
+  for t in memcheck racecheck synccheck; do run_late $t; done
+  exit 0
+fi
 if [ "$TOOL" = "all" ]; then
   for t in memcheck racecheck synccheck; do run $t; done
 else
