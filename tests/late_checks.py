@@ -279,3 +279,53 @@ def check_apply_global(device):
             assert torch.equal(p_old[:n], m0[:n])
         elif mode == 2:
             assert torch.equal(p_old[:n], flat)
+
+
+# ------------------------------------------------------------------------------------------------ convergence
+def run_tiny_rounds(tmp: str, method: str, device: str, dtype: str, rounds: int = 10):
+    """One tiny deterministic experiment (every split fits one batch, no augmentation, SGD, shared initial weights):
+    returns ``{client: [tr_loss of round 1..rounds]}``."""
+    import os
+    from helpers import tiny_common, tiny_experiment
+    from flpr_b200.data.synthetic import synthetic_source_factory
+    from flpr_b200.models import nets
+    from flpr_b200.runtime.experiment import ExperimentStage
+    os.makedirs(tmp, exist_ok=True)
+    common = tiny_common(tmp, device=device)
+    d = common["defaults"]
+    d["exp_opts"].update(comm_rounds=rounds, val_interval=rounds)
+    d["optimizer_opts"] = {"name": "sgd", "lr": 0.01, "momentum": 0.9, "weight_decay": 1e-4}
+    d["task_opts"]["train_epochs"] = 2
+    d["task_opts"]["augment_opts"].update(level="none", img_size=[64, 32])
+    d["task_opts"]["loader_opts"]["batch_size"] = 64
+    torch.manual_seed(1234)
+    init = os.path.join(tmp, "init.pt")
+    torch.save({"*": nets["resnet18"](num_classes=8000, last_stride=1, neck="bnneck").state_dict()}, init)
+    cfg = tiny_experiment(common, method, engine_opts={"compute_dtype": dtype, "init_state": init,
+                                                       "val_at_round0": False, "client_threads": False})
+    with ExperimentStage(common, [cfg], source_factory=synthetic_source_factory(
+            num_ids=4, train_per_id=4, size=(64, 32))) as stage:
+        log = stage.run_experiment(cfg)
+    out = {}
+    for client, per_round in log.records["data"].items():
+        rows = sorted(((int(r), tasks) for r, tasks in per_round.items()), key=lambda x: x[0])
+        out[client] = [float(next(v["tr_loss"] for v in tasks.values() if "tr_loss" in v)) for _, tasks in rows
+                       if any("tr_loss" in v for v in tasks.values())]
+    return out
+
+
+def check_bf16_engine_tracks_fp32(tmp: str, method: str, device: str, per_round: float = 0.10, mean_tol: float = 0.05,
+                                  rounds: int = 10):
+    """The bf16 engine on ``device`` (native kernels) follows the fp32 CPU engine round by round on the same
+    experiment: a wrong gradient / optimizer / aggregation kernel shows up as a diverging loss curve within a few
+    rounds, which the finite-metric assertions of the e2e tests cannot see."""
+    import os
+    ref = run_tiny_rounds(os.path.join(tmp, "fp32"), method, "cpu", "fp32", rounds)
+    got = run_tiny_rounds(os.path.join(tmp, "dev"), method, device, "bf16" if device != "cpu" else "fp32", rounds)
+    assert ref.keys() == got.keys() and all(len(v) == rounds for v in ref.values()), (ref, got)
+    for client in ref:
+        a, b = torch.tensor(ref[client]), torch.tensor(got[client])
+        assert a.shape == b.shape, (client, ref[client], got[client])
+        rel = (a - b).abs() / a.abs().clamp_min(1e-6)
+        assert float(rel.max()) <= per_round and float(rel.mean()) <= mean_tol, (method, client, ref[client], got[client])
+    return ref, got

@@ -39,3 +39,9 @@ def test_swin_block_fused_forward():
 
 def test_apply_global_reference_semantics():
     L.check_apply_global("cpu")
+
+
+def test_convergence_harness_is_deterministic_on_cpu(tmp_path):
+    """Same engine twice (fp32 CPU): the curves the GPU convergence test compares must be reproducible."""
+    ref, got = L.check_bf16_engine_tracks_fp32(str(tmp_path), "fedstil", "cpu", per_round=1e-5, mean_tol=1e-5, rounds=3)
+    assert all(len(v) == 3 for v in ref.values())

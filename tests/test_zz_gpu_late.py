@@ -86,3 +86,10 @@ def test_fedweit_and_atten_steps_use_the_compose_kernel(tmp_path):
             assert log is not None
     finally:
         lops.wcompose_fwd = orig
+
+
+@pytest.mark.parametrize("method", ["fedavg", "fedstil"])
+def test_bf16_gpu_engine_tracks_fp32_cpu_engine(tmp_path, method):
+    """Ten rounds of the same deterministic tiny experiment on the fp32 CPU engine and on the bf16 GPU engine: per-round
+    training loss within 10 % (5 % on average)."""
+    L.check_bf16_engine_tracks_fp32(str(tmp_path), method, "cuda:0")
