@@ -458,16 +458,18 @@ def _check_apply(dev) -> bool:
 _CHECKS = {"wcompose": _check_wcompose, "swin_tokens": _check_swin_tokens, "apply": _check_apply}
 
 
-def run_checks_inprocess(device) -> Dict[str, bool]:
-    """Run every family's numerics check on ``device`` in THIS process (what the isolated child of :func:`enabled`
-    executes; also ``FLPR_LAYER_SELFCHECK=inprocess``)."""
+def run_checks_inprocess(device, families=None) -> Dict[str, bool]:
+    """Run the numerics checks of ``families`` (default: all) on ``device`` in THIS process (what the isolated children
+    of :func:`enabled` execute; also ``FLPR_LAYER_SELFCHECK=inprocess``)."""
     dev = torch.device(device)
     out: Dict[str, bool] = {}
-    for family, fn in _CHECKS.items():
+    for family in (families or list(_CHECKS)):
+        fn = _CHECKS[family]
         try:
-            with torch.no_grad(), torch.autocast(device_type="cuda", enabled=False):
+            with torch.no_grad(), torch.autocast(device_type=dev.type, enabled=False):
                 ok = bool(fn(dev))
-            torch.cuda.synchronize(dev)
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
         except Exception as ex:  # noqa: BLE001  (a failed launch must not take the experiment down)
             _log.error("flpr layer kernels '%s': self-check raised %s: %s", family, type(ex).__name__, ex)
             ok = False
@@ -484,13 +486,15 @@ def _cache_path(dev: torch.device) -> str:
             stamp = f.read().strip()[:16]
     except OSError:
         stamp = "nostamp"
-    gpu = hashlib.sha1(torch.cuda.get_device_name(dev).encode()).hexdigest()[:8]
+    name = torch.cuda.get_device_name(dev) if dev.type == "cuda" else "cpu"      # (cpu: plumbing tests only)
+    gpu = hashlib.sha1(name.encode()).hexdigest()[:8]
     return os.path.join(tempfile.gettempdir(), f"flpr_layer_selfcheck_{stamp}_{gpu}.json")
 
 
 def _checks_isolated(dev: torch.device) -> Dict[str, bool]:
-    """The checks in a child process with its own CUDA context: a kernel fault there (illegal address = sticky context
-    error) costs the child, not the experiment. The verdict is cached per (library build, GPU model) in the temp dir."""
+    """The checks in child processes with their own CUDA contexts: a kernel fault there (illegal address = sticky
+    context error) costs the child, not the experiment. The verdict is cached per (library build, GPU model) in the
+    temp dir."""
     import json
     import subprocess
     import sys
@@ -505,21 +509,38 @@ def _checks_isolated(dev: torch.device) -> Dict[str, bool]:
                PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
         env.pop(k, None)
-    idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    code = ("import json,sys,torch;from flpr_b200.ops import layer as L;"
-            f"torch.cuda.set_device({idx});r=L.run_checks_inprocess('cuda:{idx}');"
-            "print('FLPR_SELFCHECK '+json.dumps(r))")
+    if dev.type == "cuda":
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        dev_s, pre = f"cuda:{idx}", f"torch.cuda.set_device({idx});"
+    else:
+        dev_s, pre = "cpu", ""
     verdict = {k: False for k in _CHECKS}
+    procs = {}
     try:
-        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=300)
-        for line in r.stdout.splitlines():
-            if line.startswith("FLPR_SELFCHECK "):
-                verdict.update({k: bool(v) for k, v in json.loads(line[len("FLPR_SELFCHECK "):]).items()})
-                break
-        else:
-            _log.error("flpr layer kernels: self-check child exited with code %s: %s", r.returncode, r.stderr[-2000:])
+        for fam in _CHECKS:                      # one child per family, side by side: a fault in one family's kernels
+            code = ("import json,sys,torch;from flpr_b200.ops import layer as L;"      # (dead context) cannot fail another
+                    f"{pre}r=L.run_checks_inprocess('{dev_s}',['{fam}']);"
+                    "print('FLPR_SELFCHECK '+json.dumps(r))")
+            procs[fam] = subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                          text=True, env=env, cwd=root)
+        for fam, pr in procs.items():
+            try:
+                so, se = pr.communicate(timeout=300)
+            except subprocess.TimeoutExpired:
+                pr.kill()
+                so, se = pr.communicate()
+            for line in so.splitlines():
+                if line.startswith("FLPR_SELFCHECK "):
+                    verdict[fam] = bool(json.loads(line[len("FLPR_SELFCHECK "):]).get(fam, False))
+                    break
+            else:
+                _log.error("flpr layer kernels '%s': self-check child exited with code %s: %s", fam, pr.returncode,
+                           (se or "")[-2000:])
     except Exception as ex:  # noqa: BLE001
-        _log.error("flpr layer kernels: self-check child failed: %s: %s", type(ex).__name__, ex)
+        _log.error("flpr layer kernels: self-check children failed: %s: %s", type(ex).__name__, ex)
+        for pr in procs.values():
+            if pr.poll() is None:
+                pr.kill()
     try:
         tmp = f"{path}.{os.getpid()}.tmp"
         with open(tmp, "w") as f:

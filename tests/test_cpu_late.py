@@ -1,4 +1,6 @@
 """CPU runs of ``late_checks`` (reference paths of the ops: validates the autograd glue, layouts and index maths)."""
+import os
+
 import pytest
 
 import late_checks as L
@@ -45,3 +47,20 @@ def test_convergence_harness_is_deterministic_on_cpu(tmp_path):
     """Same engine twice (fp32 CPU): the curves the GPU convergence test compares must be reproducible."""
     ref, got = L.check_bf16_engine_tracks_fp32(str(tmp_path), "fedstil", "cpu", per_round=1e-5, mean_tol=1e-5, rounds=3)
     assert all(len(v) == 3 for v in ref.values())
+
+
+def test_selfcheck_children_protocol(tmp_path, monkeypatch):
+    """The isolated self-check plumbing (one child process per kernel family, verdict parsed from its stdout, cached in
+    a file) - exercised on the CPU reference paths, where every check must pass."""
+    import tempfile
+    import torch
+    from flpr_b200.ops import layer as lops
+    monkeypatch.setattr(tempfile, "tempdir", str(tmp_path))
+    verdict = lops._checks_isolated(torch.device("cpu"))
+    assert verdict == {"wcompose": True, "swin_tokens": True, "apply": True}, verdict
+    cached = [f for f in os.listdir(tmp_path) if f.startswith("flpr_layer_selfcheck_")]
+    assert len(cached) == 1
+    with open(os.path.join(tmp_path, cached[0]), "w") as f:          # the cache is what the next process reads
+        f.write('{"wcompose": true, "swin_tokens": false, "apply": true}')
+    assert lops._checks_isolated(torch.device("cpu"))["swin_tokens"] is False
+    assert lops.run_checks_inprocess("cpu", ["apply"]) == {"apply": True}
