@@ -235,6 +235,7 @@ def run_flpr(a, impl: str) -> dict:
     from flpr_b200.runtime.experiment import ExperimentStage
     from flpr_b200.runtime.explog import ExperimentLog
     from flpr_b200.utils.misc import DeviceTimer, same_seeds
+    from flpr_b200.utils.trace import d2h_bytes
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     common, exp = build_config(a, impl, world)
@@ -321,6 +322,7 @@ def run_flpr(a, impl: str) -> dict:
         # ---- end-to-end region: K more rounds by wall clock through the public API ---------------------------------
         sync()
         ckpt0 = store.bytes_written
+        d2h0 = d2h_bytes()
         t0 = time.perf_counter()
         for _ in range(a.steps):
             r += 1
@@ -328,10 +330,12 @@ def run_flpr(a, impl: str) -> dict:
         store.flush()                           # every checkpoint of these rounds is on disk before the clock stops
         sync()
         e2e_ms = (time.perf_counter() - t0) * 1e3
+        d2h = float(d2h_bytes() - d2h0)         # bytes of the device tensors the rounds read back (losses, hit counts,
+                                                # herding group sizes, the logged mixing matrix): counted where copied
         ckpt_bytes = float(store.bytes_written - ckpt0)          # snapshot bytes that reached the writers (flushed)
         after_round()
 
-        red = torch.tensor([dev_ms, e2e_ms, float(launches), float(h2d1 - h2d0), ckpt_bytes], dtype=torch.float64,
+        red = torch.tensor([dev_ms, e2e_ms, float(launches), float(h2d1 - h2d0), ckpt_bytes, d2h], dtype=torch.float64,
                            device=dev if cuda else "cpu")
         if world > 1:
             mx = red.clone()
@@ -339,7 +343,7 @@ def run_flpr(a, impl: str) -> dict:
             sm = red.clone()
             dist.all_reduce(sm, op=dist.ReduceOp.SUM)
             dev_ms, e2e_ms = mx[0].item(), mx[1].item()
-            launches, h2d, ckpt_bytes = int(sm[2].item()), sm[3].item(), sm[4].item()
+            launches, h2d, ckpt_bytes, d2h = int(sm[2].item()), sm[3].item(), sm[4].item(), sm[5].item()
         else:
             h2d = float(h2d1 - h2d0)
         phases = {k: round(sum(v[-2 * a.steps:]) / max(len(v[-2 * a.steps:]), 1), 3) for k, v in timer.flush().items()}
@@ -379,7 +383,7 @@ def run_flpr(a, impl: str) -> dict:
         "convergence": conv,
         "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "ms_per_step": round(e2e_ms / a.steps, 3),
                 "h2d_bytes_per_step": int(h2d / a.steps),
-                "d2h_bytes_per_step": int(a.clients * a.epochs * 4 * 8),
+                "d2h_bytes_per_step": int(d2h / a.steps),
                 "checkpoint_bytes_per_step": int(ckpt_bytes / a.steps)},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -30,6 +30,8 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
+
+from ..utils.trace import host_list
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -280,7 +282,7 @@ class Model(ModelModule):
         sel_pids = pids[rows]
         order = torch.argsort(sel_pids, stable=True)
         upid, counts = torch.unique_consecutive(sel_pids[order], return_counts=True)
-        upid_l, counts_l = upid.tolist(), counts.tolist()                    # the second (and last) host sync
+        upid_l, counts_l = host_list(upid), host_list(counts)                # the second (and last) host sync
         P, nmax = len(upid_l), max(counts_l)
         starts = torch.cumsum(counts, 0) - counts
         ar = torch.arange(nmax, device=dev)
@@ -399,7 +401,7 @@ def herding_select(feats: torch.Tensor, m: int) -> List[int]:
         i = torch.argmin(sq - 2 * (f @ c))
         picks[t] = i
         S = S + f[i]
-    return picks.tolist()
+    return host_list(picks)
 
 
 def group_matrix(groups: List[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -528,7 +530,7 @@ class Operator(OperatorModule):
             data_cnt += len(idx)
         self._bn_counters(model, on=True, add=n_batches)
         src = acc if self._ce_acc is None else self._ce_acc.double()
-        vals = torch.cat([src, self.optimizer.stats.double()]).tolist()      # single host sync per epoch
+        vals = host_list(torch.cat([src, self.optimizer.stats.double()]))    # single host sync per epoch
         loss_sum, hits, _, l1_sum = vals
         train_loss = (loss_sum + model.lambda_l1 * l1_sum) / max(n_batches, 1)
         if self.scheduler:
@@ -869,7 +871,7 @@ class Server(ServerModule):
             cols = torch.tensor([col[self.client_ids[c]] for c in order], device=dev)
             rows[:, cols] = W.to(dev)
             if self.logger.enabled_for_info():
-                flat = W.tolist()                                 # ONE host sync for the whole mixing matrix
+                flat = host_list(W)                               # ONE host sync for the whole mixing matrix
                 for name, wr in zip(recv, flat):
                     for c_name, wv in zip(order, wr):
                         self.logger.info(f"Relevant ratio between {name} and {c_name}: {wv:.4f}")

@@ -20,6 +20,7 @@ import torch.nn.functional as F
 
 from ..evaluation import evaluate
 from ..utils.logger import Logger
+from ..utils.trace import host_list
 from .arena import ArenaOptimizer, ParamArena, StepLR
 from .checkpoint import CheckpointStore
 
@@ -250,7 +251,7 @@ class OperatorModule:
     def _step_totals(self) -> Tuple[float, float]:
         """(loss sum, top-1 hits) accumulated by the steps since the accumulators were last zeroed: ONE host sync."""
         src = self._acc if self._ce_acc is None else self._ce_acc.double()
-        loss_sum, hits = src.tolist()
+        loss_sum, hits = host_list(src)
         return loss_sum, hits
 
     def _zero_step_totals(self) -> None:
@@ -306,7 +307,7 @@ class OperatorModule:
                 acc[1] += (out["score"].argmax(dim=1) == target).sum()
             data_cnt += len(data)
             batch_cnt += 1
-        loss_sum, hits = acc.tolist()
+        loss_sum, hits = host_list(acc)
         return {"accuracy": hits / max(data_cnt, 1), "loss": loss_sum / max(batch_cnt, 1), "batch_count": batch_cnt,
                 "data_count": data_cnt}
 
