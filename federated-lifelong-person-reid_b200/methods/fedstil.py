@@ -30,12 +30,11 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
-
-from ..utils.trace import host_list
 import torch.nn as nn
 import torch.nn.functional as F
 
 from ..criterions import kl_distance
+from ..utils.trace import host_list
 from ..runtime.modules import ClientModule, ModelModule, OperatorModule, ServerModule
 
 
