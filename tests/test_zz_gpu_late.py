@@ -93,3 +93,18 @@ def test_bf16_gpu_engine_tracks_fp32_cpu_engine(tmp_path, method):
     """Ten rounds of the same deterministic tiny experiment on the fp32 CPU engine and on the bf16 GPU engine: per-round
     training loss within 10 % (5 % on average)."""
     L.check_bf16_engine_tracks_fp32(str(tmp_path), method, "cuda:0")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least two GPUs on the box")
+def test_collective_watchdog_fault_injection():
+    """A rank that never enters a collective: the survivors' kernels time out (flag watchdog), skip their store phase
+    and the host sees a ``NativeError`` - no hang, no partial aggregate (``tests/dist_comm_fault_check.py``)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
+                        "--nproc-per-node", "2", os.path.join(root, "tests", "dist_comm_fault_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:])
+    assert r.returncode == 0 and "DIST_COMM_FAULT_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
