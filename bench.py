@@ -85,6 +85,10 @@ def parse_args():
                          "place; the harness used to unlink them - a long run must not fill the RAM disk)")
     ap.add_argument("--staged-ckpt", action="store_true", help="round-1 checkpoint pipeline (pinned arena + writer "
                                                                "processes) instead of DMA into mapped files")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="compute dtype of the engine: bf16 = the product path (tensor-core kernels, fp32 masters); fp32 = "
+                         "the same engine with fp32 activations / weights on the library kernels (the precision-matched "
+                         "arm for convergence comparisons with the fp32 reference; not the headline)")
     ap.add_argument("--cpu-debug", action="store_true", help="tiny CPU run to exercise the harness")
     return ap.parse_args()
 
@@ -169,7 +173,7 @@ def build_config(a, impl: str, world: int):
         "clients": [{"client_name": f"client-{i}",
                      **({"model_ckpt_name": "fedstil_model"} if a.method.startswith("fedstil") else {}),
                      "tasks": [f"task-{i}-{t}" for t in range(5)]} for i in range(a.clients)],
-        "engine_opts": {"compute_dtype": "bf16", "comm_mode": "nccl" if impl == "nccl" else None,
+        "engine_opts": {"compute_dtype": getattr(a, "dtype", "bf16"), "comm_mode": "nccl" if impl == "nccl" else None,
                         "val_at_round0": False, "checkpoints": not a.no_ckpt, "save_payload_ckpts": not a.no_ckpt,
                         "mapped_checkpoints": not a.staged_ckpt, "payload_ring": a.payload_ring},
     }
@@ -371,7 +375,7 @@ def run_flpr(a, impl: str) -> dict:
     out = {
         "metric": metric_name(a), "value": round(value, 2), "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "bf16" if not a.cpu_debug else "fp32",
+        "vs_baseline": None, "dtype": a.dtype if not a.cpu_debug else "fp32",
         "data": "synthetic 256x128 uint8 crops in pinned host memory, random-init weights",
         "impl": impl,
         "config": bench_config(a, impl, ""),
