@@ -95,6 +95,12 @@ def test_bf16_gpu_engine_tracks_fp32_cpu_engine(tmp_path, method):
     L.check_bf16_engine_tracks_fp32(str(tmp_path), method, "cuda:0")
 
 
+def test_fp32_gpu_engine_tracks_fp32_cpu_engine(tmp_path):
+    """``engine_opts.compute_dtype: fp32`` on the GPU (``bench.py --dtype fp32``, the precision-matched arm): same
+    experiment, library fp32 kernels + the fused fp32 optimizer - within 5 % per round of the CPU engine."""
+    L.check_bf16_engine_tracks_fp32(str(tmp_path), "fedstil", "cuda:0", per_round=0.05, mean_tol=0.02, dtype="fp32")
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least two GPUs on the box")
 def test_collective_watchdog_fault_injection():
     """A rank that never enters a collective: the survivors' kernels time out (flag watchdog), skip their store phase
