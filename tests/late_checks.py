@@ -314,13 +314,19 @@ def run_tiny_rounds(tmp: str, method: str, device: str, dtype: str, rounds: int 
     return out
 
 
+_REF_CURVES: dict = {}
+
+
 def check_bf16_engine_tracks_fp32(tmp: str, method: str, device: str, per_round: float = 0.10, mean_tol: float = 0.05,
                                   rounds: int = 10, dtype: str = "bf16"):
     """The bf16 engine on ``device`` (native kernels) follows the fp32 CPU engine round by round on the same
     experiment: a wrong gradient / optimizer / aggregation kernel shows up as a diverging loss curve within a few
     rounds, which the finite-metric assertions of the e2e tests cannot see."""
     import os
-    ref = run_tiny_rounds(os.path.join(tmp, "fp32"), method, "cpu", "fp32", rounds)
+    key = (method, rounds)
+    if key not in _REF_CURVES:                       # the fp32 CPU curve is shared by the bf16 and the fp32 device arms
+        _REF_CURVES[key] = run_tiny_rounds(os.path.join(tmp, "fp32"), method, "cpu", "fp32", rounds)
+    ref = _REF_CURVES[key]
     got = run_tiny_rounds(os.path.join(tmp, "dev"), method, device, dtype if device != "cpu" else "fp32", rounds)
     assert ref.keys() == got.keys() and all(len(v) == rounds for v in ref.values()), (ref, got)
     for client in ref:
