@@ -9,6 +9,9 @@
 //   ln_rows                       LayerNorm over the channel dim of bf16 token rows, one warp per token, fp32 statistics;
 //                                 optionally the destination is the (cyclically shifted) window layout of a Swin block
 //                                 (models/swin_transformer.py:358-380: norm1 -> roll -> window_partition in one pass).
+//   ln_rows_train / ln_rows_bwd   the same LayerNorm for the TRAINABLE stage: the forward keeps (mean, rstd) per row, the
+//                                 backward is one sweep (dx in the source layout, per-block dgamma / dbeta partials
+//                                 folded in a fixed order by ln_colsum: deterministic, no atomics).
 //   window_merge_add              window_reverse -> roll back -> + shortcut (models/swin_transformer.py:383-391) in one pass.
 //   gelu_rows                     exact (erf) GELU over bf16 rows (models/swin_transformer.py:118-140, frozen stages).
 //   apply_global                  receiving end of the FedAvg-family dispatch (methods/fedavg.py:413-430,
@@ -169,7 +172,8 @@ template <int VPL>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const __nv_bfloat16* __restrict__ x,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       __nv_bfloat16* __restrict__ out, long long rows, int C, float eps,
-                                                      int window, int H, int W, int ws, int shift) {
+                                                      int window, int H, int W, int ws, int shift,
+                                                      float2* __restrict__ stats) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + warp;
   if (r >= rows) return;
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const __nv_bfloat16* __res
     }
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  if (stats != nullptr && lane == 0) stats[r] = make_float2(mean, rstd);       // saved for ln_rows_bwd_kernel
   uint4* op = reinterpret_cast<uint4*>(out + r * C);
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
@@ -219,6 +224,122 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const __nv_bfloat16* __res
       op[idx] = pack8(y);
     }
   }
+}
+
+// LayerNorm backward for the TRAINABLE Swin stage (bf16 token rows, fp32 statistics saved by the forward kernel).
+// One warp per destination row (the layout dy arrives in; window != 0: the forward wrote the shifted-window layout, so
+// row r belongs to image row window_row_to_image_row(r), which is where dx goes - the map is a bijection, every image
+// row is written exactly once). With xhat = (x - mean) * rstd and g = dy * gamma:
+//     dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)),   dgamma += dy * xhat,   dbeta += dy.
+// x and dy stay packed (bf16) in registers; each block walks its rows with a grid stride, folds the per-warp dgamma /
+// dbeta partials through shared memory and writes ONE [2, C] partial per block: part[block][0] = dgamma, [1] = dbeta
+// (ln_colsum_kernel adds the blocks in a fixed order: deterministic, no atomics).
+template <int VPL>
+__global__ void __launch_bounds__(256) ln_rows_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                          const __nv_bfloat16* __restrict__ x,
+                                                          const float* __restrict__ gamma,
+                                                          const float2* __restrict__ stats,
+                                                          __nv_bfloat16* __restrict__ dx, float* __restrict__ part,
+                                                          long long rows, int C, int window, int H, int W, int ws,
+                                                          int shift) {
+  __shared__ float sh[2][8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  const float inv_c = 1.f / (float)C;
+  float dg[VPL][8], db[VPL][8], gm[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * idx], g1 = reinterpret_cast<const float4*>(gamma)[2 * idx + 1];
+      gm[i][0] = g0.x; gm[i][1] = g0.y; gm[i][2] = g0.z; gm[i][3] = g0.w;
+      gm[i][4] = g1.x; gm[i][5] = g1.y; gm[i][6] = g1.z; gm[i][7] = g1.w;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) gm[i][t] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) dg[i][t] = db[i][t] = 0.f;
+  }
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
+    const long long src = window ? window_row_to_image_row(r, H, W, ws, shift) : r;
+    const uint4* xp = reinterpret_cast<const uint4*>(x + src * C);
+    const uint4* yp = reinterpret_cast<const uint4*>(dy + r * C);
+    const float2 st = stats[r];
+    uint4 xu[VPL], yu[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        xu[i] = xp[idx];
+        yu[i] = yp[idx];
+        float xv[8], yv[8];
+        unpack8(xu[i], xv);
+        unpack8(yu[i], yv);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float xh = (xv[t] - st.x) * st.y;
+          const float g = yv[t] * gm[i][t];
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+          dg[i][t] = fmaf(yv[t], xh, dg[i][t]);
+          db[i][t] += yv[t];
+        }
+      }
+    }
+    s1 = warp_sum(s1) * inv_c;
+    s2 = warp_sum(s2) * inv_c;
+    uint4* op = reinterpret_cast<uint4*>(dx + src * C);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        float xv[8], yv[8], o[8];
+        unpack8(xu[i], xv);
+        unpack8(yu[i], yv);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float xh = (xv[t] - st.x) * st.y;
+          o[t] = st.y * (yv[t] * gm[i][t] - s1 - xh * s2);
+        }
+        op[idx] = pack8(o);
+      }
+    }
+  }
+  // fold the 8 warps' partials (every thread reaches these barriers: the row loop has no early exit)
+  float* pg = part + (long long)blockIdx.x * 2 * C;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      sh[0][warp][lane * 8 + t] = dg[i][t];
+      sh[1][warp][lane * 8 + t] = db[i][t];
+    }
+    __syncthreads();
+    const int c = 256 * i + threadIdx.x;
+    if (c < C) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) {
+        a += sh[0][w8][threadIdx.x];
+        b += sh[1][w8][threadIdx.x];
+      }
+      pg[c] = a;
+      pg[C + c] = b;
+    }
+    __syncthreads();
+  }
+}
+
+// out[j] = sum_b part[b, j] over the per-block partials (j in [0, 2C): dgamma then dbeta), fixed order
+__global__ void __launch_bounds__(256) ln_colsum_kernel(const float* __restrict__ part, int blocks, int n2,
+                                                        float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n2) return;
+  float t = 0.f;
+  for (int b = 0; b < blocks; ++b) t += part[(long long)b * n2 + j];
+  out[j] = t;
 }
 
 // out[image row r] = shortcut[r] + win[image_row_to_window_row(r)]   (8 channels per thread)
@@ -344,8 +465,60 @@ int flpr_wcompose_bwd(const float* dth, const float* aw, const float* stack, int
 }
 
 // LayerNorm over rows of C bf16 channels (C % 8 == 0, C <= 2048). window != 0: see ln_rows_kernel.
+static int ln_rows_launch(const void* x, const float* gamma, const float* beta, void* out, long long rows, int C,
+                          float eps, int window, int H, int W, int ws, int shift, float2* stats, cudaStream_t st);
+
 int flpr_ln_rows(const void* x, const float* gamma, const float* beta, void* out, long long rows, int C, float eps,
                  int window, int H, int W, int ws, int shift, cudaStream_t st) {
+  return ln_rows_launch(x, gamma, beta, out, rows, C, eps, window, H, W, ws, shift, nullptr, st);
+}
+
+// Training forward: same kernel, the per-row (mean, rstd) pairs are kept for flpr_ln_rows_bwd (stats: [rows, 2] fp32).
+int flpr_ln_rows_train(const void* x, const float* gamma, const float* beta, void* out, float* stats, long long rows,
+                       int C, float eps, int window, int H, int W, int ws, int shift, cudaStream_t st) {
+  if (stats == nullptr || ((uintptr_t)stats & 7)) return -27;
+  return ln_rows_launch(x, gamma, beta, out, rows, C, eps, window, H, W, ws, shift, reinterpret_cast<float2*>(stats), st);
+}
+
+// Blocks the backward kernel is launched with for `rows` rows (= rows of the partial buffer the caller allocates).
+int flpr_ln_rows_bwd_blocks(long long rows) {
+  long long g = (rows + 7) / 8;
+  if (g > 148LL * 2) g = 148LL * 2;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// dy: [rows, C] bf16 in the forward's DESTINATION layout; x: the forward's input; dx: same layout as x;
+// part: [flpr_ln_rows_bwd_blocks(rows), 2, C] fp32 scratch; dgb: [2, C] fp32 (dgamma, dbeta).
+int flpr_ln_rows_bwd(const void* dy, const void* x, const float* gamma, const float* stats, void* dx, float* part,
+                     float* dgb, long long rows, int C, int window, int H, int W, int ws, int shift, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (C % 8 || C <= 0 || C > 2048) return -23;
+  if (window && (ws <= 0 || H % ws || W % ws || shift < 0 || shift >= ws || rows % ((long long)H * W))) return -24;
+  if (((uintptr_t)stats & 7) || ((uintptr_t)gamma & 15)) return -27;
+  bind_device_of(x);
+  const int grid = flpr_ln_rows_bwd_blocks(rows);
+  const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(dx);
+  const float2* sp = reinterpret_cast<const float2*>(stats);
+  const int nvec = C / 8;
+  if (nvec <= 32)
+    ln_rows_bwd_kernel<1><<<grid, 256, 0, st>>>(yp, xp, gamma, sp, op, part, rows, C, window, H, W, ws, shift);
+  else if (nvec <= 64)
+    ln_rows_bwd_kernel<2><<<grid, 256, 0, st>>>(yp, xp, gamma, sp, op, part, rows, C, window, H, W, ws, shift);
+  else if (nvec <= 128)
+    ln_rows_bwd_kernel<4><<<grid, 256, 0, st>>>(yp, xp, gamma, sp, op, part, rows, C, window, H, W, ws, shift);
+  else
+    ln_rows_bwd_kernel<8><<<grid, 256, 0, st>>>(yp, xp, gamma, sp, op, part, rows, C, window, H, W, ws, shift);
+  int rc = (int)cudaGetLastError();
+  if (rc) return rc;
+  ln_colsum_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(part, grid, 2 * C, dgb);
+  return (int)cudaGetLastError();
+}
+
+static int ln_rows_launch(const void* x, const float* gamma, const float* beta, void* out, long long rows, int C,
+                          float eps, int window, int H, int W, int ws, int shift, float2* stats, cudaStream_t st) {
   if (rows <= 0) return 0;
   if (C % 8 || C <= 0 || C > 2048) return -23;
   if (window && (ws <= 0 || H % ws || W % ws || shift < 0 || shift >= ws || rows % ((long long)H * W))) return -24;
@@ -355,13 +528,13 @@ int flpr_ln_rows(const void* x, const float* gamma, const float* beta, void* out
   __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out);
   const int nvec = C / 8;
   if (nvec <= 32)
-    ln_rows_kernel<1><<<grid, 256, 0, st>>>(xp, gamma, beta, op, rows, C, eps, window, H, W, ws, shift);
+    ln_rows_kernel<1><<<grid, 256, 0, st>>>(xp, gamma, beta, op, rows, C, eps, window, H, W, ws, shift, stats);
   else if (nvec <= 64)
-    ln_rows_kernel<2><<<grid, 256, 0, st>>>(xp, gamma, beta, op, rows, C, eps, window, H, W, ws, shift);
+    ln_rows_kernel<2><<<grid, 256, 0, st>>>(xp, gamma, beta, op, rows, C, eps, window, H, W, ws, shift, stats);
   else if (nvec <= 128)
-    ln_rows_kernel<4><<<grid, 256, 0, st>>>(xp, gamma, beta, op, rows, C, eps, window, H, W, ws, shift);
+    ln_rows_kernel<4><<<grid, 256, 0, st>>>(xp, gamma, beta, op, rows, C, eps, window, H, W, ws, shift, stats);
   else
-    ln_rows_kernel<8><<<grid, 256, 0, st>>>(xp, gamma, beta, op, rows, C, eps, window, H, W, ws, shift);
+    ln_rows_kernel<8><<<grid, 256, 0, st>>>(xp, gamma, beta, op, rows, C, eps, window, H, W, ws, shift, stats);
   return (int)cudaGetLastError();
 }
 

@@ -92,6 +92,26 @@ class FrozenLayerNorm(nn.LayerNorm):
             return F.layer_norm(x, self.normalized_shape, hit[1], hit[2], self.eps)
 
 
+class TrainLayerNorm(nn.LayerNorm):
+    """``norm1`` / ``norm2`` of a TRAINABLE Swin block on the bf16 path (``models/swin_transformer.py:358-395``): the
+    native warp-per-token kernels (``ops.layer.layer_norm_rows``: fp32 statistics, fp32 ``gamma`` / ``beta``, bf16 in and
+    out, one-sweep backward with deterministic ``dgamma`` / ``dbeta``) instead of the autocast ``layer_norm`` (an fp32 op:
+    fp32 output + a cast pass in front of the tensor-core Linear that consumes it, and the mirror image in backward).
+    Only block norms are switched - their consumer casts to bf16 anyway, so the GEMM operands are unchanged; the final
+    ``norm`` in front of the pooled feature stays fp32."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        c = x.shape[-1]
+        if not (x.is_cuda and x.dtype == torch.bfloat16 and torch.is_grad_enabled() and self.weight.requires_grad
+                and len(self.normalized_shape) == 1 and c % 8 == 0 and c <= 2048 and self.bias is not None
+                and self.weight.dtype == torch.float32 and self.weight.data_ptr() % 16 == 0
+                and self.bias.data_ptr() % 16 == 0 and lops.enabled("ln_train", x.device)):
+            return super().forward(x)
+        x2 = x.reshape(-1, c)
+        y = lops.layer_norm_rows(x2 if x2.is_contiguous() else x2.contiguous(), self.weight, self.bias, self.eps)
+        return y.view(x.shape)
+
+
 def use_tensor_core_linears(root: nn.Module, shadow=None, grad_slot=None) -> int:
     """Re-class every plain ``nn.Linear`` under ``root`` to :class:`TcLinear` (and the frozen ``nn.LayerNorm``s to
     :class:`FrozenLayerNorm`); returns how many Linears were switched."""
@@ -103,6 +123,11 @@ def use_tensor_core_linears(root: nn.Module, shadow=None, grad_slot=None) -> int
             n += 1
         elif type(m) is nn.LayerNorm and m.elementwise_affine and not m.weight.requires_grad:
             m.__class__ = FrozenLayerNorm
+    for blk in root.modules():
+        if isinstance(blk, SwinTransformerBlock):
+            for ln in (blk.norm1, blk.norm2):
+                if type(ln) is nn.LayerNorm and ln.elementwise_affine and ln.weight.requires_grad:
+                    ln.__class__ = TrainLayerNorm
     return n
 
 

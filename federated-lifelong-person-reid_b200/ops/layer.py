@@ -36,6 +36,8 @@ def _declare(lib) -> None:
         "flpr_wcompose_fwd": [P, P, P, I, I, P, P, L, Fl, Fl, I, P, P, L, P],
         "flpr_wcompose_bwd": [P, P, P, I, I, P, P, L, Fl, Fl, I, P, P, P, P, L, P],
         "flpr_ln_rows": [P, P, P, P, L, I, Fl, I, I, I, I, I, P],
+        "flpr_ln_rows_train": [P, P, P, P, P, L, I, Fl, I, I, I, I, I, P],
+        "flpr_ln_rows_bwd": [P, P, P, P, P, P, P, L, I, I, I, I, I, I, P],
         "flpr_window_merge_add": [P, P, P, L, I, I, I, I, I, P],
         "flpr_gelu_rows": [P, P, L, P],
         "flpr_apply_global": [P, P, P, P, I, L, P],
@@ -46,13 +48,43 @@ def _declare(lib) -> None:
         fn.restype = I
     lib.flpr_wcompose_max_k.argtypes = []
     lib.flpr_wcompose_max_k.restype = I
+    lib.flpr_ln_rows_bwd_blocks.argtypes = [L]
+    lib.flpr_ln_rows_bwd_blocks.restype = I
     lib._flpr_layer_declared = True
 
 
+_emu_lib = None    # tests only: a host build of csrc/layer_ops.cu under the SIMT emulator (tests/emu), driven with CPU tensors
+
+
+def use_emulated_library(path: Optional[str]):
+    """Route the wrappers of this module to the emulated library at ``path`` (``None``: back to normal). With it set,
+    CPU tensors take the KERNEL path (same argument marshalling, same entry points) instead of the PyTorch reference."""
+    global _emu_lib
+    if path is None:
+        _emu_lib = None
+        return None
+    import ctypes
+    lib = ctypes.CDLL(path)
+    _declare(lib)
+    _emu_lib = lib
+    return lib
+
+
 def _lib():
+    if _emu_lib is not None:
+        return _emu_lib
     lib = native.load()
     _declare(lib)
     return lib
+
+
+def _native(t: torch.Tensor) -> bool:
+    """The kernel path applies to ``t`` (a CUDA tensor - or any tensor while the emulated library is installed)."""
+    return t.is_cuda or _emu_lib is not None
+
+
+def _stream(device):
+    return native.c_void_p(0) if _emu_lib is not None else native.stream(device)
 
 
 WC_MAX_K = 16      # flpr_wcompose_max_k(): stacked weights per element the compose kernels keep in registers
@@ -125,7 +157,7 @@ def wcompose_fwd(aw: torch.Tensor, stack: Optional[torch.Tensor], atten: Optiona
     """``theta[e] = prune(aw[e]) + sum_{k<kb} atten[k] stack[e, k] + prune(mask[e // row_len]) sw[e]`` over flat fp32
     buffers; returns ``(theta_fp32, theta_bf16)`` (either may be skipped)."""
     n = aw.numel()
-    if not aw.is_cuda:
+    if not _native(aw):
         th = wcompose_fwd_ref(aw, stack, atten, kb, sw, mask, row_len, thr_aw, thr_mask, prune)
         return (th if want_f32 else None), (th.to(torch.bfloat16) if want_bf16 else None)
     lib = _lib()
@@ -144,7 +176,7 @@ def wcompose_fwd(aw: torch.Tensor, stack: Optional[torch.Tensor], atten: Optiona
                                native.ptr(atten if kb > 0 else None), int(kb), int(ks), native.ptr(sw),
                                native.ptr(mask if sw is not None else None), int(row_len), float(thr_aw),
                                float(thr_mask), int(bool(prune)), native.ptr(o32), native.ptr(o16), n,
-                               native.stream(aw.device))
+                               _stream(aw.device))
     native.check(rc, "flpr_wcompose_fwd")
     native.count_launch()
     return o32, o16
@@ -171,7 +203,7 @@ def wcompose_bwd(dth: torch.Tensor, aw: torch.Tensor, stack: Optional[torch.Tens
                  thr_aw: float = 0.0, thr_mask: float = 0.0, prune: bool = False, chunk: int = 8192):
     """Gradients of :func:`wcompose_fwd` w.r.t. ``aw`` (``None`` = identical to ``dth``: nothing was pruned),
     ``atten[:kb]`` and ``mask``. Without ``sw`` the rows of the reduction are arbitrary ``chunk``-element pieces."""
-    if not dth.is_cuda:
+    if not _native(dth):
         return wcompose_bwd_ref(dth, aw, stack, kb, sw, mask, row_len, thr_aw, thr_mask, prune)
     lib = _lib()
     n = dth.numel()
@@ -191,7 +223,7 @@ def wcompose_bwd(dth: torch.Tensor, aw: torch.Tensor, stack: Optional[torch.Tens
     rc = lib.flpr_wcompose_bwd(native.ptr(dth), native.ptr(aw), native.ptr(stack if kb > 0 else None), int(kb),
                                int(ks), native.ptr(sw), native.ptr(mask if sw is not None else None), int(row_len),
                                float(thr_aw), float(thr_mask), int(bool(prune)), native.ptr(d_aw), native.ptr(part),
-                               native.ptr(d_mask), native.ptr(d_att), n, native.stream(dth.device))
+                               native.ptr(d_mask), native.ptr(d_att), n, _stream(dth.device))
     native.check(rc, "flpr_wcompose_bwd")
     native.count_launch(2 if kb > 0 else 1)
     return d_aw, d_att, d_mask
@@ -254,7 +286,7 @@ def compose_weight(aw: torch.Tensor, stack: Optional[torch.Tensor], atten: Optio
                    thr_mask: float = 0.0, prune: bool = False, use_ref: bool = False):
     """Differentiable fused composition; returns ``(theta_fp32, theta_bf16)`` (see :class:`_WComposeFn`)."""
     return _WComposeFn.apply(aw, mask, atten, sw, stack, int(kb), float(thr_aw), float(thr_mask), bool(prune),
-                             bool(use_ref or not aw.is_cuda))
+                             bool(use_ref or not _native(aw)))
 
 
 # ===================================================================================================== Swin token ops
@@ -293,7 +325,7 @@ def ln_rows(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float
     """LayerNorm over the last dim of ``x`` ``[rows, C]`` (bf16, fp32 statistics, fp32 ``gamma`` / ``beta``).
     ``window = (H, W, ws, shift)``: ``x`` is in image layout ``[B*H*W, C]`` and the result is written in the layout of
     the shifted windows ``[B*nW*ws*ws, C]`` (norm -> roll -> window partition in one pass)."""
-    if not x.is_cuda:
+    if not _native(x):
         return ln_rows_ref(x, gamma, beta, eps, window)
     lib = _lib()
     rows, c = x.shape
@@ -302,10 +334,105 @@ def ln_rows(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float
     out = torch.empty_like(x)
     h, w, ws, sh = window if window is not None else (0, 0, 0, 0)
     rc = lib.flpr_ln_rows(native.ptr(x), native.ptr(gamma), native.ptr(beta), native.ptr(out), rows, c, float(eps),
-                          int(window is not None), int(h), int(w), int(ws), int(sh), native.stream(x.device))
+                          int(window is not None), int(h), int(w), int(ws), int(sh), _stream(x.device))
     native.check(rc, "flpr_ln_rows")
     native.count_launch()
     return out
+
+
+# ---- trainable LayerNorm (Swin blocks of the trainable stage): forward keeps (mean, rstd), backward is one sweep ----------
+def ln_rows_train(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+                  window: Optional[Tuple[int, int, int, int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """:func:`ln_rows` that also returns the per-destination-row ``[rows, 2]`` fp32 ``(mean, rstd)`` pairs."""
+    rows, c = x.shape
+    if not _native(x):
+        src = x if window is None else x[window_src_rows(rows, *window, device=x.device)]
+        xf = src.float()
+        mean = xf.mean(1)
+        rstd = torch.rsqrt(xf.var(1, unbiased=False) + eps)
+        y = ((xf - mean[:, None]) * rstd[:, None]) * gamma.float() + beta.float()
+        return y.to(x.dtype), torch.stack([mean, rstd], 1)
+    lib = _lib()
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and c % 8 == 0 and c <= 2048
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.is_contiguous() and beta.is_contiguous()
+    assert gamma.data_ptr() % 16 == 0 and beta.data_ptr() % 16 == 0
+    out = torch.empty_like(x)
+    stats = torch.empty(rows, 2, dtype=torch.float32, device=x.device)
+    h, w, ws, sh = window if window is not None else (0, 0, 0, 0)
+    rc = lib.flpr_ln_rows_train(native.ptr(x), native.ptr(gamma), native.ptr(beta), native.ptr(out), native.ptr(stats),
+                                rows, c, float(eps), int(window is not None), int(h), int(w), int(ws), int(sh),
+                                _stream(x.device))
+    native.check(rc, "flpr_ln_rows_train")
+    native.count_launch()
+    return out, stats
+
+
+def ln_rows_bwd_ref(dy, x, gamma, stats, window=None):
+    rows, c = x.shape
+    src_rows = None if window is None else window_src_rows(rows, *window, device=x.device)
+    xf = (x if src_rows is None else x[src_rows]).float()
+    xh = (xf - stats[:, :1]) * stats[:, 1:2]
+    dyf = dy.float()
+    g = dyf * gamma.float()
+    dxw = stats[:, 1:2] * (g - g.mean(1, keepdim=True) - xh * (g * xh).mean(1, keepdim=True))
+    if src_rows is None:
+        dx = dxw
+    else:
+        dx = torch.empty_like(dxw)
+        dx[src_rows] = dxw
+    return dx.to(x.dtype), (dyf * xh).sum(0), dyf.sum(0)
+
+
+def ln_rows_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, stats: torch.Tensor,
+                window: Optional[Tuple[int, int, int, int]] = None):
+    """Backward of :func:`ln_rows_train`: ``(dx [layout of x], dgamma, dbeta)``; ``dy`` is in the forward's destination
+    layout. Per-block partials of dgamma / dbeta are folded in a fixed order (deterministic)."""
+    if not _native(dy):
+        return ln_rows_bwd_ref(dy, x, gamma, stats, window)
+    lib = _lib()
+    rows, c = x.shape
+    assert dy.shape == x.shape and dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
+    assert dy.is_contiguous() and x.is_contiguous() and stats.is_contiguous() and stats.dtype == torch.float32
+    assert gamma.dtype == torch.float32 and gamma.is_contiguous() and gamma.data_ptr() % 16 == 0
+    dx = torch.empty_like(x)
+    blocks = int(lib.flpr_ln_rows_bwd_blocks(rows))
+    part = torch.empty(blocks, 2, c, dtype=torch.float32, device=x.device)
+    dgb = torch.empty(2, c, dtype=torch.float32, device=x.device)
+    h, w, ws, sh = window if window is not None else (0, 0, 0, 0)
+    rc = lib.flpr_ln_rows_bwd(native.ptr(dy), native.ptr(x), native.ptr(gamma), native.ptr(stats), native.ptr(dx),
+                              native.ptr(part), native.ptr(dgb), rows, c, int(window is not None), int(h), int(w),
+                              int(ws), int(sh), _stream(x.device))
+    native.check(rc, "flpr_ln_rows_bwd")
+    native.count_launch(2)
+    return dx, dgb[0], dgb[1]
+
+
+class _LnRowsFn(torch.autograd.Function):
+    """LayerNorm over bf16 token rows with fp32 statistics and fp32 affine parameters (``models/swin_transformer.py:
+    358-395``, ``norm1`` / ``norm2`` of a trainable block): bf16 in, bf16 out - the consumer is a tensor-core Linear that
+    would cast the fp32 result of the autocast ``layer_norm`` to bf16 anyway, so the values reaching the GEMM are the same
+    and the fp32 round trip of the token stream (forward and backward) disappears."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, window):
+        y, stats = ln_rows_train(x, gamma.detach(), beta.detach(), eps, window)
+        ctx.save_for_backward(x, gamma, stats)
+        ctx.window = window
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, stats = ctx.saved_tensors
+        dyc = dy if (dy.dtype == x.dtype and dy.is_contiguous()) else dy.to(x.dtype).contiguous()
+        dx, dg, db = ln_rows_bwd(dyc, x, gamma.detach(), stats, ctx.window)
+        return (dx if ctx.needs_input_grad[0] else None, dg.to(gamma.dtype) if ctx.needs_input_grad[1] else None,
+                db.to(gamma.dtype) if ctx.needs_input_grad[2] else None, None, None)
+
+
+def layer_norm_rows(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+                    window: Optional[Tuple[int, int, int, int]] = None) -> torch.Tensor:
+    """Differentiable :func:`ln_rows` (``x``: ``[rows, C]`` bf16 contiguous; fp32 ``gamma`` / ``beta``)."""
+    return _LnRowsFn.apply(x, gamma, beta, float(eps), window)
 
 
 def window_merge_add_ref(win, shortcut, H, W, ws, shift):
@@ -315,7 +442,7 @@ def window_merge_add_ref(win, shortcut, H, W, ws, shift):
 
 def window_merge_add(win: torch.Tensor, shortcut: torch.Tensor, H: int, W: int, ws: int, shift: int) -> torch.Tensor:
     """``shortcut + roll(window_reverse(win), +shift)`` over ``[B*H*W, C]`` bf16 rows in one pass."""
-    if not win.is_cuda:
+    if not _native(win):
         return window_merge_add_ref(win, shortcut, H, W, ws, shift)
     lib = _lib()
     rows, c = shortcut.shape
@@ -323,7 +450,7 @@ def window_merge_add(win: torch.Tensor, shortcut: torch.Tensor, H: int, W: int, 
     assert win.is_contiguous() and shortcut.is_contiguous() and c % 8 == 0
     out = torch.empty_like(shortcut)
     rc = lib.flpr_window_merge_add(native.ptr(win), native.ptr(shortcut), native.ptr(out), rows, c, int(H), int(W),
-                                   int(ws), int(shift), native.stream(win.device))
+                                   int(ws), int(shift), _stream(win.device))
     native.check(rc, "flpr_window_merge_add")
     native.count_launch()
     return out
@@ -331,12 +458,12 @@ def window_merge_add(win: torch.Tensor, shortcut: torch.Tensor, H: int, W: int, 
 
 def gelu_rows(x: torch.Tensor) -> torch.Tensor:
     """Exact (erf) GELU over a bf16 tensor."""
-    if not x.is_cuda:
+    if not _native(x):
         return F.gelu(x.float()).to(x.dtype)
     lib = _lib()
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() % 8 == 0
     out = torch.empty_like(x)
-    native.check(lib.flpr_gelu_rows(native.ptr(x), native.ptr(out), x.numel(), native.stream(x.device)),
+    native.check(lib.flpr_gelu_rows(native.ptr(x), native.ptr(out), x.numel(), _stream(x.device)),
                  "flpr_gelu_rows")
     native.count_launch()
     return out
@@ -359,7 +486,7 @@ def apply_global(flat: torch.Tensor, master: torch.Tensor, shadow: Optional[torc
     """Receiving end of a FedAvg-family dispatch: ``master[:n] <- flat`` with the bf16 compute copy refreshed and the
     FedProx anchor snapshotted in the same pass (``snap_mode`` 1: the weights being replaced, 2: the incoming ones)."""
     n = flat.numel()
-    ok = flat.is_cuda and n % 4 == 0 and flat.dtype == torch.float32 and flat.is_contiguous() and \
+    ok = _native(flat) and n % 4 == 0 and flat.dtype == torch.float32 and flat.is_contiguous() and \
         all(t is None or (t.is_contiguous() and t.data_ptr() % 16 == 0) for t in (flat, master, shadow, p_old))
     if not ok:
         return apply_global_ref(flat, master, shadow, p_old, snap_mode)
@@ -368,7 +495,7 @@ def apply_global(flat: torch.Tensor, master: torch.Tensor, shadow: Optional[torc
     assert shadow is None or (shadow.dtype == torch.bfloat16 and shadow.numel() >= n)
     assert p_old is None or (p_old.dtype == torch.float32 and p_old.numel() >= n)
     rc = lib.flpr_apply_global(native.ptr(flat), native.ptr(master), native.ptr(shadow),
-                               native.ptr(p_old if snap_mode else None), int(snap_mode), n, native.stream(flat.device))
+                               native.ptr(p_old if snap_mode else None), int(snap_mode), n, _stream(flat.device))
     native.check(rc, "flpr_apply_global")
     native.count_launch()
 
@@ -437,6 +564,30 @@ def _check_swin_tokens(dev) -> bool:
     return ok
 
 
+def _check_ln_train(dev) -> bool:
+    g = torch.Generator(device="cpu").manual_seed(14)
+    ok = True
+    for (b, h, w, ws, shift, c) in ((2, 8, 4, 4, 0, 768), (3, 14, 14, 7, 3, 96), (40, 7, 7, 7, 0, 1024),
+                                    (5, 8, 4, 4, 2, 1536), (1, 4, 4, 4, 0, 384)):
+        rows = b * h * w
+        x = (torch.randn(rows, c, generator=g) * 1.5 + 0.3).to(dev).to(torch.bfloat16)
+        gamma, beta = (1 + 0.1 * torch.randn(c, generator=g)).to(dev), (0.1 * torch.randn(c, generator=g)).to(dev)
+        dy = torch.randn(rows, c, generator=g).to(dev).to(torch.bfloat16)
+        for window in (None, (h, w, ws, shift)):
+            y, stats = ln_rows_train(x, gamma, beta, 1e-5, window)
+            ok = ok and _close(y, ln_rows_ref(x, gamma, beta, 1e-5, window), 2e-2, 1e-2)
+            # yardstick: fp32 autograd through F.layer_norm on the (gathered) rows
+            xr = x.float().requires_grad_(True)
+            gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+            with torch.enable_grad():
+                src = xr if window is None else xr[window_src_rows(rows, *window, device=dev)]
+                F.layer_norm(src, (c,), gr, br, 1e-5).backward(dy.float())
+            dx, dg, db = ln_rows_bwd(dy, x, gamma, stats, window)
+            ok = ok and _close(dx, xr.grad, 3e-2, 1e-2) and _close(dg, gr.grad, 1e-2, 5e-3) and \
+                _close(db, br.grad, 1e-3, 1e-4)
+    return ok
+
+
 def _check_apply(dev) -> bool:
     g = torch.Generator(device="cpu").manual_seed(13)
     ok = True
@@ -455,7 +606,8 @@ def _check_apply(dev) -> bool:
     return ok
 
 
-_CHECKS = {"wcompose": _check_wcompose, "swin_tokens": _check_swin_tokens, "apply": _check_apply}
+_CHECKS = {"wcompose": _check_wcompose, "swin_tokens": _check_swin_tokens, "apply": _check_apply,
+           "ln_train": _check_ln_train}
 
 
 def run_checks_inprocess(device, families=None) -> Dict[str, bool]:

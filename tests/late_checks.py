@@ -256,6 +256,66 @@ def check_swin_block_fused(device):
         close(out, ref, rtol=5e-2, atol=5e-2 * ref.abs().max().item())
 
 
+# ------------------------------------------------------------------------------------------------ trainable LayerNorm
+def check_layer_norm_rows(device):
+    """``ops.layer.layer_norm_rows`` (bf16 rows, fp32 statistics, optional shifted-window destination) forward and
+    backward vs fp32 autograd through ``F.layer_norm`` + the window gather."""
+    from flpr_b200.ops import layer as lops
+    g = torch.Generator().manual_seed(41)
+    for (b, h, w, ws, shift, c) in ((2, 8, 4, 4, 0, 768), (2, 14, 14, 7, 3, 96), (9, 8, 4, 4, 1, 1536), (1, 4, 4, 4, 0, 8)):
+        rows = b * h * w
+        x0 = (torch.randn(rows, c, generator=g) * 2 + 0.5).to(device).to(torch.bfloat16)
+        gamma0 = (1 + 0.2 * torch.randn(c, generator=g)).to(device)
+        beta0 = (0.2 * torch.randn(c, generator=g)).to(device)
+        dy = torch.randn(rows, c, generator=g).to(device).to(torch.bfloat16)
+        for window in (None, (h, w, ws, shift)):
+            x = x0.clone().requires_grad_(True)
+            gm, bt = gamma0.clone().requires_grad_(True), beta0.clone().requires_grad_(True)
+            y = lops.layer_norm_rows(x, gm, bt, 1e-5, window)
+            assert y.dtype == torch.bfloat16 and y.shape == x.shape
+            y.backward(dy)
+            xr = x0.float().requires_grad_(True)
+            gr, br = gamma0.clone().requires_grad_(True), beta0.clone().requires_grad_(True)
+            src = xr if window is None else xr[lops.window_src_rows(rows, *window, device=xr.device)]
+            yr = F.layer_norm(src, (c,), gr, br, 1e-5)
+            yr.backward(dy.float())
+            close(y, yr)
+            close(x.grad, xr.grad)
+            close(gm.grad, gr.grad, rtol=2e-2, atol=1e-2 * gr.grad.abs().max().item() + 1e-4)
+            close(bt.grad, br.grad, rtol=1e-3, atol=1e-3 * br.grad.abs().max().item() + 1e-4)
+
+
+def check_swin_train_block_norms(device):
+    """A trainable Swin block whose ``norm1`` / ``norm2`` were switched to ``TrainLayerNorm``: loss and parameter
+    gradients of one step vs the fp32 module (on the CPU the class falls through to ``nn.LayerNorm``: plumbing only)."""
+    import copy
+    from flpr_b200.models.swin import SwinTransformerBlock, TrainLayerNorm, use_tensor_core_linears
+    torch.manual_seed(5)
+    blk = SwinTransformerBlock(192, (8, 4), 6, window_size=4, shift_size=2, drop_path=0.0).to(device)
+    ref = copy.deepcopy(blk).float()
+    n = use_tensor_core_linears(blk)
+    assert n == 4 and type(blk.norm1) is TrainLayerNorm and type(blk.norm2) is TrainLayerNorm
+    x = torch.randn(6, 32, 192).to(device)
+    tgt = torch.randn(6, 32, 192).to(device)
+    blk.train()
+    ref.train()
+    if device == "cpu":
+        out = blk(x)
+    else:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = blk(x.to(torch.bfloat16))
+    loss = F.mse_loss(out.float(), tgt)
+    loss.backward()
+    rl = F.mse_loss(ref(x), tgt)
+    rl.backward()
+    assert abs(loss.item() - rl.item()) <= 3e-2 * abs(rl.item()) + 1e-4
+    for name in ("norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "attn.qkv.weight"):
+        a, b = blk.get_parameter(name).grad, ref.get_parameter(name).grad
+        assert a is not None, name
+        cos = F.cosine_similarity(a.float().flatten(), b.flatten(), dim=0).item()
+        assert cos > 0.98, (name, cos)
+
+
 # ------------------------------------------------------------------------------------------------ dispatch apply
 def check_apply_global(device):
     """``ops.layer.apply_global`` (master <- global + bf16 copy + FedProx anchor in one pass) vs the three copies."""

@@ -42,3 +42,25 @@ def test_common_defaults_match():
     assert mine["defaults"]["task_opts"]["loader_opts"].pop("multiprocessing_context") is None
     assert _strip(mine["defaults"]) == ref["defaults"]
     assert {k: v for k, v in mine.items() if k != "defaults"} == {k: v for k, v in ref.items() if k != "defaults"}
+
+
+def test_batch_launcher_runs_the_reference_experiment_list():
+    """``startup.sh`` (reference: ``startup.sh``): valid shell, launches ``main.py`` in the background with the same ten
+    basis experiments in the same order, each of which exists here."""
+    import re
+    import subprocess
+    mine = os.path.join(ROOT, "startup.sh")
+    assert subprocess.run(["bash", "-n", mine]).returncode == 0
+
+    def experiments(path):
+        with open(path) as f:
+            return [os.path.normpath(p) for p in re.findall(r"[\w./]*configs/[\w./]+\.yaml", f.read())]
+
+    ours = experiments(mine)
+    assert len(ours) == 10 and all(os.path.exists(os.path.join(ROOT, p)) for p in ours)
+    ref_sh = "/root/reference/startup.sh"               # (not part of the pip-installed copy in baseline/_ref)
+    if os.path.exists(ref_sh):
+        assert ours == experiments(ref_sh)
+    with open(mine) as f:
+        text = f.read()
+    assert "main.py --experiments" in text and "nohup" in text and text.rstrip().endswith("&")

@@ -39,6 +39,14 @@ def test_swin_block_fused_forward():
     L.check_swin_block_fused("cpu")
 
 
+def test_layer_norm_rows_reference_path():
+    L.check_layer_norm_rows("cpu")
+
+
+def test_swin_train_block_norm_classes():
+    L.check_swin_train_block_norms("cpu")
+
+
 def test_apply_global_reference_semantics():
     L.check_apply_global("cpu")
 
@@ -57,7 +65,7 @@ def test_selfcheck_children_protocol(tmp_path, monkeypatch):
     from flpr_b200.ops import layer as lops
     monkeypatch.setattr(tempfile, "tempdir", str(tmp_path))
     verdict = lops._checks_isolated(torch.device("cpu"))
-    assert verdict == {"wcompose": True, "swin_tokens": True, "apply": True}, verdict
+    assert verdict == {"wcompose": True, "swin_tokens": True, "apply": True, "ln_train": True}, verdict
     cached = [f for f in os.listdir(tmp_path) if f.startswith("flpr_layer_selfcheck_")]
     assert len(cached) == 1
     with open(os.path.join(tmp_path, cached[0]), "w") as f:          # the cache is what the next process reads

@@ -17,6 +17,7 @@ def test_layer_kernel_self_checks_pass():
     assert lops.enabled("wcompose", "cuda:0"), "compose kernels failed their numerics self-check"
     assert lops.enabled("swin_tokens", "cuda:0"), "Swin token kernels failed their numerics self-check"
     assert lops.enabled("apply", "cuda:0"), "dispatch-apply kernel failed its numerics self-check"
+    assert lops.enabled("ln_train", "cuda:0"), "LayerNorm forward / backward kernels failed their numerics self-check"
 
 
 @pytest.mark.parametrize("k,n,h,w,cin,cout", [(3, 8, 16, 8, 512, 512), (1, 8, 16, 8, 1024, 2048), (3, 4, 32, 16, 128, 256),
@@ -50,6 +51,14 @@ def test_apply_global_kernel():
 
 def test_swin_token_kernels():
     L.check_swin_token_ops("cuda")
+
+
+def test_layer_norm_rows_native():
+    L.check_layer_norm_rows("cuda")
+
+
+def test_swin_train_block_norms_native():
+    L.check_swin_train_block_norms("cuda")
 
 
 def test_swin_block_fused_native():
