@@ -1,14 +1,17 @@
 """Host build of a CUDA-core kernel source under the SIMT emulator (``cuda_emu.h``).
 
 ``build("layer_ops.cu")`` rewrites every ``kernel<<<grid, block, smem, stream>>>(args);`` into
-``flpr_emu::launch(grid, block, [=]() { kernel(args); });``, swaps ``#include "ptx.cuh"`` for the emulator header,
-compiles the result with ``g++`` (no nvcc, no CUDA runtime call) and returns the path of a shared library that exports
-the same ``extern "C"`` entry points as the real one - so the ctypes wrappers of ``flpr_b200.ops`` can drive it with CPU
-tensors (see ``tests/test_cpu_emulated_kernels.py``)."""
+``flpr_emu::launch(grid, block, stream, [=]() { kernel(args); });``, turns ``__shared__`` declarations into storage owned
+by the running block, removes the functions whose body is inline PTX (the emulator header supplies host versions),
+swaps ``#include "ptx.cuh"`` for the emulator header, compiles the result with ``g++`` (no nvcc, no CUDA runtime call)
+and returns the path of a shared library that exports the same ``extern "C"`` entry points as the real one - so the
+ctypes wrappers of ``flpr_b200.ops`` (``tests/test_cpu_emulated_kernels.py``) or a multi-rank harness
+(``comm_harness.py``, ``tests/test_cpu_emulated_collectives.py``) can drive it with CPU tensors."""
 from __future__ import annotations
 
 import hashlib
 import os
+import re
 import shutil
 import subprocess
 import tempfile
@@ -87,25 +90,66 @@ def rewrite_launches(src: str) -> Tuple[str, int]:
         name = src[name_start:k].strip()
         args = src[args_open + 1:args_end - 1]
         out.append(src[pos:name_start])
-        out.append(f"flpr_emu::launch((unsigned)({cfg[0]}), (unsigned)({cfg[1]}), [=]() {{ {name}({args}); }})")
+        key = f"(const void*)({cfg[3]})" if len(cfg) >= 4 else "nullptr"
+        out.append(f"flpr_emu::launch((unsigned)({cfg[0]}), (unsigned)({cfg[1]}), {key}, [=]() {{ {name}({args}); }})")
         pos = args_end
         n += 1
     return "".join(out), n
 
 
-def emulated_source(cu_name: str) -> str:
+_SHARED_RE = re.compile(r"__shared__\s+([A-Za-z_][\w:]*(?:\s*<[^;<>]*>)?)\s+(\w+)\s*((?:\[[^\]]*\]\s*)*);")
+
+
+def rewrite_shared(src: str) -> Tuple[str, int]:
+    """``__shared__ T name[a][b];`` -> a reference to storage owned by the running block (``flpr_emu::shared``)."""
+    n = 0
+
+    def repl(m):
+        nonlocal n
+        n += 1
+        ty, name, dims = m.group(1), m.group(2), m.group(3).replace(" ", "")
+        return (f"using flpr_sh_t{n} = {ty}{dims}; "
+                f"flpr_sh_t{n}& {name} = *flpr_emu::shared<flpr_sh_t{n}>({n});")
+    return _SHARED_RE.sub(repl, src), n
+
+
+def strip_inline_ptx_functions(src: str) -> Tuple[str, List[str]]:
+    """Remove every function whose body is inline PTX (``asm volatile``): the emulator header supplies host versions of
+    the same names (``gtimer``, ``multimem_*``). Returns the new source and the names removed."""
+    removed = []
+    while True:
+        k = src.find("asm volatile")
+        if k < 0:
+            return src, removed
+        start = src.rfind("\n__device__", 0, k)
+        assert start >= 0, "inline PTX outside a __device__ function"
+        start += 1
+        brace = src.index("{", start)
+        assert brace < k
+        end = _match_forward(src, brace, "{", "}")
+        header = src[start:brace]
+        removed.append(re.search(r"(\w+)\s*\([^()]*\)\s*$", header.strip()).group(1))
+        src = src[:start] + src[end:]
+
+
+def emulated_source(cu_name: str, mutate=None) -> str:
     with open(os.path.join(CSRC, cu_name)) as f:
         src = f.read()
+    if mutate is not None:                       # mutation checks: a deliberately broken kernel the tests must notice
+        src = mutate(src)
     assert '#include "ptx.cuh"' in src
     src = src.replace('#include "ptx.cuh"', '#include "cuda_emu.h"')
+    src, removed = strip_inline_ptx_functions(src)
+    assert set(removed) <= {"gtimer", "multimem_ld_reduce_add_f4", "multimem_st_f4"}, removed
+    src, _ = rewrite_shared(src)
     src, n = rewrite_launches(src)
     assert n > 0 and "<<<" not in src
     return src
 
 
-def build(cu_name: str = "layer_ops.cu") -> str:
+def build(cu_name: str = "layer_ops.cu", mutate=None) -> str:
     """Returns the path of the emulated shared library (cached per source hash in the temp dir)."""
-    src = emulated_source(cu_name)
+    src = emulated_source(cu_name, mutate)
     with open(os.path.join(HERE, "cuda_emu.h")) as f:
         hdr = f.read()
     tag = hashlib.sha256((src + hdr).encode()).hexdigest()[:16]
@@ -122,7 +166,10 @@ def build(cu_name: str = "layer_ops.cu") -> str:
         f.write(src)
     tmp = lib + f".{os.getpid()}.tmp"
     cmd = [gxx, "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-Wno-attributes", "-Wno-unknown-pragmas",
-           "-I", HERE, "-I", CSRC, "-I", CUDA_INCLUDE, cpp, "-o", tmp]
+           "-Wno-unused-function", "-I", HERE, "-I", CSRC, "-I", CUDA_INCLUDE, cpp, "-o", tmp]
+    cudart = os.path.join(os.path.dirname(CUDA_INCLUDE), "lib64")
+    if os.path.exists(os.path.join(cudart, "libcudart.so")):      # host-side helpers of fedcomm.cu reference the runtime
+        cmd += ["-L", cudart, "-lcudart", f"-Wl,-rpath,{cudart}"]   # (never called under emulation)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("emulator build failed:\n" + r.stderr[-4000:])

@@ -1,17 +1,25 @@
 // Host-side SIMT emulator for the flpr CUDA-core kernels (tests only; no GPU, no CUDA runtime call).
 //
 // A kernel source is compiled as plain C++ (tests/emu/build_emu.py rewrites `k<<<grid, block, smem, stream>>>(args)` into
-// flpr_emu::launch(...) and includes this header instead of csrc/ptx.cuh). Every CUDA thread of a block is a ucontext
-// fiber on ONE OS thread; blocks run one after the other:
+// flpr_emu::launch(...), turns `__shared__` declarations into block-local storage, drops the inline-PTX helpers and
+// includes this header instead of csrc/ptx.cuh). Every CUDA thread is a ucontext fiber on ONE OS thread:
 //   * __syncthreads / __syncthreads_or : cooperative block barrier (threads that returned from the kernel stop counting,
 //                                        as on the hardware);
 //   * __shfl_xor_sync / __shfl_sync / __shfl_down_sync : exchange through a per-warp buffer between two warp barriers -
 //                                        the lanes really read each other's registers, so a wrong lane mask or a shuffle
 //                                        under divergent control flow shows up as a wrong result or a reported deadlock;
-//   * __shared__                       : a function-local static (one block at a time).
-// What this checks: index mathematics, reductions, argument marshalling of the extern "C" entry points, barrier placement
-// (a barrier that not every live thread reaches is reported as a deadlock instead of hanging). What it cannot check:
-// alignment faults, memory-model races between warps, performance.
+//   * __shared__                       : storage owned by the running block.
+// Two execution modes:
+//   * immediate (default): `launch` runs the grid block by block and returns when the kernel is done (layer_ops.cu);
+//   * deferred (flpr_emu_defer(1)): launches are queued per stream key; flpr_emu_run(seed, ...) then executes ALL queues
+//     concurrently - kernels of one queue in order, every block of a running kernel resident, fibers picked in a seeded
+//     random order with random stalls. This is how the peer-memory collectives of fedcomm.cu run here: R "ranks" are R
+//     queues whose kernels spin on each other's flags (`ld_acquire_sys` yields), under many different interleavings, with
+//     a virtual `%globaltimer` so that the watchdog path is testable, and an emulated NVSwitch multicast window for the
+//     `multimem` instructions.
+// What this checks: index mathematics, reductions, barrier placement, the flag / epoch protocol under sequentially
+// consistent interleavings, argument marshalling of the extern "C" entry points. What it cannot check: alignment
+// faults, weak-memory-model effects (missing fences), performance.
 #pragma once
 
 #include <cuda_bf16.h>
@@ -23,11 +31,11 @@
 #include <string.h>
 #include <ucontext.h>
 
+#include <deque>
 #include <functional>
+#include <map>
 #include <vector>
 
-#undef __shared__
-#define __shared__ static
 #undef __global__
 #define __global__
 #undef __device__
@@ -42,77 +50,127 @@ namespace flpr_emu {
 struct Dim3 {
   unsigned x = 0, y = 0, z = 0;
 };
-static Dim3 g_tid, g_bid, g_bdim, g_gdim;   // (internal linkage: one emulator state per emulated library)
 
 constexpr int MAX_THREADS = 1024;
-constexpr int MAX_WARPS = MAX_THREADS / 32;
-constexpr size_t STACK_BYTES = 64 * 1024;
+constexpr size_t STACK_BYTES = 32 * 1024;
+
+struct Block;
+struct KernelRun;
+
+struct Fiber {
+  ucontext_t ctx;
+  Block* blk = nullptr;
+  Dim3 tid;
+  bool done = false;
+};
+
+struct WarpState {
+  int alive = 0, count = 0;
+  unsigned gen = 0;
+  uint64_t buf[32];
+};
 
 struct Block {
-  int n = 0, alive = 0, cur = 0;
-  ucontext_t main_ctx;
-  ucontext_t ctx[MAX_THREADS];
-  bool done[MAX_THREADS];
-  // block barrier
+  KernelRun* k = nullptr;
+  Dim3 bid;
+  int n = 0, alive = 0;
   int sync_count = 0, sync_or = 0, sync_or_result = 0;
   unsigned sync_gen = 0;
-  // warp barriers + exchange buffers
-  int warp_alive[MAX_WARPS], warp_count[MAX_WARPS];
-  unsigned warp_gen[MAX_WARPS];
-  uint64_t warp_buf[MAX_WARPS][32];
-  const std::function<void()>* body = nullptr;
-  unsigned long long progress = 0;   // bumped whenever a barrier releases or a thread exits (deadlock detection)
+  std::vector<WarpState> warps;
+  std::vector<Fiber> fibers;
+  std::map<int, void*> shared;
+  char* stacks = nullptr;
 };
-static Block g_blk;
-static char* g_stacks = nullptr;
+
+struct KernelRun {
+  Dim3 gdim, bdim;
+  std::function<void()> body;
+  std::vector<Block*> blocks;
+  unsigned slow = 0;             // deferred runs: this kernel's threads only run in one of `slow` passes (a slow rank)
+};
+
+struct Pending {
+  unsigned grid, block;
+  std::function<void()> body;
+};
+
+struct Multicast {
+  char* base;
+  size_t bytes;
+  std::vector<char*> members;
+};
+
+// (internal linkage: one emulator state per emulated library)
+static Fiber* g_cur = nullptr;
+static ucontext_t g_main;
+static unsigned long long g_progress = 0;   // bumped whenever a barrier releases or a thread exits
+static unsigned long long g_clock_ns = 0;   // virtual %globaltimer
 static int g_deadlocks = 0;
+static bool g_defer = false;
+static unsigned g_stall_one_in = 0;         // deferred runs: a memory-op yield point stalls with probability 1 / this
+static uint64_t g_rng = 0x9e3779b97f4a7c15ull;
+static std::map<const void*, std::deque<Pending>> g_queues;
+static std::map<const void*, int> g_start_delay;
+static std::map<const void*, unsigned> g_lane_slow;
+static std::vector<Multicast> g_mc;
 
-inline void yield() { swapcontext(&g_blk.ctx[g_blk.cur], &g_blk.main_ctx); }
+static inline uint64_t rnd() {
+  g_rng ^= g_rng << 13;
+  g_rng ^= g_rng >> 7;
+  g_rng ^= g_rng << 17;
+  return g_rng;
+}
 
-inline void release_block_barrier() {
-  Block& b = g_blk;
+static inline void yield() {
+  Fiber* me = g_cur;
+  swapcontext(&me->ctx, &g_main);
+}
+static inline void maybe_yield() {
+  if (g_stall_one_in && rnd() % g_stall_one_in == 0) yield();
+}
+
+static inline void release_block_barrier(Block& b) {
   b.sync_or_result = b.sync_or;
   b.sync_or = 0;
   b.sync_count = 0;
   b.sync_gen++;
-  b.progress++;
+  g_progress++;
 }
 
-inline int sync_impl(int pred) {
-  Block& b = g_blk;
+static inline int sync_impl(int pred) {
+  Block& b = *g_cur->blk;
   const unsigned g = b.sync_gen;
   b.sync_or |= (pred != 0);
   if (++b.sync_count == b.alive)
-    release_block_barrier();
+    release_block_barrier(b);
   else
     while (b.sync_gen == g) yield();
   return b.sync_or_result;
 }
 
-inline void warp_barrier(int w) {
-  Block& b = g_blk;
-  const unsigned g = b.warp_gen[w];
-  if (++b.warp_count[w] == b.warp_alive[w]) {
-    b.warp_count[w] = 0;
-    b.warp_gen[w]++;
-    b.progress++;
+static inline void warp_barrier() {
+  WarpState& w = g_cur->blk->warps[g_cur->tid.x >> 5];
+  const unsigned g = w.gen;
+  if (++w.count == w.alive) {
+    w.count = 0;
+    w.gen++;
+    g_progress++;
   } else {
-    while (b.warp_gen[w] == g) yield();
+    while (w.gen == g) yield();
   }
 }
 
-inline uint64_t exchange(uint64_t v, int src_lane) {
-  Block& b = g_blk;
-  const int w = b.cur >> 5, l = b.cur & 31;
-  b.warp_buf[w][l] = v;
-  warp_barrier(w);
-  const uint64_t r = b.warp_buf[w][src_lane & 31];
-  warp_barrier(w);
+static inline uint64_t exchange(uint64_t v, int src_lane) {
+  WarpState& w = g_cur->blk->warps[g_cur->tid.x >> 5];
+  w.buf[g_cur->tid.x & 31] = v;
+  warp_barrier();
+  const uint64_t r = w.buf[src_lane & 31];
+  warp_barrier();
   return r;
 }
 
 template <class T>
-inline T shfl_from(T v, int src_lane) {
+static inline T shfl_from(T v, int src_lane) {
   static_assert(sizeof(T) <= 8, "shuffle payload");
   uint64_t bits = 0;
   memcpy(&bits, &v, sizeof(T));
@@ -122,123 +180,336 @@ inline T shfl_from(T v, int src_lane) {
   return out;
 }
 
-inline void fiber_entry() {
-  Block& b = g_blk;
-  (*b.body)();
-  const int t = b.cur, w = t >> 5;
-  b.done[t] = true;
-  b.alive--;
-  b.warp_alive[w]--;
-  b.progress++;
-  // threads that exited no longer take part in barriers: release the ones that were only waiting for this thread
-  if (b.sync_count > 0 && b.sync_count == b.alive) release_block_barrier();
-  if (b.warp_count[w] > 0 && b.warp_count[w] == b.warp_alive[w]) {
-    b.warp_count[w] = 0;
-    b.warp_gen[w]++;
-  }
-  // uc_link returns to main_ctx
+// block-local storage behind a `__shared__` declaration (id = position of the declaration in the source)
+template <class T>
+static inline T* shared(int id) {
+  Block& b = *g_cur->blk;
+  auto it = b.shared.find(id);
+  if (it == b.shared.end()) it = b.shared.emplace(id, calloc(1, sizeof(T))).first;
+  return reinterpret_cast<T*>(it->second);
 }
 
-inline void run_block(unsigned bid, unsigned grid, unsigned block, const std::function<void()>& body) {
-  Block& b = g_blk;
+static void fiber_entry() {
+  Fiber* me = g_cur;
+  me->blk->k->body();
+  Block& b = *me->blk;
+  WarpState& w = b.warps[me->tid.x >> 5];
+  me->done = true;
+  b.alive--;
+  w.alive--;
+  g_progress++;
+  // threads that exited no longer take part in barriers: release the ones that were only waiting for this thread
+  if (b.sync_count > 0 && b.sync_count == b.alive) release_block_barrier(b);
+  if (w.count > 0 && w.count == w.alive) {
+    w.count = 0;
+    w.gen++;
+  }
+  // uc_link returns to g_main
+}
+
+static Block* make_block(KernelRun* k, unsigned bid) {
+  const unsigned n = k->bdim.x;
+  Block* b = new Block();
+  b->k = k;
+  b->bid.x = bid;
+  b->n = b->alive = (int)n;
+  b->warps.resize((n + 31) / 32);
+  for (unsigned w = 0; w < b->warps.size(); ++w) b->warps[w].alive = (int)((n - w * 32 >= 32) ? 32 : n - w * 32);
+  b->fibers.resize(n);
+  b->stacks = (char*)malloc(STACK_BYTES * n);
+  for (unsigned t = 0; t < n; ++t) {
+    Fiber& f = b->fibers[t];
+    f.blk = b;
+    f.tid.x = t;
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = b->stacks + STACK_BYTES * t;
+    f.ctx.uc_stack.ss_size = STACK_BYTES;
+    f.ctx.uc_link = &g_main;
+    makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+  }
+  return b;
+}
+
+static void free_block(Block* b) {
+  for (auto& kv : b->shared) free(kv.second);
+  free(b->stacks);
+  delete b;
+}
+
+static inline void resume(Fiber* f) {
+  g_cur = f;
+  swapcontext(&g_main, &f->ctx);
+  g_cur = nullptr;
+}
+
+static void check_block_size(unsigned block) {
   if (block == 0 || block > (unsigned)MAX_THREADS) {
     fprintf(stderr, "[flpr_emu] unsupported block size %u\n", block);
     abort();
   }
-  if (g_stacks == nullptr) g_stacks = (char*)malloc(STACK_BYTES * MAX_THREADS);
-  b.n = b.alive = (int)block;
-  b.body = &body;
-  b.sync_count = b.sync_or = b.sync_or_result = 0;
-  b.sync_gen = 0;
-  for (int w = 0; w < MAX_WARPS; ++w) {
-    b.warp_count[w] = 0;
-    b.warp_gen[w] = 0;
-    const int lo = w * 32;
-    b.warp_alive[w] = (int)block > lo ? ((int)block - lo >= 32 ? 32 : (int)block - lo) : 0;
-  }
-  g_bid.x = bid;
-  g_gdim.x = grid;
-  g_bdim.x = block;
-  g_bid.y = g_bid.z = 0;
-  g_gdim.y = g_gdim.z = g_bdim.y = g_bdim.z = 1;
-  for (unsigned t = 0; t < block; ++t) {
-    b.done[t] = false;
-    getcontext(&b.ctx[t]);
-    b.ctx[t].uc_stack.ss_sp = g_stacks + STACK_BYTES * t;
-    b.ctx[t].uc_stack.ss_size = STACK_BYTES;
-    b.ctx[t].uc_link = &b.main_ctx;
-    makecontext(&b.ctx[t], (void (*)())fiber_entry, 0);
-  }
-  unsigned long long last = ~0ull;
-  int idle_rounds = 0;
-  while (b.alive > 0) {
-    for (unsigned t = 0; t < block; ++t) {
-      if (b.done[t]) continue;
-      b.cur = (int)t;
-      g_tid.x = t;
-      g_tid.y = g_tid.z = 0;
-      swapcontext(&b.main_ctx, &b.ctx[t]);
-    }
-    if (b.progress == last) {
-      if (++idle_rounds > 4) {   // every live thread is parked at a barrier that can never release
-        fprintf(stderr, "[flpr_emu] deadlock in block %u: %d threads wait at a barrier not every live thread reaches\n",
-                bid, b.alive);
-        g_deadlocks++;
-        return;
+}
+
+// immediate mode: one block at a time
+static void run_now(unsigned grid, unsigned block, const std::function<void()>& body) {
+  check_block_size(block);
+  KernelRun k;
+  k.gdim.x = grid;
+  k.gdim.y = k.gdim.z = k.bdim.y = k.bdim.z = 1;
+  k.bdim.x = block;
+  k.body = body;
+  for (unsigned bid = 0; bid < grid; ++bid) {
+    Block* b = make_block(&k, bid);
+    unsigned long long last = ~0ull;
+    int idle_rounds = 0;
+    while (b->alive > 0) {
+      for (unsigned t = 0; t < block; ++t)
+        if (!b->fibers[t].done) resume(&b->fibers[t]);
+      if (g_progress == last) {
+        if (++idle_rounds > 4) {   // every live thread is parked at a barrier that can never release
+          fprintf(stderr, "[flpr_emu] deadlock in block %u: %d threads wait at a barrier not every live thread reaches\n",
+                  bid, b->alive);
+          g_deadlocks++;
+          break;
+        }
+      } else {
+        idle_rounds = 0;
+        last = g_progress;
       }
-    } else {
-      idle_rounds = 0;
-      last = b.progress;
     }
+    free_block(b);
   }
 }
 
-inline void launch(unsigned grid, unsigned block, const std::function<void()>& body) {
-  for (unsigned bid = 0; bid < grid; ++bid) run_block(bid, grid, block, body);
+static inline void launch(unsigned grid, unsigned block, const void* stream_key, const std::function<void()>& body) {
+  if (!g_defer) {
+    run_now(grid, block, body);
+    return;
+  }
+  check_block_size(block);
+  g_queues[stream_key].push_back(Pending{grid, block, body});
+}
+
+// deferred mode: every queue concurrently, kernels of a queue in order, all blocks of a running kernel resident
+static int run_queues(unsigned seed, long max_passes, unsigned stall_one_in) {
+  struct Lane {
+    const void* key;
+    std::deque<Pending>* q;
+    KernelRun* cur = nullptr;
+    int delay = 0;
+  };
+  std::vector<Lane> lanes;
+  for (auto& kv : g_queues) {
+    Lane l;
+    l.key = kv.first;
+    l.q = &kv.second;
+    auto d = g_start_delay.find(kv.first);
+    l.delay = d == g_start_delay.end() ? 0 : d->second;
+    lanes.push_back(l);
+  }
+  g_rng = 0x9e3779b97f4a7c15ull ^ ((uint64_t)seed * 0xbf58476d1ce4e5b9ull);
+  g_stall_one_in = seed ? stall_one_in : 0;
+  std::vector<Fiber*> live;
+  int rc = 0;
+  long pass = 0;
+  for (;; ++pass) {
+    bool changed = false, any = false;
+    for (Lane& l : lanes) {
+      if (l.cur != nullptr) {
+        bool done = true;
+        for (Block* b : l.cur->blocks) done = done && b->alive == 0;
+        if (done) {
+          for (Block* b : l.cur->blocks) free_block(b);
+          delete l.cur;
+          l.cur = nullptr;
+          l.q->pop_front();
+          changed = true;
+        }
+      }
+      if (l.cur == nullptr && !l.q->empty()) {
+        if (l.delay > 0) {
+          l.delay--;
+        } else {
+          const Pending& p = l.q->front();
+          KernelRun* k = new KernelRun();
+          k->gdim.x = p.grid;
+          k->gdim.y = k->gdim.z = k->bdim.y = k->bdim.z = 1;
+          k->bdim.x = p.block;
+          k->body = p.body;
+          auto sl = g_lane_slow.find(l.key);
+          k->slow = (seed && sl != g_lane_slow.end()) ? sl->second : 0;
+          for (unsigned bid = 0; bid < p.grid; ++bid) k->blocks.push_back(make_block(k, bid));
+          l.cur = k;
+          changed = true;
+          if (seed) l.delay = (int)(rnd() % 3);      // host-side gap before this lane's NEXT launch
+        }
+      }
+      any = any || l.cur != nullptr || !l.q->empty();
+    }
+    if (!any) break;
+    if (pass >= max_passes) {
+      fprintf(stderr, "[flpr_emu] %ld scheduler passes without completion: deadlock (or a livelock)\n", pass);
+      g_deadlocks++;
+      rc = 1;
+      break;
+    }
+    if (changed || live.empty()) {
+      live.clear();
+      for (Lane& l : lanes)
+        if (l.cur != nullptr)
+          for (Block* b : l.cur->blocks)
+            for (Fiber& f : b->fibers)
+              if (!f.done) live.push_back(&f);
+    }
+    if (seed) {
+      for (size_t i = live.size(); i > 1; --i) {
+        const size_t j = rnd() % i;
+        Fiber* t = live[i - 1];
+        live[i - 1] = live[j];
+        live[j] = t;
+      }
+    }
+    size_t kept = 0;
+    for (size_t i = 0; i < live.size(); ++i) {
+      Fiber* f = live[i];
+      const unsigned slow = f->blk->k->slow;
+      const bool stalled = seed && (rnd() % 5 == 0 || (slow > 1 && rnd() % slow != 0));   // this fiber skips the pass
+      if (!f->done && !stalled) resume(f);
+      if (!f->done) live[kept++] = f;
+    }
+    live.resize(kept);
+    g_clock_ns += 1000;
+  }
+  // abandoned work (deadlock): release it
+  for (Lane& l : lanes) {
+    if (l.cur != nullptr) {
+      for (Block* b : l.cur->blocks) free_block(b);
+      delete l.cur;
+    }
+  }
+  g_queues.clear();
+  g_start_delay.clear();
+  g_lane_slow.clear();
+  g_stall_one_in = 0;
+  return rc;
+}
+
+static inline const Multicast* find_mc(const void* p) {
+  const char* c = reinterpret_cast<const char*>(p);
+  for (const Multicast& m : g_mc)
+    if (c >= m.base && c < m.base + m.bytes) return &m;
+  fprintf(stderr, "[flpr_emu] multimem access outside every registered multicast window\n");
+  abort();
 }
 
 }  // namespace flpr_emu
 
-#define threadIdx flpr_emu::g_tid
-#define blockIdx flpr_emu::g_bid
-#define blockDim flpr_emu::g_bdim
-#define gridDim flpr_emu::g_gdim
+#define threadIdx (flpr_emu::g_cur->tid)
+#define blockIdx (flpr_emu::g_cur->blk->bid)
+#define blockDim (flpr_emu::g_cur->blk->k->bdim)
+#define gridDim (flpr_emu::g_cur->blk->k->gdim)
 
-inline void __syncthreads() { flpr_emu::sync_impl(0); }
-inline int __syncthreads_or(int pred) { return flpr_emu::sync_impl(pred); }
-inline void __syncwarp(unsigned = 0xffffffffu) { flpr_emu::warp_barrier(flpr_emu::g_blk.cur >> 5); }
+static inline void __syncthreads() { flpr_emu::sync_impl(0); }
+static inline int __syncthreads_or(int pred) { return flpr_emu::sync_impl(pred); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { flpr_emu::warp_barrier(); }
+static inline void __threadfence_system() {}
+static inline void __threadfence() {}
 
 template <class T>
-inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
-  return flpr_emu::shfl_from(v, (flpr_emu::g_blk.cur & 31) ^ lane_mask);
+static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+  return flpr_emu::shfl_from(v, (int)(flpr_emu::g_cur->tid.x & 31) ^ lane_mask);
 }
 template <class T>
-inline T __shfl_sync(unsigned, T v, int src_lane) {
+static inline T __shfl_sync(unsigned, T v, int src_lane) {
   return flpr_emu::shfl_from(v, src_lane);
 }
 template <class T>
-inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
-  const int l = flpr_emu::g_blk.cur & 31;
+static inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
+  const int l = (int)(flpr_emu::g_cur->tid.x & 31);
   const T r = flpr_emu::shfl_from(v, l + (int)delta);
   return (l + (int)delta < 32) ? r : v;
 }
 
-inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline unsigned atomicExch(unsigned* p, unsigned v) {
+  const unsigned o = *p;
+  *p = v;
+  return o;
+}
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 
-// ---- the pieces of csrc/ptx.cuh the CUDA-core kernels use -----------------------------------------------------------------
+// ---- the pieces of csrc/ptx.cuh (and the inline-PTX helpers of the kernel sources) the CUDA-core kernels use ------------------
 namespace flpr {
-inline void bind_device_of(const void*) {}
-inline float warp_sum(float v) {
+static inline void bind_device_of(const void*) {}
+static inline float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-inline float warp_max(float v) {
+static inline float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+// system-scope flag accesses: the spin loops of the peer-memory protocol are cooperative here
+static inline void st_release_sys(uint32_t* p, uint32_t v) {
+  flpr_emu::maybe_yield();
+  *reinterpret_cast<volatile uint32_t*>(p) = v;
+}
+static inline uint32_t ld_acquire_sys(const uint32_t* p) {
+  flpr_emu::yield();
+  return *reinterpret_cast<const volatile uint32_t*>(p);
+}
+static inline float4 ld_stream_f4(const float4* p) {
+  flpr_emu::maybe_yield();
+  return *p;
+}
+static inline void st_stream_f4(float4* p, const float4& v) {
+  flpr_emu::maybe_yield();
+  *p = v;
+}
+static inline unsigned long long gtimer() {
+  flpr_emu::g_clock_ns += 50;
+  return flpr_emu::g_clock_ns;
+}
+// NVSwitch multicast window: ld_reduce adds the word of every member, st writes it to every member
+static inline float4 multimem_ld_reduce_add_f4(const float* mc) {
+  flpr_emu::maybe_yield();
+  const flpr_emu::Multicast* m = flpr_emu::find_mc(mc);
+  const size_t off = reinterpret_cast<const char*>(mc) - m->base;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (char* b : m->members) {
+    const float4 v = *reinterpret_cast<const float4*>(b + off);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  return s;
+}
+static inline void multimem_st_f4(float* mc, const float4& v) {
+  flpr_emu::maybe_yield();
+  const flpr_emu::Multicast* m = flpr_emu::find_mc(mc);
+  const size_t off = reinterpret_cast<const char*>(mc) - m->base;
+  for (char* b : m->members) *reinterpret_cast<float4*>(b + off) = v;
 }
 }  // namespace flpr
 using flpr::bind_device_of;
 
 #define cudaGetLastError() (cudaSuccess)
 
-extern "C" int flpr_emu_deadlocks() { return flpr_emu::g_deadlocks; }
+extern "C" {
+int flpr_emu_deadlocks() { return flpr_emu::g_deadlocks; }
+void flpr_emu_defer(int on) { flpr_emu::g_defer = on != 0; }
+// Execute everything queued since flpr_emu_defer(1). seed 0: round-robin, no stalls; otherwise a seeded random schedule.
+// Returns 0, or 1 when `max_passes` scheduler passes did not finish the work (deadlock).
+int flpr_emu_run(unsigned seed, long max_passes, unsigned stall_one_in) {
+  return flpr_emu::run_queues(seed, max_passes, stall_one_in ? stall_one_in : 4);
+}
+void flpr_emu_set_start_delay(const void* stream_key, int passes) { flpr_emu::g_start_delay[stream_key] = passes; }
+// Threads of the kernels on this stream only run in one of `one_in` scheduler passes (seeded runs): a slow rank.
+void flpr_emu_set_lane_slowdown(const void* stream_key, unsigned one_in) { flpr_emu::g_lane_slow[stream_key] = one_in; }
+int flpr_emu_mc_register(void* mc_base, size_t bytes, int world, void* const* members) {
+  flpr_emu::Multicast m;
+  m.base = reinterpret_cast<char*>(mc_base);
+  m.bytes = bytes;
+  for (int r = 0; r < world; ++r) m.members.push_back(reinterpret_cast<char*>(members[r]));
+  flpr_emu::g_mc.push_back(m);
+  return (int)flpr_emu::g_mc.size() - 1;
+}
+void flpr_emu_mc_clear() { flpr_emu::g_mc.clear(); }
+unsigned long long flpr_emu_clock_ns() { return flpr_emu::g_clock_ns; }
+}
