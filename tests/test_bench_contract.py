@@ -1,0 +1,60 @@
+"""``bench.py`` prints ONE JSON line with the keys the driver reads (metric / value / e2e / gpu_launches / clocks ...).
+Exercised through ``--cpu-debug`` (a tiny CPU experiment through the same harness: build_config -> ExperimentStage rounds
+-> device-timed region -> end-to-end region -> JSON), so that a refactoring of the harness cannot break the contract
+unnoticed between GPU sessions."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+REQUIRED = {"metric": str, "value": (int, float), "unit": str, "n_gpus": int, "steps": int, "warmup": int,
+            "ms_per_step": (int, float), "higher_is_better": bool, "scaling": str, "dtype": str, "data": str,
+            "config": dict, "e2e": dict, "gpu_launches": int}
+
+
+def _run(*flags, timeout=900):
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *flags], capture_output=True, text=True,
+                       timeout=timeout, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, f"expected exactly one JSON line, got {len(lines)}"
+    return json.loads(lines[0])
+
+
+def test_bench_cpu_debug_prints_the_driver_contract():
+    d = _run("--cpu-debug", "--steps", "1", "--warmup", "1")
+    for key, ty in REQUIRED.items():
+        assert key in d, f"missing key {key}"
+        assert isinstance(d[key], ty), (key, type(d[key]))
+    assert "vs_baseline" in d and "clocks" in d
+    assert d["steps"] == 1 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["higher_is_better"] is True
+    assert d["scaling"] in ("strong", "weak") and d["impl"] == "flpr"
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert key in d["e2e"], key
+    assert d["e2e"]["value"] > 0
+    for key in ("model", "method", "clients", "global_batch"):
+        assert key in d["config"], key
+    conv = d.get("convergence")
+    assert conv and len(conv["tr_loss"]) == conv["rounds"] >= 2 and all(v == v for v in conv["tr_loss"])
+
+
+def test_reference_arm_reports_itself_when_the_reference_is_missing(tmp_path):
+    """``--impl reference`` without ``baseline/_ref`` must print ``{"impl": "reference", "unavailable": ...}`` and exit
+    0 (driver contract). Checked on the arm's own function with the reference directory pointed elsewhere."""
+    sys.path.insert(0, ROOT)
+    from baseline import reference_arm as ra
+    saved = ra.REF
+    ra.REF = str(tmp_path / "nowhere")
+    try:
+        class A:
+            cpu_debug, gpus = True, 1
+        out = ra.run_reference_arm(A(), None, None, "m", None)
+    finally:
+        ra.REF = saved
+    assert out["impl"] == "reference" and "unavailable" in out and "\n" not in out["unavailable"]
