@@ -201,11 +201,28 @@ class ReIDTaskPipeline:
         return self.current_task()
 
     def state_dict(self) -> Dict:
-        return {"current_task_idx": self.current_task_idx, "task_round_rest": list(self.task_round_rest)}
+        """Position in the task schedule + the shuffle generators of the cached train loaders (a task that sustains over
+        several rounds continues ITS permutation sequence: a run resumed in the middle of a task must too)."""
+        rng = {int(k): v for k, v in getattr(self, "_pending_rng", {}).items()}
+        for idx, task in self._cache.items():
+            gen = getattr(task["tr_loader"], "_gen", None)
+            if isinstance(gen, torch.Generator):
+                rng[int(idx)] = gen.get_state()
+        return {"current_task_idx": self.current_task_idx, "task_round_rest": list(self.task_round_rest),
+                "loader_rng": rng}
 
     def load_state_dict(self, sd: Dict) -> None:
         self.current_task_idx = int(sd["current_task_idx"])
         self.task_round_rest = list(sd["task_round_rest"])
+        self._pending_rng = {int(k): v for k, v in (sd.get("loader_rng") or {}).items()}
+        for idx in list(self._cache):
+            self._restore_loader_rng(idx)
+
+    def _restore_loader_rng(self, idx: int) -> None:
+        st = getattr(self, "_pending_rng", {}).pop(idx, None)
+        gen = getattr(self._cache[idx]["tr_loader"], "_gen", None)
+        if st is not None and isinstance(gen, torch.Generator):
+            gen.set_state(st.cpu() if isinstance(st, torch.Tensor) else st)
 
     # ---- loaders ----------------------------------------------------------------------------------------------
     def _split(self, task: str, split: str):
@@ -243,6 +260,7 @@ class ReIDTaskPipeline:
                 "query_loader": self._loader(self._split(task, "query"), False),
                 "gallery_loaders": self._loader(self._split(task, "gallery"), False),
             }
+            self._restore_loader_rng(idx)              # (a resumed run: continue the saved shuffle sequence)
         return self._cache[idx]
 
     def evict(self, keep: Optional[int] = None) -> None:

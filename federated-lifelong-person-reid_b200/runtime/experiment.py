@@ -218,19 +218,22 @@ class ExperimentStage:
         store, comm, server, clients, names = self.build(exp_config)
         timer = DeviceTimer(self.device)
         try:
-            if exp_config["engine_opts"].get("val_at_round0", True) and not (
-                    exp_config["engine_opts"].get("resume") and resume.available(store, self.rank)):
+            eng = exp_config["engine_opts"]
+            # the newest manifest committed on EVERY rank (collective: all ranks take the same branch below, also after
+            # an elastic restart in which some rank died before it could commit anything)
+            resumed = resume.agreed_round(self, store) if eng.get("resume") else 0
+            if eng.get("val_at_round0", True) and not resumed:
                 self._validate_all(clients, names, exp_config, log, 0)   # initial validation (experiment.py:163-173)
             comm_rounds = int(exp_config["exp_opts"]["comm_rounds"])
-            eng = exp_config["engine_opts"]
             first_round = 1
-            if eng.get("resume") and resume.available(store, self.rank):
-                first_round = resume.load(self, store, server, clients, comm) + 1
+            if resumed:
+                first_round = resume.load(self, store, server, clients, comm, resumed) + 1
                 self.logger.info(f"Resumed from the manifest of round {first_round - 1}.")
             interval = int(eng.get("resume_interval", 0) or 0)
             for curr_round in range(first_round, comm_rounds + 1):
                 self.logger.info(f"Start communication round: {curr_round:0>3d}/{comm_rounds:0>3d}")
                 self._process_one_round(curr_round, server, clients, names, exp_config, log, timer, comm)
+                resume.maybe_inject_fault(self, curr_round, "round")
                 if interval and curr_round % interval == 0:
                     if self.device.type == "cuda":
                         self._join_deferred_aggregate()          # the manifest snapshots the server replica

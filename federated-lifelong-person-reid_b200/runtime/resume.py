@@ -11,12 +11,29 @@ server registry or token memory is restorable; a rerun starts at round 1 on stal
         comm   : this rank's slots of every symmetric client buffer (the *last uploads* that the stale-client
                  aggregation of ``methods/fedavg.py:386-397`` keeps using) and the rank buffers
 
-It goes through the asynchronous :class:`CheckpointStore` like every other snapshot. ``load(stage, ...)`` restores it
-after ``ExperimentStage.build`` and returns the round to continue from. Method plug-ins extend the picture through
+It goes through the :class:`CheckpointStore` like every other snapshot. ``load(stage, ...)`` restores it after
+``ExperimentStage.build`` and returns the round to continue from. Method plug-ins extend the picture through
 ``resume_extra() / load_resume_extra()`` on their ``Model`` / ``Client`` / ``Server`` classes.
+
+**Rank loss / elastic restart** (SURVEY 5.3). A rank that dies takes the job down: its peers' collectives time out
+(flag watchdog -> ``NativeError``; gloo / NCCL: a failed collective), ``torchrun --max-restarts N`` restarts the whole
+group, and with ``engine_opts.resume`` every rank continues from the manifest. For that the manifests of the ranks must
+describe the SAME round even when the crash hits in the middle of a save:
+
+* two generations per rank, ``rank{r}-g0`` / ``rank{r}-g1``; a save overwrites the older one;
+* a generation counts only with its commit marker ``rank{r}-g{k}.ckpt.ok`` (``{"round": n}``, written by atomic rename).
+  The marker of the generation about to be overwritten is removed first; the new marker is written after the snapshot is
+  durable on this rank (``store.flush()``) **and every rank has reached that point** (host barrier) - so a marker for
+  round n on any rank implies a complete round-n file on all ranks, and because ranks are never more than one save
+  apart, the sets of committed rounds of any two ranks always intersect;
+* ``load`` all-gathers the committed rounds and takes the newest round every rank has.
+``FLPR_FAULT_EXIT=rank:round[:phase]`` (first attempt of an elastic job only) makes a rank exit hard at ``phase`` =
+``round`` (after the round, before the save), ``saving`` (snapshot written, marker not yet) or ``saved`` - the fault
+injection behind ``tests/dist_resume_check.py``.
 """
 from __future__ import annotations
 
+import json
 import os
 import random
 from typing import Any, Dict
@@ -90,16 +107,89 @@ def save(stage, store, curr_round: int, server, clients, comm) -> None:
             else:
                 bufs[name] = comm.rank_view(name)
         state["comm"] = bufs
-    store.save(ACTOR, f"rank{stage.rank}", state, True)
+    committed = _committed(store, stage.rank)               # {round: generation}
+    gen = 1 - committed[max(committed)] if committed else 0  # never the newest committed one: the older / uncommitted
+    marker = _marker(store, stage.rank, gen)
+    if os.path.exists(marker):
+        os.remove(marker)                                   # a torn overwrite must never look committed
+    store.save(ACTOR, _gen_name(stage.rank, gen), state, True)
+    store.flush()                                           # durable on this rank ...
+    maybe_inject_fault(stage, curr_round, "saving")
+    _host_barrier(stage)                                    # ... and on every other rank
+    tmp = f"{marker}.tmp{os.getpid()}"
+    with open(tmp, "w") as f:
+        json.dump({"round": int(curr_round), "world": stage.world}, f)
+    os.replace(tmp, marker)
+    maybe_inject_fault(stage, curr_round, "saved")
+
+
+def _gen_name(rank: int, gen: int) -> str:
+    return f"rank{rank}-g{gen}"
+
+
+def _marker(store, rank: int, gen: int) -> str:
+    return store.path(ACTOR, _gen_name(rank, gen)) + ".ok"
+
+
+def _committed(store, rank: int) -> Dict[int, int]:
+    """``{round: generation}`` of this rank's committed manifests (marker present, file present)."""
+    out: Dict[int, int] = {}
+    for gen in (0, 1):
+        marker = _marker(store, rank, gen)
+        if os.path.exists(marker) and os.path.exists(store.path(ACTOR, _gen_name(rank, gen))):
+            try:
+                with open(marker) as f:
+                    out[int(json.load(f)["round"])] = gen
+            except (OSError, ValueError, KeyError):
+                pass
+    return out
+
+
+def _host_barrier(stage) -> None:
+    import torch.distributed as dist
+    if stage.world > 1 and dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+def maybe_inject_fault(stage, curr_round: int, phase: str) -> None:
+    """``FLPR_FAULT_EXIT=rank:round[:phase]``: hard exit of one rank (``os._exit``: no cleanup, no flush - a crash), on
+    the first attempt of an elastic job only (``TORCHELASTIC_RESTART_COUNT`` 0 / unset)."""
+    spec = os.environ.get("FLPR_FAULT_EXIT")
+    if not spec or os.environ.get("TORCHELASTIC_RESTART_COUNT", "0") != "0":
+        return
+    parts = spec.split(":")
+    if int(parts[0]) == stage.rank and int(parts[1]) == int(curr_round) and (parts[2] if len(parts) > 2 else "round") == phase:
+        os._exit(17)
 
 
 def available(store, rank: int) -> bool:
-    return os.path.exists(store.path(ACTOR, f"rank{rank}"))
+    """A committed manifest of THIS rank exists (rank-local: use :func:`agreed_round` to decide what a job does)."""
+    return bool(_committed(store, rank))
 
 
-def load(stage, store, server, clients, comm) -> int:
-    """Restore a snapshot written by :func:`save`; returns the last completed round."""
-    st = store.load(ACTOR, f"rank{stage.rank}")
+def agreed_round(stage, store) -> int:
+    """Newest round whose manifest is committed on EVERY rank (0: none). Collective when ``world > 1``: every rank must
+    call it, and every rank gets the same answer."""
+    mine = sorted(_committed(store, stage.rank))
+    import torch.distributed as dist
+    if stage.world > 1 and dist.is_available() and dist.is_initialized():
+        everyone = [None] * stage.world
+        dist.all_gather_object(everyone, mine)
+        common = set(everyone[0]).intersection(*map(set, everyone[1:]))
+    else:
+        common = set(mine)
+    return max(common) if common else 0
+
+
+def load(stage, store, server, clients, comm, rnd: int = None) -> int:
+    """Restore the manifest of round ``rnd`` (default: :func:`agreed_round`, the newest one committed on every rank);
+    returns that round (0: nothing to resume from - the caller starts at round 1 on the freshly built state)."""
+    if rnd is None:
+        rnd = agreed_round(stage, store)
+    if rnd == 0:
+        return 0
+    st = store.load(ACTOR, _gen_name(stage.rank, _committed(store, stage.rank)[rnd]))
+    assert int(st["round"]) == rnd, (st["round"], rnd)
     if int(st.get("world", 1)) != stage.world:
         raise RuntimeError(f"resume manifest was written with world_size={st.get('world')}, now {stage.world}")
     random.setstate(st["py_random"])

@@ -34,7 +34,7 @@ def _run(tmp, method, rounds, resume=False, interval=0):
         store.flush()
         out = {"server": server.model.arena.master.clone(),
                "clients": [c.model.arena.master.clone() for c in clients],
-               "pipe": [c.task_pipeline.state_dict() for c in clients],
+               "pipe": [{k: v for k, v in c.task_pipeline.state_dict().items() if k != "loader_rng"} for c in clients],
                "cnt": [c.train_cnt for c in clients]}
         store.close()
         if comm is not None:
@@ -53,3 +53,73 @@ def test_resume_continues_where_it_stopped(tmp_path, method):
     assert torch.allclose(cont["server"], full["server"], atol=1e-5)
     for a, b in zip(cont["clients"], full["clients"]):
         assert torch.allclose(a, b, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------- rank loss
+def _torchrun(tmp, rounds, fault=None, timeout=600):
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(__file__), "dist_resume_check.py")
+    env = dict(os.environ, FLPR_TMP=str(tmp), OMP_NUM_THREADS="2")
+    env.pop("FLPR_FAULT_EXIT", None)
+    if fault:
+        env["FLPR_FAULT_EXIT"] = fault
+    return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
+                           "--nproc-per-node", "2", script, "fedavg", str(rounds)], env=env, capture_output=True,
+                          text=True, timeout=timeout)
+
+
+def _results(tmp):
+    return [torch.load(os.path.join(str(tmp), f"result_rank{r}.pt"), weights_only=False) for r in (0, 1)]
+
+
+def _flat(state):
+    return torch.cat([v.float().flatten() for _, v in sorted(state.items()) if torch.is_tensor(v)])
+
+
+@pytest.fixture(scope="module")
+def uninterrupted(tmp_path_factory):
+    tmp = tmp_path_factory.mktemp("resume_full")
+    r = _torchrun(tmp, 4)
+    assert r.returncode == 0 and r.stdout.count("DIST_RESUME") == 2, r.stdout[-2000:] + r.stderr[-2000:]
+    return _results(tmp)
+
+
+@pytest.mark.parametrize("phase", ["round", "saving", "saved"])
+def test_rank_loss_then_restart_resumes_consistently(tmp_path, uninterrupted, phase):
+    """World 2 (gloo): rank 1 exits hard in round 3 - after the round but before its manifest (``round``), with the
+    snapshot written but not committed (``saving``), or right after its commit marker (``saved``); the job dies with
+    it. A restart on the same directories must pick the newest manifest committed on BOTH ranks (never a torn or a
+    one-sided one) and finish with exactly the weights of the uninterrupted run."""
+    crashed = _torchrun(tmp_path, 4, fault=f"1:3:{phase}")
+    assert crashed.returncode != 0, "the fault was not injected"
+    assert "DIST_RESUME" not in crashed.stdout
+    again = _torchrun(tmp_path, 4)
+    assert again.returncode == 0 and again.stdout.count("DIST_RESUME") == 2, again.stdout[-2000:] + again.stderr[-2000:]
+    assert "Resumed from the manifest of round" in again.stdout + again.stderr
+    for full, got in zip(uninterrupted, _results(tmp_path)):
+        assert got["cnt"] == full["cnt"]
+        assert torch.allclose(_flat(got["server"]), _flat(full["server"]), atol=1e-5)
+        for name in full["clients"]:
+            assert torch.allclose(_flat(got["clients"][name]), _flat(full["clients"][name]), atol=1e-5)
+
+
+def test_manifest_generations_and_commit_markers(tmp_path):
+    """Single process: two generations alternate, the generation being overwritten loses its marker first, a file without
+    a marker (a crash between snapshot and commit) is ignored by ``load``."""
+    from flpr_b200.runtime import resume as R
+    from flpr_b200.runtime.checkpoint import CheckpointStore
+    _run(str(tmp_path), "fedavg", 3, interval=1)
+    store = CheckpointStore(os.path.join(str(tmp_path), "ckpts", "t-fedavg"), asynchronous=False)
+    committed = R._committed(store, 0)
+    assert sorted(committed) == [2, 3] and sorted(committed.values()) == [0, 1]
+    os.remove(R._marker(store, 0, committed[3]))                     # as if the process had died before committing round 3
+    assert sorted(R._committed(store, 0)) == [2]
+
+    class Stage:
+        world, rank = 1, 0
+    assert R.agreed_round(Stage(), store) == 2
+    cont, first = _run(str(tmp_path), "fedavg", 4, resume=True, interval=1)
+    assert first == 3
+    full, _ = _run(str(tmp_path / "full"), "fedavg", 4)
+    assert torch.allclose(cont["server"], full["server"], atol=1e-5)
