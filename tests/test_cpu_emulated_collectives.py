@@ -307,3 +307,51 @@ def test_ranks_launching_different_grids_are_caught_not_hung_on(comm_lib):
     assert w.error_word(0) == 1
     w.close()
     comm_lib.flpr_comm_set_one_shot_bytes(1 << 20)
+
+
+# ------------------------------------------------------------------------------------------------------------ limits
+@pytest.mark.parametrize("world,clients,local,n,blocks,one_shot", [
+    (2, 32, 8, 4 * 37, 1, False),          # MAX_CLIENTS sources, MAX_LOCAL receivers on one rank, fewer elements than threads
+    (8, 32, 4, 4 * 5, 2, False),           # MAX_RANKS, slices of the two-shot mean smaller than one element per rank
+    (8, 8, 1, 4, 4, False),                # ONE float4 spread over 8 ranks x 4 blocks
+    (4, 9, 3, 4 * 513, 2, True),           # one-shot form, a size just past a block boundary
+])
+def test_compile_time_limits_and_tiny_buffers(comm_lib, world, clients, local, n, blocks, one_shot):
+    """The table sizes of ``fedcomm.cu`` (32 clients, 8 local receivers, 8 ranks) and buffers far smaller than the grid:
+    mean (peer loads), mean (switch), mix and client-last gather with a 1-element tail, all in one queue per rank."""
+    for seed in (0, 3):
+        comm_lib.flpr_comm_set_one_shot_bytes((1 << 30) if one_shot else 0)
+        w = make_world(comm_lib, world=world, blocks=blocks)
+        up = [rand(n, 10 * seed + c) for c in range(clients)]
+        cnt = [torch.tensor([float(1 + (c % 5))]) for c in range(clients)]
+        dst, dst2, partial = ([torch.zeros(n) for _ in range(world)] for _ in range(3))
+        rows = [[torch.softmax(rand(clients, seed + 100 * r + i), 0) for i in range(local)] for r in range(world)]
+        g = [[torch.zeros(n) for _ in range(local)] for _ in range(world)]
+        b16 = [[torch.zeros(n, dtype=torch.bfloat16) for _ in range(local)] for _ in range(world)]
+        feat = [rand(n + 1, 7 * seed + c) for c in range(clients)]
+        gathered = [torch.zeros(n + 1, clients) for _ in range(world)]
+        mc_partial, mc_dst = w.multicast(partial), w.multicast(dst2)
+        hosted = {r: [c for c in range(clients) if c % world == r][:8] for r in range(world)}   # <= MAX_LOCAL per rank
+        part = sorted(c for r in range(world) for c in hosted[r])
+        tot, totp = sum(float(c) for c in cnt), sum(float(cnt[c]) for c in part)
+        for r in range(world):
+            w.reduce_bcast(r, up, dst, cnt=cnt)
+            w.mix(r, up, [x.tolist() for x in rows[r]], g[r], [None] * local, b16[r])
+            w.gather_strided(r, feat, gathered[r], n + 1)
+            w.reduce_bcast_nvls(r, [up[c] for c in hosted[r]], [cnt[c] for c in hosted[r]], None,
+                                [cnt[c] for c in part], totp, partial[r], mc_partial, mc_dst, len(part))
+        skew(w, seed)
+        assert w.run(seed, max_passes=400000) == 0
+        ref = sum(u * (float(c) / tot) for u, c in zip(up, cnt))
+        refp = sum(up[c] * (float(cnt[c]) / totp) for c in part)
+        for r in range(world):
+            close(dst[r], ref, tol=4e-6)
+            close(dst2[r], refp, tol=4e-6)
+            assert torch.equal(gathered[r], torch.stack(feat, 1))
+            for i in range(local):
+                want = sum(rows[r][i][j] * up[j] for j in range(clients))
+                close(g[r][i], want, tol=4e-6)
+                close(b16[r][i], want, tol=8e-3)
+            assert w.error_word(r) == 0
+        w.close()
+    comm_lib.flpr_comm_set_one_shot_bytes(1 << 20)
