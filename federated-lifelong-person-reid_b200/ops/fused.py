@@ -10,6 +10,43 @@ import torch.nn.functional as F
 
 from . import native
 
+# ---- tests only: host builds of csrc/fused_ops.cu / loss_ops.cu under the SIMT emulator (tests/emu) ----------------------------
+_emu_libs: list = []
+
+
+def use_emulated_libraries(paths) -> None:
+    """Route the wrappers of this module to emulated libraries (``None`` / empty: back to normal). With them installed,
+    CPU tensors take the KERNEL path - same argument marshalling, same ``extern "C"`` entry points as on the device."""
+    import ctypes
+    _emu_libs.clear()
+    for path in (paths or []):
+        lib = ctypes.CDLL(path)
+        native.declare_present(lib)
+        _emu_libs.append(lib)
+
+
+class _EmuDispatch:
+    """``lib.flpr_xyz`` resolved over the installed emulated libraries."""
+
+    def __getattr__(self, name):
+        for lib in _emu_libs:
+            if hasattr(lib, name):
+                return getattr(lib, name)
+        raise AttributeError(name)
+
+
+def _lib():
+    return _EmuDispatch() if _emu_libs else native.load()
+
+
+def _native(t: torch.Tensor) -> bool:
+    """The kernel path applies to ``t``: a CUDA tensor - or any tensor while emulated libraries are installed."""
+    return t.is_cuda or bool(_emu_libs)
+
+
+def _stream(device):
+    return native.c_void_p(0) if _emu_libs else native.stream(device)
+
 
 # --------------------------------------------------------------------------------------------- optimizers
 def fused_optimizer_step(kind: str, p: torch.Tensor, g: torch.Tensor, m: Optional[torch.Tensor],
@@ -32,9 +69,9 @@ def fused_optimizer_step(kind: str, p: torch.Tensor, g: torch.Tensor, m: Optiona
     ``-lam1*sign(p - theta0) + wd*(theta0 - atten*G)`` and its own moments (reference ``fedstil.py:53-76,639-647``).
     """
     adam = kind == "adam"
-    if hyper is not None and not p.is_cuda:
+    if hyper is not None and not _native(p):
         lr, step = float(hyper[0]), int(hyper[1])
-    if not p.is_cuda:
+    if not _native(p):
         assert anchor is None, "the CPU path of the trained anchor is ArenaOptimizer._anchor_step"
         with torch.no_grad():
             grad = g.clone()
@@ -66,25 +103,25 @@ def fused_optimizer_step(kind: str, p: torch.Tensor, g: torch.Tensor, m: Optiona
             if p_bf16 is not None:
                 p_bf16.copy_(p)
         return
-    lib = native.load()
+    lib = _lib()
     rc = lib.flpr_fused_opt(int(adam), native.ptr(p), native.ptr(g), native.ptr(m), native.ptr(v), native.ptr(Q),
                             native.ptr(R), native.ptr(G), native.ptr(p_bf16), native.ptr(stats), p.numel(), lr, beta1,
                             beta2, eps, weight_decay, int(step), lam2, lam1, atten, momentum, int(penalty_ones),
                             native.ptr(hyper), native.ptr(anchor if G is not None else None), native.ptr(anchor_m),
-                            native.ptr(anchor_v), native.stream(p.device))
+                            native.ptr(anchor_v), _stream(p.device))
     native.check(rc, "flpr_fused_opt")
     native.count_launch()
 
 
 def importance_accumulate(Fbuf: torch.Tensor, g: torch.Tensor, scale: float, mode: str = "fisher") -> None:
     """``F += scale * g**2`` (fisher) or ``F += scale * |g|`` (mas)."""
-    if not Fbuf.is_cuda:
+    if not _native(Fbuf):
         with torch.no_grad():
             Fbuf.add_((g * g) if mode == "fisher" else g.abs(), alpha=scale)
         return
-    lib = native.load()
+    lib = _lib()
     rc = lib.flpr_importance_accum(native.ptr(Fbuf), native.ptr(g), Fbuf.numel(), scale, 0 if mode == "fisher" else 1,
-                                   native.stream(Fbuf.device))
+                                   _stream(Fbuf.device))
     native.check(rc, "flpr_importance_accum")
     native.count_launch()
 
@@ -92,11 +129,11 @@ def importance_accumulate(Fbuf: torch.Tensor, g: torch.Tensor, scale: float, mod
 def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     if out is None:
         out = torch.empty_like(x, dtype=torch.bfloat16)
-    if not x.is_cuda or x.numel() % 4 or not x.is_contiguous():
+    if not _native(x) or x.numel() % 4 or not x.is_contiguous():
         out.copy_(x)
         return out
-    lib = native.load()
-    native.check(lib.flpr_cast_bf16(native.ptr(x), native.ptr(out), x.numel(), native.stream(x.device)), "flpr_cast_bf16")
+    lib = _lib()
+    native.check(lib.flpr_cast_bf16(native.ptr(x), native.ptr(out), x.numel(), _stream(x.device)), "flpr_cast_bf16")
     native.count_launch()
     return out
 
@@ -104,16 +141,16 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
 def compose_adaptive(G: torch.Tensor, A: torch.Tensor, atten: float, theta: Optional[torch.Tensor] = None,
                      theta_bf16: Optional[torch.Tensor] = None) -> None:
     """theta = atten * G + A (FedSTIL adaptive compose, ``methods/fedstil.py:85``) with optional bf16 copy."""
-    if not G.is_cuda:
+    if not _native(G):
         t = atten * G + A
         if theta is not None:
             theta.copy_(t)
         if theta_bf16 is not None:
             theta_bf16.copy_(t)
         return
-    lib = native.load()
+    lib = _lib()
     native.check(lib.flpr_compose(native.ptr(G), native.ptr(A), atten, native.ptr(theta), native.ptr(theta_bf16),
-                                  G.numel(), native.stream(G.device)), "flpr_compose")
+                                  G.numel(), _stream(G.device)), "flpr_compose")
     native.count_launch()
 
 
@@ -133,10 +170,10 @@ class _CELabelSmoothFn(torch.autograd.Function):
         b, c = logits.shape
         dlogits = torch.empty_like(logits)
         local = torch.zeros(2, dtype=torch.float32, device=logits.device)
-        lib = native.load()
+        lib = _lib()
         rc = lib.flpr_ce_label_smooth(native.ptr(logits), native.ptr(target), native.ptr(dlogits), native.ptr(local), b,
                                       c, logits.stride(0), eps, 1.0 / b, int(logits.dtype == torch.bfloat16),
-                                      int(dlogits.dtype == torch.bfloat16), native.stream(logits.device))
+                                      int(dlogits.dtype == torch.bfloat16), _stream(logits.device))
         native.check(rc, "flpr_ce_label_smooth")
         native.count_launch()
         if stats is not None:
@@ -154,7 +191,7 @@ def ce_label_smooth(logits: torch.Tensor, target: torch.Tensor, eps: float = 0.1
                     stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Label-smoothing cross entropy. ``stats`` (float[2], optional) accumulates [loss, #top-1 hits] on device, which
     replaces the per-step ``.cpu().item()`` syncs of ``methods/baseline.py:47-48``."""
-    if not logits.is_cuda:
+    if not _native(logits):
         loss = ce_label_smooth_reference(logits, target, eps)
         if stats is not None:
             with torch.no_grad():
@@ -177,7 +214,7 @@ class _BNTrainFn(torch.autograd.Function):
         m, c = x.shape
         dev = x.device
         y = torch.empty_like(x)
-        lib = native.load()
+        lib = _lib()
         scratch = torch.empty(6, c, dtype=torch.float32, device=dev)  # -, -, mean, rstd, scale, shift
         if pre_part is None:
             part = torch.empty(lib.flpr_bn_partials_floats(m, c), dtype=torch.float32, device=dev)
@@ -189,7 +226,7 @@ class _BNTrainFn(torch.autograd.Function):
                              native.ptr(part), native.ptr(scratch[2]),
                              native.ptr(scratch[3]), native.ptr(scratch[4]), native.ptr(scratch[5]),
                              native.ptr(running_mean), native.ptr(running_var), m, c, eps, momentum, int(relu),
-                             native.ptr(pre_part), npre, native.stream(dev))
+                             native.ptr(pre_part), npre, _stream(dev))
         native.check(rc, "flpr_bn_fwd")
         native.count_launch(3 if pre_part is None else 2)
         ctx.save_for_backward(x, y, gamma, scratch)
@@ -208,13 +245,13 @@ class _BNTrainFn(torch.autograd.Function):
         dgb = None if direct else torch.empty(2, c, dtype=torch.float32, device=x.device)
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
-        lib = native.load()
+        lib = _lib()
         part = torch.empty(lib.flpr_bn_partials_floats(m, c), dtype=torch.float32, device=x.device)
         rc = lib.flpr_bn_bwd(native.ptr(dy), native.ptr(y), native.ptr(x), native.ptr(scratch[2]),
                              native.ptr(scratch[3]), native.ptr(gamma),
                              native.ptr(ggrad if direct else dgb[0]), native.ptr(bgrad if direct else dgb[1]),
                              native.ptr(part), native.ptr(dres), native.ptr(dx), m, c, int(ctx.relu), int(direct),
-                             native.stream(x.device))
+                             _stream(x.device))
         native.check(rc, "flpr_bn_bwd")
         native.count_launch(3)
         if direct:
@@ -229,7 +266,7 @@ def batch_norm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, ru
     """BatchNorm over ``[M, C]`` (channels last) with fused residual + ReLU. fp32 affine parameters.
     ``pre_part`` ``[P, 2, C]``: column partials (sum, sum of squares) of the producer's fp32 output, written by the
     GEMM / conv epilogue; when given, the statistics pass over ``x`` is skipped."""
-    if not x.is_cuda:
+    if not _native(x):
         xf = x.float()
         if training:
             if pre_part is not None:
@@ -267,17 +304,17 @@ def batch_norm_nhwc(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, ru
 def affine_act(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, *, relu: bool = False,
                residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = relu?(x * scale[c] + shift[c] (+ residual)) over ``[M, C]`` bf16 (inference-mode BN)."""
-    if not x.is_cuda:
+    if not _native(x):
         y = x.float() * scale + shift
         if residual is not None:
             y = y + residual.float()
         return (torch.relu(y) if relu else y).to(x.dtype)
     m, c = x.shape
     y = torch.empty_like(x)
-    lib = native.load()
+    lib = _lib()
     rc = lib.flpr_affine_act(native.ptr(x), native.ptr(scale.float().contiguous()),
                              native.ptr(shift.float().contiguous()), native.ptr(residual), native.ptr(y), m, c,
-                             int(relu), native.stream(x.device))
+                             int(relu), _stream(x.device))
     native.check(rc, "flpr_affine_act")
     native.count_launch()
     return y
@@ -288,8 +325,8 @@ class _GapFn(torch.autograd.Function):
     def forward(ctx, x):
         n, hw, c = x.shape
         out = torch.empty(n, c, dtype=torch.float32, device=x.device)
-        lib = native.load()
-        native.check(lib.flpr_gap_fwd(native.ptr(x), native.ptr(out), None, n, hw, c, native.stream(x.device)),
+        lib = _lib()
+        native.check(lib.flpr_gap_fwd(native.ptr(x), native.ptr(out), None, n, hw, c, _stream(x.device)),
                      "flpr_gap_fwd")
         native.count_launch()
         ctx.shape = (n, hw, c)
@@ -299,16 +336,16 @@ class _GapFn(torch.autograd.Function):
     def backward(ctx, dout):
         n, hw, c = ctx.shape
         dx = torch.empty(n, hw, c, dtype=torch.bfloat16, device=dout.device)
-        lib = native.load()
+        lib = _lib()
         native.check(lib.flpr_gap_bwd(native.ptr(dout.float().contiguous()), native.ptr(dx), n, hw, c,
-                                      native.stream(dout.device)), "flpr_gap_bwd")
+                                      _stream(dout.device)), "flpr_gap_bwd")
         native.count_launch()
         return dx
 
 
 def global_avg_pool_nhwc(x: torch.Tensor) -> torch.Tensor:
     """``[N, HW, C]`` bf16 -> ``[N, C]`` fp32."""
-    if not x.is_cuda:
+    if not _native(x):
         return x.float().mean(1)
     return _GapFn.apply(x.contiguous())
 
@@ -318,12 +355,12 @@ class _WindowAttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, bias, scale):
         bw, n, three, h, d = qkv.shape
-        lib = native.load()
+        lib = _lib()
         qkv = qkv.contiguous()
         bias = bias.float().contiguous()
         out = torch.empty(bw, n, h * d, dtype=qkv.dtype, device=qkv.device)
         rc = lib.flpr_window_attn_fwd(native.ptr(qkv), native.ptr(bias), native.ptr(out), bw, n, h, d, bias.shape[0],
-                                      float(scale), int(qkv.dtype == torch.bfloat16), native.stream(qkv.device))
+                                      float(scale), int(qkv.dtype == torch.bfloat16), _stream(qkv.device))
         native.check(rc, "flpr_window_attn_fwd")
         native.count_launch()
         ctx.save_for_backward(qkv, bias)
@@ -334,20 +371,20 @@ class _WindowAttnFn(torch.autograd.Function):
     def backward(ctx, dout):
         qkv, bias = ctx.saved_tensors
         bw, n, three, h, d = qkv.shape
-        lib = native.load()
+        lib = _lib()
         dout = dout.contiguous().to(qkv.dtype)
         dqkv = torch.empty_like(qkv)
         dbias = torch.zeros_like(bias) if ctx.needs_input_grad[1] else None
         rc = lib.flpr_window_attn_bwd(native.ptr(qkv), native.ptr(bias), native.ptr(dout), native.ptr(dqkv),
                                       native.ptr(dbias), bw, n, h, d, bias.shape[0], ctx.scale,
-                                      int(qkv.dtype == torch.bfloat16), native.stream(qkv.device))
+                                      int(qkv.dtype == torch.bfloat16), _stream(qkv.device))
         native.check(rc, "flpr_window_attn_bwd")
         native.count_launch()
         return dqkv, dbias, None
 
 
 def window_attention_supported(qkv: torch.Tensor) -> bool:
-    return qkv.is_cuda and qkv.dim() == 5 and qkv.shape[1] <= 64 and qkv.shape[4] <= 64 and \
+    return _native(qkv) and qkv.dim() == 5 and qkv.shape[1] <= 64 and qkv.shape[4] <= 64 and \
         qkv.dtype in (torch.bfloat16, torch.float32)
 
 
@@ -376,7 +413,7 @@ class _MinedDistancesFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, labels, cosine, hard):
         from .rank import similarity
-        lib = native.load()
+        lib = _lib()
         xf = x.float().contiguous()
         b = xf.shape[0]
         dev = xf.device
@@ -389,7 +426,7 @@ class _MinedDistancesFn(torch.autograd.Function):
         lab = labels.to(dev).long().contiguous()
         rc = lib.flpr_triplet_mine_fwd(native.ptr(G), G.stride(0), native.ptr(sq), native.ptr(lab), b, int(cosine),
                                        int(hard), native.ptr(dist_ap), native.ptr(dist_an), native.ptr(jap),
-                                       native.ptr(jan), native.stream(dev))
+                                       native.ptr(jan), _stream(dev))
         native.check(rc, "flpr_triplet_mine_fwd")
         native.count_launch()
         ctx.save_for_backward(xf, jap, jan)
@@ -403,14 +440,14 @@ class _MinedDistancesFn(torch.autograd.Function):
         xf, jap, jan = ctx.saved_tensors
         b, d = xf.shape
         dev = xf.device
-        lib = native.load()
+        lib = _lib()
         lds = (b + 7) // 8 * 8
         S = torch.empty(b, lds, dtype=torch.bfloat16, device=dev)
         rs = torch.empty(b, dtype=torch.float32, device=dev)
         g_ap = (g_ap if g_ap is not None else torch.zeros(b, device=dev)).float().contiguous()
         g_an = (g_an if g_an is not None else torch.zeros(b, device=dev)).float().contiguous()
         rc = lib.flpr_triplet_mine_bwd(native.ptr(jap), native.ptr(jan), native.ptr(g_ap), native.ptr(g_an), b,
-                                       native.ptr(S), lds, native.ptr(rs), native.stream(dev))
+                                       native.ptr(S), lds, native.ptr(rs), _stream(dev))
         native.check(rc, "flpr_triplet_mine_bwd")
         native.count_launch()
         xb = xf.to(torch.bfloat16)
@@ -435,19 +472,19 @@ def mined_distances(x: torch.Tensor, labels: torch.Tensor, cosine: bool, hard: b
 
 
 def mined_distances_supported(x: torch.Tensor) -> bool:
-    return x.is_cuda and x.dim() == 2 and x.shape[1] % 8 == 0 and 2 <= x.shape[0] <= 4096
+    return _native(x) and x.dim() == 2 and x.shape[1] % 8 == 0 and 2 <= x.shape[0] <= 4096
 
 
 class _KDKLFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, s, t, temperature):
-        lib = native.load()
+        lib = _lib()
         s, t = s.contiguous(), t.contiguous().to(s.dtype)
         b, c = s.shape
         ds = torch.empty(b, c, dtype=torch.float32, device=s.device)
         loss = torch.zeros(1, dtype=torch.float32, device=s.device)
         rc = lib.flpr_kd_kl(native.ptr(s), native.ptr(t), native.ptr(ds), native.ptr(loss), b, c, s.stride(0),
-                            t.stride(0), float(temperature), int(s.dtype == torch.bfloat16), native.stream(s.device))
+                            t.stride(0), float(temperature), int(s.dtype == torch.bfloat16), _stream(s.device))
         native.check(rc, "flpr_kd_kl")
         native.count_launch()
         ctx.save_for_backward(ds)
@@ -462,7 +499,7 @@ class _KDKLFn(torch.autograd.Function):
 
 def kd_kl(student: torch.Tensor, teacher: torch.Tensor, temperature: float) -> torch.Tensor:
     """``KL(softmax(t/T) || softmax(s/T)) * T^2 / B`` (``criterions/kd_loss.py:10-27``), fused forward + gradient."""
-    if not student.is_cuda or student.dtype not in (torch.float32, torch.bfloat16):
+    if not _native(student) or student.dtype not in (torch.float32, torch.bfloat16):
         T = temperature
         p_s = F.log_softmax(student.float() / T, dim=1)
         p_t = F.softmax(teacher.float() / T, dim=1)
@@ -473,7 +510,7 @@ def kd_kl(student: torch.Tensor, teacher: torch.Tensor, temperature: float) -> t
 class _BCEDistillFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, target, prev):
-        lib = native.load()
+        lib = _lib()
         z = z.contiguous()
         b, c = z.shape
         p = 0 if prev is None else min(int(prev.shape[1]), c)
@@ -483,7 +520,7 @@ class _BCEDistillFn(torch.autograd.Function):
         rc = lib.flpr_bce_distill(native.ptr(z), native.ptr(target.to(z.device).long().contiguous()),
                                   native.ptr(prev_f), native.ptr(dz), native.ptr(loss), b, c, p, z.stride(0),
                                   0 if prev_f is None else prev_f.stride(0), int(z.dtype == torch.bfloat16),
-                                  native.stream(z.device))
+                                  _stream(z.device))
         native.check(rc, "flpr_bce_distill")
         native.count_launch()
         ctx.save_for_backward(dz)
@@ -499,7 +536,7 @@ class _BCEDistillFn(torch.autograd.Function):
 def bce_distill(score: torch.Tensor, target: torch.Tensor, prev_logits: Optional[torch.Tensor]) -> torch.Tensor:
     """iCaRL's distillation-pass loss (``methods/icarl.py:226-234``): ``BCEWithLogits(score, onehot(target))`` +
     ``BCEWithLogits(score[:, :P], sigmoid(prev_logits))`` (both mean-reduced), one fused kernel with gradient."""
-    if not score.is_cuda or score.dtype not in (torch.float32, torch.bfloat16):
+    if not _native(score) or score.dtype not in (torch.float32, torch.bfloat16):
         z = score.float()
         onehot = torch.zeros_like(z).scatter_(1, target.view(-1, 1).to(z.device), 1.0)
         loss = F.binary_cross_entropy_with_logits(z, onehot)

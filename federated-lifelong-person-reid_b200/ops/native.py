@@ -33,9 +33,9 @@ def available() -> bool:
     return os.path.exists(_build.LIB_PATH)
 
 
-def _declare(lib: C.CDLL) -> None:
+def _signatures() -> dict:
     P, I, F, Z, L, D = c_void_p, c_int, c_float, c_size_t, c_ll, c_double
-    sig = {
+    return {
         "flpr_gemm_bf16": [P, P, P, I, I, I, L, L, L, I, I, I, I, F, P, P, I, P, I, I, P, P],
         "flpr_conv_nhwc_bf16": [P, P, P, I, I, I, I, I, I, I, I, I, I, F, P, I, P, I, P, I, L, L, L, P],
         "flpr_conv_dgrad_nhwc_bf16": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
@@ -85,7 +85,29 @@ def _declare(lib: C.CDLL) -> None:
         "flpr_stream_create": [C.POINTER(P), I],
         "flpr_stream_destroy": [P],
     }
-    for name, argtypes in sig.items():
+
+
+def declare_present(lib: C.CDLL) -> None:
+    """Argument types of the int-returning entry points that ``lib`` exports (a partial library: the host builds of single
+    kernel sources under the SIMT emulator of ``tests/emu``)."""
+    for name, argtypes in _signatures().items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            continue
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    for name, argtypes in (("flpr_window_attn_set_tc", [c_int]),):
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            continue
+        fn.argtypes, fn.restype = argtypes, None
+
+
+def _declare(lib: C.CDLL) -> None:
+    I = c_int
+    for name, argtypes in _signatures().items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = I

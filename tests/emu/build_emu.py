@@ -90,19 +90,24 @@ def rewrite_launches(src: str) -> Tuple[str, int]:
         name = src[name_start:k].strip()
         args = src[args_open + 1:args_end - 1]
         out.append(src[pos:name_start])
+        smem = f"(size_t)({cfg[2]})" if len(cfg) >= 3 else "0"
         key = f"(const void*)({cfg[3]})" if len(cfg) >= 4 else "nullptr"
-        out.append(f"flpr_emu::launch((unsigned)({cfg[0]}), (unsigned)({cfg[1]}), {key}, [=]() {{ {name}({args}); }})")
+        out.append(f"flpr_emu::launch(flpr_emu::dims({cfg[0]}), flpr_emu::dims({cfg[1]}), {smem}, {key}, "
+                   f"[=]() {{ {name}({args}); }})")
         pos = args_end
         n += 1
     return "".join(out), n
 
 
+_DYN_SHARED_RE = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([A-Za-z_][\w:]*)\s+(\w+)\s*\[\s*\]\s*;")
 _SHARED_RE = re.compile(r"__shared__\s+([A-Za-z_][\w:]*(?:\s*<[^;<>]*>)?)\s+(\w+)\s*((?:\[[^\]]*\]\s*)*);")
 
 
 def rewrite_shared(src: str) -> Tuple[str, int]:
     """``__shared__ T name[a][b];`` -> a reference to storage owned by the running block (``flpr_emu::shared``)."""
     n = 0
+    src = _DYN_SHARED_RE.sub(lambda m: f"{m.group(1)}* {m.group(2)} = reinterpret_cast<{m.group(1)}*>("
+                                       f"flpr_emu::dyn_shared());", src)
 
     def repl(m):
         nonlocal n
@@ -141,6 +146,8 @@ def emulated_source(cu_name: str, mutate=None) -> str:
     src = src.replace('#include "ptx.cuh"', '#include "cuda_emu.h"')
     src, removed = strip_inline_ptx_functions(src)
     assert set(removed) <= {"gtimer", "multimem_ld_reduce_add_f4", "multimem_st_f4"}, removed
+    if mutate is None:
+        assert '#include "cuda_emu.h"' in src
     src, _ = rewrite_shared(src)
     src, n = rewrite_launches(src)
     assert n > 0 and "<<<" not in src

@@ -51,6 +51,19 @@ struct Dim3 {
   unsigned x = 0, y = 0, z = 0;
 };
 
+static inline Dim3 dims(const dim3& d) {
+  Dim3 o;
+  o.x = d.x; o.y = d.y; o.z = d.z;
+  return o;
+}
+template <class T>
+static inline Dim3 dims(T v) {
+  Dim3 o;
+  o.x = (unsigned)v; o.y = 1; o.z = 1;
+  return o;
+}
+static inline unsigned volume(const Dim3& d) { return d.x * d.y * d.z; }
+
 constexpr int MAX_THREADS = 1024;
 constexpr size_t STACK_BYTES = 32 * 1024;
 
@@ -61,6 +74,7 @@ struct Fiber {
   ucontext_t ctx;
   Block* blk = nullptr;
   Dim3 tid;
+  unsigned lin = 0;              // linear thread id (warp = lin / 32, lane = lin % 32)
   bool done = false;
 };
 
@@ -79,18 +93,21 @@ struct Block {
   std::vector<WarpState> warps;
   std::vector<Fiber> fibers;
   std::map<int, void*> shared;
+  void* dyn_shared = nullptr;    // `extern __shared__` storage (size from the launch configuration)
   char* stacks = nullptr;
 };
 
 struct KernelRun {
   Dim3 gdim, bdim;
+  size_t smem = 0;               // dynamic shared memory per block
   std::function<void()> body;
   std::vector<Block*> blocks;
   unsigned slow = 0;             // deferred runs: this kernel's threads only run in one of `slow` passes (a slow rank)
 };
 
 struct Pending {
-  unsigned grid, block;
+  Dim3 grid, block;
+  size_t smem;
   std::function<void()> body;
 };
 
@@ -149,7 +166,7 @@ static inline int sync_impl(int pred) {
 }
 
 static inline void warp_barrier() {
-  WarpState& w = g_cur->blk->warps[g_cur->tid.x >> 5];
+  WarpState& w = g_cur->blk->warps[g_cur->lin >> 5];
   const unsigned g = w.gen;
   if (++w.count == w.alive) {
     w.count = 0;
@@ -161,8 +178,8 @@ static inline void warp_barrier() {
 }
 
 static inline uint64_t exchange(uint64_t v, int src_lane) {
-  WarpState& w = g_cur->blk->warps[g_cur->tid.x >> 5];
-  w.buf[g_cur->tid.x & 31] = v;
+  WarpState& w = g_cur->blk->warps[g_cur->lin >> 5];
+  w.buf[g_cur->lin & 31] = v;
   warp_barrier();
   const uint64_t r = w.buf[src_lane & 31];
   warp_barrier();
@@ -189,11 +206,23 @@ static inline T* shared(int id) {
   return reinterpret_cast<T*>(it->second);
 }
 
+// storage behind `extern __shared__ T name[]`
+static inline void* dyn_shared() {
+  Block& b = *g_cur->blk;
+  if (b.dyn_shared == nullptr) b.dyn_shared = calloc(1, b.k->smem + 1024);
+  return b.dyn_shared;
+}
+
+[[noreturn]] static inline void unsupported(const char* what) {
+  fprintf(stderr, "[flpr_emu] %s is a tensor-core / TMA instruction: this kernel cannot run under the emulator\n", what);
+  abort();
+}
+
 static void fiber_entry() {
   Fiber* me = g_cur;
   me->blk->k->body();
   Block& b = *me->blk;
-  WarpState& w = b.warps[me->tid.x >> 5];
+  WarpState& w = b.warps[me->lin >> 5];
   me->done = true;
   b.alive--;
   w.alive--;
@@ -208,10 +237,12 @@ static void fiber_entry() {
 }
 
 static Block* make_block(KernelRun* k, unsigned bid) {
-  const unsigned n = k->bdim.x;
+  const unsigned n = volume(k->bdim);
   Block* b = new Block();
   b->k = k;
-  b->bid.x = bid;
+  b->bid.x = bid % k->gdim.x;
+  b->bid.y = (bid / k->gdim.x) % k->gdim.y;
+  b->bid.z = bid / (k->gdim.x * k->gdim.y);
   b->n = b->alive = (int)n;
   b->warps.resize((n + 31) / 32);
   for (unsigned w = 0; w < b->warps.size(); ++w) b->warps[w].alive = (int)((n - w * 32 >= 32) ? 32 : n - w * 32);
@@ -220,7 +251,10 @@ static Block* make_block(KernelRun* k, unsigned bid) {
   for (unsigned t = 0; t < n; ++t) {
     Fiber& f = b->fibers[t];
     f.blk = b;
-    f.tid.x = t;
+    f.lin = t;
+    f.tid.x = t % k->bdim.x;
+    f.tid.y = (t / k->bdim.x) % k->bdim.y;
+    f.tid.z = t / (k->bdim.x * k->bdim.y);
     getcontext(&f.ctx);
     f.ctx.uc_stack.ss_sp = b->stacks + STACK_BYTES * t;
     f.ctx.uc_stack.ss_size = STACK_BYTES;
@@ -232,6 +266,7 @@ static Block* make_block(KernelRun* k, unsigned bid) {
 
 static void free_block(Block* b) {
   for (auto& kv : b->shared) free(kv.second);
+  free(b->dyn_shared);
   free(b->stacks);
   delete b;
 }
@@ -242,27 +277,28 @@ static inline void resume(Fiber* f) {
   g_cur = nullptr;
 }
 
-static void check_block_size(unsigned block) {
-  if (block == 0 || block > (unsigned)MAX_THREADS) {
-    fprintf(stderr, "[flpr_emu] unsupported block size %u\n", block);
+static void check_block_size(const Dim3& block) {
+  if (volume(block) == 0 || volume(block) > (unsigned)MAX_THREADS) {
+    fprintf(stderr, "[flpr_emu] unsupported block size %u\n", volume(block));
     abort();
   }
 }
 
 // immediate mode: one block at a time
-static void run_now(unsigned grid, unsigned block, const std::function<void()>& body) {
+static void run_now(const Dim3& grid, const Dim3& block, size_t smem, const std::function<void()>& body) {
   check_block_size(block);
   KernelRun k;
-  k.gdim.x = grid;
-  k.gdim.y = k.gdim.z = k.bdim.y = k.bdim.z = 1;
-  k.bdim.x = block;
+  k.smem = smem;
+  k.gdim = grid;
+  k.bdim = block;
   k.body = body;
-  for (unsigned bid = 0; bid < grid; ++bid) {
+  const unsigned nthreads = volume(block);
+  for (unsigned bid = 0; bid < volume(grid); ++bid) {
     Block* b = make_block(&k, bid);
     unsigned long long last = ~0ull;
     int idle_rounds = 0;
     while (b->alive > 0) {
-      for (unsigned t = 0; t < block; ++t)
+      for (unsigned t = 0; t < nthreads; ++t)
         if (!b->fibers[t].done) resume(&b->fibers[t]);
       if (g_progress == last) {
         if (++idle_rounds > 4) {   // every live thread is parked at a barrier that can never release
@@ -280,13 +316,14 @@ static void run_now(unsigned grid, unsigned block, const std::function<void()>& 
   }
 }
 
-static inline void launch(unsigned grid, unsigned block, const void* stream_key, const std::function<void()>& body) {
+static inline void launch(const Dim3& grid, const Dim3& block, size_t smem, const void* stream_key,
+                          const std::function<void()>& body) {
   if (!g_defer) {
-    run_now(grid, block, body);
+    run_now(grid, block, smem, body);
     return;
   }
   check_block_size(block);
-  g_queues[stream_key].push_back(Pending{grid, block, body});
+  g_queues[stream_key].push_back(Pending{grid, block, smem, body});
 }
 
 // deferred mode: every queue concurrently, kernels of a queue in order, all blocks of a running kernel resident
@@ -331,13 +368,13 @@ static int run_queues(unsigned seed, long max_passes, unsigned stall_one_in) {
         } else {
           const Pending& p = l.q->front();
           KernelRun* k = new KernelRun();
-          k->gdim.x = p.grid;
-          k->gdim.y = k->gdim.z = k->bdim.y = k->bdim.z = 1;
-          k->bdim.x = p.block;
+          k->gdim = p.grid;
+          k->bdim = p.block;
           k->body = p.body;
+          k->smem = p.smem;
           auto sl = g_lane_slow.find(l.key);
           k->slow = (seed && sl != g_lane_slow.end()) ? sl->second : 0;
-          for (unsigned bid = 0; bid < p.grid; ++bid) k->blocks.push_back(make_block(k, bid));
+          for (unsigned bid = 0; bid < volume(p.grid); ++bid) k->blocks.push_back(make_block(k, bid));
           l.cur = k;
           changed = true;
           if (seed) l.delay = (int)(rnd() % 3);      // host-side gap before this lane's NEXT launch
@@ -416,7 +453,7 @@ static inline void __threadfence() {}
 
 template <class T>
 static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
-  return flpr_emu::shfl_from(v, (int)(flpr_emu::g_cur->tid.x & 31) ^ lane_mask);
+  return flpr_emu::shfl_from(v, (int)(flpr_emu::g_cur->lin & 31) ^ lane_mask);
 }
 template <class T>
 static inline T __shfl_sync(unsigned, T v, int src_lane) {
@@ -424,7 +461,7 @@ static inline T __shfl_sync(unsigned, T v, int src_lane) {
 }
 template <class T>
 static inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
-  const int l = (int)(flpr_emu::g_cur->tid.x & 31);
+  const int l = (int)(flpr_emu::g_cur->lin & 31);
   const T r = flpr_emu::shfl_from(v, l + (int)delta);
   return (l + (int)delta < 32) ? r : v;
 }
@@ -434,7 +471,34 @@ static inline unsigned atomicExch(unsigned* p, unsigned v) {
   *p = v;
   return o;
 }
+static inline float atomicAdd(float* p, float v) {
+  const float o = *p;
+  *p = o + v;
+  return o;
+}
+static inline int atomicAdd(int* p, int v) {
+  const int o = *p;
+  *p = o + v;
+  return o;
+}
+static inline int atomicMin(int* p, int v) {
+  const int o = *p;
+  if (v < o) *p = v;
+  return o;
+}
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+#define __expf(x) expf(x)
+template <class T>
+static inline T min(T a, T b) { return b < a ? b : a; }
+template <class T>
+static inline T max(T a, T b) { return a < b ? b : a; }
+static inline float __uint_as_float(unsigned u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+#undef __align__
+#define __align__(n) alignas(n)
 
 // ---- the pieces of csrc/ptx.cuh (and the inline-PTX helpers of the kernel sources) the CUDA-core kernels use ------------------
 namespace flpr {
@@ -446,6 +510,27 @@ static inline float warp_sum(float v) {
 static inline float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+// tcgen05 / TMEM / mbarrier helpers of ptx.cuh: declared so that a source which ALSO contains a tensor-core kernel compiles
+static inline uint32_t smem_u32(const void*) { flpr_emu::unsupported("cvta.shared"); }
+static inline void fence_mbar_init() { flpr_emu::unsupported("fence.mbarrier_init"); }
+static inline void fence_proxy_async() { flpr_emu::unsupported("fence.proxy.async"); }
+static inline uint64_t make_smem_desc_sw128(uint32_t, uint32_t, uint32_t) { flpr_emu::unsupported("smem descriptor"); }
+static inline void mbar_init(uint64_t*, uint32_t) { flpr_emu::unsupported("mbarrier.init"); }
+static inline void mbar_wait(uint64_t*, uint32_t) { flpr_emu::unsupported("mbarrier.try_wait"); }
+static inline void sts_128(uint32_t, const uint4&) { flpr_emu::unsupported("st.shared.v4"); }
+static inline void tc_fence_after() { flpr_emu::unsupported("tcgen05.fence"); }
+static inline void tc_fence_before() { flpr_emu::unsupported("tcgen05.fence"); }
+static inline void tmem_alloc(uint32_t*, uint32_t) { flpr_emu::unsupported("tcgen05.alloc"); }
+static inline void tmem_dealloc(uint32_t, uint32_t) { flpr_emu::unsupported("tcgen05.dealloc"); }
+static inline void tmem_ld_32x32b_x32(uint32_t, uint32_t (&)[32]) { flpr_emu::unsupported("tcgen05.ld"); }
+static inline void tmem_ld_wait() { flpr_emu::unsupported("tcgen05.wait"); }
+static inline void tmem_relinquish() { flpr_emu::unsupported("tcgen05.relinquish_alloc_permit"); }
+static inline void umma_commit(uint64_t*) { flpr_emu::unsupported("tcgen05.commit"); }
+static inline void umma_f16(uint32_t, uint64_t, uint64_t, uint32_t, uint32_t) { flpr_emu::unsupported("tcgen05.mma"); }
+constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 // system-scope flag accesses: the spin loops of the peer-memory protocol are cooperative here
 static inline void st_release_sys(uint32_t* p, uint32_t v) {
@@ -490,6 +575,7 @@ static inline void multimem_st_f4(float* mc, const float4& v) {
 using flpr::bind_device_of;
 
 #define cudaGetLastError() (cudaSuccess)
+#define cudaFuncSetAttribute(...) (cudaSuccess)
 
 extern "C" {
 int flpr_emu_deadlocks() { return flpr_emu::g_deadlocks; }

@@ -1,0 +1,232 @@
+"""The CUDA-core kernels of ``csrc/fused_ops.cu`` and ``csrc/loss_ops.cu`` (fused optimizer, importance accumulation,
+casts, label-smoothing CE, NHWC batch norm forward / backward, pooling, scalar window attention forward / backward,
+triplet mining, KD-KL, BCE-distill) executed on the CPU under the SIMT emulator of ``tests/emu``.
+
+These kernels are validated on the device by ``tests/test_gpu_kernels.py``; here their *source* runs in the CPU tier
+through the same wrappers (``flpr_b200.ops.fused``) and entry points, so a change to a kernel or to its argument
+marshalling is caught without a GPU. Every check calls the op twice - PyTorch reference path, then emulated kernel -
+and compares values and gradients. (The tensor-core window-attention kernel in the same source file compiles against
+aborting stubs and is never launched here.)"""
+import shutil
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+
+@pytest.fixture(scope="module")
+def emu_paths():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    from emu.build_emu import build
+    try:
+        return [build("fused_ops.cu"), build("loss_ops.cu")]
+    except RuntimeError as ex:
+        pytest.skip(f"emulator build unavailable: {ex}")
+
+
+class both:
+    """``with both(paths) as run: ref, got = run(lambda: op(...))``: the callable is evaluated on the reference path and
+    then on the emulated kernels (fresh inputs each time: it must build them itself)."""
+
+    def __init__(self, paths):
+        self.paths = paths
+
+    def __enter__(self):
+        from flpr_b200.ops import fused as fops, native
+        self.fops, self.native = fops, native
+
+        def run(fn):
+            fops.use_emulated_libraries(None)
+            ref = fn()
+            fops.use_emulated_libraries(self.paths)
+            before = native.launches()
+            try:
+                got = fn()
+            finally:
+                fops.use_emulated_libraries(None)
+            assert native.launches() > before, "the emulated run did not launch a kernel"
+            return ref, got
+        return run
+
+    def __exit__(self, *exc):
+        self.fops.use_emulated_libraries(None)
+        return False
+
+
+def close(a, b, rtol=1e-4, atol_frac=1e-5):
+    a, b = a.float(), b.float()
+    assert a.shape == b.shape
+    atol = atol_frac * float(b.abs().max()) + 1e-7
+    assert torch.allclose(a, b, rtol=rtol, atol=atol), float((a - b).abs().max())
+
+
+def rand(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+# ------------------------------------------------------------------------------------------------------------ optimizer
+@pytest.mark.parametrize("kind,penalty,l1", [("adam", False, False), ("adam", True, True), ("sgd", True, False),
+                                             ("sgd", False, True)])
+def test_fused_optimizer_step(emu_paths, kind, penalty, l1):
+    n = 4 * 777
+
+    def step():
+        from flpr_b200.ops import fused as fops
+        p, g = rand(n, seed=1), rand(n, seed=2, scale=0.1)
+        m, v = rand(n, seed=3, scale=0.01), rand(n, seed=4, scale=0.01).abs()
+        Q, R = (rand(n, seed=5).abs(), rand(n, seed=6)) if penalty else (None, None)
+        G = rand(n, seed=7) if l1 else None
+        shadow = torch.zeros(n, dtype=torch.bfloat16)
+        stats = torch.zeros(4)
+        for it in (1, 2):
+            fops.fused_optimizer_step(kind, p, g, m, v if kind == "adam" else None, lr=1e-2, step=it, weight_decay=1e-3,
+                                      momentum=0.9 if kind == "sgd" else 0.0, Q=Q, R=R, lam2=0.5 if penalty else 0.0,
+                                      G=G, lam1=1e-2 if l1 else 0.0, atten=0.9 if l1 else 0.0, p_bf16=shadow,
+                                      stats=stats)
+        return p, m, v, shadow, stats
+    with both(emu_paths) as run:
+        ref, got = run(step)
+    for a, b in zip(got[:3], ref[:3]):
+        close(a, b)
+    close(got[3], ref[0].to(torch.bfloat16), rtol=1e-2, atol_frac=1e-2)        # (the reference path does not refresh it)
+    close(got[4][:2], ref[4][:2], rtol=1e-3, atol_frac=1e-4)
+
+
+def test_importance_cast_and_compose(emu_paths):
+    n = 4 * 501
+
+    def ops():
+        from flpr_b200.ops import fused as fops
+        f1, f2, g = rand(n, seed=1).abs(), rand(n, seed=1).abs(), rand(n, seed=2)
+        fops.importance_accumulate(f1, g, 0.25, "fisher")
+        fops.importance_accumulate(f2, g, 0.25, "mas")
+        c = fops.cast_bf16(g)
+        theta, t16 = torch.zeros(n), torch.zeros(n, dtype=torch.bfloat16)
+        fops.compose_adaptive(rand(n, seed=3), rand(n, seed=4), 0.9, theta, t16)
+        return f1, f2, c, theta, t16
+    with both(emu_paths) as run:
+        ref, got = run(ops)
+    close(got[0], ref[0])
+    close(got[1], ref[1])
+    assert torch.equal(got[2], ref[2])
+    close(got[3], ref[3])
+    close(got[4], ref[4], rtol=1e-2, atol_frac=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------------------ CE
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_label_smoothing_cross_entropy(emu_paths, dtype):
+    def ce():
+        from flpr_b200.ops import fused as fops
+        logits = rand(24, 1000, seed=1, scale=3.0).to(dtype).requires_grad_(True)
+        target = torch.randint(0, 1000, (24,), generator=torch.Generator().manual_seed(2))
+        stats = torch.zeros(2)
+        loss = fops.ce_label_smooth(logits, target, 0.1, stats)
+        loss.backward()
+        return loss.detach(), logits.grad, stats
+    with both(emu_paths) as run:
+        ref, got = run(ce)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    close(got[0], ref[0], rtol=tol, atol_frac=tol)
+    close(got[1], ref[1], rtol=tol * 10, atol_frac=tol)
+    close(got[2], ref[2], rtol=tol, atol_frac=tol)
+
+
+# ------------------------------------------------------------------------------------------------------------ BN / GAP
+@pytest.mark.parametrize("relu,residual", [(False, False), (True, True)])
+def test_batch_norm_nhwc_forward_backward_and_eval(emu_paths, relu, residual):
+    m, c = 8 * 16 * 8, 256
+
+    def bn():
+        from flpr_b200.ops import fused as fops
+        x = rand(m, c, seed=1).to(torch.bfloat16).requires_grad_(True)
+        res = rand(m, c, seed=2).to(torch.bfloat16).requires_grad_(True) if residual else None
+        gamma = (1 + 0.1 * rand(c, seed=3)).requires_grad_(True)
+        beta = (0.1 * rand(c, seed=4)).requires_grad_(True)
+        rm, rv = torch.zeros(c), torch.ones(c)
+        y = fops.batch_norm_nhwc(x, gamma, beta, rm, rv, training=True, relu=relu, residual=res)
+        y.float().mul(rand(m, c, seed=5)).sum().backward()
+        ye = fops.batch_norm_nhwc(x.detach(), gamma.detach(), beta.detach(), rm, rv, training=False, relu=relu,
+                                  residual=None if res is None else res.detach())
+        return y.detach(), x.grad, gamma.grad, beta.grad, rm, rv, ye, (None if res is None else res.grad)
+    with both(emu_paths) as run:
+        ref, got = run(bn)
+    close(got[0], ref[0], rtol=2e-2, atol_frac=1e-2)
+    close(got[1], ref[1], rtol=5e-2, atol_frac=2e-2)
+    close(got[2], ref[2], rtol=2e-2, atol_frac=1e-2)
+    close(got[3], ref[3], rtol=2e-2, atol_frac=1e-2)
+    close(got[4], ref[4], rtol=1e-3, atol_frac=1e-3)
+    close(got[5], ref[5], rtol=1e-3, atol_frac=1e-3)
+    close(got[6], ref[6], rtol=2e-2, atol_frac=1e-2)
+    if residual:
+        close(got[7], ref[7], rtol=2e-2, atol_frac=1e-2)
+
+
+def test_global_average_pool(emu_paths):
+    def gap():
+        from flpr_b200.ops import fused as fops
+        x = rand(6, 32, 128, seed=1).to(torch.bfloat16).requires_grad_(True)
+        y = fops.global_avg_pool_nhwc(x)
+        y.float().mul(rand(6, 128, seed=2)).sum().backward()
+        return y.detach(), x.grad
+    with both(emu_paths) as run:
+        ref, got = run(gap)
+    close(got[0], ref[0], rtol=1e-2, atol_frac=1e-2)
+    close(got[1], ref[1], rtol=1e-2, atol_frac=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("n,heads,d,nw", [(16, 3, 32, 1), (49, 2, 32, 4)])
+def test_scalar_window_attention_forward_backward(emu_paths, n, heads, d, nw):
+    bw = 2 * nw
+
+    def attn():
+        from flpr_b200.ops import fused as fops
+        qkv = rand(bw, n, 3, heads, d, seed=1, scale=0.5).requires_grad_(True)          # fp32: the scalar kernel
+        bias = rand(nw, heads, n, n, seed=2, scale=0.2).requires_grad_(True)
+        out = fops.window_attention(qkv, bias, d ** -0.5)
+        out.mul(rand(bw, n, heads * d, seed=3)).sum().backward()
+        return out.detach(), qkv.grad, bias.grad
+    with both(emu_paths) as run:
+        ref, got = run(attn)
+    close(got[0], ref[0], rtol=1e-3, atol_frac=1e-4)
+    close(got[1], ref[1], rtol=1e-3, atol_frac=1e-3)
+    close(got[2], ref[2], rtol=1e-3, atol_frac=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------------------ losses
+@pytest.mark.parametrize("norm_feat,hard,margin", [(False, True, 0.3), (True, False, None), (False, False, 0.3),
+                                                   (True, True, None)])
+def test_triplet_mining_kernels(emu_paths, norm_feat, hard, margin):
+    def trip():
+        from flpr_b200.criterions.losses import TripletLoss
+        x = rand(32, 256, seed=1).requires_grad_(True)
+        y = torch.arange(32) // 4
+        loss = TripletLoss(margin=margin, norm_feat=norm_feat, hard_mining=hard)(feature=x, target=y)
+        loss.backward()
+        return loss.detach(), x.grad
+    with both(emu_paths) as run:
+        ref, got = run(trip)
+    close(got[0], ref[0], rtol=2e-2, atol_frac=2e-2)           # (the fused path forms the Gram matrix in bf16)
+    cos = F.cosine_similarity(got[1].flatten(), ref[1].flatten(), dim=0).item()
+    assert cos > 0.99, cos
+
+
+def test_kd_kl_and_bce_distill(emu_paths):
+    def kd():
+        from flpr_b200.ops import fused as fops
+        s = rand(16, 500, seed=1, scale=2.0).requires_grad_(True)
+        t = rand(16, 500, seed=2, scale=2.0)
+        loss = fops.kd_kl(s, t, 4.0)
+        loss.backward()
+        z = rand(16, 40, seed=3).requires_grad_(True)
+        target = torch.randint(0, 40, (16,), generator=torch.Generator().manual_seed(4))
+        prev = rand(16, 30, seed=5)
+        l2 = fops.bce_distill(z, target, prev)
+        l2.backward()
+        return loss.detach(), s.grad, l2.detach(), z.grad
+    with both(emu_paths) as run:
+        ref, got = run(kd)
+    for a, b in zip(got, ref):
+        close(a, b, rtol=1e-3, atol_frac=1e-4)

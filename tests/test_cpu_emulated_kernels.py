@@ -39,16 +39,17 @@ def test_launch_rewriter_handles_templates_casts_and_nested_calls():
            "  if (x) ns::k2<8><<<(unsigned)rows, 128>>>(p, q);\n")
     out, n = rewrite_launches(src)
     assert n == 2 and "<<<" not in out
-    assert "flpr_emu::launch((unsigned)(grid_for(n / 4, 256)), (unsigned)(256), (const void*)(st), [=]() { " \
-           "k1(reinterpret_cast<const float4*>(a), f(b, c), n / 4); });" in out
-    assert "if (x) flpr_emu::launch((unsigned)((unsigned)rows), (unsigned)(128), nullptr, [=]() { ns::k2<8>(p, q); });" \
-        in out
+    assert "flpr_emu::launch(flpr_emu::dims(grid_for(n / 4, 256)), flpr_emu::dims(256), (size_t)(0), (const void*)(st), " \
+           "[=]() { k1(reinterpret_cast<const float4*>(a), f(b, c), n / 4); });" in out
+    assert "if (x) flpr_emu::launch(flpr_emu::dims((unsigned)rows), flpr_emu::dims(128), 0, nullptr, " \
+           "[=]() { ns::k2<8>(p, q); });" in out
 
 
 def test_source_rewrites_for_shared_memory_and_inline_ptx():
     from emu.build_emu import rewrite_shared, strip_inline_ptx_functions
-    out, n = rewrite_shared("  __shared__ float sh[2][8][256];\n  __shared__ float s_inv;\n")
+    out, n = rewrite_shared("  __shared__ float sh[2][8][256];\n  __shared__ float s_inv;\n  extern __shared__ int dyn[];\n")
     assert n == 2 and "__shared__" not in out
+    assert "int* dyn = reinterpret_cast<int*>(flpr_emu::dyn_shared());" in out
     assert "using flpr_sh_t1 = float[2][8][256]; flpr_sh_t1& sh = *flpr_emu::shared<flpr_sh_t1>(1);" in out
     assert "using flpr_sh_t2 = float; flpr_sh_t2& s_inv = *flpr_emu::shared<flpr_sh_t2>(2);" in out
     src = ("int keep() { return 1; }\n"
@@ -117,8 +118,8 @@ def test_emulator_reports_a_barrier_not_every_thread_reaches(tmp_path):
                    "  __syncthreads();\n"
                    "  out[threadIdx.x] = v;\n"
                    "}\n"
-                   'extern "C" void run_bad(int* out) { flpr_emu::launch(1, 64, nullptr, [=]() { bad_kernel(out); }); }\n'
-                   'extern "C" void run_good(float* out) { flpr_emu::launch(1, 64, nullptr, [=]() { good_kernel(out); }); }\n')
+                   'extern "C" void run_bad(int* out) { flpr_emu::launch(flpr_emu::dims(1), flpr_emu::dims(64), 0, nullptr, [=]() { bad_kernel(out); }); }\n'
+                   'extern "C" void run_good(float* out) { flpr_emu::launch(flpr_emu::dims(1), flpr_emu::dims(64), 0, nullptr, [=]() { good_kernel(out); }); }\n')
     lib_path = str(tmp_path / "libbad.so")
     subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-Wno-attributes", "-I", HERE, "-I", CUDA_INCLUDE,
                     str(src), "-o", lib_path], check=True)
