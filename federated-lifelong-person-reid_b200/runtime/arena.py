@@ -205,7 +205,8 @@ class ArenaOptimizer:
 
         n_g = self.G.numel() if self.G is not None else 0
         trained_anchor = self.anchor is not None and n_g > 0 and self.lam1 != 0.0
-        fused_anchor = trained_anchor and a.device.type == "cuda" and getattr(self, "fuse_anchor", True)
+        fused_anchor = trained_anchor and getattr(self, "fuse_anchor", True) and (
+            a.device.type == "cuda" or bool(fops._emu_libs))      # (tests: the kernel under the CPU SIMT emulator)
         if fused_anchor and self.anchor_m is None and (self.kind == "adam" or d["momentum"] != 0.0):
             self.anchor_m = torch.zeros_like(self.anchor)
         if fused_anchor and self.anchor_v is None and self.kind == "adam":

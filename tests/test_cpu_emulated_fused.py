@@ -93,6 +93,42 @@ def test_fused_optimizer_step(emu_paths, kind, penalty, l1):
     close(got[4][:2], ref[4][:2], rtol=1e-3, atol_frac=1e-4)
 
 
+@pytest.mark.parametrize("kind", ["adam", "sgd"])
+def test_trained_l1_anchor_kernel_matches_the_tensor_op_twin(emu_paths, kind):
+    """FedSTIL's trained L1 anchor (reference quirk, ``fedstil.py:53-76,639-647``): ``fused_opt_kernel<true>`` under the
+    emulator vs ``ArenaOptimizer._anchor_step`` (the fp32 tensor-op form the golden tests compare with the reference)
+    over four steps - weights, anchor, both moment pairs, the reported L1 sum."""
+    import torch.nn as nn
+
+    def steps():
+        from flpr_b200.runtime.arena import ArenaOptimizer, ParamArena
+        torch.manual_seed(11)
+        lin1, lin2 = nn.Linear(64, 96, bias=False), nn.Linear(96, 16)
+        params = [("a.weight", lin1.weight), ("b.weight", lin2.weight), ("b.bias", lin2.bias)]
+        arena = ParamArena(params, "cpu", shadow=True, first=lambda n: n == "a.weight")
+        opt = ArenaOptimizer(kind, arena, lr=1e-3 if kind == "adam" else 0.05, weight_decay=1e-4, momentum=0.9)
+        n = arena.prefix_numel
+        torch.manual_seed(12)
+        G = arena.master[:n] + 0.01 * torch.randn(n)
+        opt.G, opt.lam1, opt.atten = G, 1e-2, 0.9
+        opt.anchor = G.clone()
+        opt.stats = torch.zeros(2)
+        for step in range(4):
+            torch.manual_seed(100 + step)
+            arena.grad.copy_(torch.randn(arena.numel) * (torch.rand(arena.numel) > 0.3))     # exact zeros: sign(0) = 0
+            opt.step()
+        return (arena.master.clone(), opt.anchor.clone(), opt.m.clone(),
+                opt.anchor_m.clone() if opt.anchor_m is not None else torch.zeros(1), opt.stats.clone(), G)
+    with both(emu_paths) as run:
+        ref, got = run(steps)
+    close(got[0], ref[0], rtol=1e-4, atol_frac=1e-5)
+    close(got[1], ref[1], rtol=1e-4, atol_frac=1e-5)
+    close(got[2], ref[2], rtol=1e-3, atol_frac=1e-4)
+    close(got[3], ref[3], rtol=1e-3, atol_frac=1e-4)
+    close(got[4][1:], ref[4][1:], rtol=1e-3, atol_frac=1e-3)
+    assert float((ref[1] - ref[5]).abs().max()) > 1e-5                      # the anchor did move
+
+
 def test_importance_cast_and_compose(emu_paths):
     n = 4 * 501
 
