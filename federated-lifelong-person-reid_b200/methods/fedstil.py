@@ -420,12 +420,12 @@ def herding_select_batched(feats: torch.Tensor, idx: torch.Tensor, counts: torch
     P, nmax = idx.shape
     dev = feats.device
     picks = torch.empty(P, m, dtype=torch.long, device=dev)
-    if feats.is_cuda:
-        from ..ops import native
-        lib = native.load()
-        f = feats.float().contiguous()
-        rc = lib.flpr_herding(native.ptr(f), native.ptr(idx.contiguous()), native.ptr(counts.to(torch.int32)),
-                              native.ptr(picks), P, nmax, f.shape[1], m, native.stream(dev))
+    from ..ops import native
+    if native.on_device(feats, "flpr_herding"):
+        lib = native.kernels()
+        f, idx_c, cnt32 = feats.float().contiguous(), idx.contiguous(), counts.to(torch.int32)   # (kept alive over the call)
+        rc = lib.flpr_herding(native.ptr(f), native.ptr(idx_c), native.ptr(cnt32),
+                              native.ptr(picks), P, nmax, f.shape[1], m, native.stream_of(dev))
         if rc == 0:
             native.count_launch()
             return picks

@@ -10,42 +10,12 @@ import torch.nn.functional as F
 
 from . import native
 
-# ---- tests only: host builds of csrc/fused_ops.cu / loss_ops.cu under the SIMT emulator (tests/emu) ----------------------------
-_emu_libs: list = []
-
-
-def use_emulated_libraries(paths) -> None:
-    """Route the wrappers of this module to emulated libraries (``None`` / empty: back to normal). With them installed,
-    CPU tensors take the KERNEL path - same argument marshalling, same ``extern "C"`` entry points as on the device."""
-    import ctypes
-    _emu_libs.clear()
-    for path in (paths or []):
-        lib = ctypes.CDLL(path)
-        native.declare_present(lib)
-        _emu_libs.append(lib)
-
-
-class _EmuDispatch:
-    """``lib.flpr_xyz`` resolved over the installed emulated libraries."""
-
-    def __getattr__(self, name):
-        for lib in _emu_libs:
-            if hasattr(lib, name):
-                return getattr(lib, name)
-        raise AttributeError(name)
-
-
-def _lib():
-    return _EmuDispatch() if _emu_libs else native.load()
-
-
-def _native(t: torch.Tensor) -> bool:
-    """The kernel path applies to ``t``: a CUDA tensor - or any tensor while emulated libraries are installed."""
-    return t.is_cuda or bool(_emu_libs)
-
-
-def _stream(device):
-    return native.c_void_p(0) if _emu_libs else native.stream(device)
+# (tests: ``native.use_emulated_libraries`` sends CPU tensors down the kernel paths below - tests/emu)
+use_emulated_libraries = native.use_emulated_libraries
+_emu_libs = native._emu_libs
+_lib = native.kernels
+_native = native.on_device
+_stream = native.stream_of
 
 
 # --------------------------------------------------------------------------------------------- optimizers
@@ -312,8 +282,9 @@ def affine_act(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, *, rel
     m, c = x.shape
     y = torch.empty_like(x)
     lib = _lib()
-    rc = lib.flpr_affine_act(native.ptr(x), native.ptr(scale.float().contiguous()),
-                             native.ptr(shift.float().contiguous()), native.ptr(residual), native.ptr(y), m, c,
+    scale_f, shift_f = scale.float().contiguous(), shift.float().contiguous()          # (kept alive over the call)
+    rc = lib.flpr_affine_act(native.ptr(x), native.ptr(scale_f),
+                             native.ptr(shift_f), native.ptr(residual), native.ptr(y), m, c,
                              int(relu), _stream(x.device))
     native.check(rc, "flpr_affine_act")
     native.count_launch()
@@ -337,7 +308,8 @@ class _GapFn(torch.autograd.Function):
         n, hw, c = ctx.shape
         dx = torch.empty(n, hw, c, dtype=torch.bfloat16, device=dout.device)
         lib = _lib()
-        native.check(lib.flpr_gap_bwd(native.ptr(dout.float().contiguous()), native.ptr(dx), n, hw, c,
+        dout_f = dout.float().contiguous()
+        native.check(lib.flpr_gap_bwd(native.ptr(dout_f), native.ptr(dx), n, hw, c,
                                       _stream(dout.device)), "flpr_gap_bwd")
         native.count_launch()
         return dx
@@ -517,7 +489,8 @@ class _BCEDistillFn(torch.autograd.Function):
         prev_f = None if prev is None else prev.float().contiguous()
         dz = torch.empty(b, c, dtype=torch.float32, device=z.device)
         loss = torch.zeros(1, dtype=torch.float32, device=z.device)
-        rc = lib.flpr_bce_distill(native.ptr(z), native.ptr(target.to(z.device).long().contiguous()),
+        target_l = target.to(z.device).long().contiguous()
+        rc = lib.flpr_bce_distill(native.ptr(z), native.ptr(target_l),
                                   native.ptr(prev_f), native.ptr(dz), native.ptr(loss), b, c, p, z.stride(0),
                                   0 if prev_f is None else prev_f.stride(0), int(z.dtype == torch.bfloat16),
                                   _stream(z.device))

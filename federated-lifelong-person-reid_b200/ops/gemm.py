@@ -443,15 +443,15 @@ def s2d_pad(x: torch.Tensor) -> torch.Tensor:
     """``[B,H,W,3]`` bf16 -> ``[B, H/2+3, W/2+3, 16]`` bf16 (space-to-depth cells with zero borders)."""
     b, h, w, c = x.shape
     assert c == 3 and h % 2 == 0 and w % 2 == 0
-    if not x.is_cuda:
+    if not native.on_device(x, "flpr_s2d_pad"):
         y = x.new_zeros(b, h // 2 + 3, w // 2 + 3, 16)
         cells = x.view(b, h // 2, 2, w // 2, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(b, h // 2, w // 2, 12)
         y[:, 2:2 + h // 2, 2:2 + w // 2, :12] = cells
         return y
-    lib = native.load()
+    lib = native.kernels()
     x = _bf(x).contiguous()
     y = torch.empty(b, h // 2 + 3, w // 2 + 3, 16, dtype=torch.bfloat16, device=x.device)
-    native.check(lib.flpr_s2d_pad(native.ptr(x), native.ptr(y), b, h, w, native.stream(x.device)), "flpr_s2d_pad")
+    native.check(lib.flpr_s2d_pad(native.ptr(x), native.ptr(y), b, h, w, native.stream_of(x.device)), "flpr_s2d_pad")
     native.count_launch()
     return y
 
@@ -503,12 +503,12 @@ def stem_conv(x: torch.Tensor, w4: torch.Tensor, bias: Optional[torch.Tensor], r
 def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
     """3x3 / stride 2 / pad 1 max-pool over NHWC bf16."""
     b, h, w, c = x.shape
-    if not x.is_cuda:
+    if not native.on_device(x, "flpr_maxpool3x3s2"):
         return F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).to(x.dtype).contiguous()
-    lib = native.load()
+    lib = native.kernels()
     x = _bf(x).contiguous()
     y = torch.empty(b, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c, dtype=torch.bfloat16, device=x.device)
-    native.check(lib.flpr_maxpool3x3s2(native.ptr(x), native.ptr(y), b, h, w, c, native.stream(x.device)),
+    native.check(lib.flpr_maxpool3x3s2(native.ptr(x), native.ptr(y), b, h, w, c, native.stream_of(x.device)),
                  "flpr_maxpool3x3s2")
     native.count_launch()
     return y

@@ -152,6 +152,53 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     return _lib
 
 
+# ---- tests only: host builds of single kernel sources under the SIMT emulator of tests/emu ---------------------------------------
+_emu_libs: list = []
+
+
+def use_emulated_libraries(paths) -> None:
+    """Install emulated libraries (``None`` / empty: remove them). While installed, the ops that consult
+    :func:`on_device` / :func:`kernels` / :func:`stream_of` send CPU tensors down their KERNEL path - same argument
+    marshalling, same ``extern "C"`` entry points as on the device - instead of the PyTorch reference."""
+    _emu_libs.clear()
+    for path in (paths or []):
+        lib = C.CDLL(path)
+        declare_present(lib)
+        _emu_libs.append(lib)
+
+
+class _EmuDispatch:
+    """``lib.flpr_xyz`` resolved over the installed emulated libraries."""
+
+    def __getattr__(self, name):
+        for lib in _emu_libs:
+            if hasattr(lib, name):
+                return getattr(lib, name)
+        raise AttributeError(name)
+
+
+def emulated(symbol: Optional[str] = None) -> bool:
+    """Emulated libraries are installed (and, with ``symbol``, one of them exports it)."""
+    if symbol is None:
+        return bool(_emu_libs)
+    return any(hasattr(lib, symbol) for lib in _emu_libs)
+
+
+def kernels():
+    """The object whose attributes are the ``flpr_*`` entry points: the native library, or the emulated ones."""
+    return _EmuDispatch() if _emu_libs else load()
+
+
+def on_device(t: torch.Tensor, symbol: Optional[str] = None) -> bool:
+    """The kernel path applies to ``t``: a CUDA tensor, or any tensor while an emulated library (exporting ``symbol``)
+    is installed."""
+    return t.is_cuda or emulated(symbol)
+
+
+def stream_of(device) -> c_void_p:
+    return c_void_p(0) if _emu_libs else stream(device)
+
+
 def ptr(t: Optional[torch.Tensor]) -> c_void_p:
     if t is None:
         return c_void_p(0)

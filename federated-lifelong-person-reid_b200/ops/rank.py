@@ -62,17 +62,17 @@ def rank_metrics_reference(sim: torch.Tensor, q_labels: torch.Tensor, g_labels: 
 def rank_metrics(sim: torch.Tensor, q_labels: torch.Tensor, g_labels: torch.Tensor) -> Tuple[np.ndarray, float]:
     """CMC curve (length G, float64) and mAP from a similarity matrix. Queries with no match are skipped but still
     count in the denominator (``tools/evaluate.py:137-142``)."""
-    if not sim.is_cuda:
+    if not native.on_device(sim, "flpr_rank_eval"):
         return rank_metrics_reference(sim, q_labels, g_labels)
     nq, ng = sim.shape
-    lib = native.load()
+    lib = native.kernels()
     sim = sim.float().contiguous()
     ql = q_labels.to(sim.device).long().contiguous()
     gl = g_labels.to(sim.device).long().contiguous()
     ap = torch.empty(nq, dtype=torch.float32, device=sim.device)
     first = torch.empty(nq, dtype=torch.int32, device=sim.device)
     rc = lib.flpr_rank_eval(native.ptr(sim), native.ptr(ql), native.ptr(gl), native.ptr(ap), native.ptr(first), nq, ng,
-                            sim.stride(0), native.stream(sim.device))
+                            sim.stride(0), native.stream_of(sim.device))
     native.check(rc, "flpr_rank_eval")
     native.count_launch()
     valid = first >= 0

@@ -266,3 +266,50 @@ def test_kd_kl_and_bce_distill(emu_paths):
         ref, got = run(kd)
     for a, b in zip(got, ref):
         close(a, b, rtol=1e-3, atol_frac=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------------------ the rest
+def test_ranking_kernel_cmc_and_map(emu_paths):
+    """``rank_eval_kernel`` (count-based AP / first-match rank per query, ``tools/evaluate.py:103-142``) vs the reference
+    formulation, incl. queries without any match and tied similarities."""
+    def rank():
+        from flpr_b200.ops.rank import rank_metrics
+        g = torch.Generator().manual_seed(5)
+        sim = torch.randn(37, 211, generator=g)
+        sim[:, 0:210:7] = sim[:, 1:210:7]                                    # ties
+        ql = torch.randint(0, 12, (37,), generator=g)
+        gl = torch.randint(0, 10, (211,), generator=g)                       # ids 10, 11 never appear in the gallery
+        cmc, mAP = rank_metrics(sim, ql, gl)
+        return torch.as_tensor(cmc), torch.tensor(mAP)
+    with both(emu_paths) as run:
+        ref, got = run(rank)
+    close(got[0], ref[0], rtol=1e-6, atol_frac=1e-7)
+    close(got[1], ref[1], rtol=1e-5, atol_frac=1e-6)
+
+
+def test_herding_kernel_picks_the_same_exemplars(emu_paths):
+    def herd():
+        from flpr_b200.methods.fedstil import group_matrix, herding_select_batched
+        g = torch.Generator().manual_seed(9)
+        feats = torch.randn(60, 48, generator=g)
+        groups = [torch.arange(0, 17), torch.arange(17, 20), torch.arange(20, 60)]
+        idx, counts = group_matrix(groups)
+        return (herding_select_batched(feats, idx, counts, 6),)
+    with both(emu_paths) as run:
+        ref, got = run(herd)
+    counts = [17, 3, 40]
+    for gi, c in enumerate(counts):                        # (entries past an identity's size are padding on both paths)
+        k = min(6, c)
+        assert torch.equal(got[0][gi, :k], ref[0][gi, :k]), (gi, got[0][gi], ref[0][gi])
+
+
+def test_stem_space_to_depth_and_maxpool(emu_paths):
+    def stem():
+        from flpr_b200.ops import gemm as gops
+        x = rand(3, 16, 8, 3, seed=1).to(torch.bfloat16)
+        y = rand(2, 9, 7, 64, seed=2).to(torch.bfloat16)
+        return gops.s2d_pad(x), gops.maxpool3x3s2(y)
+    with both(emu_paths) as run:
+        ref, got = run(stem)
+    assert torch.equal(got[0], ref[0])
+    assert torch.equal(got[1], ref[1])
