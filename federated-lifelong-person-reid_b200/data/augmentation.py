@@ -54,7 +54,7 @@ class DeviceAugment:
         """One fused sm_100a kernel (``csrc/fused_ops.cu: augment_u8_kernel``): normalise + flip + erase + cast."""
         import ctypes as C
         from ..ops import native
-        lib = native.load()
+        lib = native.kernels()
         b, h, w, _ = u8.shape
         u8 = u8.contiguous()
         u = torch.rand(7, b, device=u8.device, generator=generator)
@@ -68,14 +68,15 @@ class DeviceAugment:
                                  C.cast(mean3, C.c_void_p), C.cast(inv3, C.c_void_p),
                                  FLIP_P[self.level], ERASE_P[self.level], self.scale[0], self.scale[1],
                                  self.ratio[0], self.ratio[1], int(self.dtype == torch.bfloat16),
-                                 native.stream(u8.device))
+                                 native.stream_of(u8.device))
         native.check(rc, "flpr_augment_u8")
         native.count_launch()
         return out.permute(0, 3, 1, 2)
 
     def __call__(self, u8: torch.Tensor, generator: torch.Generator | None = None) -> torch.Tensor:
-        if u8.is_cuda and u8.shape[2] % 4 == 0 and self.dtype in (torch.bfloat16, torch.float32) \
-                and u8.dtype == torch.uint8:
+        from ..ops import native
+        if native.on_device(u8, "flpr_augment_u8") and u8.shape[2] % 4 == 0 \
+                and self.dtype in (torch.bfloat16, torch.float32) and u8.dtype == torch.uint8:
             return self._native(u8, generator)
         return self.reference(u8, generator)
 

@@ -100,6 +100,7 @@ def rewrite_launches(src: str) -> Tuple[str, int]:
 
 
 _DYN_SHARED_RE = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([A-Za-z_][\w:]*)\s+(\w+)\s*\[\s*\]\s*;")
+_SHARED_LIST_RE = re.compile(r"__shared__\s+([A-Za-z_][\w:]*)\s+([^;()=]*,[^;()=]*);")
 _SHARED_RE = re.compile(r"__shared__\s+([A-Za-z_][\w:]*(?:\s*<[^;<>]*>)?)\s+(\w+)\s*((?:\[[^\]]*\]\s*)*);")
 
 
@@ -109,13 +110,28 @@ def rewrite_shared(src: str) -> Tuple[str, int]:
     src = _DYN_SHARED_RE.sub(lambda m: f"{m.group(1)}* {m.group(2)} = reinterpret_cast<{m.group(1)}*>("
                                        f"flpr_emu::dyn_shared());", src)
 
-    def repl(m):
+    def one(ty, name, dims):
         nonlocal n
         n += 1
-        ty, name, dims = m.group(1), m.group(2), m.group(3).replace(" ", "")
         return (f"using flpr_sh_t{n} = {ty}{dims}; "
                 f"flpr_sh_t{n}& {name} = *flpr_emu::shared<flpr_sh_t{n}>({n});")
-    return _SHARED_RE.sub(repl, src), n
+
+    def repl(m):
+        return one(m.group(1), m.group(2), m.group(3).replace(" ", ""))
+
+    def repl_list(m):                                    # ``__shared__ int a, b[4], c;``
+        out = []
+        for decl in m.group(2).split(","):
+            d = re.match(r"\s*(\w+)\s*((?:\[[^\]]*\]\s*)*)$", decl)
+            assert d, decl
+            out.append(one(m.group(1), d.group(1), d.group(2).replace(" ", "")))
+        return " ".join(out)
+
+    src = _SHARED_LIST_RE.sub(repl_list, src)
+    src = _SHARED_RE.sub(repl, src)
+    code = re.sub(r"//[^\n]*", "", src)
+    assert "__shared__" not in code, "an unhandled __shared__ declaration would silently become a per-thread local"
+    return src, n
 
 
 def strip_inline_ptx_functions(src: str) -> Tuple[str, List[str]]:

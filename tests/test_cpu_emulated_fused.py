@@ -313,3 +313,19 @@ def test_stem_space_to_depth_and_maxpool(emu_paths):
         ref, got = run(stem)
     assert torch.equal(got[0], ref[0])
     assert torch.equal(got[1], ref[1])
+
+
+@pytest.mark.parametrize("level", ["none", "default"])
+def test_fused_augmentation_kernel(emu_paths, level):
+    """``augment_u8_kernel`` (normalise + flip + random erasing + cast in one pass) consumes the same block of uniforms as
+    the tensor-op reference: same generator state -> same batch (``datasets/image_augmentation.py:6-71``)."""
+    def aug():
+        from flpr_b200.data.augmentation import DeviceAugment
+        u8 = torch.randint(0, 256, (12, 32, 16, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3))
+        out = DeviceAugment(level, dtype=torch.float32)(u8, torch.Generator().manual_seed(77))
+        return (out.contiguous(),)
+    with both(emu_paths) as run:
+        ref, got = run(aug)
+    assert got[0].shape == ref[0].shape
+    frac = float(((got[0] - ref[0]).abs() > 1e-4).float().mean())
+    assert frac < 0.02, frac          # an erase rectangle may differ by one border pixel row (round-half cases), not more
