@@ -246,17 +246,26 @@ __global__ void __launch_bounds__(256) ln_rows_bwd_kernel(const __nv_bfloat16* _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 3;
   const float inv_c = 1.f / (float)C;
-  float dg[VPL][8], db[VPL][8], gm[VPL][8];
+  // gamma stays in registers up to C = 1024; the widest instantiation (C <= 2048: Swin-L) re-reads it from L1 instead -
+  // 64 more live registers there would spill
+  constexpr bool kCacheGamma = VPL <= 4;
+  constexpr int GV = kCacheGamma ? VPL : 1;
+  float dg[VPL][8], db[VPL][8], gm[GV][8];
+  auto load_gamma = [&](int idx, float* g8) {
+    const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * idx], g1 = reinterpret_cast<const float4*>(gamma)[2 * idx + 1];
+    g8[0] = g0.x; g8[1] = g0.y; g8[2] = g0.z; g8[3] = g0.w;
+    g8[4] = g1.x; g8[5] = g1.y; g8[6] = g1.z; g8[7] = g1.w;
+  };
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int idx = lane + 32 * i;
-    if (idx < nvec) {
-      const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * idx], g1 = reinterpret_cast<const float4*>(gamma)[2 * idx + 1];
-      gm[i][0] = g0.x; gm[i][1] = g0.y; gm[i][2] = g0.z; gm[i][3] = g0.w;
-      gm[i][4] = g1.x; gm[i][5] = g1.y; gm[i][6] = g1.z; gm[i][7] = g1.w;
-    } else {
+    if (kCacheGamma) {
+      if (idx < nvec) {
+        load_gamma(idx, gm[i % GV]);
+      } else {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) gm[i][t] = 0.f;
+        for (int t = 0; t < 8; ++t) gm[i % GV][t] = 0.f;
+      }
     }
 #pragma unroll
     for (int t = 0; t < 8; ++t) dg[i][t] = db[i][t] = 0.f;
@@ -274,13 +283,15 @@ __global__ void __launch_bounds__(256) ln_rows_bwd_kernel(const __nv_bfloat16* _
       if (idx < nvec) {
         xu[i] = xp[idx];
         yu[i] = yp[idx];
-        float xv[8], yv[8];
+        float xv[8], yv[8], gl[8];
         unpack8(xu[i], xv);
         unpack8(yu[i], yv);
+        if (!kCacheGamma) load_gamma(idx, gl);
+        const float* gv = kCacheGamma ? gm[i % GV] : gl;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           const float xh = (xv[t] - st.x) * st.y;
-          const float g = yv[t] * gm[i][t];
+          const float g = yv[t] * gv[t];
           s1 += g;
           s2 = fmaf(g, xh, s2);
           dg[i][t] = fmaf(yv[t], xh, dg[i][t]);
@@ -295,13 +306,15 @@ __global__ void __launch_bounds__(256) ln_rows_bwd_kernel(const __nv_bfloat16* _
     for (int i = 0; i < VPL; ++i) {
       const int idx = lane + 32 * i;
       if (idx < nvec) {
-        float xv[8], yv[8], o[8];
+        float xv[8], yv[8], o[8], gl[8];
         unpack8(xu[i], xv);
         unpack8(yu[i], yv);
+        if (!kCacheGamma) load_gamma(idx, gl);
+        const float* gv = kCacheGamma ? gm[i % GV] : gl;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           const float xh = (xv[t] - st.x) * st.y;
-          o[t] = st.y * (yv[t] * gm[i][t] - s1 - xh * s2);
+          o[t] = st.y * (yv[t] * gv[t] - s1 - xh * s2);
         }
         op[idx] = pack8(o);
       }
