@@ -355,11 +355,13 @@ __global__ void __launch_bounds__(256) ln_colsum_kernel(const float* __restrict_
   out[j] = t;
 }
 
-// out[image row r] = shortcut[r] + win[image_row_to_window_row(r)]   (8 channels per thread)
+// out[image row r] = shortcut[r] + scale[b(r)] * win[image_row_to_window_row(r)]   (8 channels per thread; scale: the
+// per-sample drop-path factor 0 or 1 / keep of a TRAINABLE block, nullptr = 1)
 __global__ void __launch_bounds__(256) window_merge_add_kernel(const __nv_bfloat16* __restrict__ win,
                                                                const __nv_bfloat16* __restrict__ shortcut,
                                                                __nv_bfloat16* __restrict__ out, long long rows, int C,
-                                                               int H, int W, int ws, int shift) {
+                                                               int H, int W, int ws, int shift,
+                                                               const float* __restrict__ scale) {
   const int nvec = C >> 3;
   const long long total = rows * nvec;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -372,9 +374,36 @@ __global__ void __launch_bounds__(256) window_merge_add_kernel(const __nv_bfloat
     float fa[8], fb[8];
     unpack8(a, fa);
     unpack8(b, fb);
+    const float sc = scale != nullptr ? scale[r / ((long long)H * W)] : 1.f;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) fa[t] += fb[t];
+    for (int t = 0; t < 8; ++t) fa[t] = fmaf(sc, fb[t], fa[t]);
     reinterpret_cast<uint4*>(out + r * C)[vi] = pack8(fa);
+  }
+}
+
+// Backward of the merge w.r.t. the window-layout operand: dwin[window row r] = scale[b(r)] * dy[window_row_to_image_row(r)]
+// (a pure gather; the gradient of the shortcut operand is dy itself).
+__global__ void __launch_bounds__(256) window_gather_scale_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                  __nv_bfloat16* __restrict__ dwin, long long rows,
+                                                                  int C, int H, int W, int ws, int shift,
+                                                                  const float* __restrict__ scale) {
+  const int nvec = C >> 3;
+  const long long total = rows * nvec;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / nvec;
+    const int vi = (int)(i - r * nvec);
+    const long long src = window_row_to_image_row(r, H, W, ws, shift);
+    uint4 v = reinterpret_cast<const uint4*>(dy + src * C)[vi];
+    if (scale != nullptr) {
+      float f[8];
+      unpack8(v, f);
+      const float sc = scale[src / ((long long)H * W)];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) f[t] *= sc;
+      v = pack8(f);
+    }
+    reinterpret_cast<uint4*>(dwin + r * C)[vi] = v;
   }
 }
 
@@ -558,7 +587,31 @@ int flpr_window_merge_add(const void* win, const void* shortcut, void* out, long
   bind_device_of(win);
   window_merge_add_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(win), reinterpret_cast<const __nv_bfloat16*>(shortcut),
-      reinterpret_cast<__nv_bfloat16*>(out), rows, C, H, W, ws, shift);
+      reinterpret_cast<__nv_bfloat16*>(out), rows, C, H, W, ws, shift, nullptr);
+  return (int)cudaGetLastError();
+}
+
+// Trainable block: out = shortcut + scale[sample] * merge(win)  (scale: [rows / (H*W)] fp32, nullable).
+int flpr_window_merge_add_scaled(const void* win, const void* shortcut, const float* scale, void* out, long long rows,
+                                 int C, int H, int W, int ws, int shift, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (C % 8 || ws <= 0 || H % ws || W % ws || shift < 0 || shift >= ws || rows % ((long long)H * W)) return -24;
+  bind_device_of(win);
+  window_merge_add_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(win), reinterpret_cast<const __nv_bfloat16*>(shortcut),
+      reinterpret_cast<__nv_bfloat16*>(out), rows, C, H, W, ws, shift, scale);
+  return (int)cudaGetLastError();
+}
+
+// Its backward w.r.t. win: dwin = scale[sample] * gather(dy) in window layout.
+int flpr_window_gather_scale(const void* dy, const float* scale, void* dwin, long long rows, int C, int H, int W, int ws,
+                             int shift, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (C % 8 || ws <= 0 || H % ws || W % ws || shift < 0 || shift >= ws || rows % ((long long)H * W)) return -24;
+  bind_device_of(dy);
+  window_gather_scale_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<__nv_bfloat16*>(dwin), rows, C, H, W, ws, shift,
+      scale);
   return (int)cudaGetLastError();
 }
 

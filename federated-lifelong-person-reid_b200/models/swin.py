@@ -304,12 +304,55 @@ class SwinTransformerBlock(nn.Module):
         out = gops.gemm(hid, wb, bias_n=fc2.bias.detach().float(), residual=x2)
         return out.view(b, l, c)
 
+    def _fused_train_ok(self, x: torch.Tensor) -> bool:
+        """Trainable stage on the bf16 path: both block norms are :class:`TrainLayerNorm` (fp32 affine parameters in the
+        arena) and the LayerNorm / merge kernels passed their self-check."""
+        if not (x.is_cuda and x.dtype == torch.bfloat16 and torch.is_grad_enabled()):
+            return False
+        c = x.shape[-1]
+        if c % 8 or c > 2048 or type(self.norm1) is not TrainLayerNorm or type(self.norm2) is not TrainLayerNorm:
+            return False
+        for p in (self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias):
+            if p is None or p.dtype != torch.float32 or p.data_ptr() % 16:
+                return False
+        return lops.enabled("ln_train", x.device)
+
+    def _drop_scale(self, batch: int, like: torch.Tensor) -> Optional[torch.Tensor]:
+        """This call's stochastic-depth factors ``[B]`` (0 or ``1 / keep``), drawn exactly like :class:`DropPath` does."""
+        p = self.drop_path.p
+        if p == 0.0 or not self.training:
+            return None
+        keep = 1.0 - p
+        mask = like.new_empty((batch, 1, 1)).bernoulli_(keep)
+        return (mask.float().view(batch) / keep).contiguous()
+
+    def _forward_fused_train(self, x: torch.Tensor) -> torch.Tensor:
+        """The trainable block with the token passes of the first half fused (``models/swin_transformer.py:358-395``):
+        ``norm1`` writes straight into the layout of the shifted windows (norm + roll + window partition: one kernel
+        forward, one backward), and window reverse + roll back + drop-path scaling + residual add is one kernel (its
+        backward: one gather). ``norm2`` is the native LayerNorm; the MLP half keeps its module form."""
+        h, w = self.resolution
+        b, l, c = x.shape
+        ws, sh = self.window_size, self.shift_size
+        x2 = x.reshape(b * l, c)
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        win = lops.layer_norm_rows(x2, self.norm1.weight, self.norm1.bias, self.norm1.eps, (h, w, ws, sh))
+        att = self.attn(win.view(-1, ws * ws, c), self.attn_mask).reshape(-1, c)
+        if att.dtype != x2.dtype:
+            att = att.to(x2.dtype)
+        x2 = lops.window_merge_residual(att if att.is_contiguous() else att.contiguous(), x2, self._drop_scale(b, x2),
+                                        h, w, ws, sh)
+        x3 = x2.view(b, l, c)
+        return x3 + self.drop_path(self.mlp(self.norm2(x3)))
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         h, w = self.resolution
         b, l, c = x.shape
         assert l == h * w, "input feature has wrong size"
         if self._fused_ok(x):
             return self._forward_fused(x)
+        if self._fused_train_ok(x):
+            return self._forward_fused_train(x)
         shortcut = x
         x = self.norm1(x).view(b, h, w, c)
         if self.shift_size > 0:

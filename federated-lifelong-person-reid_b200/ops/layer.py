@@ -39,6 +39,8 @@ def _declare(lib) -> None:
         "flpr_ln_rows_train": [P, P, P, P, P, L, I, Fl, I, I, I, I, I, P],
         "flpr_ln_rows_bwd": [P, P, P, P, P, P, P, L, I, I, I, I, I, I, P],
         "flpr_window_merge_add": [P, P, P, L, I, I, I, I, I, P],
+        "flpr_window_merge_add_scaled": [P, P, P, P, L, I, I, I, I, I, P],
+        "flpr_window_gather_scale": [P, P, P, L, I, I, I, I, I, P],
         "flpr_gelu_rows": [P, P, L, P],
         "flpr_apply_global": [P, P, P, P, I, L, P],
     }
@@ -456,6 +458,84 @@ def window_merge_add(win: torch.Tensor, shortcut: torch.Tensor, H: int, W: int, 
     return out
 
 
+# ---- trainable block: merge + residual with the per-sample drop-path factor, and its backward ---------------------------------
+def window_merge_add_scaled_ref(win, shortcut, scale, H, W, ws, shift):
+    rows = shortcut.shape[0]
+    g = win[image_src_rows(rows, H, W, ws, shift, win.device)].float()
+    if scale is not None:
+        g = g * scale.float().repeat_interleave(H * W)[:, None]
+    return (shortcut.float() + g).to(shortcut.dtype)
+
+
+def window_merge_add_scaled(win: torch.Tensor, shortcut: torch.Tensor, scale: Optional[torch.Tensor], H: int, W: int,
+                            ws: int, shift: int) -> torch.Tensor:
+    """``shortcut + scale[sample] * roll(window_reverse(win), +shift)`` over ``[B*H*W, C]`` bf16 rows (``scale``: ``[B]``
+    fp32 drop-path factors 0 or ``1 / keep``; ``None`` = 1)."""
+    if not _native(win):
+        return window_merge_add_scaled_ref(win, shortcut, scale, H, W, ws, shift)
+    lib = _lib()
+    rows, c = shortcut.shape
+    assert win.shape == shortcut.shape and win.dtype == torch.bfloat16 and shortcut.dtype == torch.bfloat16
+    assert win.is_contiguous() and shortcut.is_contiguous() and c % 8 == 0
+    assert scale is None or (scale.dtype == torch.float32 and scale.is_contiguous() and scale.numel() == rows // (H * W))
+    out = torch.empty_like(shortcut)
+    rc = lib.flpr_window_merge_add_scaled(native.ptr(win), native.ptr(shortcut), native.ptr(scale), native.ptr(out), rows,
+                                          c, int(H), int(W), int(ws), int(shift), _stream(win.device))
+    native.check(rc, "flpr_window_merge_add_scaled")
+    native.count_launch()
+    return out
+
+
+def window_gather_scale_ref(dy, scale, H, W, ws, shift):
+    rows = dy.shape[0]
+    src = window_src_rows(rows, H, W, ws, shift, dy.device)
+    g = dy[src].float()
+    if scale is not None:
+        g = g * scale.float().repeat_interleave(H * W)[src][:, None]
+    return g.to(dy.dtype)
+
+
+def window_gather_scale(dy: torch.Tensor, scale: Optional[torch.Tensor], H: int, W: int, ws: int, shift: int
+                        ) -> torch.Tensor:
+    """Backward of :func:`window_merge_add_scaled` w.r.t. ``win``: ``scale[sample] * dy`` gathered into window layout."""
+    if not _native(dy):
+        return window_gather_scale_ref(dy, scale, H, W, ws, shift)
+    lib = _lib()
+    rows, c = dy.shape
+    assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and c % 8 == 0
+    out = torch.empty_like(dy)
+    rc = lib.flpr_window_gather_scale(native.ptr(dy), native.ptr(scale), native.ptr(out), rows, c, int(H), int(W),
+                                      int(ws), int(shift), _stream(dy.device))
+    native.check(rc, "flpr_window_gather_scale")
+    native.count_launch()
+    return out
+
+
+class _WindowMergeAddFn(torch.autograd.Function):
+    """``out = shortcut + scale[sample] * merge(win)`` (``models/swin_transformer.py:383-391`` incl. the block's
+    ``drop_path``): window reverse, roll back, stochastic-depth scaling and the residual add in one pass; backward: the
+    shortcut gradient is ``dy`` itself, the window gradient one gather pass."""
+
+    @staticmethod
+    def forward(ctx, win, shortcut, scale, H, W, ws, shift):
+        ctx.cfg = (H, W, ws, shift)
+        ctx.save_for_backward(scale)
+        return window_merge_add_scaled(win, shortcut, scale, H, W, ws, shift)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (scale,) = ctx.saved_tensors
+        dyc = dy if dy.is_contiguous() else dy.contiguous()
+        dwin = window_gather_scale(dyc, scale, *ctx.cfg) if ctx.needs_input_grad[0] else None
+        return dwin, (dyc if ctx.needs_input_grad[1] else None), None, None, None, None, None
+
+
+def window_merge_residual(win: torch.Tensor, shortcut: torch.Tensor, scale: Optional[torch.Tensor], H: int, W: int,
+                          ws: int, shift: int) -> torch.Tensor:
+    """Differentiable :func:`window_merge_add_scaled`."""
+    return _WindowMergeAddFn.apply(win, shortcut, scale, int(H), int(W), int(ws), int(shift))
+
+
 def gelu_rows(x: torch.Tensor) -> torch.Tensor:
     """Exact (erf) GELU over a bf16 tensor."""
     if not _native(x):
@@ -585,6 +665,13 @@ def _check_ln_train(dev) -> bool:
             dx, dg, db = ln_rows_bwd(dy, x, gamma, stats, window)
             ok = ok and _close(dx, xr.grad, 3e-2, 1e-2) and _close(dg, gr.grad, 1e-2, 5e-3) and \
                 _close(db, br.grad, 1e-3, 1e-4)
+        # merge + residual with the per-sample drop-path factor, and the gather that is its backward
+        win = torch.randn(rows, c, generator=g).to(dev).to(torch.bfloat16)
+        for scale in (None, (torch.rand(b, generator=g) < 0.6).float().div(0.6).to(dev)):
+            ok = ok and _close(window_merge_add_scaled(win, x, scale, h, w, ws, shift),
+                               window_merge_add_scaled_ref(win, x, scale, h, w, ws, shift), 1e-2, 1e-2)
+            ok = ok and _close(window_gather_scale(dy, scale, h, w, ws, shift),
+                               window_gather_scale_ref(dy, scale, h, w, ws, shift), 1e-2, 1e-2)
     return ok
 
 

@@ -316,6 +316,79 @@ def check_swin_train_block_norms(device):
         assert cos > 0.98, (name, cos)
 
 
+def check_window_merge_residual(device):
+    """``ops.layer.window_merge_residual`` (window reverse + roll back + per-sample drop-path factor + residual, one op)
+    forward and both gradients vs the block's original formulation."""
+    from flpr_b200.models.swin import window_reverse
+    from flpr_b200.ops import layer as lops
+    g = torch.Generator().manual_seed(51)
+    for (b, h, w, ws, shift, c) in ((3, 8, 8, 4, 2, 96), (2, 14, 14, 7, 0, 192), (4, 8, 4, 4, 1, 768)):
+        rows = b * h * w
+        win0 = torch.randn(rows, c, generator=g).to(device).to(torch.bfloat16)
+        sc0 = torch.randn(rows, c, generator=g).to(device).to(torch.bfloat16)
+        dy = torch.randn(rows, c, generator=g).to(device).to(torch.bfloat16)
+        for scale in (None, (torch.rand(b, generator=g) < 0.7).float().div(0.7).to(device)):
+            win, sc = win0.clone().requires_grad_(True), sc0.clone().requires_grad_(True)
+            out = lops.window_merge_residual(win, sc, scale, h, w, ws, shift)
+            out.backward(dy)
+            wr, sr = win0.float().requires_grad_(True), sc0.float().requires_grad_(True)
+            back = window_reverse(wr.view(-1, ws * ws, c), ws, h, w)
+            if shift:
+                back = torch.roll(back, shifts=(shift, shift), dims=(1, 2))
+            back = back.reshape(b, h * w, c)
+            if scale is not None:
+                back = back * scale.view(b, 1, 1)
+            ref = sr + back.reshape(rows, c)
+            ref.backward(dy.float())
+            close(out, ref, rtol=2e-2, atol=2e-2)
+            close(win.grad, wr.grad, rtol=2e-2, atol=2e-2)
+            close(sc.grad, sr.grad, rtol=0, atol=0)
+
+
+def check_swin_train_block_fused(device):
+    """``SwinTransformerBlock._forward_fused_train`` (norm1 into the window layout, merge + drop-path + residual in one op)
+    vs the plain block: outputs and every parameter / input gradient, without and with stochastic depth (same seed ->
+    same per-sample masks). On the CPU both run in fp32 through the reference forms of the ops: a tight comparison of
+    the autograd glue and the index mathematics; on CUDA the fused side runs the kernels in bf16."""
+    import copy
+    from flpr_b200.models.swin import SwinTransformerBlock
+    for (dim, res, heads, ws, shift, dp) in ((96, (8, 8), 3, 4, 2, 0.0), (192, (8, 4), 6, 4, 0, 0.3), (96, (14, 14), 3, 7, 3, 0.2)):
+        torch.manual_seed(7)
+        blk = SwinTransformerBlock(dim, res, heads, ws, shift, drop_path=dp).to(device).train()
+        ref = copy.deepcopy(blk)
+        bsz = 5
+        x0 = torch.randn(bsz, res[0] * res[1], dim).to(device)
+        tgt = torch.randn(bsz, res[0] * res[1], dim).to(device)
+        xr = x0.clone().requires_grad_(True)
+        torch.manual_seed(99)
+        out_r = ref(xr)
+        F.mse_loss(out_r, tgt).backward()
+        if device == "cpu":
+            xf = x0.clone().requires_grad_(True)
+            torch.manual_seed(99)
+            out_f = blk._forward_fused_train(xf)
+            tol, gtol = 1e-5, 1e-4
+        else:
+            from flpr_b200.models.swin import use_tensor_core_linears
+            use_tensor_core_linears(blk)
+            xf = x0.to(torch.bfloat16).requires_grad_(True)
+            assert blk._fused_train_ok(xf) or not __import__("flpr_b200.ops.layer", fromlist=["x"]).enabled("ln_train", device)
+            torch.manual_seed(99)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out_f = blk._forward_fused_train(xf)
+            tol, gtol = 5e-2, 5e-2
+        F.mse_loss(out_f.float(), tgt).backward()
+        close(out_f, out_r, rtol=tol, atol=tol * out_r.abs().max().item())
+        close(xf.grad, xr.grad, rtol=gtol * 10, atol=gtol * xr.grad.abs().max().item())
+        for (name, pf), (_, pr) in zip(blk.named_parameters(), ref.named_parameters()):
+            assert pf.grad is not None, name
+            if device == "cpu":
+                close(pf.grad, pr.grad, rtol=1e-3, atol=gtol * pr.grad.abs().max().item() + 1e-7)
+            else:
+                cos = F.cosine_similarity(pf.grad.float().flatten(), pr.grad.flatten(), dim=0).item()
+                assert cos > 0.97, (name, cos)
+
+
 # ------------------------------------------------------------------------------------------------ dispatch apply
 def check_apply_global(device):
     """``ops.layer.apply_global`` (master <- global + bf16 copy + FedProx anchor in one pass) vs the three copies."""

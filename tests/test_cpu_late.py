@@ -47,6 +47,14 @@ def test_swin_train_block_norm_classes():
     L.check_swin_train_block_norms("cpu")
 
 
+def test_window_merge_residual_reference_path():
+    L.check_window_merge_residual("cpu")
+
+
+def test_swin_train_block_fused_path_matches_plain_block():
+    L.check_swin_train_block_fused("cpu")
+
+
 def test_apply_global_reference_semantics():
     L.check_apply_global("cpu")
 

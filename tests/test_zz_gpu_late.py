@@ -61,6 +61,14 @@ def test_swin_train_block_norms_native():
     L.check_swin_train_block_norms("cuda")
 
 
+def test_window_merge_residual_native():
+    L.check_window_merge_residual("cuda")
+
+
+def test_swin_train_block_fused_native():
+    L.check_swin_train_block_fused("cuda")
+
+
 def test_swin_block_fused_native():
     L.check_swin_block_fused("cuda")
 
