@@ -421,6 +421,25 @@ __global__ void __launch_bounds__(256) gelu_rows_kernel(const __nv_bfloat16* __r
   }
 }
 
+// d/dx GELU(x) = Phi(x) + x * phi(x)   (exact form; x is the saved pre-activation), 8 bf16 per thread
+__global__ void __launch_bounds__(256) gelu_bwd_rows_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ dy,
+                                                            __nv_bfloat16* __restrict__ dx, long long nvec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float f[8], g[8];
+    unpack8(reinterpret_cast<const uint4*>(x)[i], f);
+    unpack8(reinterpret_cast<const uint4*>(dy)[i], g);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float cdf = 0.5f * (1.f + erff(f[t] * 0.70710678118654752440f));
+      const float pdf = 0.39894228040143267794f * expf(-0.5f * f[t] * f[t]);
+      g[t] *= fmaf(f[t], pdf, cdf);
+    }
+    reinterpret_cast<uint4*>(dx)[i] = pack8(g);
+  }
+}
+
 // C2 tail on the receiving client: master <- aggregated parameters, bf16 compute copy refreshed and the FedProx anchor
 // snapshotted in the same pass (snap_mode 1: the weights being replaced = the reference's order of operations,
 // methods/fedprox.py:351-364; 2: the incoming global model = textbook FedProx). 4 floats per thread.
@@ -612,6 +631,16 @@ int flpr_window_gather_scale(const void* dy, const float* scale, void* dwin, lon
   window_gather_scale_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<__nv_bfloat16*>(dwin), rows, C, H, W, ws, shift,
       scale);
+  return (int)cudaGetLastError();
+}
+
+int flpr_gelu_bwd_rows(const void* x, const void* dy, void* dx, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (n % 8) return -23;
+  bind_device_of(x);
+  gelu_bwd_rows_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                            reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                            reinterpret_cast<__nv_bfloat16*>(dx), n / 8);
   return (int)cudaGetLastError();
 }
 

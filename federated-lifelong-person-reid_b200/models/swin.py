@@ -153,7 +153,13 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+        h = self.fc1(x)
+        if h.is_cuda and h.dtype == torch.bfloat16 and torch.is_grad_enabled() and h.requires_grad \
+                and h.numel() % 8 == 0 and lops.enabled("ln_train", h.device):
+            h = lops.gelu_act(h if h.is_contiguous() else h.contiguous())   # native forward / backward (trainable stage)
+        else:
+            h = self.act(h)
+        return self.drop(self.fc2(self.drop(h)))
 
 
 def window_partition(x: torch.Tensor, ws: int) -> torch.Tensor:

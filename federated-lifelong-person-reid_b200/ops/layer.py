@@ -42,6 +42,7 @@ def _declare(lib) -> None:
         "flpr_window_merge_add_scaled": [P, P, P, P, L, I, I, I, I, I, P],
         "flpr_window_gather_scale": [P, P, P, L, I, I, I, I, I, P],
         "flpr_gelu_rows": [P, P, L, P],
+        "flpr_gelu_bwd_rows": [P, P, P, L, P],
         "flpr_apply_global": [P, P, P, P, I, L, P],
     }
     for name, argtypes in sig.items():
@@ -549,6 +550,47 @@ def gelu_rows(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gelu_bwd_rows_ref(x, dy):
+    xf = x.float()
+    cdf = 0.5 * (1 + torch.erf(xf * 0.7071067811865476))
+    pdf = 0.3989422804014327 * torch.exp(-0.5 * xf * xf)
+    return (dy.float() * (cdf + xf * pdf)).to(x.dtype)
+
+
+def gelu_bwd_rows(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """``dy * GELU'(x)`` (exact form) over bf16 tensors; ``x`` is the saved pre-activation."""
+    if not _native(x):
+        return gelu_bwd_rows_ref(x, dy)
+    lib = _lib()
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
+    assert x.shape == dy.shape and x.numel() % 8 == 0
+    dx = torch.empty_like(x)
+    native.check(lib.flpr_gelu_bwd_rows(native.ptr(x), native.ptr(dy), native.ptr(dx), x.numel(), _stream(x.device)),
+                 "flpr_gelu_bwd_rows")
+    native.count_launch()
+    return dx
+
+
+class _GeluFn(torch.autograd.Function):
+    """Exact GELU of the Swin MLP (``models/swin_transformer.py:118-140``) in the trainable stage: one pass forward, one
+    pass backward from the saved pre-activation."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return gelu_rows(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return gelu_bwd_rows(x, dy if (dy.dtype == x.dtype and dy.is_contiguous()) else dy.to(x.dtype).contiguous())
+
+
+def gelu_act(x: torch.Tensor) -> torch.Tensor:
+    """Differentiable :func:`gelu_rows` (``x``: bf16, contiguous, numel % 8 == 0)."""
+    return _GeluFn.apply(x)
+
+
 # ===================================================================================================== dispatch apply
 def apply_global_ref(flat, master, shadow, p_old, snap_mode):
     n = flat.numel()
@@ -665,6 +707,7 @@ def _check_ln_train(dev) -> bool:
             dx, dg, db = ln_rows_bwd(dy, x, gamma, stats, window)
             ok = ok and _close(dx, xr.grad, 3e-2, 1e-2) and _close(dg, gr.grad, 1e-2, 5e-3) and \
                 _close(db, br.grad, 1e-3, 1e-4)
+        ok = ok and _close(gelu_bwd_rows(x, dy), gelu_bwd_rows_ref(x, dy), 2e-2, 1e-2)
         # merge + residual with the per-sample drop-path factor, and the gather that is its backward
         win = torch.randn(rows, c, generator=g).to(dev).to(torch.bfloat16)
         for scale in (None, (torch.rand(b, generator=g) < 0.6).float().div(0.6).to(dev)):

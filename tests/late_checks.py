@@ -316,6 +316,23 @@ def check_swin_train_block_norms(device):
         assert cos > 0.98, (name, cos)
 
 
+def check_gelu_act(device):
+    """``ops.layer.gelu_act`` (exact GELU, native forward / backward from the saved pre-activation) vs ``F.gelu`` autograd."""
+    from flpr_b200.ops import layer as lops
+    g = torch.Generator().manual_seed(61)
+    for shape in ((37, 384), (5, 32, 3072), (8,)):
+        x0 = (torch.randn(*shape, generator=g) * 2).to(device).to(torch.bfloat16)
+        dy = torch.randn(*shape, generator=g).to(device).to(torch.bfloat16)
+        x = x0.clone().requires_grad_(True)
+        y = lops.gelu_act(x)
+        y.backward(dy)
+        xr = x0.float().requires_grad_(True)
+        yr = F.gelu(xr)
+        yr.backward(dy.float())
+        close(y, yr, rtol=2e-2, atol=2e-2)
+        close(x.grad, xr.grad, rtol=2e-2, atol=2e-2)
+
+
 def check_window_merge_residual(device):
     """``ops.layer.window_merge_residual`` (window reverse + roll back + per-sample drop-path factor + residual, one op)
     forward and both gradients vs the block's original formulation."""

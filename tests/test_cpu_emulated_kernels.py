@@ -92,6 +92,10 @@ def test_swin_token_kernels_emulated(emu):
     L.check_swin_token_ops("cpu")
 
 
+def test_gelu_act_emulated(emu):
+    L.check_gelu_act("cpu")
+
+
 def test_window_merge_residual_emulated(emu):
     L.check_window_merge_residual("cpu")
 

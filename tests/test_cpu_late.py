@@ -47,6 +47,10 @@ def test_swin_train_block_norm_classes():
     L.check_swin_train_block_norms("cpu")
 
 
+def test_gelu_act_reference_path():
+    L.check_gelu_act("cpu")
+
+
 def test_window_merge_residual_reference_path():
     L.check_window_merge_residual("cpu")
 

@@ -61,6 +61,10 @@ def test_swin_train_block_norms_native():
     L.check_swin_train_block_norms("cuda")
 
 
+def test_gelu_act_native():
+    L.check_gelu_act("cuda")
+
+
 def test_window_merge_residual_native():
     L.check_window_merge_residual("cuda")
 
