@@ -329,3 +329,44 @@ def test_fused_augmentation_kernel(emu_paths, level):
     assert got[0].shape == ref[0].shape
     frac = float(((got[0] - ref[0]).abs() > 1e-4).float().mean())
     assert frac < 0.02, frac          # an erase rectangle may differ by one border pixel row (round-half cases), not more
+
+
+# ------------------------------------------------------------------------------------------------------------ integration
+def _run_tiny(tmp, method, emu_paths):
+    from helpers import tiny_common, tiny_experiment, tiny_factory
+    from flpr_b200.ops import native
+    from flpr_b200.runtime.experiment import ExperimentStage
+    native.use_emulated_libraries(emu_paths)
+    try:
+        common = tiny_common(str(tmp))
+        common["defaults"]["exp_opts"].update(comm_rounds=2, val_interval=2)
+        cfg = tiny_experiment(common, method)
+        cfg["engine_opts"].update(val_at_round0=False)
+        before = native.launches()
+        with ExperimentStage(common, [cfg], source_factory=tiny_factory()) as stage:
+            log = stage.run_experiment(cfg)
+        launches = native.launches() - before
+    finally:
+        native.use_emulated_libraries(None)
+    out = {}
+    for client, per_round in log.records["data"].items():
+        for rnd, tasks in per_round.items():
+            for task, v in tasks.items():
+                for key in ("tr_loss", "val_map", "val_rank_1"):
+                    if key in v:
+                        out[(client, int(rnd), task, key)] = float(v[key])
+    return out, launches
+
+
+@pytest.mark.parametrize("method", ["fedavg", "ewc"] + (["fedstil"] if __import__("os").environ.get("FLPR_EMU_FULL") else []))
+def test_whole_experiment_on_the_emulated_kernels(tmp_path, emu_paths, method):
+    """A tiny experiment run twice through the engine - PyTorch reference paths, then with the emulated libraries installed,
+    so that the fused optimizer, importance accumulation, label-smoothing CE (+ its device accumulators), the augmentation
+    kernel, the ranking kernel of the validation pass (and, with ``FLPR_EMU_FULL=1``, FedSTIL's herding / compose) run
+    from the engine's own call sites. Logged training losses and CMC / mAP must agree."""
+    ref, n0 = _run_tiny(tmp_path / "ref", method, None)
+    got, n1 = _run_tiny(tmp_path / "emu", method, emu_paths)
+    assert n0 == 0 and n1 >= 20, (n0, n1)
+    assert ref.keys() == got.keys() and len(ref) >= 6
+    for key in ref:
+        assert abs(ref[key] - got[key]) <= 5e-3 * abs(ref[key]) + 1e-6, (key, ref[key], got[key])
