@@ -58,3 +58,16 @@ def test_reference_arm_reports_itself_when_the_reference_is_missing(tmp_path):
     finally:
         ra.REF = saved
     assert out["impl"] == "reference" and "unavailable" in out and "\n" not in out["unavailable"]
+
+
+def test_reference_arm_runs_the_installed_reference():
+    """``--impl reference --cpu-debug``: the unmodified reference in ``baseline/_ref`` driven through its own builder /
+    ``ExperimentStage._process_one_round`` prints the same JSON line (``impl: reference``)."""
+    import pytest
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "methods")):
+        pytest.skip("reference is not installed in baseline/_ref")
+    d = _run("--impl", "reference", "--cpu-debug", "--steps", "1", "--warmup", "1")
+    assert d.get("impl") == "reference" and "unavailable" not in d
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config"):
+        assert key in d, key
+    assert d["value"] > 0 and d["steps"] == 1
