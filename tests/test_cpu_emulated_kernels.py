@@ -140,3 +140,46 @@ def test_emulator_reports_a_barrier_not_every_thread_reaches(tmp_path):
     lib.run_bad(ctypes.c_void_p(bad.data_ptr()))
     assert lib.flpr_emu_deadlocks() == 1
     assert os.path.exists(lib_path)
+
+
+def test_emulator_primitives(tmp_path):
+    """The emulator's own building blocks on a purpose-written kernel: 2-D grids, multi-dimensional blocks, dynamic and
+    static shared memory (per block, zero-initialised), ``atomicAdd``, ``__syncthreads_or``, ``__shfl_down_sync``."""
+    import ctypes
+    import subprocess
+    from emu.build_emu import CUDA_INCLUDE, HERE, rewrite_launches, rewrite_shared
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    cu = ('#include "cuda_emu.h"\n'
+          "__global__ void k(int* out, int* votes, float* red, int n) {\n"
+          "  extern __shared__ int dyn[];\n"
+          "  __shared__ int s_count, s_flag[2];\n"
+          "  const int lin = threadIdx.y * blockDim.x + threadIdx.x;\n"
+          "  const int b = blockIdx.y * gridDim.x + blockIdx.x;\n"
+          "  dyn[lin] = lin + b;\n"
+          "  atomicAdd(&s_count, 1);\n"
+          "  const int any = __syncthreads_or(lin == 5 && b == 1);\n"
+          "  if (lin == 0) { out[b] = s_count + dyn[blockDim.x * blockDim.y - 1]; votes[b] = any; s_flag[0] = b; }\n"
+          "  float v = (float)(lin & 31);\n"
+          "  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);\n"
+          "  if ((lin & 31) == 0) red[b * (n / 32) + lin / 32] = v;\n"
+          "}\n"
+          'extern "C" void run(int* out, int* votes, float* red) {\n'
+          "  k<<<dim3(2, 3), dim3(16, 4), 64 * sizeof(int), 0>>>(out, votes, red, 64);\n"
+          "}\n")
+    src, n_sh = rewrite_shared(cu)
+    src, n_l = rewrite_launches(src)
+    assert n_sh == 2 and n_l == 1
+    path = tmp_path / "prim.cpp"
+    path.write_text(src)
+    lib_path = str(tmp_path / "libprim.so")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-Wno-attributes", "-Wno-unused-function", "-I", HERE,
+                    "-I", CUDA_INCLUDE, str(path), "-o", lib_path], check=True)
+    lib = ctypes.CDLL(lib_path)
+    out, votes = torch.zeros(6, dtype=torch.int32), torch.full((6,), -1, dtype=torch.int32)
+    red = torch.zeros(6 * 2)
+    lib.run(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(votes.data_ptr()), ctypes.c_void_p(red.data_ptr()))
+    assert out.tolist() == [64 + 63 + b for b in range(6)]              # 64 threads counted, dyn[63] = 63 + b
+    assert votes.tolist() == [0, 1, 0, 0, 0, 0]                          # only block 1 had a voting thread
+    assert torch.equal(red, torch.full((12,), float(sum(range(32)))))   # lane 0 holds the warp sum
+    assert lib.flpr_emu_deadlocks() == 0
