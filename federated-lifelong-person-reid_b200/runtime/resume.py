@@ -120,6 +120,7 @@ def save(stage, store, curr_round: int, server, clients, comm) -> None:
     with open(tmp, "w") as f:
         json.dump({"round": int(curr_round), "world": stage.world}, f)
     os.replace(tmp, marker)
+    _drop_other_worlds(stage, store)
     maybe_inject_fault(stage, curr_round, "saved")
 
 
@@ -167,11 +168,53 @@ def available(store, rank: int) -> bool:
     return bool(_committed(store, rank))
 
 
+def _markers(store):
+    """``(path, round, world)`` of every commit marker in the store's ``_resume`` directory."""
+    d = os.path.dirname(store.path(ACTOR, "x"))
+    out = []
+    if os.path.isdir(d):
+        for name in os.listdir(d):
+            if name.endswith(".ok"):
+                try:
+                    with open(os.path.join(d, name)) as f:
+                        m = json.load(f)
+                    out.append((os.path.join(d, name), int(m["round"]), int(m.get("world", 1))))
+                except (OSError, ValueError, KeyError):
+                    pass
+    return out
+
+
+def written_world(store) -> int:
+    """World size of the job that wrote the NEWEST committed manifest in the store's ``_resume`` directory (0: none)."""
+    marks = _markers(store)
+    return max(marks, key=lambda m: m[1])[2] if marks else 0
+
+
+def _drop_other_worlds(stage, store) -> None:
+    """After the first commit of a re-sharded job: the manifests of the previous world size are history."""
+    for path, _, world in _markers(store):
+        if world != stage.world:
+            for p in (path, path[:-len(".ok")]):
+                try:
+                    os.remove(p)
+                except OSError:
+                    pass
+
+
 def agreed_round(stage, store) -> int:
-    """Newest round whose manifest is committed on EVERY rank (0: none). Collective when ``world > 1``: every rank must
-    call it, and every rank gets the same answer."""
-    mine = sorted(_committed(store, stage.rank))
+    """Newest round whose manifest is committed on EVERY rank of the job that wrote it (0: none). Collective when
+    ``world > 1``: every rank must call it, and every rank gets the same answer.
+
+    When the world size changed (a GPU was lost for good and the job is restarted on fewer ranks, or grown again) the
+    writers' ranks no longer exist: every new rank then reads the markers of ALL old ranks from the shared checkpoint
+    directory and the new ranks agree on the minimum of what they see."""
     import torch.distributed as dist
+    old_world = written_world(store)
+    if old_world in (0, stage.world):
+        mine = sorted(_committed(store, stage.rank))
+    else:
+        per_rank = [set(_committed(store, r)) for r in range(old_world)]
+        mine = sorted(set.intersection(*per_rank)) if per_rank else []
     if stage.world > 1 and dist.is_available() and dist.is_initialized():
         everyone = [None] * stage.world
         dist.all_gather_object(everyone, mine)
@@ -181,17 +224,43 @@ def agreed_round(stage, store) -> int:
     return max(common) if common else 0
 
 
+def _merged_manifest(stage, store, rnd: int, old_world: int) -> Dict[str, Any]:
+    """The manifests of all ``old_world`` writer ranks folded into one picture: clients and per-client symmetric
+    buffers are the union (every client was hosted by exactly one old rank), everything replicated (server, rank
+    buffers, host RNG streams - identical on every rank by construction) is taken from old rank 0."""
+    merged: Dict[str, Any] = {}
+    for r in range(old_world):
+        st = store.load(ACTOR, _gen_name(r, _committed(store, r)[rnd]))
+        assert int(st["round"]) == rnd, (r, st["round"], rnd)
+        if r == 0:
+            merged = st
+            merged["comm"] = dict(st.get("comm") or {})
+            continue
+        merged["clients"].update(st["clients"])
+        for name, val in (st.get("comm") or {}).items():
+            if isinstance(val, dict):
+                merged["comm"].setdefault(name, {})
+                merged["comm"][name] = {**merged["comm"][name], **val}
+    merged["world"] = stage.world
+    return merged
+
+
 def load(stage, store, server, clients, comm, rnd: int = None) -> int:
     """Restore the manifest of round ``rnd`` (default: :func:`agreed_round`, the newest one committed on every rank);
-    returns that round (0: nothing to resume from - the caller starts at round 1 on the freshly built state)."""
+    returns that round (0: nothing to resume from - the caller starts at round 1 on the freshly built state). A job
+    restarted with a different world size re-shards: each new rank takes the clients it hosts now out of the merged
+    manifests of the old ranks (shared checkpoint directory required)."""
     if rnd is None:
         rnd = agreed_round(stage, store)
     if rnd == 0:
         return 0
-    st = store.load(ACTOR, _gen_name(stage.rank, _committed(store, stage.rank)[rnd]))
+    old_world = written_world(store)
+    if old_world not in (0, stage.world):
+        st = _merged_manifest(stage, store, rnd, old_world)
+        stage.logger.info(f"Resume: re-sharding the round-{rnd} manifests of {old_world} ranks over {stage.world}.")
+    else:
+        st = store.load(ACTOR, _gen_name(stage.rank, _committed(store, stage.rank)[rnd]))
     assert int(st["round"]) == rnd, (st["round"], rnd)
-    if int(st.get("world", 1)) != stage.world:
-        raise RuntimeError(f"resume manifest was written with world_size={st.get('world')}, now {stage.world}")
     random.setstate(st["py_random"])
     torch.set_rng_state(st["torch_rng"])
     if st.get("cuda_rng") is not None and stage.device.type == "cuda":
@@ -215,6 +284,8 @@ def load(stage, store, server, clients, comm, rnd: int = None) -> int:
                 continue
             if isinstance(val, dict):
                 for cid, t in val.items():
+                    if comm.owner(int(cid)) != comm.rank:
+                        continue                                  # (re-sharded: this slot lives on another rank now)
                     comm.client_view(name, int(cid)).copy_(t.to(comm.client_view(name, int(cid)).device))
             else:
                 comm.rank_view(name).copy_(val.to(comm.rank_view(name).device))

@@ -28,7 +28,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     attempt = int(os.environ.get("TORCHELASTIC_RESTART_COUNT", "0"))
     base = os.environ["FLPR_TMP"]
-    tmp = os.path.join(base, f"r{rank}")
+    tmp = os.path.join(base, "shared" if os.environ.get("FLPR_SHARED_ROOT") else f"r{rank}")
     common = tiny_common(tmp)
     common["defaults"]["exp_opts"].update(comm_rounds=rounds, val_interval=100)
     common["defaults"]["task_opts"]["sustain_rounds"] = 2

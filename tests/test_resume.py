@@ -123,3 +123,68 @@ def test_manifest_generations_and_commit_markers(tmp_path):
     assert first == 3
     full, _ = _run(str(tmp_path / "full"), "fedavg", 4)
     assert torch.allclose(cont["server"], full["server"], atol=1e-5)
+
+
+def test_resume_reshards_to_a_different_world_size(tmp_path):
+    """A job written by 2 ranks is continued by 1 (a GPU lost for good): the single rank reads both old ranks' committed
+    manifests from the shared directory, takes over both clients (models, counters, task positions, loader shuffle
+    state, upload slots) and the replicated server state, trains on, and its first commit retires the old world's files.
+    (Bitwise equality with the 2-rank continuation is not defined - host RNG streams are per process - so the check is
+    that what was restored IS what was saved.)"""
+    import subprocess
+    import sys
+    from flpr_b200.runtime import resume as R
+    from flpr_b200.runtime.explog import ExperimentLog
+    from flpr_b200.utils.misc import DeviceTimer, same_seeds
+    script = os.path.join(os.path.dirname(__file__), "dist_resume_check.py")
+    env = dict(os.environ, FLPR_TMP=str(tmp_path), FLPR_SHARED_ROOT="1", OMP_NUM_THREADS="2")
+    env.pop("FLPR_FAULT_EXIT", None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
+                        "--nproc-per-node", "2", script, "fedavg", "2"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.count("DIST_RESUME") == 2, r.stdout[-2000:] + r.stderr[-2000:]
+
+    tmp = os.path.join(str(tmp_path), "shared")
+    common = tiny_common(tmp)
+    common["defaults"]["exp_opts"].update(comm_rounds=4, val_interval=100)
+    common["defaults"]["task_opts"]["sustain_rounds"] = 2
+    cfg = tiny_experiment(common, "fedavg", n_clients=2, n_tasks=2)
+    cfg["engine_opts"].update(resume=True, resume_interval=1, val_at_round0=False)
+    with ExperimentStage(common, [cfg], source_factory=tiny_factory()) as stage:
+        same_seeds(cfg["random_seed"])
+        store, comm, server, clients, names = stage.build(cfg)
+        assert R.written_world(store) == 2 and stage.world == 1
+        assert R.agreed_round(stage, store) == 2
+        saved = [store.load(R.ACTOR, R._gen_name(rk, R._committed(store, rk)[2])) for rk in (0, 1)]
+        assert R.load(stage, store, server, clients, comm) == 2
+        by_name = {c.client_name: c for c in clients}
+        assert set(by_name) == {"client-0", "client-1"}
+        for st in saved:
+            for name, cs in st["clients"].items():                   # every client of every old rank landed here
+                c = by_name[name]
+                assert c.train_cnt == cs["train_cnt"]
+                pipe = c.task_pipeline.state_dict()
+                assert pipe["current_task_idx"] == cs["pipeline"]["current_task_idx"]
+                assert pipe["task_round_rest"] == cs["pipeline"]["task_round_rest"]
+                mine = c.model.full_state()
+                for k, v in cs["model"].items():
+                    if torch.is_tensor(v):
+                        assert torch.equal(mine[k].cpu().float(), v.float()), (name, k)
+            for bname, val in (st.get("comm") or {}).items():
+                if isinstance(val, dict):
+                    for cid, t in val.items():
+                        assert torch.equal(comm.client_view(bname, int(cid)).cpu(), t), (bname, cid)
+        sv = server.model.full_state()
+        for k, v in saved[0]["server"]["model"].items():
+            if torch.is_tensor(v):
+                assert torch.equal(sv[k].cpu().float(), v.float()), k
+        log = ExperimentLog(os.path.join(tmp, "log.json"), enabled=False)
+        timer = DeviceTimer(stage.device)
+        for rnd in (3, 4):
+            stage._process_one_round(rnd, server, clients, names, cfg, log, timer, comm)
+            R.save(stage, store, rnd, server, clients, comm)
+        assert all(torch.isfinite(c.model.arena.master).all() for c in clients)
+        assert R.written_world(store) == 1 and sorted(R._committed(store, 0)) == [3, 4]
+        assert not R._committed(store, 1), "the old world's manifests were not retired"
+        store.close()
+        if comm is not None:
+            comm.close()
