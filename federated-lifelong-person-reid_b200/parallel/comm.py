@@ -165,6 +165,10 @@ class FedComm:
         native.check(lib.flpr_comm_set_mailbox(C.c_void_p(self._base), C.c_void_p(self._mailbox.data_ptr())),
                      "flpr_comm_set_mailbox")
 
+    def _stream(self):
+        """Stream handle the collectives are launched on (the calling thread's current CUDA stream)."""
+        return native.stream(self.device)
+
     def set_channel(self, channel: int) -> None:
         """Flag channel of the collectives launched by the calling thread from now on (concurrent collectives - one
         on a communication stream, one on the compute stream - must use different channels; same choice on every
@@ -283,7 +287,7 @@ class FedComm:
     def barrier(self) -> None:
         if self.mode == "p2p":
             rc = self._lib.flpr_comm_barrier(self.rank, self.world, self._flag_pages, self.timeout_s,
-                                             native.stream(self.device))
+                                             self._stream())
             native.check(rc, "flpr_comm_barrier")
             native.count_launch()
         elif self.world > 1:
@@ -311,7 +315,7 @@ class FedComm:
             rc = self._lib.flpr_comm_reduce_bcast(self.rank, self.world, self._flag_pages, self.timeout_s, len(clients),
                                                   srcp, cntp, wv, self._rank_ptrs(dst), bs.n,
                                                   self._grid_for(bs.n * 4 * max(len(clients), 1) // max(self.world, 1)),
-                                                  native.stream(self.device))
+                                                  self._stream())
             native.check(rc, "flpr_comm_reduce_bcast")
             native.count_launch()
             self.poll_errors()
@@ -346,7 +350,7 @@ class FedComm:
             self.rank, self.world, self._flag_pages, self.timeout_s, len(mine), srcp, cntp, wv, len(clients), cnt_all,
             w_total, C.c_void_p(self._addr(bp, self.rank, 0)), C.c_void_p(self._mc_base + bp.offset),
             C.c_void_p(self._mc_base + bd.offset), bs.n, self._grid_for(bs.n * 4 * len(clients) // self.world),
-            native.stream(self.device))
+            self._stream())
         native.check(rc, "flpr_comm_reduce_bcast_nvls")
         native.count_launch()
         self.poll_errors()
@@ -389,7 +393,7 @@ class FedComm:
                 rc = self._lib.flpr_comm_mix(self.rank, self.world, self._flag_pages, self.timeout_s, len(clients),
                                              len(idx), srcp, wv, native.ptr(wd), arr(dst_g), arr(dst_theta),
                                              arr(dst_bf16), bs.n,
-                                             self._grid_for(bs.n * 4 * len(clients)), native.stream(self.device))
+                                             self._grid_for(bs.n * 4 * len(clients)), self._stream())
                 native.check(rc, "flpr_comm_mix")
                 native.count_launch()
                 self.poll_errors()
@@ -416,7 +420,7 @@ class FedComm:
                                                   self._rank_ptrs(dst_f), self._rank_ptrs(dst_fp),
                                                   self._rank_ptrs(dst_fpp), bf.n,
                                                   self._grid_for(2 * bf.n * 4 * max(len(clients), 1) // max(self.world, 1)),
-                                                  native.stream(self.device))
+                                                  self._stream())
             native.check(rc, "flpr_comm_curv_moments")
             native.count_launch()
             self.poll_errors()
@@ -437,7 +441,7 @@ class FedComm:
             rc = self._lib.flpr_comm_gather_strided(self.rank, self.world, self._flag_pages, self.timeout_s,
                                                     len(clients), self._client_ptrs(src, clients), native.ptr(out),
                                                     bs.n, self._grid_for(bs.n * 4 * len(clients)),
-                                                    native.stream(self.device))
+                                                    self._stream())
             native.check(rc, "flpr_comm_gather_strided")
             native.count_launch()
             self.poll_errors()
@@ -454,7 +458,7 @@ class FedComm:
             addr = self._addr(bs, self.owner(client), self.slot(client))
             rc = self._lib.flpr_comm_pull_copy(self.rank, self.world, self._flag_pages, self.timeout_s,
                                                C.c_void_p(addr), native.ptr(dst), native.ptr(dst_bf16), bs.n,
-                                               self._grid_for(bs.n * 4), native.stream(self.device))
+                                               self._grid_for(bs.n * 4), self._stream())
             native.check(rc, "flpr_comm_pull_copy")
             native.count_launch()
             self.poll_errors()

@@ -172,3 +172,69 @@ class EmuWorld:
     def close(self) -> None:
         self.lib.flpr_emu_mc_clear()
         self.lib.flpr_emu_defer(0)
+
+
+# ---------------------------------------------------------------------------------------------------- FedComm on the emulator
+def make_fedcomm_world(lib: C.CDLL, world: int, num_clients: int, arena_bytes: int = 8 << 20, blocks: int = 2,
+                       multicast: bool = True):
+    """``world`` instances of the product's ``FedComm`` (``parallel/comm.py``) in ONE process, in ``p2p`` mode, on host
+    arenas and the emulated kernels: the Python half of the communication layer - buffer placement, owner / slot maps,
+    pointer tables, kernel choice (two-shot / one-shot / NVLS), grid sizes, the launch loop of the mix - runs unchanged;
+    only the arena construction (VMM / IPC) and the stream handle are replaced. Every collective must be called on all
+    ranks, then ``run(lib, seed)`` executes what was queued."""
+    from flpr_b200.ops import native
+    from flpr_b200.parallel.comm import FedComm
+
+    native.declare_present(lib)
+    lib.flpr_emu_defer(1)
+    flag_bytes = ((lib.flpr_comm_flag_page_bytes() + 4095) // 4096) * 4096
+    arenas = [torch.zeros(arena_bytes, dtype=torch.uint8) for _ in range(world)]
+    window = torch.empty(arena_bytes, dtype=torch.uint8) if multicast else None
+    if multicast:
+        lib.flpr_emu_mc_register(window.data_ptr(), arena_bytes, world, ptr_array(arenas))
+
+    class EmuFedComm(FedComm):
+        def __init__(self, rank: int):                      # (no torch.distributed, no CUDA: fields set by hand)
+            self.device = torch.device("cpu")
+            self.group = None
+            self.rank, self.world, self.K = rank, world, int(num_clients)
+            self.slots = (self.K + world - 1) // world
+            self.mode = self.backend = "p2p"
+            self.timeout_s = 1e3
+            self.arena_bytes = arena_bytes
+            self.bufs = {}
+            self._cursor = flag_bytes
+            self._keep = []
+            self.bytes_moved = 0
+            self.nvls, self.nvls_min_bytes, self.nvls_launches = True, 1 << 20, 0
+            self.block_cap, self.comm_blocks = 0, blocks
+            self._vmm = None
+            self._lib = lib
+            self._arena = arenas[rank]
+            self._base = arenas[rank].data_ptr()
+            self._peer_base = [a.data_ptr() for a in arenas]
+            self._mc_base = window.data_ptr() if multicast else 0
+            self._flag_pages = (C.c_void_p * world)(*[C.c_void_p(b) for b in self._peer_base])
+            self._mailbox = torch.zeros(4, dtype=torch.int32)
+            self._window = window
+
+        def _stream(self):
+            return P(0x200000 + self.rank * 0x100)
+
+        def error_word(self) -> int:
+            words = lib.flpr_comm_flag_page_bytes() // 4
+            return int(self._arena[:words * 4].view(torch.int32)[words - 4])
+
+        def close(self) -> None:
+            pass
+
+    return [EmuFedComm(r) for r in range(world)]
+
+
+def run(lib: C.CDLL, seed: int, max_passes: int = 400000, stall_one_in: int = 4) -> int:
+    return lib.flpr_emu_run(seed, max_passes, stall_one_in)
+
+
+def end(lib: C.CDLL) -> None:
+    lib.flpr_emu_mc_clear()
+    lib.flpr_emu_defer(0)
