@@ -176,7 +176,7 @@ class EmuWorld:
 
 # ---------------------------------------------------------------------------------------------------- FedComm on the emulator
 def make_fedcomm_world(lib: C.CDLL, world: int, num_clients: int, arena_bytes: int = 8 << 20, blocks: int = 2,
-                       multicast: bool = True):
+                       multicast: bool = True, timeout_s: float = 1e3):
     """``world`` instances of the product's ``FedComm`` (``parallel/comm.py``) in ONE process, in ``p2p`` mode, on host
     arenas and the emulated kernels: the Python half of the communication layer - buffer placement, owner / slot maps,
     pointer tables, kernel choice (two-shot / one-shot / NVLS), grid sizes, the launch loop of the mix - runs unchanged;
@@ -200,7 +200,7 @@ def make_fedcomm_world(lib: C.CDLL, world: int, num_clients: int, arena_bytes: i
             self.rank, self.world, self.K = rank, world, int(num_clients)
             self.slots = (self.K + world - 1) // world
             self.mode = self.backend = "p2p"
-            self.timeout_s = 1e3
+            self.timeout_s = float(timeout_s)
             self.arena_bytes = arena_bytes
             self.bufs = {}
             self._cursor = flag_bytes
@@ -217,6 +217,13 @@ def make_fedcomm_world(lib: C.CDLL, world: int, num_clients: int, arena_bytes: i
             self._flag_pages = (C.c_void_p * world)(*[C.c_void_p(b) for b in self._peer_base])
             self._mailbox = torch.zeros(4, dtype=torch.int32)
             self._window = window
+            # what flpr_comm_set_mailbox does with a cudaMemcpy: the 64-bit address of the host mailbox at MAILBOX_OFF
+            words = lib.flpr_comm_flag_page_bytes() // 4
+            page = self._arena[:words * 4].view(torch.int32)
+            addr = self._mailbox.data_ptr()
+            lo, hi = addr & 0xFFFFFFFF, addr >> 32
+            page[words - 2] = lo - (1 << 32) if lo >= (1 << 31) else lo
+            page[words - 1] = hi - (1 << 32) if hi >= (1 << 31) else hi
 
         def _stream(self):
             return P(0x200000 + self.rank * 0x100)

@@ -147,3 +147,29 @@ def test_moments_gather_and_first_contact_pull_through_fedcomm(lib):
         assert torch.equal(pulled[c.rank], param[4]) and torch.equal(pulled16[c.rank], param[4].to(torch.bfloat16))
         assert c.bytes_moved > 0
     done(lib)
+
+
+def test_a_missing_rank_surfaces_as_native_error_on_the_host(lib):
+    """Rank 2 never enters the collective: the watchdog of the survivors' kernels fires on the virtual clock, mirrors the
+    error word into the host mailbox, and ``FedComm.poll_errors`` - what the engine calls after every collective and at
+    every round boundary - raises on exactly those ranks; nothing was published."""
+    from flpr_b200.ops.native import NativeError
+    world, clients, n = 3, 6, 4 * 100
+    comms = world_of(lib, world, clients, timeout_s=2e-4)
+    lib.flpr_comm_set_one_shot_bytes(0)
+    for c in comms:
+        c.alloc_client_buffer("up", n)
+        c.alloc_rank_buffer("glob", n)
+        for cid in c.local_clients():
+            c.client_view("up", cid).copy_(rand(n, cid))
+        c.rank_view("glob").fill_(-1.0)
+    for c in comms[:2]:
+        c.reduce_bcast("up", "glob", list(range(clients)), weights=[1.0 / clients] * clients)
+        c.poll_errors()                                   # nothing has run yet: clean
+    run(lib, 2)
+    for c in comms[:2]:
+        with pytest.raises(NativeError, match="timed out waiting for a peer rank"):
+            c.poll_errors()
+        assert bool((c.rank_view("glob") == -1.0).all())
+    comms[2].poll_errors()                                # the absent rank saw nothing
+    done(lib)
