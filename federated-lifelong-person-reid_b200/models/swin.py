@@ -155,7 +155,7 @@ class Mlp(nn.Module):
     def forward(self, x):
         h = self.fc1(x)
         if h.is_cuda and h.dtype == torch.bfloat16 and torch.is_grad_enabled() and h.requires_grad \
-                and h.numel() % 8 == 0 and lops.enabled("ln_train", h.device):
+                and h.numel() % 8 == 0 and lops.enabled("ln_train", h.device) and lops.enabled("swin_tokens", h.device):
             h = lops.gelu_act(h if h.is_contiguous() else h.contiguous())   # native forward / backward (trainable stage)
         else:
             h = self.act(h)
