@@ -23,8 +23,22 @@ def _ensure_reference_installed() -> None:
         print(f"[conftest] reference install failed: {ex}")
 
 
+def _ensure_native_library() -> None:
+    """``lib/libflpr_b200.so`` is git-ignored: a fresh checkout builds it before the first test needs it (``nvcc``
+    cross-compiles for sm_100a without a GPU; about a minute). A current library is left alone."""
+    if os.environ.get("PYTEST_XDIST_WORKER"):
+        return
+    try:
+        from flpr_b200 import _build
+        if not _build.is_current():
+            _build.build(verbose=False)
+    except Exception as ex:  # noqa: BLE001  (tests that need the library then fail with its own message)
+        print(f"[conftest] native build failed: {ex}")
+
+
 def pytest_configure(config):
     _ensure_reference_installed()
+    _ensure_native_library()
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "multigpu: test needs >= 2 CUDA devices")
 
