@@ -71,3 +71,20 @@ def test_reference_arm_runs_the_installed_reference():
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config"):
         assert key in d, key
     assert d["value"] > 0 and d["steps"] == 1
+
+
+def test_bench_under_torchrun_prints_one_line_from_rank0():
+    """The driver's multi-GPU launch form (``python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py
+    --gpus N``) on the CPU debug path (gloo): the cross-rank reductions of the harness run, rank 0 alone prints the line."""
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29733", os.path.join(ROOT, "bench.py"),
+                        "--gpus", "2", "--steps", "1", "--warmup", "1", "--cpu-debug"], capture_output=True, text=True,
+                       timeout=900, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["value"] > 0 and d["e2e"]["value"] > 0 and d["steps"] == 1
