@@ -79,8 +79,12 @@ def test_bench_under_torchrun_prints_one_line_from_rank0():
     env = dict(os.environ, OMP_NUM_THREADS="2")
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
+    import socket
+    with socket.socket() as sock:                        # a free port: a fixed one would collide with a parallel run
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29733", os.path.join(ROOT, "bench.py"),
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
                         "--gpus", "2", "--steps", "1", "--warmup", "1", "--cpu-debug"], capture_output=True, text=True,
                        timeout=900, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-3000:]
