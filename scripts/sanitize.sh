@@ -26,7 +26,7 @@ run_late() {
   FLPR_LAYER_SELFCHECK=inprocess timeout 1500 compute-sanitizer --tool "$tool" --error-exitcode 9 \
     --log-file "gpurun_out/sanitizer_${tool}_layer_ops.log" \
     python -m pytest tests/test_zz_gpu_late.py -q -x --timeout 1200 -p no:cacheprovider \
-      -k "compose_kernels or swin_token_kernels or apply_global_kernel" 2>&1 | tail -4
+      -k "compose_kernels or swin_token_kernels or apply_global_kernel or layer_norm_rows or window_merge_residual or gelu_act" 2>&1 | tail -4
   echo "sanitizer ${tool} (layer_ops) exit: $?"
   tail -5 "gpurun_out/sanitizer_${tool}_layer_ops.log"
 }
